@@ -1,0 +1,283 @@
+"""CLIP object of the B200 path: same attribute / parameter names as openai-CLIP's `CLIP` and `VisionTransformer`
+(`clip/model.py`, third-party to the reference), so the reference's classifiers, LoRA injection and checkpoints see
+the object they expect (.visual.conv1, .visual.proj, .visual.class_embedding,
+.visual.transformer.resblocks[i].attn : nn.MultiheadAttention, .logit_scale, .encode_image, module-level load()).
+
+nn.Module / nn.Parameter are used as parameter containers only.  `VisionTransformer.forward` does not run a single
+PyTorch op on the data path: it packs weights to bf16 once and enqueues the library's kernels
+(tcgen05 GEMMs with fused epilogues, LayerNorm, attention) through the C ABI.
+"""
+import math
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops
+
+ARCHS = {
+    # name: (patch, width, layers, heads, embed_dim) -- openai-CLIP released ViTs
+    "ViT-B/32": (32, 768, 12, 12, 512),
+    "ViT-B/16": (16, 768, 12, 12, 512),
+    "ViT-L/14": (14, 1024, 24, 16, 768),
+    # small shapes for tests
+    "ViT-tiny/32": (32, 128, 2, 2, 64),
+    "ViT-tiny/16": (16, 128, 2, 2, 64),
+}
+
+# algorithmic FLOPs per image (2*MAC), SURVEY.md section 8(d)
+def flops_per_image(arch):
+    P, d, layers, _, C = ARCHS[arch]
+    Ltok = (224 // P) ** 2 + 1
+    patch = 2 * (Ltok - 1) * (3 * P * P) * d
+    blocks = layers * (2 * Ltok * d * 3 * d + 2 * Ltok * d * d + 2 * 2 * Ltok * d * 4 * d + 2 * 2 * Ltok * Ltok * d)
+    return patch + blocks + 2 * d * C
+
+
+class QuickGELU(nn.Module):
+    """Parameter-free marker module (keeps the mlp Sequential's key names c_fc / gelu / c_proj)."""
+
+    def forward(self, x):  # pragma: no cover - never on the B200 data path
+        raise L.ECError("the B200 path applies QuickGELU inside the c_fc GEMM epilogue")
+
+
+class ResidualAttentionBlock(nn.Module):
+    def __init__(self, d, heads):
+        super().__init__()
+        self.attn = nn.MultiheadAttention(d, heads)
+        self.ln_1 = nn.LayerNorm(d)
+        self.mlp = nn.Sequential(OrderedDict([("c_fc", nn.Linear(d, d * 4)), ("gelu", QuickGELU()),
+                                              ("c_proj", nn.Linear(d * 4, d))]))
+        self.ln_2 = nn.LayerNorm(d)
+
+
+class Transformer(nn.Module):
+    def __init__(self, width, layers, heads):
+        super().__init__()
+        self.width, self.layers, self.heads = width, layers, heads
+        self.resblocks = nn.Sequential(*[ResidualAttentionBlock(width, heads) for _ in range(layers)])
+
+
+def _attn_weights(attn):
+    """(in_proj fp32 [3d,d] parts + optional LoRA factors, in_proj_bias, out_proj W/b + optional LoRA) of an
+    nn.MultiheadAttention or of the LoRA-injected variant (eventclip_b200.models.lora / reference models/lora.py)."""
+    ipw = attn.in_proj_weight
+    lora_in = None
+    if isinstance(ipw, nn.Module):   # LoraInjectedMergedProj: .merged_proj + lora_{up,down}_{q,k,v}
+        lora_in = ipw
+        W = ipw.merged_proj
+    else:
+        W = ipw
+    op = attn.out_proj
+    lora_out = None
+    if hasattr(op, "lora_up"):       # LoraInjectedLinear: .linear + lora_down / lora_up
+        lora_out = op
+        oW, ob = op.linear.weight, op.linear.bias
+    else:
+        oW, ob = op.weight, op.bias
+    return W, lora_in, attn.in_proj_bias, oW, ob, lora_out
+
+
+class VisionTransformer(nn.Module):
+    def __init__(self, input_resolution, patch_size, width, layers, heads, output_dim):
+        super().__init__()
+        if input_resolution != 224:
+            raise L.ECError("the fused path is built for CLIP's 224-pixel ViTs")
+        self.input_resolution, self.output_dim = input_resolution, output_dim
+        self.patch_size, self.width, self.heads = patch_size, width, heads
+        self.conv1 = nn.Conv2d(3, width, kernel_size=patch_size, stride=patch_size, bias=False)
+        scale = width ** -0.5
+        self.grid = input_resolution // patch_size
+        self.class_embedding = nn.Parameter(scale * torch.randn(width))
+        self.positional_embedding = nn.Parameter(scale * torch.randn(self.grid ** 2 + 1, width))
+        self.ln_pre = nn.LayerNorm(width)
+        self.transformer = Transformer(width, layers, heads)
+        self.ln_post = nn.LayerNorm(width)
+        self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
+        self._packed = None
+        self._packed_key = None
+
+    # -- weight packing -------------------------------------------------------------------------------------------
+    @property
+    def k_patch(self):
+        """Row length of the im2col / patch matrix: 3*P*P rounded up to a multiple of 8 (16-byte TMA stride)."""
+        k = 3 * self.patch_size ** 2
+        return (k + 7) // 8 * 8
+
+    def _version_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def invalidate_packed(self):
+        """Call after mutating weights in a way the version counters cannot see (e.g. .data swaps)."""
+        self._packed = None
+
+    def packed(self):
+        """bf16 copies of the GEMM weights in the layout the kernels read (LoRA factors merged, models/lora.py:138-149).
+        Rebuilt when any parameter's version counter changes (optimizer step, load_state_dict)."""
+        key = self._version_key()
+        if self._packed is not None and key == self._packed_key:
+            return self._packed
+        dev = self.proj.device
+        if dev.type != "cuda":
+            raise L.ECError("VisionTransformer weights must live on a CUDA device (B200); there is no CPU path")
+        d, P = self.width, self.patch_size
+        f32 = lambda t: t.detach().to(torch.float32).contiguous()
+        pk = {}
+        w = f32(self.conv1.weight).reshape(d, 3 * P * P)
+        if self.k_patch != 3 * P * P:
+            wp = torch.zeros((d, self.k_patch), dtype=torch.float32, device=dev)
+            wp[:, :3 * P * P] = w
+            w = wp
+        pk["conv1"] = ops.f32_to_bf16(w)
+        pk["cls"], pk["pos"] = f32(self.class_embedding), f32(self.positional_embedding)
+        pk["ln_pre"] = (f32(self.ln_pre.weight), f32(self.ln_pre.bias))
+        pk["ln_post"] = (f32(self.ln_post.weight), f32(self.ln_post.bias))
+        pk["proj"] = ops.f32_to_bf16(f32(self.proj).t().contiguous())   # [C, d] so that out = x @ proj
+        blocks = []
+        for blk in self.transformer.resblocks:
+            W, lora_in, ib, oW, ob, lora_out = _attn_weights(blk.attn)
+            W = f32(W)
+            if lora_in is None:
+                w_in = ops.f32_to_bf16(W)
+            else:
+                w_in = torch.empty((3 * d, d), dtype=torch.bfloat16, device=dev)
+                for j, n in enumerate("qkv"):
+                    up = getattr(lora_in, f"lora_up_{n}", None)
+                    down = getattr(lora_in, f"lora_down_{n}", None)
+                    ops.lora_merge(W[j * d:(j + 1) * d], f32(up) if up is not None else None,
+                                   f32(down) if down is not None else None, out=w_in[j * d:(j + 1) * d])
+            if lora_out is None:
+                w_out = ops.f32_to_bf16(f32(oW))
+            else:
+                w_out = ops.lora_merge(f32(oW), f32(lora_out.lora_up.weight), f32(lora_out.lora_down.weight))
+            blocks.append(dict(
+                ln1=(f32(blk.ln_1.weight), f32(blk.ln_1.bias)), ln2=(f32(blk.ln_2.weight), f32(blk.ln_2.bias)),
+                w_in=w_in, b_in=f32(ib), w_out=w_out, b_out=f32(ob),
+                w_fc=ops.f32_to_bf16(f32(blk.mlp.c_fc.weight)), b_fc=f32(blk.mlp.c_fc.bias),
+                w_proj=ops.f32_to_bf16(f32(blk.mlp.c_proj.weight)), b_proj=f32(blk.mlp.c_proj.bias)))
+        pk["blocks"] = blocks
+        self._packed, self._packed_key = pk, key
+        return pk
+
+    # -- forward ----------------------------------------------------------------------------------------------------
+    def forward_patches(self, patches, n_img):
+        """patches: bf16 [n_img*G*G, k_patch] im2col rows (what ec_event2img's EC_OUT_BF16_PATCH writes).
+        Returns fp32 [n_img, output_dim]."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(
+                "gradients through the B200 image encoder (fine-tune step, SURVEY 8 row A12) are not built yet; "
+                "run under torch.no_grad()")
+        pk = self.packed()
+        d, G2, heads = self.width, self.grid ** 2, self.heads
+        Ltok = G2 + 1
+        M = n_img * Ltok
+        dev = patches.device
+        x0 = torch.empty((M, d), dtype=torch.float32, device=dev)       # tokens before ln_pre
+        ops.gemm_bf16(patches, pk["conv1"], None, "patch", out=x0, res=pk["pos"], row_map=G2, M=n_img * G2)
+        ops.cls_rows(x0, pk["cls"], pk["pos"], n_img, Ltok, d)
+        x = torch.empty((M, d), dtype=torch.float32, device=dev)        # fp32 residual stream
+        ops.layernorm(x0, *pk["ln_pre"], M, d, out_f32=x)
+        del x0
+        xn = torch.empty((M, d), dtype=torch.bfloat16, device=dev)
+        qkv = torch.empty((M, 3 * d), dtype=torch.bfloat16, device=dev)
+        att = torch.empty((M, d), dtype=torch.bfloat16, device=dev)
+        hid = torch.empty((M, 4 * d), dtype=torch.bfloat16, device=dev)
+        for b in pk["blocks"]:
+            ops.layernorm(x, *b["ln1"], M, d, out_bf16=xn)
+            ops.gemm_bf16(xn, b["w_in"], b["b_in"], "bf16", out=qkv)
+            ops.attention(qkv, att, n_img, Ltok, heads)
+            ops.gemm_bf16(att, b["w_out"], b["b_out"], "f32_resadd", out=x, res=x)
+            ops.layernorm(x, *b["ln2"], M, d, out_bf16=xn)
+            ops.gemm_bf16(xn, b["w_fc"], b["b_fc"], "bf16_qgelu", out=hid)
+            ops.gemm_bf16(hid, b["w_proj"], b["b_proj"], "f32_resadd", out=x, res=x)
+        cls = torch.empty((n_img, d), dtype=torch.bfloat16, device=dev)
+        ops.layernorm(x, *pk["ln_post"], n_img, d, row_stride=Ltok * d, out_bf16=cls)
+        return ops.gemm_bf16(cls, pk["proj"], None, "f32")
+
+    def forward(self, x):
+        """x: CUDA [n,3,224,224] float32 / bfloat16 images (the reference's data_dict['img'] rows)."""
+        if x.dtype == torch.float16:
+            raise L.ECError("pass float32 or bfloat16 images; the B200 encoder computes in bf16 with fp32 accumulation")
+        n = x.shape[0]
+        if n == 0:
+            return torch.empty((0, self.output_dim), dtype=torch.float32, device=x.device)
+        patches = ops.im2col(x.contiguous(), self.patch_size, self.k_patch)
+        return self.forward_patches(patches, n)
+
+
+class CLIP(nn.Module):
+    """Image tower + logit scale.  The text tower is SURVEY section 8(f) row F3 (needs the BPE vocabulary, absent
+    offline): encode_text raises; classifiers take precomputed text features instead (models/clip_cls.py:71-72)."""
+
+    def __init__(self, arch):
+        super().__init__()
+        patch, width, layers, heads, embed = ARCHS[arch]
+        self.arch = arch
+        self.visual = VisionTransformer(224, patch, width, layers, heads, embed)
+        self.logit_scale = nn.Parameter(torch.ones([]) * math.log(1 / 0.07))
+
+    @property
+    def dtype(self):
+        return self.visual.conv1.weight.dtype
+
+    def encode_image(self, image):
+        return self.visual(image)
+
+    def encode_text(self, text):
+        raise NotImplementedError("text tower not built (SURVEY section 8(f) F3); pass text features to the classifier")
+
+
+def init_weights_(model, seed=0, logit_scale=100.0):
+    """Seeded random init with CLIP's published scales (no pretrained checkpoints offline).  Mirrors the oracle's
+    init so both sides can be built from one seed without sharing tensors."""
+    g = torch.Generator().manual_seed(seed)
+    v = model.visual
+    d, layers = v.width, v.transformer.layers
+    attn_std, proj_std, fc_std = d ** -0.5, (d ** -0.5) * ((2 * layers) ** -0.5), (2 * d) ** -0.5
+
+    def rn(t, std, mean=0.0):
+        with torch.no_grad():
+            t.copy_((torch.randn(t.shape, generator=g) * std + mean).to(t.device))
+
+    rn(v.conv1.weight, (3 * v.patch_size ** 2) ** -0.5)
+    rn(v.class_embedding, d ** -0.5)
+    rn(v.positional_embedding, d ** -0.5)
+    rn(v.proj, d ** -0.5)
+    for ln in [v.ln_pre, v.ln_post] + [m for b in v.transformer.resblocks for m in (b.ln_1, b.ln_2)]:
+        rn(ln.weight, 0.1, 1.0)
+        rn(ln.bias, 0.05)
+    for b in v.transformer.resblocks:
+        rn(b.attn.in_proj_weight, attn_std)
+        rn(b.attn.in_proj_bias, 0.02)
+        rn(b.attn.out_proj.weight, proj_std)
+        rn(b.attn.out_proj.bias, 0.02)
+        rn(b.mlp.c_fc.weight, fc_std)
+        rn(b.mlp.c_fc.bias, 0.02)
+        rn(b.mlp.c_proj.weight, proj_std)
+        rn(b.mlp.c_proj.bias, 0.02)
+    with torch.no_grad():
+        model.logit_scale.fill_(math.log(logit_scale))
+    return model
+
+
+def _transform(n_px=224):
+    """CLIP's preprocess (openai-CLIP `_transform`), for callers that still feed PIL images."""
+    import torchvision.transforms as T
+    return T.Compose([T.Resize(n_px, interpolation=T.InterpolationMode.BICUBIC), T.CenterCrop(n_px),
+                      lambda im: im.convert("RGB"), T.ToTensor(),
+                      T.Normalize((0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711))])
+
+
+def load(name, device="cuda", seed=0, state_dict=None):
+    """clip.load(arch, device) -> (model, preprocess)  (test.py:26, train.py:26).
+    Checkpoints cannot be downloaded offline: weights are seeded random unless `state_dict` is given."""
+    model = CLIP(name)
+    init_weights_(model, seed)
+    if state_dict is not None:
+        model.load_state_dict(state_dict, strict=False)
+    return model.to(device).eval(), _transform(224)
+
+
+def tokenize(texts, context_length=77):
+    raise NotImplementedError("BPE vocabulary is not available offline (SURVEY section 8(f) F3)")

@@ -1,0 +1,268 @@
+// elementwise.cu -- memory-bound glue kernels of the encoder / heads: LayerNorm, class-token rows, im2col,
+// dtype conversion, LoRA weight merge, adapter residual blend.
+//
+// Reference semantics (paths relative to the reference root / openai-CLIP `clip/model.py` [3P]):
+//   LayerNorm         fp32 statistics, eps 1e-5 (CLIP's LayerNorm subclass upcasts to fp32)
+//   class token       x = cat([class_embedding, patches]) + positional_embedding
+//   LoRA merge        models/lora.py:138-149 (q/k/v) and 49-52 (out_proj): W + up @ down, no alpha/r scaling
+//   residual blend    models/adapter.py:22-25: in*r + new*(1-r)
+#include "common.cuh"
+
+namespace {
+
+// One warp per row; two-pass (mean, then centred variance) on register-cached values.
+template <bool CACHE>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict__ x, int64_t row_stride,
+                                                        const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                        int M, int d, __nv_bfloat16 *__restrict__ out_bf16,
+                                                        float *__restrict__ out_f32)
+{
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)row * row_stride);
+    const int n4 = d >> 2;
+    constexpr int MAXV = 8;   // d <= 1024 when CACHE
+    float4 v[MAXV];
+    float s = 0.f;
+    if (CACHE) {
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int j = lane + i * 32;
+            if (j < n4) { v[i] = xr[j]; s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+        }
+    } else {
+        for (int j = lane; j < n4; j += 32) { const float4 t = xr[j]; s += (t.x + t.y) + (t.z + t.w); }
+    }
+    const float mean = ec::warp_sum(s) / (float)d;
+    float q = 0.f;
+    if (CACHE) {
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int j = lane + i * 32;
+            if (j < n4) {
+                const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+                q += (a * a + b * b) + (c * c + e * e);
+            }
+        }
+    } else {
+        for (int j = lane; j < n4; j += 32) {
+            const float4 t = xr[j];
+            const float a = t.x - mean, b = t.y - mean, c = t.z - mean, e = t.w - mean;
+            q += (a * a + b * b) + (c * c + e * e);
+        }
+    }
+    const float rstd = rsqrtf(ec::warp_sum(q) / (float)d + 1e-5f);
+    const float4 *g4 = reinterpret_cast<const float4 *>(gamma);
+    const float4 *b4 = reinterpret_cast<const float4 *>(beta);
+    auto emit = [&](int j, const float4 &t) {
+        const float4 g = g4[j], b = b4[j];
+        float4 o;
+        o.x = (t.x - mean) * rstd * g.x + b.x;
+        o.y = (t.y - mean) * rstd * g.y + b.y;
+        o.z = (t.z - mean) * rstd * g.z + b.z;
+        o.w = (t.w - mean) * rstd * g.w + b.w;
+        if (out_f32) reinterpret_cast<float4 *>(out_f32 + (size_t)row * d)[j] = o;
+        if (out_bf16) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
+            uint2 u;
+            u.x = *reinterpret_cast<uint32_t *>(&h0);
+            u.y = *reinterpret_cast<uint32_t *>(&h1);
+            reinterpret_cast<uint2 *>(out_bf16 + (size_t)row * d)[j] = u;
+        }
+    };
+    if (CACHE) {
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int j = lane + i * 32;
+            if (j < n4) emit(j, v[i]);
+        }
+    } else {
+        for (int j = lane; j < n4; j += 32) emit(j, xr[j]);
+    }
+}
+
+int launch_ln(const float *x, int64_t row_stride, const float *gamma, const float *beta, int M, int d, void *out_bf16,
+              float *out_f32, cudaStream_t stream)
+{
+    EC_REQUIRE(x && gamma && beta && (out_bf16 || out_f32), "layernorm: null pointer");
+    EC_REQUIRE(M > 0 && d > 0 && d % 4 == 0 && row_stride % 4 == 0, "layernorm: d and row stride must be multiples of 4");
+    const int rows_per_block = 8;
+    const int grid = (M + rows_per_block - 1) / rows_per_block;
+    if (d <= 1024)
+        layernorm_kernel<true><<<grid, 256, 0, stream>>>(x, row_stride, gamma, beta, M, d, (__nv_bfloat16 *)out_bf16, out_f32);
+    else
+        layernorm_kernel<false><<<grid, 256, 0, stream>>>(x, row_stride, gamma, beta, M, d, (__nv_bfloat16 *)out_bf16, out_f32);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
+__global__ void cls_rows_kernel(float *x, const float *cls, const float *pos, int n_img, int L, int d)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n_img * d) return;
+    const int img = (int)(i / d), c = (int)(i % d);
+    x[(size_t)img * L * d + c] = cls[c] + pos[c];
+}
+
+__global__ void f32_to_bf16_kernel(const float *src, __nv_bfloat16 *dst, int64_t n)
+{
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        const float4 t = *reinterpret_cast<const float4 *>(src + i);
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(t.x, t.y), h1 = __floats2bfloat162_rn(t.z, t.w);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t *>(&h0);
+        u.y = *reinterpret_cast<uint32_t *>(&h1);
+        *reinterpret_cast<uint2 *>(dst + i) = u;
+    } else {
+        for (int64_t j = i; j < n; ++j) dst[j] = __float2bfloat16(src[j]);
+    }
+}
+
+// NCHW [n,3,224,224] -> rows [n*G*G, ldk], column order (c, dy, dx) = conv1.weight.flatten(1) order.
+template <typename T>
+__global__ void im2col_kernel(const T *img, int n_img, int P, int G, int ldk, __nv_bfloat16 *out)
+{
+    const int K = 3 * P * P;
+    const int64_t total = (int64_t)n_img * G * G * K;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int col = (int)(i % K);
+        const int64_t row = i / K;
+        const int img_i = (int)(row / (G * G)), pr = (int)(row % (G * G));
+        const int py = pr / G, px = pr % G;
+        const int c = col / (P * P), dy = (col / P) % P, dx = col % P;
+        const float v = (float)img[(((size_t)img_i * 3 + c) * 224 + py * P + dy) * 224 + px * P + dx];
+        out[row * ldk + col] = __float2bfloat16(v);
+    }
+}
+
+__global__ void lora_merge_kernel(const float *W, const float *up, const float *down, int rows, int d, int r,
+                                  __nv_bfloat16 *Wm)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)rows * d) return;
+    const int row = (int)(i / d), col = (int)(i % d);
+    float acc = 0.f;
+    if (up && down)
+        for (int k = 0; k < r; ++k) acc = fmaf(up[(size_t)row * r + k], down[(size_t)k * d + col], acc);
+    Wm[i] = __float2bfloat16(W[i] + acc);
+}
+
+__global__ void blend_kernel(const float *a, const float *b, float r, float q, float *out, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __fadd_rn(__fmul_rn(a[i], r), __fmul_rn(b[i], q));
+}
+
+// dst[s] = idx[s] >= 0 ? src[idx[s]] : 0   (the zeros + masked assignment of models/clip_cls.py:320-321)
+__global__ void gather_rows_kernel(const float *src, const int32_t *idx, float *dst, int n_rows, int C)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n_rows * C) return;
+    const int r = (int)(i / C), c = (int)(i % C);
+    const int sr = idx[r];
+    dst[i] = sr >= 0 ? src[(size_t)sr * C + c] : 0.f;
+}
+
+// F.normalize(x, p=2, dim=-1): x / max(||x||, 1e-12); one warp per row
+__global__ void l2norm_rows_kernel(const float *x, float *out, int M, int C)
+{
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= M) return;
+    float ss = 0.f;
+    for (int c = lane; c < C; c += 32) { const float v = x[(size_t)row * C + c]; ss += v * v; }
+    const float inv = 1.f / fmaxf(sqrtf(ec::warp_sum(ss)), 1e-12f);
+    for (int c = lane; c < C; c += 32) out[(size_t)row * C + c] = x[(size_t)row * C + c] * inv;
+}
+
+}  // namespace
+
+extern "C" int ec_gather_rows(const float *src, const int32_t *idx, float *dst, int n_rows, int C, void *stream)
+{
+    EC_REQUIRE(src && idx && dst && n_rows > 0 && C > 0, "ec_gather_rows: bad arguments");
+    const int64_t n = (int64_t)n_rows * C;
+    gather_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, idx, dst, n_rows, C);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
+extern "C" int ec_l2norm_rows(const float *x, float *out, int M, int C, void *stream)
+{
+    EC_REQUIRE(x && out && M > 0 && C > 0, "ec_l2norm_rows: bad arguments");
+    l2norm_rows_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, out, M, C);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
+extern "C" int ec_layernorm(const float *x, int64_t row_stride_in, const float *gamma, const float *beta, int M, int d,
+                            void *out_bf16, float *out_f32, void *stream)
+{
+    return launch_ln(x, row_stride_in, gamma, beta, M, d, out_bf16, out_f32, (cudaStream_t)stream);
+}
+
+extern "C" int ec_layernorm_f32(const float *x, const float *gamma, const float *beta, int M, int d, float *out,
+                                void *stream)
+{
+    return launch_ln(x, d, gamma, beta, M, d, nullptr, out, (cudaStream_t)stream);
+}
+
+extern "C" int ec_cls_rows(float *x, const float *class_embedding, const float *pos, int n_img, int L, int d,
+                           void *stream)
+{
+    EC_REQUIRE(x && class_embedding && pos && n_img > 0 && L > 0 && d > 0, "ec_cls_rows: bad arguments");
+    const int64_t n = (int64_t)n_img * d;
+    cls_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, class_embedding, pos, n_img, L, d);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
+extern "C" int ec_f32_to_bf16(const float *src, void *dst, int64_t n, void *stream)
+{
+    EC_REQUIRE(src && dst && n >= 0, "ec_f32_to_bf16: bad arguments");
+    EC_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0, "ec_f32_to_bf16: misaligned pointers");
+    if (n == 0) return EC_OK;
+    const int64_t thr = (n + 3) / 4;
+    f32_to_bf16_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16 *)dst, n);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
+extern "C" int ec_im2col(const void *img, int in_is_bf16, int n_img, int patch, int ldk, void *out, void *stream)
+{
+    EC_REQUIRE(img && out && n_img > 0, "ec_im2col: bad arguments");
+    EC_REQUIRE(patch > 0 && 224 % patch == 0 && ldk >= 3 * patch * patch, "ec_im2col: bad patch %d / ldk %d", patch, ldk);
+    const int G = 224 / patch;
+    const int64_t total = (int64_t)n_img * G * G * 3 * patch * patch;
+    const unsigned grid = (unsigned)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);
+    if (in_is_bf16)
+        im2col_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)img, n_img, patch, G, ldk,
+                                                                              (__nv_bfloat16 *)out);
+    else
+        im2col_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float *)img, n_img, patch, G, ldk,
+                                                                      (__nv_bfloat16 *)out);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
+extern "C" int ec_lora_merge(const float *W, const float *up, const float *down, int rows, int d, int r, void *Wm_bf16,
+                             void *stream)
+{
+    EC_REQUIRE(W && Wm_bf16 && rows > 0 && d > 0, "ec_lora_merge: bad arguments");
+    EC_REQUIRE((up == nullptr) == (down == nullptr), "ec_lora_merge: up and down must both be given or both be NULL");
+    const int64_t n = (int64_t)rows * d;
+    lora_merge_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(W, up, down, rows, d, r,
+                                                                                     (__nv_bfloat16 *)Wm_bf16);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
+extern "C" int ec_blend(const float *a, const float *b, double r, float *out, int64_t n, void *stream)
+{
+    EC_REQUIRE(a && b && out && n >= 0, "ec_blend: bad arguments");
+    if (n == 0) return EC_OK;
+    // python evaluates (1. - residual) in double before torch narrows both scalars to float32
+    blend_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, b, (float)r, (float)(1.0 - r), out, n);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}

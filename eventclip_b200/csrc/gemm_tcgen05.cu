@@ -1,0 +1,393 @@
+// gemm_tcgen05.cu -- C[M,N] = epilogue(A[M,K] . W[N,K]^T), bf16 x bf16 -> fp32, sm_100a.
+//
+// Every dense contraction of the CLIP ViT image encoder (openai/CLIP VisionTransformer, called from the reference
+// at models/clip_cls.py:101 and models/clip_cls_ft.py:180) runs through this kernel: the conv1 patch embedding
+// (stride == kernel, i.e. a GEMM over im2col rows), in_proj (QKV), out_proj, mlp.c_fc, mlp.c_proj and the final
+// `@ proj`.  Bias, QuickGELU, the residual add and the positional-embedding add are fused epilogues.
+//
+// Structure (persistent, one CTA per SM, 320 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of A (128x64) and W (BNx64) tiles, SWIZZLE_128B,
+//               4-stage mbarrier ring
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16),
+//               accumulators in TMEM (2 x BN fp32 columns, double buffered against the epilogue)
+//   warps 2-9   epilogue: tcgen05.ld 32x32b.x32 -> registers -> bias/activation/residual -> global stores
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;             // 64 bf16 = 128 bytes = one SWIZZLE_128B atom row
+constexpr int STAGES = 4;
+constexpr int NUM_THREADS = 320;   // 10 warps
+constexpr int EPI_WARPS = 8;
+constexpr int UMMA_K = 16;
+
+struct GemmParams {
+    int M, N, K;
+    int epi;
+    void *out;
+    int ldo;
+    const float *bias;
+    const float *res;
+    int row_map;          // tokens per image (G*G) for EC_EPI_PATCH
+    int tiles_m, tiles_n;
+    uint32_t tx_bytes;    // bytes landing per stage (A box + W box)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a protocol bug traps after ~2 s instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    uint64_t t0 = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!done && (spins & 0x3ff) == 0x3ff) {
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull) __trap();
+        }
+    }
+}
+
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major operand tile, SWIZZLE_128B: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), descriptor version 1.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)1 << 16;                  // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset
+    d |= (uint64_t)1 << 46;                  // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// arrives on `bar` when every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float quick_gelu(float x)
+{
+    // x * sigmoid(1.702 x) = x / (1 + 2^(-1.702 * log2(e) * x))
+    const float e = exp2f(-2.4554669595930157f * x);
+    return __fdividef(x, 1.0f + e);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const GemmParams p)
+{
+    constexpr uint32_t A_BYTES = BM * BK * 2;
+    constexpr uint32_t B_BYTES = BN * BK * 2;
+    constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t TMEM_COLS = 2 * BN;   // 256 or 512: power of two >= 32
+    // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
+    __shared__ __align__(8) uint64_t tfull_bar[2];
+    __shared__ __align__(8) uint64_t tempty_bar[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = p.tiles_m * p.tiles_n;
+    const int num_kb = (p.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    unsigned char *sa = smem + stage * STAGE_BYTES;
+                    unsigned char *sb = sa + A_BYTES;
+                    mbar_expect_tx(&full_bar[stage], p.tx_bytes);
+                    tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, tm * BM);
+                    tma_load_2d(sb, &map_w, &full_bar[stage], kb * BK, tn * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[as], aphase ^ 1);   // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint64_t adesc = make_smem_desc(sa);
+                    const uint64_t bdesc = make_smem_desc(sa + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
+                        umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);        // smem slot reusable once these MMAs retire
+                    if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue =====================
+        const int ew = warp - 2;           // 0..7
+        const int quarter = warp & 3;      // TMEM lane quarter this warp may touch
+        const int half = ew >> 2;          // which half of the BN columns
+        constexpr int COLS_PER_WARP = BN / 2;
+        uint32_t as = 0, aphase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+            mbar_wait(&tfull_bar[as], aphase);
+            tc_fence_after();
+            const int row = tm * BM + quarter * 32 + lane;
+            const bool row_ok = row < p.M;
+            size_t orow = (size_t)row;
+            const float *posrow = nullptr;
+            if (p.epi == EC_EPI_PATCH) {
+                const int g2 = p.row_map;
+                const int img = row / g2, tok = row % g2;
+                orow = (size_t)img * (g2 + 1) + 1 + tok;
+                posrow = p.res + (size_t)(1 + tok) * p.N;
+            }
+#pragma unroll 1
+            for (int c = 0; c < COLS_PER_WARP; c += 32) {
+                const int col0 = tn * BN + half * COLS_PER_WARP + c;
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * COLS_PER_WARP + c);
+                tmem_ld32(taddr, v);
+                if (row_ok && col0 < p.N) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        const int col = col0 + j;
+                        if (col >= p.N) break;      // N is a multiple of 8
+                        float f[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]);
+                        if (p.bias) {
+                            const float4 b0 = *reinterpret_cast<const float4 *>(p.bias + col);
+                            const float4 b1 = *reinterpret_cast<const float4 *>(p.bias + col + 4);
+                            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                        }
+                        if (p.epi == EC_EPI_BF16 || p.epi == EC_EPI_BF16_QGELU) {
+                            if (p.epi == EC_EPI_BF16_QGELU) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) f[e] = quick_gelu(f[e]);
+                            }
+                            uint4 o;
+                            __nv_bfloat162 h;
+                            h = __floats2bfloat162_rn(f[0], f[1]); o.x = *reinterpret_cast<uint32_t *>(&h);
+                            h = __floats2bfloat162_rn(f[2], f[3]); o.y = *reinterpret_cast<uint32_t *>(&h);
+                            h = __floats2bfloat162_rn(f[4], f[5]); o.z = *reinterpret_cast<uint32_t *>(&h);
+                            h = __floats2bfloat162_rn(f[6], f[7]); o.w = *reinterpret_cast<uint32_t *>(&h);
+                            *reinterpret_cast<uint4 *>((__nv_bfloat16 *)p.out + orow * p.ldo + col) = o;
+                        } else {
+                            const float *r = nullptr;
+                            if (p.epi == EC_EPI_F32_RESADD) r = p.res + orow * p.ldo + col;
+                            else if (p.epi == EC_EPI_PATCH) r = posrow + col;
+                            if (r) {
+                                const float4 r0 = *reinterpret_cast<const float4 *>(r);
+                                const float4 r1 = *reinterpret_cast<const float4 *>(r + 4);
+                                f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
+                                f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
+                            }
+                            float *o = (float *)p.out + orow * p.ldo + col;
+                            *reinterpret_cast<float4 *>(o) = make_float4(f[0], f[1], f[2], f[3]);
+                            *reinterpret_cast<float4 *>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                        }
+                    }
+                }
+            }
+            // all tcgen05.ld of this warp have completed (wait::ld inside tmem_ld32): release the accumulator
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host: tensor maps through the driver entry point (no link-time libcuda dependency) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode()
+{
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    });
+    return fn;
+}
+
+// 2D bf16 row-major [rows, cols] with row stride ld (elements); box = [box_rows, 64] ; SWIZZLE_128B
+int make_map(CUtensorMap *m, const void *base, int rows, int cols, int ld, int box_rows)
+{
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { ec::set_error("cuTensorMapEncodeTiled entry point not available"); return EC_ERR_CUDA; }
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { ec::set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return EC_ERR_CUDA; }
+    return EC_OK;
+}
+
+template <int BN>
+int launch(const CUtensorMap &ma, const CUtensorMap &mw, GemmParams &p, cudaStream_t stream)
+{
+    constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        EC_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    p.tiles_m = (p.M + BM - 1) / BM;
+    p.tiles_n = (p.N + BN - 1) / BN;
+    const int tiles = p.tiles_m * p.tiles_n;
+    const int grid = tiles < ec::sm_count() ? tiles : ec::sm_count();
+    gemm_kernel<BN><<<grid, NUM_THREADS, smem, stream>>>(ma, mw, p);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
+}  // namespace
+
+extern "C" int ec_gemm_bf16(const void *A, int lda, const void *W, int ldw, const float *bias, int M, int N, int K,
+                            int epi, void *out, int ldo, const float *res, int row_map, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    EC_REQUIRE(A && W && out, "ec_gemm_bf16: null pointer");
+    EC_REQUIRE(M > 0 && N > 0 && K >= BK, "ec_gemm_bf16: need M,N > 0 and K >= 64 (got %d,%d,%d)", M, N, K);
+    EC_REQUIRE(N % 8 == 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= K,
+               "ec_gemm_bf16: N, K, lda, ldw must be multiples of 8 (N=%d K=%d lda=%d ldw=%d)", N, K, lda, ldw);
+    EC_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)out & 15) == 0,
+               "ec_gemm_bf16: pointers must be 16-byte aligned");
+    EC_REQUIRE(epi >= EC_EPI_BF16 && epi <= EC_EPI_PATCH, "ec_gemm_bf16: bad epilogue %d", epi);
+    EC_REQUIRE(ldo >= N && ldo % 8 == 0, "ec_gemm_bf16: bad ldo %d", ldo);
+    if (epi == EC_EPI_F32_RESADD || epi == EC_EPI_PATCH) EC_REQUIRE(res != nullptr, "ec_gemm_bf16: epilogue needs res");
+    if (epi == EC_EPI_PATCH) EC_REQUIRE(row_map > 0 && M % row_map == 0, "ec_gemm_bf16: bad row_map %d", row_map);
+
+    const int BN = (N % 256 == 0) ? 256 : 128;
+    const int box_a = M < BM ? M : BM;
+    const int box_w = N < BN ? N : BN;
+    CUtensorMap ma, mw;
+    int rc = make_map(&ma, A, M, K, lda, box_a);
+    if (rc != EC_OK) return rc;
+    rc = make_map(&mw, W, N, K, ldw, box_w);
+    if (rc != EC_OK) return rc;
+
+    GemmParams p;
+    p.M = M; p.N = N; p.K = K; p.epi = epi; p.out = out; p.ldo = ldo; p.bias = bias; p.res = res; p.row_map = row_map;
+    p.tx_bytes = (uint32_t)(box_a + box_w) * BK * 2;
+    return BN == 256 ? launch<256>(ma, mw, p, stream) : launch<128>(ma, mw, p, stream);
+}

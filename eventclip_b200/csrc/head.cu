@@ -1,0 +1,300 @@
+// head.cu -- classifier heads: text-cosine logits + per-sample aggregation, and the fp32 few-shot adapter pieces.
+//
+// Reference semantics (paths relative to the reference root):
+//   zero-shot head      models/clip_cls.py:144-154   logits = scale * feats @ text.T (feats NOT normalised)
+//   few-shot / FT head  models/clip_cls.py:326-342, models/clip_cls_ft.py:232-248  (L2-normalise, mask, logits)
+//   _aggregate_logits   models/clip_cls.py:104-121   sum | mean over valid | max with -1e6 on invalid
+//   _aggregate_probs    models/clip_cls.py:123-129   softmax per view, masked mean
+//   top-1 / top-5       test.py:66-81
+//   adapter             models/adapter.py:82-105 (nn.TransformerEncoderLayer, norm_first, ReLU FFN, key padding mask)
+// All of it is fp32 SIMT: < 0.1 % of the FLOPs and it decides top-1, so it is kept in the reference's precision.
+#include "common.cuh"
+
+namespace {
+
+constexpr int HEAD_THREADS = 256;
+
+// block-wide (value, index) arg-max; ties resolve to the lowest index (torch.argmax convention)
+__device__ void block_argmax(float v, int idx, float *sv, int *si, float &best, int &besti)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+    __syncthreads();
+    if (lane == 0) { sv[warp] = v; si[warp] = idx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float b = sv[0];
+        int bi = si[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+            if (sv[w] > b || (sv[w] == b && si[w] < bi)) { b = sv[w]; bi = si[w]; }
+        sv[0] = b; si[0] = bi;
+    }
+    __syncthreads();
+    best = sv[0]; besti = si[0];
+}
+
+__device__ float block_reduce(float v, float *sv, bool is_max)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = is_max ? ec::warp_max(v) : ec::warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sv[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float b = sv[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) b = is_max ? fmaxf(b, sv[w]) : b + sv[w];
+        sv[0] = b;
+    }
+    __syncthreads();
+    return sv[0];
+}
+
+// One CTA per sample.  smem: feats [T][C] | logits [T][n_cls] | agg [n_cls] | probs [n_cls]
+__global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const float *__restrict__ feats, const uint8_t *__restrict__ valid,
+                                                            const float *__restrict__ text, int T, int C, int n_cls,
+                                                            float scale, int normalize, int agg, float *out_full,
+                                                            float *out_logits, float *out_probs, int32_t *out_top)
+{
+    extern __shared__ __align__(16) float sm[];
+    float *sf = sm;
+    float *sl = sf + (size_t)T * C;
+    float *sagg = sl + (size_t)T * n_cls;
+    float *sprob = sagg + n_cls;
+    __shared__ float sv[32];
+    __shared__ int si[32];
+    __shared__ float vmask[16];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+
+    if (tid < T) vmask[tid] = valid[(size_t)b * T + tid] ? 1.f : 0.f;
+    __syncthreads();
+    float nvalid = 0.f;
+    for (int t = 0; t < T; ++t) nvalid += vmask[t];
+
+    // features of the T views: optional L2 normalisation (F.normalize eps 1e-12), mask, then * scale
+    for (int t = warp; t < T; t += nwarp) {
+        const float *f = feats + ((size_t)b * T + t) * C;
+        float mul = 0.f;
+        if (vmask[t] != 0.f) {
+            mul = 1.f;
+            if (normalize) {
+                float ss = 0.f;
+                for (int c = lane; c < C; c += 32) { const float x = f[c]; ss += x * x; }
+                ss = ec::warp_sum(ss);
+                mul = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+            }
+        }
+        for (int c = lane; c < C; c += 32) sf[(size_t)t * C + c] = vmask[t] != 0.f ? (f[c] * mul) * scale : 0.f;
+    }
+    __syncthreads();
+
+    // logits[t][k] = <scale * f_t, text_k>; one warp per class row, all views at once
+    for (int k = warp; k < n_cls; k += nwarp) {
+        const float *tx = text + (size_t)k * C;
+        float acc[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) acc[t] = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float w = tx[c];
+#pragma unroll
+            for (int t = 0; t < 16; ++t)
+                if (t < T) acc[t] = fmaf(sf[(size_t)t * C + c], w, acc[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < 16; ++t)
+            if (t < T) {
+                const float v = ec::warp_sum(acc[t]);
+                if (lane == 0) sl[(size_t)t * n_cls + k] = vmask[t] != 0.f ? v : 0.f;
+            }
+    }
+    __syncthreads();
+
+    // aggregated logits
+    for (int k = tid; k < n_cls; k += blockDim.x) {
+        float a;
+        if (agg == EC_AGG_MAX) {
+            a = -INFINITY;
+            for (int t = 0; t < T; ++t) a = fmaxf(a, sl[(size_t)t * n_cls + k] - (1.f - vmask[t]) * 1e6f);
+        } else {
+            a = 0.f;
+            for (int t = 0; t < T; ++t) a += sl[(size_t)t * n_cls + k];
+            if (agg == EC_AGG_MEAN) a = a / nvalid;
+        }
+        sagg[k] = a;
+        sprob[k] = 0.f;
+        if (out_logits) out_logits[(size_t)b * n_cls + k] = a;
+        if (out_full)
+            for (int t = 0; t < T; ++t) out_full[((size_t)b * T + t) * n_cls + k] = sl[(size_t)t * n_cls + k];
+    }
+    __syncthreads();
+
+    // probs = mean over valid views of softmax(logits_t)
+    for (int t = 0; t < T; ++t) {
+        if (vmask[t] == 0.f) continue;   // uniform across the block
+        float m = -INFINITY;
+        for (int k = tid; k < n_cls; k += blockDim.x) m = fmaxf(m, sl[(size_t)t * n_cls + k]);
+        m = block_reduce(m, sv, true);
+        float s = 0.f;
+        for (int k = tid; k < n_cls; k += blockDim.x) s += expf(sl[(size_t)t * n_cls + k] - m);
+        s = block_reduce(s, sv, false);
+        for (int k = tid; k < n_cls; k += blockDim.x) sprob[k] += expf(sl[(size_t)t * n_cls + k] - m) / s;
+    }
+    __syncthreads();
+    for (int k = tid; k < n_cls; k += blockDim.x) {
+        const float pr = sprob[k] / nvalid;
+        sprob[k] = pr;
+        if (out_probs) out_probs[(size_t)b * n_cls + k] = pr;
+    }
+    __syncthreads();
+
+    // top-5 of logits and probs (repeated arg-max with exclusion)
+    if (out_top) {
+        for (int which = 0; which < 2; ++which) {
+            float *src = which == 0 ? sagg : sprob;
+            for (int r = 0; r < 5; ++r) {
+                float v = -INFINITY;
+                int idx = 0x7fffffff;
+                for (int k = tid; k < n_cls; k += blockDim.x)
+                    if (src[k] > v) { v = src[k]; idx = k; }
+                float bv;
+                int bi;
+                block_argmax(v, idx, sv, si, bv, bi);
+                if (tid == 0) {
+                    out_top[((size_t)b * 2 + which) * 5 + r] = (r < n_cls && bi != 0x7fffffff) ? bi : -1;
+                    if (bi != 0x7fffffff) src[bi] = -INFINITY;
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+
+// ---- fp32 SGEMM for the adapter: out = act(A W^T + bias) (+ res); 64x64 tile, 16-deep, 256 threads, 4x4 per thread ----
+__global__ void __launch_bounds__(256) sgemm_kernel(const float *__restrict__ A, const float *__restrict__ W,
+                                                    const float *__restrict__ bias, const float *__restrict__ res, int M,
+                                                    int N, int K, int act, float *__restrict__ out)
+{
+    __shared__ float sa[16][64 + 4];
+    __shared__ float sw[16][64 + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    const int tx = tid & 15, ty = tid >> 4;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        for (int i = tid; i < 64 * 16; i += 256) {
+            const int r = i >> 4, c = i & 15;
+            sa[c][r] = (m0 + r < M && k0 + c < K) ? A[(size_t)(m0 + r) * K + k0 + c] : 0.f;
+            sw[c][r] = (n0 + r < N && k0 + c < K) ? W[(size_t)(n0 + r) * K + k0 + c] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            float a[4], w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = sa[c][ty * 4 + i]; w[i] = sw[c][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+            if (m < M && n < N) {
+                float v = acc[i][j] + (bias ? bias[n] : 0.f);
+                if (act == 1) v = fmaxf(v, 0.f);
+                if (res) v += res[(size_t)m * N + n];
+                out[(size_t)m * N + n] = v;
+            }
+        }
+}
+
+// One CTA per sample, one warp per head; T <= 16 views.
+__global__ void adapter_attention_kernel(const float *__restrict__ qkv, const uint8_t *__restrict__ valid, int T, int D,
+                                         int heads, float *__restrict__ out)
+{
+    const int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (h >= heads) return;
+    const int hd = D / heads;
+    const float sc = rsqrtf((float)hd);
+    const float *base = qkv + (size_t)b * T * 3 * D + h * hd;
+    for (int t = 0; t < T; ++t) {
+        float s[16];
+        float m = -INFINITY;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            s[u] = -INFINITY;
+            if (u < T) {
+                float acc = 0.f;
+                for (int c = lane; c < hd; c += 32) acc = fmaf(base[(size_t)t * 3 * D + c], base[(size_t)u * 3 * D + D + c], acc);
+                acc = ec::warp_sum(acc) * sc;
+                if (valid[(size_t)b * T + u]) { s[u] = acc; m = fmaxf(m, acc); }
+            }
+        }
+        float den = 0.f;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            s[u] = (u < T && s[u] != -INFINITY) ? expf(s[u] - m) : 0.f;
+            den += s[u];
+        }
+        for (int c = lane; c < hd; c += 32) {
+            float acc = 0.f;
+#pragma unroll
+            for (int u = 0; u < 16; ++u)
+                if (u < T) acc = fmaf(s[u], base[(size_t)u * 3 * D + 2 * D + c], acc);
+            out[((size_t)b * T + t) * D + h * hd + c] = acc / den;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int ec_head(const float *feats, const uint8_t *valid, const float *text, int B, int T, int C, int n_cls,
+                       float scale, int normalize, int agg, float *out_full, float *out_logits, float *out_probs,
+                       int32_t *out_top, void *stream)
+{
+    EC_REQUIRE(feats && valid && text, "ec_head: null pointer");
+    EC_REQUIRE(B > 0 && T > 0 && T <= 16 && C > 0 && n_cls > 0, "ec_head: bad shape B=%d T=%d C=%d n_cls=%d (T <= 16)", B, T, C,
+               n_cls);
+    EC_REQUIRE(agg >= EC_AGG_SUM && agg <= EC_AGG_MAX, "ec_head: bad aggregation %d", agg);
+    const size_t smem = ((size_t)T * C + (size_t)T * n_cls + 2 * (size_t)n_cls) * sizeof(float);
+    EC_REQUIRE(smem <= 220 * 1024, "ec_head: T*C + T*n_cls too large for shared memory (%zu bytes)", smem);
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        EC_CUDA_CHECK(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    head_kernel<<<B, HEAD_THREADS, smem, (cudaStream_t)stream>>>(feats, valid, text, T, C, n_cls, scale, normalize, agg, out_full,
+                                                                 out_logits, out_probs, out_top);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
+extern "C" int ec_gemm_f32(const float *A, const float *W, const float *bias, const float *res, int M, int N, int K, int act,
+                           float *out, void *stream)
+{
+    EC_REQUIRE(A && W && out && M > 0 && N > 0 && K > 0, "ec_gemm_f32: bad arguments");
+    EC_REQUIRE(act == 0 || act == 1, "ec_gemm_f32: bad activation %d", act);
+    sgemm_kernel<<<dim3((N + 63) / 64, (M + 63) / 64), 256, 0, (cudaStream_t)stream>>>(A, W, bias, res, M, N, K, act, out);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
+extern "C" int ec_adapter_attention(const float *qkv, const uint8_t *valid, int B, int T, int D, int heads, float *out,
+                                    void *stream)
+{
+    EC_REQUIRE(qkv && valid && out, "ec_adapter_attention: null pointer");
+    EC_REQUIRE(B > 0 && T > 0 && T <= 16 && heads > 0 && heads <= 32 && D % heads == 0,
+               "ec_adapter_attention: bad shape B=%d T=%d D=%d heads=%d", B, T, D, heads);
+    adapter_attention_kernel<<<B, heads * 32, 0, (cudaStream_t)stream>>>(qkv, valid, T, D, heads, out);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}

@@ -1,0 +1,269 @@
+"""Tensor-level wrappers over the C ABI.  PyTorch is plumbing here (device memory, streams); all arithmetic happens
+in libeventclip_b200.so.  Every function enqueues on torch's current stream and returns immediately."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+OUT_FMT = {"f32": L.EC_OUT_F32_NCHW, "bf16": L.EC_OUT_BF16_NCHW, "patch": L.EC_OUT_BF16_PATCH}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _dev(t, dtype=None, name="tensor"):
+    if not t.is_cuda:
+        raise L.ECError(f"{name} must be a CUDA tensor (no CPU fallback exists)")
+    if not t.is_contiguous():
+        raise L.ECError(f"{name} must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise L.ECError(f"{name} must be {dtype}, got {t.dtype}")
+    L.require_device(t.device.index)
+    return t
+
+
+# ------------------------------------------------------------------------------------------------ event2img
+def plan_frames(offsets, N, T, sel=None, compact=False):
+    """Host planning (ec_plan_frames).  offsets: int64 [B+1] (CPU tensor / array).
+    Returns (frames uint8 CPU tensor [n_frames,16] (pinned when CUDA is available), valid bool [B,T] CPU,
+    chunks int32 [B] CPU, n_valid)."""
+    off = np.ascontiguousarray(np.asarray(offsets, dtype=np.int64))
+    B = off.shape[0] - 1
+    cap = B * T
+    pin = torch.cuda.is_available()
+    frames = torch.empty((max(cap, 1), 16), dtype=torch.uint8, pin_memory=pin)
+    valid = np.zeros((B, T), np.uint8)
+    chunks = np.zeros(B, np.int32)
+    selp = C.c_void_p(0)
+    if sel is not None:
+        sel = np.ascontiguousarray(np.asarray(sel, dtype=np.int32))
+        if sel.shape != (B, T):
+            raise L.ECError(f"sel must have shape {(B, T)}, got {sel.shape}")
+        selp = C.c_void_p(sel.ctypes.data)
+    nf, nv = C.c_int(0), C.c_int(0)
+    rc = L.load().ec_plan_frames(C.c_void_p(off.ctypes.data), B, int(N), int(T), selp, int(bool(compact)),
+                                 C.c_void_p(frames.data_ptr()), cap, C.c_void_p(valid.ctypes.data),
+                                 C.c_void_p(chunks.ctypes.data), C.byref(nf), C.byref(nv))
+    if rc == L.EC_ERR_ARG and "no events" in L.load().ec_last_error().decode():
+        raise AssertionError(L.load().ec_last_error().decode())
+    L.check(rc, "ec_plan_frames")
+    return frames[:nf.value], torch.from_numpy(valid.astype(bool)), torch.from_numpy(chunks), nv.value
+
+
+def event2img(events, frames, shape, n_slots, count_non_zero=False, background_mask=True, out="f32", patch=0,
+              ldk=0, out_tensor=None, debug=False, status=None):
+    """Fused frames (ec_event2img).  events: CUDA float32 [E,4]; frames: CUDA uint8 [n_frames,16].
+    Returns (images, status int32[1] CUDA tensor, debug dict or None)."""
+    _dev(events, torch.float32, "events")
+    _dev(frames, torch.uint8, "frames")
+    if events.dim() != 2 or events.shape[1] != 4:
+        raise L.ECError("events must be [E, 4] rows of (x, y, t, p)")
+    H, W = shape
+    n_frames = frames.shape[0]
+    fmt = OUT_FMT[out]
+    dev = events.device
+    if out_tensor is None:
+        if fmt == L.EC_OUT_F32_NCHW:
+            out_tensor = torch.empty((n_slots, 3, 224, 224), dtype=torch.float32, device=dev)
+        elif fmt == L.EC_OUT_BF16_NCHW:
+            out_tensor = torch.empty((n_slots, 3, 224, 224), dtype=torch.bfloat16, device=dev)
+        else:
+            G = 224 // patch
+            ldk = ldk or 3 * patch * patch
+            out_tensor = torch.zeros((n_slots * G * G, ldk), dtype=torch.bfloat16, device=dev)
+    if status is None:
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+    dbg = None
+    dc = dg = du = None
+    if debug:
+        dc = torch.zeros((n_frames, H, W, 2), dtype=torch.int32, device=dev)
+        dg = torch.zeros((n_frames, H, W), dtype=torch.uint8, device=dev)
+        du = torch.zeros((n_frames, 224, 224), dtype=torch.uint8, device=dev)
+        dbg = dict(counts=dc, gray=dg, u8=du)
+    flags = (L.EC_FLAG_COUNT_NON_ZERO if count_non_zero else 0) | (L.EC_FLAG_BACKGROUND_MASK if background_mask else 0)
+    with torch.cuda.device(dev):
+        rc = L.load().ec_event2img(_ptr(events), _ptr(frames), n_frames, H, W, flags, fmt, int(patch), int(ldk),
+                                   _ptr(out_tensor), _ptr(dc), _ptr(dg), _ptr(du), _ptr(status), _stream())
+    L.check(rc, "ec_event2img")
+    return out_tensor, status, dbg
+
+
+def raise_on_status(status):
+    """Synchronising check of the device status word; mirrors the reference's exception types."""
+    s = int(status.item())
+    if s & L.EC_STATUS_BAD_COORD:
+        # np.bincount / reshape raise ValueError on such input (datasets/vis.py:12-14)
+        raise ValueError("event coordinates outside the sensor: x + y*W must lie in [0, H*W)")
+    if s & L.EC_STATUS_COUNT_OVERFLOW:
+        raise L.ECError("a per-pixel event count exceeded 65535 in one frame (packed histogram overflow)")
+
+
+def event2img_geometry(shape):
+    cs, nt, sm = C.c_int(), C.c_int(), C.c_int()
+    L.check(L.load().ec_event2img_geometry(shape[0], shape[1], C.byref(cs), C.byref(nt), C.byref(sm)),
+            "ec_event2img_geometry")
+    return dict(cluster=cs.value, threads=nt.value, smem=sm.value)
+
+
+# ------------------------------------------------------------------------------------------------ encoder pieces
+def gemm_bf16(A, W, bias=None, epi="bf16", out=None, res=None, row_map=0, M=None):
+    """out = epilogue(A @ W.T).  A bf16 [M,K] (row stride may exceed K), W bf16 [N,K]."""
+    _dev(A, torch.bfloat16, "A")
+    _dev(W, torch.bfloat16, "W")
+    M = A.shape[0] if M is None else M
+    N, K = W.shape
+    epi_id = {"bf16": L.EC_EPI_BF16, "bf16_qgelu": L.EC_EPI_BF16_QGELU, "f32_resadd": L.EC_EPI_F32_RESADD,
+              "f32": L.EC_EPI_F32, "patch": L.EC_EPI_PATCH}[epi]
+    if out is None:
+        if epi == "patch":
+            raise L.ECError("patch epilogue needs a preallocated token matrix")
+        out = torch.empty((M, N), dtype=torch.bfloat16 if epi_id <= 1 else torch.float32, device=A.device)
+    with torch.cuda.device(A.device):
+        rc = L.load().ec_gemm_bf16(_ptr(A), A.stride(0), _ptr(W), W.stride(0), _ptr(bias), M, N, K, epi_id,
+                                   _ptr(out), out.stride(0), _ptr(res), int(row_map), _stream())
+    L.check(rc, "ec_gemm_bf16")
+    return out
+
+
+def layernorm(x, gamma, beta, M, d, row_stride=None, out_bf16=None, out_f32=None):
+    _dev(x, torch.float32, "x")
+    with torch.cuda.device(x.device):
+        rc = L.load().ec_layernorm(_ptr(x), int(row_stride or d), _ptr(gamma), _ptr(beta), M, d, _ptr(out_bf16),
+                                   _ptr(out_f32), _stream())
+    L.check(rc, "ec_layernorm")
+
+
+def attention(qkv, out, n_img, Ltok, heads):
+    _dev(qkv, torch.bfloat16, "qkv")
+    with torch.cuda.device(qkv.device):
+        rc = L.load().ec_attention(_ptr(qkv), _ptr(out), n_img, Ltok, heads, _stream())
+    L.check(rc, "ec_attention")
+    return out
+
+
+def cls_rows(x, cls, pos, n_img, Ltok, d):
+    _dev(x, torch.float32, "x")
+    with torch.cuda.device(x.device):
+        L.check(L.load().ec_cls_rows(_ptr(x), _ptr(cls), _ptr(pos), n_img, Ltok, d, _stream()), "ec_cls_rows")
+
+
+def f32_to_bf16(src, dst=None):
+    _dev(src, torch.float32, "src")
+    if dst is None:
+        dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    with torch.cuda.device(src.device):
+        L.check(L.load().ec_f32_to_bf16(_ptr(src), _ptr(dst), src.numel(), _stream()), "ec_f32_to_bf16")
+    return dst
+
+
+def im2col(img, patch, ldk=None):
+    """img CUDA [n,3,224,224] fp32 or bf16 -> bf16 [n*G*G, ldk]."""
+    _dev(img, None, "img")
+    if img.dtype not in (torch.float32, torch.bfloat16):
+        raise L.ECError(f"img must be float32 or bfloat16, got {img.dtype}")
+    n = img.shape[0]
+    G = 224 // patch
+    K = 3 * patch * patch
+    ldk = ldk or K
+    out = (torch.zeros if ldk != K else torch.empty)((n * G * G, ldk), dtype=torch.bfloat16, device=img.device)
+    with torch.cuda.device(img.device):
+        L.check(L.load().ec_im2col(_ptr(img), int(img.dtype == torch.bfloat16), n, patch, ldk, _ptr(out), _stream()),
+                "ec_im2col")
+    return out
+
+
+def lora_merge(W, up, down, out=None):
+    """bf16(W + up @ down) in fp32 math (models/lora.py:138-149)."""
+    _dev(W, torch.float32, "W")
+    rows, d = W.shape
+    r = up.shape[1] if up is not None else 0
+    if out is None:
+        out = torch.empty((rows, d), dtype=torch.bfloat16, device=W.device)
+    with torch.cuda.device(W.device):
+        L.check(L.load().ec_lora_merge(_ptr(W), _ptr(up), _ptr(down), rows, d, r, _ptr(out), _stream()), "ec_lora_merge")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ heads
+def head(feats, valid_u8, text, B, T, scale, normalize, agg, want_top=True):
+    _dev(feats, torch.float32, "feats")
+    _dev(text, torch.float32, "text")
+    _dev(valid_u8, torch.uint8, "valid")
+    C_ = feats.shape[-1]
+    n_cls = text.shape[0]
+    dev = feats.device
+    full = torch.empty((B, T, n_cls), dtype=torch.float32, device=dev)
+    logits = torch.empty((B, n_cls), dtype=torch.float32, device=dev)
+    probs = torch.empty((B, n_cls), dtype=torch.float32, device=dev)
+    top = torch.empty((B, 2, 5), dtype=torch.int32, device=dev) if want_top else None
+    with torch.cuda.device(dev):
+        rc = L.load().ec_head(_ptr(feats), _ptr(valid_u8), _ptr(text), B, T, C_, n_cls, float(scale), int(normalize),
+                              L.EC_AGG[agg], _ptr(full), _ptr(logits), _ptr(probs), _ptr(top), _stream())
+    L.check(rc, "ec_head")
+    return full, logits, probs, top
+
+
+def gemm_f32(A, W, bias=None, res=None, act=0):
+    _dev(A, torch.float32, "A")
+    _dev(W, torch.float32, "W")
+    M, K = A.shape
+    N = W.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    with torch.cuda.device(A.device):
+        L.check(L.load().ec_gemm_f32(_ptr(A), _ptr(W), _ptr(bias), _ptr(res), M, N, K, act, _ptr(out), _stream()),
+                "ec_gemm_f32")
+    return out
+
+
+def adapter_attention(qkv, valid_u8, B, T, D, heads):
+    _dev(qkv, torch.float32, "qkv")
+    out = torch.empty((B * T, D), dtype=torch.float32, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        L.check(L.load().ec_adapter_attention(_ptr(qkv), _ptr(valid_u8), B, T, D, heads, _ptr(out), _stream()),
+                "ec_adapter_attention")
+    return out
+
+
+def blend(a, b, r):
+    _dev(a, torch.float32, "a")
+    out = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        L.check(L.load().ec_blend(_ptr(a), _ptr(b), float(r), _ptr(out), a.numel(), _stream()), "ec_blend")
+    return out
+
+
+def layernorm_f32(x, gamma, beta):
+    _dev(x, torch.float32, "x")
+    M, d = x.shape
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        L.check(L.load().ec_layernorm_f32(_ptr(x), _ptr(gamma), _ptr(beta), M, d, _ptr(out), _stream()),
+                "ec_layernorm_f32")
+    return out
+
+
+def gather_rows(src, idx_i32, n_rows):
+    """dst[s] = src[idx[s]] or zeros where idx[s] < 0."""
+    _dev(src, torch.float32, "src")
+    _dev(idx_i32, torch.int32, "idx")
+    Cdim = src.shape[-1]
+    dst = torch.empty((n_rows, Cdim), dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        L.check(L.load().ec_gather_rows(_ptr(src), _ptr(idx_i32), _ptr(dst), n_rows, Cdim, _stream()), "ec_gather_rows")
+    return dst
+
+
+def l2norm_rows(x):
+    _dev(x, torch.float32, "x")
+    M, Cdim = x.shape
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        L.check(L.load().ec_l2norm_rows(_ptr(x), _ptr(out), M, Cdim, _stream()), "ec_l2norm_rows")
+    return out

@@ -1,0 +1,182 @@
+/*
+ * eventclip_b200.h -- C ABI of the B200-native EventCLIP inference hot path.
+ *
+ * Every entry point is plain `extern "C"`: raw device/host pointers, sizes and a
+ * cudaStream_t passed as void*.  No torch types, no C++ types, no exceptions.
+ * Functions return 0 on success or a negative EC_ERR_* code; ec_last_error()
+ * returns a thread-local message for the last failure.  All device work is
+ * enqueued on the given stream and is asynchronous; the library never
+ * synchronises.  The caller (PyTorch on the reference side) owns every buffer.
+ *
+ * Each function cites the reference interface it replaces (paths relative to
+ * the reference repository root).  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ */
+#ifndef EVENTCLIP_B200_H
+#define EVENTCLIP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define EC_API __attribute__((visibility("default")))
+#else
+#define EC_API
+#endif
+
+#define EC_OK 0
+#define EC_ERR_ARG -1         /* bad shape / null pointer / unsupported option   */
+#define EC_ERR_CUDA -2        /* CUDA runtime error (see ec_last_error)          */
+#define EC_ERR_UNSUPPORTED -3 /* device is not sm_100 or shape exceeds limits    */
+#define EC_ERR_CAPACITY -4    /* caller-provided table / workspace too small     */
+
+/* bits of the device status word written by ec_event2img (0 = clean) */
+#define EC_STATUS_BAD_COORD 1      /* x + y*W outside [0, H*W): numpy would raise ValueError (vis.py:12-14) */
+#define EC_STATUS_COUNT_OVERFLOW 2 /* a per-pixel polarity count exceeded 65535 in the packed histogram     */
+
+/* flags of ec_event2img */
+#define EC_FLAG_COUNT_NON_ZERO 1  /* quantize_args['count_non_zero'] (vis.py:18-20)   */
+#define EC_FLAG_BACKGROUND_MASK 2 /* quantize_args['background_mask'] (vis.py:34-37)  */
+
+/* output formats of ec_event2img */
+#define EC_OUT_F32_NCHW 0  /* float32 [slot,3,224,224] -- the tensor the reference DataLoader yields */
+#define EC_OUT_BF16_NCHW 1 /* same layout, bf16 (round-to-nearest-even of the float32 value)      */
+#define EC_OUT_BF16_PATCH 2 /* bf16 [slot, G*G, ldk] im2col rows (c,dy,dx) feeding the patch GEMM  */
+
+EC_API const char *ec_last_error(void);
+EC_API int ec_version(void);
+/* 0 when the current CUDA device is sm_100 (B200); EC_ERR_UNSUPPORTED otherwise. No CPU fallback exists. */
+EC_API int ec_device_check(void);
+
+/* One frame of work for ec_event2img: events [ev_start, ev_start+ev_count) of the packed
+ * stream are histogrammed and written to output image `out_slot`.  ev_count == 0 writes an
+ * all-zero image (the reference's zero padding of missing views, datasets/event2img.py:89-91). */
+typedef struct ec_frame {
+    int64_t ev_start;
+    int32_t ev_count;
+    int32_t out_slot;
+} ec_frame;
+
+/* HOST function.  Replaces split_event_count (datasets/vis.py:55-72), the view-count rule and
+ * _subsample_imgs (datasets/event2img.py:70-72, 80-92) for a batch of B packed samples.
+ *   offsets   host int64 [B+1]  event offsets of each sample in the packed stream
+ *   N         events per frame;  T = number of view slots per sample (max_imgs)
+ *   sel       host int32 [B,T] or NULL: chunk ids to use for samples with K > T (the caller's
+ *             torch.randperm(K)[:T] draw, event2img.py:85); NULL selects chunks 0..T-1
+ *   compact   0: out_slot = b*T + t and padded slots get an ev_count==0 frame (reference layout
+ *             [B,T,...]);  1: only valid views, out_slot = running index (the imgs[valid_mask]
+ *             gather of models/clip_cls.py:139)
+ *   frames    host ec_frame [cap] out;  valid host uint8 [B,T] out;  chunks host int32 [B] out
+ *             (K per sample, nullable);  n_frames / n_valid out. */
+EC_API int ec_plan_frames(const int64_t *offsets, int B, int64_t N, int T, const int32_t *sel, int compact,
+                   ec_frame *frames, int cap, uint8_t *valid, int32_t *chunks, int *n_frames, int *n_valid);
+
+/* DEVICE.  Fused event stream -> CLIP input.  Replaces, in one launch and with no intermediate
+ * tensor in HBM: parse_events + make_event_histogram (datasets/vis.py:44-52, 6-41, colour map
+ * 95-101) and the CLIP preprocess applied at datasets/event2img.py:119-122
+ * (Resize(224,bicubic) / CenterCrop(224) / ToTensor / Normalize).
+ *   events    device float32 [*,4] packed (x,y,t,p) rows, 16-byte aligned
+ *   frames    device ec_frame [n_frames]
+ *   H, W      sensor shape;  flags EC_FLAG_*;  out_fmt EC_OUT_*
+ *   patch, ldk  only for EC_OUT_BF16_PATCH: patch size P and row stride (elements, >= 3*P*P)
+ *   out       device output images (format above)
+ *   dbg_counts device int32 [n_frames,H,W,2] or NULL   (parity taps: raw counts,
+ *   dbg_gray   device uint8 [n_frames,H,W]   or NULL    uint8 frame = any channel of vis.py's output,
+ *   dbg_u8     device uint8 [n_frames,224,224] or NULL   resized+cropped uint8) indexed by frame, not slot
+ *   status    device int32 [1], OR-ed with EC_STATUS_* bits (caller zeroes it) */
+EC_API int ec_event2img(const float *events, const ec_frame *frames, int n_frames, int H, int W, int flags,
+                 int out_fmt, int patch, int ldk, void *out, int32_t *dbg_counts, uint8_t *dbg_gray,
+                 uint8_t *dbg_u8, int32_t *status, void *stream);
+
+/* Launch geometry ec_event2img will use for a sensor (for bench/roofline reporting). */
+EC_API int ec_event2img_geometry(int H, int W, int *cluster_size, int *threads, int *smem_bytes);
+
+/* ---- CLIP ViT image encoder (openai/CLIP VisionTransformer; call sites models/clip_cls.py:101,
+ *      models/clip_cls_ft.py:180) ------------------------------------------------------------ */
+
+/* C[M,N] = epilogue(A[M,K] . W[N,K]^T): bf16 operands, fp32 accumulation in TMEM (tcgen05.mma), TMA loads.
+ * The nn.Linear / conv1 / proj contractions of the encoder all go through this entry.
+ *   A   device bf16 [M,lda]   W device bf16 [N,ldw]   (lda, ldw in elements, multiples of 8, >= K)
+ *   bias device fp32 [N] or NULL
+ *   epi  EC_EPI_*;  out: bf16 or fp32 [M,ldo] depending on epi;  res: fp32 [M,ldo] residual or NULL
+ *   row_map: for EC_EPI_PATCH, tokens per image G*G (output row = (m/G2)*(G2+1) + 1 + m%G2 and
+ *            pos = fp32 [G2+1, N] positional embedding passed through `res`) */
+#define EC_EPI_BF16 0        /* out bf16 = acc + bias                                       */
+#define EC_EPI_BF16_QGELU 1  /* out bf16 = QuickGELU(acc + bias)  (x * sigmoid(1.702 x))     */
+#define EC_EPI_F32_RESADD 2  /* out fp32 = res + acc + bias       (residual stream update)   */
+#define EC_EPI_F32 3         /* out fp32 = acc + bias                                        */
+#define EC_EPI_PATCH 4       /* out fp32 token rows = acc + pos[1 + m%G2]  (patch embedding) */
+EC_API int ec_gemm_bf16(const void *A, int lda, const void *W, int ldw, const float *bias, int M, int N, int K,
+                 int epi, void *out, int ldo, const float *res, int row_map, void *stream);
+
+/* LayerNorm over the last dim (eps 1e-5, fp32 statistics): x fp32 [M, ldx] rows -> bf16 [M,d] (out_bf16)
+ * and/or fp32 [M,d] (out_f32); either output may be NULL.  row_stride_in lets ln_post read only the
+ * class-token rows (stride L*d). */
+EC_API int ec_layernorm(const float *x, int64_t row_stride_in, const float *gamma, const float *beta, int M, int d,
+                 void *out_bf16, float *out_f32, void *stream);
+
+/* Multi-head self-attention core on the packed QKV activations of nn.MultiheadAttention:
+ * qkv bf16 [n_img*L, 3*d] (q | k | v, head h at columns h*64), out bf16 [n_img*L, d].
+ * softmax(q k^T / sqrt(64)) v per (image, head); head_dim is 64 for every CLIP ViT. */
+EC_API int ec_attention(const void *qkv, void *out, int n_img, int L, int heads, void *stream);
+
+/* Writes the class-token rows of the pre-LN token matrix: x[n*L + 0, :] = class_embedding + pos[0]. */
+EC_API int ec_cls_rows(float *x, const float *class_embedding, const float *pos, int n_img, int L, int d, void *stream);
+
+/* float32 -> bf16 conversion (weights, activations). n elements. */
+EC_API int ec_f32_to_bf16(const float *src, void *dst, int64_t n, void *stream);
+
+/* NCHW image (fp32 or bf16) -> bf16 im2col rows [n_img*G*G, ldk] for images that did not come from
+ * ec_event2img (the reference's data_dict['img'] input, models/clip_cls.py:133). in_is_bf16: 0 fp32, 1 bf16. */
+EC_API int ec_im2col(const void *img, int in_is_bf16, int n_img, int patch, int ldk, void *out, void *stream);
+
+/* LoRA merge (models/lora.py:138-149 q/k/v, 49-52 out_proj): Wm[rows,d] bf16 = W[rows,d] + up[rows,r] . down[r,d],
+ * fp32 math, one rounding to bf16.  up/down NULL copies W. */
+EC_API int ec_lora_merge(const float *W, const float *up, const float *down, int rows, int d, int r, void *Wm_bf16,
+                  void *stream);
+
+/* ---- classifier heads ---------------------------------------------------------------------- */
+#define EC_AGG_SUM 0
+#define EC_AGG_MEAN 1
+#define EC_AGG_MAX 2
+/* Logit head of ZS/FS/FT classifiers (models/clip_cls.py:144-154, 326-342; models/clip_cls_ft.py:232-248).
+ *   feats  fp32 [B*T, C] view features in slot order (zeros for invalid slots are not required)
+ *   valid  uint8 [B*T];  text fp32 [n_cls, C] (already L2-normalised)
+ *   normalize  0: zero-shot (image features used as is, clip_cls.py:148)  1: L2-normalise each view first
+ *   out_full fp32 [B,T,n_cls] (invalid rows = 0), out_logits / out_probs fp32 [B,n_cls],
+ *   out_top int32 [B,2,5]: top-5 class ids of logits and of probs (nullable). */
+EC_API int ec_head(const float *feats, const uint8_t *valid, const float *text, int B, int T, int C, int n_cls,
+            float scale, int normalize, int agg, float *out_full, float *out_logits, float *out_probs,
+            int32_t *out_top, void *stream);
+
+/* fp32 SIMT GEMM for the few-shot adapter (models/adapter.py:82-105 runs in fp32):
+ * out[M,N] = act(A[M,K] . W[N,K]^T + bias) (+ res);  act: 0 none, 1 ReLU. */
+EC_API int ec_gemm_f32(const float *A, const float *W, const float *bias, const float *res, int M, int N, int K,
+                int act, float *out, void *stream);
+
+/* Adapter self-attention over the <=16 views of each sample with key-padding mask
+ * (nn.TransformerEncoderLayer, src_key_padding_mask=~valid; models/adapter.py:96-97).
+ * qkv fp32 [B*T, 3*D], out fp32 [B*T, D]. */
+EC_API int ec_adapter_attention(const float *qkv, const uint8_t *valid, int B, int T, int D, int heads, float *out,
+                         void *stream);
+
+/* out = r*a + (1-r)*b  (Adapter.residual_add, models/adapter.py:22-25); n elements. */
+EC_API int ec_blend(const float *a, const float *b, double r, float *out, int64_t n, void *stream);
+
+/* dst[s,:] = idx[s] >= 0 ? src[idx[s],:] : 0 -- places the features of the valid views into the zero-initialised
+ * [B*T, C] slot matrix (models/clip_cls.py:320-321).  idx device int32 [n_rows]. */
+EC_API int ec_gather_rows(const float *src, const int32_t *idx, float *dst, int n_rows, int C, void *stream);
+
+/* F.normalize(x, p=2, dim=-1) on fp32 rows [M,C] (text features, models/clip_cls.py:85, 295). */
+EC_API int ec_l2norm_rows(const float *x, float *out, int M, int C, void *stream);
+
+/* fp32 LayerNorm rows [M,d] -> fp32 (adapter pre-norm). */
+EC_API int ec_layernorm_f32(const float *x, const float *gamma, const float *beta, int M, int d, float *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,247 @@
+"""Generates the committed golden fixtures by running the UNMODIFIED reference in the authoring container.
+
+    python tests/golden/make_golden.py
+
+Needs /root/reference (read-only) plus PIL / torchvision; nothing here runs on the GPU box.  The reference has no
+tests or golden vectors of its own, so these files are the parity pins:
+  split_cases.json      datasets/vis.py:55-72 split_event_count on edge-case (E, N) pairs
+  gray_lut.npz          datasets/vis.py:27-39 uint8 value for (pos, neg, max) grids, both background_mask settings
+  event2img_small.npz   full stage-by-stage arrays for a small sensor (events, counts, frames, resized u8)
+  event2img_sha.json    sha256 of every stage for the three real sensor shapes x {uniform, clustered, hotpixel}
+  heads_golden.npz      outputs of the reference ZS / FS / FT classifiers (models/clip_cls.py, clip_cls_ft.py,
+                        adapter.py, lora.py) driven by the oracle CLIP image tower on seeded inputs
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+from oracle import ref_import, clip_oracle  # noqa: E402
+from eventclip_b200.synth import SENSORS, synth_events  # noqa: E402
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def clip_preprocess():
+    import torchvision.transforms as T
+    return T.Compose([T.Resize(224, interpolation=T.InterpolationMode.BICUBIC), T.CenterCrop(224),
+                      lambda im: im.convert("RGB"), T.ToTensor(),
+                      T.Normalize((0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711))])
+
+
+def ref_counts(vis, ev, shape, N):
+    """int64 [K,H,W,2] via the reference's own parse/split + np.bincount (vis.py:9-14)."""
+    x, y, t, p = vis.parse_events(ev)
+    i0, i1, _, _ = vis.split_event_count(t, N)
+    H, W = shape
+    out = []
+    for a, b in zip(i0, i1):
+        xx, yy, pp = x[a:b], y[a:b], p[a:b]
+        pos = np.bincount(xx[pp > 0] + yy[pp > 0] * W, minlength=H * W).reshape(H, W)
+        neg = np.bincount(xx[pp < 0] + yy[pp < 0] * W, minlength=H * W).reshape(H, W)
+        out.append(np.stack([pos, neg], -1))
+    return np.stack(out).astype(np.int64)
+
+
+def ref_pipeline(vis, prep, ev, shape, q):
+    from PIL import Image
+    frames = vis.events2frames(ev.copy(), "event_count", "event_histogram", shape=shape, **q)
+    tens = torch.stack([prep(Image.fromarray(f)) for f in frames]).numpy()
+    # resized+cropped uint8 = invert ToTensor/Normalize is lossy; recompute the uint8 stage with PIL directly
+    import torchvision.transforms as T
+    rc = T.Compose([T.Resize(224, interpolation=T.InterpolationMode.BICUBIC), T.CenterCrop(224)])
+    u8 = np.stack([np.asarray(rc(Image.fromarray(f)))[:, :, 0] for f in frames])
+    return frames, u8, tens
+
+
+def make_split_cases(vis):
+    cases = []
+    for E, N in [(1, 10), (9, 10), (10, 10), (11, 10), (14, 10), (15, 10), (16, 10), (19, 10), (20, 10), (21, 10),
+                 (25, 10), (26, 10), (30, 10), (99999, 20000), (100000, 20000), (110000, 20000), (110001, 20000),
+                 (4000, 30000), (45000, 30000), (45001, 30000), (1000000, 70000), (1015000, 70000), (1015001, 70000),
+                 (225000, 20000), (7, 7), (3, 2), (5, 3)]:
+        t = np.arange(E, dtype=np.float64)
+        i0, i1, _, _ = vis.split_event_count(t, N)
+        cases.append(dict(E=E, N=N, idx0=[int(v) for v in i0], idx1=[int(v) for v in i1]))
+    json.dump(cases, open(os.path.join(HERE, "split_cases.json"), "w"))
+    print("split_cases", len(cases))
+
+
+def make_gray_lut(vis):
+    red = np.full(3, 127, np.uint8)
+    out = {}
+    rng = np.random.default_rng(5)
+    for mask in (True, False):
+        grids, rand = [], []
+        for mx in range(1, 41):
+            pp, nn = np.meshgrid(np.arange(mx + 1), np.arange(mx + 1))
+            grids.append((mx, pp.ravel(), nn.ravel()))
+        for mx in (63, 64, 127, 254, 255, 256, 300, 508, 511, 512, 1000, 4095, 20000, 65535):
+            pos = rng.integers(0, mx + 1, 400)
+            neg = rng.integers(0, mx + 1, 400)
+            grids.append((mx, pos, neg))
+        rows = []
+        for mx, pos, neg in grids:
+            n = len(pos) + 1
+            P = np.concatenate([pos, [mx]]).astype(np.int64)
+            Ng = np.concatenate([neg, [0]]).astype(np.int64)
+            xs = np.concatenate([np.repeat(np.arange(n), P), np.repeat(np.arange(n), Ng)]).astype(np.int32)
+            ps = np.concatenate([np.ones(P.sum()), -np.ones(Ng.sum())]).astype(np.int32)
+            img = vis.make_event_histogram(xs, np.zeros_like(xs), ps, red, red, (1, n), thresh=0.,
+                                           background_mask=mask)
+            g = img[0, :-1, 0]
+            rows.append(np.stack([np.full(len(pos), mx), pos, neg, g], 1))
+        out["mask" if mask else "nomask"] = np.concatenate(rows).astype(np.int32)
+    np.savez_compressed(os.path.join(HERE, "gray_lut.npz"), **out)
+    print("gray_lut", {k: v.shape for k, v in out.items()})
+
+
+def make_event2img(vis):
+    prep = clip_preprocess()
+    # (1) small sensor, everything stored
+    small = {}
+    for name, shape, E, N, cnz, bg, kind in [("a", (40, 56), 3300, 1000, False, True, "clustered"),
+                                             ("b", (40, 56), 2600, 1000, True, False, "uniform"),
+                                             ("c", (36, 48), 700, 1000, True, True, "hotpixel")]:
+        ev = synth_events(shape, E, 900 + ord(name), kind)
+        q = dict(N=N, grayscale=True, count_non_zero=cnz, background_mask=bg)
+        frames, u8, tens = ref_pipeline(vis, prep, ev, shape, q)
+        small[f"{name}_events"] = ev
+        small[f"{name}_cfg"] = np.array([shape[0], shape[1], N, int(cnz), int(bg)])
+        small[f"{name}_counts"] = ref_counts(vis, ev, shape, N).astype(np.int32)
+        small[f"{name}_frames"] = frames[..., 0]
+        assert (frames[..., 0] == frames[..., 1]).all() and (frames[..., 0] == frames[..., 2]).all()
+        small[f"{name}_u8"] = u8
+        small[f"{name}_img_sha"] = np.frombuffer(bytes.fromhex(sha(tens)), np.uint8)
+    np.savez_compressed(os.path.join(HERE, "event2img_small.npz"), **small)
+    # (2) real sensors: checksums per stage
+    shas = []
+    for ds, cfg in SENSORS.items():
+        for kind in ("uniform", "clustered", "hotpixel"):
+            E = cfg["E"] if ds != "n_imagenet" else 300000
+            seed = 4242
+            ev = synth_events(cfg["shape"], E, seed, kind, cfg["max_t"])
+            q = dict(N=cfg["N"], grayscale=True, count_non_zero=cfg["count_non_zero"],
+                     background_mask=cfg["background_mask"])
+            frames, u8, tens = ref_pipeline(vis, prep, ev, cfg["shape"], q)
+            counts = ref_counts(vis, ev, cfg["shape"], cfg["N"])
+            shas.append(dict(dataset=ds, kind=kind, E=E, seed=seed, K=int(frames.shape[0]), events=sha(ev),
+                             counts=sha(counts.astype(np.int32)), frames=sha(frames[..., 0]), u8=sha(u8),
+                             img=sha(tens)))
+            print(ds, kind, frames.shape)
+    json.dump(shas, open(os.path.join(HERE, "event2img_sha.json"), "w"), indent=1)
+
+
+def make_heads():
+    """Reference classifiers (unmodified, via nerv/clip stubs) on top of the oracle CLIP tower."""
+    rm = ref_import.load_models()
+    out = {}
+    arch = "ViT-tiny/32"
+    B, T, n_cls = 6, 4, 11
+    g = torch.Generator().manual_seed(77)
+    imgs = torch.randn(B, T, 3, 224, 224, generator=g)
+    valid = torch.tensor([[1, 1, 1, 1], [1, 1, 0, 0], [1, 0, 0, 0], [1, 1, 1, 0], [1, 1, 1, 1], [1, 1, 0, 0]]).bool()
+    imgs = imgs * valid[:, :, None, None, None].float()     # padded views are zeros (event2img.py:89-91)
+    out["valid"] = valid.numpy()
+    C = clip_oracle.ARCHS[arch][4]
+    text = clip_oracle.synth_text_feats(n_cls, C, 5)
+    out["text"] = text.numpy()
+    names = [f"class_{i}" for i in range(n_cls)]
+    data = dict(img=imgs, valid_mask=valid)
+
+    def fresh_clip():
+        return clip_oracle.build_clip(arch, seed=3)
+
+    with torch.no_grad():
+        feats = fresh_clip().encode_image(imgs[valid])
+    out["img_feats"] = feats.numpy()
+    # zero-shot; agg_func='max' raises in the reference itself (clip_cls.py:117 subtracts a [B,T] mask from
+    # [B,T,n_cls] logits without unsqueezing), so only the two working aggregations have golden outputs
+    for agg in ("mean", "sum"):
+        m = rm.ZSCLIPClassifier(clip_dict=dict(clip_model=fresh_clip(), prompt="a {}", class_names=names, agg_func=agg))
+        m.text_feats = text.clone()
+        m.eval()
+        with torch.no_grad():
+            o = m(data)
+        for k in ("full_logits", "logits", "probs"):
+            out[f"zs_{agg}_{k}"] = o[k].numpy()
+    # few-shot: joint adapter (text-trans, residual 0.8) and text-identity
+    for tag, ad in (("fs_trans", dict(adapter_type="text-trans", in_dim=C, d_model=32, num_heads=2, ffn_dim=64,
+                                      norm_first=True, num_layers=2, residual=0.8)),
+                    ("fs_ident", dict(adapter_type="text-identity", residual=True))):
+        torch.manual_seed(11)
+        clipm = fresh_clip()
+        cd = dict(clip_model=clipm, prompt="a {}", class_names=names, agg_func="mean")
+        # FS builds its prompt parameter from cached text feats: pre-seed through a ZS pass-through
+        orig = rm.FSCLIPClassifier._build_prompts
+
+        def seeded(self, adapter_type, _t=text):
+            self.text_feats = torch.nn.Parameter(_t.clone().float(), requires_grad=True)
+            return adapter_type[5:]
+
+        rm.FSCLIPClassifier._build_prompts = seeded
+        try:
+            m = rm.FSCLIPClassifier(adapter_dict=ad, clip_dict=cd, loss_dict=dict(use_logits_loss=True, use_probs_loss=False))
+        finally:
+            rm.FSCLIPClassifier._build_prompts = orig
+        with torch.no_grad():      # make the learned parts non-trivial
+            m.text_feats.add_(0.05 * torch.randn(m.text_feats.shape, generator=g))
+        m.eval()
+        with torch.no_grad():
+            o = m(data)
+        for k in ("full_logits", "logits", "probs"):
+            out[f"{tag}_{k}"] = o[k].numpy()
+        for k, v in m.state_dict().items():
+            out[f"{tag}_sd_{k}"] = v.numpy()
+    # fine-tune with LoRA qkvo-4, non-zero up factors
+    torch.manual_seed(12)
+    clipm = fresh_clip()
+    cd = dict(clip_model=clipm, prompt="a {}", class_names=names, agg_func="mean", lora="qkvo-4", only_conv1=False,
+              only_bias=False, only_ln=False)
+    origf = rm.FTCLIPClassifier._build_prompts
+
+    def seededf(self, adapter_type, _t=text):
+        self.text_feats = torch.nn.Parameter(_t.clone().float(), requires_grad=True)
+        return adapter_type[5:]
+
+    rm.FTCLIPClassifier._build_prompts = seededf
+    try:
+        m = rm.FTCLIPClassifier(adapter_dict=dict(adapter_type="text-identity", residual=True), clip_dict=cd,
+                                loss_dict=dict(use_logits_loss=True, use_probs_loss=False))
+    finally:
+        rm.FTCLIPClassifier._build_prompts = origf
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "lora_up" in n:
+                p.copy_(0.05 * torch.randn(p.shape, generator=g))
+    m.eval()
+    with torch.no_grad():
+        o = m(data)
+    for k in ("full_logits", "logits", "probs"):
+        out[f"ft_lora_{k}"] = o[k].numpy()
+    sd = m.state_dict()
+    out["ft_lora_keys"] = np.array(sorted(sd.keys()))
+    for k, v in sd.items():
+        if "lora" in k or k == "text_feats":
+            out[f"ft_lora_sd_{k}"] = v.numpy()
+    np.savez_compressed(os.path.join(HERE, "heads_golden.npz"), **out)
+    print("heads_golden", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    assert ref_import.available(), "/root/reference is required to (re)generate the golden fixtures"
+    vis = ref_import.load_vis()
+    make_split_cases(vis)
+    make_gray_lut(vis)
+    make_event2img(vis)
+    make_heads()
+    print("sizes:", {f: os.path.getsize(os.path.join(HERE, f)) for f in sorted(os.listdir(HERE)) if not f.endswith(".py")})
