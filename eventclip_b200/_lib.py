@@ -73,7 +73,14 @@ def load():
     return _lib
 
 
+# number of kernel launches enqueued through the ABI (every device entry point launches exactly one kernel)
+LAUNCHES = 0
+
+
 def check(rc, what):
+    global LAUNCHES
+    if what not in ("ec_plan_frames", "ec_event2img_geometry", "ec_device_check"):
+        LAUNCHES += 1
     if rc != EC_OK:
         msg = load().ec_last_error().decode("utf-8", "replace")
         raise ECError(f"{what} failed (code {rc}): {msg}")

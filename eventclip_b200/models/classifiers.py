@@ -132,7 +132,7 @@ class _CLIPClassifierBase(nn.Module):
             full = ops.gather_rows(feats, row_of_slot.to(dev, non_blocking=True), B * T)
         valid_dev = valid.to(dev)
         full = self._adapt(full.view(B, T, -1), valid_dev).reshape(B * T, -1).contiguous()
-        text = self.get_text_feats().to(torch.float32).contiguous()
+        text = self.get_text_feats().to(device=dev, dtype=torch.float32).contiguous()
         full_logits, logits, probs, top = ops.head(full, valid_dev.to(torch.uint8).contiguous(), text, B, T,
                                                    self.logit_scale, self.normalize_img_feats, self.agg_func)
         return {

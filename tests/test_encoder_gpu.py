@@ -1,0 +1,138 @@
+"""GPU parity of the CLIP ViT image encoder pieces (through the C ABI) against plain fp32 PyTorch on the CPU.
+
+Tolerances (bf16 operands, fp32 accumulation, fp32 residual stream):
+  GEMM / attention vs an fp32 reference fed the SAME bf16-rounded operands: rel-L2 <= 2e-3 (accumulation order only)
+  whole encoder vs the fp32 oracle: rel-L2 <= 2e-2 (SURVEY.md section 8(c) pin 7)
+"""
+import numpy as np
+import pytest
+import torch
+
+from eventclip_b200 import clip, ops
+from oracle import clip_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def bf(t):
+    return t.to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 256, 128), (256, 512, 768), (1000, 768, 3072), (197 * 3, 2304, 768),
+                                   (50, 64, 128), (130, 384, 592), (4096, 1024, 1024), (77, 512, 768)])
+def test_gemm_plain(cuda_dev, M, N, K):
+    g = torch.Generator().manual_seed(M * 7 + N)
+    A = bf(torch.randn(M, K, generator=g))
+    W = bf(torch.randn(N, K, generator=g) * K ** -0.5)
+    bias = torch.randn(N, generator=g)
+    ref = A.float() @ W.float().t() + bias
+    out = ops.gemm_bf16(A.to(cuda_dev), W.to(cuda_dev), bias.to(cuda_dev), "f32")
+    torch.cuda.synchronize()
+    assert rel(out, ref) < 2e-3, rel(out, ref)
+    out16 = ops.gemm_bf16(A.to(cuda_dev), W.to(cuda_dev), bias.to(cuda_dev), "bf16")
+    assert rel(out16.float(), ref) < 6e-3
+
+
+def test_gemm_epilogues(cuda_dev):
+    g = torch.Generator().manual_seed(3)
+    M, N, K = 394, 768, 768
+    A, W = bf(torch.randn(M, K, generator=g)), bf(torch.randn(N, K, generator=g) * K ** -0.5)
+    bias, res = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    acc = A.float() @ W.float().t() + bias
+    Ad, Wd, bd = A.to(cuda_dev), W.to(cuda_dev), bias.to(cuda_dev)
+    q = ops.gemm_bf16(Ad, Wd, bd, "bf16_qgelu")
+    assert rel(q.float(), acc * torch.sigmoid(1.702 * acc)) < 6e-3
+    x = res.to(cuda_dev).clone()
+    ops.gemm_bf16(Ad, Wd, bd, "f32_resadd", out=x, res=x)               # in place on the residual stream
+    assert rel(x, acc + res) < 2e-3
+    nobias = ops.gemm_bf16(Ad, Wd, None, "f32")
+    assert rel(nobias, acc - bias) < 2e-3
+    # patch epilogue: rows land at token 1 + m % G2 of image m // G2 and get the positional embedding
+    G2, n_img, d = 49, 6, 256
+    P = bf(torch.randn(n_img * G2, 128, generator=g))
+    Wp = bf(torch.randn(d, 128, generator=g) * 0.1)
+    pos = torch.randn(G2 + 1, d, generator=g)
+    tok = torch.full((n_img * (G2 + 1), d), 7.0, device=cuda_dev)
+    ops.gemm_bf16(P.to(cuda_dev), Wp.to(cuda_dev), None, "patch", out=tok, res=pos.to(cuda_dev), row_map=G2)
+    want = (P.float() @ Wp.float().t()).view(n_img, G2, d) + pos[1:]
+    got = tok.view(n_img, G2 + 1, d).cpu()
+    assert rel(got[:, 1:], want) < 2e-3 and (got[:, 0] == 7.0).all()
+
+
+def test_layernorm_and_helpers(cuda_dev):
+    g = torch.Generator().manual_seed(4)
+    for M, d in ((37, 768), (5, 1024), (9, 128), (3, 2048)):
+        x = torch.randn(M, d, generator=g) * 3 + 1
+        w, b = torch.randn(d, generator=g), torch.randn(d, generator=g)
+        ref = torch.nn.functional.layer_norm(x, (d,), w, b, 1e-5)
+        o32 = torch.empty(M, d, device=cuda_dev)
+        o16 = torch.empty(M, d, dtype=torch.bfloat16, device=cuda_dev)
+        ops.layernorm(x.to(cuda_dev), w.to(cuda_dev), b.to(cuda_dev), M, d, out_bf16=o16, out_f32=o32)
+        assert (o32.cpu() - ref).abs().max() < 2e-5 * ref.abs().max().clamp_min(1)
+        assert torch.equal(o16, o32.to(torch.bfloat16))
+        assert (ops.layernorm_f32(x.to(cuda_dev), w.to(cuda_dev), b.to(cuda_dev)).cpu() - ref).abs().max() < 1e-4
+    # strided rows (ln_post reads the class token of every image)
+    x = torch.randn(4, 5, 128, generator=g)
+    w, b = torch.ones(128), torch.zeros(128)
+    o = torch.empty(4, 128, device=cuda_dev)
+    ops.layernorm(x.to(cuda_dev), w.to(cuda_dev), b.to(cuda_dev), 4, 128, row_stride=5 * 128, out_f32=o)
+    assert (o.cpu() - torch.nn.functional.layer_norm(x[:, 0], (128,))).abs().max() < 1e-5
+    s = torch.randn(1001, generator=g)
+    assert torch.equal(ops.f32_to_bf16(s.to(cuda_dev)).cpu(), s.to(torch.bfloat16))
+    # LoRA merge: bf16(W + up @ down), fp32 math (models/lora.py:138-149)
+    W, up, down = torch.randn(96, 64, generator=g), torch.randn(96, 4, generator=g), torch.randn(4, 64, generator=g)
+    m = ops.lora_merge(W.to(cuda_dev), up.to(cuda_dev), down.to(cuda_dev)).cpu()
+    assert (m.float() - (W + up @ down)).abs().max() <= 2 ** -8 * (W + up @ down).abs().max()
+    assert torch.equal(ops.lora_merge(W.to(cuda_dev), None, None).cpu(), W.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("L,heads,n_img", [(50, 12, 3), (197, 12, 2), (257, 16, 2), (5, 2, 4), (64, 2, 1), (65, 2, 1)])
+def test_attention(cuda_dev, L, heads, n_img):
+    g = torch.Generator().manual_seed(L)
+    d = heads * 64
+    qkv = bf(torch.randn(n_img * L, 3 * d, generator=g))
+    out = torch.empty(n_img * L, d, dtype=torch.bfloat16, device=cuda_dev)
+    ops.attention(qkv.to(cuda_dev), out, n_img, L, heads)
+    q, k, v = [t.view(n_img, L, heads, 64).transpose(1, 2) for t in qkv.float().chunk(3, -1)]
+    ref = (torch.softmax(q @ k.transpose(-1, -2) / 8.0, -1) @ v).transpose(1, 2).reshape(n_img * L, d)
+    assert rel(out.float(), ref) < 8e-3, rel(out.float(), ref)
+
+
+@pytest.mark.parametrize("arch,n", [("ViT-tiny/32", 5), ("ViT-tiny/16", 3), ("ViT-B/32", 4)])
+def test_encoder_vs_oracle(cuda_dev, arch, n):
+    oracle = clip_oracle.build_clip(arch, seed=21)
+    model = clip.CLIP(arch)
+    model.load_state_dict(oracle.state_dict())
+    model = model.to(cuda_dev).eval()
+    g = torch.Generator().manual_seed(8)
+    imgs = torch.randn(n, 3, 224, 224, generator=g)
+    with torch.no_grad():
+        ref = oracle.encode_image(imgs)
+        got = model.encode_image(imgs.to(cuda_dev))
+        got_bf = model.encode_image(imgs.to(cuda_dev).to(torch.bfloat16))
+    assert got.shape == ref.shape and got.dtype == torch.float32
+    assert rel(got, ref) < 2e-2, rel(got, ref)
+    assert rel(got_bf, ref) < 2e-2
+    # weight updates are picked up (version counters) -- optimizer steps / load_state_dict must not see stale packs
+    with torch.no_grad():
+        model.visual.proj.mul_(2.0)
+        got2 = model.encode_image(imgs.to(cuda_dev))
+    assert rel(got2, 2 * ref) < 2e-2
+
+
+@pytest.mark.parametrize("arch", ["ViT-B/16", "ViT-L/14"])
+def test_encoder_large_archs_vs_oracle(cuda_dev, arch):
+    oracle = clip_oracle.build_clip(arch, seed=22)
+    model = clip.CLIP(arch)
+    model.load_state_dict(oracle.state_dict())
+    model = model.to(cuda_dev).eval()
+    imgs = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        ref = oracle.encode_image(imgs)
+        got = model.encode_image(imgs.to(cuda_dev))
+    assert rel(got, ref) < 2e-2, rel(got, ref)

@@ -1,0 +1,192 @@
+"""GPU parity: the fused event2img kernel (through the C ABI) against the oracle and the golden fixtures.
+Integer stages are bit-exact; the float32 output is bit-exact (LUT of IEEE float32 values); bf16 = RNE of it."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from eventclip_b200 import ops, _lib
+from eventclip_b200.datasets import Event2Image, events2frames
+from eventclip_b200.synth import SENSORS, synth_batch, synth_events
+from oracle import event2img as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _qargs(cfg, max_imgs=10):
+    return dict(max_imgs=max_imgs, N=cfg["N"], split_method="event_count", convert_method="event_histogram",
+                grayscale=True, count_non_zero=cfg["count_non_zero"], background_mask=cfg["background_mask"])
+
+
+def _run_frames(ev, shape, N, cnz, bg, dev, out="f32"):
+    E = len(ev)
+    T = int(E // N) + 2
+    frames, valid, chunks, K = ops.plan_frames([0, E], N, T, compact=True)
+    img, status, dbg = ops.event2img(torch.from_numpy(ev).to(dev), frames.to(dev), shape, K, cnz, bg, out=out, debug=True)
+    torch.cuda.synchronize()
+    assert int(status.item()) == 0
+    return img, dbg, K
+
+
+def test_small_sensor_all_stages_vs_golden(cuda_dev, golden_dir):
+    z = np.load(os.path.join(golden_dir, "event2img_small.npz"))
+    for name in "abc":
+        H, W, N, cnz, bg = [int(v) for v in z[f"{name}_cfg"]]
+        img, dbg, K = _run_frames(z[f"{name}_events"], (H, W), N, bool(cnz), bool(bg), cuda_dev)
+        assert K == z[f"{name}_counts"].shape[0]
+        assert (dbg["counts"].cpu().numpy() == z[f"{name}_counts"]).all(), name
+        assert (dbg["gray"].cpu().numpy() == z[f"{name}_frames"]).all(), name
+        assert (dbg["u8"].cpu().numpy() == z[f"{name}_u8"]).all(), name
+        assert sha(img.cpu().numpy()) == bytes(z[f"{name}_img_sha"]).hex(), name
+
+
+@pytest.mark.parametrize("idx", range(9))
+def test_real_sensors_vs_golden_checksums(cuda_dev, golden_dir, idx):
+    c = json.load(open(os.path.join(golden_dir, "event2img_sha.json")))[idx]
+    cfg = SENSORS[c["dataset"]]
+    ev = synth_events(cfg["shape"], c["E"], c["seed"], c["kind"], cfg["max_t"])
+    assert sha(ev) == c["events"]
+    img, dbg, K = _run_frames(ev, cfg["shape"], cfg["N"], cfg["count_non_zero"], cfg["background_mask"], cuda_dev)
+    assert K == c["K"]
+    assert sha(dbg["counts"].cpu().numpy()) == c["counts"]
+    assert sha(dbg["gray"].cpu().numpy()) == c["frames"]
+    assert sha(dbg["u8"].cpu().numpy()) == c["u8"]
+    assert sha(img.cpu().numpy()) == c["img"]
+
+
+@pytest.mark.parametrize("ds", ["n_caltech101", "n_cars", "n_imagenet"])
+@pytest.mark.parametrize("kind", ["uniform", "clustered", "hotpixel"])
+def test_batch_vs_oracle_every_stage(cuda_dev, ds, kind):
+    """Packed batch with ragged lengths: padding, overlapping tail chunks, host-drawn view selection."""
+    cfg = SENSORS[ds]
+    N = cfg["N"]
+    lens = {"n_caltech101": [100000, 50001, 19999, 20000, 30000, 30001],
+            "n_cars": [4000, 12500, 300, 45001],
+            "n_imagenet": [250000, 70000, 69999, 105001]}[ds]
+    evs = [synth_events(cfg["shape"], E, 100 + i, kind, cfg["max_t"]) for i, E in enumerate(lens)]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    e2i = Event2Image(_qargs(cfg), cfg["shape"], cfg["max_n"])
+    T = e2i.max_imgs
+    torch.manual_seed(5)
+    sel = e2i.draw_selection(off)
+    r = e2i(torch.from_numpy(np.concatenate(evs)).to(cuda_dev), off, sel=sel, out="f32", debug=True, check=True)
+    img = r["img"].cpu().numpy()
+    valid = r["valid_mask"].numpy()
+    fi = 0
+    rec = np.frombuffer(r["frames"].numpy().tobytes(), dtype=[("s", "<i8"), ("n", "<i4"), ("o", "<i4")])
+    for b, ev in enumerate(evs):
+        oimg, ovalid, K = orc.event2img_sample(ev, cfg["shape"], N, T, cfg["count_non_zero"], cfg["background_mask"],
+                                               sel=sel[b] if K_gt(ev, N, T) else None, only_selected=True)
+        assert (valid[b] == ovalid).all() and int(r["chunks"][b]) == K
+        assert (img[b] == oimg).all(), (ds, kind, b)
+        i0, i1 = orc.split_event_count(len(ev), N)
+        for t in range(T):
+            if rec[fi]["n"] > 0:
+                k = int(sel[b][t]) if K > T else t
+                counts = orc.histogram(ev[i0[k]:i1[k]], cfg["shape"])
+                assert (r["debug"]["counts"][fi].cpu().numpy() == counts).all()
+                gray, _, _ = orc.frame_from_counts(counts, cfg["count_non_zero"], cfg["background_mask"])
+                assert (r["debug"]["gray"][fi].cpu().numpy() == gray).all()
+                assert (r["debug"]["u8"][fi].cpu().numpy() == orc.resize_crop_224(gray)).all()
+            fi += 1
+
+
+def K_gt(ev, N, T):
+    return len(orc.split_event_count(len(ev), N)[0]) > T
+
+
+def test_output_formats_agree(cuda_dev):
+    """bf16 NCHW = round-to-nearest-even of the float32 tensor; patch layout = its im2col; compact = gather."""
+    cfg = SENSORS["n_caltech101"]
+    ev, off = synth_batch("n_caltech101", 3, 40, E=50001)
+    evd = torch.from_numpy(ev).to(cuda_dev)
+    e2i = Event2Image(_qargs(cfg), cfg["shape"], cfg["max_n"])
+    f32 = e2i(evd, off, out="f32")
+    b16 = e2i(evd, off, out="bf16")
+    assert torch.equal(b16["img"], f32["img"].to(torch.bfloat16))
+    valid = f32["valid_mask"]
+    assert (f32["img"][~valid.to(cuda_dev)] == 0).all()
+    for P, ldk in ((32, 3072), (16, 768), (14, 592)):
+        pt = e2i(evd, off, out="patch", compact=True, patch=P, ldk=ldk)
+        G = 224 // P
+        ref = f32["img"][valid.to(cuda_dev)].to(torch.bfloat16)                 # [Nv,3,224,224]
+        ref = ref.view(-1, 3, G, P, G, P).permute(0, 2, 4, 1, 3, 5).reshape(-1, 3 * P * P)
+        assert pt["n_valid"] == int(valid.sum())
+        assert torch.equal(pt["img"][:, :3 * P * P], ref)
+        assert (pt["img"][:, 3 * P * P:] == 0).all()
+        assert torch.equal(ops.im2col(f32["img"][valid.to(cuda_dev)].contiguous(), P, ldk), pt["img"])
+
+
+def test_events2frames_drop_in(cuda_dev):
+    """Same call as the reference's datasets.vis.events2frames; uint8 [K,H,W,3] identical to the oracle."""
+    for ds in ("n_caltech101", "n_cars"):
+        cfg = SENSORS[ds]
+        ev = synth_events(cfg["shape"], 45001, 9, "clustered")
+        fr = events2frames(ev, split_method="event_count", convert_method="event_histogram", shape=cfg["shape"],
+                           N=cfg["N"], grayscale=True, count_non_zero=cfg["count_non_zero"],
+                           background_mask=cfg["background_mask"])
+        ref = orc.events2frames(ev, cfg["shape"], cfg["N"], cfg["count_non_zero"], cfg["background_mask"])
+        assert fr.dtype == np.uint8 and fr.shape == ref.shape and (fr == ref).all()
+    with pytest.raises(NotImplementedError):
+        events2frames(ev, "event_count", "voxel", shape=(100, 120), N=100)
+    with pytest.raises(AssertionError):
+        events2frames(ev, "time", "event_histogram", shape=(100, 120), N=100)
+
+
+def test_error_flags(cuda_dev):
+    ev = synth_events((100, 120), 500, 1)
+    ev[7, 0], ev[7, 1] = 119, 100          # flat index == H*W
+    with pytest.raises(ValueError):
+        events2frames(ev, "event_count", "event_histogram", shape=(100, 120), N=30000, count_non_zero=True,
+                      background_mask=False)
+    ev[7, 0], ev[7, 1] = -3, 0
+    with pytest.raises(ValueError):
+        events2frames(ev, "event_count", "event_histogram", shape=(100, 120), N=30000)
+    ev[7, 3] = 0                           # p == 0 events are never histogrammed, so their coordinates are not checked
+    events2frames(ev, "event_count", "event_histogram", shape=(100, 120), N=30000)
+    # x >= W aliases into the next row exactly like np.bincount(x + y*W) (vis.py:12)
+    ev = synth_events((100, 120), 500, 2)
+    ev[3, 0], ev[3, 1] = 125, 4
+    fr = events2frames(ev, "event_count", "event_histogram", shape=(100, 120), N=30000)
+    assert (fr == orc.events2frames(ev, (100, 120), 30000)).all()
+    # 16-bit packed bins: 70000 events on one pixel of one polarity must be reported, not silently wrapped
+    ev = np.zeros((70000, 4), np.float32)
+    ev[:, 0], ev[:, 1], ev[:, 3] = 5, 6, 1
+    ev[:3000, 0] = np.arange(3000) % 640
+    ev[:, 2] = np.linspace(0, 1, 70000)
+    frames, _, _, K = ops.plan_frames([0, 70000], 70000, 2, compact=True)
+    _, status, _ = ops.event2img(torch.from_numpy(ev).to(cuda_dev), frames.to(cuda_dev), (480, 640), K)
+    assert int(status.item()) & _lib.EC_STATUS_COUNT_OVERFLOW
+    with pytest.raises(_lib.ECError):
+        ops.raise_on_status(status)
+
+
+def test_full_size_properties(cuda_dev):
+    """BASELINE-size batch: size-independent checks (event conservation, determinism, padding, permutation
+    invariance of the histogram within a chunk)."""
+    cfg = SENSORS["n_caltech101"]
+    B = 32
+    ev, off = synth_batch("n_caltech101", B, 1000)
+    e2i = Event2Image(_qargs(cfg), cfg["shape"], cfg["max_n"])
+    evd = torch.from_numpy(ev).to(cuda_dev)
+    a = e2i(evd, off, debug=True, check=True)
+    b = e2i(evd, off, debug=True, check=True)
+    assert torch.equal(a["img"], b["img"])                                   # shared-memory atomics are order-free
+    counts = a["debug"]["counts"]
+    n = torch.tensor([f for f in np.frombuffer(a["frames"].numpy().tobytes(),
+                                               dtype=[("s", "<i8"), ("n", "<i4"), ("o", "<i4")])["n"]])
+    assert torch.equal(counts.sum((1, 2, 3)).cpu(), n.to(torch.int64))        # every event lands in exactly one bin
+    assert a["valid_mask"].sum().item() == B * 5 and (a["img"][:, 5:] == 0).all()
+    # shuffling events inside one chunk must not change its frame
+    ev2 = ev.copy()
+    rng = np.random.default_rng(0)
+    ev2[:20000] = ev2[rng.permutation(20000)]
+    c = e2i(torch.from_numpy(ev2).to(cuda_dev), off)
+    assert torch.equal(c["img"], a["img"])
