@@ -275,6 +275,12 @@ def b200_arm(args):
     ms_total = float(ms.item())
     value = world * B * K / (ms_total / 1e3)
 
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "ms_per_step": ms_total / K, "gpu_launches": launches, "quick": True}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     # ---- end-to-end: host buffers, H2D + D2H inside ----
     for i in range(2):
         step(i, resident=False).cpu()
@@ -363,8 +369,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--quick", action="store_true", help="timed region only (for ncu launch lists)")
+    ap.add_argument("--e2i-only", action="store_true", help="only the event2img Gevents/s section")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.e2i_only:
+        torch.cuda.set_device(0)
+        print(json.dumps(event2img_metric(torch.device("cuda", 0), peaks())))
+    elif args.impl == "reference":
         reference_arm(args)
     else:
         b200_arm(args)

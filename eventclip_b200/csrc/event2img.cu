@@ -51,9 +51,12 @@ struct E2IParams {
 };
 
 struct Part {            // per-CTA partial statistics exchanged over DSMEM
-    unsigned long long s1, s2, nnz, nacc;
-    unsigned mx;
-    unsigned bad;
+    unsigned long long s2;   // sum of squared counts
+    unsigned nnz;            // non-empty bins
+    unsigned nacc;           // events accumulated (= sum of counts)
+    unsigned mall;           // largest count (before hot-pixel removal)
+    unsigned mx;             // largest surviving count (second exchange, only when needed)
+    unsigned flags;          // EC_STATUS_* bits seen by this CTA
 };
 
 __device__ __forceinline__ float4 ld_stream(const float4 *p)
@@ -69,6 +72,18 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ unsigned warp_sum_u32(unsigned v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ unsigned warp_max_u32(unsigned v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
 
@@ -116,28 +131,10 @@ __device__ __forceinline__ unsigned clip8(int v)
     return (unsigned)min(max(v, 0), 255);
 }
 
-__device__ __forceinline__ void store_pair(const E2IParams &p, int slot, int yo, int x, unsigned v0, unsigned v1,
-                                           const float *nl)
-{
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const float f0 = nl[c * 256 + v0], f1 = nl[c * 256 + v1];
-        if (p.out_fmt == EC_OUT_F32_NCHW) {
-            float *o = (float *)p.out + (((size_t)slot * 3 + c) * OUT + yo) * OUT + x;
-            *reinterpret_cast<float2 *>(o) = make_float2(f0, f1);
-        } else if (p.out_fmt == EC_OUT_BF16_NCHW) {
-            __nv_bfloat16 *o = (__nv_bfloat16 *)p.out + (((size_t)slot * 3 + c) * OUT + yo) * OUT + x;
-            *reinterpret_cast<__nv_bfloat162 *>(o) = __floats2bfloat162_rn(f0, f1);
-        } else {
-            const int P = p.patch;
-            const size_t row = (size_t)slot * p.G * p.G + (size_t)(yo / P) * p.G + x / P;
-            const int col = c * P * P + (yo % P) * P + (x % P);
-            __nv_bfloat16 *o = (__nv_bfloat16 *)p.out + row * p.ldk + col;
-            *reinterpret_cast<__nv_bfloat162 *>(o) = __floats2bfloat162_rn(f0, f1);
-        }
-    }
-}
+constexpr int MAXG = 14;   // 4-pixel groups per thread in P4: band pixels <= 56320 (220 KB of bins) / 4 / 1024
 
+// KHMAX: compile-time bound on the horizontal taps (5 when upsampling, 11 for 640 -> 298); 0 = dynamic loop.
+template <int KHMAX>
 __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
 {
     cg::cluster_group cluster = cg::this_cluster();
@@ -158,21 +155,33 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
     const bool cnz = (p.flags & EC_FLAG_COUNT_NON_ZERO) != 0;
     const int yo_begin = (OUT * rank) / CS, yo_end = (OUT * (rank + 1)) / CS;
 
+    // One buffer, three lives: packed bins (RB*W words) -> gray bytes (first RB*W bytes) + resampled rows after them.
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw);            // RB*W packed bins, later gray bytes
-    uint8_t *hrow = smem_raw + (size_t)RB * W * 4;                       // RB*224 horizontally resampled rows
+    uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw);
+    uint8_t *gray = smem_raw;
+    uint8_t *hrow = smem_raw + (((size_t)RB * W + 15) & ~(size_t)15);   // RB*224 bytes, inside the bins' footprint
     __shared__ Part part;
-    __shared__ unsigned long long red[32][4];
-    __shared__ unsigned redm[32];
-    __shared__ unsigned s_keep, s_mx;
+    __shared__ unsigned long long red64[32];
+    __shared__ unsigned red32[32][4];
+    __shared__ unsigned s_keep, s_mx, s_mall;
     __shared__ uint8_t glut[GLUT_N * GLUT_N];
     __shared__ float nlut[768];
+    __shared__ __nv_bfloat16 nlut16[768];
+    __shared__ short ypq[OUT], ypr[OUT], xpq[OUT / 2], xpr[OUT / 2];   // patch coordinates of output rows / column pairs
 
-    for (int i = tid; i < 768; i += NT) nlut[i] = p.nlut[i];
+    for (int i = tid; i < 768; i += NT) {
+        const float f = p.nlut[i];
+        nlut[i] = f;
+        nlut16[i] = __float2bfloat16_rn(f);
+    }
+    if (p.out_fmt == EC_OUT_BF16_PATCH) {
+        const int P = p.patch;
+        for (int i = tid; i < OUT; i += NT) { ypq[i] = (short)(i / P); ypr[i] = (short)(i % P); }
+        for (int i = tid; i < OUT / 2; i += NT) { xpq[i] = (short)((2 * i) / P); xpr[i] = (short)((2 * i) % P); }
+    }
 
     // ---- padding frame: the reference pads missing views with zeros (event2img.py:89-91) ----
     if (fr.ev_count <= 0) {
-        __syncthreads();
         const int slot = fr.out_slot;
         if (p.out_fmt == EC_OUT_BF16_PATCH) {
             const int P = p.patch, G = p.G;
@@ -195,13 +204,18 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
         return;
     }
 
-    // ---- P0: clear the band's bins ----
-    for (int i = tid; i < nband; i += NT) hist[i] = 0u;
+    // ---- P0: clear the band's bins (16-byte stores; the buffer is padded to 16 bytes) ----
+    {
+        uint4 *h4 = reinterpret_cast<uint4 *>(hist);
+        const int n4 = (nband + 3) >> 2;
+        for (int i = tid; i < n4; i += NT) h4[i] = make_uint4(0, 0, 0, 0);
+    }
     __syncthreads();
 
-    // ---- P1: scan events, accumulate the ones that fall into this band ----
-    unsigned long long nacc = 0;
-    unsigned bad = 0;
+    // ---- P1: scan events; returning atomics give the statistics for free:
+    //      adding 1 to a bin holding c raises sum(c^2) by 2c+1 and the non-empty count by [c == 0] ----
+    unsigned long long s2 = 0;
+    unsigned nnz = 0, nacc = 0, mall = 0, flags = 0;
     {
         const float4 *ev = p.events + fr.ev_start;
         const int n = fr.ev_count;
@@ -221,11 +235,16 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
                     if (pol != 0) {
                         const long long idx = (long long)x + (long long)y * W;   // flat index as np.bincount sees it
                         if (idx < 0 || idx >= HW) {
-                            bad = 1;
+                            flags |= EC_STATUS_BAD_COORD;
                         } else {
                             const long long l = idx - band_lo;
                             if (l >= 0 && l < nband) {
-                                atomicAdd(&hist[(int)l], pol > 0 ? 1u : 65536u);
+                                const uint32_t old = atomicAdd(&hist[(int)l], pol > 0 ? 1u : 65536u);
+                                const uint32_t c = pol > 0 ? (old & 0xffffu) : (old >> 16);
+                                if (c == 0xffffu) flags |= EC_STATUS_COUNT_OVERFLOW;   // the 16-bit field wraps
+                                s2 += 2ull * c + 1ull;
+                                nnz += (c == 0);
+                                mall = max(mall, c + 1);
                                 ++nacc;
                             }
                         }
@@ -234,115 +253,141 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
             }
         }
     }
-    __syncthreads();
-
-    // ---- P2: exact statistics of the band ----
-    {
-        unsigned long long s1 = 0, s2 = 0, nnz = 0;
-        int32_t *dc = p.dbg_counts ? p.dbg_counts + ((size_t)fid * HW + band_lo) * 2 : nullptr;
-        for (int i = tid; i < nband; i += NT) {
-            const uint32_t w = hist[i];
-            const uint32_t a = w & 0xffffu, b = w >> 16;
-            s1 += a + b;
-            s2 += (unsigned long long)(a * a) + (unsigned long long)(b * b);
-            nnz += (a > 0) + (b > 0);
-            if (dc) { dc[2 * i] = (int32_t)a; dc[2 * i + 1] = (int32_t)b; }
+    // block reduction of the partials
+    s2 = warp_sum_u64(s2); nnz = warp_sum_u32(nnz); nacc = warp_sum_u32(nacc); mall = warp_max_u32(mall);
+    flags |= __shfl_xor_sync(0xffffffffu, flags, 16); flags |= __shfl_xor_sync(0xffffffffu, flags, 8);
+    flags |= __shfl_xor_sync(0xffffffffu, flags, 4); flags |= __shfl_xor_sync(0xffffffffu, flags, 2);
+    flags |= __shfl_xor_sync(0xffffffffu, flags, 1);
+    if (lane == 0) { red64[wid] = s2; red32[wid][0] = nnz; red32[wid][1] = nacc; red32[wid][2] = mall; red32[wid][3] = flags; }
+    __syncthreads();   // also: all atomics of this CTA have landed
+    if (tid == 0) {
+        Part t = {0, 0, 0, 0, 0, 0};
+        for (int w = 0; w < nwarps; ++w) {
+            t.s2 += red64[w]; t.nnz += red32[w][0]; t.nacc += red32[w][1]; t.mall = max(t.mall, red32[w][2]);
+            t.flags |= red32[w][3];
         }
-        s1 = warp_sum_u64(s1); s2 = warp_sum_u64(s2); nnz = warp_sum_u64(nnz); nacc = warp_sum_u64(nacc);
-        bad = __any_sync(0xffffffffu, bad) ? 1u : 0u;
-        if (lane == 0) { red[wid][0] = s1; red[wid][1] = s2; red[wid][2] = nnz; red[wid][3] = nacc; redm[wid] = bad; }
-        __syncthreads();
-        if (tid == 0) {
-            Part t = {0, 0, 0, 0, 0, 0};
-            for (int w = 0; w < nwarps; ++w) {
-                t.s1 += red[w][0]; t.s2 += red[w][1]; t.nnz += red[w][2]; t.nacc += red[w][3]; t.bad |= redm[w];
-            }
-            part = t;
-        }
+        part = t;
     }
     cluster.sync();
     if (tid == 0) {
-        unsigned long long S1 = 0, S2 = 0, NNZ = 0, NACC = 0;
-        unsigned anybad = 0;
+        unsigned long long S1 = 0, S2 = 0, NNZ = 0;
+        unsigned M = 0, fl = 0;
         for (int r = 0; r < CS; ++r) {
             const Part *q = cluster.map_shared_rank(&part, r);
-            S1 += q->s1; S2 += q->s2; NNZ += q->nnz; NACC += q->nacc; anybad |= q->bad;
+            S1 += q->nacc; S2 += q->s2; NNZ += q->nnz; M = max(M, q->mall); fl |= q->flags;
         }
         const unsigned long long n = cnz ? NNZ : (unsigned long long)HW * 2ull;
         s_keep = compute_keep(n, S1, S2, 10);
-        if (rank == 0) {
-            unsigned st = 0;
-            if (anybad) st |= EC_STATUS_BAD_COORD;
-            if (S1 != NACC) st |= EC_STATUS_COUNT_OVERFLOW;   // a 16-bit field wrapped
-            if (st) atomicOr(p.status, (int)st);
-        }
+        s_mall = M;
+        if (rank == 0 && fl) atomicOr(p.status, (int)fl);
     }
     __syncthreads();
     const unsigned keep = s_keep;
+    unsigned mx = s_mall;
 
-    // ---- P3: max of the surviving bins ----
-    {
-        unsigned mx = 0;
+    // ---- P3 (only when some bin exceeds `keep`): max of the surviving bins ----
+    if (mx > keep) {   // uniform across the cluster: s_keep / s_mall derive from the same cluster totals
+        unsigned m = 0;
         for (int i = tid; i < nband; i += NT) {
             const uint32_t w = hist[i];
             const uint32_t a = w & 0xffffu, b = w >> 16;
-            if (a <= keep) mx = max(mx, a);
-            if (b <= keep) mx = max(mx, b);
+            if (a <= keep) m = max(m, a);
+            if (b <= keep) m = max(m, b);
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if (lane == 0) redm[wid] = mx;
+        m = warp_max_u32(m);
+        if (lane == 0) red32[wid][0] = m;
         __syncthreads();
         if (tid == 0) {
-            unsigned m = 0;
-            for (int w = 0; w < nwarps; ++w) m = max(m, redm[w]);
-            part.mx = m;
+            unsigned mm = 0;
+            for (int w = 0; w < nwarps; ++w) mm = max(mm, red32[w][0]);
+            part.mx = mm;
         }
+        cluster.sync();
+        if (tid == 0) {
+            unsigned mm = 0;
+            for (int r = 0; r < CS; ++r) mm = max(mm, cluster.map_shared_rank(&part, r)->mx);
+            s_mx = mm;
+        }
+        __syncthreads();
+        mx = s_mx;
     }
-    cluster.sync();
-    if (tid == 0) {
-        unsigned m = 0;
-        for (int r = 0; r < CS; ++r) m = max(m, cluster.map_shared_rank(&part, r)->mx);
-        s_mx = m;
-    }
-    __syncthreads();
-    const unsigned mx = s_mx;
 
-    // ---- P4: gray value per pixel, in place (small counts through a per-frame LUT) ----
+    // ---- P4: gray byte per pixel (small counts through a per-frame LUT), compacted in place ----
     for (int i = tid; i < GLUT_N * GLUT_N; i += NT) glut[i] = (uint8_t)gray_px(i % GLUT_N, i / GLUT_N, mx, mask);
     __syncthreads();
     {
-        uint8_t *dg = p.dbg_gray ? p.dbg_gray + (size_t)fid * HW + band_lo : nullptr;
-        for (int i = tid; i < nband; i += NT) {
-            const uint32_t w = hist[i];
-            uint32_t a = w & 0xffffu, b = w >> 16;
-            if (a > keep) a = 0;
-            if (b > keep) b = 0;
-            const unsigned g = (a < GLUT_N && b < GLUT_N) ? glut[b * GLUT_N + a] : gray_px(a, b, mx, mask);
-            hist[i] = g;
-            if (dg) dg[i] = (uint8_t)g;
+        const int ng = (nband + 3) >> 2;
+        uint32_t gpack[MAXG];
+        int32_t *dc = p.dbg_counts ? p.dbg_counts + ((size_t)fid * HW + band_lo) * 2 : nullptr;
+        const uint4 *h4 = reinterpret_cast<const uint4 *>(hist);
+#pragma unroll
+        for (int k = 0; k < MAXG; ++k) {
+            const int j = tid + k * NT;
+            gpack[k] = 0;
+            if (j < ng) {
+                const uint4 w4 = h4[j];
+                const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
+                uint32_t pk = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t a = ws[q] & 0xffffu, b = ws[q] >> 16;
+                    if (dc && 4 * j + q < nband) { dc[2 * (4 * j + q)] = (int32_t)a; dc[2 * (4 * j + q) + 1] = (int32_t)b; }
+                    if (a > keep) a = 0;
+                    if (b > keep) b = 0;
+                    const unsigned g = (a < GLUT_N && b < GLUT_N) ? glut[b * GLUT_N + a] : gray_px(a, b, mx, mask);
+                    pk |= g << (8 * q);
+                }
+                gpack[k] = pk;
+            }
+        }
+        __syncthreads();   // every bin has been read: the buffer can be overwritten with bytes
+        uint32_t *g32 = reinterpret_cast<uint32_t *>(gray);
+        uint32_t *dg = p.dbg_gray ? reinterpret_cast<uint32_t *>(p.dbg_gray + (size_t)fid * HW + band_lo) : nullptr;
+#pragma unroll
+        for (int k = 0; k < MAXG; ++k) {
+            const int j = tid + k * NT;
+            if (j < ng) {
+                g32[j] = gpack[k];
+                if (dg) {
+                    if (4 * j + 3 < nband && (((size_t)fid * HW + band_lo) & 3) == 0) dg[j] = gpack[k];
+                    else
+                        for (int q = 0; q < 4 && 4 * j + q < nband; ++q)
+                            reinterpret_cast<uint8_t *>(dg)[4 * j + q] = (uint8_t)(gpack[k] >> (8 * q));
+                }
+            }
         }
     }
     __syncthreads();
 
-    // ---- P5: horizontal Pillow pass (only the 224 columns that survive the centre crop) ----
+    // ---- P5: horizontal Pillow pass, one thread per cropped output column, taps in registers ----
     {
-        const int stride = 2 + p.KH;
-        uint32_t *hrow32 = reinterpret_cast<uint32_t *>(hrow);
-        const int items = rows * (OUT / 4);
-        for (int it = tid; it < items; it += NT) {
-            const int y = it / (OUT / 4), xg = it % (OUT / 4);
-            const uint32_t *src = hist + y * W;
-            uint32_t packed = 0;
+        const int RG = NT / OUT;
+        const int x = tid % OUT, rg = tid / OUT;
+        if (rg < RG) {
+            const int32_t *tab = p.hx + x * (2 + p.KH);
+            const int lo = __ldg(tab), cnt = __ldg(tab + 1);
+            if (KHMAX > 0) {
+                int k[KHMAX > 0 ? KHMAX : 1], off[KHMAX > 0 ? KHMAX : 1];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int32_t *tab = p.hx + (xg * 4 + j) * stride;
-                const int lo = __ldg(tab), cnt = __ldg(tab + 1);
-                int ss = 1 << (PREC - 1);
-                for (int t = 0; t < cnt; ++t) ss += (int)(src[lo + t] & 0xffu) * __ldg(tab + 2 + t);
-                packed |= clip8(ss) << (8 * j);
+                for (int t = 0; t < KHMAX; ++t) {
+                    k[t] = t < cnt ? __ldg(tab + 2 + t) : 0;
+                    off[t] = min(lo + t, W - 1);
+                }
+                for (int y = rg; y < rows; y += RG) {
+                    const uint8_t *src = gray + y * W;
+                    int ss = 1 << (PREC - 1);
+#pragma unroll
+                    for (int t = 0; t < KHMAX; ++t) ss += (int)src[off[t]] * k[t];
+                    hrow[y * OUT + x] = (uint8_t)clip8(ss);
+                }
+            } else {
+                for (int y = rg; y < rows; y += RG) {
+                    const uint8_t *src = gray + y * W + lo;
+                    int ss = 1 << (PREC - 1);
+                    for (int t = 0; t < cnt; ++t) ss += (int)src[t] * __ldg(tab + 2 + t);
+                    hrow[y * OUT + x] = (uint8_t)clip8(ss);
+                }
             }
-            hrow32[y * (OUT / 4) + xg] = packed;
         }
     }
     cluster.sync();
@@ -350,25 +395,99 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
     // ---- P6: vertical pass (+DSMEM reads of neighbour bands), normalise, store ----
     {
         const int stride = 2 + p.KV;
-        const int items = (yo_end - yo_begin) * (OUT / 2);
         uint8_t *du = p.dbg_u8 ? p.dbg_u8 + (size_t)fid * OUT * OUT : nullptr;
-        for (int it = tid; it < items; it += NT) {
-            const int yo = yo_begin + it / (OUT / 2), x = (it % (OUT / 2)) * 2;
-            const int32_t *tab = p.vy + yo * stride;
-            const int lo = __ldg(tab), cnt = __ldg(tab + 1);
-            int s0 = 1 << (PREC - 1), s1 = s0;
-            for (int t = 0; t < cnt; ++t) {
-                const int ys = lo + t;
-                const int owner = ys / RB;
-                const uint8_t *hr = (owner == rank) ? hrow : cluster.map_shared_rank(hrow, owner);
-                const unsigned two = *reinterpret_cast<const uint16_t *>(hr + (ys - owner * RB) * OUT + x);
-                const int k = __ldg(tab + 2 + t);
-                s0 += (int)(two & 0xffu) * k;
-                s1 += (int)(two >> 8) * k;
+        const int slot = fr.out_slot;
+        const bool wide = p.out_fmt != EC_OUT_BF16_PATCH || (p.patch % 8) == 0;
+        if (wide) {
+            constexpr int NG = OUT / 8;
+            const int items = (yo_end - yo_begin) * NG;
+            for (int it = tid; it < items; it += NT) {
+                const int yo = yo_begin + it / NG, xg = it % NG;
+                const int32_t *tab = p.vy + yo * stride;
+                const int lo = __ldg(tab), cnt = __ldg(tab + 1);
+                int acc[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = 1 << (PREC - 1);
+                int own = lo / RB, rin = lo - own * RB;
+                const uint8_t *base = (own == rank) ? hrow : cluster.map_shared_rank(hrow, own);
+                for (int t = 0; t < cnt; ++t) {
+                    const uint2 v = *reinterpret_cast<const uint2 *>(base + rin * OUT + xg * 8);
+                    const int k = __ldg(tab + 2 + t);
+                    acc[0] += (int)(v.x & 0xffu) * k;          acc[1] += (int)((v.x >> 8) & 0xffu) * k;
+                    acc[2] += (int)((v.x >> 16) & 0xffu) * k;  acc[3] += (int)(v.x >> 24) * k;
+                    acc[4] += (int)(v.y & 0xffu) * k;          acc[5] += (int)((v.y >> 8) & 0xffu) * k;
+                    acc[6] += (int)((v.y >> 16) & 0xffu) * k;  acc[7] += (int)(v.y >> 24) * k;
+                    if (++rin == RB) { rin = 0; ++own; base = (own == rank) ? hrow : cluster.map_shared_rank(hrow, own); }
+                }
+                unsigned v8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v8[j] = clip8(acc[j]);
+                const int x = xg * 8;
+                if (du) {
+                    uint2 pk;
+                    pk.x = v8[0] | (v8[1] << 8) | (v8[2] << 16) | (v8[3] << 24);
+                    pk.y = v8[4] | (v8[5] << 8) | (v8[6] << 16) | (v8[7] << 24);
+                    *reinterpret_cast<uint2 *>(du + yo * OUT + x) = pk;
+                }
+                if (p.out_fmt == EC_OUT_F32_NCHW) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        float *o = (float *)p.out + (((size_t)slot * 3 + c) * OUT + yo) * OUT + x;
+                        const float *nl = nlut + c * 256;
+                        *reinterpret_cast<float4 *>(o) = make_float4(nl[v8[0]], nl[v8[1]], nl[v8[2]], nl[v8[3]]);
+                        *reinterpret_cast<float4 *>(o + 4) = make_float4(nl[v8[4]], nl[v8[5]], nl[v8[6]], nl[v8[7]]);
+                    }
+                } else {
+                    size_t obase;
+                    size_t cstride;
+                    if (p.out_fmt == EC_OUT_BF16_NCHW) {
+                        obase = (((size_t)slot * 3) * OUT + yo) * OUT + x;
+                        cstride = (size_t)OUT * OUT;
+                    } else {
+                        const int P = p.patch;
+                        obase = ((size_t)slot * p.G * p.G + (size_t)ypq[yo] * p.G + xpq[x >> 1]) * p.ldk + ypr[yo] * P + xpr[x >> 1];
+                        cstride = (size_t)P * P;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const unsigned short *nl = reinterpret_cast<const unsigned short *>(nlut16) + c * 256;
+                        uint4 o;
+                        o.x = (unsigned)nl[v8[0]] | ((unsigned)nl[v8[1]] << 16);
+                        o.y = (unsigned)nl[v8[2]] | ((unsigned)nl[v8[3]] << 16);
+                        o.z = (unsigned)nl[v8[4]] | ((unsigned)nl[v8[5]] << 16);
+                        o.w = (unsigned)nl[v8[6]] | ((unsigned)nl[v8[7]] << 16);
+                        *reinterpret_cast<uint4 *>((__nv_bfloat16 *)p.out + obase + c * cstride) = o;
+                    }
+                }
             }
-            const unsigned v0 = clip8(s0), v1 = clip8(s1);
-            if (du) { du[yo * OUT + x] = (uint8_t)v0; du[yo * OUT + x + 1] = (uint8_t)v1; }
-            store_pair(p, fr.out_slot, yo, x, v0, v1, nlut);
+        } else {
+            // patch size not a multiple of 8 (ViT-L/14): column pairs never straddle a patch
+            const int P = p.patch;
+            const int items = (yo_end - yo_begin) * (OUT / 2);
+            for (int it = tid; it < items; it += NT) {
+                const int yo = yo_begin + it / (OUT / 2), xp = it % (OUT / 2), x = 2 * xp;
+                const int32_t *tab = p.vy + yo * stride;
+                const int lo = __ldg(tab), cnt = __ldg(tab + 1);
+                int s0 = 1 << (PREC - 1), s1 = s0;
+                int own = lo / RB, rin = lo - own * RB;
+                const uint8_t *base = (own == rank) ? hrow : cluster.map_shared_rank(hrow, own);
+                for (int t = 0; t < cnt; ++t) {
+                    const unsigned two = *reinterpret_cast<const uint16_t *>(base + rin * OUT + x);
+                    const int k = __ldg(tab + 2 + t);
+                    s0 += (int)(two & 0xffu) * k;
+                    s1 += (int)(two >> 8) * k;
+                    if (++rin == RB) { rin = 0; ++own; base = (own == rank) ? hrow : cluster.map_shared_rank(hrow, own); }
+                }
+                const unsigned v0 = clip8(s0), v1 = clip8(s1);
+                if (du) { du[yo * OUT + x] = (uint8_t)v0; du[yo * OUT + x + 1] = (uint8_t)v1; }
+                const size_t obase = ((size_t)slot * p.G * p.G + (size_t)ypq[yo] * p.G + xpq[xp]) * p.ldk + ypr[yo] * P + xpr[xp];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const unsigned short *nl = reinterpret_cast<const unsigned short *>(nlut16) + c * 256;
+                    *reinterpret_cast<unsigned *>((__nv_bfloat16 *)p.out + obase + (size_t)c * P * P) =
+                        (unsigned)nl[v0] | ((unsigned)nl[v1] << 16);
+                }
+            }
         }
     }
     cluster.sync();   // peers may still be reading this CTA's hrow
@@ -480,8 +599,9 @@ int get_tables(int H, int W, cudaStream_t stream, Tables &out)
 
 int geometry(int H, int W, int &CS, int &RB, int &NT, size_t &smem)
 {
-    const size_t budget = 220 * 1024;   // 227 KB per CTA minus static shared memory
-    const size_t per_row = (size_t)W * 4 + OUT;
+    const size_t budget = 216 * 1024;   // 227 KB per CTA minus ~9 KB of static shared memory (LUTs, tables)
+    // bins (4 bytes/pixel) are later reused as gray bytes (1 byte/pixel) followed by the 224-byte resampled rows
+    const size_t per_row = (size_t)W * 4 > (size_t)W + OUT + 16 ? (size_t)W * 4 : (size_t)W + OUT + 16;
     const int rb_max = (int)(budget / per_row);
     if (rb_max < 1) return EC_ERR_UNSUPPORTED;
     CS = 1;
@@ -489,8 +609,9 @@ int geometry(int H, int W, int &CS, int &RB, int &NT, size_t &smem)
     if (CS > 8) return EC_ERR_UNSUPPORTED;   // portable cluster limit
     RB = (H + CS - 1) / CS;
     smem = (size_t)RB * per_row;
-    smem = (smem + 15) & ~(size_t)15;
+    smem = (smem + 31) & ~(size_t)15;
     NT = ((size_t)RB * W <= 16384) ? 512 : 1024;
+    if (((size_t)RB * W + 3) / 4 > (size_t)MAXG * NT) return EC_ERR_UNSUPPORTED;
     return EC_OK;
 }
 
@@ -546,7 +667,8 @@ extern "C" int ec_event2img(const float *events, const ec_frame *frames, int n_f
     p.hx = tb.dev; p.vy = tb.dev + tb.off_vy; p.nlut = reinterpret_cast<const float *>(tb.dev + tb.off_lut);
     p.KH = tb.KH; p.KV = tb.KV;
 
-    EC_CUDA_CHECK(cudaFuncSetAttribute(event2img_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = tb.KH <= 5 ? event2img_kernel<5> : (tb.KH <= 11 ? event2img_kernel<11> : event2img_kernel<0>);
+    EC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)n_frames * CS);
     cfg.blockDim = dim3(NT);
@@ -556,7 +678,7 @@ extern "C" int ec_event2img(const float *events, const ec_frame *frames, int n_f
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    EC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, event2img_kernel, p));
+    EC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
     return EC_OK;
 }
 

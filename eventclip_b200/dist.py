@@ -1,0 +1,76 @@
+"""Sample sharding and the final metric reduction of the multi-GPU inference path.
+
+The path shards by sample (every events -> logits unit is independent): rank r takes a
+contiguous block of the sample index range, weights and text features are replicated, and the only collective is
+one all-reduce of six int64 counters at the end -- the state of the reference's AverageMeters (test.py:55-81):
+    [n_samples, top1_probs, top1_logits, top5_probs, top5_logits, n_valid_views]
+Backend: NCCL over NVLink on B200 (one process per GPU), gloo in the CPU tests.
+"""
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(n, rank=None, world_size=None):
+    """Contiguous block [lo, hi) of n samples for `rank`; sizes differ by at most one."""
+    if rank is None:
+        rank, world_size = world()
+    base, extra = divmod(n, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+class AccuracyMeter:
+    """Counts what test.py:66-81 averages, as exact integers so that the cross-rank reduction is order-independent."""
+
+    def __init__(self, device="cpu"):
+        self.counters = torch.zeros(6, dtype=torch.int64, device=device)
+
+    def update(self, out_dict, labels):
+        labels = labels.to(out_dict["logits"].device).long()
+        B = labels.shape[0]
+        if "top5_logits" in out_dict:
+            t5l, t5p = out_dict["top5_logits"].long(), out_dict["top5_probs"].long()
+        else:
+            k = min(5, out_dict["logits"].shape[-1])
+            t5l = out_dict["logits"].topk(k, dim=-1).indices
+            t5p = out_dict["probs"].topk(k, dim=-1).indices
+        upd = torch.stack([
+            torch.tensor(B, device=labels.device),
+            (t5p[:, 0] == labels).sum(), (t5l[:, 0] == labels).sum(),
+            (t5p == labels[:, None]).any(-1).sum(), (t5l == labels[:, None]).any(-1).sum(),
+            out_dict["valid_masks"].sum().to(labels.device),
+        ]).to(self.counters.device)
+        self.counters += upd
+
+    def all_reduce(self):
+        """The one collective of the inference path."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.counters, op=dist.ReduceOp.SUM)
+        return self
+
+    def result(self):
+        c = self.counters.tolist()
+        n = max(c[0], 1)
+        return dict(n=c[0], probs_acc=c[1] / n, logits_acc=c[2] / n, probs_acc5=c[3] / n, logits_acc5=c[4] / n,
+                    valid_views=c[5])
+
+
+def gather_predictions(pred):
+    """All ranks' per-sample predictions in rank order (parity checks); pred: int tensor [b_local]."""
+    rank, ws = world()
+    if ws == 1:
+        return pred
+    sizes = [torch.zeros(1, dtype=torch.int64, device=pred.device) for _ in range(ws)]
+    dist.all_gather(sizes, torch.tensor([pred.shape[0]], dtype=torch.int64, device=pred.device))
+    m = int(max(s.item() for s in sizes))
+    pad = torch.full((m,), -1, dtype=pred.dtype, device=pred.device)
+    pad[:pred.shape[0]] = pred
+    bufs = [torch.empty_like(pad) for _ in range(ws)]
+    dist.all_gather(bufs, pad)
+    return torch.cat([b[:int(s.item())] for b, s in zip(bufs, sizes)])
