@@ -110,7 +110,7 @@ __device__ unsigned compute_keep(unsigned long long n, unsigned long long S1, un
 }
 
 // vis.py:27-39 evaluated as numpy >= 2 does (float64); `hist @ cmap` is a 2-term BLAS dot = one fma.
-__device__ __forceinline__ unsigned gray_px(unsigned pos, unsigned neg, unsigned mx, bool mask)
+__device__ __noinline__ unsigned gray_px(unsigned pos, unsigned neg, unsigned mx, bool mask)
 {
     if (mx == 0) return 0;   // 0/0 in the reference (undefined there; NaN -> uint8 gives 0 on x86)
     const double m = (double)mx;
@@ -131,10 +131,9 @@ __device__ __forceinline__ unsigned clip8(int v)
     return (unsigned)min(max(v, 0), 255);
 }
 
-constexpr int MAXG = 14;   // 4-pixel groups per thread in P4: band pixels <= 56320 (220 KB of bins) / 4 / 1024
 
 // KHMAX: compile-time bound on the horizontal taps (5 when upsampling, 11 for 640 -> 298); 0 = dynamic loop.
-template <int KHMAX>
+template <int KHMAX, bool DBG>
 __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
 {
     cg::cluster_group cluster = cg::this_cluster();
@@ -219,6 +218,7 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
     {
         const float4 *ev = p.events + fr.ev_start;
         const int n = fr.ev_count;
+        const int iband_lo = (int)band_lo, iHW = (int)HW;
         for (int base = 0; base < n; base += NT * 4) {
             float4 e[4];
 #pragma unroll
@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
                 const int i = base + u * NT + tid;
                 if (i < n) e[u] = ld_stream(ev + i);
             }
+            unsigned s2p = 0;   // <= 4 * (2*65535 + 1): no 32-bit overflow within one round
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int i = base + u * NT + tid;
@@ -233,16 +234,26 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
                     const int x = __float2int_rz(e[u].x), y = __float2int_rz(e[u].y);
                     const int pol = __float2int_rz(e[u].w);
                     if (pol != 0) {
-                        const long long idx = (long long)x + (long long)y * W;   // flat index as np.bincount sees it
-                        if (idx < 0 || idx >= HW) {
+                        // flat index as np.bincount sees it; 32-bit math when it provably cannot overflow
+                        int idx;
+                        bool ok;
+                        if ((unsigned)(x + 32768) < 65536u && (unsigned)(y + 32768) < 65536u && W < 32768) {
+                            idx = x + y * W;
+                            ok = (unsigned)idx < (unsigned)iHW;
+                        } else {
+                            const long long i64 = (long long)x + (long long)y * W;
+                            ok = i64 >= 0 && i64 < HW;
+                            idx = (int)i64;
+                        }
+                        if (!ok) {
                             flags |= EC_STATUS_BAD_COORD;
                         } else {
-                            const long long l = idx - band_lo;
-                            if (l >= 0 && l < nband) {
-                                const uint32_t old = atomicAdd(&hist[(int)l], pol > 0 ? 1u : 65536u);
+                            const unsigned l = (unsigned)(idx - iband_lo);
+                            if (l < (unsigned)nband) {
+                                const uint32_t old = atomicAdd(&hist[l], pol > 0 ? 1u : 65536u);
                                 const uint32_t c = pol > 0 ? (old & 0xffffu) : (old >> 16);
                                 if (c == 0xffffu) flags |= EC_STATUS_COUNT_OVERFLOW;   // the 16-bit field wraps
-                                s2 += 2ull * c + 1ull;
+                                s2p += 2u * c + 1u;
                                 nnz += (c == 0);
                                 mall = max(mall, c + 1);
                                 ++nacc;
@@ -251,6 +262,7 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
                     }
                 }
             }
+            s2 += s2p;
         }
     }
     // block reduction of the partials
@@ -316,44 +328,36 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
     for (int i = tid; i < GLUT_N * GLUT_N; i += NT) glut[i] = (uint8_t)gray_px(i % GLUT_N, i / GLUT_N, mx, mask);
     __syncthreads();
     {
+        // Round r packs pixel groups [r*NT, (r+1)*NT): it reads words [4rNT, 4(r+1)NT) and writes words [rNT, (r+1)NT),
+        // which only earlier rounds (or this one, before the barrier) have read.
         const int ng = (nband + 3) >> 2;
-        uint32_t gpack[MAXG];
-        int32_t *dc = p.dbg_counts ? p.dbg_counts + ((size_t)fid * HW + band_lo) * 2 : nullptr;
         const uint4 *h4 = reinterpret_cast<const uint4 *>(hist);
-#pragma unroll
-        for (int k = 0; k < MAXG; ++k) {
-            const int j = tid + k * NT;
-            gpack[k] = 0;
+        uint32_t *g32 = reinterpret_cast<uint32_t *>(gray);
+        for (int j0 = 0; j0 < ng; j0 += NT) {
+            const int j = j0 + tid;
+            uint32_t pk = 0;
             if (j < ng) {
                 const uint4 w4 = h4[j];
                 const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
-                uint32_t pk = 0;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     uint32_t a = ws[q] & 0xffffu, b = ws[q] >> 16;
-                    if (dc && 4 * j + q < nband) { dc[2 * (4 * j + q)] = (int32_t)a; dc[2 * (4 * j + q) + 1] = (int32_t)b; }
+                    if (DBG && p.dbg_counts && 4 * j + q < nband) {
+                        int32_t *dc = p.dbg_counts + ((size_t)fid * HW + band_lo + 4 * j + q) * 2;
+                        dc[0] = (int32_t)a; dc[1] = (int32_t)b;
+                    }
                     if (a > keep) a = 0;
                     if (b > keep) b = 0;
-                    const unsigned g = (a < GLUT_N && b < GLUT_N) ? glut[b * GLUT_N + a] : gray_px(a, b, mx, mask);
+                    const unsigned g = ((a | b) < GLUT_N) ? glut[b * GLUT_N + a] : gray_px(a, b, mx, mask);
                     pk |= g << (8 * q);
                 }
-                gpack[k] = pk;
             }
-        }
-        __syncthreads();   // every bin has been read: the buffer can be overwritten with bytes
-        uint32_t *g32 = reinterpret_cast<uint32_t *>(gray);
-        uint32_t *dg = p.dbg_gray ? reinterpret_cast<uint32_t *>(p.dbg_gray + (size_t)fid * HW + band_lo) : nullptr;
-#pragma unroll
-        for (int k = 0; k < MAXG; ++k) {
-            const int j = tid + k * NT;
+            __syncthreads();
             if (j < ng) {
-                g32[j] = gpack[k];
-                if (dg) {
-                    if (4 * j + 3 < nband && (((size_t)fid * HW + band_lo) & 3) == 0) dg[j] = gpack[k];
-                    else
-                        for (int q = 0; q < 4 && 4 * j + q < nband; ++q)
-                            reinterpret_cast<uint8_t *>(dg)[4 * j + q] = (uint8_t)(gpack[k] >> (8 * q));
-                }
+                g32[j] = pk;
+                if (DBG && p.dbg_gray)
+                    for (int q = 0; q < 4 && 4 * j + q < nband; ++q)
+                        p.dbg_gray[(size_t)fid * HW + band_lo + 4 * j + q] = (uint8_t)(pk >> (8 * q));
             }
         }
     }
@@ -395,7 +399,7 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
     // ---- P6: vertical pass (+DSMEM reads of neighbour bands), normalise, store ----
     {
         const int stride = 2 + p.KV;
-        uint8_t *du = p.dbg_u8 ? p.dbg_u8 + (size_t)fid * OUT * OUT : nullptr;
+        uint8_t *du = (DBG && p.dbg_u8) ? p.dbg_u8 + (size_t)fid * OUT * OUT : nullptr;
         const int slot = fr.out_slot;
         const bool wide = p.out_fmt != EC_OUT_BF16_PATCH || (p.patch % 8) == 0;
         if (wide) {
@@ -611,7 +615,6 @@ int geometry(int H, int W, int &CS, int &RB, int &NT, size_t &smem)
     smem = (size_t)RB * per_row;
     smem = (smem + 31) & ~(size_t)15;
     NT = ((size_t)RB * W <= 16384) ? 512 : 1024;
-    if (((size_t)RB * W + 3) / 4 > (size_t)MAXG * NT) return EC_ERR_UNSUPPORTED;
     return EC_OK;
 }
 
@@ -667,7 +670,9 @@ extern "C" int ec_event2img(const float *events, const ec_frame *frames, int n_f
     p.hx = tb.dev; p.vy = tb.dev + tb.off_vy; p.nlut = reinterpret_cast<const float *>(tb.dev + tb.off_lut);
     p.KH = tb.KH; p.KV = tb.KV;
 
-    auto kern = tb.KH <= 5 ? event2img_kernel<5> : (tb.KH <= 11 ? event2img_kernel<11> : event2img_kernel<0>);
+    const bool dbg = dbg_counts || dbg_gray || dbg_u8;
+    auto kern = dbg ? (tb.KH <= 5 ? event2img_kernel<5, true> : (tb.KH <= 11 ? event2img_kernel<11, true> : event2img_kernel<0, true>))
+                    : (tb.KH <= 5 ? event2img_kernel<5, false> : (tb.KH <= 11 ? event2img_kernel<11, false> : event2img_kernel<0, false>));
     EC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)n_frames * CS);

@@ -25,6 +25,8 @@ constexpr int STAGES = 4;
 constexpr int NUM_THREADS = 320;   // 10 warps
 constexpr int EPI_WARPS = 8;
 constexpr int UMMA_K = 16;
+constexpr int STG_PITCH = 20;       // floats per row of an epilogue warp's 32x16 staging tile (80 B: conflict-free)
+constexpr int STG_BYTES = EPI_WARPS * 32 * STG_PITCH * 4;
 
 struct GemmParams {
     int M, N, K;
@@ -223,70 +225,121 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         }
     } else {
         // ===================== epilogue =====================
+        // TMEM -> registers (thread = accumulator row) -> warp-private smem tile (transpose) -> coalesced global
+        // accesses: in the second half each instruction touches 8 rows x 64 contiguous bytes (fp32) or 16 rows x
+        // 32 bytes (bf16) instead of 32 rows x 16 bytes.  The residual for the next chunk is prefetched.
         const int ew = warp - 2;           // 0..7
         const int quarter = warp & 3;      // TMEM lane quarter this warp may touch
         const int half = ew >> 2;          // which half of the BN columns
         constexpr int COLS_PER_WARP = BN / 2;
+        constexpr int NCHUNK = COLS_PER_WARP / 32;
+        float *stg = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES) + ew * (32 * STG_PITCH);
+        const bool f32out = p.epi >= EC_EPI_F32_RESADD;
+        const bool has_res = p.epi == EC_EPI_F32_RESADD || p.epi == EC_EPI_PATCH;
+        // transposed lane mapping inside a 16-column pass
+        const int f_r = lane >> 2, f_c = (lane & 3) * 4;     // fp32 out: rows f_r + 8i (i<4), cols f_c..f_c+3
+        const int h_r = lane >> 1, h_c = (lane & 1) * 8;     // bf16 out: rows h_r + 16i (i<2), cols h_c..h_c+7
         uint32_t as = 0, aphase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+            const int row0 = tm * BM + quarter * 32;
+            const int colw = tn * BN + half * COLS_PER_WARP;
+            // per-lane output rows / residual rows of the fp32 mapping
+            size_t orow[4];
+            const float *rrow[4];
+            bool rok[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = row0 + f_r + 8 * i;
+                rok[i] = r < p.M;
+                orow[i] = (size_t)r;
+                rrow[i] = nullptr;
+                if (p.epi == EC_EPI_PATCH) {
+                    const int g2 = p.row_map;
+                    const int img = r / g2, tok = r - img * g2;
+                    orow[i] = (size_t)img * (g2 + 1) + 1 + tok;
+                    rrow[i] = p.res + (size_t)(1 + tok) * p.N;
+                } else if (p.epi == EC_EPI_F32_RESADD) {
+                    rrow[i] = p.res + (size_t)r * p.ldo;
+                }
+            }
+            float4 rnext[4];
+            auto load_res = [&](int pass) {   // residual / positional values of one 16-column pass (4 rows per lane)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int col = colw + pass * 16 + f_c;
+                    rnext[i] = (rok[i] && col < p.N) ? *reinterpret_cast<const float4 *>(rrow[i] + col)
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            if (has_res) load_res(0);
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
-            const int row = tm * BM + quarter * 32 + lane;
-            const bool row_ok = row < p.M;
-            size_t orow = (size_t)row;
-            const float *posrow = nullptr;
-            if (p.epi == EC_EPI_PATCH) {
-                const int g2 = p.row_map;
-                const int img = row / g2, tok = row % g2;
-                orow = (size_t)img * (g2 + 1) + 1 + tok;
-                posrow = p.res + (size_t)(1 + tok) * p.N;
-            }
 #pragma unroll 1
-            for (int c = 0; c < COLS_PER_WARP; c += 32) {
-                const int col0 = tn * BN + half * COLS_PER_WARP + c;
+            for (int c = 0; c < NCHUNK; ++c) {
                 uint32_t v[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * COLS_PER_WARP + c);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * COLS_PER_WARP + c * 32);
                 tmem_ld32(taddr, v);
-                if (row_ok && col0 < p.N) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        const int col = col0 + j;
-                        if (col >= p.N) break;      // N is a multiple of 8
-                        float f[8];
+                for (int ps = 0; ps < 2; ++ps) {
+                    float4 rcur[4];
+                    if (has_res) {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]);
-                        if (p.bias) {
-                            const float4 b0 = *reinterpret_cast<const float4 *>(p.bias + col);
-                            const float4 b1 = *reinterpret_cast<const float4 *>(p.bias + col + 4);
-                            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                        for (int i = 0; i < 4; ++i) rcur[i] = rnext[i];
+                        if (c * 2 + ps + 1 < 2 * NCHUNK) load_res(c * 2 + ps + 1);   // prefetch the next pass
+                    }
+                    // stage 32 rows x 16 columns (row = lane)
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<float4 *>(stg + lane * STG_PITCH + 4 * j) =
+                            make_float4(__uint_as_float(v[ps * 16 + 4 * j]), __uint_as_float(v[ps * 16 + 4 * j + 1]),
+                                        __uint_as_float(v[ps * 16 + 4 * j + 2]), __uint_as_float(v[ps * 16 + 4 * j + 3]));
+                    __syncwarp();
+                    const int col0 = colw + c * 32 + ps * 16;
+                    if (col0 >= p.N) continue;        // warp-uniform (N is a multiple of 8; 16-col passes may be half full)
+                    if (f32out) {
+                        const int col = col0 + f_c;
+                        if (col < p.N) {
+                            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (p.bias) b = *reinterpret_cast<const float4 *>(p.bias + col);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                if (!rok[i]) continue;
+                                float4 a = *reinterpret_cast<const float4 *>(stg + (f_r + 8 * i) * STG_PITCH + f_c);
+                                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+                                if (has_res) { a.x += rcur[i].x; a.y += rcur[i].y; a.z += rcur[i].z; a.w += rcur[i].w; }
+                                *reinterpret_cast<float4 *>((float *)p.out + orow[i] * p.ldo + col) = a;
+                            }
                         }
-                        if (p.epi == EC_EPI_BF16 || p.epi == EC_EPI_BF16_QGELU) {
-                            if (p.epi == EC_EPI_BF16_QGELU) {
+                    } else {
+                        const int col = col0 + h_c;
+                        if (col < p.N) {
+                            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                            if (p.bias) {
+                                b0 = *reinterpret_cast<const float4 *>(p.bias + col);
+                                b1 = *reinterpret_cast<const float4 *>(p.bias + col + 4);
+                            }
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) f[e] = quick_gelu(f[e]);
+                            for (int i = 0; i < 2; ++i) {
+                                const int r = row0 + h_r + 16 * i;
+                                if (r >= p.M) continue;
+                                const float4 a0 = *reinterpret_cast<const float4 *>(stg + (h_r + 16 * i) * STG_PITCH + h_c);
+                                const float4 a1 = *reinterpret_cast<const float4 *>(stg + (h_r + 16 * i) * STG_PITCH + h_c + 4);
+                                float f[8] = {a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w,
+                                              a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w};
+                                if (p.epi == EC_EPI_BF16_QGELU) {
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) f[e] = quick_gelu(f[e]);
+                                }
+                                uint4 o;
+                                __nv_bfloat162 h;
+                                h = __floats2bfloat162_rn(f[0], f[1]); o.x = *reinterpret_cast<uint32_t *>(&h);
+                                h = __floats2bfloat162_rn(f[2], f[3]); o.y = *reinterpret_cast<uint32_t *>(&h);
+                                h = __floats2bfloat162_rn(f[4], f[5]); o.z = *reinterpret_cast<uint32_t *>(&h);
+                                h = __floats2bfloat162_rn(f[6], f[7]); o.w = *reinterpret_cast<uint32_t *>(&h);
+                                *reinterpret_cast<uint4 *>((__nv_bfloat16 *)p.out + (size_t)r * p.ldo + col) = o;
                             }
-                            uint4 o;
-                            __nv_bfloat162 h;
-                            h = __floats2bfloat162_rn(f[0], f[1]); o.x = *reinterpret_cast<uint32_t *>(&h);
-                            h = __floats2bfloat162_rn(f[2], f[3]); o.y = *reinterpret_cast<uint32_t *>(&h);
-                            h = __floats2bfloat162_rn(f[4], f[5]); o.z = *reinterpret_cast<uint32_t *>(&h);
-                            h = __floats2bfloat162_rn(f[6], f[7]); o.w = *reinterpret_cast<uint32_t *>(&h);
-                            *reinterpret_cast<uint4 *>((__nv_bfloat16 *)p.out + orow * p.ldo + col) = o;
-                        } else {
-                            const float *r = nullptr;
-                            if (p.epi == EC_EPI_F32_RESADD) r = p.res + orow * p.ldo + col;
-                            else if (p.epi == EC_EPI_PATCH) r = posrow + col;
-                            if (r) {
-                                const float4 r0 = *reinterpret_cast<const float4 *>(r);
-                                const float4 r1 = *reinterpret_cast<const float4 *>(r + 4);
-                                f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
-                                f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
-                            }
-                            float *o = (float *)p.out + orow * p.ldo + col;
-                            *reinterpret_cast<float4 *>(o) = make_float4(f[0], f[1], f[2], f[3]);
-                            *reinterpret_cast<float4 *>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
                         }
                     }
                 }
@@ -345,7 +398,7 @@ int make_map(CUtensorMap *m, const void *base, int rows, int cols, int ld, int b
 template <int BN>
 int launch(const CUtensorMap &ma, const CUtensorMap &mw, GemmParams &p, cudaStream_t stream)
 {
-    constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024;
+    constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + STG_BYTES + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         EC_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
