@@ -239,11 +239,14 @@ def b200_arm(args):
     counters = torch.zeros(2, dtype=torch.int64, device=dev)     # {n, top-1 hits}: the AverageMeter state of test.py:67
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
+    from eventclip_b200.graph import GraphedClassifier
+    runner = zs if args.no_graph else GraphedClassifier(zs, max_events=host[0][0].shape[0])
+
     def step(i, resident=True):
         ev, off = (devb if resident else host)[i % NB]
         flush.zero_()                                    # L2 flush between iterations (inside the timed region)
         with torch.no_grad():
-            out = zs(dict(events=ev, event_offsets=off, sel_idx=sel))
+            out = runner(dict(events=ev, event_offsets=off, sel_idx=sel))
         pred = out["top5_logits"][:, 0]
         counters[0] += B
         counters[1] += (pred == labels).sum()
@@ -308,18 +311,28 @@ def b200_arm(args):
             a.record()
             r = orig(A, Wt, bias, epi, out, res, row_map, M)
             b.record()
-            rec.append((a, b, 2.0 * m * Wt.shape[0] * Wt.shape[1]))
+            rec.append((a, b, 2.0 * m * Wt.shape[0] * Wt.shape[1], (m, Wt.shape[0], Wt.shape[1], epi)))
             return r
 
         import eventclip_b200.clip as clipmod
         clipmod.ops.gemm_bf16 = timed_gemm
         nrep = 3
-        for i in range(nrep):
-            step(i)
+        for i in range(nrep):       # eager launches here: events cannot be recorded around nodes of a replayed graph
+            flush.zero_()
+            with torch.no_grad():
+                zs(dict(events=devb[i % NB][0], event_offsets=devb[i % NB][1], sel_idx=sel))
         torch.cuda.synchronize()
         clipmod.ops.gemm_bf16 = orig
-        gemm_ms = sum(a.elapsed_time(b) for a, b, _ in rec)
-        gemm_flops = sum(f for _, _, f in rec)
+        gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in rec)
+        gemm_flops = sum(f for _, _, f, _ in rec)
+        shapes = {}
+        for a, b, f, key in rec:
+            t = shapes.setdefault("M%d_N%d_K%d_%s" % key, [0, 0.0, 0.0])
+            t[0] += 1
+            t[1] += a.elapsed_time(b)
+            t[2] += f
+        by_shape = {k: dict(launches=v[0] // nrep, us_per_launch=1e3 * v[1] / v[0], tflops=v[2] / (v[1] / 1e3) / 1e12)
+                    for k, v in shapes.items()}
         n_gemm = len(rec) // nrep
         achieved = gemm_flops / (gemm_ms / 1e3) / 1e12
         peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
@@ -330,7 +343,7 @@ def b200_arm(args):
         roofline = dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=traffic,
                         kernel="gemm_kernel<BN> (tcgen05.mma kind::f16, TMA, TMEM)", launches_per_step=n_gemm,
                         flops_per_step=gemm_flops / nrep, gemm_ms_per_step=gemm_ms / nrep, peak_source=pk["_source"],
-                        peak_kind="sustained cuBLAS bf16")
+                        peak_kind="sustained cuBLAS bf16", by_shape=by_shape)
         enc_flops = clip.flops_per_image(ARCH) * B * T
         e2i = event2img_metric(dev, pk)
         # ---- CPU baseline: oracle port on this host, bounded sample ----
@@ -344,7 +357,8 @@ def b200_arm(args):
             "config": {"workload": f"zero-shot {ARCH} on synthetic N-Cars-shaped streams (120x100, 4000 events/sample, "
                                    f"2 classes), batch {B} per GPU, random-init CLIP (BASELINE.json configs[1])",
                        "per_gpu_batch": B, "views_per_sample": T, "l2": "256 MiB buffer rewritten before every step (inside the timed region)",
-                       "sharding": "samples by rank; one all-reduce of 2 int64 counters at the end"},
+                       "sharding": "samples by rank; one all-reduce of 2 int64 counters at the end",
+                       "launch": "eager" if args.no_graph else "CUDA graph replay of the device part (event2img..head)"},
             "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "clocks": clk.summary(),
@@ -371,6 +385,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--quick", action="store_true", help="timed region only (for ncu launch lists)")
     ap.add_argument("--e2i-only", action="store_true", help="only the event2img Gevents/s section")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     args = ap.parse_args()
     if args.e2i_only:
         torch.cuda.set_device(0)

@@ -673,7 +673,18 @@ extern "C" int ec_event2img(const float *events, const ec_frame *frames, int n_f
     const bool dbg = dbg_counts || dbg_gray || dbg_u8;
     auto kern = dbg ? (tb.KH <= 5 ? event2img_kernel<5, true> : (tb.KH <= 11 ? event2img_kernel<11, true> : event2img_kernel<0, true>))
                     : (tb.KH <= 5 ? event2img_kernel<5, false> : (tb.KH <= 11 ? event2img_kernel<11, false> : event2img_kernel<0, false>));
-    EC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        static std::mutex mu;
+        static std::map<std::pair<int, const void *>, size_t> granted;   // the attribute is per device
+        std::lock_guard<std::mutex> lk(mu);
+        int dev_id = 0;
+        EC_CUDA_CHECK(cudaGetDevice(&dev_id));
+        size_t &g = granted[std::make_pair(dev_id, (const void *)kern)];
+        if (smem > g) {
+            EC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            g = smem;
+        }
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)n_frames * CS);
     cfg.blockDim = dim3(NT);

@@ -131,6 +131,32 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
+    return r;
+}
+
 __device__ __forceinline__ float quick_gelu(float x)
 {
     // x * sigmoid(1.702 x) = x / (1 + 2^(-1.702 * log2(e) * x))
@@ -233,12 +259,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         const int half = ew >> 2;          // which half of the BN columns
         constexpr int COLS_PER_WARP = BN / 2;
         constexpr int NCHUNK = COLS_PER_WARP / 32;
-        float *stg = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES) + ew * (32 * STG_PITCH);
+        const uint32_t stg = smem_u32(smem + STAGES * STAGE_BYTES) + (uint32_t)ew * (32 * STG_PITCH * 4);   // shared-space address
         const bool f32out = p.epi >= EC_EPI_F32_RESADD;
         const bool has_res = p.epi == EC_EPI_F32_RESADD || p.epi == EC_EPI_PATCH;
         // transposed lane mapping inside a 16-column pass
         const int f_r = lane >> 2, f_c = (lane & 3) * 4;     // fp32 out: rows f_r + 8i (i<4), cols f_c..f_c+3
         const int h_r = lane >> 1, h_c = (lane & 1) * 8;     // bf16 out: rows h_r + 16i (i<2), cols h_c..h_c+7
+        constexpr int NPASS = 2 * NCHUNK;
         uint32_t as = 0, aphase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
@@ -263,51 +290,58 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     rrow[i] = p.res + (size_t)r * p.ldo;
                 }
             }
-            float4 rnext[4];
-            auto load_res = [&](int pass) {   // residual / positional values of one 16-column pass (4 rows per lane)
+            // operands of the NEXT pass are fetched while the current one is processed
+            float4 rnext[4], bnext0, bnext1;
+            auto prefetch = [&](int pass) {
+                const int colb = colw + pass * 16 + (f32out ? f_c : h_c);
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                bnext0 = z; bnext1 = z;
+                if (p.bias && colb < p.N) {
+                    bnext0 = *reinterpret_cast<const float4 *>(p.bias + colb);
+                    if (!f32out) bnext1 = *reinterpret_cast<const float4 *>(p.bias + colb + 4);
+                }
+                if (has_res) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int col = colw + pass * 16 + f_c;
-                    rnext[i] = (rok[i] && col < p.N) ? *reinterpret_cast<const float4 *>(rrow[i] + col)
-                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int i = 0; i < 4; ++i)
+                        rnext[i] = (rok[i] && colb < p.N) ? *reinterpret_cast<const float4 *>(rrow[i] + colb) : z;
                 }
             };
-            if (has_res) load_res(0);
+            prefetch(0);
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
+            const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * COLS_PER_WARP);
+            uint32_t v[32];
+            tmem_ld32_issue(tbase, v);
 #pragma unroll 1
             for (int c = 0; c < NCHUNK; ++c) {
-                uint32_t v[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * COLS_PER_WARP + c * 32);
-                tmem_ld32(taddr, v);
+                tmem_ld_wait();
 #pragma unroll
                 for (int ps = 0; ps < 2; ++ps) {
+                    const int pass = c * 2 + ps;
                     float4 rcur[4];
-                    if (has_res) {
+                    const float4 b0 = bnext0, b1 = bnext1;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) rcur[i] = rnext[i];
-                        if (c * 2 + ps + 1 < 2 * NCHUNK) load_res(c * 2 + ps + 1);   // prefetch the next pass
-                    }
+                    for (int i = 0; i < 4; ++i) rcur[i] = rnext[i];
+                    if (pass + 1 < NPASS) prefetch(pass + 1);
                     // stage 32 rows x 16 columns (row = lane)
                     __syncwarp();
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        *reinterpret_cast<float4 *>(stg + lane * STG_PITCH + 4 * j) =
-                            make_float4(__uint_as_float(v[ps * 16 + 4 * j]), __uint_as_float(v[ps * 16 + 4 * j + 1]),
-                                        __uint_as_float(v[ps * 16 + 4 * j + 2]), __uint_as_float(v[ps * 16 + 4 * j + 3]));
+                        sts128(stg + (uint32_t)(lane * STG_PITCH + 4 * j) * 4, __uint_as_float(v[ps * 16 + 4 * j]),
+                               __uint_as_float(v[ps * 16 + 4 * j + 1]), __uint_as_float(v[ps * 16 + 4 * j + 2]),
+                               __uint_as_float(v[ps * 16 + 4 * j + 3]));
+                    if (ps == 1 && c + 1 < NCHUNK) tmem_ld32_issue(tbase + (uint32_t)((c + 1) * 32), v);   // overlaps this pass
                     __syncwarp();
-                    const int col0 = colw + c * 32 + ps * 16;
+                    const int col0 = colw + pass * 16;
                     if (col0 >= p.N) continue;        // warp-uniform (N is a multiple of 8; 16-col passes may be half full)
                     if (f32out) {
                         const int col = col0 + f_c;
                         if (col < p.N) {
-                            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (p.bias) b = *reinterpret_cast<const float4 *>(p.bias + col);
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 if (!rok[i]) continue;
-                                float4 a = *reinterpret_cast<const float4 *>(stg + (f_r + 8 * i) * STG_PITCH + f_c);
-                                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+                                float4 a = lds128(stg + (uint32_t)((f_r + 8 * i) * STG_PITCH + f_c) * 4);
+                                a.x += b0.x; a.y += b0.y; a.z += b0.z; a.w += b0.w;
                                 if (has_res) { a.x += rcur[i].x; a.y += rcur[i].y; a.z += rcur[i].z; a.w += rcur[i].w; }
                                 *reinterpret_cast<float4 *>((float *)p.out + orow[i] * p.ldo + col) = a;
                             }
@@ -315,17 +349,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     } else {
                         const int col = col0 + h_c;
                         if (col < p.N) {
-                            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-                            if (p.bias) {
-                                b0 = *reinterpret_cast<const float4 *>(p.bias + col);
-                                b1 = *reinterpret_cast<const float4 *>(p.bias + col + 4);
-                            }
 #pragma unroll
                             for (int i = 0; i < 2; ++i) {
                                 const int r = row0 + h_r + 16 * i;
                                 if (r >= p.M) continue;
-                                const float4 a0 = *reinterpret_cast<const float4 *>(stg + (h_r + 16 * i) * STG_PITCH + h_c);
-                                const float4 a1 = *reinterpret_cast<const float4 *>(stg + (h_r + 16 * i) * STG_PITCH + h_c + 4);
+                                const float4 a0 = lds128(stg + (uint32_t)((h_r + 16 * i) * STG_PITCH + h_c) * 4);
+                                const float4 a1 = lds128(stg + (uint32_t)((h_r + 16 * i) * STG_PITCH + h_c + 4) * 4);
                                 float f[8] = {a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w,
                                               a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w};
                                 if (p.epi == EC_EPI_BF16_QGELU) {
@@ -399,10 +428,12 @@ template <int BN>
 int launch(const CUtensorMap &ma, const CUtensorMap &mw, GemmParams &p, cudaStream_t stream)
 {
     constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + STG_BYTES + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};   // per device
+    int dev_id = 0;
+    EC_CUDA_CHECK(cudaGetDevice(&dev_id));
+    if (dev_id < 64 && !attr_set[dev_id]) {
         EC_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        attr_set[dev_id] = true;
     }
     p.tiles_m = (p.M + BM - 1) / BM;
     p.tiles_n = (p.N + BN - 1) / BN;

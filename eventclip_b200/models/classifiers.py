@@ -89,60 +89,91 @@ class _CLIPClassifierBase(nn.Module):
     def _adapt(self, full_feats, valid_masks):
         return full_feats
 
-    def _encode_views(self, data_dict):
-        """Returns (feats fp32 [Nv,C] of the valid views in (b,t) order, valid bool [B,T] on the host)."""
-        visual = self.model.visual
-        if "events" in data_dict:
-            if self.event_frontend is None:
-                raise L.ECError("call attach_event_frontend(quantize_args, resolution, max_n) before passing events")
-            fe = self.event_frontend
-            offsets = data_dict["event_offsets"]
-            offsets = offsets.cpu().numpy() if isinstance(offsets, torch.Tensor) else offsets
-            sel = data_dict.get("sel_idx", None)
-            if sel is None:
-                sel = fe.draw_selection(offsets)
-            elif isinstance(sel, torch.Tensor):
-                sel = sel.cpu().numpy()
-            r = fe(data_dict["events"], offsets, sel=sel, out="patch", compact=True, patch=visual.patch_size,
-                   ldk=visual.k_patch)
-            self._last_status = r["status"]
-            feats = visual.forward_patches(r["img"], r["n_valid"])
-            return feats, r["valid_mask"]
-        imgs = data_dict["img"]
-        valid = data_dict["valid_mask"]
-        valid_host = valid.cpu() if isinstance(valid, torch.Tensor) else torch.as_tensor(valid)
-        B, T = valid_host.shape
-        flat = imgs.reshape(B * T, *imgs.shape[2:])
-        if not bool(valid_host.all()):
-            idx = valid_host.reshape(-1).nonzero().squeeze(1).to(flat.device)
-            flat = flat.index_select(0, idx)          # the imgs[valid_masks] gather of clip_cls.py:139
-        return self.get_img_feats(flat), valid_host
-
-    # ---- forward --------------------------------------------------------------------------------------------
-    def forward(self, data_dict):
-        feats, valid = self._encode_views(data_dict)
+    # The events route is split into a host plan and a pure device part so that the latter can be captured in a
+    # CUDA graph (eventclip_b200/graph.py): nothing in device_forward touches the host.
+    def plan_events(self, offsets, sel=None):
+        """Host side of the fused route: chunking + view selection (ec_plan_frames) and the slot map."""
+        if self.event_frontend is None:
+            raise L.ECError("call attach_event_frontend(quantize_args, resolution, max_n) before passing events")
+        fe = self.event_frontend
+        offsets = offsets.cpu().numpy() if isinstance(offsets, torch.Tensor) else offsets
+        if sel is None:
+            sel = fe.draw_selection(offsets)
+        elif isinstance(sel, torch.Tensor):
+            sel = sel.cpu().numpy()
+        frames, valid, chunks, n_valid = ops.plan_frames(offsets, fe.N, fe.max_imgs, sel=sel, compact=True)
         B, T = valid.shape
-        dev = feats.device
         vflat = valid.reshape(-1)
-        if bool(vflat.all()):
-            full = feats
-        else:
+        row_of_slot = None
+        if not bool(vflat.all()):
             row_of_slot = torch.full((B * T,), -1, dtype=torch.int32)
-            row_of_slot[vflat] = torch.arange(int(vflat.sum()), dtype=torch.int32)
-            full = ops.gather_rows(feats, row_of_slot.to(dev, non_blocking=True), B * T)
-        valid_dev = valid.to(dev)
-        full = self._adapt(full.view(B, T, -1), valid_dev).reshape(B * T, -1).contiguous()
+            row_of_slot[vflat] = torch.arange(n_valid, dtype=torch.int32)
+        return dict(frames=frames, valid=valid, valid_u8=valid.to(torch.uint8), row_of_slot=row_of_slot,
+                    n_valid=n_valid, B=B, T=T)
+
+    @staticmethod
+    def plan_to_device(plan, dev):
+        pin = lambda t: t if t.is_pinned() else t.pin_memory()
+        d = dict(plan)
+        d["frames"] = plan["frames"].to(dev, non_blocking=True)
+        d["valid_u8"] = pin(plan["valid_u8"]).to(dev, non_blocking=True)
+        d["valid_dev"] = d["valid_u8"].bool()
+        if plan["row_of_slot"] is not None:
+            d["row_of_slot"] = pin(plan["row_of_slot"]).to(dev, non_blocking=True)
+        return d
+
+    def device_forward(self, events, plan, status=None):
+        """events: CUDA float32 [sum E, 4]; plan: output of plan_to_device.  Enqueues kernels only."""
+        fe, visual = self.event_frontend, self.model.visual
+        patches, st, _ = ops.event2img(events, plan["frames"], fe.resolution, plan["n_valid"], fe.count_non_zero,
+                                       fe.background_mask, out="patch", patch=visual.patch_size, ldk=visual.k_patch,
+                                       status=status)
+        self._last_status = st
+        feats = visual.forward_patches(patches, plan["n_valid"])
+        return self._head(feats, plan)
+
+    def _head(self, feats, plan):
+        B, T = plan["B"], plan["T"]
+        dev = feats.device
+        full = feats if plan["row_of_slot"] is None else ops.gather_rows(feats, plan["row_of_slot"], B * T)
+        full = self._adapt(full.view(B, T, -1), plan["valid_dev"]).reshape(B * T, -1).contiguous()
         text = self.get_text_feats().to(device=dev, dtype=torch.float32).contiguous()
-        full_logits, logits, probs, top = ops.head(full, valid_dev.to(torch.uint8).contiguous(), text, B, T,
-                                                   self.logit_scale, self.normalize_img_feats, self.agg_func)
+        full_logits, logits, probs, top = ops.head(full, plan["valid_u8"], text, B, T, self.logit_scale,
+                                                   self.normalize_img_feats, self.agg_func)
         return {
             "full_logits": full_logits,      # [B, T, n_classes]
-            "valid_masks": valid_dev,        # [B, T]
+            "valid_masks": plan["valid_dev"],  # [B, T]
             "logits": logits,                # [B, n_classes]
             "probs": probs,                  # [B, n_classes]
             "top5_logits": top[:, 0],
             "top5_probs": top[:, 1],
         }
+
+    # ---- forward --------------------------------------------------------------------------------------------
+    def forward(self, data_dict):
+        if "events" in data_dict:
+            plan = self.plan_events(data_dict["event_offsets"], data_dict.get("sel_idx", None))
+            events = data_dict["events"]
+            dev = events.device if events.is_cuda else torch.device("cuda", torch.cuda.current_device())
+            if not events.is_cuda:
+                events = events.to(dev, non_blocking=True)
+            return self.device_forward(events.contiguous(), self.plan_to_device(plan, dev))
+        imgs = data_dict["img"]
+        valid = data_dict["valid_mask"]
+        valid_host = valid.cpu() if isinstance(valid, torch.Tensor) else torch.as_tensor(valid)
+        B, T = valid_host.shape
+        flat = imgs.reshape(B * T, *imgs.shape[2:])
+        vflat = valid_host.reshape(-1)
+        row_of_slot = None
+        if not bool(vflat.all()):
+            idx = vflat.nonzero().squeeze(1)
+            flat = flat.index_select(0, idx.to(flat.device))          # the imgs[valid_masks] gather of clip_cls.py:139
+            row_of_slot = torch.full((B * T,), -1, dtype=torch.int32)
+            row_of_slot[vflat] = torch.arange(idx.numel(), dtype=torch.int32)
+        feats = self.get_img_feats(flat)
+        plan = dict(frames=torch.empty(0, 16, dtype=torch.uint8), valid=valid_host, valid_u8=valid_host.to(torch.uint8),
+                    row_of_slot=row_of_slot, n_valid=int(vflat.sum()), B=B, T=T)
+        return self._head(feats, self.plan_to_device(plan, feats.device))
 
     # ---- losses / metrics (host-side glue; clip_cls.py:164-192) ---------------------------------------------
     def calc_train_loss(self, data_dict, out_dict):

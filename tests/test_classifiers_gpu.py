@@ -194,3 +194,27 @@ def test_events_to_logits_vs_oracle(cuda_dev, ds, arch, B):
     with torch.no_grad():
         o2 = zs(dict(img=imgs.to(cuda_dev), valid_mask=valid.to(cuda_dev)))
     assert torch.equal(o2["logits"], o["logits"])     # same bf16 patch rows either way -> bitwise equal logits
+
+
+def test_cuda_graph_replay_matches_eager(cuda_dev):
+    """GraphedClassifier replays the captured device part; results are bitwise those of the eager launches,
+    across batches and across two different plans (cache of graphs)."""
+    from eventclip_b200.graph import GraphedClassifier
+    cfg = SENSORS["n_caltech101"]
+    q = dict(max_imgs=10, N=cfg["N"], split_method="event_count", convert_method="event_histogram", grayscale=True,
+             count_non_zero=False, background_mask=True)
+    model = clip.init_weights_(clip.CLIP("ViT-tiny/32"), seed=5).to(cuda_dev).eval()
+    text = clip_oracle.synth_text_feats(cfg["n_cls"], 64, 6)
+    zs = ZSCLIPClassifier(clip_dict=dict(clip_model=model, prompt="a {}", class_names=None, agg_func="mean",
+                                         text_feats=text)).to(cuda_dev).eval()
+    zs.attach_event_frontend(q, cfg["shape"], cfg["max_n"])
+    g = GraphedClassifier(zs, max_events=4 * 100000)
+    for seed, E in ((1, 50001), (2, 50001), (3, 100000), (4, 50001)):
+        ev, off = synth_batch("n_caltech101", 3, seed, E=E)
+        d = dict(events=torch.from_numpy(ev).pin_memory(), event_offsets=torch.from_numpy(off))
+        with torch.no_grad():
+            eager = zs(d)
+            got = g(d)
+        for k in ("full_logits", "logits", "probs", "top5_logits"):
+            assert torch.equal(got[k], eager[k]), (seed, k)
+    assert len(g.cache) == 2
