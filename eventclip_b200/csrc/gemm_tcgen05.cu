@@ -6,14 +6,22 @@
 // `@ proj`.  Bias, QuickGELU, the residual add and the positional-embedding add are fused epilogues.
 //
 // Structure (persistent, one CTA per SM, 320 threads):
-//   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of A (128x64) and W (BNx64) tiles, SWIZZLE_128B,
-//               4-stage mbarrier ring
-//   warp 1      MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16),
-//               accumulators in TMEM (2 x BN fp32 columns, double buffered against the epilogue)
-//   warps 2-9   epilogue: tcgen05.ld 32x32b.x32 -> registers -> bias/activation/residual -> global stores
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of A (128x64) and W tiles, SWIZZLE_128B, mbarrier ring
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma kind::f16, accumulators in TMEM
+//               (2 x BN fp32 columns, double buffered against the epilogue)
+//   warps 2-9   epilogue: tcgen05.ld 32x32b.x32 -> registers -> smem transpose -> bias/activation/residual ->
+//               coalesced global stores
+// Two variants of the same code (template parameter CG):
+//   CG = 1  tcgen05.mma.cta_group::1, tile 128 x BN, 4 stages of (16 + BN/8) KB.  Shared-memory traffic per SM is
+//           the TMA fill plus the operand reads of a 128-row MMA: ~192 B/clk at full tensor rate, above the
+//           128 B/clk the SM has, so this variant tops out near 2/3 of peak (measured).
+//   CG = 2  CTA pair (cluster 2x1x1), tcgen05.mma.cta_group::2 with M = 256: each CTA stages its own 128 rows of A
+//           and HALF of the W tile, the pair shares W through the tensor-core datapath, 6 stages of 32 KB.
+//           The leader CTA issues the MMAs; commits are multicast to both CTAs' barriers.
 #include <cuda.h>
 
 #include <mutex>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -21,7 +29,6 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;             // 64 bf16 = 128 bytes = one SWIZZLE_128B atom row
-constexpr int STAGES = 4;
 constexpr int NUM_THREADS = 320;   // 10 warps
 constexpr int EPI_WARPS = 8;
 constexpr int UMMA_K = 16;
@@ -83,6 +90,49 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
+}
+
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-parity bit of a shared::cluster address: leader of the pair
+
+// 2-CTA TMA load: data lands in this CTA's smem, the transaction bytes are credited to the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_2sm(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1)
+        : "memory");
+}
+// arrive on the leader CTA's copy of `bar` (works from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// commit of a cta_group::2 MMA batch, delivered to the same barrier offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
 }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -164,16 +214,21 @@ __device__ __forceinline__ float quick_gelu(float x)
     return __fdividef(x, 1.0f + e);
 }
 
-template <int BN>
+template <int BN, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const GemmParams p)
 {
+    constexpr int STAGES = CG == 2 ? 6 : 4;
     constexpr uint32_t A_BYTES = BM * BK * 2;
-    constexpr uint32_t B_BYTES = BN * BK * 2;
+    constexpr uint32_t B_BYTES = (BN / CG) * BK * 2;         // a CTA of a pair stages half of the W tile
     constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr uint32_t TMEM_COLS = 2 * BN;   // 256 or 512: power of two >= 32
-    // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128
-    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128 per CTA of the group
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
+    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    // persistent schedule: work unit = one (CG*128) x BN output tile per CTA group
+    const int group_id = blockIdx.x / CG, num_groups = gridDim.x / CG;
 
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -192,17 +247,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], EPI_WARPS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], EPI_WARPS * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
-                     "r"(TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                         "r"(TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                         "r"(TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();     // the peer's barriers are initialised before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
 
@@ -210,25 +273,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = group_id; tile < num_tiles; tile += num_groups) {
                 const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char *sa = smem + stage * STAGE_BYTES;
                     unsigned char *sb = sa + A_BYTES;
-                    mbar_expect_tx(&full_bar[stage], p.tx_bytes);
-                    tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, tm * BM);
-                    tma_load_2d(sb, &map_w, &full_bar[stage], kb * BK, tn * BN);
+                    if (CG == 2) {
+                        // both CTAs load their halves; all bytes are credited to the leader's barrier
+                        if (leader) mbar_expect_tx(&full_bar[stage], p.tx_bytes);
+                        tma_load_2d_2sm(sa, &map_a, &full_bar[stage], kb * BK, (tm * CG + (int)cta_rank) * BM);
+                        tma_load_2d_2sm(sb, &map_w, &full_bar[stage], kb * BK, tn * BN + (int)cta_rank * (BN / CG));
+                    } else {
+                        mbar_expect_tx(&full_bar[stage], p.tx_bytes);
+                        tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, tm * BM);
+                        tma_load_2d(sb, &map_w, &full_bar[stage], kb * BK, tn * BN);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (lane == 0 && leader) {
             uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(&tempty_bar[as], aphase ^ 1);   // epilogue has drained this accumulator
+            for (int tile = group_id; tile < num_tiles; tile += num_groups) {
+                mbar_wait(&tempty_bar[as], aphase ^ 1);   // epilogue (of both CTAs) has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -240,10 +310,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
-                        umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
+                        if (CG == 2) umma_bf16_2sm(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
+                        else umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
                     }
-                    umma_commit(&empty_bar[stage]);        // smem slot reusable once these MMAs retire
-                    if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);
+                    // smem slot reusable / accumulator readable once these MMAs retire (in both CTAs of a pair)
+                    if (CG == 2) {
+                        umma_commit_2sm(&empty_bar[stage]);
+                        if (kb == num_kb - 1) umma_commit_2sm(&tfull_bar[as]);
+                    } else {
+                        umma_commit(&empty_bar[stage]);
+                        if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 if (++as == 2) { as = 0; aphase ^= 1; }
@@ -267,9 +344,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         const int h_r = lane >> 1, h_c = (lane & 1) * 8;     // bf16 out: rows h_r + 16i (i<2), cols h_c..h_c+7
         constexpr int NPASS = 2 * NCHUNK;
         uint32_t as = 0, aphase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = group_id; tile < num_tiles; tile += num_groups) {
             const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
-            const int row0 = tm * BM + quarter * 32;
+            const int row0 = (tm * CG + (int)cta_rank) * BM + quarter * 32;
             const int colw = tn * BN + half * COLS_PER_WARP;
             // per-lane output rows / residual rows of the fp32 mapping
             size_t orow[4];
@@ -376,16 +453,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             // all tcgen05.ld of this warp have completed (wait::ld inside tmem_ld32): release the accumulator
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_leader(&tempty_bar[as]);
+                else mbar_arrive(&tempty_bar[as]);
+            }
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
     }
 
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();     // no signal may target a CTA that has already exited
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -424,23 +506,33 @@ int make_map(CUtensorMap *m, const void *base, int rows, int cols, int ld, int b
     return EC_OK;
 }
 
-template <int BN>
+template <int BN, int CG>
 int launch(const CUtensorMap &ma, const CUtensorMap &mw, GemmParams &p, cudaStream_t stream)
 {
-    constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + STG_BYTES + 1024;
+    constexpr int STAGES = CG == 2 ? 6 : 4;
+    constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + (BN / CG) * BK * 2) + STG_BYTES + 1024;
     static bool attr_set[64] = {false};   // per device
     int dev_id = 0;
     EC_CUDA_CHECK(cudaGetDevice(&dev_id));
     if (dev_id < 64 && !attr_set[dev_id]) {
-        EC_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        EC_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[dev_id] = true;
     }
-    p.tiles_m = (p.M + BM - 1) / BM;
+    p.tiles_m = (p.M + BM * CG - 1) / (BM * CG);
     p.tiles_n = (p.N + BN - 1) / BN;
     const int tiles = p.tiles_m * p.tiles_n;
-    const int grid = tiles < ec::sm_count() ? tiles : ec::sm_count();
-    gemm_kernel<BN><<<grid, NUM_THREADS, smem, stream>>>(ma, mw, p);
-    EC_CUDA_CHECK(cudaGetLastError());
+    const int max_groups = ec::sm_count() / CG;
+    const int groups = tiles < max_groups ? tiles : max_groups;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(groups * CG));
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    EC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, CG>, ma, mw, p));
     return EC_OK;
 }
 
@@ -462,8 +554,11 @@ extern "C" int ec_gemm_bf16(const void *A, int lda, const void *W, int ldw, cons
     if (epi == EC_EPI_PATCH) EC_REQUIRE(row_map > 0 && M % row_map == 0, "ec_gemm_bf16: bad row_map %d", row_map);
 
     const int BN = (N % 256 == 0) ? 256 : 128;
+    // CTA pairs (cta_group::2, 256 x 256 tiles) whenever the shape fills them; EC_GEMM_CG=1 forces the single-CTA kernel
+    static const int force_cg = getenv("EC_GEMM_CG") ? atoi(getenv("EC_GEMM_CG")) : 0;
+    const int CG = (force_cg == 1 || BN != 256 || M < 2 * BM) ? 1 : 2;
     const int box_a = M < BM ? M : BM;
-    const int box_w = N < BN ? N : BN;
+    const int box_w = CG == 2 ? BN / 2 : (N < BN ? N : BN);
     CUtensorMap ma, mw;
     int rc = make_map(&ma, A, M, K, lda, box_a);
     if (rc != EC_OK) return rc;
@@ -472,6 +567,7 @@ extern "C" int ec_gemm_bf16(const void *A, int lda, const void *W, int ldw, cons
 
     GemmParams p;
     p.M = M; p.N = N; p.K = K; p.epi = epi; p.out = out; p.ldo = ldo; p.bias = bias; p.res = res; p.row_map = row_map;
-    p.tx_bytes = (uint32_t)(box_a + box_w) * BK * 2;
-    return BN == 256 ? launch<256>(ma, mw, p, stream) : launch<128>(ma, mw, p, stream);
+    p.tx_bytes = (uint32_t)(box_a + box_w) * BK * 2 * CG;   // a pair's leader barrier collects both CTAs' bytes
+    if (CG == 2) return launch<256, 2>(ma, mw, p, stream);
+    return BN == 256 ? launch<256, 1>(ma, mw, p, stream) : launch<128, 1>(ma, mw, p, stream);
 }

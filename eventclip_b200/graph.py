@@ -42,8 +42,11 @@ class GraphedClassifier:
         torch.cuda.current_stream(self.dev).wait_stream(side)
         torch.cuda.synchronize(self.dev)
         e.graph = torch.cuda.CUDAGraph()
+        n0 = L.LAUNCHES
         with torch.cuda.graph(e.graph), torch.no_grad():
             e.out = self.model.device_forward(self.events, e.plan, status=self.status)
+        e.n_launch = L.LAUNCHES - n0          # kernel nodes of the graph
+        L.LAUNCHES = n0                       # capture enqueued nothing
         return e
 
     def __call__(self, data_dict):
@@ -62,4 +65,5 @@ class GraphedClassifier:
             ent = self.cache[key] = self._build(plan)
         self.events[:n].copy_(ev, non_blocking=True)
         ent.graph.replay()
+        L.LAUNCHES += ent.n_launch
         return ent.out
