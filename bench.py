@@ -166,7 +166,8 @@ def event2img_metric(dev, pk):
     from eventclip_b200.datasets import Event2Image
     from eventclip_b200.synth import SENSORS, synth_batch
     out = {}
-    for ds, B, reps in (("n_caltech101", 128, 5), ("n_cars", 2048, 5), ("n_imagenet", 32, 3)):
+    # batch sizes give whole waves of clusters on 148 SMs (1480 / 2072 / 296 frames) and inputs far beyond L2
+    for ds, B, reps in (("n_caltech101", 296, 5), ("n_cars", 2072, 5), ("n_imagenet", 144, 3)):
         cfg = SENSORS[ds]
         e2i = Event2Image(qargs(cfg), cfg["shape"], cfg["max_n"])
         ev1, off1 = synth_batch(ds, 8, 100)

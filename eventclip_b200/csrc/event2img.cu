@@ -44,6 +44,7 @@ struct E2IParams {
     uint8_t *dbg_gray;
     uint8_t *dbg_u8;
     int32_t *status;
+    unsigned long long band_magic; // ceil(2^40 / (RB*W)): flat index -> owning CTA by multiply-shift
     const int32_t *hx;   // [224][2+KH]: lo, cnt, taps  (cropped output columns)
     const int32_t *vy;   // [224][2+KV]: lo, cnt, taps  (cropped output rows)
     const float *nlut;   // [3][256] normalise LUT
@@ -165,14 +166,20 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
     __shared__ unsigned s_keep, s_mx, s_mall;
     __shared__ uint8_t glut[GLUT_N * GLUT_N];
     __shared__ float nlut[768];
-    __shared__ __nv_bfloat16 nlut16[768];
+    __shared__ uint2 nlut3[256];                 // bf16 (c0, c1, c2, 0) of each uint8 value: one 8-byte load per pixel
+    __shared__ int vtab[OUT * (2 + 11)];         // vertical taps (lo, cnt, k[]) when KV <= 11
     __shared__ short ypq[OUT], ypr[OUT], xpq[OUT / 2], xpr[OUT / 2];   // patch coordinates of output rows / column pairs
 
-    for (int i = tid; i < 768; i += NT) {
-        const float f = p.nlut[i];
-        nlut[i] = f;
-        nlut16[i] = __float2bfloat16_rn(f);
+    for (int i = tid; i < 768; i += NT) nlut[i] = p.nlut[i];
+    for (int i = tid; i < 256; i += NT) {
+        const __nv_bfloat162 c01 = __floats2bfloat162_rn(p.nlut[i], p.nlut[256 + i]);
+        const __nv_bfloat162 c2z = __floats2bfloat162_rn(p.nlut[512 + i], 0.f);
+        nlut3[i] = make_uint2(*reinterpret_cast<const uint32_t *>(&c01), *reinterpret_cast<const uint32_t *>(&c2z));
     }
+    const bool vsm = p.KV <= 11;
+    if (vsm)
+        for (int i = tid; i < OUT * (2 + p.KV); i += NT) vtab[i] = p.vy[i];
+    const int *vy = vsm ? vtab : p.vy;
     if (p.out_fmt == EC_OUT_BF16_PATCH) {
         const int P = p.patch;
         for (int i = tid; i < OUT; i += NT) { ypq[i] = (short)(i / P); ypr[i] = (short)(i % P); }
@@ -209,57 +216,79 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
         const int n4 = (nband + 3) >> 2;
         for (int i = tid; i < n4; i += NT) h4[i] = make_uint4(0, 0, 0, 0);
     }
-    __syncthreads();
+    if (CS > 1) cluster.sync(); else __syncthreads();
 
     // ---- P1: scan events; returning atomics give the statistics for free:
-    //      adding 1 to a bin holding c raises sum(c^2) by 2c+1 and the non-empty count by [c == 0] ----
+    //      adding 1 to a bin holding c raises sum(c^2) by 2c+1 and the non-empty count by [c == 0].
+    //      In a multi-CTA cluster every CTA scans 1/CS of the frame's events and routes each one to the CTA that
+    //      owns its sensor row with a distributed-shared-memory atomic (no event is read twice). ----
     unsigned long long s2 = 0;
     unsigned nnz = 0, nacc = 0, mall = 0, flags = 0;
     {
-        const float4 *ev = p.events + fr.ev_start;
-        const int n = fr.ev_count;
-        const int iband_lo = (int)band_lo, iHW = (int)HW;
-        for (int base = 0; base < n; base += NT * 4) {
-            float4 e[4];
+        // this CTA's slice of the frame's events
+        const int per = (fr.ev_count + CS - 1) / CS;
+        const int e_lo = min(rank * per, fr.ev_count);
+        const int n = min(per, fr.ev_count - e_lo);
+        const float4 *ev = p.events + fr.ev_start + e_lo;
+        const int iHW = (int)HW, bandpx = RB * W;
+        constexpr int U = 4;   // events in flight per thread: all loads, then all atomics, then the statistics
+        for (int base = 0; base < n; base += NT * U) {
+            float4 ev4[U];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const int i = base + u * NT + tid;
-                if (i < n) e[u] = ld_stream(ev + i);
+                if (i < n) ev4[u] = ld_stream(ev + i);
             }
-            unsigned s2p = 0;   // <= 4 * (2*65535 + 1): no 32-bit overflow within one round
+            unsigned code[U];   // bit 31: valid, bit 30: positive polarity, low bits: flat pixel index
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const int i = base + u * NT + tid;
+                code[u] = 0;
                 if (i < n) {
-                    const int x = __float2int_rz(e[u].x), y = __float2int_rz(e[u].y);
-                    const int pol = __float2int_rz(e[u].w);
+                    const float4 e = ev4[u];
+                    const int x = __float2int_rz(e.x), y = __float2int_rz(e.y), pol = __float2int_rz(e.w);
                     if (pol != 0) {
                         // flat index as np.bincount sees it; 32-bit math when it provably cannot overflow
-                        int idx;
+                        unsigned l;
                         bool ok;
-                        if ((unsigned)(x + 32768) < 65536u && (unsigned)(y + 32768) < 65536u && W < 32768) {
-                            idx = x + y * W;
-                            ok = (unsigned)idx < (unsigned)iHW;
+                        if (((unsigned)x | (unsigned)y) < 32768u && W < 32768) {
+                            l = (unsigned)(y * W + x);
+                            ok = l < (unsigned)iHW;
                         } else {
                             const long long i64 = (long long)x + (long long)y * W;
                             ok = i64 >= 0 && i64 < HW;
-                            idx = (int)i64;
+                            l = (unsigned)i64;
                         }
-                        if (!ok) {
-                            flags |= EC_STATUS_BAD_COORD;
-                        } else {
-                            const unsigned l = (unsigned)(idx - iband_lo);
-                            if (l < (unsigned)nband) {
-                                const uint32_t old = atomicAdd(&hist[l], pol > 0 ? 1u : 65536u);
-                                const uint32_t c = pol > 0 ? (old & 0xffffu) : (old >> 16);
-                                if (c == 0xffffu) flags |= EC_STATUS_COUNT_OVERFLOW;   // the 16-bit field wraps
-                                s2p += 2u * c + 1u;
-                                nnz += (c == 0);
-                                mall = max(mall, c + 1);
-                                ++nacc;
-                            }
-                        }
+                        if (ok) code[u] = 0x80000000u | (pol > 0 ? 0x40000000u : 0u) | l;
+                        else flags |= EC_STATUS_BAD_COORD;
                     }
+                }
+            }
+            uint32_t old[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                old[u] = 0;
+                if (code[u] & 0x80000000u) {
+                    unsigned l = code[u] & 0x3fffffffu;
+                    uint32_t *dst = hist;
+                    if (CS > 1) {
+                        const unsigned owner = (unsigned)(((unsigned long long)l * p.band_magic) >> 40);   // l / (RB*W), exact for l < 2^24
+                        l -= owner * (unsigned)bandpx;
+                        dst = cluster.map_shared_rank(hist, owner);
+                    }
+                    old[u] = atomicAdd(dst + l, (code[u] & 0x40000000u) ? 1u : 65536u);
+                }
+            }
+            unsigned s2p = 0;   // <= 4 * (2*65535 + 1): no 32-bit overflow within one round
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (code[u] & 0x80000000u) {
+                    const uint32_t c = (code[u] & 0x40000000u) ? (old[u] & 0xffffu) : (old[u] >> 16);
+                    if (c == 0xffffu) flags |= EC_STATUS_COUNT_OVERFLOW;   // the 16-bit field wraps
+                    s2p += 2u * c + 1u;
+                    nnz += (c == 0);
+                    mall = max(mall, c + 1);
+                    ++nacc;
                 }
             }
             s2 += s2p;
@@ -296,15 +325,25 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
     __syncthreads();
     const unsigned keep = s_keep;
     unsigned mx = s_mall;
+    const bool hot = mx > keep;
 
     // ---- P3 (only when some bin exceeds `keep`): max of the surviving bins ----
-    if (mx > keep) {   // uniform across the cluster: s_keep / s_mall derive from the same cluster totals
+    if (hot) {   // uniform across the cluster: s_keep / s_mall derive from the same cluster totals
         unsigned m = 0;
-        for (int i = tid; i < nband; i += NT) {
-            const uint32_t w = hist[i];
-            const uint32_t a = w & 0xffffu, b = w >> 16;
-            if (a <= keep) m = max(m, a);
-            if (b <= keep) m = max(m, b);
+        {
+            const uint4 *h4 = reinterpret_cast<const uint4 *>(hist);   // words past nband are zero (P0 cleared them)
+            const int n4 = (nband + 3) >> 2;
+            for (int i = tid; i < n4; i += NT) {
+                const uint4 w4 = h4[i];
+                if ((w4.x | w4.y | w4.z | w4.w) == 0) continue;
+                const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t a = ws[q] & 0xffffu, b = ws[q] >> 16;
+                    if (a <= keep) m = max(m, a);
+                    if (b <= keep) m = max(m, b);
+                }
+            }
         }
         m = warp_max_u32(m);
         if (lane == 0) red32[wid][0] = m;
@@ -339,16 +378,23 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
             if (j < ng) {
                 const uint4 w4 = h4[j];
                 const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
+                if (!DBG && (w4.x | w4.y | w4.z | w4.w) == 0) {
+                    pk = 0x01010101u * glut[0];          // four empty pixels
+                } else
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    uint32_t a = ws[q] & 0xffffu, b = ws[q] >> 16;
+                    uint32_t w = ws[q];
                     if (DBG && p.dbg_counts && 4 * j + q < nband) {
                         int32_t *dc = p.dbg_counts + ((size_t)fid * HW + band_lo + 4 * j + q) * 2;
-                        dc[0] = (int32_t)a; dc[1] = (int32_t)b;
+                        dc[0] = (int32_t)(w & 0xffffu); dc[1] = (int32_t)(w >> 16);
                     }
-                    if (a > keep) a = 0;
-                    if (b > keep) b = 0;
-                    const unsigned g = ((a | b) < GLUT_N) ? glut[b * GLUT_N + a] : gray_px(a, b, mx, mask);
+                    if (hot) {   // some bin exceeds the cut (uniform): remove those fields
+                        if ((w & 0xffffu) > keep) w &= 0xffff0000u;
+                        if ((w >> 16) > keep) w &= 0x0000ffffu;
+                    }
+                    unsigned g;
+                    if ((w & 0xffe0ffe0u) == 0) g = glut[((w >> 11) & 0x3e0u) | (w & 0x1fu)];   // both counts < 32
+                    else g = gray_px(w & 0xffffu, w >> 16, mx, mask);
                     pk |= g << (8 * q);
                 }
             }
@@ -371,18 +417,18 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
             const int32_t *tab = p.hx + x * (2 + p.KH);
             const int lo = __ldg(tab), cnt = __ldg(tab + 1);
             if (KHMAX > 0) {
-                int k[KHMAX > 0 ? KHMAX : 1], off[KHMAX > 0 ? KHMAX : 1];
+                // taps beyond cnt carry weight 0 and read at most KHMAX-1 bytes past the row: still inside the buffer
+                int k[KHMAX > 0 ? KHMAX : 1];
 #pragma unroll
-                for (int t = 0; t < KHMAX; ++t) {
-                    k[t] = t < cnt ? __ldg(tab + 2 + t) : 0;
-                    off[t] = min(lo + t, W - 1);
-                }
-                for (int y = rg; y < rows; y += RG) {
-                    const uint8_t *src = gray + y * W;
+                for (int t = 0; t < KHMAX; ++t) k[t] = t < cnt ? __ldg(tab + 2 + t) : 0;
+                const uint8_t *src = gray + rg * W + lo;
+                uint8_t *dst = hrow + rg * OUT + x;
+                const int sstep = RG * W, dstep = RG * OUT;
+                for (int y = rg; y < rows; y += RG, src += sstep, dst += dstep) {
                     int ss = 1 << (PREC - 1);
 #pragma unroll
-                    for (int t = 0; t < KHMAX; ++t) ss += (int)src[off[t]] * k[t];
-                    hrow[y * OUT + x] = (uint8_t)clip8(ss);
+                    for (int t = 0; t < KHMAX; ++t) ss += (int)src[t] * k[t];
+                    *dst = (uint8_t)clip8(ss);
                 }
             } else {
                 for (int y = rg; y < rows; y += RG) {
@@ -407,21 +453,33 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
             const int items = (yo_end - yo_begin) * NG;
             for (int it = tid; it < items; it += NT) {
                 const int yo = yo_begin + it / NG, xg = it % NG;
-                const int32_t *tab = p.vy + yo * stride;
-                const int lo = __ldg(tab), cnt = __ldg(tab + 1);
+                const int *tab = vy + yo * stride;
+                const int lo = tab[0], cnt = tab[1];
                 int acc[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc[j] = 1 << (PREC - 1);
-                int own = lo / RB, rin = lo - own * RB;
-                const uint8_t *base = (own == rank) ? hrow : cluster.map_shared_rank(hrow, own);
-                for (int t = 0; t < cnt; ++t) {
-                    const uint2 v = *reinterpret_cast<const uint2 *>(base + rin * OUT + xg * 8);
-                    const int k = __ldg(tab + 2 + t);
-                    acc[0] += (int)(v.x & 0xffu) * k;          acc[1] += (int)((v.x >> 8) & 0xffu) * k;
-                    acc[2] += (int)((v.x >> 16) & 0xffu) * k;  acc[3] += (int)(v.x >> 24) * k;
-                    acc[4] += (int)(v.y & 0xffu) * k;          acc[5] += (int)((v.y >> 8) & 0xffu) * k;
-                    acc[6] += (int)((v.y >> 16) & 0xffu) * k;  acc[7] += (int)(v.y >> 24) * k;
-                    if (++rin == RB) { rin = 0; ++own; base = (own == rank) ? hrow : cluster.map_shared_rank(hrow, own); }
+                if (CS == 1) {
+                    const uint8_t *src = hrow + lo * OUT + xg * 8;
+                    for (int t = 0; t < cnt; ++t, src += OUT) {
+                        const uint2 v = *reinterpret_cast<const uint2 *>(src);
+                        const int k = tab[2 + t];
+                        acc[0] += (int)__byte_perm(v.x, 0, 0x4440) * k; acc[1] += (int)__byte_perm(v.x, 0, 0x4441) * k;
+                        acc[2] += (int)__byte_perm(v.x, 0, 0x4442) * k; acc[3] += (int)__byte_perm(v.x, 0, 0x4443) * k;
+                        acc[4] += (int)__byte_perm(v.y, 0, 0x4440) * k; acc[5] += (int)__byte_perm(v.y, 0, 0x4441) * k;
+                        acc[6] += (int)__byte_perm(v.y, 0, 0x4442) * k; acc[7] += (int)__byte_perm(v.y, 0, 0x4443) * k;
+                    }
+                } else {
+                    int own = lo / RB, rin = lo - own * RB;
+                    const uint8_t *base = (own == rank) ? hrow : cluster.map_shared_rank(hrow, own);
+                    for (int t = 0; t < cnt; ++t) {
+                        const uint2 v = *reinterpret_cast<const uint2 *>(base + rin * OUT + xg * 8);
+                        const int k = tab[2 + t];
+                        acc[0] += (int)__byte_perm(v.x, 0, 0x4440) * k; acc[1] += (int)__byte_perm(v.x, 0, 0x4441) * k;
+                        acc[2] += (int)__byte_perm(v.x, 0, 0x4442) * k; acc[3] += (int)__byte_perm(v.x, 0, 0x4443) * k;
+                        acc[4] += (int)__byte_perm(v.y, 0, 0x4440) * k; acc[5] += (int)__byte_perm(v.y, 0, 0x4441) * k;
+                        acc[6] += (int)__byte_perm(v.y, 0, 0x4442) * k; acc[7] += (int)__byte_perm(v.y, 0, 0x4443) * k;
+                        if (++rin == RB) { rin = 0; ++own; base = (own == rank) ? hrow : cluster.map_shared_rank(hrow, own); }
+                    }
                 }
                 unsigned v8[8];
 #pragma unroll
@@ -442,8 +500,16 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
                         *reinterpret_cast<float4 *>(o + 4) = make_float4(nl[v8[4]], nl[v8[5]], nl[v8[6]], nl[v8[7]]);
                     }
                 } else {
-                    size_t obase;
-                    size_t cstride;
+                    // bf16: one 8-byte LUT read per pixel yields all three channels
+                    uint2 t8[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) t8[j] = nlut3[v8[j]];
+                    uint4 o0, o1, o2;
+                    o0.x = __byte_perm(t8[0].x, t8[1].x, 0x5410); o1.x = __byte_perm(t8[0].x, t8[1].x, 0x7632); o2.x = __byte_perm(t8[0].y, t8[1].y, 0x5410);
+                    o0.y = __byte_perm(t8[2].x, t8[3].x, 0x5410); o1.y = __byte_perm(t8[2].x, t8[3].x, 0x7632); o2.y = __byte_perm(t8[2].y, t8[3].y, 0x5410);
+                    o0.z = __byte_perm(t8[4].x, t8[5].x, 0x5410); o1.z = __byte_perm(t8[4].x, t8[5].x, 0x7632); o2.z = __byte_perm(t8[4].y, t8[5].y, 0x5410);
+                    o0.w = __byte_perm(t8[6].x, t8[7].x, 0x5410); o1.w = __byte_perm(t8[6].x, t8[7].x, 0x7632); o2.w = __byte_perm(t8[6].y, t8[7].y, 0x5410);
+                    size_t obase, cstride;
                     if (p.out_fmt == EC_OUT_BF16_NCHW) {
                         obase = (((size_t)slot * 3) * OUT + yo) * OUT + x;
                         cstride = (size_t)OUT * OUT;
@@ -452,16 +518,10 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
                         obase = ((size_t)slot * p.G * p.G + (size_t)ypq[yo] * p.G + xpq[x >> 1]) * p.ldk + ypr[yo] * P + xpr[x >> 1];
                         cstride = (size_t)P * P;
                     }
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const unsigned short *nl = reinterpret_cast<const unsigned short *>(nlut16) + c * 256;
-                        uint4 o;
-                        o.x = (unsigned)nl[v8[0]] | ((unsigned)nl[v8[1]] << 16);
-                        o.y = (unsigned)nl[v8[2]] | ((unsigned)nl[v8[3]] << 16);
-                        o.z = (unsigned)nl[v8[4]] | ((unsigned)nl[v8[5]] << 16);
-                        o.w = (unsigned)nl[v8[6]] | ((unsigned)nl[v8[7]] << 16);
-                        *reinterpret_cast<uint4 *>((__nv_bfloat16 *)p.out + obase + c * cstride) = o;
-                    }
+                    __nv_bfloat16 *ob = (__nv_bfloat16 *)p.out + obase;
+                    *reinterpret_cast<uint4 *>(ob) = o0;
+                    *reinterpret_cast<uint4 *>(ob + cstride) = o1;
+                    *reinterpret_cast<uint4 *>(ob + 2 * cstride) = o2;
                 }
             }
         } else {
@@ -470,14 +530,14 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
             const int items = (yo_end - yo_begin) * (OUT / 2);
             for (int it = tid; it < items; it += NT) {
                 const int yo = yo_begin + it / (OUT / 2), xp = it % (OUT / 2), x = 2 * xp;
-                const int32_t *tab = p.vy + yo * stride;
-                const int lo = __ldg(tab), cnt = __ldg(tab + 1);
+                const int *tab = vy + yo * stride;
+                const int lo = tab[0], cnt = tab[1];
                 int s0 = 1 << (PREC - 1), s1 = s0;
                 int own = lo / RB, rin = lo - own * RB;
                 const uint8_t *base = (own == rank) ? hrow : cluster.map_shared_rank(hrow, own);
                 for (int t = 0; t < cnt; ++t) {
                     const unsigned two = *reinterpret_cast<const uint16_t *>(base + rin * OUT + x);
-                    const int k = __ldg(tab + 2 + t);
+                    const int k = tab[2 + t];
                     s0 += (int)(two & 0xffu) * k;
                     s1 += (int)(two >> 8) * k;
                     if (++rin == RB) { rin = 0; ++own; base = (own == rank) ? hrow : cluster.map_shared_rank(hrow, own); }
@@ -485,12 +545,11 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
                 const unsigned v0 = clip8(s0), v1 = clip8(s1);
                 if (du) { du[yo * OUT + x] = (uint8_t)v0; du[yo * OUT + x + 1] = (uint8_t)v1; }
                 const size_t obase = ((size_t)slot * p.G * p.G + (size_t)ypq[yo] * p.G + xpq[xp]) * p.ldk + ypr[yo] * P + xpr[xp];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const unsigned short *nl = reinterpret_cast<const unsigned short *>(nlut16) + c * 256;
-                    *reinterpret_cast<unsigned *>((__nv_bfloat16 *)p.out + obase + (size_t)c * P * P) =
-                        (unsigned)nl[v0] | ((unsigned)nl[v1] << 16);
-                }
+                const uint2 t0 = nlut3[v0], t1 = nlut3[v1];
+                __nv_bfloat16 *ob = (__nv_bfloat16 *)p.out + obase;
+                *reinterpret_cast<unsigned *>(ob) = __byte_perm(t0.x, t1.x, 0x5410);
+                *reinterpret_cast<unsigned *>(ob + (size_t)P * P) = __byte_perm(t0.x, t1.x, 0x7632);
+                *reinterpret_cast<unsigned *>(ob + 2 * (size_t)P * P) = __byte_perm(t0.y, t1.y, 0x5410);
             }
         }
     }
@@ -603,7 +662,7 @@ int get_tables(int H, int W, cudaStream_t stream, Tables &out)
 
 int geometry(int H, int W, int &CS, int &RB, int &NT, size_t &smem)
 {
-    const size_t budget = 216 * 1024;   // 227 KB per CTA minus ~9 KB of static shared memory (LUTs, tables)
+    const size_t budget = 206 * 1024;   // 227 KB per CTA minus ~20 KB of static shared memory (LUTs, tap tables)
     // bins (4 bytes/pixel) are later reused as gray bytes (1 byte/pixel) followed by the 224-byte resampled rows
     const size_t per_row = (size_t)W * 4 > (size_t)W + OUT + 16 ? (size_t)W * 4 : (size_t)W + OUT + 16;
     const int rb_max = (int)(budget / per_row);
@@ -669,6 +728,7 @@ extern "C" int ec_event2img(const float *events, const ec_frame *frames, int n_f
     p.out = out; p.dbg_counts = dbg_counts; p.dbg_gray = dbg_gray; p.dbg_u8 = dbg_u8; p.status = status;
     p.hx = tb.dev; p.vy = tb.dev + tb.off_vy; p.nlut = reinterpret_cast<const float *>(tb.dev + tb.off_lut);
     p.KH = tb.KH; p.KV = tb.KV;
+    p.band_magic = ((1ull << 40) + (unsigned long long)RB * W - 1) / ((unsigned long long)RB * W);
 
     const bool dbg = dbg_counts || dbg_gray || dbg_u8;
     auto kern = dbg ? (tb.KH <= 5 ? event2img_kernel<5, true> : (tb.KH <= 11 ? event2img_kernel<11, true> : event2img_kernel<0, true>))
