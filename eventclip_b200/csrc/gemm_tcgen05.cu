@@ -135,6 +135,19 @@ __device__ __forceinline__ uint32_t cluster_ctarank()
     return r;
 }
 
+// One lane of a converged warp.  Role loops run warp-wide and only the asynchronous instruction itself is elected:
+// descriptors / coordinates stay in uniform registers instead of being re-broadcast around every issue.
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t.reg .b32 rx;\n\t"
+        "elect.sync rx|P1, 0xffffffff;\n\t"
+        "@P1 mov.s32 %0, 1;\n\t}"
+        : "+r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -271,7 +284,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        {
             uint32_t stage = 0, phase = 0;
             for (int tile = group_id; tile < num_tiles; tile += num_groups) {
                 const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
@@ -279,23 +292,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char *sa = smem + stage * STAGE_BYTES;
                     unsigned char *sb = sa + A_BYTES;
-                    if (CG == 2) {
-                        // both CTAs load their halves; all bytes are credited to the leader's barrier
-                        if (leader) mbar_expect_tx(&full_bar[stage], p.tx_bytes);
-                        tma_load_2d_2sm(sa, &map_a, &full_bar[stage], kb * BK, (tm * CG + (int)cta_rank) * BM);
-                        tma_load_2d_2sm(sb, &map_w, &full_bar[stage], kb * BK, tn * BN + (int)cta_rank * (BN / CG));
-                    } else {
-                        mbar_expect_tx(&full_bar[stage], p.tx_bytes);
-                        tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, tm * BM);
-                        tma_load_2d(sb, &map_w, &full_bar[stage], kb * BK, tn * BN);
+                    if (elect_one()) {
+                        if (CG == 2) {
+                            // both CTAs load their halves; all bytes are credited to the leader's barrier
+                            if (leader) mbar_expect_tx(&full_bar[stage], p.tx_bytes);
+                            tma_load_2d_2sm(sa, &map_a, &full_bar[stage], kb * BK, (tm * CG + (int)cta_rank) * BM);
+                            tma_load_2d_2sm(sb, &map_w, &full_bar[stage], kb * BK, tn * BN + (int)cta_rank * (BN / CG));
+                        } else {
+                            mbar_expect_tx(&full_bar[stage], p.tx_bytes);
+                            tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, tm * BM);
+                            tma_load_2d(sb, &map_w, &full_bar[stage], kb * BK, tn * BN);
+                        }
                     }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0 && leader) {
+        if (leader) {
             uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
             for (int tile = group_id; tile < num_tiles; tile += num_groups) {
                 mbar_wait(&tempty_bar[as], aphase ^ 1);   // epilogue (of both CTAs) has drained this accumulator
@@ -307,20 +323,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                     const uint64_t adesc = make_smem_desc(sa);
                     const uint64_t bdesc = make_smem_desc(sa + A_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
-                        if (CG == 2) umma_bf16_2sm(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
-                        else umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
+                            if (CG == 2) umma_bf16_2sm(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
+                            else umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
+                        }
+                        // smem slot reusable / accumulator readable once these MMAs retire (in both CTAs of a pair)
+                        if (CG == 2) {
+                            umma_commit_2sm(&empty_bar[stage]);
+                            if (kb == num_kb - 1) umma_commit_2sm(&tfull_bar[as]);
+                        } else {
+                            umma_commit(&empty_bar[stage]);
+                            if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);
+                        }
                     }
-                    // smem slot reusable / accumulator readable once these MMAs retire (in both CTAs of a pair)
-                    if (CG == 2) {
-                        umma_commit_2sm(&empty_bar[stage]);
-                        if (kb == num_kb - 1) umma_commit_2sm(&tfull_bar[as]);
-                    } else {
-                        umma_commit(&empty_bar[stage]);
-                        if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);
-                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 if (++as == 2) { as = 0; aphase ^= 1; }
