@@ -33,7 +33,8 @@ constexpr int NUM_THREADS = 320;   // 10 warps
 constexpr int EPI_WARPS = 8;
 constexpr int UMMA_K = 16;
 constexpr int STG_PITCH = 20;       // floats per row of an epilogue warp's 32x16 staging tile (80 B: conflict-free)
-constexpr int STG_BYTES = EPI_WARPS * 32 * STG_PITCH * 4;
+constexpr int STG_WARP_BYTES = 4096;  // per epilogue warp: fp32 transpose tile (2560 B) or two bf16 TMA-store boxes (2 x 2048 B)
+constexpr int STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
 
 struct GemmParams {
     int M, N, K;
@@ -220,16 +221,38 @@ __device__ __forceinline__ float4 lds128(uint32_t addr)
     return r;
 }
 
+// TMA store of a [32 rows x 32 bf16] box (SWIZZLE_64B staging) and its bulk-group bookkeeping
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t smem_addr, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_addr), "r"(c0), "r"(c1)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 __device__ __forceinline__ float quick_gelu(float x)
 {
-    // x * sigmoid(1.702 x) = x / (1 + 2^(-1.702 * log2(e) * x))
-    const float e = exp2f(-2.4554669595930157f * x);
-    return __fdividef(x, 1.0f + e);
+    // x * sigmoid(1.702 x) with sigmoid(y) = 0.5 tanh(y/2) + 0.5: one SFU op (MUFU.TANH) per element instead of
+    // ex2 + rcp -- the c_fc epilogue is SFU-bound otherwise.  tanh.approx error (~2^-11) is far below bf16 rounding.
+    const float h = 0.5f * x;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(1.702f * h));
+    return fmaf(h, t, h);
 }
 
 template <int BN, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const GemmParams p)
+gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+            const __grid_constant__ CUtensorMap map_o, const GemmParams p)
 {
     constexpr int STAGES = CG == 2 ? 6 : 4;
     constexpr uint32_t A_BYTES = BM * BK * 2;
@@ -259,6 +282,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_o) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], EPI_WARPS * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -355,8 +379,65 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         const int half = ew >> 2;          // which half of the BN columns
         constexpr int COLS_PER_WARP = BN / 2;
         constexpr int NCHUNK = COLS_PER_WARP / 32;
-        const uint32_t stg = smem_u32(smem + STAGES * STAGE_BYTES) + (uint32_t)ew * (32 * STG_PITCH * 4);   // shared-space address
+        const uint32_t stg = smem_u32(smem + STAGES * STAGE_BYTES) + (uint32_t)ew * STG_WARP_BYTES;   // shared-space address
         const bool f32out = p.epi >= EC_EPI_F32_RESADD;
+        if (!f32out) {
+            // ---- bf16 outputs (in_proj, c_fc): bias / QuickGELU in registers (thread = row), packed rows staged in a
+            //      64B-swizzled [32 x 32] box, one elected lane hands the box to the TMA store engine.  Two boxes per
+            //      warp alternate; cp.async.bulk.wait_group.read guards their reuse.  Rows >= M and columns >= N are
+            //      clipped by the tensor map. ----
+            uint32_t as = 0, aphase = 0, nbox = 0;
+            for (int tile = group_id; tile < num_tiles; tile += num_groups) {
+                const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+                const int row0 = (tm * CG + (int)cta_rank) * BM + quarter * 32;
+                const int colw = tn * BN + half * COLS_PER_WARP;
+                mbar_wait(&tfull_bar[as], aphase);
+                tc_fence_after();
+                const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * COLS_PER_WARP);
+                uint32_t v[32];
+                tmem_ld32_issue(tbase, v);
+#pragma unroll 1
+                for (int c = 0; c < NCHUNK; ++c) {
+                    const int col0 = colw + c * 32;
+                    // lane j holds the bias of column col0 + j; broadcast by shuffle below
+                    float bl = 0.f;
+                    if (p.bias && col0 + lane < p.N) bl = p.bias[col0 + lane];
+                    tmem_ld_wait();
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        float f0 = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bl, j);
+                        float f1 = __uint_as_float(v[j + 1]) + __shfl_sync(0xffffffffu, bl, j + 1);
+                        if (p.epi == EC_EPI_BF16_QGELU) { f0 = quick_gelu(f0); f1 = quick_gelu(f1); }
+                        __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+                        pk[j >> 1] = *reinterpret_cast<uint32_t *>(&h);
+                    }
+                    if (c + 1 < NCHUNK) tmem_ld32_issue(tbase + (uint32_t)((c + 1) * 32), v);   // overlaps the store below
+                    const uint32_t box = stg + (nbox & 1) * 2048;
+                    if (lane == 0) bulk_wait_read<1>();       // the store issued two boxes ago has drained this buffer
+                    __syncwarp();
+                    if (col0 < p.N) {
+                        const uint32_t rowaddr = box + (uint32_t)lane * 64;
+                        const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            sts128u(rowaddr + ((q ^ sw) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0 && row0 < p.M) tma_store_2d(&map_o, box, col0, row0);
+                    }
+                    ++nbox;
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 2) mbar_arrive_leader(&tempty_bar[as]);
+                    else mbar_arrive(&tempty_bar[as]);
+                }
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        } else {
         const bool has_res = p.epi == EC_EPI_F32_RESADD || p.epi == EC_EPI_PATCH;
         // transposed lane mapping inside a 16-column pass
         const int f_r = lane >> 2, f_c = (lane & 3) * 4;     // fp32 out: rows f_r + 8i (i<4), cols f_c..f_c+3
@@ -478,6 +559,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             }
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
+        }   // fp32 epilogues
     }
 
     tc_fence_before();
@@ -525,8 +607,23 @@ int make_map(CUtensorMap *m, const void *base, int rows, int cols, int ld, int b
     return EC_OK;
 }
 
+// bf16 output [M, ldo]: box = 32 rows x 32 columns (64 bytes), SWIZZLE_64B; the store clips rows >= M / cols >= N
+int make_out_map(CUtensorMap *m, void *base, int M, int N, int ldo)
+{
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { ec::set_error("cuTensorMapEncodeTiled entry point not available"); return EC_ERR_CUDA; }
+    cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    cuuint64_t gstr[1] = {(cuuint64_t)ldo * 2};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { ec::set_error("cuTensorMapEncodeTiled (output) failed with CUresult %d", (int)r); return EC_ERR_CUDA; }
+    return EC_OK;
+}
+
 template <int BN, int CG>
-int launch(const CUtensorMap &ma, const CUtensorMap &mw, GemmParams &p, cudaStream_t stream)
+int launch(const CUtensorMap &ma, const CUtensorMap &mw, const CUtensorMap &mo, GemmParams &p, cudaStream_t stream)
 {
     constexpr int STAGES = CG == 2 ? 6 : 4;
     constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + (BN / CG) * BK * 2) + STG_BYTES + 1024;
@@ -551,7 +648,7 @@ int launch(const CUtensorMap &ma, const CUtensorMap &mw, GemmParams &p, cudaStre
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    EC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, CG>, ma, mw, p));
+    EC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, CG>, ma, mw, mo, p));
     return EC_OK;
 }
 
@@ -587,6 +684,11 @@ extern "C" int ec_gemm_bf16(const void *A, int lda, const void *W, int ldw, cons
     GemmParams p;
     p.M = M; p.N = N; p.K = K; p.epi = epi; p.out = out; p.ldo = ldo; p.bias = bias; p.res = res; p.row_map = row_map;
     p.tx_bytes = (uint32_t)(box_a + box_w) * BK * 2 * CG;   // a pair's leader barrier collects both CTAs' bytes
-    if (CG == 2) return launch<256, 2>(ma, mw, p, stream);
-    return BN == 256 ? launch<256, 1>(ma, mw, p, stream) : launch<128, 1>(ma, mw, p, stream);
+    CUtensorMap mo = ma;   // placeholder for fp32 epilogues (never dereferenced there)
+    if (epi == EC_EPI_BF16 || epi == EC_EPI_BF16_QGELU) {
+        rc = make_out_map(&mo, out, M, N, ldo);
+        if (rc != EC_OK) return rc;
+    }
+    if (CG == 2) return launch<256, 2>(ma, mw, mo, p, stream);
+    return BN == 256 ? launch<256, 1>(ma, mw, mo, p, stream) : launch<128, 1>(ma, mw, mo, p, stream);
 }
