@@ -12,11 +12,11 @@
 //   warps 2-9   epilogue: tcgen05.ld 32x32b.x32 -> registers -> smem transpose -> bias/activation/residual ->
 //               coalesced global stores
 // Two variants of the same code (template parameter CG):
-//   CG = 1  tcgen05.mma.cta_group::1, tile 128 x BN, 4 stages of (16 + BN/8) KB.  Shared-memory traffic per SM is
+//   CG = 1  tcgen05.mma.cta_group::1, tile 128 x BN, 3 stages of (16 + BN/8) KB.  Shared-memory traffic per SM is
 //           the TMA fill plus the operand reads of a 128-row MMA: ~192 B/clk at full tensor rate, above the
 //           128 B/clk the SM has, so this variant tops out near 2/3 of peak (measured).
 //   CG = 2  CTA pair (cluster 2x1x1), tcgen05.mma.cta_group::2 with M = 256: each CTA stages its own 128 rows of A
-//           and HALF of the W tile, the pair shares W through the tensor-core datapath, 6 stages of 32 KB.
+//           and HALF of the W tile, the pair shares W through the tensor-core datapath, 5 stages of 32 KB.
 //           The leader CTA issues the MMAs; commits are multicast to both CTAs' barriers.
 #include <cuda.h>
 
@@ -33,7 +33,7 @@ constexpr int NUM_THREADS = 320;   // 10 warps
 constexpr int EPI_WARPS = 8;
 constexpr int UMMA_K = 16;
 constexpr int STG_PITCH = 20;       // floats per row of an epilogue warp's 32x16 staging tile (80 B: conflict-free)
-constexpr int STG_WARP_BYTES = 4096;  // per epilogue warp: fp32 transpose tile (2560 B) or two bf16 TMA-store boxes (2 x 2048 B)
+constexpr int STG_WARP_BYTES = 8192;  // per epilogue warp: two fp32 residual/output boxes (2 x 4096 B), two bf16 boxes, or the transpose tile
 constexpr int STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
 
 struct GemmParams {
@@ -252,9 +252,9 @@ __device__ __forceinline__ float quick_gelu(float x)
 template <int BN, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-            const __grid_constant__ CUtensorMap map_o, const GemmParams p)
+            const __grid_constant__ CUtensorMap map_o, const __grid_constant__ CUtensorMap map_r, const GemmParams p)
 {
-    constexpr int STAGES = CG == 2 ? 6 : 4;
+    constexpr int STAGES = CG == 2 ? 5 : 3;
     constexpr uint32_t A_BYTES = BM * BK * 2;
     constexpr uint32_t B_BYTES = (BN / CG) * BK * 2;         // a CTA of a pair stages half of the W tile
     constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
@@ -273,6 +273,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     __shared__ __align__(8) uint64_t tfull_bar[2];
     __shared__ __align__(8) uint64_t tempty_bar[2];
     __shared__ uint32_t tmem_base_slot;
+    __shared__ __align__(8) uint64_t res_bar[EPI_WARPS][2];   // residual boxes landed (fp32 residual epilogue)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -285,6 +286,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_o) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], EPI_WARPS * CG); }
+        for (int w = 0; w < EPI_WARPS; ++w) { mbar_init(&res_bar[w][0], 1); mbar_init(&res_bar[w][1], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -426,6 +428,70 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                         __syncwarp();
                         if (lane == 0 && row0 < p.M) tma_store_2d(&map_o, box, col0, row0);
                     }
+                    ++nbox;
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 2) mbar_arrive_leader(&tempty_bar[as]);
+                    else mbar_arrive(&tempty_bar[as]);
+                }
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        } else if (p.epi == EC_EPI_F32_RESADD) {
+            // ---- residual-stream update (out_proj, c_proj): the fp32 residual box [32 rows x 32 cols] is fetched by
+            //      TMA (SWIZZLE_128B) one chunk ahead, each thread adds accumulator + bias to its own row in place, and
+            //      the same box goes back out through a TMA store.  No per-thread global loads or stores. ----
+            uint32_t as = 0, aphase = 0, nbox = 0;
+            uint64_t *rb = res_bar[ew];
+            auto load_res = [&](int tile_, int c_, uint32_t n_) {     // lane 0 only
+                const int tm_ = tile_ / p.tiles_n, tn_ = tile_ % p.tiles_n;
+                const int r_ = (tm_ * CG + (int)cta_rank) * BM + quarter * 32;
+                const int c0_ = tn_ * BN + half * COLS_PER_WARP + c_ * 32;
+                mbar_expect_tx(&rb[n_ & 1], 4096);
+                tma_load_2d(smem + STAGES * STAGE_BYTES + ew * STG_WARP_BYTES + (n_ & 1) * 4096, &map_r, &rb[n_ & 1], c0_, r_);
+            };
+            if (lane == 0 && group_id < num_tiles) load_res(group_id, 0, 0);
+            for (int tile = group_id; tile < num_tiles; tile += num_groups) {
+                const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+                const int row0 = (tm * CG + (int)cta_rank) * BM + quarter * 32;
+                const int colw = tn * BN + half * COLS_PER_WARP;
+                mbar_wait(&tfull_bar[as], aphase);
+                tc_fence_after();
+                const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * COLS_PER_WARP);
+                uint32_t v[32];
+                tmem_ld32_issue(tbase, v);
+#pragma unroll 1
+                for (int c = 0; c < NCHUNK; ++c) {
+                    const int col0 = colw + c * 32;
+                    float bl = 0.f;
+                    if (p.bias && col0 + lane < p.N) bl = p.bias[col0 + lane];
+                    // prefetch the next residual box (next chunk, or first chunk of this CTA's next tile)
+                    if (lane == 0) {
+                        bulk_wait_read<0>();     // the store that last used the other buffer has finished reading it
+                        if (c + 1 < NCHUNK) load_res(tile, c + 1, nbox + 1);
+                        else if (tile + num_groups < num_tiles) load_res(tile + num_groups, 0, nbox + 1);
+                    }
+                    const uint32_t box = stg + (nbox & 1) * 4096;
+                    mbar_wait(&rb[nbox & 1], (nbox >> 1) & 1);
+                    tmem_ld_wait();
+                    const uint32_t rowaddr = box + (uint32_t)lane * 128;
+                    const uint32_t sw = (uint32_t)(lane & 7);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint32_t a = rowaddr + ((q ^ sw) << 4);
+                        float4 r = lds128(a);
+                        r.x += __uint_as_float(v[4 * q]) + __shfl_sync(0xffffffffu, bl, 4 * q);
+                        r.y += __uint_as_float(v[4 * q + 1]) + __shfl_sync(0xffffffffu, bl, 4 * q + 1);
+                        r.z += __uint_as_float(v[4 * q + 2]) + __shfl_sync(0xffffffffu, bl, 4 * q + 2);
+                        r.w += __uint_as_float(v[4 * q + 3]) + __shfl_sync(0xffffffffu, bl, 4 * q + 3);
+                        sts128(a, r.x, r.y, r.z, r.w);
+                    }
+                    if (c + 1 < NCHUNK) tmem_ld32_issue(tbase + (uint32_t)((c + 1) * 32), v);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0 && row0 < p.M && col0 < p.N) tma_store_2d(&map_o, box, col0, row0);
                     ++nbox;
                 }
                 tc_fence_before();
@@ -622,10 +688,27 @@ int make_out_map(CUtensorMap *m, void *base, int M, int N, int ldo)
     return EC_OK;
 }
 
-template <int BN, int CG>
-int launch(const CUtensorMap &ma, const CUtensorMap &mw, const CUtensorMap &mo, GemmParams &p, cudaStream_t stream)
+// fp32 [M, ld]: box = 32 rows x 32 columns (128 bytes), SWIZZLE_128B -- residual loads and residual-stream stores
+int make_f32_map(CUtensorMap *m, const void *base, int M, int N, int ld)
 {
-    constexpr int STAGES = CG == 2 ? 6 : 4;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { ec::set_error("cuTensorMapEncodeTiled entry point not available"); return EC_ERR_CUDA; }
+    cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { ec::set_error("cuTensorMapEncodeTiled (fp32) failed with CUresult %d", (int)r); return EC_ERR_CUDA; }
+    return EC_OK;
+}
+
+template <int BN, int CG>
+int launch(const CUtensorMap &ma, const CUtensorMap &mw, const CUtensorMap &mo, const CUtensorMap &mr, GemmParams &p,
+           cudaStream_t stream)
+{
+    constexpr int STAGES = CG == 2 ? 5 : 3;
     constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + (BN / CG) * BK * 2) + STG_BYTES + 1024;
     static bool attr_set[64] = {false};   // per device
     int dev_id = 0;
@@ -648,7 +731,7 @@ int launch(const CUtensorMap &ma, const CUtensorMap &mw, const CUtensorMap &mo, 
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    EC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, CG>, ma, mw, mo, p));
+    EC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, CG>, ma, mw, mo, mr, p));
     return EC_OK;
 }
 
@@ -689,6 +772,14 @@ extern "C" int ec_gemm_bf16(const void *A, int lda, const void *W, int ldw, cons
         rc = make_out_map(&mo, out, M, N, ldo);
         if (rc != EC_OK) return rc;
     }
-    if (CG == 2) return launch<256, 2>(ma, mw, mo, p, stream);
-    return BN == 256 ? launch<256, 1>(ma, mw, mo, p, stream) : launch<128, 1>(ma, mw, mo, p, stream);
+    CUtensorMap mr = ma;
+    if (epi == EC_EPI_F32_RESADD) {
+        EC_REQUIRE(((uintptr_t)res & 15) == 0 && ldo % 4 == 0, "ec_gemm_bf16: residual must be 16-byte aligned");
+        rc = make_f32_map(&mo, out, M, N, ldo);
+        if (rc != EC_OK) return rc;
+        rc = make_f32_map(&mr, res, M, N, ldo);
+        if (rc != EC_OK) return rc;
+    }
+    if (CG == 2) return launch<256, 2>(ma, mw, mo, mr, p, stream);
+    return BN == 256 ? launch<256, 1>(ma, mw, mo, mr, p, stream) : launch<128, 1>(ma, mw, mo, mr, p, stream);
 }
