@@ -6,6 +6,9 @@
 // One CTA per (image, head): Q, K and V of the whole sequence staged once in shared memory (cp.async), each of the
 // 7 warps owns 16-query row tiles and runs an online-softmax loop over 64-key chunks on bf16 mma.sync tiles.
 // (4 % of the encoder FLOPs; the tcgen05 budget goes to the GEMMs -- see DESIGN.md.)
+#include <cstdlib>
+#include <string>
+
 #include "common.cuh"
 
 namespace {
@@ -185,6 +188,12 @@ extern "C" int ec_attention(const void *qkv, void *out, int n_img, int L, int he
     EC_REQUIRE(qkv && out && n_img > 0 && L > 0 && heads > 0, "ec_attention: bad arguments");
     EC_REQUIRE(L <= 1024, "ec_attention: L=%d exceeds the shared-memory K/V staging limit", L);
     EC_REQUIRE(n_img <= 65535, "ec_attention: n_img=%d exceeds grid.y", n_img);
+    // tensor-memory kernel for L <= 256 (ViT-B/32, ViT-B/16); EC_ATTN=mma forces the mma.sync kernel below
+    static const bool force_mma = getenv("EC_ATTN") && std::string(getenv("EC_ATTN")) == "mma";
+    if (!force_mma) {
+        const int rc = ec::attention_tc(qkv, out, n_img, L, heads, (cudaStream_t)stream);
+        if (rc != EC_ERR_UNSUPPORTED) return rc;
+    }
     const int Lp = (L + 15) & ~15;
     const size_t smem = (size_t)3 * Lp * LDS * sizeof(__nv_bfloat16);
     EC_REQUIRE(smem <= 220 * 1024, "ec_attention: L=%d needs %zu bytes of shared memory", L, smem);

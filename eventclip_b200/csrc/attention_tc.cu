@@ -1,0 +1,353 @@
+// attention_tc.cu -- softmax(q k^T / sqrt(64)) v on the 5th-generation tensor cores (tcgen05 + TMEM), L <= 256.
+//
+// Same contract as attention.cu (nn.MultiheadAttention core of openai-CLIP's ResidualAttentionBlock [3P]; LoRA variant
+// models/lora.py:165-303): qkv bf16 [n_img*L, 3d] -> out bf16 [n_img*L, d], head_dim 64.
+//
+// One CTA per (image, head), two CTAs per SM (96 KB smem, 256 TMEM columns each):
+//   warp 0      issues everything asynchronous: six TMA box loads (Q, K, V; rows >= L are zero-filled by the 3-D tensor
+//               map), then per 128-query tile  S = Q K^T  (tcgen05.mma, A and B from shared memory, N = ceil16(L))
+//               and  O = P V  (A = P read from TENSOR MEMORY, B = V as an MN-major shared-memory operand)
+//   warps 1-4   one thread per query row: two passes over the S row in TMEM (max, then exp2 / row sum), P written back
+//               as packed bf16 over the first half of S's own columns (tcgen05.st), finally O * (1/rowsum) -> global.
+// S never leaves the SM and P never touches shared memory.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int HD = 64;
+constexpr int TILE_BYTES = 128 * 128;           // 128 rows x 64 bf16, SWIZZLE_128B
+constexpr int NTHREADS = 160;
+constexpr uint32_t TMEM_COLS = 256;
+constexpr uint32_t O_COL = 128;                 // O accumulator columns [128, 192)
+
+struct AttnParams {
+    __nv_bfloat16 *out;
+    int L, heads, d;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    uint64_t t0 = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!done && (spins & 0x3ff) == 0x3ff) {      // a protocol bug traps after ~2 s instead of hanging the GPU
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t.reg .b32 rx;\n\t"
+        "elect.sync rx|P1, 0xffffffff;\n\t"
+        "@P1 mov.s32 %0, 1;\n\t}"
+        : "+r"(pred));
+    return pred != 0;
+}
+
+// shared-memory operand descriptors, SWIZZLE_128B, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// D[tmem] (+)= A[smem] . B[smem]
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ float fast_exp2(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
+{
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char *sQ = smem;                         // 2 tiles of 128 query rows
+    unsigned char *sK = smem + 2 * TILE_BYTES;        // 256 key rows (K-major B operand of S = Q K^T)
+    unsigned char *sV = smem + 4 * TILE_BYTES;        // 256 key rows x 64 dims (MN-major B operand of O = P V)
+    __shared__ __align__(8) uint64_t bar_load, bar_s, bar_p, bar_o, bar_oe;
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = blockIdx.x, img = blockIdx.y;
+    const int L = p.L, d = p.d;
+    const int KP = (L + 15) & ~15;                    // keys rounded to a whole MMA K step
+    const int MT = (L + 127) >> 7;                    // 128-query tiles
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qkv) : "memory");
+        mbar_init(&bar_load, 1);
+        mbar_init(&bar_s, 1);
+        mbar_init(&bar_p, 4);
+        mbar_init(&bar_o, 1);
+        mbar_init(&bar_oe, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA + MMA issuer =====================
+        if (elect_one()) {
+            const int nbox = MT;                      // 128-row boxes per operand
+            mbar_expect_tx(&bar_load, (uint32_t)(3 * nbox * TILE_BYTES));
+            for (int b = 0; b < nbox; ++b) {
+                tma_load_3d(sQ + b * TILE_BYTES, &map_qkv, &bar_load, h * HD, b * 128, img);
+                tma_load_3d(sK + b * TILE_BYTES, &map_qkv, &bar_load, d + h * HD, b * 128, img);
+                tma_load_3d(sV + b * TILE_BYTES, &map_qkv, &bar_load, 2 * d + h * HD, b * 128, img);
+            }
+        }
+        __syncwarp();
+        mbar_wait(&bar_load, 0);
+        tc_fence_after();
+        // S: D fp32, A/B bf16 K-major, M = 128, N = KP.   O: B is MN-major (bit 16), N = 64.
+        const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        for (int t = 0; t < MT; ++t) {
+            if (t > 0) { mbar_wait(&bar_oe, (t - 1) & 1); tc_fence_after(); }   // O (and P, S) of the previous tile consumed
+            const uint64_t qdesc = make_desc(smem_u32(sQ + t * TILE_BYTES));
+            const uint64_t kdesc = make_desc(smem_u32(sK));
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_ss(tmem_base, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, k != 0);
+                umma_commit(&bar_s);
+            }
+            __syncwarp();
+            mbar_wait(&bar_p, t & 1);                // P is in tensor memory
+            tc_fence_after();
+            const uint64_t vdesc = make_desc(smem_u32(sV));
+            if (elect_one()) {
+                for (int j = 0; j < KP / 16; ++j)     // 16 keys per step: 8 packed columns of P, 16 rows (2048 B) of V
+                    umma_ts(tmem_base + O_COL, tmem_base + (uint32_t)(8 * j), vdesc + (uint64_t)(128 * j), idesc_o, j != 0);
+                umma_commit(&bar_o);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================== softmax + epilogue: thread = query row =====================
+        const int quarter = warp & 3;                 // TMEM lane quarter of this warp
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const float sl2 = 0.125f * 1.4426950408889634f;
+        const int nch = (KP + 31) >> 5;               // 32-column chunks of S
+        for (int t = 0; t < MT; ++t) {
+            const int row = t * 128 + quarter * 32 + lane;
+            mbar_wait(&bar_s, t & 1);
+            tc_fence_after();
+            // pass 1: row maximum
+            float m = -INFINITY;
+            for (int c = 0; c < nch; ++c) {
+                uint32_t v[32];
+                tmem_ld32(lane_base + (uint32_t)(c * 32), v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (c * 32 + j < L) m = fmaxf(m, __uint_as_float(v[j]));
+            }
+            const float ms = m * sl2;
+            // pass 2: P = exp2((s - m) * scale * log2 e) as packed bf16 pairs over S's own columns, row sum
+            float sum = 0.f;
+            for (int c = 0; c < nch; ++c) {
+                uint32_t v[32];
+                tmem_ld32(lane_base + (uint32_t)(c * 32), v);
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const float p0 = (c * 32 + j < L) ? fast_exp2(fmaf(__uint_as_float(v[j]), sl2, -ms)) : 0.f;
+                    const float p1 = (c * 32 + j + 1 < L) ? fast_exp2(fmaf(__uint_as_float(v[j + 1]), sl2, -ms)) : 0.f;
+                    sum += p0 + p1;
+                    __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+                    pk[j >> 1] = *reinterpret_cast<uint32_t *>(&hh);
+                }
+                tmem_st16(lane_base + (uint32_t)(c * 16), pk);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_p);
+            // epilogue: O / rowsum -> bf16 -> global
+            mbar_wait(&bar_o, t & 1);
+            tc_fence_after();
+            const float inv = 1.f / sum;
+            __nv_bfloat16 *orow = p.out + ((size_t)img * L + row) * d + h * HD;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t v[32];
+                tmem_ld32(lane_base + O_COL + (uint32_t)(c * 32), v);
+                if (row < L) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        uint4 o;
+                        __nv_bfloat162 hh;
+                        hh = __floats2bfloat162_rn(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv); o.x = *reinterpret_cast<uint32_t *>(&hh);
+                        hh = __floats2bfloat162_rn(__uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv); o.y = *reinterpret_cast<uint32_t *>(&hh);
+                        hh = __floats2bfloat162_rn(__uint_as_float(v[j + 4]) * inv, __uint_as_float(v[j + 5]) * inv); o.z = *reinterpret_cast<uint32_t *>(&hh);
+                        hh = __floats2bfloat162_rn(__uint_as_float(v[j + 6]) * inv, __uint_as_float(v[j + 7]) * inv); o.w = *reinterpret_cast<uint32_t *>(&hh);
+                        *reinterpret_cast<uint4 *>(orow + c * 32 + j) = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_oe);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode()
+{
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    });
+    return fn;
+}
+
+}  // namespace
+
+namespace ec {
+
+// Returns EC_OK when the tcgen05 kernel was launched, EC_ERR_UNSUPPORTED when the shape is outside its range.
+int attention_tc(const void *qkv, void *out, int n_img, int L, int heads, cudaStream_t stream)
+{
+    if (L > 256 || n_img > 65535) return EC_ERR_UNSUPPORTED;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return EC_ERR_CUDA; }
+    const int d = heads * HD;
+    CUtensorMap map;
+    cuuint64_t gdim[3] = {(cuuint64_t)3 * d, (cuuint64_t)L, (cuuint64_t)n_img};
+    cuuint64_t gstr[2] = {(cuuint64_t)3 * d * 2, (cuuint64_t)L * 3 * d * 2};
+    cuuint32_t box[3] = {64, 128, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(qkv), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (attention) failed with CUresult %d", (int)r); return EC_ERR_CUDA; }
+    const size_t smem = 6 * TILE_BYTES + 1024;
+    static bool attr_set[64] = {false};
+    int dev_id = 0;
+    EC_CUDA_CHECK(cudaGetDevice(&dev_id));
+    if (dev_id < 64 && !attr_set[dev_id]) {
+        EC_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[dev_id] = true;
+    }
+    AttnParams p;
+    p.out = (__nv_bfloat16 *)out; p.L = L; p.heads = heads; p.d = d;
+    attention_tc_kernel<<<dim3(heads, n_img), NTHREADS, smem, stream>>>(map, p);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
+}  // namespace ec

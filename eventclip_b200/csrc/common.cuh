@@ -33,6 +33,9 @@ void set_error(const char *fmt, ...);
 // number of SMs of the current device (cached)
 int sm_count();
 
+// tcgen05 attention (attention_tc.cu): EC_OK when launched, EC_ERR_UNSUPPORTED when the shape is outside its range
+int attention_tc(const void *qkv, void *out, int n_img, int L, int heads, cudaStream_t stream);
+
 __device__ __forceinline__ float warp_sum(float v)
 {
 #pragma unroll
