@@ -7,8 +7,9 @@
 //   warp 0      issues everything asynchronous: six TMA box loads (Q, K, V; rows >= L are zero-filled by the 3-D tensor
 //               map), then per 128-query tile  S = Q K^T  (tcgen05.mma, A and B from shared memory, N = ceil16(L))
 //               and  O = P V  (A = P read from TENSOR MEMORY, B = V as an MN-major shared-memory operand)
-//   warps 1-4   one thread per query row: two passes over the S row in TMEM (max, then exp2 / row sum), P written back
-//               as packed bf16 over the first half of S's own columns (tcgen05.st), finally O * (1/rowsum) -> global.
+//   warps 1-4   one thread per query row: row maximum over S in TMEM, then exp2 on packed bf16 pairs, P written back
+//               as packed bf16 over the first half of S's own columns (tcgen05.st); the softmax denominators come from
+//               a companion MMA (P . ones); O / denominator -> global.
 // S never leaves the SM and P never touches shared memory.
 #include <cuda.h>
 
@@ -20,9 +21,11 @@ namespace {
 
 constexpr int HD = 64;
 constexpr int TILE_BYTES = 128 * 128;           // 128 rows x 64 bf16, SWIZZLE_128B
-constexpr int NTHREADS = 160;
+constexpr int NTHREADS = 160;                   // warp 0: TMA + MMA issue; warps 1-4: one thread per query row
 constexpr uint32_t TMEM_COLS = 256;
 constexpr uint32_t O_COL = 128;                 // O accumulator columns [128, 192)
+constexpr uint32_t SUM_COL = 192;               // row sums = P . ones, columns [192, 208)
+constexpr int ONES_BYTES = 2048;                // 16 rows x 64 bf16 of 1.0: B operand of the row-sum MMA (layout-proof)
 
 struct AttnParams {
     __nv_bfloat16 *out;
@@ -133,6 +136,35 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr)
+{
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    return __uint_as_float(r);
+}
+// two probabilities per SFU op: exp2 of a packed bf16 pair, result already in the packed bf16 form P is stored in
+__device__ __forceinline__ uint32_t exp2_bf16x2(float lo, float hi)
+{
+    uint32_t x, y;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(x) : "f"(hi), "f"(lo));
+    asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16])
 {
     asm volatile(
@@ -156,7 +188,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
     unsigned char *sQ = smem;                         // 2 tiles of 128 query rows
     unsigned char *sK = smem + 2 * TILE_BYTES;        // 256 key rows (K-major B operand of S = Q K^T)
     unsigned char *sV = smem + 4 * TILE_BYTES;        // 256 key rows x 64 dims (MN-major B operand of O = P V)
-    __shared__ __align__(8) uint64_t bar_load, bar_s, bar_p, bar_o, bar_oe;
+    unsigned char *sOnes = smem + 6 * TILE_BYTES;     // all-ones operand: O's companion MMA yields the softmax denominators
+    __shared__ __align__(8) uint64_t bar_load, bar_v, bar_s, bar_p, bar_o, bar_oe;
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -168,6 +201,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qkv) : "memory");
         mbar_init(&bar_load, 1);
+        mbar_init(&bar_v, 1);
         mbar_init(&bar_s, 1);
         mbar_init(&bar_p, 4);
         mbar_init(&bar_o, 1);
@@ -179,6 +213,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    for (int i = threadIdx.x; i < ONES_BYTES / 4; i += NTHREADS) reinterpret_cast<uint32_t *>(sOnes)[i] = 0x3f803f80u;   // bf16 1.0 x2
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -188,12 +224,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
         // ===================== TMA + MMA issuer =====================
         if (elect_one()) {
             const int nbox = MT;                      // 128-row boxes per operand
-            mbar_expect_tx(&bar_load, (uint32_t)(3 * nbox * TILE_BYTES));
+            // Q and K gate the first MMA; V is only needed once P exists, so it gets its own barrier
+            mbar_expect_tx(&bar_load, (uint32_t)(2 * nbox * TILE_BYTES));
             for (int b = 0; b < nbox; ++b) {
-                tma_load_3d(sQ + b * TILE_BYTES, &map_qkv, &bar_load, h * HD, b * 128, img);
                 tma_load_3d(sK + b * TILE_BYTES, &map_qkv, &bar_load, d + h * HD, b * 128, img);
-                tma_load_3d(sV + b * TILE_BYTES, &map_qkv, &bar_load, 2 * d + h * HD, b * 128, img);
+                tma_load_3d(sQ + b * TILE_BYTES, &map_qkv, &bar_load, h * HD, b * 128, img);
             }
+            mbar_expect_tx(&bar_v, (uint32_t)(nbox * TILE_BYTES));
+            for (int b = 0; b < nbox; ++b) tma_load_3d(sV + b * TILE_BYTES, &map_qkv, &bar_v, 2 * d + h * HD, b * 128, img);
         }
         __syncwarp();
         mbar_wait(&bar_load, 0);
@@ -201,6 +239,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
         // S: D fp32, A/B bf16 K-major, M = 128, N = KP.   O: B is MN-major (bit 16), N = 64.
         const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc_1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint64_t odesc = make_desc(smem_u32(sOnes));
         for (int t = 0; t < MT; ++t) {
             if (t > 0) { mbar_wait(&bar_oe, (t - 1) & 1); tc_fence_after(); }   // O (and P, S) of the previous tile consumed
             const uint64_t qdesc = make_desc(smem_u32(sQ + t * TILE_BYTES));
@@ -212,18 +252,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
             }
             __syncwarp();
             mbar_wait(&bar_p, t & 1);                // P is in tensor memory
+            if (t == 0) mbar_wait(&bar_v, 0);
             tc_fence_after();
             const uint64_t vdesc = make_desc(smem_u32(sV));
             if (elect_one()) {
-                for (int j = 0; j < KP / 16; ++j)     // 16 keys per step: 8 packed columns of P, 16 rows (2048 B) of V
+                for (int j = 0; j < KP / 16; ++j) {   // 16 keys per step: 8 packed columns of P, 16 rows (2048 B) of V
                     umma_ts(tmem_base + O_COL, tmem_base + (uint32_t)(8 * j), vdesc + (uint64_t)(128 * j), idesc_o, j != 0);
+                    umma_ts(tmem_base + SUM_COL, tmem_base + (uint32_t)(8 * j), odesc, idesc_1, j != 0);   // += P . 1
+                }
                 umma_commit(&bar_o);
             }
             __syncwarp();
         }
     } else {
         // ===================== softmax + epilogue: thread = query row =====================
-        const int quarter = warp & 3;                 // TMEM lane quarter of this warp
+        const int quarter = warp & 3;                 // TMEM lane quarter of this warp (hardware: lanes 32*(warp%4)..+31)
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const float sl2 = 0.125f * 1.4426950408889634f;
         const int nch = (KP + 31) >> 5;               // 32-column chunks of S
@@ -231,31 +274,78 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
             const int row = t * 128 + quarter * 32 + lane;
             mbar_wait(&bar_s, t & 1);
             tc_fence_after();
-            // pass 1: row maximum
+            const bool live = t * 128 + quarter * 32 < L;    // warp-uniform: this warp owns at least one real query row
+            // pass 1: row maximum (chunk c+1 is in flight while chunk c is reduced; only the last chunk needs the mask)
             float m = -INFINITY;
-            for (int c = 0; c < nch; ++c) {
-                uint32_t v[32];
-                tmem_ld32(lane_base + (uint32_t)(c * 32), v);
+            if (live) {
+                uint32_t va[32], vb[32];
+                tmem_ld32_issue(lane_base, va);
+                for (int c = 0; c < nch; c += 2) {
+                    tmem_ld_wait();
+                    if (c + 1 < nch) tmem_ld32_issue(lane_base + (uint32_t)((c + 1) * 32), vb);
+                    if ((c + 1) * 32 <= L) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (c * 32 + j < L) m = fmaxf(m, __uint_as_float(v[j]));
+                        for (int j = 0; j < 32; j += 2) m = fmaxf(m, fmaxf(__uint_as_float(va[j]), __uint_as_float(va[j + 1])));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (c * 32 + j < L) m = fmaxf(m, __uint_as_float(va[j]));
+                    }
+                    if (c + 1 < nch) {
+                        tmem_ld_wait();
+                        if (c + 2 < nch) tmem_ld32_issue(lane_base + (uint32_t)((c + 2) * 32), va);
+                        if ((c + 2) * 32 <= L) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) m = fmaxf(m, fmaxf(__uint_as_float(vb[j]), __uint_as_float(vb[j + 1])));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if ((c + 1) * 32 + j < L) m = fmaxf(m, __uint_as_float(vb[j]));
+                        }
+                    }
+                }
             }
             const float ms = m * sl2;
-            // pass 2: P = exp2((s - m) * scale * log2 e) as packed bf16 pairs over S's own columns, row sum
-            float sum = 0.f;
-            for (int c = 0; c < nch; ++c) {
-                uint32_t v[32];
-                tmem_ld32(lane_base + (uint32_t)(c * 32), v);
-                uint32_t pk[16];
+            // pass 2: P = exp2((s - m) * scale * log2 e), two per SFU op, written back as packed bf16 over S's own
+            // columns; the denominators come out of the tensor core (P . ones), so no scalar row sum is kept here
+            // P chunk c lands on columns [16c, 16c+16), which this thread has already read (chunks are taken in order)
+            if (live) {
+                uint32_t va[32], vb[32];
+                tmem_ld32_issue(lane_base, va);
+                for (int c = 0; c < nch; c += 2) {
+                    tmem_ld_wait();
+                    if (c + 1 < nch) tmem_ld32_issue(lane_base + (uint32_t)((c + 1) * 32), vb);
+                    {
+                        uint32_t pk[16];
+                        const bool full = (c + 1) * 32 <= L;
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    const float p0 = (c * 32 + j < L) ? fast_exp2(fmaf(__uint_as_float(v[j]), sl2, -ms)) : 0.f;
-                    const float p1 = (c * 32 + j + 1 < L) ? fast_exp2(fmaf(__uint_as_float(v[j + 1]), sl2, -ms)) : 0.f;
-                    sum += p0 + p1;
-                    __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
-                    pk[j >> 1] = *reinterpret_cast<uint32_t *>(&hh);
+                        for (int j = 0; j < 32; j += 2) {
+                            float x0 = fmaf(__uint_as_float(va[j]), sl2, -ms), x1 = fmaf(__uint_as_float(va[j + 1]), sl2, -ms);
+                            if (!full) {
+                                if (c * 32 + j >= L) x0 = -INFINITY;
+                                if (c * 32 + j + 1 >= L) x1 = -INFINITY;
+                            }
+                            pk[j >> 1] = exp2_bf16x2(x0, x1);
+                        }
+                        tmem_st16(lane_base + (uint32_t)(c * 16), pk);
+                    }
+                    if (c + 1 < nch) {
+                        tmem_ld_wait();
+                        if (c + 2 < nch) tmem_ld32_issue(lane_base + (uint32_t)((c + 2) * 32), va);
+                        uint32_t pk[16];
+                        const bool full = (c + 2) * 32 <= L;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            float x0 = fmaf(__uint_as_float(vb[j]), sl2, -ms), x1 = fmaf(__uint_as_float(vb[j + 1]), sl2, -ms);
+                            if (!full) {
+                                if ((c + 1) * 32 + j >= L) x0 = -INFINITY;
+                                if ((c + 1) * 32 + j + 1 >= L) x1 = -INFINITY;
+                            }
+                            pk[j >> 1] = exp2_bf16x2(x0, x1);
+                        }
+                        tmem_st16(lane_base + (uint32_t)((c + 1) * 16), pk);
+                    }
                 }
-                tmem_st16(lane_base + (uint32_t)(c * 16), pk);
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
@@ -264,7 +354,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
             // epilogue: O / rowsum -> bf16 -> global
             mbar_wait(&bar_o, t & 1);
             tc_fence_after();
-            const float inv = 1.f / sum;
+            if (!live) {      // nothing to store: keep the barrier protocol and move on
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_oe);
+                continue;
+            }
+            const float inv = 1.f / tmem_ld1(lane_base + SUM_COL);
             __nv_bfloat16 *orow = p.out + ((size_t)img * L + row) * d + h * HD;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
@@ -335,7 +431,7 @@ int attention_tc(const void *qkv, void *out, int n_img, int L, int heads, cudaSt
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (attention) failed with CUresult %d", (int)r); return EC_ERR_CUDA; }
-    const size_t smem = 6 * TILE_BYTES + 1024;
+    const size_t smem = 6 * TILE_BYTES + ONES_BYTES + 1024;
     static bool attr_set[64] = {false};
     int dev_id = 0;
     EC_CUDA_CHECK(cudaGetDevice(&dev_id));
