@@ -3,13 +3,15 @@
 // Same contract as attention.cu (nn.MultiheadAttention core of openai-CLIP's ResidualAttentionBlock [3P]; LoRA variant
 // models/lora.py:165-303): qkv bf16 [n_img*L, 3d] -> out bf16 [n_img*L, d], head_dim 64.
 //
-// One CTA per (image, head), two CTAs per SM (96 KB smem, 256 TMEM columns each):
+// Persistent CTAs (one per SM) walk over (image, head) units; shared memory holds two units (next one prefetched),
+// tensor memory both 128-query tiles of the current unit (2 x 256 columns):
 //   warp 0      issues everything asynchronous: six TMA box loads (Q, K, V; rows >= L are zero-filled by the 3-D tensor
 //               map), then per 128-query tile  S = Q K^T  (tcgen05.mma, A and B from shared memory, N = ceil16(L))
 //               and  O = P V  (A = P read from TENSOR MEMORY, B = V as an MN-major shared-memory operand)
-//   warps 1-4   one thread per query row: row maximum over S in TMEM, then exp2 on packed bf16 pairs, P written back
-//               as packed bf16 over the first half of S's own columns (tcgen05.st); the softmax denominators come from
-//               a companion MMA (P . ones); O / denominator -> global.
+//   warps 1-8   one thread per query row (one warpgroup per 128-query tile): a single pass over S in TMEM -- exponentials
+//               relative to the maximum of the row's first 32 scores, P written back as packed bf16 over the first
+//               half of S's own columns (tcgen05.st); the softmax denominators come from a companion MMA (P . ones);
+//               O / denominator -> global.
 // S never leaves the SM and P never touches shared memory.
 #include <cuda.h>
 
@@ -21,15 +23,17 @@ namespace {
 
 constexpr int HD = 64;
 constexpr int TILE_BYTES = 128 * 128;           // 128 rows x 64 bf16, SWIZZLE_128B
-constexpr int NTHREADS = 160;                   // warp 0: TMA + MMA issue; warps 1-4: one thread per query row
-constexpr uint32_t TMEM_COLS = 256;
+constexpr int NTHREADS = 288;                   // warp 0: TMA + MMA issue; warps 1-4 / 5-8: one thread per query row of tile 0 / 1
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t TILE_COLS = 256;             // tensor-memory columns per 128-query tile
+constexpr int STAGE_BYTES = 6 * TILE_BYTES;     // Q, K, V of one (image, head): 2 tiles each
 constexpr uint32_t O_COL = 128;                 // O accumulator columns [128, 192)
 constexpr uint32_t SUM_COL = 192;               // row sums = P . ones, columns [192, 208)
 constexpr int ONES_BYTES = 2048;                // 16 rows x 64 bf16 of 1.0: B operand of the row-sum MMA (layout-proof)
 
 struct AttnParams {
     __nv_bfloat16 *out;
-    int L, heads, d;
+    int L, heads, d, n_img;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -180,32 +184,32 @@ __device__ __forceinline__ float fast_exp2(float x)
     return y;
 }
 
-__global__ void __launch_bounds__(NTHREADS, 2)
+// Persistent: one CTA per SM walks over (image, head) units.  Shared memory holds two units (the next one is fetched
+// while the current one is computed); tensor memory holds both 128-query tiles of a unit, each served by its own
+// softmax warpgroup, so the two tiles of a unit run side by side.
+__global__ void __launch_bounds__(NTHREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
 {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-    unsigned char *sQ = smem;                         // 2 tiles of 128 query rows
-    unsigned char *sK = smem + 2 * TILE_BYTES;        // 256 key rows (K-major B operand of S = Q K^T)
-    unsigned char *sV = smem + 4 * TILE_BYTES;        // 256 key rows x 64 dims (MN-major B operand of O = P V)
-    unsigned char *sOnes = smem + 6 * TILE_BYTES;     // all-ones operand: O's companion MMA yields the softmax denominators
-    __shared__ __align__(8) uint64_t bar_load, bar_v, bar_s, bar_p, bar_o, bar_oe;
+    // stage s: Q (2 tiles) | K (2 tiles, K-major B of S = Q K^T) | V (2 tiles, MN-major B of O = P V)
+    unsigned char *sOnes = smem + 2 * STAGE_BYTES;    // all-ones operand: O's companion MMA yields the softmax denominators
+    __shared__ __align__(8) uint64_t bar_qk[2], bar_v[2], bar_free[2];       // per smem stage
+    __shared__ __align__(8) uint64_t bar_s[2], bar_p[2], bar_o[2], bar_oe[2];   // per query tile / warpgroup
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int h = blockIdx.x, img = blockIdx.y;
-    const int L = p.L, d = p.d;
+    const int L = p.L, d = p.d, heads = p.heads;
     const int KP = (L + 15) & ~15;                    // keys rounded to a whole MMA K step
-    const int MT = (L + 127) >> 7;                    // 128-query tiles
+    const int MT = (L + 127) >> 7;                    // 128-query tiles (1 or 2)
+    const int n_units = p.n_img * heads;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qkv) : "memory");
-        mbar_init(&bar_load, 1);
-        mbar_init(&bar_v, 1);
-        mbar_init(&bar_s, 1);
-        mbar_init(&bar_p, 4);
-        mbar_init(&bar_o, 1);
-        mbar_init(&bar_oe, 4);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_qk[i], 1); mbar_init(&bar_v[i], 1); mbar_init(&bar_free[i], 1);
+            mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 4); mbar_init(&bar_o[i], 1); mbar_init(&bar_oe[i], 4);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -222,142 +226,138 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
 
     if (warp == 0) {
         // ===================== TMA + MMA issuer =====================
-        if (elect_one()) {
-            const int nbox = MT;                      // 128-row boxes per operand
+        auto load_unit = [&](int unit, int stage) {      // elected lane only
+            const int img = unit / heads, h = unit % heads;
+            unsigned char *sQ = smem + stage * STAGE_BYTES, *sK = sQ + 2 * TILE_BYTES, *sV = sQ + 4 * TILE_BYTES;
             // Q and K gate the first MMA; V is only needed once P exists, so it gets its own barrier
-            mbar_expect_tx(&bar_load, (uint32_t)(2 * nbox * TILE_BYTES));
-            for (int b = 0; b < nbox; ++b) {
-                tma_load_3d(sK + b * TILE_BYTES, &map_qkv, &bar_load, d + h * HD, b * 128, img);
-                tma_load_3d(sQ + b * TILE_BYTES, &map_qkv, &bar_load, h * HD, b * 128, img);
+            mbar_expect_tx(&bar_qk[stage], (uint32_t)(2 * MT * TILE_BYTES));
+            for (int b = 0; b < MT; ++b) {
+                tma_load_3d(sK + b * TILE_BYTES, &map_qkv, &bar_qk[stage], d + h * HD, b * 128, img);
+                tma_load_3d(sQ + b * TILE_BYTES, &map_qkv, &bar_qk[stage], h * HD, b * 128, img);
             }
-            mbar_expect_tx(&bar_v, (uint32_t)(nbox * TILE_BYTES));
-            for (int b = 0; b < nbox; ++b) tma_load_3d(sV + b * TILE_BYTES, &map_qkv, &bar_v, 2 * d + h * HD, b * 128, img);
-        }
-        __syncwarp();
-        mbar_wait(&bar_load, 0);
-        tc_fence_after();
-        // S: D fp32, A/B bf16 K-major, M = 128, N = KP.   O: B is MN-major (bit 16), N = 64.
+            mbar_expect_tx(&bar_v[stage], (uint32_t)(MT * TILE_BYTES));
+            for (int b = 0; b < MT; ++b) tma_load_3d(sV + b * TILE_BYTES, &map_qkv, &bar_v[stage], 2 * d + h * HD, b * 128, img);
+        };
+        // S: D fp32, A/B bf16 K-major, M = 128, N = KP.   O: B is MN-major (bit 16), N = 64.   sums: N = 16.
         const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t idesc_1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint64_t odesc = make_desc(smem_u32(sOnes));
-        for (int t = 0; t < MT; ++t) {
-            if (t > 0) { mbar_wait(&bar_oe, (t - 1) & 1); tc_fence_after(); }   // O (and P, S) of the previous tile consumed
-            const uint64_t qdesc = make_desc(smem_u32(sQ + t * TILE_BYTES));
-            const uint64_t kdesc = make_desc(smem_u32(sK));
-            if (elect_one()) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_ss(tmem_base, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, k != 0);
-                umma_commit(&bar_s);
+        if ((int)blockIdx.x < n_units && elect_one()) load_unit(blockIdx.x, 0);
+        __syncwarp();
+        int i = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++i) {
+            const int stage = i & 1;
+            const uint32_t sph = (uint32_t)(i >> 1) & 1, uph = (uint32_t)i & 1;
+            const int next = unit + gridDim.x;
+            if (next < n_units) {
+                // the other stage was last read by the MMAs of unit i-1
+                if (i >= 1) mbar_wait(&bar_free[stage ^ 1], (uint32_t)((i - 1) >> 1) & 1);
+                if (elect_one()) load_unit(next, stage ^ 1);
+                __syncwarp();
             }
-            __syncwarp();
-            mbar_wait(&bar_p, t & 1);                // P is in tensor memory
-            if (t == 0) mbar_wait(&bar_v, 0);
+            unsigned char *sQ = smem + stage * STAGE_BYTES, *sK = sQ + 2 * TILE_BYTES, *sV = sQ + 4 * TILE_BYTES;
+            mbar_wait(&bar_qk[stage], sph);
             tc_fence_after();
-            const uint64_t vdesc = make_desc(smem_u32(sV));
-            if (elect_one()) {
-                for (int j = 0; j < KP / 16; ++j) {   // 16 keys per step: 8 packed columns of P, 16 rows (2048 B) of V
-                    umma_ts(tmem_base + O_COL, tmem_base + (uint32_t)(8 * j), vdesc + (uint64_t)(128 * j), idesc_o, j != 0);
-                    umma_ts(tmem_base + SUM_COL, tmem_base + (uint32_t)(8 * j), odesc, idesc_1, j != 0);   // += P . 1
+            const uint64_t kdesc = make_desc(smem_u32(sK));
+            for (int t = 0; t < MT; ++t) {
+                if (i >= 1) { mbar_wait(&bar_oe[t], uph ^ 1); tc_fence_after(); }   // tile t's TMEM of unit i-1 fully consumed
+                const uint64_t qdesc = make_desc(smem_u32(sQ + t * TILE_BYTES));
+                const uint32_t tb = tmem_base + (uint32_t)(t * TILE_COLS);
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_ss(tb, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, k != 0);
+                    umma_commit(&bar_s[t]);
                 }
-                umma_commit(&bar_o);
+                __syncwarp();
             }
-            __syncwarp();
+            mbar_wait(&bar_v[stage], sph);
+            const uint64_t vdesc = make_desc(smem_u32(sV));
+            for (int t = 0; t < MT; ++t) {
+                mbar_wait(&bar_p[t], uph);               // P is in tensor memory
+                tc_fence_after();
+                const uint32_t tb = tmem_base + (uint32_t)(t * TILE_COLS);
+                if (elect_one()) {
+                    for (int j = 0; j < KP / 16; ++j) {   // 16 keys per step: 8 packed columns of P, 16 rows (2048 B) of V
+                        umma_ts(tb + O_COL, tb + (uint32_t)(8 * j), vdesc + (uint64_t)(128 * j), idesc_o, j != 0);
+                        umma_ts(tb + SUM_COL, tb + (uint32_t)(8 * j), odesc, idesc_1, j != 0);   // += P . 1
+                    }
+                    umma_commit(&bar_o[t]);
+                    if (t == MT - 1) umma_commit(&bar_free[stage]);   // every MMA that reads this stage has retired
+                }
+                __syncwarp();
+            }
         }
-    } else {
-        // ===================== softmax + epilogue: thread = query row =====================
+    } else if ((warp - 1) / 4 < MT) {
+        // ===================== softmax + epilogue: thread = query row, one warpgroup per 128-query tile =====================
+        const int t = (warp - 1) >> 2;                // tile served by this warpgroup
         const int quarter = warp & 3;                 // TMEM lane quarter of this warp (hardware: lanes 32*(warp%4)..+31)
-        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const uint32_t lane_base = tmem_base + (uint32_t)(t * TILE_COLS) + ((uint32_t)(quarter * 32) << 16);
         const float sl2 = 0.125f * 1.4426950408889634f;
         const int nch = (KP + 31) >> 5;               // 32-column chunks of S
-        for (int t = 0; t < MT; ++t) {
-            const int row = t * 128 + quarter * 32 + lane;
-            mbar_wait(&bar_s, t & 1);
+        const int row = t * 128 + quarter * 32 + lane;
+        const bool live = t * 128 + quarter * 32 < L; // warp-uniform: this warp owns at least one real query row
+        int i = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++i) {
+            const uint32_t uph = (uint32_t)i & 1;
+            const int img = unit / heads, h = unit % heads;
+            mbar_wait(&bar_s[t], uph);
             tc_fence_after();
-            const bool live = t * 128 + quarter * 32 < L;    // warp-uniform: this warp owns at least one real query row
-            // pass 1: row maximum (chunk c+1 is in flight while chunk c is reduced; only the last chunk needs the mask)
-            float m = -INFINITY;
+            // Single pass over S (tensor-memory reads are the scarce resource: ~64 B/clk per SM).  Softmax is invariant to
+            // the constant subtracted before the exponential, so the reference point is the maximum of the FIRST 32 scores
+            // of the row instead of the exact row maximum; exponents are evaluated in fp32 (range 2^+-126, clamped at
+            // +120) and the denominators come from the tensor core (P . ones), so the result is the same softmax.
+            // P chunk c lands on columns [16c, 16c+16), which this thread has already read (chunks are taken in order).
             if (live) {
                 uint32_t va[32], vb[32];
                 tmem_ld32_issue(lane_base, va);
-                for (int c = 0; c < nch; c += 2) {
-                    tmem_ld_wait();
-                    if (c + 1 < nch) tmem_ld32_issue(lane_base + (uint32_t)((c + 1) * 32), vb);
-                    if ((c + 1) * 32 <= L) {
+                tmem_ld_wait();
+                if (nch > 1) tmem_ld32_issue(lane_base + 32u, vb);
+                float m = -INFINITY;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 2) m = fmaxf(m, fmaxf(__uint_as_float(va[j]), __uint_as_float(va[j + 1])));
-                    } else {
+                for (int j = 0; j < 32; ++j)
+                    if (j < L) m = fmaxf(m, __uint_as_float(va[j]));
+                const float ms = m * sl2;
+                auto emit = [&](const uint32_t (&v)[32], int c) {
+                    uint32_t pk[16];
+                    const bool full = (c + 1) * 32 <= L;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (c * 32 + j < L) m = fmaxf(m, __uint_as_float(va[j]));
+                    for (int j = 0; j < 32; j += 2) {
+                        float x0 = fminf(fmaf(__uint_as_float(v[j]), sl2, -ms), 120.f);
+                        float x1 = fminf(fmaf(__uint_as_float(v[j + 1]), sl2, -ms), 120.f);
+                        if (!full) {
+                            if (c * 32 + j >= L) x0 = -INFINITY;
+                            if (c * 32 + j + 1 >= L) x1 = -INFINITY;
+                        }
+                        __nv_bfloat162 hh = __floats2bfloat162_rn(fast_exp2(x0), fast_exp2(x1));
+                        pk[j >> 1] = *reinterpret_cast<uint32_t *>(&hh);
                     }
+                    tmem_st16(lane_base + (uint32_t)(c * 16), pk);
+                };
+                for (int c = 0; c < nch; c += 2) {
+                    if (c > 0) {
+                        tmem_ld_wait();
+                        if (c + 1 < nch) tmem_ld32_issue(lane_base + (uint32_t)((c + 1) * 32), vb);
+                    }
+                    emit(va, c);
                     if (c + 1 < nch) {
                         tmem_ld_wait();
                         if (c + 2 < nch) tmem_ld32_issue(lane_base + (uint32_t)((c + 2) * 32), va);
-                        if ((c + 2) * 32 <= L) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 2) m = fmaxf(m, fmaxf(__uint_as_float(vb[j]), __uint_as_float(vb[j + 1])));
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if ((c + 1) * 32 + j < L) m = fmaxf(m, __uint_as_float(vb[j]));
-                        }
-                    }
-                }
-            }
-            const float ms = m * sl2;
-            // pass 2: P = exp2((s - m) * scale * log2 e), two per SFU op, written back as packed bf16 over S's own
-            // columns; the denominators come out of the tensor core (P . ones), so no scalar row sum is kept here
-            // P chunk c lands on columns [16c, 16c+16), which this thread has already read (chunks are taken in order)
-            if (live) {
-                uint32_t va[32], vb[32];
-                tmem_ld32_issue(lane_base, va);
-                for (int c = 0; c < nch; c += 2) {
-                    tmem_ld_wait();
-                    if (c + 1 < nch) tmem_ld32_issue(lane_base + (uint32_t)((c + 1) * 32), vb);
-                    {
-                        uint32_t pk[16];
-                        const bool full = (c + 1) * 32 <= L;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            float x0 = fmaf(__uint_as_float(va[j]), sl2, -ms), x1 = fmaf(__uint_as_float(va[j + 1]), sl2, -ms);
-                            if (!full) {
-                                if (c * 32 + j >= L) x0 = -INFINITY;
-                                if (c * 32 + j + 1 >= L) x1 = -INFINITY;
-                            }
-                            pk[j >> 1] = exp2_bf16x2(x0, x1);
-                        }
-                        tmem_st16(lane_base + (uint32_t)(c * 16), pk);
-                    }
-                    if (c + 1 < nch) {
-                        tmem_ld_wait();
-                        if (c + 2 < nch) tmem_ld32_issue(lane_base + (uint32_t)((c + 2) * 32), va);
-                        uint32_t pk[16];
-                        const bool full = (c + 2) * 32 <= L;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            float x0 = fmaf(__uint_as_float(vb[j]), sl2, -ms), x1 = fmaf(__uint_as_float(vb[j + 1]), sl2, -ms);
-                            if (!full) {
-                                if ((c + 1) * 32 + j >= L) x0 = -INFINITY;
-                                if ((c + 1) * 32 + j + 1 >= L) x1 = -INFINITY;
-                            }
-                            pk[j >> 1] = exp2_bf16x2(x0, x1);
-                        }
-                        tmem_st16(lane_base + (uint32_t)((c + 1) * 16), pk);
+                        emit(vb, c + 1);
                     }
                 }
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_p);
+            if (lane == 0) mbar_arrive(&bar_p[t]);
             // epilogue: O / rowsum -> bf16 -> global
-            mbar_wait(&bar_o, t & 1);
+            mbar_wait(&bar_o[t], uph);
             tc_fence_after();
             if (!live) {      // nothing to store: keep the barrier protocol and move on
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_oe);
+                if (lane == 0) mbar_arrive(&bar_oe[t]);
                 continue;
             }
             const float inv = 1.f / tmem_ld1(lane_base + SUM_COL);
@@ -381,7 +381,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_oe);
+            if (lane == 0) mbar_arrive(&bar_oe[t]);
         }
     }
 
@@ -431,7 +431,7 @@ int attention_tc(const void *qkv, void *out, int n_img, int L, int heads, cudaSt
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (attention) failed with CUresult %d", (int)r); return EC_ERR_CUDA; }
-    const size_t smem = 6 * TILE_BYTES + ONES_BYTES + 1024;
+    const size_t smem = 2 * STAGE_BYTES + ONES_BYTES + 1024;
     static bool attr_set[64] = {false};
     int dev_id = 0;
     EC_CUDA_CHECK(cudaGetDevice(&dev_id));
@@ -440,8 +440,10 @@ int attention_tc(const void *qkv, void *out, int n_img, int L, int heads, cudaSt
         attr_set[dev_id] = true;
     }
     AttnParams p;
-    p.out = (__nv_bfloat16 *)out; p.L = L; p.heads = heads; p.d = d;
-    attention_tc_kernel<<<dim3(heads, n_img), NTHREADS, smem, stream>>>(map, p);
+    p.out = (__nv_bfloat16 *)out; p.L = L; p.heads = heads; p.d = d; p.n_img = n_img;
+    const int units = n_img * heads;
+    const int grid = units < sm_count() ? units : sm_count();
+    attention_tc_kernel<<<grid, NTHREADS, smem, stream>>>(map, p);
     EC_CUDA_CHECK(cudaGetLastError());
     return EC_OK;
 }
