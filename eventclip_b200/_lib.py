@@ -37,6 +37,8 @@ SIGNATURES = {
     "ec_plan_frames": ([_vp, _i, _i64, _i, _vp, _i, _vp, _i, _vp, _vp, _ip, _ip], _i),
     "ec_event2img": ([_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "ec_event2img_geometry": ([_i, _i, _ip, _ip, _ip], _i),
+    "ec_center_events": ([_vp, _vp, _i, _i, _i, _vp], _i),
+    "ec_flip_events": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp], _i),
     "ec_gemm_bf16": ([_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp], _i),
     "ec_layernorm": ([_vp, _i64, _vp, _vp, _i, _i, _vp, _vp, _vp], _i),
     "ec_attention": ([_vp, _vp, _i, _i, _i, _vp], _i),

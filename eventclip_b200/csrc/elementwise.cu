@@ -176,7 +176,86 @@ __global__ void l2norm_rows_kernel(const float *x, float *out, int M, int C)
     for (int c = lane; c < C; c += 32) out[(size_t)row * C + c] = x[(size_t)row * C + c] * inv;
 }
 
+// center_events (datasets/utils.py:38-57): one CTA per sample, min/max reduction then the shift, float32 like numpy
+__global__ void __launch_bounds__(1024) center_events_kernel(float4 *ev, const int64_t *offsets, int H, int W)
+{
+    const int64_t lo = offsets[blockIdx.x], hi = offsets[blockIdx.x + 1];
+    __shared__ float red[5][32];
+    __shared__ float sh[3];
+    float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY, tmin = INFINITY;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const float4 e = ev[i];
+        xmin = fminf(xmin, e.x); xmax = fmaxf(xmax, e.x);
+        ymin = fminf(ymin, e.y); ymax = fmaxf(ymax, e.y);
+        tmin = fminf(tmin, e.z);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)); xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+        ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, o)); ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+        tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { red[0][w] = xmin; red[1][w] = xmax; red[2][w] = ymin; red[3][w] = ymax; red[4][w] = tmin; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) {
+            red[0][0] = fminf(red[0][0], red[0][k]); red[1][0] = fmaxf(red[1][0], red[1][k]);
+            red[2][0] = fminf(red[2][0], red[2][k]); red[3][0] = fmaxf(red[3][0], red[3][k]);
+            red[4][0] = fminf(red[4][0], red[4][k]);
+        }
+        // ((max + min + 1.) - W) // 2.  in float32
+        sh[0] = floorf(__fdiv_rn(__fsub_rn(__fadd_rn(__fadd_rn(red[1][0], red[0][0]), 1.0f), (float)W), 2.0f));
+        sh[1] = floorf(__fdiv_rn(__fsub_rn(__fadd_rn(__fadd_rn(red[3][0], red[2][0]), 1.0f), (float)H), 2.0f));
+        sh[2] = red[4][0];
+    }
+    __syncthreads();
+    const float sx = sh[0], sy = sh[1], st = sh[2];
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        float4 e = ev[i];
+        e.x = __fsub_rn(e.x, sx); e.y = __fsub_rn(e.y, sy); e.z = __fsub_rn(e.z, st);
+        ev[i] = e;
+    }
+}
+
+// h-flip / t-flip with p = 1 (datasets/utils.py:18-35); one CTA per sample
+__global__ void __launch_bounds__(1024) flip_events_kernel(const float4 *src, float4 *dst, const int64_t *offsets, int W,
+                                                           int hflip, int tflip)
+{
+    const int64_t lo = offsets[blockIdx.x], hi = offsets[blockIdx.x + 1];
+    if (hi <= lo) return;
+    const float t_last = src[hi - 1].z;     // after the reversal this is events[0, 2]
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        float4 e = src[tflip ? (hi - 1 - (i - lo)) : i];
+        if (hflip) e.x = __fsub_rn((float)(W - 1), e.x);
+        if (tflip) { e.z = __fsub_rn(t_last, e.z); e.w = -e.w; }
+        dst[i] = e;
+    }
+}
+
 }  // namespace
+
+extern "C" int ec_center_events(float *events, const int64_t *offsets, int B, int H, int W, void *stream)
+{
+    EC_REQUIRE(events && offsets && B >= 0 && H > 0 && W > 0, "ec_center_events: bad arguments");
+    EC_REQUIRE(((uintptr_t)events & 15) == 0, "ec_center_events: events must be 16-byte aligned");
+    if (B == 0) return EC_OK;
+    center_events_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4 *>(events), offsets, H, W);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
+extern "C" int ec_flip_events(const float *src, float *dst, const int64_t *offsets, int B, int W, int hflip, int tflip,
+                              void *stream)
+{
+    EC_REQUIRE(src && dst && offsets && src != dst && B >= 0 && W > 0, "ec_flip_events: bad arguments (out of place only)");
+    EC_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "ec_flip_events: events must be 16-byte aligned");
+    if (B == 0) return EC_OK;
+    flip_events_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst),
+                                                              offsets, W, hflip, tflip);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
 
 extern "C" int ec_gather_rows(const float *src, const int32_t *idx, float *dst, int n_rows, int C, void *stream)
 {

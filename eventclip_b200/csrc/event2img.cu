@@ -23,6 +23,7 @@
 #include <mutex>
 #include <vector>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -674,6 +675,19 @@ int geometry(int H, int W, int &CS, int &RB, int &NT, size_t &smem)
     smem = (size_t)RB * per_row;
     smem = (smem + 31) & ~(size_t)15;
     NT = ((size_t)RB * W <= 16384) ? 512 : 1024;
+    // experiment hooks (profiling only): EC_E2I_CS forces a larger cluster, EC_E2I_NT the block size
+    if (const char *e = getenv("EC_E2I_CS")) {
+        const int want = atoi(e);
+        if (want > CS && want <= 8 && (want & (want - 1)) == 0) {
+            CS = want;
+            RB = (H + CS - 1) / CS;
+            smem = ((size_t)RB * per_row + 31) & ~(size_t)15;
+        }
+    }
+    if (const char *e = getenv("EC_E2I_NT")) {
+        const int want = atoi(e);
+        if (want == 256 || want == 512 || want == 1024) NT = want;
+    }
     return EC_OK;
 }
 

@@ -105,6 +105,27 @@ def raise_on_status(status):
         raise L.ECError("a per-pixel event count exceeded 65535 in one frame (packed histogram overflow)")
 
 
+def center_events(events, offsets_dev, shape):
+    """In place on the device (ec_center_events); offsets_dev: CUDA int64 [B+1]."""
+    _dev(events, torch.float32, "events")
+    _dev(offsets_dev, torch.int64, "offsets")
+    with torch.cuda.device(events.device):
+        L.check(L.load().ec_center_events(_ptr(events), _ptr(offsets_dev), offsets_dev.numel() - 1, shape[0], shape[1],
+                                          _stream()), "ec_center_events")
+    return events
+
+
+def flip_events(events, offsets_dev, W, hflip=False, tflip=False):
+    """Out of place (ec_flip_events): the reference's h-/t-flip TTA variants of a packed batch."""
+    _dev(events, torch.float32, "events")
+    _dev(offsets_dev, torch.int64, "offsets")
+    out = torch.empty_like(events)
+    with torch.cuda.device(events.device):
+        L.check(L.load().ec_flip_events(_ptr(events), _ptr(out), _ptr(offsets_dev), offsets_dev.numel() - 1, int(W),
+                                        int(bool(hflip)), int(bool(tflip)), _stream()), "ec_flip_events")
+    return out
+
+
 def event2img_geometry(shape):
     cs, nt, sm = C.c_int(), C.c_int(), C.c_int()
     L.check(L.load().ec_event2img_geometry(shape[0], shape[1], C.byref(cs), C.byref(nt), C.byref(sm)),

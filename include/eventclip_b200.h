@@ -91,6 +91,17 @@ EC_API int ec_event2img(const float *events, const ec_frame *frames, int n_frame
                  int out_fmt, int patch, int ldk, void *out, int32_t *dbg_counts, uint8_t *dbg_gray,
                  uint8_t *dbg_u8, int32_t *status, void *stream);
 
+/* DEVICE, in place.  center_events (datasets/utils.py:38-57), applied to every sample before the frames are built
+ * (datasets/caltech.py:176): per sample t -= min t, x -= ((x_max + x_min + 1) - W) // 2, y likewise (float32 math).
+ *   events device float32 [*,4];  offsets device int64 [B+1] */
+EC_API int ec_center_events(float *events, const int64_t *offsets, int B, int H, int W, void *stream);
+
+/* DEVICE, out of place.  The deterministic flips of the reference's test-time augmentation
+ * (datasets/utils.py:18-35 with p = 1, used at datasets/event2img.py:100-103): hflip x -> W-1-x;
+ * tflip reverses the event order of each sample, t -> t_last - t, p -> -p.  src/dst device float32 [*,4]. */
+EC_API int ec_flip_events(const float *src, float *dst, const int64_t *offsets, int B, int W, int hflip, int tflip,
+                          void *stream);
+
 /* Launch geometry ec_event2img will use for a sensor (for bench/roofline reporting). */
 EC_API int ec_event2img_geometry(int H, int W, int *cluster_size, int *threads, int *smem_bytes);
 

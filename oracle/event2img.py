@@ -149,3 +149,29 @@ def event2img_sample(events, shape, N, T, count_non_zero=False, background_mask=
                                           int(background_mask), selp, int(only_selected), _p(img, C.c_float),
                                           _p(valid, C.c_uint8)))
     return img, valid.astype(bool), K
+
+
+def center_events(events, shape):
+    """datasets/utils.py:38-57 (float32 arithmetic on a float32 [E,4] array, returns a new array)."""
+    ev = np.array(events, dtype=np.float32, copy=True)
+    H, W = shape
+    ev[:, 2] -= ev[:, 2].min()
+    x_min, x_max = ev[:, 0].min(), ev[:, 0].max()
+    y_min, y_max = ev[:, 1].min(), ev[:, 1].max()
+    x_shift = ((x_max + x_min + np.float32(1.)) - np.float32(W)) // np.float32(2.)
+    y_shift = ((y_max + y_min + np.float32(1.)) - np.float32(H)) // np.float32(2.)
+    ev[:, 0] -= x_shift
+    ev[:, 1] -= y_shift
+    return ev
+
+
+def flip_events(events, W, hflip=False, tflip=False):
+    """datasets/utils.py:18-23 (h-flip) and 26-35 (t-flip) with p = 1, in the order event2img.py:100-103 applies them."""
+    ev = np.array(events, dtype=np.float32, copy=True)
+    if hflip:
+        ev[:, 0] = np.float32(W - 1) - ev[:, 0]
+    if tflip:
+        ev = np.ascontiguousarray(np.flip(ev, axis=0))
+        ev[:, 2] = ev[0, 2] - ev[:, 2]
+        ev[:, 3] = -ev[:, 3]
+    return ev

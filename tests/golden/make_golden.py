@@ -237,6 +237,26 @@ def make_heads():
     print("heads_golden", len(out), "arrays")
 
 
+def make_event_transforms():
+    """datasets/utils.py center_events / flips on off-centre synthetic streams."""
+    from oracle import event2img as orc
+    U = ref_import.load_utils()
+    out = []
+    for seed, (shape, E) in enumerate([((180, 240), 5000), ((100, 120), 777), ((480, 640), 20000)]):
+        ev = synth_events(shape, E, 50 + seed, "clustered")
+        ev = ev[(ev[:, 0] < shape[1] * 0.6) & (ev[:, 1] < shape[0] * 0.7)].copy()
+        ev[:, 2] += np.float32(0.37)
+        ref = U.center_events(ev.copy(), resolution=shape)
+        h = U.random_flip_events_along_x(ev.copy(), resolution=shape, p=1.)
+        t = U.random_time_flip_events(ev.copy(), p=1.)
+        ht = U.random_time_flip_events(h.copy(), p=1.)
+        assert (ref == orc.center_events(ev, shape)).all()
+        out.append(dict(shape=list(shape), E=E, seed=50 + seed, n=int(len(ev)), events=sha(ev), centered=sha(ref),
+                        hflip=sha(h), tflip=sha(t), htflip=sha(ht)))
+    json.dump(out, open(os.path.join(HERE, "event_transforms_sha.json"), "w"), indent=1)
+    print("event_transforms", len(out))
+
+
 if __name__ == "__main__":
     assert ref_import.available(), "/root/reference is required to (re)generate the golden fixtures"
     vis = ref_import.load_vis()
@@ -244,4 +264,5 @@ if __name__ == "__main__":
     make_gray_lut(vis)
     make_event2img(vis)
     make_heads()
+    make_event_transforms()
     print("sizes:", {f: os.path.getsize(os.path.join(HERE, f)) for f in sorted(os.listdir(HERE)) if not f.endswith(".py")})

@@ -218,3 +218,73 @@ def test_cuda_graph_replay_matches_eager(cuda_dev):
         for k in ("full_logits", "logits", "probs", "top5_logits"):
             assert torch.equal(got[k], eager[k]), (seed, k)
     assert len(g.cache) == 2
+
+
+def test_few_shot_nimagenet_events_to_logits_vs_oracle(cuda_dev):
+    """BASELINE config 3 in miniature: few-shot joint adapter (text-trans, residual 0.95) on N-ImageNet-shaped streams
+    (480x640, 8-CTA cluster kernel, 14 chunks of which 2 host-drawn ones are used), ViT-B/16, 1000 classes."""
+    cfg = SENSORS["n_imagenet"]
+    q = dict(max_imgs=10, N=cfg["N"], split_method="event_count", convert_method="event_histogram", grayscale=True,
+             count_non_zero=False, background_mask=True)
+    B = 2
+    ev, off = synth_batch("n_imagenet", B, 900, kind="clustered")
+    arch = "ViT-B/16"
+    oracle = clip_oracle.build_clip(arch, seed=41)
+    text = clip_oracle.synth_text_feats(cfg["n_cls"], 512, 7)
+    model = clip.CLIP(arch)
+    model.load_state_dict(oracle.state_dict())
+    ad = dict(adapter_type="text-trans", in_dim=512, d_model=256, num_heads=4, ffn_dim=1024, norm_first=True,
+              num_layers=2, residual=0.95)
+    torch.manual_seed(3)
+    fs = FSCLIPClassifier(adapter_dict=ad, clip_dict=dict(clip_model=model.to(cuda_dev).eval(), prompt="a {}", class_names=None,
+                                                         agg_func="mean", text_feats=text),
+                          loss_dict=dict(use_logits_loss=True, use_probs_loss=False)).to(cuda_dev).eval()
+    fs.attach_event_frontend(q, cfg["shape"], cfg["max_n"])
+    T = fs.event_frontend.max_imgs
+    assert T == 2
+    torch.manual_seed(11)
+    sel = fs.event_frontend.draw_selection(off)          # the torch.randperm(14)[:2] draw of event2img.py:85
+    with torch.no_grad():
+        o = fs(dict(events=torch.from_numpy(ev).to(cuda_dev), event_offsets=torch.from_numpy(off), sel_idx=sel))
+    imgs, valids = [], []
+    for b in range(B):
+        im, va, K = orc.event2img_sample(ev[off[b]:off[b + 1]], cfg["shape"], cfg["N"], T, False, True, sel=sel[b],
+                                         only_selected=True)
+        assert K == 14
+        imgs.append(im)
+        valids.append(va)
+    imgs, valid = torch.from_numpy(np.stack(imgs)), torch.from_numpy(np.stack(valids))
+    with torch.no_grad():
+        feats = oracle.encode_image(imgs[valid])
+    ap = {k[len("adapter."):]: v.cpu() for k, v in fs.state_dict().items() if k.startswith("adapter.")}
+    adapter = lambda f, v: heads_oracle.adapter_forward(ap, f, v, num_heads=4, residual=0.95)
+    ref = heads_oracle.fs_head(feats, valid, fs.state_dict()["text_feats"].cpu(), 100.0, "mean", adapter)
+    assert rel(o["logits"], ref["logits"]) < 2e-2, rel(o["logits"], ref["logits"])
+    top5 = ref["logits"].topk(5, -1).indices
+    assert (o["top5_logits"][:, 0].cpu() == top5[:, 0]).all() or rel(o["logits"], ref["logits"]) < 5e-3
+
+
+def test_zero_shot_vitl14_nimagenet_vs_oracle(cuda_dev):
+    """BASELINE config 4 in miniature: zero-shot ViT-L/14 (L = 257 tokens, K = 588 patch GEMM padded to 592,
+    mma.sync attention fallback) on N-ImageNet-shaped streams."""
+    cfg = SENSORS["n_imagenet"]
+    q = dict(max_imgs=10, N=cfg["N"], split_method="event_count", convert_method="event_histogram", grayscale=True,
+             count_non_zero=False, background_mask=True)
+    ev, off = synth_batch("n_imagenet", 1, 901, kind="uniform", E=150000)
+    arch = "ViT-L/14"
+    oracle = clip_oracle.build_clip(arch, seed=42)
+    text = clip_oracle.synth_text_feats(cfg["n_cls"], 768, 8)
+    model = clip.CLIP(arch)
+    model.load_state_dict(oracle.state_dict())
+    zs = ZSCLIPClassifier(clip_dict=dict(clip_model=model.to(cuda_dev).eval(), prompt="a {}", class_names=None,
+                                         agg_func="mean", text_feats=text)).to(cuda_dev).eval()
+    zs.attach_event_frontend(q, cfg["shape"], cfg["max_n"])
+    with torch.no_grad():
+        o = zs(dict(events=torch.from_numpy(ev).to(cuda_dev), event_offsets=torch.from_numpy(off)))
+    im, va, K = orc.event2img_sample(ev, cfg["shape"], cfg["N"], 2, False, True)
+    assert K == 2 and va.all()
+    with torch.no_grad():
+        feats = oracle.encode_image(torch.from_numpy(im))
+    ref = heads_oracle.zs_head(feats, torch.from_numpy(va)[None], text, 100.0, "mean")
+    assert rel(o["logits"], ref["logits"]) < 2e-2, rel(o["logits"], ref["logits"])
+    assert (o["probs"].sum(-1).cpu() - 1).abs().max() < 1e-4

@@ -190,3 +190,30 @@ def test_full_size_properties(cuda_dev):
     ev2[:20000] = ev2[rng.permutation(20000)]
     c = e2i(torch.from_numpy(ev2).to(cuda_dev), off)
     assert torch.equal(c["img"], a["img"])
+
+
+def test_center_and_flip_events_on_device(cuda_dev, golden_dir):
+    """Row F1: ec_center_events / ec_flip_events against the reference's golden checksums and the oracle, on a packed
+    batch (one CTA per sample), then frames of the centred stream against the oracle."""
+    cases = json.load(open(os.path.join(golden_dir, "event_transforms_sha.json")))
+    from tests.test_oracle_golden import _transform_case
+    for c in cases:
+        shape, ev = _transform_case(c)
+        evs = [ev, ev[: len(ev) // 2].copy(), ev[len(ev) // 3:].copy()]
+        off = np.concatenate([[0], np.cumsum([len(e) for e in evs])]).astype(np.int64)
+        packed = torch.from_numpy(np.concatenate(evs)).to(cuda_dev)
+        offd = torch.from_numpy(off).to(cuda_dev)
+        for hf, tf, key in ((True, False, "hflip"), (False, True, "tflip"), (True, True, "htflip")):
+            out = ops.flip_events(packed, offd, shape[1], hf, tf).cpu().numpy()
+            assert sha(out[: len(ev)]) == c[key]
+            for i, e in enumerate(evs):
+                assert (out[off[i]:off[i + 1]] == orc.flip_events(e, shape[1], hf, tf)).all()
+        cen = ops.center_events(packed.clone(), offd, shape).cpu().numpy()
+        assert sha(cen[: len(ev)]) == c["centered"]
+        for i, e in enumerate(evs):
+            assert (cen[off[i]:off[i + 1]] == orc.center_events(e, shape)).all()
+    # centred stream -> frames
+    shape, ev = _transform_case(cases[0])
+    cen = ops.center_events(torch.from_numpy(ev).to(cuda_dev), torch.tensor([0, len(ev)], device=cuda_dev), shape)
+    fr = events2frames(cen, "event_count", "event_histogram", shape=shape, N=20000, grayscale=True)
+    assert (fr == orc.events2frames(orc.center_events(ev, shape), shape, 20000)).all()

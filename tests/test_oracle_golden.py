@@ -116,3 +116,23 @@ def test_hot_pixel_rule_ties_and_constant():
     gray, zeroed, st = orc.frame_from_counts(counts, False, True)
     assert zeroed[3, 4, 0] and zeroed.sum() == 1 and st["max"] == 3
     assert gray[3, 4] == 255 and gray[0, 0] == 255 and gray[5, 5] == 127
+
+
+def _transform_case(c):
+    shape = tuple(c["shape"])
+    ev = synth_events(shape, c["E"], c["seed"], "clustered")
+    ev = ev[(ev[:, 0] < shape[1] * 0.6) & (ev[:, 1] < shape[0] * 0.7)].copy()
+    ev[:, 2] += np.float32(0.37)
+    assert len(ev) == c["n"] and sha(ev) == c["events"]
+    return shape, ev
+
+
+def test_center_and_flip_events_vs_reference_golden(golden_dir):
+    """datasets/utils.py:18-57."""
+    for c in json.load(open(os.path.join(golden_dir, "event_transforms_sha.json"))):
+        shape, ev = _transform_case(c)
+        cen = orc.center_events(ev, shape)
+        assert sha(cen) == c["centered"] and cen[:, 2].min() == 0
+        assert sha(orc.flip_events(ev, shape[1], True, False)) == c["hflip"]
+        assert sha(orc.flip_events(ev, shape[1], False, True)) == c["tflip"]
+        assert sha(orc.flip_events(ev, shape[1], True, True)) == c["htflip"]
