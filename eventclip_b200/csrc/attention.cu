@@ -188,7 +188,7 @@ extern "C" int ec_attention(const void *qkv, void *out, int n_img, int L, int he
     EC_REQUIRE(qkv && out && n_img > 0 && L > 0 && heads > 0, "ec_attention: bad arguments");
     EC_REQUIRE(L <= 1024, "ec_attention: L=%d exceeds the shared-memory K/V staging limit", L);
     EC_REQUIRE(n_img <= 65535, "ec_attention: n_img=%d exceeds grid.y", n_img);
-    // tensor-memory kernel for L <= 256 (ViT-B/32, ViT-B/16); EC_ATTN=mma forces the mma.sync kernel below
+    // tensor-memory kernels for L <= 384 (every CLIP ViT at 224 px); EC_ATTN=mma forces the mma.sync kernel below
     static const bool force_mma = getenv("EC_ATTN") && std::string(getenv("EC_ATTN")) == "mma";
     if (!force_mma) {
         const int rc = ec::attention_tc(qkv, out, n_img, L, heads, (cudaStream_t)stream);

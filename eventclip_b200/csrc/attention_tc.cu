@@ -1,4 +1,4 @@
-// attention_tc.cu -- softmax(q k^T / sqrt(64)) v on the 5th-generation tensor cores (tcgen05 + TMEM), L <= 256.
+// attention_tc.cu -- softmax(q k^T / sqrt(64)) v on the 5th-generation tensor cores (tcgen05 + TMEM), L <= 384.
 //
 // Same contract as attention.cu (nn.MultiheadAttention core of openai-CLIP's ResidualAttentionBlock [3P]; LoRA variant
 // models/lora.py:165-303): qkv bf16 [n_img*L, 3d] -> out bf16 [n_img*L, d], head_dim 64.
@@ -184,6 +184,92 @@ __device__ __forceinline__ float fast_exp2(float x)
     return y;
 }
 
+// Softmax of one 128-query tile (thread = query row) followed by the O epilogue.
+template <uint32_t OCOL, uint32_t SUMCOL>
+__device__ __forceinline__ void softmax_tile(uint32_t lane_base, int L, int nch, bool live, int row, int lane, uint64_t *bar_p,
+                                             uint64_t *bar_o, uint32_t o_parity, uint64_t *bar_oe, __nv_bfloat16 *orow)
+{
+    const float sl2 = 0.125f * 1.4426950408889634f;
+                // Single pass over S (tensor-memory reads are the scarce resource: ~64 B/clk per SM).  Softmax is invariant to
+                // the constant subtracted before the exponential, so the reference point is the maximum of the FIRST 32 scores
+                // of the row instead of the exact row maximum; exponents are evaluated in fp32 (range 2^+-126, clamped at
+                // +120) and the denominators come from the tensor core (P . ones), so the result is the same softmax.
+                // P chunk c lands on columns [16c, 16c+16), which this thread has already read (chunks are taken in order).
+                if (live) {
+                    uint32_t va[32], vb[32];
+                    tmem_ld32_issue(lane_base, va);
+                    tmem_ld_wait();
+                    if (nch > 1) tmem_ld32_issue(lane_base + 32u, vb);
+                    float m = -INFINITY;
+    #pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < L) m = fmaxf(m, __uint_as_float(va[j]));
+                    const float ms = m * sl2;
+                    auto emit = [&](const uint32_t (&v)[32], int c) {
+                        uint32_t pk[16];
+                        const bool full = (c + 1) * 32 <= L;
+    #pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            float x0 = fminf(fmaf(__uint_as_float(v[j]), sl2, -ms), 120.f);
+                            float x1 = fminf(fmaf(__uint_as_float(v[j + 1]), sl2, -ms), 120.f);
+                            if (!full) {
+                                if (c * 32 + j >= L) x0 = -INFINITY;
+                                if (c * 32 + j + 1 >= L) x1 = -INFINITY;
+                            }
+                            __nv_bfloat162 hh = __floats2bfloat162_rn(fast_exp2(x0), fast_exp2(x1));
+                            pk[j >> 1] = *reinterpret_cast<uint32_t *>(&hh);
+                        }
+                        tmem_st16(lane_base + (uint32_t)(c * 16), pk);
+                    };
+                    for (int c = 0; c < nch; c += 2) {
+                        if (c > 0) {
+                            tmem_ld_wait();
+                            if (c + 1 < nch) tmem_ld32_issue(lane_base + (uint32_t)((c + 1) * 32), vb);
+                        }
+                        emit(va, c);
+                        if (c + 1 < nch) {
+                            tmem_ld_wait();
+                            if (c + 2 < nch) tmem_ld32_issue(lane_base + (uint32_t)((c + 2) * 32), va);
+                            emit(vb, c + 1);
+                        }
+                    }
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_p);
+                // epilogue: O / rowsum -> bf16 -> global
+                mbar_wait(bar_o, o_parity);
+                tc_fence_after();
+                if (!live) {      // nothing to store: keep the barrier protocol and move on
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_oe);
+                    return;
+                }
+                const float inv = 1.f / tmem_ld1(lane_base + SUMCOL);
+    #pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(lane_base + OCOL + (uint32_t)(c * 32), v);
+                    if (row < L) {
+    #pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 o;
+                            __nv_bfloat162 hh;
+                            hh = __floats2bfloat162_rn(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv); o.x = *reinterpret_cast<uint32_t *>(&hh);
+                            hh = __floats2bfloat162_rn(__uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv); o.y = *reinterpret_cast<uint32_t *>(&hh);
+                            hh = __floats2bfloat162_rn(__uint_as_float(v[j + 4]) * inv, __uint_as_float(v[j + 5]) * inv); o.z = *reinterpret_cast<uint32_t *>(&hh);
+                            hh = __floats2bfloat162_rn(__uint_as_float(v[j + 6]) * inv, __uint_as_float(v[j + 7]) * inv); o.w = *reinterpret_cast<uint32_t *>(&hh);
+                            *reinterpret_cast<uint4 *>(orow + c * 32 + j) = o;
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_oe);
+}
+
 // Persistent: one CTA per SM walks over (image, head) units.  Shared memory holds two units (the next one is fetched
 // while the current one is computed); tensor memory holds both 128-query tiles of a unit, each served by its own
 // softmax warpgroup, so the two tiles of a unit run side by side.
@@ -303,85 +389,145 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
             const int img = unit / heads, h = unit % heads;
             mbar_wait(&bar_s[t], uph);
             tc_fence_after();
-            // Single pass over S (tensor-memory reads are the scarce resource: ~64 B/clk per SM).  Softmax is invariant to
-            // the constant subtracted before the exponential, so the reference point is the maximum of the FIRST 32 scores
-            // of the row instead of the exact row maximum; exponents are evaluated in fp32 (range 2^+-126, clamped at
-            // +120) and the denominators come from the tensor core (P . ones), so the result is the same softmax.
-            // P chunk c lands on columns [16c, 16c+16), which this thread has already read (chunks are taken in order).
-            if (live) {
-                uint32_t va[32], vb[32];
-                tmem_ld32_issue(lane_base, va);
-                tmem_ld_wait();
-                if (nch > 1) tmem_ld32_issue(lane_base + 32u, vb);
-                float m = -INFINITY;
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (j < L) m = fmaxf(m, __uint_as_float(va[j]));
-                const float ms = m * sl2;
-                auto emit = [&](const uint32_t (&v)[32], int c) {
-                    uint32_t pk[16];
-                    const bool full = (c + 1) * 32 <= L;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        float x0 = fminf(fmaf(__uint_as_float(v[j]), sl2, -ms), 120.f);
-                        float x1 = fminf(fmaf(__uint_as_float(v[j + 1]), sl2, -ms), 120.f);
-                        if (!full) {
-                            if (c * 32 + j >= L) x0 = -INFINITY;
-                            if (c * 32 + j + 1 >= L) x1 = -INFINITY;
-                        }
-                        __nv_bfloat162 hh = __floats2bfloat162_rn(fast_exp2(x0), fast_exp2(x1));
-                        pk[j >> 1] = *reinterpret_cast<uint32_t *>(&hh);
-                    }
-                    tmem_st16(lane_base + (uint32_t)(c * 16), pk);
-                };
-                for (int c = 0; c < nch; c += 2) {
-                    if (c > 0) {
-                        tmem_ld_wait();
-                        if (c + 1 < nch) tmem_ld32_issue(lane_base + (uint32_t)((c + 1) * 32), vb);
-                    }
-                    emit(va, c);
-                    if (c + 1 < nch) {
-                        tmem_ld_wait();
-                        if (c + 2 < nch) tmem_ld32_issue(lane_base + (uint32_t)((c + 2) * 32), va);
-                        emit(vb, c + 1);
-                    }
-                }
+            softmax_tile<O_COL, SUM_COL>(lane_base, L, nch, live, row, lane, &bar_p[t], &bar_o[t], uph, &bar_oe[t],
+                                         p.out + ((size_t)img * L + row) * d + h * HD);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// Variant for 256 < L <= 384 (ViT-L/14: 257 tokens).  The S row no longer fits twice in tensor memory, so the 128-query
+// tiles of a unit are processed one after the other by a single softmax warpgroup:
+//   TMEM  S [0,384)  P [0,192)  O [384,448)  sums [448,464);   S = Q K^T is issued as N = 256 plus N = KP-256 MMAs.
+// Shared memory holds one unit (3 tiles each of Q, K, V); Q/K of the next unit are fetched as soon as the last S MMA
+// of the current one has retired, V after the last P V MMA.
+constexpr uint32_t BIG_O_COL = 384, BIG_SUM_COL = 448;
+constexpr int BIG_NTHREADS = 160;
+constexpr int BIG_TILES = 3;
+
+__global__ void __launch_bounds__(BIG_NTHREADS, 1)
+attention_tc_big_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
+{
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char *sQ = smem, *sK = smem + BIG_TILES * TILE_BYTES, *sV = smem + 2 * BIG_TILES * TILE_BYTES;
+    unsigned char *sOnes = smem + 3 * BIG_TILES * TILE_BYTES;
+    __shared__ __align__(8) uint64_t bar_qk, bar_v, bar_qk_free, bar_v_free, bar_s, bar_p, bar_o, bar_oe;
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int L = p.L, d = p.d, heads = p.heads;
+    const int KP = (L + 15) & ~15;
+    const int MT = (L + 127) >> 7;                    // 3 for L = 257
+    const int n_units = p.n_img * heads;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qkv) : "memory");
+        mbar_init(&bar_qk, 1); mbar_init(&bar_v, 1); mbar_init(&bar_qk_free, 1); mbar_init(&bar_v_free, 1);
+        mbar_init(&bar_s, 1); mbar_init(&bar_p, 4); mbar_init(&bar_o, 1); mbar_init(&bar_oe, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < ONES_BYTES / 4; i += BIG_NTHREADS) reinterpret_cast<uint32_t *>(sOnes)[i] = 0x3f803f80u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        auto load_qk = [&](int unit) {
+            const int img = unit / heads, h = unit % heads;
+            mbar_expect_tx(&bar_qk, (uint32_t)(2 * MT * TILE_BYTES));
+            for (int b = 0; b < MT; ++b) {
+                tma_load_3d(sK + b * TILE_BYTES, &map_qkv, &bar_qk, d + h * HD, b * 128, img);
+                tma_load_3d(sQ + b * TILE_BYTES, &map_qkv, &bar_qk, h * HD, b * 128, img);
             }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_p[t]);
-            // epilogue: O / rowsum -> bf16 -> global
-            mbar_wait(&bar_o[t], uph);
+        };
+        auto load_v = [&](int unit) {
+            const int img = unit / heads, h = unit % heads;
+            mbar_expect_tx(&bar_v, (uint32_t)(MT * TILE_BYTES));
+            for (int b = 0; b < MT; ++b) tma_load_3d(sV + b * TILE_BYTES, &map_qkv, &bar_v, 2 * d + h * HD, b * 128, img);
+        };
+        const int n1 = KP < 256 ? KP : 256, n2 = KP - n1;          // S is issued in two column blocks
+        const uint32_t idesc_s1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n1 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc_s2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n2 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc_1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint64_t odesc = make_desc(smem_u32(sOnes));
+        const uint64_t kdesc = make_desc(smem_u32(sK)), k2desc = make_desc(smem_u32(sK + 2 * TILE_BYTES));
+        const uint64_t vdesc = make_desc(smem_u32(sV));
+        if ((int)blockIdx.x < n_units && elect_one()) { load_qk(blockIdx.x); load_v(blockIdx.x); }
+        __syncwarp();
+        int i = 0;
+        uint32_t n = 0;                                   // tiles issued so far (parity source of the per-tile barriers)
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++i) {
+            const uint32_t uph = (uint32_t)i & 1;
+            const int next = unit + gridDim.x;
+            mbar_wait(&bar_qk, uph);
             tc_fence_after();
-            if (!live) {      // nothing to store: keep the barrier protocol and move on
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_oe[t]);
-                continue;
-            }
-            const float inv = 1.f / tmem_ld1(lane_base + SUM_COL);
-            __nv_bfloat16 *orow = p.out + ((size_t)img * L + row) * d + h * HD;
+            for (int t = 0; t < MT; ++t, ++n) {
+                if (n >= 1) { mbar_wait(&bar_oe, (n - 1) & 1); tc_fence_after(); }   // previous tile's TMEM fully consumed
+                const uint64_t qdesc = make_desc(smem_u32(sQ + t * TILE_BYTES));
+                if (elect_one()) {
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t v[32];
-                tmem_ld32(lane_base + O_COL + (uint32_t)(c * 32), v);
-                if (row < L) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        uint4 o;
-                        __nv_bfloat162 hh;
-                        hh = __floats2bfloat162_rn(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv); o.x = *reinterpret_cast<uint32_t *>(&hh);
-                        hh = __floats2bfloat162_rn(__uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv); o.y = *reinterpret_cast<uint32_t *>(&hh);
-                        hh = __floats2bfloat162_rn(__uint_as_float(v[j + 4]) * inv, __uint_as_float(v[j + 5]) * inv); o.z = *reinterpret_cast<uint32_t *>(&hh);
-                        hh = __floats2bfloat162_rn(__uint_as_float(v[j + 6]) * inv, __uint_as_float(v[j + 7]) * inv); o.w = *reinterpret_cast<uint32_t *>(&hh);
-                        *reinterpret_cast<uint4 *>(orow + c * 32 + j) = o;
+                    for (int k = 0; k < 4; ++k) {
+                        umma_ss(tmem_base, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s1, k != 0);
+                        if (n2 > 0) umma_ss(tmem_base + 256, qdesc + (uint64_t)(2 * k), k2desc + (uint64_t)(2 * k), idesc_s2, k != 0);
                     }
+                    umma_commit(&bar_s);
+                    if (t == MT - 1) umma_commit(&bar_qk_free);
                 }
+                __syncwarp();
+                if (t == MT - 1 && next < n_units) {          // Q and K of this unit are dead: fetch the next unit's
+                    mbar_wait(&bar_qk_free, uph);
+                    if (elect_one()) load_qk(next);
+                    __syncwarp();
+                }
+                mbar_wait(&bar_p, n & 1);                    // P is in tensor memory
+                if (t == 0) mbar_wait(&bar_v, uph);
+                tc_fence_after();
+                if (elect_one()) {
+                    for (int j = 0; j < KP / 16; ++j) {
+                        umma_ts(tmem_base + BIG_O_COL, tmem_base + (uint32_t)(8 * j), vdesc + (uint64_t)(128 * j), idesc_o, j != 0);
+                        umma_ts(tmem_base + BIG_SUM_COL, tmem_base + (uint32_t)(8 * j), odesc, idesc_1, j != 0);
+                    }
+                    umma_commit(&bar_o);
+                    if (t == MT - 1) umma_commit(&bar_v_free);
+                }
+                __syncwarp();
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_oe[t]);
+            if (next < n_units) {
+                mbar_wait(&bar_v_free, uph);
+                if (elect_one()) load_v(next);
+                __syncwarp();
+            }
+        }
+    } else {
+        const int quarter = warp & 3;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const int nch = (KP + 31) >> 5;
+        uint32_t n = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            const int img = unit / heads, h = unit % heads;
+            for (int t = 0; t < MT; ++t, ++n) {
+                const int row = t * 128 + quarter * 32 + lane;
+                const bool live = t * 128 + quarter * 32 < L;
+                mbar_wait(&bar_s, n & 1);
+                tc_fence_after();
+                softmax_tile<BIG_O_COL, BIG_SUM_COL>(lane_base, L, nch, live, row, lane, &bar_p, &bar_o, n & 1, &bar_oe,
+                                                     p.out + ((size_t)img * L + row) * d + h * HD);
+            }
         }
     }
 
@@ -418,7 +564,7 @@ namespace ec {
 // Returns EC_OK when the tcgen05 kernel was launched, EC_ERR_UNSUPPORTED when the shape is outside its range.
 int attention_tc(const void *qkv, void *out, int n_img, int L, int heads, cudaStream_t stream)
 {
-    if (L > 256 || n_img > 65535) return EC_ERR_UNSUPPORTED;
+    if (L > 384) return EC_ERR_UNSUPPORTED;
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return EC_ERR_CUDA; }
     const int d = heads * HD;
@@ -432,18 +578,21 @@ int attention_tc(const void *qkv, void *out, int n_img, int L, int heads, cudaSt
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (attention) failed with CUresult %d", (int)r); return EC_ERR_CUDA; }
     const size_t smem = 2 * STAGE_BYTES + ONES_BYTES + 1024;
+    const size_t smem_big = 3 * BIG_TILES * TILE_BYTES + ONES_BYTES + 1024;
     static bool attr_set[64] = {false};
     int dev_id = 0;
     EC_CUDA_CHECK(cudaGetDevice(&dev_id));
     if (dev_id < 64 && !attr_set[dev_id]) {
         EC_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        EC_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
         attr_set[dev_id] = true;
     }
     AttnParams p;
     p.out = (__nv_bfloat16 *)out; p.L = L; p.heads = heads; p.d = d; p.n_img = n_img;
     const int units = n_img * heads;
     const int grid = units < sm_count() ? units : sm_count();
-    attention_tc_kernel<<<grid, NTHREADS, smem, stream>>>(map, p);
+    if (L > 256) attention_tc_big_kernel<<<grid, BIG_NTHREADS, smem_big, stream>>>(map, p);
+    else attention_tc_kernel<<<grid, NTHREADS, smem, stream>>>(map, p);
     EC_CUDA_CHECK(cudaGetLastError());
     return EC_OK;
 }
