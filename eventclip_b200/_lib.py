@@ -42,6 +42,8 @@ SIGNATURES = {
     "ec_gemm_bf16": ([_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp], _i),
     "ec_layernorm": ([_vp, _i64, _vp, _vp, _i, _i, _vp, _vp, _vp], _i),
     "ec_attention": ([_vp, _vp, _i, _i, _i, _vp], _i),
+    "ec_attention_ex": ([_vp, _vp, _i, _i, _i, _i, _vp], _i),
+    "ec_embed_tokens": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp], _i),
     "ec_cls_rows": ([_vp, _vp, _vp, _i, _i, _i, _vp], _i),
     "ec_f32_to_bf16": ([_vp, _vp, _i64, _vp], _i),
     "ec_im2col": ([_vp, _i, _i, _i, _i, _vp, _vp], _i),

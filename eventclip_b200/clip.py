@@ -79,6 +79,52 @@ def _attn_weights(attn):
     return W, lora_in, attn.in_proj_bias, oW, ob, lora_out
 
 
+def pack_blocks(resblocks, d, dev):
+    """bf16 GEMM weights (LoRA factors merged, models/lora.py:138-149) + fp32 biases / LayerNorm affine per block."""
+    f32 = lambda t: t.detach().to(torch.float32).contiguous()
+    blocks = []
+    for blk in resblocks:
+        W, lora_in, ib, oW, ob, lora_out = _attn_weights(blk.attn)
+        W = f32(W)
+        if lora_in is None:
+            w_in = ops.f32_to_bf16(W)
+        else:
+            w_in = torch.empty((3 * d, d), dtype=torch.bfloat16, device=dev)
+            for j, n in enumerate("qkv"):
+                up = getattr(lora_in, f"lora_up_{n}", None)
+                down = getattr(lora_in, f"lora_down_{n}", None)
+                ops.lora_merge(W[j * d:(j + 1) * d], f32(up) if up is not None else None,
+                               f32(down) if down is not None else None, out=w_in[j * d:(j + 1) * d])
+        if lora_out is None:
+            w_out = ops.f32_to_bf16(f32(oW))
+        else:
+            w_out = ops.lora_merge(f32(oW), f32(lora_out.lora_up.weight), f32(lora_out.lora_down.weight))
+        blocks.append(dict(
+            ln1=(f32(blk.ln_1.weight), f32(blk.ln_1.bias)), ln2=(f32(blk.ln_2.weight), f32(blk.ln_2.bias)),
+            w_in=w_in, b_in=f32(ib), w_out=w_out, b_out=f32(ob),
+            w_fc=ops.f32_to_bf16(f32(blk.mlp.c_fc.weight)), b_fc=f32(blk.mlp.c_fc.bias),
+            w_proj=ops.f32_to_bf16(f32(blk.mlp.c_proj.weight)), b_proj=f32(blk.mlp.c_proj.bias)))
+    return blocks
+
+
+def run_blocks(x, blocks, n_seq, Ltok, d, heads, causal=False):
+    """x: fp32 residual stream [n_seq*Ltok, d], updated in place by the GEMM epilogues."""
+    M, dev = n_seq * Ltok, x.device
+    xn = torch.empty((M, d), dtype=torch.bfloat16, device=dev)
+    qkv = torch.empty((M, 3 * d), dtype=torch.bfloat16, device=dev)
+    att = torch.empty((M, d), dtype=torch.bfloat16, device=dev)
+    hid = torch.empty((M, 4 * d), dtype=torch.bfloat16, device=dev)
+    for b in blocks:
+        ops.layernorm(x, *b["ln1"], M, d, out_bf16=xn)
+        ops.gemm_bf16(xn, b["w_in"], b["b_in"], "bf16", out=qkv)
+        ops.attention(qkv, att, n_seq, Ltok, heads, causal=causal)
+        ops.gemm_bf16(att, b["w_out"], b["b_out"], "f32_resadd", out=x, res=x)
+        ops.layernorm(x, *b["ln2"], M, d, out_bf16=xn)
+        ops.gemm_bf16(xn, b["w_fc"], b["b_fc"], "bf16_qgelu", out=hid)
+        ops.gemm_bf16(hid, b["w_proj"], b["b_proj"], "f32_resadd", out=x, res=x)
+    return x
+
+
 class VisionTransformer(nn.Module):
     def __init__(self, input_resolution, patch_size, width, layers, heads, output_dim):
         super().__init__()
@@ -134,28 +180,7 @@ class VisionTransformer(nn.Module):
         pk["ln_pre"] = (f32(self.ln_pre.weight), f32(self.ln_pre.bias))
         pk["ln_post"] = (f32(self.ln_post.weight), f32(self.ln_post.bias))
         pk["proj"] = ops.f32_to_bf16(f32(self.proj).t().contiguous())   # [C, d] so that out = x @ proj
-        blocks = []
-        for blk in self.transformer.resblocks:
-            W, lora_in, ib, oW, ob, lora_out = _attn_weights(blk.attn)
-            W = f32(W)
-            if lora_in is None:
-                w_in = ops.f32_to_bf16(W)
-            else:
-                w_in = torch.empty((3 * d, d), dtype=torch.bfloat16, device=dev)
-                for j, n in enumerate("qkv"):
-                    up = getattr(lora_in, f"lora_up_{n}", None)
-                    down = getattr(lora_in, f"lora_down_{n}", None)
-                    ops.lora_merge(W[j * d:(j + 1) * d], f32(up) if up is not None else None,
-                                   f32(down) if down is not None else None, out=w_in[j * d:(j + 1) * d])
-            if lora_out is None:
-                w_out = ops.f32_to_bf16(f32(oW))
-            else:
-                w_out = ops.lora_merge(f32(oW), f32(lora_out.lora_up.weight), f32(lora_out.lora_down.weight))
-            blocks.append(dict(
-                ln1=(f32(blk.ln_1.weight), f32(blk.ln_1.bias)), ln2=(f32(blk.ln_2.weight), f32(blk.ln_2.bias)),
-                w_in=w_in, b_in=f32(ib), w_out=w_out, b_out=f32(ob),
-                w_fc=ops.f32_to_bf16(f32(blk.mlp.c_fc.weight)), b_fc=f32(blk.mlp.c_fc.bias),
-                w_proj=ops.f32_to_bf16(f32(blk.mlp.c_proj.weight)), b_proj=f32(blk.mlp.c_proj.bias)))
+        blocks = pack_blocks(self.transformer.resblocks, d, dev)
         pk["blocks"] = blocks
         self._packed, self._packed_key = pk, key
         return pk
@@ -179,18 +204,7 @@ class VisionTransformer(nn.Module):
         x = torch.empty((M, d), dtype=torch.float32, device=dev)        # fp32 residual stream
         ops.layernorm(x0, *pk["ln_pre"], M, d, out_f32=x)
         del x0
-        xn = torch.empty((M, d), dtype=torch.bfloat16, device=dev)
-        qkv = torch.empty((M, 3 * d), dtype=torch.bfloat16, device=dev)
-        att = torch.empty((M, d), dtype=torch.bfloat16, device=dev)
-        hid = torch.empty((M, 4 * d), dtype=torch.bfloat16, device=dev)
-        for b in pk["blocks"]:
-            ops.layernorm(x, *b["ln1"], M, d, out_bf16=xn)
-            ops.gemm_bf16(xn, b["w_in"], b["b_in"], "bf16", out=qkv)
-            ops.attention(qkv, att, n_img, Ltok, heads)
-            ops.gemm_bf16(att, b["w_out"], b["b_out"], "f32_resadd", out=x, res=x)
-            ops.layernorm(x, *b["ln2"], M, d, out_bf16=xn)
-            ops.gemm_bf16(xn, b["w_fc"], b["b_fc"], "bf16_qgelu", out=hid)
-            ops.gemm_bf16(hid, b["w_proj"], b["b_proj"], "f32_resadd", out=x, res=x)
+        run_blocks(x, pk["blocks"], n_img, Ltok, d, heads)
         cls = torch.empty((n_img, d), dtype=torch.bfloat16, device=dev)
         ops.layernorm(x, *pk["ln_post"], n_img, d, row_stride=Ltok * d, out_bf16=cls)
         return ops.gemm_bf16(cls, pk["proj"], None, "f32")
@@ -206,16 +220,38 @@ class VisionTransformer(nn.Module):
         return self.forward_patches(patches, n)
 
 
-class CLIP(nn.Module):
-    """Image tower + logit scale.  The text tower is SURVEY section 8(f) row F3 (needs the BPE vocabulary, absent
-    offline): encode_text raises; classifiers take precomputed text features instead (models/clip_cls.py:71-72)."""
+# text tower shapes of the released models: (width, layers, heads, context, vocab)
+TEXT = {
+    "ViT-B/32": (512, 12, 8, 77, 49408),
+    "ViT-B/16": (512, 12, 8, 77, 49408),
+    "ViT-L/14": (768, 12, 12, 77, 49408),
+    "ViT-tiny/32": (64, 2, 1, 16, 97),
+    "ViT-tiny/16": (64, 2, 1, 16, 97),
+}
 
-    def __init__(self, arch):
+
+class CLIP(nn.Module):
+    """Image tower + logit scale (+ optional text tower).  With text=True the module also
+    owns openai-CLIP's text parameters under their original names (token_embedding, positional_embedding,
+    transformer.resblocks.*, ln_final, text_projection) and encode_text runs them through the same kernels with the
+    causal tcgen05 attention.  The BPE tokenizer is not part of this (vocabulary absent offline): callers pass ids."""
+
+    def __init__(self, arch, text=False):
         super().__init__()
         patch, width, layers, heads, embed = ARCHS[arch]
         self.arch = arch
         self.visual = VisionTransformer(224, patch, width, layers, heads, embed)
         self.logit_scale = nn.Parameter(torch.ones([]) * math.log(1 / 0.07))
+        self.has_text = text
+        if text:
+            w, tl, th, ctx, vocab = TEXT[arch]
+            self.context_length, self.vocab_size = ctx, vocab
+            self.token_embedding = nn.Embedding(vocab, w)
+            self.positional_embedding = nn.Parameter(0.01 * torch.randn(ctx, w))
+            self.transformer = Transformer(w, tl, th)
+            self.ln_final = nn.LayerNorm(w)
+            self.text_projection = nn.Parameter(w ** -0.5 * torch.randn(w, embed))
+            self._tpacked, self._tpacked_key = None, None
 
     @property
     def dtype(self):
@@ -224,8 +260,36 @@ class CLIP(nn.Module):
     def encode_image(self, image):
         return self.visual(image)
 
+    def _text_params(self):
+        return [self.token_embedding.weight, self.positional_embedding, self.text_projection] + \
+            list(self.transformer.parameters()) + list(self.ln_final.parameters())
+
     def encode_text(self, text):
-        raise NotImplementedError("text tower not built (SURVEY section 8(f) F3); pass text features to the classifier")
+        """text: int [n, context_length] token ids (clip.tokenize output) -> fp32 [n, embed_dim].
+        Features are read at the end-of-text position = argmax of the ids, as in openai-CLIP."""
+        if not self.has_text:
+            raise NotImplementedError("this CLIP object was built without the text tower (CLIP(arch, text=True)); "
+                                      "pass precomputed text features to the classifier instead")
+        dev = self.text_projection.device
+        key = tuple((p.data_ptr(), p._version) for p in self._text_params())
+        if self._tpacked is None or key != self._tpacked_key:
+            f32 = lambda t: t.detach().to(torch.float32).contiguous()
+            w = self.transformer.width
+            self._tpacked = dict(table=f32(self.token_embedding.weight), pos=f32(self.positional_embedding),
+                                 blocks=pack_blocks(self.transformer.resblocks, w, dev),
+                                 ln=(f32(self.ln_final.weight), f32(self.ln_final.bias)),
+                                 proj=ops.f32_to_bf16(f32(self.text_projection).t().contiguous()))
+            self._tpacked_key = key
+        pk = self._tpacked
+        n, ctx = text.shape
+        w, heads = self.transformer.width, self.transformer.heads
+        x = ops.embed_tokens(pk["table"], text.to(device=dev, dtype=torch.int32).contiguous(), pk["pos"])
+        run_blocks(x, pk["blocks"], n, ctx, w, heads, causal=True)
+        eot = (torch.arange(n) * ctx + text.cpu().argmax(dim=-1)).to(torch.int32)
+        rows = ops.gather_rows(x, eot.to(dev), n)
+        feat = torch.empty((n, w), dtype=torch.bfloat16, device=dev)
+        ops.layernorm(rows, *pk["ln"], n, w, out_bf16=feat)
+        return ops.gemm_bf16(feat, pk["proj"], None, "f32")
 
 
 def init_weights_(model, seed=0, logit_scale=100.0):
@@ -256,6 +320,20 @@ def init_weights_(model, seed=0, logit_scale=100.0):
         rn(b.mlp.c_fc.bias, 0.02)
         rn(b.mlp.c_proj.weight, proj_std)
         rn(b.mlp.c_proj.bias, 0.02)
+    if getattr(model, "has_text", False):
+        w, tl = model.transformer.width, model.transformer.layers
+        a_std, p_std, f_std = w ** -0.5, (w ** -0.5) * ((2 * tl) ** -0.5), (2 * w) ** -0.5
+        rn(model.token_embedding.weight, 0.02)
+        rn(model.positional_embedding, 0.01)
+        rn(model.text_projection, w ** -0.5)
+        rn(model.ln_final.weight, 0.1, 1.0)
+        rn(model.ln_final.bias, 0.05)
+        for b in model.transformer.resblocks:
+            rn(b.ln_1.weight, 0.1, 1.0); rn(b.ln_1.bias, 0.05); rn(b.ln_2.weight, 0.1, 1.0); rn(b.ln_2.bias, 0.05)
+            rn(b.attn.in_proj_weight, a_std); rn(b.attn.in_proj_bias, 0.02)
+            rn(b.attn.out_proj.weight, p_std); rn(b.attn.out_proj.bias, 0.02)
+            rn(b.mlp.c_fc.weight, f_std); rn(b.mlp.c_fc.bias, 0.02)
+            rn(b.mlp.c_proj.weight, p_std); rn(b.mlp.c_proj.bias, 0.02)
     with torch.no_grad():
         model.logit_scale.fill_(math.log(logit_scale))
     return model
@@ -269,10 +347,10 @@ def _transform(n_px=224):
                       T.Normalize((0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711))])
 
 
-def load(name, device="cuda", seed=0, state_dict=None):
+def load(name, device="cuda", seed=0, state_dict=None, text=True):
     """clip.load(arch, device) -> (model, preprocess)  (test.py:26, train.py:26).
     Checkpoints cannot be downloaded offline: weights are seeded random unless `state_dict` is given."""
-    model = CLIP(name)
+    model = CLIP(name, text=text)
     init_weights_(model, seed)
     if state_dict is not None:
         model.load_state_dict(state_dict, strict=False)
@@ -280,4 +358,5 @@ def load(name, device="cuda", seed=0, state_dict=None):
 
 
 def tokenize(texts, context_length=77):
-    raise NotImplementedError("BPE vocabulary is not available offline (SURVEY section 8(f) F3)")
+    raise NotImplementedError("the BPE vocabulary file is not available offline; pass token ids to encode_text, a "
+                              "tokenizer callable in clip_dict['tokenizer'], or text features in clip_dict['text_feats']")

@@ -185,15 +185,21 @@ __global__ void __launch_bounds__(WARPS * 32, 2) attention_kernel(const __nv_bfl
 
 extern "C" int ec_attention(const void *qkv, void *out, int n_img, int L, int heads, void *stream)
 {
+    return ec_attention_ex(qkv, out, n_img, L, heads, 0, stream);
+}
+
+extern "C" int ec_attention_ex(const void *qkv, void *out, int n_img, int L, int heads, int causal, void *stream)
+{
     EC_REQUIRE(qkv && out && n_img > 0 && L > 0 && heads > 0, "ec_attention: bad arguments");
     EC_REQUIRE(L <= 1024, "ec_attention: L=%d exceeds the shared-memory K/V staging limit", L);
     EC_REQUIRE(n_img <= 65535, "ec_attention: n_img=%d exceeds grid.y", n_img);
     // tensor-memory kernels for L <= 384 (every CLIP ViT at 224 px); EC_ATTN=mma forces the mma.sync kernel below
     static const bool force_mma = getenv("EC_ATTN") && std::string(getenv("EC_ATTN")) == "mma";
     if (!force_mma) {
-        const int rc = ec::attention_tc(qkv, out, n_img, L, heads, (cudaStream_t)stream);
+        const int rc = ec::attention_tc(qkv, out, n_img, L, heads, causal, (cudaStream_t)stream);
         if (rc != EC_ERR_UNSUPPORTED) return rc;
     }
+    EC_REQUIRE(!causal, "ec_attention_ex: the causal mask is only built into the tensor-memory kernels (L <= 384)");
     const int Lp = (L + 15) & ~15;
     const size_t smem = (size_t)3 * Lp * LDS * sizeof(__nv_bfloat16);
     EC_REQUIRE(smem <= 220 * 1024, "ec_attention: L=%d needs %zu bytes of shared memory", L, smem);

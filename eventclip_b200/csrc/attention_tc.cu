@@ -33,7 +33,7 @@ constexpr int ONES_BYTES = 2048;                // 16 rows x 64 bf16 of 1.0: B o
 
 struct AttnParams {
     __nv_bfloat16 *out;
-    int L, heads, d, n_img;
+    int L, heads, d, n_img, causal;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -185,10 +185,13 @@ __device__ __forceinline__ float fast_exp2(float x)
 }
 
 // Softmax of one 128-query tile (thread = query row) followed by the O epilogue.
+// causal != 0: key j contributes to query `row` only if j <= row (text tower).
 template <uint32_t OCOL, uint32_t SUMCOL>
 __device__ __forceinline__ void softmax_tile(uint32_t lane_base, int L, int nch, bool live, int row, int lane, uint64_t *bar_p,
-                                             uint64_t *bar_o, uint32_t o_parity, uint64_t *bar_oe, __nv_bfloat16 *orow)
+                                             uint64_t *bar_o, uint32_t o_parity, uint64_t *bar_oe, __nv_bfloat16 *orow,
+                                             int causal)
 {
+    const int klim = causal ? min(L, row + 1) : L;     // keys [0, klim) are visible to this row
     const float sl2 = 0.125f * 1.4426950408889634f;
                 // Single pass over S (tensor-memory reads are the scarce resource: ~64 B/clk per SM).  Softmax is invariant to
                 // the constant subtracted before the exponential, so the reference point is the maximum of the FIRST 32 scores
@@ -203,18 +206,18 @@ __device__ __forceinline__ void softmax_tile(uint32_t lane_base, int L, int nch,
                     float m = -INFINITY;
     #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (j < L) m = fmaxf(m, __uint_as_float(va[j]));
+                        if (j < klim) m = fmaxf(m, __uint_as_float(va[j]));
                     const float ms = m * sl2;
                     auto emit = [&](const uint32_t (&v)[32], int c) {
                         uint32_t pk[16];
-                        const bool full = (c + 1) * 32 <= L;
+                        const bool full = (c + 1) * 32 <= klim;
     #pragma unroll
                         for (int j = 0; j < 32; j += 2) {
                             float x0 = fminf(fmaf(__uint_as_float(v[j]), sl2, -ms), 120.f);
                             float x1 = fminf(fmaf(__uint_as_float(v[j + 1]), sl2, -ms), 120.f);
                             if (!full) {
-                                if (c * 32 + j >= L) x0 = -INFINITY;
-                                if (c * 32 + j + 1 >= L) x1 = -INFINITY;
+                                if (c * 32 + j >= klim) x0 = -INFINITY;
+                                if (c * 32 + j + 1 >= klim) x1 = -INFINITY;
                             }
                             __nv_bfloat162 hh = __floats2bfloat162_rn(fast_exp2(x0), fast_exp2(x1));
                             pk[j >> 1] = *reinterpret_cast<uint32_t *>(&hh);
@@ -390,7 +393,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
             mbar_wait(&bar_s[t], uph);
             tc_fence_after();
             softmax_tile<O_COL, SUM_COL>(lane_base, L, nch, live, row, lane, &bar_p[t], &bar_o[t], uph, &bar_oe[t],
-                                         p.out + ((size_t)img * L + row) * d + h * HD);
+                                         p.out + ((size_t)img * L + row) * d + h * HD, p.causal);
         }
     }
 
@@ -526,7 +529,7 @@ attention_tc_big_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnP
                 mbar_wait(&bar_s, n & 1);
                 tc_fence_after();
                 softmax_tile<BIG_O_COL, BIG_SUM_COL>(lane_base, L, nch, live, row, lane, &bar_p, &bar_o, n & 1, &bar_oe,
-                                                     p.out + ((size_t)img * L + row) * d + h * HD);
+                                                     p.out + ((size_t)img * L + row) * d + h * HD, p.causal);
             }
         }
     }
@@ -562,7 +565,7 @@ EncodeTiledFn get_encode()
 namespace ec {
 
 // Returns EC_OK when the tcgen05 kernel was launched, EC_ERR_UNSUPPORTED when the shape is outside its range.
-int attention_tc(const void *qkv, void *out, int n_img, int L, int heads, cudaStream_t stream)
+int attention_tc(const void *qkv, void *out, int n_img, int L, int heads, int causal, cudaStream_t stream)
 {
     if (L > 384) return EC_ERR_UNSUPPORTED;
     EncodeTiledFn enc = get_encode();
@@ -588,7 +591,7 @@ int attention_tc(const void *qkv, void *out, int n_img, int L, int heads, cudaSt
         attr_set[dev_id] = true;
     }
     AttnParams p;
-    p.out = (__nv_bfloat16 *)out; p.L = L; p.heads = heads; p.d = d; p.n_img = n_img;
+    p.out = (__nv_bfloat16 *)out; p.L = L; p.heads = heads; p.d = d; p.n_img = n_img; p.causal = causal;
     const int units = n_img * heads;
     const int grid = units < sm_count() ? units : sm_count();
     if (L > 256) attention_tc_big_kernel<<<grid, BIG_NTHREADS, smem_big, stream>>>(map, p);

@@ -233,7 +233,30 @@ __global__ void __launch_bounds__(1024) flip_events_kernel(const float4 *src, fl
     }
 }
 
+// x[n*L + l, :] = table[tokens[n, l], :] + pos[l, :]   (CLIP text tower input, openai-CLIP encode_text [3P])
+__global__ void embed_tokens_kernel(const float *table, const int32_t *tokens, const float *pos, float *out, int n_rows, int L,
+                                    int d, int vocab)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n_rows * d) return;
+    const int r = (int)(i / d), c = (int)(i % d);
+    int tok = tokens[r];
+    tok = min(max(tok, 0), vocab - 1);
+    out[i] = table[(size_t)tok * d + c] + pos[(size_t)(r % L) * d + c];
+}
+
 }  // namespace
+
+extern "C" int ec_embed_tokens(const float *table, const int32_t *tokens, const float *pos, float *out, int n_seq, int L,
+                               int d, int vocab, void *stream)
+{
+    EC_REQUIRE(table && tokens && pos && out && n_seq > 0 && L > 0 && d > 0 && vocab > 0, "ec_embed_tokens: bad arguments");
+    const int64_t n = (int64_t)n_seq * L * d;
+    embed_tokens_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(table, tokens, pos, out, n_seq * L, L, d,
+                                                                                       vocab);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
 
 extern "C" int ec_center_events(float *events, const int64_t *offsets, int B, int H, int W, void *stream)
 {

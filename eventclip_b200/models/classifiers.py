@@ -72,7 +72,8 @@ class _CLIPClassifierBase(nn.Module):
         names = self.class_names if class_names is None else class_names
         from .. import clip
         prompts = [self.prompt.format(c.lower().replace("_", " ")) for c in names]
-        tokens = torch.cat([clip.tokenize(p) for p in prompts]).to(self.device)   # raises offline
+        tokenize = self.clip_dict.get("tokenizer", None) or clip.tokenize          # clip.tokenize raises offline (no BPE vocab)
+        tokens = torch.cat([tokenize(p) for p in prompts]).to(self.device)
         feats = ops.l2norm_rows(self.model.encode_text(tokens).float().contiguous())
         if class_names is None or self._same_class_names(class_names):
             self.text_feats = feats

@@ -161,11 +161,24 @@ def layernorm(x, gamma, beta, M, d, row_stride=None, out_bf16=None, out_f32=None
     L.check(rc, "ec_layernorm")
 
 
-def attention(qkv, out, n_img, Ltok, heads):
+def attention(qkv, out, n_img, Ltok, heads, causal=False):
     _dev(qkv, torch.bfloat16, "qkv")
     with torch.cuda.device(qkv.device):
-        rc = L.load().ec_attention(_ptr(qkv), _ptr(out), n_img, Ltok, heads, _stream())
+        rc = L.load().ec_attention_ex(_ptr(qkv), _ptr(out), n_img, Ltok, heads, int(bool(causal)), _stream())
     L.check(rc, "ec_attention")
+    return out
+
+
+def embed_tokens(table, tokens_i32, pos):
+    """x[n*L + l] = table[tokens[n,l]] + pos[l]  (fp32 [n*L, d])."""
+    _dev(table, torch.float32, "table")
+    _dev(tokens_i32, torch.int32, "tokens")
+    n, Lc = tokens_i32.shape
+    d = table.shape[1]
+    out = torch.empty((n * Lc, d), dtype=torch.float32, device=table.device)
+    with torch.cuda.device(table.device):
+        L.check(L.load().ec_embed_tokens(_ptr(table), _ptr(tokens_i32), _ptr(pos), _ptr(out), n, Lc, d, table.shape[0],
+                                         _stream()), "ec_embed_tokens")
     return out
 
 

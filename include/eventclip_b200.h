@@ -134,6 +134,15 @@ EC_API int ec_layernorm(const float *x, int64_t row_stride_in, const float *gamm
  * softmax(q k^T / sqrt(64)) v per (image, head); head_dim is 64 for every CLIP ViT. */
 EC_API int ec_attention(const void *qkv, void *out, int n_img, int L, int heads, void *stream);
 
+/* Same with an optional causal mask (key j visible to query i iff j <= i): the attention of CLIP's text tower
+ * (openai-CLIP encode_text [3P], called at models/clip_cls.py:84, models/clip_cls_ft.py:152). */
+EC_API int ec_attention_ex(const void *qkv, void *out, int n_seq, int L, int heads, int causal, void *stream);
+
+/* Text-tower input: out[n*L + l, :] = token_embedding[tokens[n,l], :] + positional_embedding[l, :]  (fp32).
+ * tokens device int32 [n_seq, L]. */
+EC_API int ec_embed_tokens(const float *table, const int32_t *tokens, const float *pos, float *out, int n_seq, int L, int d,
+                           int vocab, void *stream);
+
 /* Writes the class-token rows of the pre-LN token matrix: x[n*L + 0, :] = class_embedding + pos[0]. */
 EC_API int ec_cls_rows(float *x, const float *class_embedding, const float *pos, int n_img, int L, int d, void *stream);
 

@@ -81,15 +81,46 @@ class VisionTransformer(nn.Module):
         return self.ln_post(x[:, 0]) @ self.proj
 
 
-class CLIP(nn.Module):
-    """Shell exposing what the reference touches: .visual, .logit_scale, .encode_image, .dtype."""
+# text tower shapes of the released models: (width, layers, heads, context, vocab); embed dim = the image tower's
+TEXT = {
+    "ViT-B/32": (512, 12, 8, 77, 49408),
+    "ViT-B/16": (512, 12, 8, 77, 49408),
+    "ViT-L/14": (768, 12, 12, 77, 49408),
+    "ViT-tiny/32": (64, 2, 1, 16, 97),
+    "ViT-tiny/16": (64, 2, 1, 16, 97),
+}
 
-    def __init__(self, arch):
+
+class CausalBlock(Block):
+    """Text-tower block: same as Block with the additive upper-triangular -inf attention mask."""
+
+    def forward(self, x):
+        L = x.shape[0]
+        mask = torch.full((L, L), float("-inf"), dtype=x.dtype).triu_(1)
+        h = self.ln_1(x)
+        x = x + self.attn(h, h, h, need_weights=False, attn_mask=mask)[0]
+        return x + self.mlp(self.ln_2(x))
+
+
+class CLIP(nn.Module):
+    """Shell exposing what the reference touches: .visual, .logit_scale, .encode_image, .encode_text, .dtype."""
+
+    def __init__(self, arch, text=False):
         super().__init__()
         patch, d, layers, heads, out_dim = ARCHS[arch]
         self.arch = arch
         self.visual = VisionTransformer(patch, d, layers, heads, out_dim)
         self.logit_scale = nn.Parameter(torch.ones([]) * math.log(1 / 0.07))
+        self.has_text = text
+        if text:      # openai-CLIP text tower (SURVEY section 8(f) row F3), same parameter names
+            w, tl, th, ctx, vocab = TEXT[arch]
+            self.context_length, self.vocab_size = ctx, vocab
+            self.token_embedding = nn.Embedding(vocab, w)
+            self.positional_embedding = nn.Parameter(0.01 * torch.randn(ctx, w))
+            self.transformer = Tower(w, tl, th)
+            self.transformer.resblocks = nn.Sequential(*[CausalBlock(w, th) for _ in range(tl)])
+            self.ln_final = nn.LayerNorm(w)
+            self.text_projection = nn.Parameter(w ** -0.5 * torch.randn(w, out_dim))
 
     @property
     def dtype(self):
@@ -99,7 +130,13 @@ class CLIP(nn.Module):
         return self.visual(image.type(self.dtype))
 
     def encode_text(self, tokens):
-        raise NotImplementedError("text tower is SURVEY section 8(f) row F3; tests pre-seed text_feats")
+        """tokens int [n, context] -> [n, embed]; features are read at the end-of-text position = argmax of the ids."""
+        if not self.has_text:
+            raise NotImplementedError("build the oracle with text=True, or pre-seed text_feats")
+        x = self.token_embedding(tokens).type(self.dtype) + self.positional_embedding.type(self.dtype)
+        x = self.transformer(x.transpose(0, 1)).transpose(0, 1)
+        x = self.ln_final(x)
+        return x[torch.arange(x.shape[0]), tokens.argmax(dim=-1)] @ self.text_projection
 
 
 def init_clip_(model, seed, logit_scale=100.0):
@@ -131,13 +168,39 @@ def init_clip_(model, seed, logit_scale=100.0):
         rn(b.mlp.c_fc.bias, 0.02)
         rn(b.mlp.c_proj.weight, proj_std)
         rn(b.mlp.c_proj.bias, 0.02)
+    if getattr(model, "has_text", False):
+        w, tl = model.transformer.width, model.transformer.layers
+        a_std, p_std, f_std = w ** -0.5, (w ** -0.5) * ((2 * tl) ** -0.5), (2 * w) ** -0.5
+        rn(model.token_embedding.weight, 0.02)
+        rn(model.positional_embedding, 0.01)
+        rn(model.text_projection, w ** -0.5)
+        rn(model.ln_final.weight, 0.1, 1.0)
+        rn(model.ln_final.bias, 0.05)
+        for b in model.transformer.resblocks:
+            rn(b.ln_1.weight, 0.1, 1.0); rn(b.ln_1.bias, 0.05); rn(b.ln_2.weight, 0.1, 1.0); rn(b.ln_2.bias, 0.05)
+            rn(b.attn.in_proj_weight, a_std); rn(b.attn.in_proj_bias, 0.02)
+            rn(b.attn.out_proj.weight, p_std); rn(b.attn.out_proj.bias, 0.02)
+            rn(b.mlp.c_fc.weight, f_std); rn(b.mlp.c_fc.bias, 0.02)
+            rn(b.mlp.c_proj.weight, p_std); rn(b.mlp.c_proj.bias, 0.02)
     with torch.no_grad():
         model.logit_scale.fill_(math.log(logit_scale))
     return model
 
 
-def build_clip(arch, seed=0):
-    return init_clip_(CLIP(arch), seed).eval()
+def build_clip(arch, seed=0, text=False):
+    return init_clip_(CLIP(arch, text=text), seed).eval()
+
+
+def synth_tokens(n, context, vocab, seed):
+    """Random prompts in CLIP's token format: <sot> body <eot> 0-padding; <eot> = vocab-1 is the largest id."""
+    g = torch.Generator().manual_seed(seed)
+    tok = torch.zeros(n, context, dtype=torch.long)
+    for i in range(n):
+        ln = int(torch.randint(3, context - 1, (1,), generator=g))
+        tok[i, 0] = vocab - 2
+        tok[i, 1:ln] = torch.randint(1, vocab - 2, (ln - 1,), generator=g)
+        tok[i, ln] = vocab - 1
+    return tok
 
 
 def synth_text_feats(n_cls, C, seed):

@@ -288,3 +288,29 @@ def test_zero_shot_vitl14_nimagenet_vs_oracle(cuda_dev):
     ref = heads_oracle.zs_head(feats, torch.from_numpy(va)[None], text, 100.0, "mean")
     assert rel(o["logits"], ref["logits"]) < 2e-2, rel(o["logits"], ref["logits"])
     assert (o["probs"].sum(-1).cpu() - 1).abs().max() < 1e-4
+
+
+def test_text_features_from_prompts(cuda_dev):
+    """get_text_feats without pre-seeded features: prompt formatting (clip_cls.py:79-85) -> caller-supplied tokenizer ->
+    encode_text on the device -> L2 normalisation, cached afterwards."""
+    arch = "ViT-tiny/32"
+    oracle = clip_oracle.build_clip(arch, seed=24, text=True)
+    model = clip.CLIP(arch, text=True)
+    model.load_state_dict(oracle.state_dict())
+    seen = []
+
+    def toy_tokenizer(prompt):      # stands in for clip.tokenize (BPE vocabulary absent offline): int [1, context]
+        seen.append(prompt)
+        ids = [95] + [1 + (ord(ch) % 90) for ch in prompt][:13] + [96]
+        return torch.tensor([ids + [0] * (16 - len(ids))])
+
+    names = ["Faces_easy", "airplanes", "car_side"]
+    zs = ZSCLIPClassifier(clip_dict=dict(clip_model=model.to(cuda_dev).eval(), prompt="a point cloud image of a {}",
+                                         class_names=names, agg_func="mean", tokenizer=toy_tokenizer)).to(cuda_dev).eval()
+    with torch.no_grad():
+        tf = zs.get_text_feats()
+        ref = oracle.encode_text(torch.cat([toy_tokenizer(p) for p in seen[:3]]))
+    assert seen[:3] == ["a point cloud image of a faces easy", "a point cloud image of a airplanes",
+                        "a point cloud image of a car side"]
+    ref = ref / ref.norm(dim=-1, keepdim=True)
+    assert rel(tf, ref) < 2e-2 and zs.get_text_feats() is tf      # cached (clip_cls.py:71-72)

@@ -136,3 +136,34 @@ def test_encoder_large_archs_vs_oracle(cuda_dev, arch):
         ref = oracle.encode_image(imgs)
         got = model.encode_image(imgs.to(cuda_dev))
     assert rel(got, ref) < 2e-2, rel(got, ref)
+
+
+@pytest.mark.parametrize("L,heads,n_seq", [(77, 8, 5), (16, 1, 3), (197, 12, 2), (257, 16, 1)])
+def test_causal_attention(cuda_dev, L, heads, n_seq):
+    """Text-tower attention: key j is visible to query i iff j <= i (both tensor-memory kernels)."""
+    g = torch.Generator().manual_seed(L + 1)
+    d = heads * 64
+    qkv = bf(torch.randn(n_seq * L, 3 * d, generator=g))
+    out = torch.empty(n_seq * L, d, dtype=torch.bfloat16, device=cuda_dev)
+    ops.attention(qkv.to(cuda_dev), out, n_seq, L, heads, causal=True)
+    q, k, v = [t.view(n_seq, L, heads, 64).transpose(1, 2) for t in qkv.float().chunk(3, -1)]
+    s = q @ k.transpose(-1, -2) / 8.0 + torch.full((L, L), float("-inf")).triu_(1)
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(n_seq * L, d)
+    assert rel(out.float(), ref) < 8e-3, rel(out.float(), ref)
+
+
+@pytest.mark.parametrize("arch,n", [("ViT-tiny/32", 7), ("ViT-B/16", 5)])
+def test_text_tower_vs_oracle(cuda_dev, arch, n):
+    """encode_text from token ids (models/clip_cls.py:84) against the fp32 oracle."""
+    oracle = clip_oracle.build_clip(arch, seed=23, text=True)
+    model = clip.CLIP(arch, text=True)
+    model.load_state_dict(oracle.state_dict())
+    model = model.to(cuda_dev).eval()
+    tok = clip_oracle.synth_tokens(n, oracle.context_length, oracle.vocab_size, 4)
+    with torch.no_grad():
+        ref = oracle.encode_text(tok)
+        got = model.encode_text(tok.to(cuda_dev))
+    assert got.shape == ref.shape
+    assert rel(got, ref) < 2e-2, rel(got, ref)
+    with pytest.raises(NotImplementedError):
+        clip.CLIP(arch).encode_text(tok)
