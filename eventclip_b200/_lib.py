@@ -55,6 +55,16 @@ SIGNATURES = {
     "ec_layernorm_f32": ([_vp, _vp, _vp, _i, _i, _vp, _vp], _i),
     "ec_gather_rows": ([_vp, _vp, _vp, _i, _i, _vp], _i),
     "ec_l2norm_rows": ([_vp, _vp, _i, _i, _vp], _i),
+    # fine-tune step
+    "ec_layernorm_bwd": ([_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _vp, _i64, _vp], _i),
+    "ec_quickgelu": ([_vp, _vp, _i64, _vp], _i),
+    "ec_quickgelu_bwd": ([_vp, _vp, _vp, _i64, _vp], _i),
+    "ec_transpose_bf16": ([_vp, _vp, _i, _i, _i64, _i64, _vp], _i),
+    "ec_attention_bwd": ([_vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
+    "ec_adam": ([_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _vp], _i),
+    "ec_gemm_f32_strided": ([_vp, _i64, _i64, _vp, _i64, _i64, _i, _i, _i, _f, _vp, _i64, _i, _vp], _i),
+    "ec_l2norm_rows_bwd": ([_vp, _vp, _vp, _i, _i, _vp, _vp], _i),
+    "ec_ce_loss_bwd": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp], _i),
 }
 
 _lib = None

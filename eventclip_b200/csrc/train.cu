@@ -1,0 +1,279 @@
+// train.cu -- elementwise / row kernels of the fine-tune step's backward pass (SURVEY.md section 8 row A12:
+// models/clip_cls_ft.py:214-269 trains through model.visual; the reference relies on autograd for all of this).
+//   LayerNorm backward, QuickGELU forward/backward on the saved pre-activation, bf16 transpose (weight-gradient GEMMs
+//   reduce over the token dimension), Adam (method.py:150-191 uses torch.optim.Adam with two learning rates).
+#include "common.cuh"
+
+namespace {
+
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma ; one warp per row; dx is ADDED to `acc` when given
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float *__restrict__ x, int64_t x_stride,
+                                                            const float *__restrict__ dy, const float *__restrict__ gamma,
+                                                            const float *__restrict__ acc, int64_t acc_stride, int M, int d,
+                                                            float *__restrict__ dx, int64_t dx_stride)
+{
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float *xr = x + (size_t)row * x_stride, *dr = dy + (size_t)row * d;
+    float s = 0.f;
+    for (int c = lane; c < d; c += 32) s += xr[c];
+    const float mean = ec::warp_sum(s) / (float)d;
+    float q = 0.f;
+    for (int c = lane; c < d; c += 32) { const float t = xr[c] - mean; q += t * t; }
+    const float rstd = rsqrtf(ec::warp_sum(q) / (float)d + 1e-5f);
+    float sg = 0.f, sgx = 0.f;
+    for (int c = lane; c < d; c += 32) {
+        const float g = dr[c] * gamma[c], xh = (xr[c] - mean) * rstd;
+        sg += g; sgx += g * xh;
+    }
+    sg = ec::warp_sum(sg) / (float)d; sgx = ec::warp_sum(sgx) / (float)d;
+    for (int c = lane; c < d; c += 32) {
+        const float g = dr[c] * gamma[c], xh = (xr[c] - mean) * rstd;
+        float v = rstd * (g - sg - xh * sgx);
+        if (acc) v += acc[(size_t)row * acc_stride + c];
+        dx[(size_t)row * dx_stride + c] = v;
+    }
+}
+
+__global__ void quickgelu_kernel(const __nv_bfloat16 *a, __nv_bfloat16 *h, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = __bfloat162float(a[i]);
+    h[i] = __float2bfloat16(x / (1.f + __expf(-1.702f * x)));
+}
+
+// d/da [a * sigmoid(1.702 a)] = s + 1.702 a s (1 - s)
+__global__ void quickgelu_bwd_kernel(const __nv_bfloat16 *a, const __nv_bfloat16 *dh, __nv_bfloat16 *da, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = __bfloat162float(a[i]);
+    const float s = 1.f / (1.f + __expf(-1.702f * x));
+    da[i] = __float2bfloat16(__bfloat162float(dh[i]) * (s + 1.702f * x * s * (1.f - s)));
+}
+
+// out[c, r] = in[r, c]; 32x32 tiles through shared memory
+__global__ void transpose_bf16_kernel(const __nv_bfloat16 *in, __nv_bfloat16 *out, int rows, int cols, int64_t ld_in,
+                                      int64_t ld_out)
+{
+    __shared__ __nv_bfloat16 t[32][34];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        t[i][threadIdx.x] = (r < rows && c < cols) ? in[(size_t)r * ld_in + c] : __float2bfloat16(0.f);
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (c < cols && r < rows) out[(size_t)c * ld_out + r] = t[threadIdx.x][i];
+    }
+}
+
+__global__ void adam_kernel(float *p, const float *g, float *m, float *v, int64_t n, float lr, float b1, float b2, float eps,
+                            float wd, float bc1, float bc2)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float gi = g[i] + wd * p[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);   // torch.optim.Adam: denom = sqrt(v_hat) + eps
+}
+
+
+// out[m,n] (+)= sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn]; 32x32 tiles (LoRA factor gradients, head backward: small shapes)
+__global__ void __launch_bounds__(256) sgemm_strided_kernel(const float *__restrict__ A, int64_t sam, int64_t sak,
+                                                            const float *__restrict__ B, int64_t sbk, int64_t sbn, int M, int N,
+                                                            int K, float alpha, float *__restrict__ out, int64_t ldo, int accumulate)
+{
+    __shared__ float sa[32][33], sb[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+    const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        for (int i = ty; i < 32; i += 8) {
+            // pick the thread->element mapping that is contiguous in memory for each operand
+            if (sak == 1) { const int m = m0 + i, k = k0 + tx; sa[i][tx] = (m < M && k < K) ? A[m * sam + k] : 0.f; }
+            else          { const int m = m0 + tx, k = k0 + i; sa[tx][i] = (m < M && k < K) ? A[m * sam + k * sak] : 0.f; }
+            if (sbn == 1) { const int k = k0 + i, n = n0 + tx; sb[i][tx] = (k < K && n < N) ? B[k * sbk + n] : 0.f; }
+            else          { const int k = k0 + tx, n = n0 + i; sb[tx][i] = (k < K && n < N) ? B[k * sbk + n * sbn] : 0.f; }
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const float b = sb[k][tx];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r] += sa[ty + 8 * r][k] * b;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int m = m0 + ty + 8 * r, n = n0 + tx;
+        if (m < M && n < N) {
+            float *o = out + (size_t)m * ldo + n;
+            *o = accumulate ? *o + alpha * acc[r] : alpha * acc[r];
+        }
+    }
+}
+
+// Backward of F.normalize(x, dim=-1) (eps 1e-12) followed by the valid mask: dx = (dy - y <y, dy>) / max(|x|, eps), y = x / max(|x|, eps)
+__global__ void __launch_bounds__(256) l2norm_bwd_kernel(const float *__restrict__ x, const float *__restrict__ dy,
+                                                         const uint8_t *__restrict__ mask, int M, int C, float *__restrict__ dx)
+{
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float *xr = x + (size_t)row * C, *dr = dy + (size_t)row * C;
+    float *o = dx + (size_t)row * C;
+    if (mask && !mask[row]) { for (int c = lane; c < C; c += 32) o[c] = 0.f; return; }
+    float ss = 0.f, sd = 0.f;
+    for (int c = lane; c < C; c += 32) { ss += xr[c] * xr[c]; sd += xr[c] * dr[c]; }
+    ss = ec::warp_sum(ss); sd = ec::warp_sum(sd);
+    const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    const float dot = sd * inv;                       // <y, dy>
+    for (int c = lane; c < C; c += 32) o[c] = (dr[c] - xr[c] * inv * dot) * inv;
+}
+
+// Loss head of the fine-tune step (clip_cls_ft.py:191-212 aggregate, 258-269 F.cross_entropy on the aggregated logits):
+// one warp per sample; writes the per-sample loss, the gradient of the MEAN loss w.r.t. full_logits, and (one CTA only,
+// after a grid-wide count) nothing else -- the mean is taken by mean_kernel below so the result is order-deterministic.
+__global__ void __launch_bounds__(256) ce_bwd_kernel(const float *__restrict__ full, const uint8_t *__restrict__ valid,
+                                                     const int32_t *__restrict__ labels, int B, int T, int K, int agg,
+                                                     float *__restrict__ loss_b, float *__restrict__ dfull)
+{
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= B) return;
+    int nv = 0;
+    for (int t = 0; t < T; ++t) nv += valid[b * T + t] ? 1 : 0;
+    const float w = agg == EC_AGG_MEAN ? 1.f / (float)nv : 1.f;     // nv == 0 gives inf/nan exactly like the reference's 0/0
+    const float *fb = full + (size_t)b * T * K;
+    const int y = labels[b];
+    float mx = -INFINITY;
+    for (int k = lane; k < K; k += 32) {
+        float z = 0.f;
+        for (int t = 0; t < T; ++t) z += fb[(size_t)t * K + k];
+        mx = fmaxf(mx, z * w);
+    }
+    mx = ec::warp_max(mx);
+    float se = 0.f, zy = 0.f;
+    for (int k = lane; k < K; k += 32) {
+        float z = 0.f;
+        for (int t = 0; t < T; ++t) z += fb[(size_t)t * K + k];
+        z *= w;
+        se += __expf(z - mx);
+        if (k == y) zy = z;
+    }
+    se = ec::warp_sum(se); zy = ec::warp_sum(zy);
+    const float lse = mx + __logf(se);
+    if (lane == 0) loss_b[b] = lse - zy;
+    const float invB = 1.f / (float)B;
+    for (int k = lane; k < K; k += 32) {
+        float z = 0.f;
+        for (int t = 0; t < T; ++t) z += fb[(size_t)t * K + k];
+        z *= w;
+        const float g = (__expf(z - lse) - (k == y ? 1.f : 0.f)) * invB * w;
+        // every view slot receives the gradient of the sum (the reference sums over all T rows; invalid rows are zero
+        // features, whose gradient is cut by the mask downstream)
+        for (int t = 0; t < T; ++t) dfull[((size_t)b * T + t) * K + k] = g;
+    }
+}
+
+__global__ void mean_kernel(const float *v, int n, float *out)
+{
+    __shared__ float s[32];
+    float a = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a += v[i];
+    a = ec::warp_sum(a);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        a = threadIdx.x < (blockDim.x >> 5) ? s[threadIdx.x] : 0.f;
+        a = ec::warp_sum(a);
+        if (threadIdx.x == 0) out[0] = a / (float)n;
+    }
+}
+
+}  // namespace
+
+extern "C" int ec_layernorm_bwd(const float *x, int64_t x_stride, const float *dy, const float *gamma, const float *acc,
+                                int64_t acc_stride, int M, int d, float *dx, int64_t dx_stride, void *stream)
+{
+    EC_REQUIRE(x && dy && gamma && dx && M > 0 && d > 0, "ec_layernorm_bwd: bad arguments");
+    layernorm_bwd_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, x_stride, dy, gamma, acc, acc_stride, M, d, dx,
+                                                                        dx_stride);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
+extern "C" int ec_quickgelu(const void *a, void *h, int64_t n, void *stream)
+{
+    EC_REQUIRE(a && h && n >= 0, "ec_quickgelu: bad arguments");
+    if (n == 0) return EC_OK;
+    quickgelu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)a, (__nv_bfloat16 *)h, n);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
+extern "C" int ec_quickgelu_bwd(const void *a, const void *dh, void *da, int64_t n, void *stream)
+{
+    EC_REQUIRE(a && dh && da && n >= 0, "ec_quickgelu_bwd: bad arguments");
+    if (n == 0) return EC_OK;
+    quickgelu_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)a,
+                                                                                        (const __nv_bfloat16 *)dh,
+                                                                                        (__nv_bfloat16 *)da, n);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
+extern "C" int ec_transpose_bf16(const void *in, void *out, int rows, int cols, int64_t ld_in, int64_t ld_out, void *stream)
+{
+    EC_REQUIRE(in && out && rows > 0 && cols > 0 && ld_in >= cols && ld_out >= rows, "ec_transpose_bf16: bad arguments");
+    transpose_bf16_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16 *)in, (__nv_bfloat16 *)out, rows, cols, ld_in, ld_out);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
+extern "C" int ec_adam(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, int step, void *stream)
+{
+    EC_REQUIRE(param && grad && exp_avg && exp_avg_sq && n >= 0 && step >= 1, "ec_adam: bad arguments");
+    if (n == 0) return EC_OK;
+    const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
+                                                                               eps, weight_decay, bc1, bc2);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
+extern "C" int ec_gemm_f32_strided(const float *A, int64_t sam, int64_t sak, const float *B, int64_t sbk, int64_t sbn, int M, int N,
+                                   int K, float alpha, float *out, int64_t ldo, int accumulate, void *stream)
+{
+    EC_REQUIRE(A && B && out && M > 0 && N > 0 && K > 0 && ldo >= N, "ec_gemm_f32_strided: bad arguments");
+    sgemm_strided_kernel<<<dim3((N + 31) / 32, (M + 31) / 32), 256, 0, (cudaStream_t)stream>>>(A, sam, sak, B, sbk, sbn, M, N, K, alpha, out,
+                                                                                               ldo, accumulate);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
+extern "C" int ec_l2norm_rows_bwd(const float *x, const float *dy, const uint8_t *mask, int M, int C, float *dx, void *stream)
+{
+    EC_REQUIRE(x && dy && dx && M > 0 && C > 0, "ec_l2norm_rows_bwd: bad arguments");
+    l2norm_bwd_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, dy, mask, M, C, dx);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
+extern "C" int ec_ce_loss_bwd(const float *full_logits, const uint8_t *valid, const int32_t *labels, int B, int T, int n_cls, int agg,
+                              float *loss_per_sample, float *loss_mean, float *d_full, void *stream)
+{
+    EC_REQUIRE(full_logits && valid && labels && loss_per_sample && loss_mean && d_full && B > 0 && T > 0 && n_cls > 0,
+               "ec_ce_loss_bwd: bad arguments");
+    EC_REQUIRE(agg == EC_AGG_SUM || agg == EC_AGG_MEAN, "ec_ce_loss_bwd: training supports agg sum / mean (got %d)", agg);
+    ce_bwd_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(full_logits, valid, labels, B, T, n_cls, agg, loss_per_sample, d_full);
+    mean_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(loss_per_sample, B, loss_mean);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}

@@ -301,3 +301,118 @@ def l2norm_rows(x):
     with torch.cuda.device(x.device):
         L.check(L.load().ec_l2norm_rows(_ptr(x), _ptr(out), M, Cdim, _stream()), "ec_l2norm_rows")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ fine-tune step
+def layernorm_bwd(x, dy, gamma, M, d, acc=None, x_stride=None, dx=None, dx_stride=None, acc_stride=None):
+    """dx = (acc +) LayerNorm'(x) . dy; strides let ln_post touch only the class-token rows."""
+    _dev(x, torch.float32, "x")
+    _dev(dy, torch.float32, "dy")
+    if dx is None:
+        dx = torch.empty((M, d), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        L.check(L.load().ec_layernorm_bwd(_ptr(x), int(x_stride or d), _ptr(dy), _ptr(gamma), _ptr(acc), int(acc_stride or d),
+                                          M, d, _ptr(dx), int(dx_stride or d), _stream()), "ec_layernorm_bwd")
+    return dx
+
+
+def quickgelu(a, out=None):
+    _dev(a, torch.bfloat16, "a")
+    out = torch.empty_like(a) if out is None else out
+    with torch.cuda.device(a.device):
+        L.check(L.load().ec_quickgelu(_ptr(a), _ptr(out), a.numel(), _stream()), "ec_quickgelu")
+    return out
+
+
+def quickgelu_bwd(a, dh, out=None):
+    _dev(a, torch.bfloat16, "a")
+    _dev(dh, torch.bfloat16, "dh")
+    out = torch.empty_like(a) if out is None else out
+    with torch.cuda.device(a.device):
+        L.check(L.load().ec_quickgelu_bwd(_ptr(a), _ptr(dh), _ptr(out), a.numel(), _stream()), "ec_quickgelu_bwd")
+    return out
+
+
+def transpose_bf16(x, out=None, pad=8):
+    """x bf16 [R, Ccols] -> bf16 [Ccols, Rp] with Rp = R rounded up to `pad` (zero filled): the K-major operand of a
+    weight-gradient GEMM."""
+    _dev(x, torch.bfloat16, "x")
+    R, Cc = x.shape
+    Rp = (R + pad - 1) // pad * pad
+    if out is None:
+        out = torch.zeros((Cc, Rp), dtype=torch.bfloat16, device=x.device) if Rp != R else \
+            torch.empty((Cc, Rp), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        L.check(L.load().ec_transpose_bf16(_ptr(x), _ptr(out), R, Cc, x.stride(0), out.stride(0), _stream()),
+                "ec_transpose_bf16")
+    return out
+
+
+def attention_bwd(qkv, o, d_o, n_img, Ltok, heads, out=None):
+    _dev(qkv, torch.bfloat16, "qkv")
+    _dev(o, torch.bfloat16, "o")
+    _dev(d_o, torch.bfloat16, "d_o")
+    out = torch.empty_like(qkv) if out is None else out
+    with torch.cuda.device(qkv.device):
+        L.check(L.load().ec_attention_bwd(_ptr(qkv), _ptr(o), _ptr(d_o), _ptr(out), n_img, Ltok, heads, _stream()),
+                "ec_attention_bwd")
+    return out
+
+
+def adam(param, grad, exp_avg, exp_avg_sq, lr, step, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    for t, n in ((param, "param"), (grad, "grad"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        _dev(t, torch.float32, n)
+    with torch.cuda.device(param.device):
+        L.check(L.load().ec_adam(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), float(lr),
+                                 float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step), _stream()),
+                "ec_adam")
+
+
+def mm_f32(A, B, trans_a=False, trans_b=False, out=None, accumulate=False, alpha=1.0):
+    """fp32 matrix product of 2-D views (any strides): out (+)= alpha * op(A) @ op(B)."""
+    if trans_a:
+        A = A.t()
+    if trans_b:
+        B = B.t()
+    M, K = A.shape
+    K2, N = B.shape
+    if K != K2:
+        raise L.ECError(f"mm_f32: inner dimensions differ ({K} vs {K2})")
+    if not (A.is_cuda and B.is_cuda and A.dtype == B.dtype == torch.float32):
+        raise L.ECError("mm_f32 needs fp32 CUDA tensors (no CPU fallback exists)")
+    L.require_device(A.device.index)
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    with torch.cuda.device(A.device):
+        L.check(L.load().ec_gemm_f32_strided(_ptr(A), A.stride(0), A.stride(1), _ptr(B), B.stride(0), B.stride(1), M, N, K,
+                                             float(alpha), _ptr(out), out.stride(0), int(bool(accumulate)), _stream()),
+                "ec_gemm_f32_strided")
+    return out
+
+
+def l2norm_rows_bwd(x, dy, mask_u8=None):
+    _dev(x, torch.float32, "x")
+    _dev(dy, torch.float32, "dy")
+    M, Cdim = x.shape
+    dx = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        L.check(L.load().ec_l2norm_rows_bwd(_ptr(x), _ptr(dy), _ptr(mask_u8), M, Cdim, _ptr(dx), _stream()),
+                "ec_l2norm_rows_bwd")
+    return dx
+
+
+def ce_loss_bwd(full_logits, valid_u8, labels_i32, agg):
+    """Returns (per-sample loss [B], mean loss [1], d mean-loss / d full_logits [B,T,K])."""
+    _dev(full_logits, torch.float32, "full_logits")
+    _dev(labels_i32, torch.int32, "labels")
+    B, T, K = full_logits.shape
+    loss_b = torch.empty(B, dtype=torch.float32, device=full_logits.device)
+    loss = torch.empty(1, dtype=torch.float32, device=full_logits.device)
+    dfull = torch.empty_like(full_logits)
+    agg_id = {"sum": L.EC_AGG["sum"], "mean": L.EC_AGG["mean"]}.get(agg)
+    if agg_id is None:
+        raise L.ECError(f"training supports agg_func 'sum' or 'mean', got {agg!r}")
+    with torch.cuda.device(full_logits.device):
+        L.check(L.load().ec_ce_loss_bwd(_ptr(full_logits), _ptr(valid_u8), _ptr(labels_i32), B, T, K, agg_id, _ptr(loss_b),
+                                        _ptr(loss), _ptr(dfull), _stream()), "ec_ce_loss_bwd")
+    return loss_b, loss, dfull

@@ -196,6 +196,45 @@ EC_API int ec_l2norm_rows(const float *x, float *out, int M, int C, void *stream
 /* fp32 LayerNorm rows [M,d] -> fp32 (adapter pre-norm). */
 EC_API int ec_layernorm_f32(const float *x, const float *gamma, const float *beta, int M, int d, float *out, void *stream);
 
+/* ---- fine-tune step (models/clip_cls_ft.py:214-269; backward the reference leaves to autograd) ------------------ */
+
+/* LayerNorm backward over rows: dx = acc + rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*gamma (eps 1e-5).
+ * x fp32 rows with stride x_stride (the LayerNorm input), dy fp32 [M,d]; acc (nullable) fp32 rows added to the result. */
+EC_API int ec_layernorm_bwd(const float *x, int64_t x_stride, const float *dy, const float *gamma, const float *acc,
+                            int64_t acc_stride, int M, int d, float *dx, int64_t dx_stride, void *stream);
+
+/* QuickGELU on a saved bf16 pre-activation (training forward keeps it) and its backward; n elements. */
+EC_API int ec_quickgelu(const void *a, void *h, int64_t n, void *stream);
+EC_API int ec_quickgelu_bwd(const void *a, const void *dh, void *da, int64_t n, void *stream);
+
+/* out[c, r] = in[r, c] for bf16 matrices (weight-gradient GEMMs reduce over the token dimension). */
+EC_API int ec_transpose_bf16(const void *in, void *out, int rows, int cols, int64_t ld_in, int64_t ld_out, void *stream);
+
+/* Attention backward for the packed QKV layout of ec_attention: dqkv bf16 [n_img*L, 3d] from qkv, the forward
+ * output o bf16 [n_img*L, d] and its gradient do bf16 [n_img*L, d]; softmax recomputed per tile (flash-style). */
+EC_API int ec_attention_bwd(const void *qkv, const void *o, const void *d_o, void *dqkv, int n_img, int L, int heads,
+                            void *stream);
+
+/* One Adam update (torch.optim.Adam semantics, method.py:150-191): fp32 parameters, bias correction by `step` >= 1. */
+EC_API int ec_adam(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int step, void *stream);
+
+/* out[m,n] (+)= alpha * sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn]: fp32 SIMT GEMM with arbitrary operand strides for the small
+ * backward products -- LoRA factor gradients dUp = dW . down^T, dDown = up^T . dW (models/lora.py:138-149 under autograd)
+ * and the logit head's d_feats / d_text. */
+EC_API int ec_gemm_f32_strided(const float *A, int64_t sam, int64_t sak, const float *B, int64_t sbk, int64_t sbn, int M, int N,
+                               int K, float alpha, float *out, int64_t ldo, int accumulate, void *stream);
+
+/* Backward of F.normalize(x, p=2, dim=-1) followed by the valid-mask multiply (clip_cls_ft.py:229-232; text features
+ * :163): dx = (dy - y<y,dy>) / max(|x|, 1e-12); rows with mask == 0 get dx = 0.  mask nullable. */
+EC_API int ec_l2norm_rows_bwd(const float *x, const float *dy, const uint8_t *mask, int M, int C, float *dx, void *stream);
+
+/* Loss of the fine-tune step and its gradient: logits = aggregate(full_logits) (clip_cls_ft.py:191-202, sum or mean),
+ * loss = F.cross_entropy(logits, labels) (:258-264).  full_logits fp32 [B,T,n_cls] with zero rows for invalid views,
+ * labels device int32 [B].  Outputs: per-sample loss [B], mean loss [1], d(mean loss)/d(full_logits) [B,T,n_cls]. */
+EC_API int ec_ce_loss_bwd(const float *full_logits, const uint8_t *valid, const int32_t *labels, int B, int T, int n_cls, int agg,
+                          float *loss_per_sample, float *loss_mean, float *d_full, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,136 @@
+"""GPU parity of the fine-tune step's backward kernels (through the C ABI) against torch autograd in fp32 on the CPU.
+
+The reference obtains every one of these gradients from autograd (models/clip_cls_ft.py:214-269 trains through
+model.visual), so autograd on the same bf16-rounded operands is the oracle.  Tolerances: fp32 kernels rel-L2 <= 1e-5;
+bf16-operand kernels (attention backward, QuickGELU) rel-L2 <= 1.5e-2 (P and dS are rounded to bf16 for the second
+matmul, outputs are bf16).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from eventclip_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("M,d,stride", [(37, 768, None), (5, 1024, 3 * 1024), (64, 256, None)])
+def test_layernorm_bwd(cuda_dev, M, d, stride):
+    g = torch.Generator().manual_seed(M)
+    rows = stride // d if stride else 1
+    xfull = (torch.randn(M * rows, d, generator=g) * 2 + 0.5)
+    x = xfull.view(M, rows * d)[:, :d].clone().requires_grad_(True)
+    gamma, beta = torch.randn(d, generator=g), torch.randn(d, generator=g)
+    dy, acc = torch.randn(M, d, generator=g), torch.randn(M, d, generator=g)
+    F.layer_norm(x, (d,), gamma, beta).backward(dy)
+    dx = ops.layernorm_bwd(xfull.to(cuda_dev), dy.to(cuda_dev), gamma.to(cuda_dev), M, d, x_stride=stride)
+    assert rel(dx, x.grad) < 1e-5
+    dx2 = ops.layernorm_bwd(xfull.to(cuda_dev), dy.to(cuda_dev), gamma.to(cuda_dev), M, d, acc=acc.to(cuda_dev), x_stride=stride)
+    assert rel(dx2, x.grad + acc) < 1e-5
+
+
+def test_quickgelu_fwd_bwd(cuda_dev):
+    g = torch.Generator().manual_seed(3)
+    a = (torch.randn(1000, 96, generator=g) * 3).to(torch.bfloat16)
+    dh = torch.randn(1000, 96, generator=g).to(torch.bfloat16)
+    af = a.float().requires_grad_(True)
+    h = af * torch.sigmoid(1.702 * af)
+    h.backward(dh.float())
+    out = ops.quickgelu(a.to(cuda_dev))
+    assert rel(out.float(), h.detach()) < 4e-3
+    da = ops.quickgelu_bwd(a.to(cuda_dev), dh.to(cuda_dev))
+    assert rel(da.float(), af.grad) < 4e-3
+
+
+@pytest.mark.parametrize("R,Cc", [(197 * 3, 768), (50, 64), (1001, 40)])
+def test_transpose_bf16(cuda_dev, R, Cc):
+    x = torch.randn(R, Cc).to(torch.bfloat16)
+    out = ops.transpose_bf16(x.to(cuda_dev)).cpu()
+    Rp = (R + 7) // 8 * 8
+    assert out.shape == (Cc, Rp)
+    assert torch.equal(out[:, :R], x.t())
+    assert (out[:, R:] == 0).all()
+
+
+@pytest.mark.parametrize("n_img,Ltok,heads", [(2, 197, 12), (3, 50, 4), (1, 257, 16), (2, 64, 2), (1, 77, 8)])
+def test_attention_bwd(cuda_dev, n_img, Ltok, heads):
+    g = torch.Generator().manual_seed(Ltok)
+    d = heads * 64
+    qkv = (torch.randn(n_img * Ltok, 3 * d, generator=g) * 1.5).to(torch.bfloat16)
+    d_o = torch.randn(n_img * Ltok, d, generator=g).to(torch.bfloat16)
+    x = qkv.float().requires_grad_(True)
+    q, k, v = [t.reshape(n_img, Ltok, heads, 64).transpose(1, 2) for t in x.split(d, dim=1)]
+    p = torch.softmax(q @ k.transpose(-1, -2) * 0.125, dim=-1)
+    o = (p @ v).transpose(1, 2).reshape(n_img * Ltok, d)
+    o.backward(d_o.float())
+    dev_qkv = qkv.to(cuda_dev)
+    o_dev = torch.empty((n_img * Ltok, d), dtype=torch.bfloat16, device=cuda_dev)
+    ops.attention(dev_qkv, o_dev, n_img, Ltok, heads)
+    dqkv = ops.attention_bwd(dev_qkv, o_dev, d_o.to(cuda_dev), n_img, Ltok, heads)
+    torch.cuda.synchronize()
+    for j, name in enumerate("qkv"):
+        r = rel(dqkv[:, j * d:(j + 1) * d].float(), x.grad[:, j * d:(j + 1) * d])
+        assert r < 1.5e-2, (name, r)
+
+
+def test_adam_matches_torch(cuda_dev):
+    g = torch.Generator().manual_seed(5)
+    p0 = torch.randn(10007, generator=g)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=2e-3)
+    p = p0.to(cuda_dev)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 6):
+        grad = torch.randn(10007, generator=g)
+        ref.grad = grad.clone()
+        opt.step()
+        ops.adam(p, grad.to(cuda_dev), m, v, lr=2e-3, step=step)
+    assert rel(p, ref.detach()) < 1e-6
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
+def test_mm_f32(cuda_dev, ta, tb):
+    g = torch.Generator().manual_seed(11)
+    M, N, K = 45, 70, 133
+    A = torch.randn((K, M) if ta else (M, K), generator=g)
+    B = torch.randn((N, K) if tb else (K, N), generator=g)
+    ref = (A.t() if ta else A) @ (B.t() if tb else B)
+    out = ops.mm_f32(A.to(cuda_dev), B.to(cuda_dev), ta, tb)
+    assert rel(out, ref) < 1e-5
+    out2 = ops.mm_f32(A.to(cuda_dev), B.to(cuda_dev), ta, tb, out=out.clone(), accumulate=True)
+    assert rel(out2, 2 * ref) < 1e-5
+
+
+def test_l2norm_rows_bwd(cuda_dev):
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(20, 512, generator=g).requires_grad_(True)
+    mask = torch.rand(20, generator=g) > 0.3
+    dy = torch.randn(20, 512, generator=g)
+    (F.normalize(x, p=2, dim=-1) * mask.float()[:, None]).backward(dy)
+    dx = ops.l2norm_rows_bwd(x.detach().to(cuda_dev), dy.to(cuda_dev), mask.to(torch.uint8).to(cuda_dev))
+    assert rel(dx, x.grad) < 1e-5
+
+
+@pytest.mark.parametrize("agg", ["sum", "mean"])
+def test_ce_loss_bwd(cuda_dev, agg):
+    g = torch.Generator().manual_seed(17)
+    B, T, K = 9, 3, 101
+    valid = torch.rand(B, T, generator=g) > 0.3
+    valid[:, 0] = True
+    full = (torch.randn(B, T, K, generator=g) * 3 * valid[..., None].float()).requires_grad_(True)
+    labels = torch.randint(0, K, (B,), generator=g)
+    logits = full.sum(1)
+    if agg == "mean":
+        logits = logits / valid.float().sum(1, keepdim=True)
+    loss = F.cross_entropy(logits, labels)
+    loss.backward()
+    lb, lm, dfull = ops.ce_loss_bwd(full.detach().to(cuda_dev), valid.to(torch.uint8).to(cuda_dev),
+                                    labels.to(torch.int32).to(cuda_dev), agg)
+    assert abs(lm.item() - loss.item()) < 1e-5 * max(1.0, abs(loss.item()))
+    assert rel(lb, F.cross_entropy(logits, labels, reduction="none").detach()) < 1e-5
+    assert rel(dfull, full.grad) < 1e-5
