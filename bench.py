@@ -207,8 +207,7 @@ def b200_arm(args):
     import torch.distributed as dist
     from eventclip_b200 import clip, ops, _lib
     from eventclip_b200.models import ZSCLIPClassifier
-    from eventclip_b200.synth import SENSORS, synth_batch
-    from oracle import clip_oracle   # text features generator only (synthetic stand-in for encode_text)
+    from eventclip_b200.synth import SENSORS, synth_batch, synth_text_feats
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -223,7 +222,7 @@ def b200_arm(args):
     B, K, Wm = BATCH, args.steps, max(args.warmup, 3)
 
     model = clip.init_weights_(clip.CLIP(ARCH), seed=0).to(dev).eval()
-    text = clip_oracle.synth_text_feats(cfg["n_cls"], 512, 1)
+    text = synth_text_feats(cfg["n_cls"], 512, 1)
     zs = ZSCLIPClassifier(clip_dict=dict(clip_model=model, prompt="a point cloud image of a {}", class_names=None,
                                          agg_func="mean", text_feats=text)).to(dev).eval()
     zs.attach_event_frontend(qargs(cfg), cfg["shape"], cfg["max_n"])

@@ -79,29 +79,38 @@ def _attn_weights(attn):
     return W, lora_in, attn.in_proj_bias, oW, ob, lora_out
 
 
+def merge_attn_weights(blk, d, dev, w_in=None, w_out=None):
+    """bf16 in_proj [3d,d] and out_proj [d,d] of a block with the LoRA factors merged (models/lora.py:138-149, 49-52);
+    writes into w_in / w_out when given."""
+    f32 = lambda t: t.detach().to(torch.float32).contiguous()
+    W, lora_in, ib, oW, ob, lora_out = _attn_weights(blk.attn)
+    W = f32(W)
+    if lora_in is None:
+        w_in = ops.f32_to_bf16(W, dst=w_in)
+    else:
+        if w_in is None:
+            w_in = torch.empty((3 * d, d), dtype=torch.bfloat16, device=dev)
+        for j, n in enumerate("qkv"):
+            up = getattr(lora_in, f"lora_up_{n}", None)
+            down = getattr(lora_in, f"lora_down_{n}", None)
+            ops.lora_merge(W[j * d:(j + 1) * d], f32(up) if up is not None else None,
+                           f32(down) if down is not None else None, out=w_in[j * d:(j + 1) * d])
+    if lora_out is None:
+        w_out = ops.f32_to_bf16(f32(oW), dst=w_out)
+    else:
+        w_out = ops.lora_merge(f32(oW), f32(lora_out.lora_up.weight), f32(lora_out.lora_down.weight), out=w_out)
+    return w_in, w_out, ib, ob, (lora_in is not None or lora_out is not None)
+
+
 def pack_blocks(resblocks, d, dev):
-    """bf16 GEMM weights (LoRA factors merged, models/lora.py:138-149) + fp32 biases / LayerNorm affine per block."""
+    """bf16 GEMM weights (LoRA factors merged) + fp32 biases / LayerNorm affine per block."""
     f32 = lambda t: t.detach().to(torch.float32).contiguous()
     blocks = []
     for blk in resblocks:
-        W, lora_in, ib, oW, ob, lora_out = _attn_weights(blk.attn)
-        W = f32(W)
-        if lora_in is None:
-            w_in = ops.f32_to_bf16(W)
-        else:
-            w_in = torch.empty((3 * d, d), dtype=torch.bfloat16, device=dev)
-            for j, n in enumerate("qkv"):
-                up = getattr(lora_in, f"lora_up_{n}", None)
-                down = getattr(lora_in, f"lora_down_{n}", None)
-                ops.lora_merge(W[j * d:(j + 1) * d], f32(up) if up is not None else None,
-                               f32(down) if down is not None else None, out=w_in[j * d:(j + 1) * d])
-        if lora_out is None:
-            w_out = ops.f32_to_bf16(f32(oW))
-        else:
-            w_out = ops.lora_merge(f32(oW), f32(lora_out.lora_up.weight), f32(lora_out.lora_down.weight))
+        w_in, w_out, ib, ob, has_lora = merge_attn_weights(blk, d, dev)
         blocks.append(dict(
             ln1=(f32(blk.ln_1.weight), f32(blk.ln_1.bias)), ln2=(f32(blk.ln_2.weight), f32(blk.ln_2.bias)),
-            w_in=w_in, b_in=f32(ib), w_out=w_out, b_out=f32(ob),
+            w_in=w_in, b_in=f32(ib), w_out=w_out, b_out=f32(ob), has_lora=has_lora,
             w_fc=ops.f32_to_bf16(f32(blk.mlp.c_fc.weight)), b_fc=f32(blk.mlp.c_fc.bias),
             w_proj=ops.f32_to_bf16(f32(blk.mlp.c_proj.weight)), b_proj=f32(blk.mlp.c_proj.bias)))
     return blocks
@@ -185,14 +194,37 @@ class VisionTransformer(nn.Module):
         self._packed, self._packed_key = pk, key
         return pk
 
+    def packed_train(self):
+        """packed() plus the transposed bf16 weights the data-gradient GEMMs read (dX = dY . W needs W^T K-major)."""
+        pk = self.packed()
+        if "proj_t" not in pk:
+            pk["proj_t"] = ops.f32_to_bf16(self.proj.detach().to(torch.float32).contiguous())     # [d, C]
+            for b in pk["blocks"]:
+                for n in ("w_in", "w_out", "w_fc", "w_proj"):
+                    b[n + "_t"] = ops.transpose_bf16(b[n])
+        return pk
+
+    def refresh_lora_packed(self):
+        """After an optimizer step that changed only LoRA factors: re-merge them into the existing packed buffers (and
+        their transposes) instead of repacking the whole tower."""
+        if self._packed is None:
+            return
+        pk = self._packed
+        for blk, b in zip(self.transformer.resblocks, pk["blocks"]):
+            if b["has_lora"]:
+                merge_attn_weights(blk, self.width, self.proj.device, w_in=b["w_in"], w_out=b["w_out"])
+                if "w_in_t" in b:
+                    ops.transpose_bf16(b["w_in"], out=b["w_in_t"])
+                    ops.transpose_bf16(b["w_out"], out=b["w_out_t"])
+        self._packed_key = self._version_key()
+
     # -- forward ----------------------------------------------------------------------------------------------------
     def forward_patches(self, patches, n_img):
         """patches: bf16 [n_img*G*G, k_patch] im2col rows (what ec_event2img's EC_OUT_BF16_PATCH writes).
         Returns fp32 [n_img, output_dim]."""
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                "gradients through the B200 image encoder (fine-tune step, SURVEY 8 row A12) are not built yet; "
-                "run under torch.no_grad()")
+            from . import train
+            return train.encode_patches_autograd(self, patches, n_img)
         pk = self.packed()
         d, G2, heads = self.width, self.grid ** 2, self.heads
         Ltok = G2 + 1

@@ -74,3 +74,50 @@ def gather_predictions(pred):
     bufs = [torch.empty_like(pad) for _ in range(ws)]
     dist.all_gather(bufs, pad)
     return torch.cat([b[:int(s.item())] for b, s in zip(bufs, sizes)])
+
+
+class FlatParams:
+    """Trainable parameters re-homed as views of ONE flat fp32 buffer with a same-layout flat gradient buffer, so that
+    the fine-tune step needs one collective (the reference's DDP buckets the same gradients, SURVEY.md section 8(e):
+    LoRA qkvo-16 + 101x512 text features = 1 231 360 floats = 4.9 MB) and one optimizer launch per parameter group.
+
+    groups: list of lists of nn.Parameter (e.g. [outside model.visual, inside model.visual] for the reference's two
+    learning rates, method.py:165-182).  Each group occupies one contiguous span."""
+
+    def __init__(self, groups):
+        params = [p for g in groups for p in g]
+        if not params:
+            raise ValueError("FlatParams needs at least one parameter")
+        dev = params[0].device
+        for p in params:
+            if p.dtype != torch.float32 or p.device != dev:
+                raise ValueError("FlatParams keeps fp32 master parameters on one device")
+        n = sum(p.numel() for p in params)
+        self.flat_p = torch.empty(n, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.spans, self._where = [], {}
+        off = 0
+        for g in groups:
+            lo = off
+            for p in g:
+                k = p.numel()
+                self.flat_p[off:off + k].copy_(p.detach().reshape(-1))
+                p.data = self.flat_p[off:off + k].view(p.shape)
+                self._where[id(p)] = (off, k, p.shape)
+                off += k
+            self.spans.append((lo, off))
+        self.numel = n
+
+    def grad_view(self, p):
+        off, k, shape = self._where[id(p)]
+        return self.flat_g[off:off + k].view(shape)
+
+    def average_gradients(self, group=None):
+        """The one collective of the fine-tune step: mean of the flat gradient over the ranks, in place."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            if self.flat_g.is_cuda:      # NCCL averages inside the collective
+                dist.all_reduce(self.flat_g, op=dist.ReduceOp.AVG, group=group)
+            else:                        # gloo (CPU tests) has no AVG
+                dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=group)
+                self.flat_g.div_(dist.get_world_size(group))
+        return self.flat_g

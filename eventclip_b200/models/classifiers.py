@@ -319,7 +319,33 @@ class FTCLIPClassifier(_AdaptedClassifier):
                 p.requires_grad = True
 
     def get_img_feats(self, imgs):
-        return self.model.encode_image(imgs)     # gradients would flow here in training (clip_cls_ft.py:180)
+        return self.model.encode_image(imgs)     # gradients flow here in training (clip_cls_ft.py:180; eventclip_b200/train.py)
+
+    # ---- training mode: the same forward with activations kept, attached to autograd through train.py's Functions ----
+    def _training_active(self):
+        return self.training and torch.is_grad_enabled()
+
+    def device_forward(self, events, plan, status=None):
+        if not self._training_active():
+            return super().device_forward(events, plan, status)
+        fe, visual = self.event_frontend, self.model.visual
+        patches, st, _ = ops.event2img(events, plan["frames"], fe.resolution, plan["n_valid"], fe.count_non_zero,
+                                       fe.background_mask, out="patch", patch=visual.patch_size, ldk=visual.k_patch,
+                                       status=status)
+        self._last_status = st
+        return self._head(visual.forward_patches(patches, plan["n_valid"]), plan)
+
+    def _head(self, feats, plan):
+        if not self._training_active():
+            return super()._head(feats.detach(), plan)
+        from .. import train
+        return train.train_forward(self, feats, plan)
+
+    def calc_train_loss(self, data_dict, out_dict):
+        if "_plan" in out_dict and torch.is_grad_enabled():
+            from .. import train
+            return train.train_loss(self, data_dict, out_dict)
+        return super().calc_train_loss(data_dict, out_dict)
 
     def train(self, mode=True):
         nn.Module.train(self, mode)

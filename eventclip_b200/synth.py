@@ -49,3 +49,12 @@ def synth_batch(dataset, B, seed0, kind="uniform", E=None):
     offsets = np.zeros(B + 1, np.int64)
     offsets[1:] = np.cumsum([len(e) for e in evs])
     return np.concatenate(evs, axis=0), offsets
+
+
+def synth_text_feats(n_cls, C, seed):
+    """L2-normalised seeded Gaussian [n_cls, C]: stand-in for the cached encode_text output (models/clip_cls.py:84-85)
+    when no tokenizer vocabulary / checkpoint is available (bench and scripts; same draw as the oracle's helper)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    t = torch.randn(n_cls, C, generator=g)
+    return t / t.norm(dim=-1, keepdim=True)

@@ -1,0 +1,327 @@
+"""Fine-tune step of FTCLIPClassifier on the B200 path (BASELINE config 5).
+
+The reference trains through `model.visual` with autograd (models/clip_cls_ft.py:214-269, LoRA factors of
+models/lora.py:101-159 / 14-57 plus the prompt-tuned text features), DDP averaging the gradients and
+torch.optim.Adam with two learning rates (method.py:150-191).  Here the forward keeps the activations it needs, the
+backward is an explicit chain of the library's kernels (tcgen05 GEMMs for data and weight gradients, mma.sync
+attention backward, LayerNorm / QuickGELU / normalize / cross-entropy backward kernels), gradients live in ONE flat fp32
+buffer that is all-reduced with a single NCCL call, and Adam is one kernel launch per parameter group.
+
+Two ways in:
+  * torch.autograd compatible: `FTCLIPClassifier.forward` in training mode builds a graph of three autograd
+    Functions (encoder, logit head, loss) whose backward methods run the kernels below, so the reference's
+    `loss.backward(); optimizer.step()` loop works unchanged.
+  * `FineTuner`: the fused step `events -> frames -> forward -> loss -> backward -> all-reduce -> Adam` without autograd.
+
+Trainable sets supported: LoRA factors on q/k/v/o (`lora='qv-r' | 'qkv-r' | 'qkvo-r' | int`) and the text features of
+the 'text-identity' adapter -- the configuration shipped for fine-tuning (configs/ftclip/*lora16.py).  Any other
+trainable parameter of model.visual (the only_* switches, full fine-tuning) raises NotImplementedError.
+"""
+import torch
+
+from . import ops
+from . import _lib as L
+
+
+# ------------------------------------------------------------------------------------------------ trainable set
+def lora_slots(vis):
+    """[(block index, 'q'|'k'|'v'|'o', up Parameter [rows,r], down Parameter [r,d])] in a fixed order, and a check that
+    nothing else in the image tower wants a gradient."""
+    slots, seen = [], set()
+    for i, blk in enumerate(vis.transformer.resblocks):
+        ipw = blk.attn.in_proj_weight
+        if isinstance(ipw, torch.nn.Module):
+            for n in "qkv":
+                up, down = getattr(ipw, f"lora_up_{n}", None), getattr(ipw, f"lora_down_{n}", None)
+                if up is not None and (up.requires_grad or down.requires_grad):
+                    slots.append((i, n, up, down))
+                    seen.update((id(up), id(down)))
+        op = blk.attn.out_proj
+        if hasattr(op, "lora_up") and (op.lora_up.weight.requires_grad or op.lora_down.weight.requires_grad):
+            slots.append((i, "o", op.lora_up.weight, op.lora_down.weight))
+            seen.update((id(op.lora_up.weight), id(op.lora_down.weight)))
+    other = [n for n, p in vis.named_parameters() if p.requires_grad and id(p) not in seen]
+    if other:
+        raise NotImplementedError(
+            "the B200 fine-tune step trains LoRA factors (and the text features); these parameters of model.visual also "
+            f"require gradients and have no backward here: {other[:6]}{' ...' if len(other) > 6 else ''}")
+    return slots
+
+
+# ------------------------------------------------------------------------------------------------ encoder forward/backward
+def encoder_forward(vis, patches, n_img):
+    """Training forward of VisionTransformer.forward_patches: same kernels, out-of-place residual updates, QuickGELU on the
+    stored bf16 pre-activation.  Returns (feats fp32 [n_img, C], ctx)."""
+    pk = vis.packed_train()
+    d, G2, heads = vis.width, vis.grid ** 2, vis.heads
+    Ltok = G2 + 1
+    M, dev = n_img * Ltok, patches.device
+    bf = lambda *shape: torch.empty(shape, dtype=torch.bfloat16, device=dev)
+    f32 = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+    x0 = f32(M, d)
+    ops.gemm_bf16(patches, pk["conv1"], None, "patch", out=x0, res=pk["pos"], row_map=G2, M=n_img * G2)
+    ops.cls_rows(x0, pk["cls"], pk["pos"], n_img, Ltok, d)
+    x = f32(M, d)
+    ops.layernorm(x0, *pk["ln_pre"], M, d, out_f32=x)
+    del x0
+    saved = []
+    for b in pk["blocks"]:
+        h1, qkv, att = bf(M, d), bf(M, 3 * d), bf(M, d)
+        ops.layernorm(x, *b["ln1"], M, d, out_bf16=h1)
+        ops.gemm_bf16(h1, b["w_in"], b["b_in"], "bf16", out=qkv)
+        ops.attention(qkv, att, n_img, Ltok, heads)
+        x2 = f32(M, d)
+        ops.gemm_bf16(att, b["w_out"], b["b_out"], "f32_resadd", out=x2, res=x)
+        h2, a = bf(M, d), bf(M, 4 * d)
+        ops.layernorm(x2, *b["ln2"], M, d, out_bf16=h2)
+        ops.gemm_bf16(h2, b["w_fc"], b["b_fc"], "bf16", out=a)
+        g = ops.quickgelu(a)
+        x3 = f32(M, d)
+        ops.gemm_bf16(g, b["w_proj"], b["b_proj"], "f32_resadd", out=x3, res=x2)
+        saved.append((x, h1, qkv, att, x2, h2, a, g))
+        x = x3
+    cls = bf(n_img, d)
+    ops.layernorm(x, *pk["ln_post"], n_img, d, row_stride=Ltok * d, out_bf16=cls)
+    feats = ops.gemm_bf16(cls, pk["proj"], None, "f32")
+    return feats, dict(pk=pk, saved=saved, x_last=x, n_img=n_img, Ltok=Ltok, d=d, heads=heads)
+
+
+def encoder_backward(vis, ctx, d_feats, slots, dest=None):
+    """d_feats fp32 [n_img, C] -> {(block, name): (d_up, d_down)} for the LoRA slots.  Frees ctx['saved'] as it goes.
+    dest(param) may return the tensor a gradient is to be written into (FineTuner's flat buffer views)."""
+    pk, saved = ctx["pk"], ctx["saved"]
+    n_img, Ltok, d, heads = ctx["n_img"], ctx["Ltok"], ctx["d"], ctx["heads"]
+    M, dev = n_img * Ltok, d_feats.device
+    want = {}
+    for i, n, up, down in slots:
+        want.setdefault(i, {})[n] = (up, down)
+    first = min(want) if want else len(saved)
+    grads = {}
+    f32w = lambda t: t.detach().to(torch.float32).contiguous()
+    to = (lambda p: None) if dest is None else dest
+
+    def factor_grads(dW, up, down):       # dUp = dW . down^T,  dDown = up^T . dW   (W_eff = W + up . down)
+        return (ops.mm_f32(dW, f32w(down), trans_b=True, out=to(up)), ops.mm_f32(f32w(up), dW, trans_a=True, out=to(down)))
+
+    # feats = ln_post(x[cls rows]) @ proj
+    d_cls = ops.gemm_bf16(ops.f32_to_bf16(d_feats.contiguous()), pk["proj_t"], None, "f32")       # [n_img, d]
+    dx = torch.zeros((M, d), dtype=torch.float32, device=dev)
+    ops.layernorm_bwd(ctx["x_last"], d_cls, pk["ln_post"][0], n_img, d, x_stride=Ltok * d, dx=dx, dx_stride=Ltok * d)
+    for i in range(len(saved) - 1, first - 1, -1):
+        b = pk["blocks"][i]
+        x, h1, qkv, att, x2, h2, a, g = saved[i]
+        saved[i] = None
+        # MLP:  x3 = x2 + c_proj(QuickGELU(c_fc(ln_2(x2))))
+        dxb = ops.f32_to_bf16(dx)
+        dg = ops.gemm_bf16(dxb, b["w_proj_t"], None, "bf16")                 # [M, 4d]
+        da = ops.quickgelu_bwd(a, dg, out=dg)
+        dh2 = ops.gemm_bf16(da, b["w_fc_t"], None, "f32")                    # [M, d]
+        dx2 = ops.layernorm_bwd(x2, dh2, b["ln2"][0], M, d, acc=dx)
+        del dg, da, dh2, a, g, h2
+        # attention:  x2 = x + out_proj(attn(in_proj(ln_1(x))))
+        dx2b = ops.f32_to_bf16(dx2, dst=dxb)
+        d_att = ops.gemm_bf16(dx2b, b["w_out_t"], None, "bf16")              # [M, d]
+        w = want.get(i, {})
+        if "o" in w:
+            dW = ops.gemm_bf16(ops.transpose_bf16(dx2b), ops.transpose_bf16(att), None, "f32")      # [d_out, d_in]
+            grads[(i, "o")] = factor_grads(dW, *w["o"])
+        dqkv = ops.attention_bwd(qkv, att, d_att, n_img, Ltok, heads)
+        if any(n in w for n in "qkv"):
+            dW = ops.gemm_bf16(ops.transpose_bf16(dqkv), ops.transpose_bf16(h1), None, "f32")       # [3d, d]
+            for j, n in enumerate("qkv"):
+                if n in w:
+                    grads[(i, n)] = factor_grads(dW[j * d:(j + 1) * d], *w[n])
+        if i > first:                                                        # nothing trainable below the first LoRA block
+            dh1 = ops.gemm_bf16(dqkv, b["w_in_t"], None, "f32")
+            dx = ops.layernorm_bwd(x, dh1, b["ln1"][0], M, d, acc=dx2)
+    ctx["saved"] = None
+    return grads
+
+
+# ------------------------------------------------------------------------------------------------ logit head
+def head_forward(feats, plan, text_raw, scale, agg):
+    """clip_cls_ft.py:224-248 with the kernels of the inference head.  feats fp32 [n_valid, C]; text_raw fp32 [K, C]
+    (re-normalised every forward, :163).  Returns (out_dict, ctx)."""
+    B, T = plan["B"], plan["T"]
+    slots = feats if plan["row_of_slot"] is None else ops.gather_rows(feats, plan["row_of_slot"], B * T)
+    slots = slots.contiguous()
+    that = ops.l2norm_rows(text_raw)
+    full, logits, probs, top = ops.head(slots, plan["valid_u8"], that, B, T, scale, True, agg)
+    out = {"full_logits": full, "valid_masks": plan["valid_dev"], "logits": logits, "probs": probs,
+           "top5_logits": top[:, 0], "top5_probs": top[:, 1]}
+    return out, dict(slots=slots, that=that, text_raw=text_raw, plan=plan, scale=scale)
+
+
+def head_backward(ctx, d_full):
+    """d_full fp32 [B,T,K] -> (d_feats [n_valid, C], d_text_raw [K, C])."""
+    plan, slots, that, scale = ctx["plan"], ctx["slots"], ctx["that"], ctx["scale"]
+    B, T = plan["B"], plan["T"]
+    S, K = B * T, that.shape[0]
+    dz = d_full.reshape(S, K)
+    fhat = ops.l2norm_rows(slots)                                   # zero rows (invalid views) stay zero
+    d_fhat = ops.mm_f32(dz, that, alpha=scale)                      # [S, C]
+    d_that = ops.mm_f32(dz, fhat, trans_a=True, alpha=scale)        # [K, C]; invalid rows of fhat are zero
+    d_slots = ops.l2norm_rows_bwd(slots, d_fhat, plan["valid_u8"])
+    d_text = ops.l2norm_rows_bwd(ctx["text_raw"], d_that)
+    if plan["row_of_slot"] is None:
+        return d_slots, d_text
+    return ops.gather_rows(d_slots, plan["slot_of_row"], plan["n_valid"]), d_text
+
+
+def add_slot_of_row(plan, dev):
+    """Inverse of row_of_slot (valid row -> slot), needed to route feature gradients back."""
+    if plan["row_of_slot"] is not None and "slot_of_row" not in plan:
+        ros = plan["row_of_slot"]
+        plan["slot_of_row"] = (ros >= 0).nonzero().squeeze(1).to(torch.int32).to(dev)
+    return plan
+
+
+# ------------------------------------------------------------------------------------------------ autograd plumbing
+class _EncoderFn(torch.autograd.Function):
+    """autograd node whose backward is encoder_backward; inputs after `n_img` are the LoRA factors (up, down, up, ...)."""
+
+    @staticmethod
+    def forward(fctx, vis, patches, n_img, *factors):
+        feats, ctx = encoder_forward(vis, patches, n_img)
+        fctx.vis, fctx.ctx = vis, ctx
+        return feats
+
+    @staticmethod
+    def backward(fctx, d_feats):
+        slots = lora_slots(fctx.vis)
+        grads = encoder_backward(fctx.vis, fctx.ctx, d_feats.contiguous(), slots)
+        flat = []
+        for i, n, up, down in slots:
+            du, dd = grads[(i, n)]
+            flat += [du.to(up.dtype) if up.requires_grad else None, dd.to(down.dtype) if down.requires_grad else None]
+        return (None, None, None, *flat)
+
+
+def encode_patches_autograd(vis, patches, n_img):
+    slots = lora_slots(vis)
+    factors = [p for _, _, up, down in slots for p in (up, down)]
+    return _EncoderFn.apply(vis, patches, n_img, *factors)
+
+
+class _HeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(fctx, feats, text_raw, plan, scale, agg):
+        out, ctx = head_forward(feats.detach().float().contiguous(), plan, text_raw.detach().float().contiguous(), scale, agg)
+        fctx.ctx = ctx
+        fctx.mark_non_differentiable(out["logits"], out["probs"], out["top5_logits"], out["top5_probs"])
+        return out["full_logits"], out["logits"], out["probs"], out["top5_logits"], out["top5_probs"]
+
+    @staticmethod
+    def backward(fctx, d_full, *unused):
+        d_feats, d_text = head_backward(fctx.ctx, d_full.contiguous())
+        return d_feats, d_text, None, None, None
+
+
+class _CELossFn(torch.autograd.Function):
+    """F.cross_entropy(aggregate(full_logits), labels) with the gradient produced by the same kernel."""
+
+    @staticmethod
+    def forward(fctx, full_logits, valid_u8, labels_i32, agg):
+        _, loss, d_full = ops.ce_loss_bwd(full_logits.detach().contiguous(), valid_u8, labels_i32, agg)
+        fctx.d_full = d_full
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(fctx, g):
+        return _scale(fctx.d_full, g), None, None, None
+
+
+def _scale(t, g):
+    """t * g for a scalar upstream gradient (exactly 1.0 for a plain loss.backward(), where t is returned as is)."""
+    gv = float(g)
+    if gv == 1.0:
+        return t
+    return ops.blend(t.reshape(-1), torch.zeros_like(t).reshape(-1), gv).reshape(t.shape)
+
+
+def train_forward(model, feats, plan):
+    """Head of FTCLIPClassifier.forward in training mode: returns the reference's out_dict with `full_logits` attached
+    to the autograd graph (clip_cls_ft.py:224-256)."""
+    add_slot_of_row(plan, feats.device)
+    text_raw = model.text_feats if model.prompt_tuning else model.get_text_feats()
+    full, logits, probs, t5l, t5p = _HeadFn.apply(feats, text_raw, plan, model.logit_scale, model.agg_func)
+    return {"full_logits": full, "valid_masks": plan["valid_dev"], "logits": logits, "probs": probs,
+            "top5_logits": t5l, "top5_probs": t5p, "_plan": plan}
+
+
+def train_loss(model, data_dict, out_dict):
+    """calc_train_loss in training mode (clip_cls_ft.py:258-269, use_logits_loss)."""
+    if not model.use_logits_loss:
+        raise NotImplementedError("the B200 fine-tune step implements the logits loss (use_logits_loss=True), the one the "
+                                  "reference's fine-tune configs use")
+    plan = out_dict["_plan"]
+    labels = data_dict["label"].to(device=out_dict["full_logits"].device, dtype=torch.int32).contiguous()
+    return {"ce_loss": _CELossFn.apply(out_dict["full_logits"], plan["valid_u8"], labels, model.agg_func)}
+
+
+# ------------------------------------------------------------------------------------------------ fused trainer
+class FineTuner:
+    """The whole fine-tune step without autograd: forward, loss, backward into one flat gradient buffer, ONE all-reduce
+    (NCCL when torch.distributed is initialised; the reference's DDP averages the same gradients), Adam with the
+    reference's two learning rates (method.py:155-182: `lr` for everything outside model.visual, `clip_lr` inside).
+
+        ft = FineTuner(model, lr=2e-5, clip_lr=2e-5)
+        loss = ft.step(events, offsets, labels)            # device events, host offsets, device/host labels
+    """
+
+    def __init__(self, model, lr, clip_lr=None, betas=(0.9, 0.999), eps=1e-8, process_group=None):
+        if not getattr(model, "prompt_tuning", False):
+            raise NotImplementedError("FineTuner expects the 'text-identity' adapter (prompt-tuned text features)")
+        self.model, self.vis = model, model.model.visual
+        self.slots = lora_slots(self.vis)
+        self.lr, self.clip_lr = lr, (lr if clip_lr is None else clip_lr)
+        self.betas, self.eps, self.pg = betas, eps, process_group
+        # group 0: outside model.visual (text features), group 1: LoRA factors -- each one contiguous span of the flat buffers
+        self.group0 = [model.text_feats]
+        self.group1 = [p for _, _, up, down in self.slots for p in (up, down)]
+        from .dist import FlatParams
+        self.flat = FlatParams([self.group0, self.group1])
+        self.flat_p, self.flat_g = self.flat.flat_p, self.flat.flat_g
+        self.m, self.v = torch.zeros_like(self.flat_g), torch.zeros_like(self.flat_g)
+        self.vis.invalidate_packed()
+        self.t = 0
+        self.last = {}
+
+    def _grad_view(self, p):
+        return self.flat.grad_view(p)
+
+    def forward_backward(self, events, offsets, labels, sel=None):
+        model = self.model
+        with torch.no_grad():
+            plan = model.plan_to_device(model.plan_events(offsets, sel), events.device)
+            add_slot_of_row(plan, events.device)
+            fe = model.event_frontend
+            patches, st, _ = ops.event2img(events, plan["frames"], fe.resolution, plan["n_valid"], fe.count_non_zero,
+                                           fe.background_mask, out="patch", patch=self.vis.patch_size, ldk=self.vis.k_patch)
+            feats, ctx = encoder_forward(self.vis, patches, plan["n_valid"])
+            out, hctx = head_forward(feats, plan, model.text_feats.detach(), model.logit_scale, model.agg_func)
+            labels = labels.to(device=events.device, dtype=torch.int32).contiguous()
+            _, loss, d_full = ops.ce_loss_bwd(out["full_logits"], plan["valid_u8"], labels, model.agg_func)
+            d_feats, d_text = head_backward(hctx, d_full)
+            encoder_backward(self.vis, ctx, d_feats, self.slots, dest=self.flat.grad_view)
+            self._grad_view(model.text_feats).copy_(d_text)
+        self.last = {"out": out, "status": st}
+        return loss
+
+    def allreduce(self):
+        self.flat.average_gradients(self.pg)
+
+    def optimizer_step(self, lr=None, clip_lr=None):
+        self.t += 1
+        lr = self.lr if lr is None else lr
+        clip_lr = self.clip_lr if clip_lr is None else clip_lr
+        for (lo, hi), rate in zip(self.flat.spans, (lr, clip_lr)):
+            if hi > lo:
+                ops.adam(self.flat_p[lo:hi], self.flat_g[lo:hi], self.m[lo:hi], self.v[lo:hi], rate, self.t, self.betas, self.eps)
+        self.vis.refresh_lora_packed()        # re-merge W + up.down into the packed bf16 weights (and their transposes)
+
+    def step(self, events, offsets, labels, sel=None, lr=None, clip_lr=None):
+        loss = self.forward_backward(events, offsets, labels, sel)
+        self.allreduce()
+        self.optimizer_step(lr, clip_lr)
+        return loss

@@ -68,7 +68,7 @@ def fs_head(img_feats, valid, text_param, scale, agg, adapter=None, normalize_te
     """Few-shot / fine-tune head.  adapter: None (identity / FT) or a callable (feats,valid)->feats."""
     B, T = valid.shape
     C = img_feats.shape[-1]
-    full = torch.zeros(B, T, C, dtype=img_feats.dtype)
+    full = torch.zeros(B, T, C, dtype=img_feats.dtype, device=img_feats.device)
     full[valid] = img_feats
     if adapter is not None:
         full = adapter(full, valid)
@@ -88,3 +88,25 @@ def lora_merged_in_proj(W, d, lora):
             w = w + lora[f"lora_up_{n}"] @ lora[f"lora_down_{n}"]
         parts.append(w)
     return torch.cat(parts, 0)
+
+
+def ft_train_loss(visual, lora, imgs, valid, text_param, labels, scale, agg):
+    """Loss of one fine-tune step, differentiable w.r.t. the LoRA factors and text_param (autograd is the backward the
+    reference uses): models/clip_cls_ft.py:214-269 with models/lora.py's merged weights.
+      visual  oracle VisionTransformer (fp32);  lora {(block, 'q'|'k'|'v'|'o'): (up [rows,r], down [r,d])}
+      imgs    [n_valid, 3, 224, 224] views of the valid slots;  valid bool [B,T]
+    Pinned against the unmodified reference by tests/golden/ft_train_golden.npz (tests/test_oracle_models.py)."""
+    d = visual.transformer.width
+    over = {}
+    for i, blk in enumerate(visual.transformer.resblocks):
+        qkv = {n: lora[(i, n)] for n in "qkv" if (i, n) in lora}
+        if qkv:
+            W = blk.attn.in_proj_weight.detach()
+            over[f"transformer.resblocks.{i}.attn.in_proj_weight"] = torch.cat(
+                [W[j * d:(j + 1) * d] + (qkv[n][0] @ qkv[n][1] if n in qkv else 0) for j, n in enumerate("qkv")], 0)
+        if (i, "o") in lora:
+            up, down = lora[(i, "o")]
+            over[f"transformer.resblocks.{i}.attn.out_proj.weight"] = blk.attn.out_proj.weight.detach() + up @ down
+    feats = torch.func.functional_call(visual, over, (imgs,))
+    o = fs_head(feats, valid, text_param, scale, agg)
+    return F.cross_entropy(o["logits"], labels), o

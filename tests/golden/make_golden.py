@@ -257,6 +257,59 @@ def make_event_transforms():
     print("event_transforms", len(out))
 
 
+def make_ft_train():
+    """One fine-tune step of the UNMODIFIED reference FTCLIPClassifier (LoRA qkvo-4 + prompt-tuned text features) on the
+    oracle CLIP tower: train-mode forward, calc_train_loss, autograd backward, one torch.optim.Adam step with the two
+    learning rates of method.py:150-191.  Starts from the state stored in heads_golden.npz."""
+    rm = ref_import.load_models()
+    G = np.load(os.path.join(HERE, "heads_golden.npz"))
+    arch, n_cls = "ViT-tiny/32", 11
+    g = torch.Generator().manual_seed(77)
+    valid = torch.from_numpy(G["valid"])
+    imgs = torch.randn(6, 4, 3, 224, 224, generator=g) * valid[:, :, None, None, None].float()
+    names = [f"class_{i}" for i in range(n_cls)]
+    labels = torch.tensor([3, 0, 10, 7, 7, 1])
+    out = {"labels": labels.numpy()}
+    for agg in ("mean", "sum"):
+        clipm = clip_oracle.build_clip(arch, seed=3)
+        cd = dict(clip_model=clipm, prompt="a {}", class_names=names, agg_func=agg, lora="qkvo-4", only_conv1=False,
+                  only_bias=False, only_ln=False)
+        origf = rm.FTCLIPClassifier._build_prompts
+
+        def seededf(self, adapter_type, _t=torch.from_numpy(G["text"])):
+            self.text_feats = torch.nn.Parameter(_t.clone().float(), requires_grad=True)
+            return adapter_type[5:]
+
+        rm.FTCLIPClassifier._build_prompts = seededf
+        try:
+            m = rm.FTCLIPClassifier(adapter_dict=dict(adapter_type="text-identity", residual=True), clip_dict=cd,
+                                    loss_dict=dict(use_logits_loss=True, use_probs_loss=False))
+        finally:
+            rm.FTCLIPClassifier._build_prompts = origf
+        sd = {k[len("ft_lora_sd_"):]: torch.from_numpy(G[k]) for k in G.files if k.startswith("ft_lora_sd_")}
+        m.load_state_dict(sd, strict=False)      # the reference's override returns nothing
+        for k, v in sd.items():
+            assert torch.equal(m.state_dict()[k], v), k
+        m.train()
+        data = dict(img=imgs, valid_mask=valid, label=labels)
+        o = m(data)
+        loss = m.calc_train_loss(data, o)["ce_loss"]
+        loss.backward()
+        out[f"{agg}_loss"] = np.float32(loss.item())
+        out[f"{agg}_logits"] = o["logits"].detach().numpy()
+        named = [(n, p) for n, p in m.named_parameters() if p.requires_grad]
+        for n, p in named:
+            out[f"{agg}_grad_{n}"] = p.grad.numpy().copy()
+        # method.py:165-182: parameters outside model.visual get `lr`, those inside get `clip_lr`
+        opt = torch.optim.Adam([{"params": [p for n, p in named if "model.visual" not in n], "lr": 1e-3},
+                                {"params": [p for n, p in named if "model.visual" in n], "lr": 5e-4}])
+        opt.step()
+        for n, p in named:
+            out[f"{agg}_step1_{n}"] = p.detach().numpy().copy()
+        print("ft_train", agg, "loss", loss.item(), "trainable", len(named), sum(p.numel() for _, p in named))
+    np.savez_compressed(os.path.join(HERE, "ft_train_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     assert ref_import.available(), "/root/reference is required to (re)generate the golden fixtures"
     vis = ref_import.load_vis()
@@ -265,4 +318,5 @@ if __name__ == "__main__":
     make_event2img(vis)
     make_heads()
     make_event_transforms()
+    make_ft_train()
     print("sizes:", {f: os.path.getsize(os.path.join(HERE, f)) for f in sorted(os.listdir(HERE)) if not f.endswith(".py")})

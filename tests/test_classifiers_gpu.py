@@ -152,9 +152,8 @@ def test_fine_tuned_lora_classifier_vs_reference_golden(cuda_dev, G):
     assert rel(o["logits"], G["ft_lora_logits"]) < 2e-2 and rel(o["full_logits"], G["ft_lora_full_logits"]) < 2e-2
     assert rel(o["logits"], base) > 1e-3        # the LoRA factors did change the result
     _assert_top1(o["logits"], G["ft_lora_logits"])
-    with pytest.raises(NotImplementedError):    # gradients through the encoder are not built yet: loud, not silent
-        m.train()
-        m(data)
+    m.train()                                   # training mode attaches the graph (tests/test_train_gpu.py checks the gradients)
+    assert m(data)["full_logits"].requires_grad
 
 
 @pytest.mark.parametrize("ds,arch,B", [("n_cars", "ViT-B/16", 8), ("n_caltech101", "ViT-B/32", 4)])

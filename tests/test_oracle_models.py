@@ -76,3 +76,38 @@ def test_fine_tune_lora_head(G):
     assert "model.visual.transformer.resblocks.0.attn.in_proj_weight.lora_down_q" in keys
     assert "model.visual.transformer.resblocks.1.attn.out_proj.lora_up.weight" in keys
     assert "model.visual.transformer.resblocks.0.attn.out_proj.linear.weight" in keys
+
+
+def lora_from_sd(sd, n_blocks, requires_grad=True):
+    """{(block, 'q'|'k'|'v'|'o'): (up, down)} leaf tensors from a reference-named state dict, and the name of each."""
+    lora, names = {}, {}
+    for i in range(n_blocks):
+        pre = f"model.visual.transformer.resblocks.{i}.attn."
+        for n in "qkvo":
+            ku, kd = (pre + "out_proj.lora_up.weight", pre + "out_proj.lora_down.weight") if n == "o" else \
+                (pre + f"in_proj_weight.lora_up_{n}", pre + f"in_proj_weight.lora_down_{n}")
+            if ku in sd:
+                lora[(i, n)] = (sd[ku].clone().requires_grad_(requires_grad), sd[kd].clone().requires_grad_(requires_grad))
+                names[(i, n)] = (ku, kd)
+    return lora, names
+
+
+@pytest.mark.parametrize("agg", ["mean", "sum"])
+def test_fine_tune_step_gradients(G, golden_dir, agg):
+    """oracle ft_train_loss + autograd == the unmodified reference's train-mode forward / calc_train_loss / backward."""
+    T = np.load(os.path.join(golden_dir, "ft_train_golden.npz"))
+    valid = torch.from_numpy(G["valid"])
+    g = torch.Generator().manual_seed(77)
+    imgs = torch.randn(6, 4, 3, 224, 224, generator=g) * valid[:, :, None, None, None].float()
+    clip = clip_oracle.build_clip(ARCH, seed=3)
+    sd = {k[len("ft_lora_sd_"):]: torch.from_numpy(G[k]) for k in G.files if k.startswith("ft_lora_sd_")}
+    lora, names = lora_from_sd(sd, 2)
+    text = sd["text_feats"].clone().requires_grad_(True)
+    loss, o = heads_oracle.ft_train_loss(clip.visual, lora, imgs[valid], valid, text, torch.from_numpy(T["labels"]), 100.0, agg)
+    loss.backward()
+    assert abs(loss.item() - float(T[f"{agg}_loss"])) < 1e-4 * float(T[f"{agg}_loss"])
+    assert _close(o["logits"].detach(), T[f"{agg}_logits"], 1e-4)
+    assert _close(text.grad, T[f"{agg}_grad_text_feats"], 1e-4)
+    for key, (up, down) in lora.items():
+        assert _close(up.grad, T[f"{agg}_grad_{names[key][0]}"], 1e-4), key
+        assert _close(down.grad, T[f"{agg}_grad_{names[key][1]}"], 1e-4), key
