@@ -35,38 +35,152 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float *__restr
     }
 }
 
-__global__ void quickgelu_kernel(const __nv_bfloat16 *a, __nv_bfloat16 *h, int64_t n)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float x = __bfloat162float(a[i]);
-    h[i] = __float2bfloat16(x / (1.f + __expf(-1.702f * x)));
-}
-
+// 8 bf16 per thread (one 16-byte access); n8 = n / 8 full vectors, the tail is handled by the last thread scalar-wise
+__device__ __forceinline__ float qg(float x) { return x / (1.f + __expf(-1.702f * x)); }
 // d/da [a * sigmoid(1.702 a)] = s + 1.702 a s (1 - s)
-__global__ void quickgelu_bwd_kernel(const __nv_bfloat16 *a, const __nv_bfloat16 *dh, __nv_bfloat16 *da, int64_t n)
+__device__ __forceinline__ float qg_grad(float x)
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float x = __bfloat162float(a[i]);
-    const float s = 1.f / (1.f + __expf(-1.702f * x));
-    da[i] = __float2bfloat16(__bfloat162float(dh[i]) * (s + 1.702f * x * s * (1.f - s)));
+    const float sg = 1.f / (1.f + __expf(-1.702f * x));
+    return sg + 1.702f * x * sg * (1.f - sg);
 }
 
-// out[c, r] = in[r, c]; 32x32 tiles through shared memory
-__global__ void transpose_bf16_kernel(const __nv_bfloat16 *in, __nv_bfloat16 *out, int rows, int cols, int64_t ld_in,
-                                      int64_t ld_out)
+__global__ void __launch_bounds__(256) quickgelu_kernel(const __nv_bfloat16 *__restrict__ a, __nv_bfloat16 *__restrict__ h, int64_t n)
 {
-    __shared__ __nv_bfloat16 t[32][34];
-    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const int r = r0 + i, c = c0 + threadIdx.x;
-        t[i][threadIdx.x] = (r < rows && c < cols) ? in[(size_t)r * ld_in + c] : __float2bfloat16(0.f);
+    const int64_t n8 = n >> 3;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        uint4 v = reinterpret_cast<const uint4 *>(a)[i];
+        __nv_bfloat162 *p = reinterpret_cast<__nv_bfloat162 *>(&v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 x = __bfloat1622float2(p[e]);
+            p[e] = __floats2bfloat162_rn(qg(x.x), qg(x.y));
+        }
+        reinterpret_cast<uint4 *>(h)[i] = v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int64_t i = n8 << 3; i < n; ++i) h[i] = __float2bfloat16(qg(__bfloat162float(a[i])));
+}
+
+__global__ void __launch_bounds__(256) quickgelu_bwd_kernel(const __nv_bfloat16 *__restrict__ a, const __nv_bfloat16 *__restrict__ dh,
+                                                            __nv_bfloat16 *__restrict__ da, int64_t n)
+{
+    const int64_t n8 = n >> 3;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 va = reinterpret_cast<const uint4 *>(a)[i];
+        uint4 vd = reinterpret_cast<const uint4 *>(dh)[i];
+        const __nv_bfloat162 *pa = reinterpret_cast<const __nv_bfloat162 *>(&va);
+        __nv_bfloat162 *pd = reinterpret_cast<__nv_bfloat162 *>(&vd);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 x = __bfloat1622float2(pa[e]), g = __bfloat1622float2(pd[e]);
+            pd[e] = __floats2bfloat162_rn(g.x * qg_grad(x.x), g.y * qg_grad(x.y));
+        }
+        reinterpret_cast<uint4 *>(da)[i] = vd;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int64_t i = n8 << 3; i < n; ++i)
+            da[i] = __float2bfloat16(__bfloat162float(dh[i]) * qg_grad(__bfloat162float(a[i])));
+}
+
+// LoRA factor gradients from the gradient of the merged weight (W_eff = W + up . down, models/lora.py:138-149, 49-52):
+//   d_up[rows, r] = dW . down^T        d_down[r, d] = up^T . dW
+// dW holds n_mat matrices of `rows` rows stacked (q | k | v of in_proj, or the single out_proj); blockIdx.y picks one.
+struct LoraGradArgs {
+    const float *up[4], *down[4];
+    float *d_up[4], *d_down[4];
+};
+
+// one warp per row of dW; 16 ranks at a time
+__global__ void __launch_bounds__(256) lora_dup_kernel(const float *__restrict__ dW, int64_t ld, int rows, int d, int r, LoraGradArgs g)
+{
+    const int z = blockIdx.y, row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (!g.d_up[z] || row >= rows) return;
+    const float *w = dW + ((size_t)z * rows + row) * ld, *dn = g.down[z];
+    for (int j0 = 0; j0 < r; j0 += 16) {
+        float acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+        for (int c = lane; c < d; c += 32) {
+            const float x = w[c];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (j0 + j < r) acc[j] += x * dn[(size_t)(j0 + j) * d + c];
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float t = ec::warp_sum(acc[j]);
+            if (lane == 0 && j0 + j < r) g.d_up[z][(size_t)row * r + j0 + j] = t;
+        }
+    }
+}
+
+// 32 columns x 8 row groups per CTA; partial sums of the row groups are folded through shared memory in a fixed order
+__global__ void __launch_bounds__(256) lora_ddown_kernel(const float *__restrict__ dW, int64_t ld, int rows, int d, int r, LoraGradArgs g)
+{
+    __shared__ float part[8][16][33];
+    const int z = blockIdx.y, tx = threadIdx.x & 31, rg = threadIdx.x >> 5, c = blockIdx.x * 32 + tx;
+    if (!g.d_down[z]) return;
+    const float *w = dW + (size_t)z * rows * ld, *up = g.up[z];
+    for (int j0 = 0; j0 < r; j0 += 16) {
+        float acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+        if (c < d)
+            for (int i = rg; i < rows; i += 8) {
+                const float x = w[(size_t)i * ld + c];
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (j0 + j < r) acc[j] += x * up[(size_t)i * r + j0 + j];
+            }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) part[rg][j][tx] = acc[j];
+        __syncthreads();
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+            const int j = rg * 2 + jj;
+            float t = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) t += part[q][j][tx];
+            if (c < d && j0 + j < r) g.d_down[z][(size_t)(j0 + j) * d + c] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// out[c, r] = in[r, c]; 64x64 tiles through shared memory, 4-byte (bf16x2) global accesses on both sides when the
+// strides allow it (even ld_in / ld_out), 128 B per warp row
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16 *__restrict__ in, __nv_bfloat16 *__restrict__ out,
+                                                             int rows, int cols, int64_t ld_in, int64_t ld_out, int vec)
+{
+    __shared__ __nv_bfloat16 t[64][66];
+    const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const __nv_bfloat16 zero = __float2bfloat16(0.f);
+    for (int i = ty; i < 64; i += 8) {
+        const int r = r0 + i, c = c0 + 2 * tx;
+        __nv_bfloat16 a = zero, b = zero;
+        if (r < rows) {
+            if (vec && c + 1 < cols) {
+                const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162 *>(in + (size_t)r * ld_in + c);
+                a = v.x; b = v.y;
+            } else {
+                if (c < cols) a = in[(size_t)r * ld_in + c];
+                if (c + 1 < cols) b = in[(size_t)r * ld_in + c + 1];
+            }
+        }
+        t[i][2 * tx] = a; t[i][2 * tx + 1] = b;
     }
     __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const int c = c0 + i, r = r0 + threadIdx.x;
-        if (c < cols && r < rows) out[(size_t)c * ld_out + r] = t[threadIdx.x][i];
+    for (int i = ty; i < 64; i += 8) {
+        const int c = c0 + i, r = r0 + 2 * tx;
+        if (c >= cols) continue;
+        const __nv_bfloat16 a = t[2 * tx][i], b = t[2 * tx + 1][i];
+        if (vec && r + 1 < rows) {
+            __nv_bfloat162 v; v.x = a; v.y = b;
+            *reinterpret_cast<__nv_bfloat162 *>(out + (size_t)c * ld_out + r) = v;
+        } else {
+            if (r < rows) out[(size_t)c * ld_out + r] = a;
+            if (r + 1 < rows) out[(size_t)c * ld_out + r + 1] = b;
+        }
     }
 }
 
@@ -209,18 +323,19 @@ extern "C" int ec_layernorm_bwd(const float *x, int64_t x_stride, const float *d
 
 extern "C" int ec_quickgelu(const void *a, void *h, int64_t n, void *stream)
 {
-    EC_REQUIRE(a && h && n >= 0, "ec_quickgelu: bad arguments");
+    EC_REQUIRE(a && h && n >= 0 && (((uintptr_t)a | (uintptr_t)h) & 15) == 0, "ec_quickgelu: bad arguments (16-byte aligned pointers)");
     if (n == 0) return EC_OK;
-    quickgelu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)a, (__nv_bfloat16 *)h, n);
+    quickgelu_kernel<<<(unsigned)((n / 8 + 255) / 256 + 1 < 148 * 16 ? (n / 8 + 255) / 256 + 1 : 148 * 16), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)a, (__nv_bfloat16 *)h, n);
     EC_CUDA_CHECK(cudaGetLastError());
     return EC_OK;
 }
 
 extern "C" int ec_quickgelu_bwd(const void *a, const void *dh, void *da, int64_t n, void *stream)
 {
-    EC_REQUIRE(a && dh && da && n >= 0, "ec_quickgelu_bwd: bad arguments");
+    EC_REQUIRE(a && dh && da && n >= 0 && (((uintptr_t)a | (uintptr_t)dh | (uintptr_t)da) & 15) == 0,
+               "ec_quickgelu_bwd: bad arguments (16-byte aligned pointers)");
     if (n == 0) return EC_OK;
-    quickgelu_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)a,
+    quickgelu_bwd_kernel<<<(unsigned)((n / 8 + 255) / 256 + 1 < 148 * 16 ? (n / 8 + 255) / 256 + 1 : 148 * 16), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)a,
                                                                                         (const __nv_bfloat16 *)dh,
                                                                                         (__nv_bfloat16 *)da, n);
     EC_CUDA_CHECK(cudaGetLastError());
@@ -230,8 +345,9 @@ extern "C" int ec_quickgelu_bwd(const void *a, const void *dh, void *da, int64_t
 extern "C" int ec_transpose_bf16(const void *in, void *out, int rows, int cols, int64_t ld_in, int64_t ld_out, void *stream)
 {
     EC_REQUIRE(in && out && rows > 0 && cols > 0 && ld_in >= cols && ld_out >= rows, "ec_transpose_bf16: bad arguments");
-    transpose_bf16_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16 *)in, (__nv_bfloat16 *)out, rows, cols, ld_in, ld_out);
+    const int vec = (ld_in % 2 == 0) && (ld_out % 2 == 0) && (((uintptr_t)in | (uintptr_t)out) & 3) == 0;
+    transpose_bf16_kernel<<<dim3((cols + 63) / 64, (rows + 63) / 64), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16 *)in, (__nv_bfloat16 *)out, rows, cols, ld_in, ld_out, vec);
     EC_CUDA_CHECK(cudaGetLastError());
     return EC_OK;
 }
@@ -274,6 +390,24 @@ extern "C" int ec_ce_loss_bwd(const float *full_logits, const uint8_t *valid, co
     EC_REQUIRE(agg == EC_AGG_SUM || agg == EC_AGG_MEAN, "ec_ce_loss_bwd: training supports agg sum / mean (got %d)", agg);
     ce_bwd_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(full_logits, valid, labels, B, T, n_cls, agg, loss_per_sample, d_full);
     mean_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(loss_per_sample, B, loss_mean);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
+extern "C" int ec_lora_grad(const float *dW, int64_t ld, int n_mat, int rows, int d, int r, const float *const *up,
+                            const float *const *down, float *const *d_up, float *const *d_down, void *stream)
+{
+    EC_REQUIRE(dW && up && down && d_up && d_down && n_mat >= 1 && n_mat <= 4 && rows > 0 && d > 0 && r > 0 && ld >= d,
+               "ec_lora_grad: bad arguments");
+    LoraGradArgs g;
+    for (int z = 0; z < 4; ++z) {
+        const bool on = z < n_mat && up[z] && down[z];
+        g.up[z] = on ? up[z] : nullptr; g.down[z] = on ? down[z] : nullptr;
+        g.d_up[z] = on ? d_up[z] : nullptr; g.d_down[z] = on ? d_down[z] : nullptr;
+        if (on) EC_REQUIRE(d_up[z] && d_down[z], "ec_lora_grad: matrix %d has factors but no gradient buffers", z);
+    }
+    lora_dup_kernel<<<dim3((rows + 7) / 8, n_mat), 256, 0, (cudaStream_t)stream>>>(dW, ld, rows, d, r, g);
+    lora_ddown_kernel<<<dim3((d + 31) / 32, n_mat), 256, 0, (cudaStream_t)stream>>>(dW, ld, rows, d, r, g);
     EC_CUDA_CHECK(cudaGetLastError());
     return EC_OK;
 }

@@ -2,8 +2,11 @@
 
 The device part of the classifier forward (`device_forward`: ec_event2img -> patch GEMM -> ViT blocks -> head, ~100
 kernel launches) is captured once and replayed, so a step costs one graph launch instead of ~100 ctypes calls.
-A graph is specific to (number of frames, number of valid views, slot map); batches whose plan differs get their
-own graph (`GraphedClassifier` keeps a small cache keyed by the plan).
+A graph is specific to the COUNTS of a plan (frames, valid views, B, T); the frame table, the valid mask and the slot
+maps are static device tensors refreshed before every replay, so batches with different chunk offsets or padding share
+a graph (`GraphedClassifier` keeps a small cache keyed by the counts).  `GraphedFineTuner` does the same for the
+fine-tune step: one graph for forward + loss + backward, the gradient all-reduce outside it, one graph for Adam + the
+LoRA re-merge.
 """
 import torch
 
@@ -12,6 +15,37 @@ from . import _lib as L
 
 class _Entry:
     pass
+
+
+def _static_plan(model, plan, dev):
+    """Device copy of a host plan whose tensors are STATIC graph inputs: the slot map is always materialised so that two
+    batches with the same counts (frames, valid views, B, T) share a graph whatever their chunk offsets / padding."""
+    B, T, nv = plan["B"], plan["T"], plan["n_valid"]
+    d = model.plan_to_device(plan, dev)
+    if d["row_of_slot"] is None:
+        d["row_of_slot"] = torch.arange(B * T, dtype=torch.int32, device=dev)
+    d["slot_of_row"] = torch.zeros(nv, dtype=torch.int32, device=dev)
+    _refresh_plan(d, plan)
+    return d
+
+
+def _refresh_plan(static, plan):
+    """Copies a new host plan of the same counts into the static device tensors (async from pinned memory)."""
+    pin = lambda t: t if (t.is_pinned() or not torch.cuda.is_available()) else t.pin_memory()
+    B, T = plan["B"], plan["T"]
+    static["frames"].copy_(pin(plan["frames"]), non_blocking=True)
+    static["valid_u8"].copy_(pin(plan["valid_u8"]), non_blocking=True)
+    static["valid_dev"].copy_(pin(plan["valid"]), non_blocking=True)
+    ros = plan["row_of_slot"]
+    if ros is None:
+        ros = torch.arange(B * T, dtype=torch.int32)
+    static["row_of_slot"].copy_(pin(ros), non_blocking=True)
+    static["slot_of_row"].copy_(pin((ros >= 0).nonzero().squeeze(1).to(torch.int32)), non_blocking=True)
+    static["valid"] = plan["valid"]
+
+
+def _plan_key(plan):
+    return (plan["frames"].shape[0], plan["n_valid"], plan["B"], plan["T"])
 
 
 class GraphedClassifier:
@@ -25,14 +59,9 @@ class GraphedClassifier:
         self.cache = {}
         self.max_graphs = max_graphs
 
-    def _key(self, plan):
-        ros = plan["row_of_slot"]
-        return (plan["n_valid"], plan["B"], plan["T"], plan["frames"].numpy().tobytes(),
-                None if ros is None else ros.numpy().tobytes())
-
     def _build(self, plan):
         e = _Entry()
-        e.plan = self.model.plan_to_device(plan, self.dev)
+        e.plan = _static_plan(self.model, plan, self.dev)
         torch.cuda.synchronize(self.dev)
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream(self.dev))
@@ -57,13 +86,99 @@ class GraphedClassifier:
         n = ev.shape[0]
         if n > self.events.shape[0]:
             raise L.ECError(f"batch has {n} events but the graph buffer holds {self.events.shape[0]}")
-        key = self._key(plan)
+        key = _plan_key(plan)
         ent = self.cache.get(key)
         if ent is None:
             if len(self.cache) >= self.max_graphs:
                 self.cache.pop(next(iter(self.cache)))
             ent = self.cache[key] = self._build(plan)
+        else:
+            _refresh_plan(ent.plan, plan)
         self.events[:n].copy_(ev, non_blocking=True)
         ent.graph.replay()
         L.LAUNCHES += ent.n_launch
         return ent.out
+
+
+class GraphedFineTuner:
+    """train.FineTuner with the device work replayed from CUDA graphs (a step is ~470 kernel launches on ViT-B/16).
+
+        gt = GraphedFineTuner(train.FineTuner(model, lr=2e-5), max_events=...)
+        loss = gt.step(events, offsets, labels)      # loss: static device scalar, valid until the next step
+    """
+
+    def __init__(self, tuner, max_events, max_graphs=4):
+        self.tuner, self.model = tuner, tuner.model
+        self.dev = tuner.flat_p.device
+        self.events = torch.zeros((max_events, 4), dtype=torch.float32, device=self.dev)
+        self.cache, self.max_graphs = {}, max_graphs
+        # Adam's bias correction is computed on the host from the step count, so the two ec_adam launches stay eager; the
+        # LoRA re-merge that follows (6 launches per block, pointer-stable) is replayed from its own graph.
+        self.refresh_graph, self.refresh_launches = None, 0
+
+    def _refresh_weights(self):
+        vis = self.tuner.vis
+        if self.refresh_graph is None:
+            vis.refresh_lora_packed()                    # eager once (also the warm-up)
+            torch.cuda.synchronize(self.dev)
+            g = torch.cuda.CUDAGraph()
+            n0 = L.LAUNCHES
+            with torch.cuda.graph(g):
+                vis.refresh_lora_packed()
+            self.refresh_launches = L.LAUNCHES - n0
+            L.LAUNCHES = n0
+            self.refresh_graph = g
+            return
+        self.refresh_graph.replay()
+        L.LAUNCHES += self.refresh_launches
+
+    def _build(self, plan, labels):
+        e = _Entry()
+        t = self.tuner
+        e.plan = _static_plan(self.model, plan, self.dev)
+        e.labels = torch.zeros(plan["B"], dtype=torch.int32, device=self.dev)
+        e.labels.copy_(labels)
+        torch.cuda.synchronize(self.dev)
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            t.device_forward_backward(self.events, e.plan, e.labels)
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        e.graph = torch.cuda.CUDAGraph()
+        n0 = L.LAUNCHES
+        with torch.cuda.graph(e.graph):
+            e.loss = t.device_forward_backward(self.events, e.plan, e.labels)
+            e.out = t.last["out"]
+        e.n_launch = L.LAUNCHES - n0
+        L.LAUNCHES = n0
+        return e
+
+    def forward_backward(self, events, offsets, labels, sel=None):
+        plan = self.model.plan_events(offsets, sel)
+        n = events.shape[0]
+        if n > self.events.shape[0]:
+            raise L.ECError(f"batch has {n} events but the graph buffer holds {self.events.shape[0]}")
+        labels = labels.to(dtype=torch.int32)
+        key = _plan_key(plan)
+        ent = self.cache.get(key)
+        if ent is None:
+            if len(self.cache) >= self.max_graphs:
+                self.cache.pop(next(iter(self.cache)))
+            self.events[:n].copy_(events, non_blocking=True)
+            ent = self.cache[key] = self._build(plan, labels)
+        else:
+            _refresh_plan(ent.plan, plan)
+            ent.labels.copy_(labels, non_blocking=True)
+            self.events[:n].copy_(events, non_blocking=True)
+        ent.graph.replay()
+        L.LAUNCHES += ent.n_launch
+        self.tuner.last = {"out": ent.out}
+        return ent.loss
+
+    def step(self, events, offsets, labels, sel=None, lr=None, clip_lr=None):
+        loss = self.forward_backward(events, offsets, labels, sel)
+        self.tuner.allreduce()
+        self.tuner.optimizer_step(lr, clip_lr, refresh=False)
+        self._refresh_weights()
+        return loss

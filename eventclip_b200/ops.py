@@ -416,3 +416,32 @@ def ce_loss_bwd(full_logits, valid_u8, labels_i32, agg):
         L.check(L.load().ec_ce_loss_bwd(_ptr(full_logits), _ptr(valid_u8), _ptr(labels_i32), B, T, K, agg_id, _ptr(loss_b),
                                         _ptr(loss), _ptr(dfull), _stream()), "ec_ce_loss_bwd")
     return loss_b, loss, dfull
+
+
+def lora_grad(dW, rows, factors, dests=None):
+    """factors: list (<= 4) of (up [rows,r], down [r,d]) or None per stacked matrix of dW [n*rows, d]; dests: matching list
+    of (d_up, d_down) output tensors or None.  Returns the list of (d_up, d_down) (None where skipped)."""
+    _dev(dW, torch.float32, "dW")
+    n = len(factors)
+    d = dW.shape[1]
+    outs, arrs = [], [(C.c_void_p * n)() for _ in range(4)]
+    r = 0
+    for z, f in enumerate(factors):
+        if f is None:
+            outs.append(None)
+            continue
+        up, down = f
+        r = up.shape[1]
+        dst = dests[z] if dests is not None and dests[z] is not None else (None, None)
+        du = dst[0] if dst[0] is not None else torch.empty((rows, r), dtype=torch.float32, device=dW.device)
+        dd = dst[1] if dst[1] is not None else torch.empty((r, d), dtype=torch.float32, device=dW.device)
+        for t, nme in ((up, "up"), (down, "down"), (du, "d_up"), (dd, "d_down")):
+            _dev(t, torch.float32, nme)
+        arrs[0][z], arrs[1][z], arrs[2][z], arrs[3][z] = up.data_ptr(), down.data_ptr(), du.data_ptr(), dd.data_ptr()
+        outs.append((du, dd))
+    if r == 0:
+        return outs
+    with torch.cuda.device(dW.device):
+        L.check(L.load().ec_lora_grad(_ptr(dW), dW.stride(0), n, rows, d, r, arrs[0], arrs[1], arrs[2], arrs[3], _stream()),
+                "ec_lora_grad")
+    return outs

@@ -100,8 +100,12 @@ def encoder_backward(vis, ctx, d_feats, slots, dest=None):
     f32w = lambda t: t.detach().to(torch.float32).contiguous()
     to = (lambda p: None) if dest is None else dest
 
-    def factor_grads(dW, up, down):       # dUp = dW . down^T,  dDown = up^T . dW   (W_eff = W + up . down)
-        return (ops.mm_f32(dW, f32w(down), trans_b=True, out=to(up)), ops.mm_f32(f32w(up), dW, trans_a=True, out=to(down)))
+    def factor_grads(dW, rows, names, i, w):      # dUp = dW . down^T,  dDown = up^T . dW   (W_eff = W + up . down)
+        fac = [(f32w(w[n][0]), f32w(w[n][1])) if n in w else None for n in names]
+        dst = [(to(w[n][0]), to(w[n][1])) if n in w else None for n in names]
+        for n, g in zip(names, ops.lora_grad(dW, rows, fac, dst)):
+            if g is not None:
+                grads[(i, n)] = g
 
     # feats = ln_post(x[cls rows]) @ proj
     d_cls = ops.gemm_bf16(ops.f32_to_bf16(d_feats.contiguous()), pk["proj_t"], None, "f32")       # [n_img, d]
@@ -124,13 +128,11 @@ def encoder_backward(vis, ctx, d_feats, slots, dest=None):
         w = want.get(i, {})
         if "o" in w:
             dW = ops.gemm_bf16(ops.transpose_bf16(dx2b), ops.transpose_bf16(att), None, "f32")      # [d_out, d_in]
-            grads[(i, "o")] = factor_grads(dW, *w["o"])
+            factor_grads(dW, d, "o", i, w)
         dqkv = ops.attention_bwd(qkv, att, d_att, n_img, Ltok, heads)
         if any(n in w for n in "qkv"):
             dW = ops.gemm_bf16(ops.transpose_bf16(dqkv), ops.transpose_bf16(h1), None, "f32")       # [3d, d]
-            for j, n in enumerate("qkv"):
-                if n in w:
-                    grads[(i, n)] = factor_grads(dW[j * d:(j + 1) * d], *w[n])
+            factor_grads(dW, d, "qkv", i, w)
         if i > first:                                                        # nothing trainable below the first LoRA block
             dh1 = ops.gemm_bf16(dqkv, b["w_in_t"], None, "f32")
             dx = ops.layernorm_bwd(x, dh1, b["ln1"][0], M, d, acc=dx2)
@@ -292,15 +294,21 @@ class FineTuner:
 
     def forward_backward(self, events, offsets, labels, sel=None):
         model = self.model
+        plan = model.plan_to_device(model.plan_events(offsets, sel), events.device)
+        add_slot_of_row(plan, events.device)
+        labels = labels.to(device=events.device, dtype=torch.int32).contiguous()
+        return self.device_forward_backward(events, plan, labels)
+
+    def device_forward_backward(self, events, plan, labels):
+        """Device part of the step (kernel launches only, capturable in a CUDA graph): frames, forward, loss, backward
+        into the flat gradient buffer.  Returns the mean loss as a device scalar [1]."""
+        model = self.model
         with torch.no_grad():
-            plan = model.plan_to_device(model.plan_events(offsets, sel), events.device)
-            add_slot_of_row(plan, events.device)
             fe = model.event_frontend
             patches, st, _ = ops.event2img(events, plan["frames"], fe.resolution, plan["n_valid"], fe.count_non_zero,
                                            fe.background_mask, out="patch", patch=self.vis.patch_size, ldk=self.vis.k_patch)
             feats, ctx = encoder_forward(self.vis, patches, plan["n_valid"])
             out, hctx = head_forward(feats, plan, model.text_feats.detach(), model.logit_scale, model.agg_func)
-            labels = labels.to(device=events.device, dtype=torch.int32).contiguous()
             _, loss, d_full = ops.ce_loss_bwd(out["full_logits"], plan["valid_u8"], labels, model.agg_func)
             d_feats, d_text = head_backward(hctx, d_full)
             encoder_backward(self.vis, ctx, d_feats, self.slots, dest=self.flat.grad_view)
@@ -311,14 +319,15 @@ class FineTuner:
     def allreduce(self):
         self.flat.average_gradients(self.pg)
 
-    def optimizer_step(self, lr=None, clip_lr=None):
+    def optimizer_step(self, lr=None, clip_lr=None, refresh=True):
         self.t += 1
         lr = self.lr if lr is None else lr
         clip_lr = self.clip_lr if clip_lr is None else clip_lr
         for (lo, hi), rate in zip(self.flat.spans, (lr, clip_lr)):
             if hi > lo:
                 ops.adam(self.flat_p[lo:hi], self.flat_g[lo:hi], self.m[lo:hi], self.v[lo:hi], rate, self.t, self.betas, self.eps)
-        self.vis.refresh_lora_packed()        # re-merge W + up.down into the packed bf16 weights (and their transposes)
+        if refresh:
+            self.vis.refresh_lora_packed()    # re-merge W + up.down into the packed bf16 weights (and their transposes)
 
     def step(self, events, offsets, labels, sel=None, lr=None, clip_lr=None):
         loss = self.forward_backward(events, offsets, labels, sel)

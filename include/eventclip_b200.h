@@ -225,6 +225,13 @@ EC_API int ec_adam(float *param, const float *grad, float *exp_avg, float *exp_a
 EC_API int ec_gemm_f32_strided(const float *A, int64_t sam, int64_t sak, const float *B, int64_t sbk, int64_t sbn, int M, int N,
                                int K, float alpha, float *out, int64_t ldo, int accumulate, void *stream);
 
+/* LoRA factor gradients from the gradient of the merged weight W_eff = W + up . down (models/lora.py:138-149 q/k/v,
+ * 49-52 out_proj; the reference gets them from autograd):  d_up[rows,r] = dW . down^T,  d_down[r,d] = up^T . dW.
+ * dW fp32 holds n_mat (<= 4) matrices of `rows` rows stacked (q | k | v of in_proj, or out_proj alone), row stride ld.
+ * up / down / d_up / d_down: HOST arrays of n_mat device pointers; a NULL up[z] skips matrix z (e.g. no LoRA on k). */
+EC_API int ec_lora_grad(const float *dW, int64_t ld, int n_mat, int rows, int d, int r, const float *const *up,
+                        const float *const *down, float *const *d_up, float *const *d_down, void *stream);
+
 /* Backward of F.normalize(x, p=2, dim=-1) followed by the valid-mask multiply (clip_cls_ft.py:229-232; text features
  * :163): dx = (dy - y<y,dy>) / max(|x|, 1e-12); rows with mask == 0 get dx = 0.  mask nullable. */
 EC_API int ec_l2norm_rows_bwd(const float *x, const float *dy, const uint8_t *mask, int M, int C, float *dx, void *stream);

@@ -67,7 +67,7 @@ def run(name, ds, arch, B, few_shot, steps=8):
     return r
 
 
-def run_finetune(name, ds, arch, B, lora="qkvo-16", steps=8):
+def run_finetune(name, ds, arch, B, lora="qkvo-16", steps=8, eager=False):
     """BASELINE config 5: one fine-tune step = events -> frames -> forward -> loss -> backward -> (all-reduce) -> Adam."""
     from eventclip_b200 import train
     from eventclip_b200 import _lib
@@ -88,30 +88,35 @@ def run_finetune(name, ds, arch, B, lora="qkvo-16", steps=8):
     labels = torch.randint(0, cfg["n_cls"], (B,), generator=torch.Generator().manual_seed(1)).to(dev)
     torch.manual_seed(0)
     sel = m.event_frontend.draw_selection(off)
+    from eventclip_b200.graph import GraphedFineTuner
     tuner = train.FineTuner(m, lr=2e-5)
+    stepper = tuner if eager else GraphedFineTuner(tuner, max_events=ev.shape[0])
     for _ in range(3):
-        loss = tuner.step(evd, off, labels, sel=sel)
+        loss = stepper.step(evd, off, labels, sel=sel)
     torch.cuda.synchronize()
     l0 = _lib.LAUNCHES
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(steps):
-        loss = tuner.step(evd, off, labels, sel=sel)
+        loss = stepper.step(evd, off, labels, sel=sel)
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / steps
     nv = int(tuner.last["out"]["valid_masks"].sum())
-    r = dict(config=name, dataset=ds, arch=arch, batch=B, valid_views=nv, ms_per_step=ms, samples_per_s=B / ms * 1e3,
-             views_per_s=nv / ms * 1e3, trainable=tuner.flat.numel, loss=float(loss), launches_per_step=(_lib.LAUNCHES - l0) / steps,
+    r = dict(config=name, mode="eager" if eager else "cuda graph", dataset=ds, arch=arch, batch=B, valid_views=nv, ms_per_step=ms,
+             samples_per_s=B / ms * 1e3, views_per_s=nv / ms * 1e3, trainable=tuner.flat.numel, loss=float(loss), launches_per_step=(_lib.LAUNCHES - l0) / steps,
              encoder_tflops_fwd_bwd=3 * clip.flops_per_image(arch) * nv / ms / 1e9,
              peak_mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30)
     print(json.dumps(r))
-    del tuner, m, model
+    del stepper, tuner, m, model
     torch.cuda.empty_cache()
     return r
 
 
 if __name__ == "__main__":
+    if "--finetune-one" in sys.argv:      # for ncu launch lists: one configuration, eager launches
+        run_finetune("C5 (eager, profiling run)", "n_caltech101", "ViT-B/16", 32, steps=2, eager=True)
+        sys.exit(0)
     if "--finetune" in sys.argv:
         res = [run_finetune("C5 LoRA qkvo-16 fine-tune step ViT-B/16 N-Caltech101 (32 samples x 2 views)", "n_caltech101", "ViT-B/16", 32),
                run_finetune("C5 at batch 128 (the 4-GPU global batch of configs/ftclip on one GPU)", "n_caltech101", "ViT-B/16", 128),

@@ -186,3 +186,42 @@ def test_fused_step_vs_oracle_autograd(cuda_dev):
     assert not torch.equal(before, tuner.flat_p)
     assert abs(l1.item() - loss.item()) < 1e-6 * max(1.0, abs(loss.item()))     # same inputs, same weights: deterministic
     assert l2.item() < l1.item()                                                # the step went downhill
+
+
+def test_graphed_step_matches_eager(cuda_dev):
+    """GraphedFineTuner replays forward + loss + backward (and the LoRA re-merge) from CUDA graphs; over several steps on
+    DIFFERENT batches of the same geometry its losses and parameters are bitwise those of the eager FineTuner."""
+    from eventclip_b200.graph import GraphedFineTuner
+    ds, B = "n_cars", 6
+    cfg = SENSORS[ds]
+    q = dict(max_imgs=2, N=cfg["N"], split_method="event_count", convert_method="event_histogram", grayscale=True,
+             count_non_zero=cfg["count_non_zero"], background_mask=cfg["background_mask"])
+    text = clip_oracle.synth_text_feats(cfg["n_cls"], 64, 8)
+
+    def make():
+        m = clip.init_weights_(clip.CLIP(ARCH), seed=9).to(cuda_dev).eval()
+        cd = dict(clip_model=m, prompt="a {}", class_names=None, agg_func="mean", lora="qkvo-4", only_conv1=False,
+                  only_bias=False, only_ln=False, text_feats=text)
+        ft = FTCLIPClassifier(adapter_dict=dict(adapter_type="text-identity", residual=True), clip_dict=cd,
+                              loss_dict=dict(use_logits_loss=True, use_probs_loss=False)).to(cuda_dev)
+        ft.attach_event_frontend(q, cfg["shape"], cfg["max_n"])
+        gen = torch.Generator().manual_seed(5)
+        with torch.no_grad():
+            for n, p in ft.named_parameters():
+                if "lora" in n:
+                    p.copy_((0.05 * torch.randn(p.shape, generator=gen)).to(cuda_dev))
+        return train.FineTuner(ft.train(), lr=1e-3, clip_lr=5e-4)
+
+    eager, graphed = make(), make()
+    gt = GraphedFineTuner(graphed, max_events=B * 8000)
+    for step in range(4):
+        Bs = B if step < 3 else B - 2                   # last step: smaller batch -> different counts, second graph
+        ev, off = synth_batch(ds, Bs, 300 + 10 * step, kind="clustered", E=6000)
+        labels = torch.randint(0, cfg["n_cls"], (Bs,), generator=torch.Generator().manual_seed(step))
+        evd = torch.from_numpy(ev).to(cuda_dev)
+        l_e = eager.step(evd, off, labels).clone()
+        l_g = gt.step(evd, off, labels).clone()
+        assert torch.equal(l_e, l_g), (step, l_e.item(), l_g.item())
+        assert torch.equal(eager.flat_g, graphed.flat_g)
+        assert torch.equal(eager.flat_p, graphed.flat_p), step
+    assert len(gt.cache) == 2

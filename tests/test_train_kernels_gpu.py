@@ -134,3 +134,19 @@ def test_ce_loss_bwd(cuda_dev, agg):
     assert abs(lm.item() - loss.item()) < 1e-5 * max(1.0, abs(loss.item()))
     assert rel(lb, F.cross_entropy(logits, labels, reduction="none").detach()) < 1e-5
     assert rel(dfull, full.grad) < 1e-5
+
+
+@pytest.mark.parametrize("rows,d,r,skip", [(128, 128, 4, None), (768, 768, 16, 1), (96, 200, 20, None)])
+def test_lora_grad(cuda_dev, rows, d, r, skip):
+    """d_up = dW . down^T, d_down = up^T . dW for three stacked matrices (q | k | v), optionally without LoRA on k."""
+    g = torch.Generator().manual_seed(rows + r)
+    dW = torch.randn(3 * rows, d, generator=g)
+    fac = [(torch.randn(rows, r, generator=g), torch.randn(r, d, generator=g)) for _ in range(3)]
+    dev_fac = [None if z == skip else (u.to(cuda_dev), dn.to(cuda_dev)) for z, (u, dn) in enumerate(fac)]
+    outs = ops.lora_grad(dW.to(cuda_dev), rows, dev_fac)
+    for z, (u, dn) in enumerate(fac):
+        if z == skip:
+            assert outs[z] is None
+            continue
+        w = dW[z * rows:(z + 1) * rows]
+        assert rel(outs[z][0], w @ dn.t()) < 1e-5 and rel(outs[z][1], u.t() @ w) < 1e-5
