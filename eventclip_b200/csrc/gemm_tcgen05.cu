@@ -46,6 +46,8 @@ struct GemmParams {
     int row_map;          // tokens per image (G*G) for EC_EPI_PATCH
     int tiles_m, tiles_n;
     uint32_t tx_bytes;    // bytes landing per stage (A box + W box)
+    int splits;           // split-K (EC_EPI_F32 only): tile index = split * tiles_m * tiles_n + tile; partial sums go to
+    int kb_per_split;     //   out + split * M * ldo, each covering kb_per_split 64-wide K blocks
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -277,7 +279,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = p.tiles_m * p.tiles_n;
+    const int tiles_mn = p.tiles_m * p.tiles_n;
+    const int num_tiles = tiles_mn * p.splits;
     const int num_kb = (p.K + BK - 1) / BK;
 
     if (warp == 0 && lane == 0) {
@@ -313,8 +316,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         {
             uint32_t stage = 0, phase = 0;
             for (int tile = group_id; tile < num_tiles; tile += num_groups) {
-                const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int sp = tile / tiles_mn, t2 = tile - sp * tiles_mn;
+                const int tm = t2 / p.tiles_n, tn = t2 % p.tiles_n;
+                const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char *sa = smem + stage * STAGE_BYTES;
                     unsigned char *sb = sa + A_BYTES;
@@ -343,7 +348,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 mbar_wait(&tempty_bar[as], aphase ^ 1);   // epilogue (of both CTAs) has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int sp = tile / tiles_mn;
+                const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
@@ -353,16 +360,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k) {
                             // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
-                            if (CG == 2) umma_bf16_2sm(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
-                            else umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
+                            if (CG == 2) umma_bf16_2sm(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, ((kb - kb0) | k) != 0);
+                            else umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, ((kb - kb0) | k) != 0);
                         }
                         // smem slot reusable / accumulator readable once these MMAs retire (in both CTAs of a pair)
                         if (CG == 2) {
                             umma_commit_2sm(&empty_bar[stage]);
-                            if (kb == num_kb - 1) umma_commit_2sm(&tfull_bar[as]);
+                            if (kb == kb1 - 1) umma_commit_2sm(&tfull_bar[as]);
                         } else {
                             umma_commit(&empty_bar[stage]);
-                            if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);
+                            if (kb == kb1 - 1) umma_commit(&tfull_bar[as]);
                         }
                     }
                     __syncwarp();
@@ -511,7 +518,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         constexpr int NPASS = 2 * NCHUNK;
         uint32_t as = 0, aphase = 0;
         for (int tile = group_id; tile < num_tiles; tile += num_groups) {
-            const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+            const int sp = tile / tiles_mn, t2 = tile - sp * tiles_mn;
+            const int tm = t2 / p.tiles_n, tn = t2 % p.tiles_n;
             const int row0 = (tm * CG + (int)cta_rank) * BM + quarter * 32;
             const int colw = tn * BN + half * COLS_PER_WARP;
             // per-lane output rows / residual rows of the fp32 mapping
@@ -522,7 +530,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             for (int i = 0; i < 4; ++i) {
                 const int r = row0 + f_r + 8 * i;
                 rok[i] = r < p.M;
-                orow[i] = (size_t)r;
+                orow[i] = (size_t)r + (size_t)sp * p.M;      // split-K partials are stacked [splits, M, ldo]
                 rrow[i] = nullptr;
                 if (p.epi == EC_EPI_PATCH) {
                     const int g2 = p.row_map;
@@ -719,7 +727,7 @@ int launch(const CUtensorMap &ma, const CUtensorMap &mw, const CUtensorMap &mo, 
     }
     p.tiles_m = (p.M + BM * CG - 1) / (BM * CG);
     p.tiles_n = (p.N + BN - 1) / BN;
-    const int tiles = p.tiles_m * p.tiles_n;
+    const int tiles = p.tiles_m * p.tiles_n * p.splits;
     const int max_groups = ec::sm_count() / CG;
     const int groups = tiles < max_groups ? tiles : max_groups;
     cudaLaunchConfig_t cfg = {};
@@ -735,12 +743,71 @@ int launch(const CUtensorMap &ma, const CUtensorMap &mw, const CUtensorMap &mo, 
     return EC_OK;
 }
 
+// out[m, n] = sum_s ws[s, m, n] in a fixed order (split-K partial sums)
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float4 *__restrict__ ws, int splits, int64_t mn4, int n4, int ldo4,
+                                                            float4 *__restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < mn4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 a = ws[i];
+        for (int s = 1; s < splits; ++s) {
+            const float4 b = ws[(int64_t)s * mn4 + i];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        const int64_t m = i / n4;
+        out[m * ldo4 + (i - m * n4)] = a;
+    }
+}
+
+int gemm_impl(const void *A, int lda, const void *W, int ldw, const float *bias, int M, int N, int K, int epi, void *out, int ldo,
+              const float *res, int row_map, int splits, cudaStream_t stream);
+
 }  // namespace
 
 extern "C" int ec_gemm_bf16(const void *A, int lda, const void *W, int ldw, const float *bias, int M, int N, int K,
                             int epi, void *out, int ldo, const float *res, int row_map, void *stream_)
 {
+    return gemm_impl(A, lda, W, ldw, bias, M, N, K, epi, out, ldo, res, row_map, 1, (cudaStream_t)stream_);
+}
+
+extern "C" int ec_gemm_splitk_choose(int M, int N, int K)
+{
+    if (M <= 0 || N <= 0 || K < BK) return 1;
+    const int BN = (N % 256 == 0) ? 256 : 128;
+    const int CG = (BN != 256 || M < 2 * BM) ? 1 : 2;
+    const int tiles = ((M + BM * CG - 1) / (BM * CG)) * ((N + BN - 1) / BN);
+    const int groups = ec::sm_count() / CG;
+    int s = groups / tiles;                       // fill the machine once
+    const int num_kb = (K + BK - 1) / BK;
+    if (s > num_kb / 8) s = num_kb / 8;           // keep at least 8 K blocks (512 elements) per split
+    return s < 1 ? 1 : (s > 32 ? 32 : s);
+}
+
+extern "C" int ec_gemm_bf16_splitk(const void *A, int lda, const void *W, int ldw, int M, int N, int K, int splits,
+                                   float *workspace, float *out, int ldo, void *stream_)
+{
     cudaStream_t stream = (cudaStream_t)stream_;
+    EC_REQUIRE(splits >= 1 && splits <= 64, "ec_gemm_bf16_splitk: splits must be in [1, 64] (got %d)", splits);
+    if (K >= BK) {      // drop splits that would be empty: every split covers ceil(num_kb / splits) K blocks
+        const int num_kb = (K + BK - 1) / BK, per = (num_kb + splits - 1) / splits;
+        splits = (num_kb + per - 1) / per;
+    }
+    if (splits == 1) return gemm_impl(A, lda, W, ldw, nullptr, M, N, K, EC_EPI_F32, out, ldo, nullptr, 0, 1, stream);
+    EC_REQUIRE(workspace && out && ldo % 4 == 0 && N % 8 == 0 && ((uintptr_t)workspace & 15) == 0 && ((uintptr_t)out & 15) == 0,
+               "ec_gemm_bf16_splitk: needs a 16-byte aligned workspace of splits*M*N floats and ldo %% 4 == 0");
+    int rc = gemm_impl(A, lda, W, ldw, nullptr, M, N, K, EC_EPI_F32, workspace, N, nullptr, 0, splits, stream);
+    if (rc != EC_OK) return rc;
+    const int64_t mn4 = (int64_t)M * N / 4;
+    const int blocks = (int)((mn4 + 255) / 256 < 148 * 8 ? (mn4 + 255) / 256 : 148 * 8);
+    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>((const float4 *)workspace, splits, mn4, N / 4, ldo / 4, (float4 *)out);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
+namespace {
+
+int gemm_impl(const void *A, int lda, const void *W, int ldw, const float *bias, int M, int N, int K, int epi, void *out, int ldo,
+              const float *res, int row_map, int splits, cudaStream_t stream)
+{
     EC_REQUIRE(A && W && out, "ec_gemm_bf16: null pointer");
     EC_REQUIRE(M > 0 && N > 0 && K >= BK, "ec_gemm_bf16: need M,N > 0 and K >= 64 (got %d,%d,%d)", M, N, K);
     EC_REQUIRE(N % 8 == 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= K,
@@ -767,6 +834,13 @@ extern "C" int ec_gemm_bf16(const void *A, int lda, const void *W, int ldw, cons
     GemmParams p;
     p.M = M; p.N = N; p.K = K; p.epi = epi; p.out = out; p.ldo = ldo; p.bias = bias; p.res = res; p.row_map = row_map;
     p.tx_bytes = (uint32_t)(box_a + box_w) * BK * 2 * CG;   // a pair's leader barrier collects both CTAs' bytes
+    {
+        const int num_kb = (K + BK - 1) / BK;
+        EC_REQUIRE(splits == 1 || (epi == EC_EPI_F32 && !bias), "ec_gemm: split-K needs the plain fp32 epilogue");
+        p.kb_per_split = (num_kb + splits - 1) / splits;
+        p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;   // no empty split
+        EC_REQUIRE(p.splits == splits, "ec_gemm: %d splits leave an empty split for K=%d; use ec_gemm_splitk_choose", splits, K);
+    }
     CUtensorMap mo = ma;   // placeholder for fp32 epilogues (never dereferenced there)
     if (epi == EC_EPI_BF16 || epi == EC_EPI_BF16_QGELU) {
         rc = make_out_map(&mo, out, M, N, ldo);
@@ -783,3 +857,5 @@ extern "C" int ec_gemm_bf16(const void *A, int lda, const void *W, int ldw, cons
     if (CG == 2) return launch<256, 2>(ma, mw, mo, mr, p, stream);
     return BN == 256 ? launch<256, 1>(ma, mw, mo, mr, p, stream) : launch<128, 1>(ma, mw, mo, mr, p, stream);
 }
+
+}  // namespace

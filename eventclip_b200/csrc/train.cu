@@ -90,60 +90,54 @@ struct LoraGradArgs {
     float *d_up[4], *d_down[4];
 };
 
-// one warp per row of dW; 16 ranks at a time
-__global__ void __launch_bounds__(256) lora_dup_kernel(const float *__restrict__ dW, int64_t ld, int rows, int d, int r, LoraGradArgs g)
+// One launch, both products: blockIdx.x < ceil(rows/16) computes a 16-row tile of d_up (all ranks, 16 at a time), the other
+// blocks a 16-column tile of d_down.  256 threads = 16 x 16 outputs; the reduction index is staged through shared memory
+// 128 deep, so a CTA issues 6 rounds of wide loads for d = rows = 768 instead of a dependent load per multiply-add.
+constexpr int LG_KC = 128;
+__global__ void __launch_bounds__(256) lora_grad_kernel(const float *__restrict__ dW, int64_t ld, int rows, int d, int r, LoraGradArgs g)
 {
-    const int z = blockIdx.y, row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (!g.d_up[z] || row >= rows) return;
-    const float *w = dW + ((size_t)z * rows + row) * ld, *dn = g.down[z];
-    for (int j0 = 0; j0 < r; j0 += 16) {
-        float acc[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-        for (int c = lane; c < d; c += 32) {
-            const float x = w[c];
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (j0 + j < r) acc[j] += x * dn[(size_t)(j0 + j) * d + c];
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const float t = ec::warp_sum(acc[j]);
-            if (lane == 0 && j0 + j < r) g.d_up[z][(size_t)row * r + j0 + j] = t;
-        }
-    }
-}
-
-// 32 columns x 8 row groups per CTA; partial sums of the row groups are folded through shared memory in a fixed order
-__global__ void __launch_bounds__(256) lora_ddown_kernel(const float *__restrict__ dW, int64_t ld, int rows, int d, int r, LoraGradArgs g)
-{
-    __shared__ float part[8][16][33];
-    const int z = blockIdx.y, tx = threadIdx.x & 31, rg = threadIdx.x >> 5, c = blockIdx.x * 32 + tx;
-    if (!g.d_down[z]) return;
-    const float *w = dW + (size_t)z * rows * ld, *up = g.up[z];
-    for (int j0 = 0; j0 < r; j0 += 16) {
-        float acc[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-        if (c < d)
-            for (int i = rg; i < rows; i += 8) {
-                const float x = w[(size_t)i * ld + c];
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (j0 + j < r) acc[j] += x * up[(size_t)i * r + j0 + j];
+    __shared__ float sa[16][LG_KC + 1];      // d_up: dW[row][k]      d_down: up^T[j][k]   (k = reduction index)
+    __shared__ float sb[16][LG_KC + 1];      // d_up: down[j][k]      d_down: dW^T[c][k]
+    const int z = blockIdx.y, tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    if (!g.d_up[z]) return;
+    const float *w = dW + (size_t)z * rows * ld, *up = g.up[z], *dn = g.down[z];
+    const int up_tiles = (rows + 15) / 16;
+    if ((int)blockIdx.x < up_tiles) {
+        // d_up[row0 + ty][j0 + tx] = sum_c dW[row][c] * down[j][c]
+        const int row0 = blockIdx.x * 16;
+        for (int j0 = 0; j0 < r; j0 += 16) {
+            float acc = 0.f;
+            for (int k0 = 0; k0 < d; k0 += LG_KC) {
+                for (int e = tid; e < 16 * LG_KC; e += 256) {
+                    const int rr = e / LG_KC, k = e - rr * LG_KC;
+                    sa[rr][k] = (row0 + rr < rows && k0 + k < d) ? w[(size_t)(row0 + rr) * ld + k0 + k] : 0.f;
+                    sb[rr][k] = (j0 + rr < r && k0 + k < d) ? dn[(size_t)(j0 + rr) * d + k0 + k] : 0.f;
+                }
+                __syncthreads();
+#pragma unroll 16
+                for (int k = 0; k < LG_KC; ++k) acc += sa[ty][k] * sb[tx][k];
+                __syncthreads();
             }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) part[rg][j][tx] = acc[j];
-        __syncthreads();
-#pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
-            const int j = rg * 2 + jj;
-            float t = 0.f;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) t += part[q][j][tx];
-            if (c < d && j0 + j < r) g.d_down[z][(size_t)(j0 + j) * d + c] = t;
+            if (row0 + ty < rows && j0 + tx < r) g.d_up[z][(size_t)(row0 + ty) * r + j0 + tx] = acc;
         }
-        __syncthreads();
+    } else {
+        // d_down[j0 + ty][c0 + tx] = sum_i up[i][j] * dW[i][c]
+        const int c0 = ((int)blockIdx.x - up_tiles) * 16;
+        for (int j0 = 0; j0 < r; j0 += 16) {
+            float acc = 0.f;
+            for (int k0 = 0; k0 < rows; k0 += LG_KC) {
+                for (int e = tid; e < 16 * LG_KC; e += 256) {
+                    const int k = e >> 4, q = e & 15;          // 16 consecutive floats of one row per half-warp
+                    sa[q][k] = (k0 + k < rows && j0 + q < r) ? up[(size_t)(k0 + k) * r + j0 + q] : 0.f;
+                    sb[q][k] = (k0 + k < rows && c0 + q < d) ? w[(size_t)(k0 + k) * ld + c0 + q] : 0.f;
+                }
+                __syncthreads();
+#pragma unroll 16
+                for (int k = 0; k < LG_KC; ++k) acc += sa[ty][k] * sb[tx][k];
+                __syncthreads();
+            }
+            if (j0 + ty < r && c0 + tx < d) g.d_down[z][(size_t)(j0 + ty) * d + c0 + tx] = acc;
+        }
     }
 }
 
@@ -406,8 +400,7 @@ extern "C" int ec_lora_grad(const float *dW, int64_t ld, int n_mat, int rows, in
         g.d_up[z] = on ? d_up[z] : nullptr; g.d_down[z] = on ? d_down[z] : nullptr;
         if (on) EC_REQUIRE(d_up[z] && d_down[z], "ec_lora_grad: matrix %d has factors but no gradient buffers", z);
     }
-    lora_dup_kernel<<<dim3((rows + 7) / 8, n_mat), 256, 0, (cudaStream_t)stream>>>(dW, ld, rows, d, r, g);
-    lora_ddown_kernel<<<dim3((d + 31) / 32, n_mat), 256, 0, (cudaStream_t)stream>>>(dW, ld, rows, d, r, g);
+    lora_grad_kernel<<<dim3((rows + 15) / 16 + (d + 15) / 16, n_mat), 256, 0, (cudaStream_t)stream>>>(dW, ld, rows, d, r, g);
     EC_CUDA_CHECK(cudaGetLastError());
     return EC_OK;
 }

@@ -445,3 +445,23 @@ def lora_grad(dW, rows, factors, dests=None):
         L.check(L.load().ec_lora_grad(_ptr(dW), dW.stride(0), n, rows, d, r, arrs[0], arrs[1], arrs[2], arrs[3], _stream()),
                 "ec_lora_grad")
     return outs
+
+
+def gemm_bf16_splitk(A, W, splits=None, out=None, M=None, K=None):
+    """fp32 out = A @ W.T for weight-gradient shapes (small M x N, long K): split-K over the SMs, deterministic sum."""
+    _dev(A, torch.bfloat16, "A")
+    _dev(W, torch.bfloat16, "W")
+    M = A.shape[0] if M is None else M
+    N = W.shape[0]
+    K = W.shape[1] if K is None else K
+    lib = L.load()
+    if splits is None:
+        with torch.cuda.device(A.device):
+            splits = lib.ec_gemm_splitk_choose(M, N, K)
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    ws = torch.empty((splits, M, N), dtype=torch.float32, device=A.device) if splits > 1 else None
+    with torch.cuda.device(A.device):
+        L.check(lib.ec_gemm_bf16_splitk(_ptr(A), A.stride(0), _ptr(W), W.stride(0), M, N, K, int(splits), _ptr(ws), _ptr(out),
+                                        out.stride(0), _stream()), "ec_gemm_bf16_splitk")
+    return out

@@ -127,11 +127,11 @@ def encoder_backward(vis, ctx, d_feats, slots, dest=None):
         d_att = ops.gemm_bf16(dx2b, b["w_out_t"], None, "bf16")              # [M, d]
         w = want.get(i, {})
         if "o" in w:
-            dW = ops.gemm_bf16(ops.transpose_bf16(dx2b), ops.transpose_bf16(att), None, "f32")      # [d_out, d_in]
+            dW = ops.gemm_bf16_splitk(ops.transpose_bf16(dx2b), ops.transpose_bf16(att))            # [d_out, d_in]
             factor_grads(dW, d, "o", i, w)
         dqkv = ops.attention_bwd(qkv, att, d_att, n_img, Ltok, heads)
         if any(n in w for n in "qkv"):
-            dW = ops.gemm_bf16(ops.transpose_bf16(dqkv), ops.transpose_bf16(h1), None, "f32")       # [3d, d]
+            dW = ops.gemm_bf16_splitk(ops.transpose_bf16(dqkv), ops.transpose_bf16(h1))             # [3d, d]
             factor_grads(dW, d, "qkv", i, w)
         if i > first:                                                        # nothing trainable below the first LoRA block
             dh1 = ops.gemm_bf16(dqkv, b["w_in_t"], None, "f32")

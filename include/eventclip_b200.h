@@ -123,6 +123,14 @@ EC_API int ec_event2img_geometry(int H, int W, int *cluster_size, int *threads, 
 EC_API int ec_gemm_bf16(const void *A, int lda, const void *W, int ldw, const float *bias, int M, int N, int K,
                  int epi, void *out, int ldo, const float *res, int row_map, void *stream);
 
+/* Split-K variant for weight-gradient shapes (small M x N, long K = tokens): out fp32 [M,ldo] = A[M,K] . W[N,K]^T with the
+ * K range cut into `splits` parts that run as separate tiles and are summed in a fixed order (deterministic).
+ * workspace: device fp32 [splits * M * N] (unused when splits == 1).  ec_gemm_splitk_choose returns the split count that
+ * fills the SMs once for a shape (>= 512 K elements per split). */
+EC_API int ec_gemm_splitk_choose(int M, int N, int K);
+EC_API int ec_gemm_bf16_splitk(const void *A, int lda, const void *W, int ldw, int M, int N, int K, int splits,
+                               float *workspace, float *out, int ldo, void *stream);
+
 /* LayerNorm over the last dim (eps 1e-5, fp32 statistics): x fp32 [M, ldx] rows -> bf16 [M,d] (out_bf16)
  * and/or fp32 [M,d] (out_f32); either output may be NULL.  row_stride_in lets ln_post read only the
  * class-token rows (stride L*d). */

@@ -8,9 +8,10 @@ Tolerances: the backward runs on bf16 operands with fp32 accumulation (activatio
 reference is fp32 end to end: loss within 2e-2 relative; gradients of text features and of the v / out_proj LoRA factors
 within 6e-2 relative L2 and cosine >= 0.998.  Gradients of the q / k factors go through the softmax Jacobian
 (dS = P * (dP - <P, dP>), a cancellation) and on the 12-layer random-init ViT-B/16 they are ill-conditioned in ANY bf16
-pipeline: torch.autocast(bfloat16) of the fp32 oracle sits 2-11 % from fp32 per tensor, this library 2-15 %
-(tests/tools/ft_noise_floor.py, profiles/r01_ft_gradient_noise_floor.txt).  For those tensors: per tensor rel-L2 <= 0.25
-and cosine >= 0.97, and over all q/k factors together rel-L2 <= 0.12.
+pipeline: over ten draws of the LoRA factors, torch.autocast(bfloat16) of the fp32 oracle sits up to 0.10-0.29 from fp32
+on its worst q/k tensor (0.03-0.07 over all q/k factors together) and this library up to 0.08-0.32 (0.03-0.06 together)
+(tests/tools/ft_noise_floor.py, profiles/r01_ft_gradient_noise_floor.txt).  For those tensors, with the draw fixed by a
+seed: per tensor rel-L2 <= 0.4 and cosine >= 0.92, and over all q/k factors together rel-L2 <= 0.1.
 Adam applied to the reference's own gradient reproduces the reference's updated parameters to 1e-6.
 """
 import os
@@ -30,7 +31,7 @@ pytestmark = pytest.mark.gpu
 ARCH = "ViT-tiny/32"
 NAMES = [f"class_{i}" for i in range(11)]
 GRAD_TOL, COS_TOL = 6e-2, 0.998
-QK_TOL, QK_COS, QK_ALL = 0.25, 0.97, 0.12
+QK_TOL, QK_COS, QK_ALL = 0.4, 0.92, 0.1
 
 
 def rel(a, b):
@@ -126,6 +127,7 @@ def test_fused_step_vs_oracle_autograd(cuda_dev):
     """BASELINE config 5 in miniature: ViT-B/16, LoRA qkvo-16 + prompt-tuned text features, N-Caltech101-shaped streams,
     2 views per sample; loss and every gradient against fp32 autograd through the oracle frames / CLIP / head."""
     ds, arch, B = "n_caltech101", "ViT-B/16", 4
+    torch.manual_seed(0)                # lora_down is drawn from the global generator at injection (models/lora.py:8-11)
     cfg = SENSORS[ds]
     q = dict(max_imgs=2, N=cfg["N"], split_method="event_count", convert_method="event_histogram", grayscale=True,
              count_non_zero=cfg["count_non_zero"], background_mask=cfg["background_mask"])
@@ -199,6 +201,7 @@ def test_graphed_step_matches_eager(cuda_dev):
     text = clip_oracle.synth_text_feats(cfg["n_cls"], 64, 8)
 
     def make():
+        torch.manual_seed(0)
         m = clip.init_weights_(clip.CLIP(ARCH), seed=9).to(cuda_dev).eval()
         cd = dict(clip_model=m, prompt="a {}", class_names=None, agg_func="mean", lora="qkvo-4", only_conv1=False,
                   only_bias=False, only_ln=False, text_feats=text)

@@ -150,3 +150,20 @@ def test_lora_grad(cuda_dev, rows, d, r, skip):
             continue
         w = dW[z * rows:(z + 1) * rows]
         assert rel(outs[z][0], w @ dn.t()) < 1e-5 and rel(outs[z][1], u.t() @ w) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(768, 768, 12608, None), (2304, 768, 3 * 197 + 5, None), (384, 128, 304, 4),
+                                          (128, 128, 1000, 16), (768, 768, 12608, 1)])
+def test_gemm_splitk(cuda_dev, M, N, K, splits):
+    """Weight-gradient shapes: split-K partial tiles + fixed-order reduction equal the single-pass GEMM's result."""
+    g = torch.Generator().manual_seed(M + K)
+    Kp = (K + 7) // 8 * 8
+    A = torch.zeros(M, Kp).to(torch.bfloat16)
+    W = torch.zeros(N, Kp).to(torch.bfloat16)
+    A[:, :K] = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    W[:, :K] = (torch.randn(N, K, generator=g) * K ** -0.5).to(torch.bfloat16)
+    ref = A.float() @ W.float().t()
+    out = ops.gemm_bf16_splitk(A.to(cuda_dev), W.to(cuda_dev), splits=splits)
+    assert rel(out, ref) < 2e-3
+    again = ops.gemm_bf16_splitk(A.to(cuda_dev), W.to(cuda_dev), splits=splits)
+    assert torch.equal(out, again)            # deterministic

@@ -24,8 +24,10 @@ def rel(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
-def main():
+def main(seed=None, verbose=True):
     dev = torch.device("cuda", 0)
+    if seed is not None:
+        torch.manual_seed(seed)                 # lora_down is drawn from the global generator at injection
     ds, arch, B = "n_caltech101", "ViT-B/16", 4
     cfg = SENSORS[ds]
     q = dict(max_imgs=2, N=cfg["N"], split_method="event_count", convert_method="event_histogram", grayscale=True,
@@ -69,12 +71,29 @@ def main():
         feats_loss.backward()
         res[mode] = ({names[k][j]: t[j].grad for k, t in lora.items() for j in (0, 1)}, feats_loss.item())
     named = dict(ft.named_parameters())
-    print("loss fp32 %.5f autocast %.5f" % (res["fp32"][1], res["autocast"][1]))
-    print("%-70s %8s %8s" % ("tensor", "autocast", "library"))
+    if verbose:
+        print("loss fp32 %.5f autocast %.5f" % (res["fp32"][1], res["autocast"][1]))
+        print("%-70s %8s %8s" % ("tensor", "autocast", "library"))
+    qk = {"autocast": [], "library": []}
+    cat = {"ref": [], "autocast": [], "library": []}
     for nm, gref in res["fp32"][0].items():
-        print("%-70s %8.4f %8.4f" % (nm[len("model.visual.transformer."):], rel(res["autocast"][0][nm], gref),
-                                     rel(tuner._grad_view(named[nm]), gref)))
+        ra, rl = rel(res["autocast"][0][nm], gref), rel(tuner._grad_view(named[nm]), gref)
+        if verbose:
+            print("%-70s %8.4f %8.4f" % (nm[len("model.visual.transformer."):], ra, rl))
+        if nm.endswith(("_q", "_k")):
+            qk["autocast"].append(ra)
+            qk["library"].append(rl)
+            cat["ref"].append(gref.reshape(-1).float().cpu())
+            cat["autocast"].append(res["autocast"][0][nm].reshape(-1).float().cpu())
+            cat["library"].append(tuner._grad_view(named[nm]).reshape(-1).float().cpu())
+    ref = torch.cat(cat["ref"])
+    print("seed %s: q/k factor gradients vs fp32 -- autocast max %.3f all %.3f | library max %.3f all %.3f" % (
+        seed, max(qk["autocast"]), rel(torch.cat(cat["autocast"]), ref), max(qk["library"]), rel(torch.cat(cat["library"]), ref)))
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1:
+        for sd in range(int(sys.argv[1])):
+            main(seed=sd, verbose=False)
+    else:
+        main(seed=0)
