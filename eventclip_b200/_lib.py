@@ -66,6 +66,9 @@ SIGNATURES = {
     "ec_adam": ([_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _vp], _i),
     "ec_gemm_f32_strided": ([_vp, _i64, _i64, _vp, _i64, _i64, _i, _i, _i, _f, _vp, _i64, _i, _vp], _i),
     "ec_lora_grad": ([_vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp], _i),
+    "ec_colsum": ([_vp, _i, _i, _i, _i64, _vp, _i, _vp, _vp], _i),
+    "ec_layernorm_param_grad": ([_vp, _i64, _vp, _i, _i, _vp, _i, _vp, _vp, _vp], _i),
+    "ec_patch_rows_bf16": ([_vp, _i, _i, _i, _vp, _vp], _i),
     "ec_l2norm_rows_bwd": ([_vp, _vp, _vp, _i, _i, _vp, _vp], _i),
     "ec_ce_loss_bwd": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp], _i),
 }

@@ -204,19 +204,40 @@ class VisionTransformer(nn.Module):
                     b[n + "_t"] = ops.transpose_bf16(b[n])
         return pk
 
-    def refresh_lora_packed(self):
-        """After an optimizer step that changed only LoRA factors: re-merge them into the existing packed buffers (and
-        their transposes) instead of repacking the whole tower."""
+    def refresh_packed(self):
+        """After an optimizer step: rewrite, IN PLACE, the bf16 GEMM copies (and their transposes) of every trainable
+        weight -- LoRA factors are re-merged into in_proj / out_proj.  Pointer-stable, so CUDA graphs captured over the
+        packed weights stay valid.  fp32 vectors (biases, LayerNorm affine, embeddings) alias the master parameters and
+        need nothing."""
         if self._packed is None:
             return
-        pk = self._packed
+        pk, d, P, dev = self._packed, self.width, self.patch_size, self.proj.device
+        f32 = lambda t: t.detach().to(torch.float32).contiguous()
+        if self.conv1.weight.requires_grad:
+            w = f32(self.conv1.weight).reshape(d, 3 * P * P)
+            if self.k_patch != 3 * P * P:
+                wp = torch.zeros((d, self.k_patch), dtype=torch.float32, device=dev)
+                wp[:, :3 * P * P] = w
+                w = wp
+            ops.f32_to_bf16(w, dst=pk["conv1"])
+        if self.proj.requires_grad:
+            ops.f32_to_bf16(f32(self.proj).t().contiguous(), dst=pk["proj"])
+            if "proj_t" in pk:
+                ops.f32_to_bf16(f32(self.proj), dst=pk["proj_t"])
         for blk, b in zip(self.transformer.resblocks, pk["blocks"]):
-            if b["has_lora"]:
-                merge_attn_weights(blk, self.width, self.proj.device, w_in=b["w_in"], w_out=b["w_out"])
+            if any(p.requires_grad for p in blk.attn.parameters()):
+                merge_attn_weights(blk, d, dev, w_in=b["w_in"], w_out=b["w_out"])
                 if "w_in_t" in b:
                     ops.transpose_bf16(b["w_in"], out=b["w_in_t"])
                     ops.transpose_bf16(b["w_out"], out=b["w_out_t"])
+            for name, lin in (("w_fc", blk.mlp.c_fc), ("w_proj", blk.mlp.c_proj)):
+                if lin.weight.requires_grad:
+                    ops.f32_to_bf16(f32(lin.weight), dst=b[name])
+                    if name + "_t" in b:
+                        ops.transpose_bf16(b[name], out=b[name + "_t"])
         self._packed_key = self._version_key()
+
+    refresh_lora_packed = refresh_packed
 
     # -- forward ----------------------------------------------------------------------------------------------------
     def forward_patches(self, patches, n_img):

@@ -303,6 +303,100 @@ __global__ void mean_kernel(const float *v, int n, float *out)
     }
 }
 
+
+// ---- column reductions over the token dimension (bias / LayerNorm affine / embedding gradients), two deterministic stages:
+//      partial sums of row slabs, then a fixed-order fold ----
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(128) colsum_part_kernel(const T *__restrict__ a, int M, int N, int64_t ld, float *__restrict__ part)
+{
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c >= N) return;
+    const int per = (M + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * per, r1 = min(M, r0 + per);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int r = r0;
+    for (; r + 3 < r1; r += 4) {
+        s0 += to_f(a[(size_t)r * ld + c]); s1 += to_f(a[(size_t)(r + 1) * ld + c]);
+        s2 += to_f(a[(size_t)(r + 2) * ld + c]); s3 += to_f(a[(size_t)(r + 3) * ld + c]);
+    }
+    for (; r < r1; ++r) s0 += to_f(a[(size_t)r * ld + c]);
+    part[(size_t)blockIdx.y * N + c] = (s0 + s1) + (s2 + s3);
+}
+
+// out[c] = sum_p part[p, c] for n_out stacked outputs of width N each (part is [n_out][P][N])
+__global__ void __launch_bounds__(128) fold_kernel(const float *__restrict__ part, int P, int N, float *const o0, float *const o1)
+{
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c >= N) return;
+    float *const out = blockIdx.y == 0 ? o0 : o1;
+    const float *p = part + (size_t)blockIdx.y * P * N;
+    float s = 0.f;
+    for (int q = 0; q < P; ++q) s += p[(size_t)q * N + c];
+    out[c] = s;
+}
+
+// LayerNorm affine gradients: dgamma[c] = sum_rows dy * xhat, dbeta[c] = sum_rows dy.  Row statistics are recomputed per
+// row by a warp (the row is read once into registers for d <= 1024), then the 8 rows of a CTA are folded through shared
+// memory; slabs of rows -> part[2][P][d].
+__global__ void __launch_bounds__(256) ln_param_part_kernel(const float *__restrict__ x, int64_t x_stride, const float *__restrict__ dy,
+                                                            int M, int d, float *__restrict__ part, int P)
+{
+    extern __shared__ float sm[];                 // [2][d] accumulators of this CTA
+    float *sg = sm, *sbv = sm + d;
+    for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) sm[c] = 0.f;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per = (M + P - 1) / P, r0 = blockIdx.x * per, r1 = min(M, r0 + per);
+    // rows are taken by the 8 warps in turn; the shared accumulators are updated one warp at a time (fixed order)
+    for (int rb = r0; rb < r1; rb += 8) {
+        const int row = rb + warp;
+        float mean = 0.f, rstd = 0.f;
+        if (row < r1) {
+            const float *xr = x + (size_t)row * x_stride;
+            float s = 0.f;
+            for (int c = lane; c < d; c += 32) s += xr[c];
+            mean = ec::warp_sum(s) / (float)d;
+            float q = 0.f;
+            for (int c = lane; c < d; c += 32) { const float t = xr[c] - mean; q += t * t; }
+            rstd = rsqrtf(ec::warp_sum(q) / (float)d + 1e-5f);
+        }
+        for (int w = 0; w < 8; ++w) {
+            if (w == warp && row < r1) {
+                const float *xr = x + (size_t)row * x_stride, *dr = dy + (size_t)row * d;
+                for (int c = lane; c < d; c += 32) {
+                    const float g = dr[c];
+                    sg[c] += g * (xr[c] - mean) * rstd;
+                    sbv[c] += g;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        part[(size_t)blockIdx.x * d + c] = sg[c];
+        part[(size_t)(P + blockIdx.x) * d + c] = sbv[c];
+    }
+}
+
+// dst[r, :] = src[map(r), :] where map skips the class-token row of every image: r -> (r / G2) * (G2 + 1) + 1 + r % G2;
+// fp32 -> bf16 (the patch-token rows of d_x0 as the A operand of conv1's weight gradient)
+__global__ void __launch_bounds__(256) patch_rows_bf16_kernel(const float *__restrict__ src, int n_rows, int G2, int d,
+                                                              __nv_bfloat16 *__restrict__ dst)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // one thread per 4 elements
+    const int d4 = d >> 2;
+    if (i >= (int64_t)n_rows * d4) return;
+    const int r = (int)(i / d4), c = (int)(i - (int64_t)r * d4) * 4;
+    const int img = r / G2, tok = r - img * G2;
+    const float4 v = *reinterpret_cast<const float4 *>(src + ((size_t)img * (G2 + 1) + 1 + tok) * d + c);
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o; o.x = *reinterpret_cast<uint32_t *>(&a); o.y = *reinterpret_cast<uint32_t *>(&b);
+    *reinterpret_cast<uint2 *>(dst + (size_t)r * d + c) = o;
+}
+
 }  // namespace
 
 extern "C" int ec_layernorm_bwd(const float *x, int64_t x_stride, const float *dy, const float *gamma, const float *acc,
@@ -401,6 +495,37 @@ extern "C" int ec_lora_grad(const float *dW, int64_t ld, int n_mat, int rows, in
         if (on) EC_REQUIRE(d_up[z] && d_down[z], "ec_lora_grad: matrix %d has factors but no gradient buffers", z);
     }
     lora_grad_kernel<<<dim3((rows + 15) / 16 + (d + 15) / 16, n_mat), 256, 0, (cudaStream_t)stream>>>(dW, ld, rows, d, r, g);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
+extern "C" int ec_colsum(const void *a, int is_bf16, int M, int N, int64_t ld, float *scratch, int n_part, float *out, void *stream)
+{
+    EC_REQUIRE(a && scratch && out && M > 0 && N > 0 && ld >= N && n_part >= 1 && n_part <= 4096, "ec_colsum: bad arguments");
+    const dim3 grid((N + 127) / 128, n_part);
+    if (is_bf16) colsum_part_kernel<__nv_bfloat16><<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)a, M, N, ld, scratch);
+    else colsum_part_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>((const float *)a, M, N, ld, scratch);
+    fold_kernel<<<dim3((N + 127) / 128, 1), 128, 0, (cudaStream_t)stream>>>(scratch, n_part, N, out, out);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
+extern "C" int ec_layernorm_param_grad(const float *x, int64_t x_stride, const float *dy, int M, int d, float *scratch, int n_part,
+                                       float *dgamma, float *dbeta, void *stream)
+{
+    EC_REQUIRE(x && dy && scratch && dgamma && dbeta && M > 0 && d > 0 && n_part >= 1 && n_part <= 4096 && d <= 4096,
+               "ec_layernorm_param_grad: bad arguments");
+    ln_param_part_kernel<<<n_part, 256, 2 * d * sizeof(float), (cudaStream_t)stream>>>(x, x_stride, dy, M, d, scratch, n_part);
+    fold_kernel<<<dim3((d + 127) / 128, 2), 128, 0, (cudaStream_t)stream>>>(scratch, n_part, d, dgamma, dbeta);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
+extern "C" int ec_patch_rows_bf16(const float *src, int n_img, int G2, int d, void *dst, void *stream)
+{
+    EC_REQUIRE(src && dst && n_img > 0 && G2 > 0 && d > 0 && d % 4 == 0, "ec_patch_rows_bf16: bad arguments");
+    const int64_t n = (int64_t)n_img * G2 * (d / 4);
+    patch_rows_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, n_img * G2, G2, d, (__nv_bfloat16 *)dst);
     EC_CUDA_CHECK(cudaGetLastError());
     return EC_OK;
 }

@@ -117,14 +117,13 @@ class GraphedFineTuner:
         self.refresh_graph, self.refresh_launches = None, 0
 
     def _refresh_weights(self):
-        vis = self.tuner.vis
         if self.refresh_graph is None:
-            vis.refresh_lora_packed()                    # eager once (also the warm-up)
+            self.tuner.refresh_weights()                 # eager once (also the warm-up)
             torch.cuda.synchronize(self.dev)
             g = torch.cuda.CUDAGraph()
             n0 = L.LAUNCHES
             with torch.cuda.graph(g):
-                vis.refresh_lora_packed()
+                self.tuner.refresh_weights()
             self.refresh_launches = L.LAUNCHES - n0
             L.LAUNCHES = n0
             self.refresh_graph = g

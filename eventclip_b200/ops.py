@@ -465,3 +465,41 @@ def gemm_bf16_splitk(A, W, splits=None, out=None, M=None, K=None):
         L.check(lib.ec_gemm_bf16_splitk(_ptr(A), A.stride(0), _ptr(W), W.stride(0), M, N, K, int(splits), _ptr(ws), _ptr(out),
                                         out.stride(0), _stream()), "ec_gemm_bf16_splitk")
     return out
+
+
+def colsum(a, out=None, M=None, n_part=None):
+    """out[c] = sum_r a[r, c] (fp32 result) for a 2-D fp32 / bf16 tensor (row stride may exceed the width)."""
+    if a.dtype not in (torch.float32, torch.bfloat16) or not a.is_cuda or a.stride(1) != 1:
+        raise L.ECError("colsum needs a CUDA fp32 / bf16 matrix with unit column stride")
+    L.require_device(a.device.index)
+    M = a.shape[0] if M is None else M
+    N = a.shape[1]
+    n_part = n_part or max(1, min(512, M // 64))
+    scratch = torch.empty((n_part, N), dtype=torch.float32, device=a.device)
+    if out is None:
+        out = torch.empty(N, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        L.check(L.load().ec_colsum(_ptr(a), int(a.dtype == torch.bfloat16), M, N, a.stride(0), _ptr(scratch), n_part, _ptr(out),
+                                   _stream()), "ec_colsum")
+    return out
+
+
+def layernorm_param_grad(x, dy, M, d, x_stride=None, dgamma=None, dbeta=None, n_part=None):
+    _dev(x, torch.float32, "x")
+    _dev(dy, torch.float32, "dy")
+    n_part = n_part or max(1, min(296, M // 32))
+    scratch = torch.empty((2, n_part, d), dtype=torch.float32, device=x.device)
+    dgamma = torch.empty(d, dtype=torch.float32, device=x.device) if dgamma is None else dgamma
+    dbeta = torch.empty(d, dtype=torch.float32, device=x.device) if dbeta is None else dbeta
+    with torch.cuda.device(x.device):
+        L.check(L.load().ec_layernorm_param_grad(_ptr(x), int(x_stride or d), _ptr(dy), M, d, _ptr(scratch), n_part, _ptr(dgamma),
+                                                 _ptr(dbeta), _stream()), "ec_layernorm_param_grad")
+    return dgamma, dbeta
+
+
+def patch_rows_bf16(x, n_img, G2, d):
+    _dev(x, torch.float32, "x")
+    out = torch.empty((n_img * G2, d), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        L.check(L.load().ec_patch_rows_bf16(_ptr(x), n_img, G2, d, _ptr(out), _stream()), "ec_patch_rows_bf16")
+    return out

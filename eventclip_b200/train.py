@@ -13,9 +13,10 @@ Two ways in:
     `loss.backward(); optimizer.step()` loop works unchanged.
   * `FineTuner`: the fused step `events -> frames -> forward -> loss -> backward -> all-reduce -> Adam` without autograd.
 
-Trainable sets supported: LoRA factors on q/k/v/o (`lora='qv-r' | 'qkv-r' | 'qkvo-r' | int`) and the text features of
-the 'text-identity' adapter -- the configuration shipped for fine-tuning (configs/ftclip/*lora16.py).  Any other
-trainable parameter of model.visual (the only_* switches, full fine-tuning) raises NotImplementedError.
+Trainable sets: whatever clip_cls_ft.py:45-80 leaves with requires_grad -- LoRA factors on q/k/v/o
+(`lora='qv-r' | 'qkv-r' | 'qkvo-r' | int`, configs/ftclip/*lora16.py), the only_conv1 / only_bias / only_ln / only_cls_fc /
+only_cls_token subsets, or the whole image tower (`lora=-1`, configs/ftclip/*vitb16.py) -- plus the text features of
+the 'text-identity' adapter.  Every parameter of model.visual has a gradient kernel path here.
 """
 import torch
 
@@ -24,28 +25,18 @@ from . import _lib as L
 
 
 # ------------------------------------------------------------------------------------------------ trainable set
-def lora_slots(vis):
-    """[(block index, 'q'|'k'|'v'|'o', up Parameter [rows,r], down Parameter [r,d])] in a fixed order, and a check that
-    nothing else in the image tower wants a gradient."""
-    slots, seen = [], set()
-    for i, blk in enumerate(vis.transformer.resblocks):
-        ipw = blk.attn.in_proj_weight
-        if isinstance(ipw, torch.nn.Module):
-            for n in "qkv":
-                up, down = getattr(ipw, f"lora_up_{n}", None), getattr(ipw, f"lora_down_{n}", None)
-                if up is not None and (up.requires_grad or down.requires_grad):
-                    slots.append((i, n, up, down))
-                    seen.update((id(up), id(down)))
-        op = blk.attn.out_proj
-        if hasattr(op, "lora_up") and (op.lora_up.weight.requires_grad or op.lora_down.weight.requires_grad):
-            slots.append((i, "o", op.lora_up.weight, op.lora_down.weight))
-            seen.update((id(op.lora_up.weight), id(op.lora_down.weight)))
-    other = [n for n, p in vis.named_parameters() if p.requires_grad and id(p) not in seen]
-    if other:
-        raise NotImplementedError(
-            "the B200 fine-tune step trains LoRA factors (and the text features); these parameters of model.visual also "
-            f"require gradients and have no backward here: {other[:6]}{' ...' if len(other) > 6 else ''}")
-    return slots
+def trainable_params(vis):
+    """Parameters of the image tower that want a gradient, in named_parameters order: whatever clip_cls_ft.py:45-80 left
+    trainable (LoRA factors, conv1 / bias / LayerNorm / proj / class token subsets, or the whole tower)."""
+    return [p for _, p in vis.named_parameters() if p.requires_grad]
+
+
+def _req(p):
+    return p is not None and p.requires_grad
+
+
+def _block_needs(blk):
+    return any(p.requires_grad for p in blk.parameters())
 
 
 # ------------------------------------------------------------------------------------------------ encoder forward/backward
@@ -63,7 +54,8 @@ def encoder_forward(vis, patches, n_img):
     ops.cls_rows(x0, pk["cls"], pk["pos"], n_img, Ltok, d)
     x = f32(M, d)
     ops.layernorm(x0, *pk["ln_pre"], M, d, out_f32=x)
-    del x0
+    bottom = any(_req(p) for p in (vis.conv1.weight, vis.class_embedding, vis.positional_embedding, vis.ln_pre.weight,
+                                   vis.ln_pre.bias))
     saved = []
     for b in pk["blocks"]:
         h1, qkv, att = bf(M, d), bf(M, 3 * d), bf(M, d)
@@ -81,63 +73,143 @@ def encoder_forward(vis, patches, n_img):
         saved.append((x, h1, qkv, att, x2, h2, a, g))
         x = x3
     cls = bf(n_img, d)
-    ops.layernorm(x, *pk["ln_post"], n_img, d, row_stride=Ltok * d, out_bf16=cls)
+    cls32 = f32(n_img, d) if _req(vis.proj) else None
+    ops.layernorm(x, *pk["ln_post"], n_img, d, row_stride=Ltok * d, out_bf16=cls, out_f32=cls32)
     feats = ops.gemm_bf16(cls, pk["proj"], None, "f32")
-    return feats, dict(pk=pk, saved=saved, x_last=x, n_img=n_img, Ltok=Ltok, d=d, heads=heads)
+    return feats, dict(pk=pk, saved=saved, x_last=x, cls=cls, cls32=cls32, n_img=n_img, Ltok=Ltok, d=d, heads=heads,
+                       x0=x0 if bottom else None, patches=patches if _req(vis.conv1.weight) else None)
 
 
-def encoder_backward(vis, ctx, d_feats, slots, dest=None):
-    """d_feats fp32 [n_img, C] -> {(block, name): (d_up, d_down)} for the LoRA slots.  Frees ctx['saved'] as it goes.
-    dest(param) may return the tensor a gradient is to be written into (FineTuner's flat buffer views)."""
+def encoder_backward(vis, ctx, d_feats, dest=None):
+    """d_feats fp32 [n_img, C] -> {id(param): fp32 gradient} for every trainable parameter of the image tower.
+    dest(param) may return the tensor a gradient is to be written into (FineTuner's flat-buffer views).
+    Frees ctx['saved'] as it goes; stops at the lowest block that has anything trainable."""
     pk, saved = ctx["pk"], ctx["saved"]
     n_img, Ltok, d, heads = ctx["n_img"], ctx["Ltok"], ctx["d"], ctx["heads"]
+    G2 = Ltok - 1
     M, dev = n_img * Ltok, d_feats.device
-    want = {}
-    for i, n, up, down in slots:
-        want.setdefault(i, {})[n] = (up, down)
-    first = min(want) if want else len(saved)
+    blocks = list(vis.transformer.resblocks)
+    bottom = ctx["x0"] is not None
+    first = 0 if bottom else next((i for i, blk in enumerate(blocks) if _block_needs(blk)), len(blocks))
     grads = {}
     f32w = lambda t: t.detach().to(torch.float32).contiguous()
     to = (lambda p: None) if dest is None else dest
 
-    def factor_grads(dW, rows, names, i, w):      # dUp = dW . down^T,  dDown = up^T . dW   (W_eff = W + up . down)
-        fac = [(f32w(w[n][0]), f32w(w[n][1])) if n in w else None for n in names]
-        dst = [(to(w[n][0]), to(w[n][1])) if n in w else None for n in names]
-        for n, g in zip(names, ops.lora_grad(dW, rows, fac, dst)):
+    def wgrad(p, dy_bf16, x_bf16):                 # dW[out, in] = dY^T X over the token dimension (split-K tcgen05 GEMM)
+        out = to(p)
+        view = None if out is None else out.view(p.shape[0], -1)
+        g = ops.gemm_bf16_splitk(ops.transpose_bf16(dy_bf16), ops.transpose_bf16(x_bf16), out=view)
+        grads[id(p)] = g.view(p.shape)
+        return g
+
+    def bgrad(p, dy):                              # bias gradient: column sums over the tokens
+        grads[id(p)] = ops.colsum(dy, out=to(p))
+
+    def lngrad(ln, xin, dy, Mrows, x_stride=None):
+        if _req(ln.weight) or _req(ln.bias):
+            dg, db = ops.layernorm_param_grad(xin, dy, Mrows, d, x_stride=x_stride,
+                                              dgamma=to(ln.weight) if _req(ln.weight) else None,
+                                              dbeta=to(ln.bias) if _req(ln.bias) else None)
+            if _req(ln.weight):
+                grads[id(ln.weight)] = dg
+            if _req(ln.bias):
+                grads[id(ln.bias)] = db
+
+    def factor_grads(dW, names, facs):             # dUp = dW . down^T,  dDown = up^T . dW   (W_eff = W + up . down)
+        fac = [(f32w(f[0]), f32w(f[1])) if f is not None else None for f in facs]
+        dst = [(to(f[0]), to(f[1])) if f is not None else None for f in facs]
+        for f, g in zip(facs, ops.lora_grad(dW, d, fac, dst)):
             if g is not None:
-                grads[(i, n)] = g
+                grads[id(f[0])], grads[id(f[1])] = g
 
     # feats = ln_post(x[cls rows]) @ proj
-    d_cls = ops.gemm_bf16(ops.f32_to_bf16(d_feats.contiguous()), pk["proj_t"], None, "f32")       # [n_img, d]
+    dfb = ops.f32_to_bf16(d_feats.contiguous())
+    if _req(vis.proj):                             # d_proj[d, C] = cls^T d_feats (n_img rows: tiny, fp32 SIMT)
+        grads[id(vis.proj)] = ops.mm_f32(ctx["cls32"], d_feats.contiguous(), trans_a=True, out=to(vis.proj))
+    d_cls = ops.gemm_bf16(dfb, pk["proj_t"], None, "f32")                       # [n_img, d]
+    lngrad(vis.ln_post, ctx["x_last"], d_cls, n_img, x_stride=Ltok * d)
     dx = torch.zeros((M, d), dtype=torch.float32, device=dev)
     ops.layernorm_bwd(ctx["x_last"], d_cls, pk["ln_post"][0], n_img, d, x_stride=Ltok * d, dx=dx, dx_stride=Ltok * d)
     for i in range(len(saved) - 1, first - 1, -1):
-        b = pk["blocks"][i]
+        b, blk = pk["blocks"][i], blocks[i]
         x, h1, qkv, att, x2, h2, a, g = saved[i]
         saved[i] = None
+        W, lora_in, ib, oW, ob, lora_out = _attn_parts(blk.attn)
+        fc, pj = blk.mlp.c_fc, blk.mlp.c_proj
         # MLP:  x3 = x2 + c_proj(QuickGELU(c_fc(ln_2(x2))))
         dxb = ops.f32_to_bf16(dx)
+        if _req(pj.weight):
+            wgrad(pj.weight, dxb, g)
+        if _req(pj.bias):
+            bgrad(pj.bias, dx)
         dg = ops.gemm_bf16(dxb, b["w_proj_t"], None, "bf16")                 # [M, 4d]
         da = ops.quickgelu_bwd(a, dg, out=dg)
+        if _req(fc.weight):
+            wgrad(fc.weight, da, h2)
+        if _req(fc.bias):
+            bgrad(fc.bias, da)
         dh2 = ops.gemm_bf16(da, b["w_fc_t"], None, "f32")                    # [M, d]
+        lngrad(blk.ln_2, x2, dh2, M)
         dx2 = ops.layernorm_bwd(x2, dh2, b["ln2"][0], M, d, acc=dx)
         del dg, da, dh2, a, g, h2
         # attention:  x2 = x + out_proj(attn(in_proj(ln_1(x))))
         dx2b = ops.f32_to_bf16(dx2, dst=dxb)
         d_att = ops.gemm_bf16(dx2b, b["w_out_t"], None, "bf16")              # [M, d]
-        w = want.get(i, {})
-        if "o" in w:
+        if _req(ob):
+            bgrad(ob, dx2)
+        if _req(oW):
+            wgrad(oW, dx2b, att)
+        elif lora_out is not None and (_req(lora_out.lora_up.weight) or _req(lora_out.lora_down.weight)):
             dW = ops.gemm_bf16_splitk(ops.transpose_bf16(dx2b), ops.transpose_bf16(att))            # [d_out, d_in]
-            factor_grads(dW, d, "o", i, w)
+            factor_grads(dW, "o", [(lora_out.lora_up.weight, lora_out.lora_down.weight)])
         dqkv = ops.attention_bwd(qkv, att, d_att, n_img, Ltok, heads)
-        if any(n in w for n in "qkv"):
+        if _req(ib):
+            bgrad(ib, dqkv)
+        facs = None
+        if lora_in is not None:
+            facs = [(getattr(lora_in, f"lora_up_{n}"), getattr(lora_in, f"lora_down_{n}"))
+                    if hasattr(lora_in, f"lora_up_{n}") and (_req(getattr(lora_in, f"lora_up_{n}")) or
+                                                             _req(getattr(lora_in, f"lora_down_{n}"))) else None for n in "qkv"]
+        if _req(W):
+            wgrad(W, dqkv, h1)
+        elif facs is not None and any(f is not None for f in facs):
             dW = ops.gemm_bf16_splitk(ops.transpose_bf16(dqkv), ops.transpose_bf16(h1))             # [3d, d]
-            factor_grads(dW, d, "qkv", i, w)
-        if i > first:                                                        # nothing trainable below the first LoRA block
+            factor_grads(dW, "qkv", facs)
+        need_ln1 = _req(blk.ln_1.weight) or _req(blk.ln_1.bias)
+        if i > first or bottom or need_ln1:
             dh1 = ops.gemm_bf16(dqkv, b["w_in_t"], None, "f32")
-            dx = ops.layernorm_bwd(x, dh1, b["ln1"][0], M, d, acc=dx2)
+            lngrad(blk.ln_1, x, dh1, M)
+            if i > first or bottom:                                          # nothing trainable below the first block otherwise
+                dx = ops.layernorm_bwd(x, dh1, b["ln1"][0], M, d, acc=dx2)
     ctx["saved"] = None
+    if bottom:
+        # x = ln_pre(x0),  x0[img, 0] = class_embedding + pos[0],  x0[img, 1 + t] = conv1(patch t) + pos[1 + t]
+        x0 = ctx["x0"]
+        lngrad(vis.ln_pre, x0, dx, M)
+        dx0 = ops.layernorm_bwd(x0, dx, pk["ln_pre"][0], M, d)
+        if _req(vis.positional_embedding) or _req(vis.class_embedding):
+            dpos = ops.colsum(dx0.view(n_img, Ltok * d), out=to(vis.positional_embedding).view(-1)
+                              if _req(vis.positional_embedding) and to(vis.positional_embedding) is not None else None,
+                              n_part=1 if n_img < 128 else None).view(Ltok, d)
+            if _req(vis.positional_embedding):
+                grads[id(vis.positional_embedding)] = dpos
+            if _req(vis.class_embedding):          # the class token sits in row 0 of every image next to pos[0]
+                dst = to(vis.class_embedding)
+                grads[id(vis.class_embedding)] = dpos[0].clone() if dst is None else dst.copy_(dpos[0])
+        if _req(vis.conv1.weight):                 # conv1 as a GEMM over im2col rows: dW[d, 3PP] = d_x0[patch rows]^T patches
+            w = vis.conv1.weight
+            kp, k = vis.k_patch, 3 * vis.patch_size ** 2
+            dyp = ops.patch_rows_bf16(dx0, n_img, G2, d)
+            gw = ops.gemm_bf16_splitk(ops.transpose_bf16(dyp), ops.transpose_bf16(ctx["patches"]))   # [d, k_patch]
+            gw = gw[:, :k].reshape(w.shape)
+            dst = to(w)
+            grads[id(w)] = gw.contiguous() if dst is None else dst.copy_(gw)
     return grads
+
+
+def _attn_parts(attn):
+    from .clip import _attn_weights
+    return _attn_weights(attn)
 
 
 # ------------------------------------------------------------------------------------------------ logit head
@@ -180,29 +252,22 @@ def add_slot_of_row(plan, dev):
 
 # ------------------------------------------------------------------------------------------------ autograd plumbing
 class _EncoderFn(torch.autograd.Function):
-    """autograd node whose backward is encoder_backward; inputs after `n_img` are the LoRA factors (up, down, up, ...)."""
+    """autograd node whose backward is encoder_backward; inputs after `n_img` are the trainable parameters of the tower."""
 
     @staticmethod
-    def forward(fctx, vis, patches, n_img, *factors):
+    def forward(fctx, vis, patches, n_img, *params):
         feats, ctx = encoder_forward(vis, patches, n_img)
-        fctx.vis, fctx.ctx = vis, ctx
+        fctx.vis, fctx.ctx, fctx.params = vis, ctx, params
         return feats
 
     @staticmethod
     def backward(fctx, d_feats):
-        slots = lora_slots(fctx.vis)
-        grads = encoder_backward(fctx.vis, fctx.ctx, d_feats.contiguous(), slots)
-        flat = []
-        for i, n, up, down in slots:
-            du, dd = grads[(i, n)]
-            flat += [du.to(up.dtype) if up.requires_grad else None, dd.to(down.dtype) if down.requires_grad else None]
-        return (None, None, None, *flat)
+        grads = encoder_backward(fctx.vis, fctx.ctx, d_feats.contiguous())
+        return (None, None, None, *[grads[id(p)].to(p.dtype).reshape(p.shape) for p in fctx.params])
 
 
 def encode_patches_autograd(vis, patches, n_img):
-    slots = lora_slots(vis)
-    factors = [p for _, _, up, down in slots for p in (up, down)]
-    return _EncoderFn.apply(vis, patches, n_img, *factors)
+    return _EncoderFn.apply(vis, patches, n_img, *trainable_params(vis))
 
 
 class _HeadFn(torch.autograd.Function):
@@ -275,12 +340,13 @@ class FineTuner:
         if not getattr(model, "prompt_tuning", False):
             raise NotImplementedError("FineTuner expects the 'text-identity' adapter (prompt-tuned text features)")
         self.model, self.vis = model, model.model.visual
-        self.slots = lora_slots(self.vis)
         self.lr, self.clip_lr = lr, (lr if clip_lr is None else clip_lr)
         self.betas, self.eps, self.pg = betas, eps, process_group
-        # group 0: outside model.visual (text features), group 1: LoRA factors -- each one contiguous span of the flat buffers
+        # group 0: outside model.visual (text features), group 1: trainable parameters of the image tower -- each group is
+        # one contiguous span of the flat buffers
         self.group0 = [model.text_feats]
-        self.group1 = [p for _, _, up, down in self.slots for p in (up, down)]
+        self.group1 = trainable_params(self.vis)
+
         from .dist import FlatParams
         self.flat = FlatParams([self.group0, self.group1])
         self.flat_p, self.flat_g = self.flat.flat_p, self.flat.flat_g
@@ -311,7 +377,7 @@ class FineTuner:
             out, hctx = head_forward(feats, plan, model.text_feats.detach(), model.logit_scale, model.agg_func)
             _, loss, d_full = ops.ce_loss_bwd(out["full_logits"], plan["valid_u8"], labels, model.agg_func)
             d_feats, d_text = head_backward(hctx, d_full)
-            encoder_backward(self.vis, ctx, d_feats, self.slots, dest=self.flat.grad_view)
+            encoder_backward(self.vis, ctx, d_feats, dest=self.flat.grad_view)
             self._grad_view(model.text_feats).copy_(d_text)
         self.last = {"out": out, "status": st}
         return loss
@@ -327,7 +393,11 @@ class FineTuner:
             if hi > lo:
                 ops.adam(self.flat_p[lo:hi], self.flat_g[lo:hi], self.m[lo:hi], self.v[lo:hi], rate, self.t, self.betas, self.eps)
         if refresh:
-            self.vis.refresh_lora_packed()    # re-merge W + up.down into the packed bf16 weights (and their transposes)
+            self.refresh_weights()
+
+    def refresh_weights(self):
+        """bf16 GEMM copies of the updated master weights, rewritten in place (pointer-stable, graph-capturable)."""
+        self.vis.refresh_packed()
 
     def step(self, events, offsets, labels, sel=None, lr=None, clip_lr=None):
         loss = self.forward_backward(events, offsets, labels, sel)

@@ -240,6 +240,19 @@ EC_API int ec_gemm_f32_strided(const float *A, int64_t sam, int64_t sak, const f
 EC_API int ec_lora_grad(const float *dW, int64_t ld, int n_mat, int rows, int d, int r, const float *const *up,
                         const float *const *down, float *const *d_up, float *const *d_down, void *stream);
 
+/* Column sums over the token dimension: out[c] = sum_r a[r, c] for a fp32 or bf16 matrix [M, ld] (bias gradients of the
+ * nn.Linear layers, positional / class embedding gradients).  Two deterministic stages; scratch fp32 [n_part * N]. */
+EC_API int ec_colsum(const void *a, int is_bf16, int M, int N, int64_t ld, float *scratch, int n_part, float *out, void *stream);
+
+/* LayerNorm affine gradients: dgamma[c] = sum_r dy[r,c] * xhat[r,c], dbeta[c] = sum_r dy[r,c]; x fp32 rows of stride x_stride
+ * (the LayerNorm INPUT, statistics recomputed), dy fp32 [M,d]; scratch fp32 [2 * n_part * d]. */
+EC_API int ec_layernorm_param_grad(const float *x, int64_t x_stride, const float *dy, int M, int d, float *scratch, int n_part,
+                                   float *dgamma, float *dbeta, void *stream);
+
+/* dst bf16 [n_img*G2, d] = the patch-token rows of the fp32 token matrix src [n_img*(G2+1), d] (class-token rows skipped):
+ * the A operand of conv1's weight gradient. */
+EC_API int ec_patch_rows_bf16(const float *src, int n_img, int G2, int d, void *dst, void *stream);
+
 /* Backward of F.normalize(x, p=2, dim=-1) followed by the valid-mask multiply (clip_cls_ft.py:229-232; text features
  * :163): dx = (dy - y<y,dy>) / max(|x|, 1e-12); rows with mask == 0 get dx = 0.  mask nullable. */
 EC_API int ec_l2norm_rows_bwd(const float *x, const float *dy, const uint8_t *mask, int M, int C, float *dx, void *stream);

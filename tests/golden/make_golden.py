@@ -270,10 +270,16 @@ def make_ft_train():
     names = [f"class_{i}" for i in range(n_cls)]
     labels = torch.tensor([3, 0, 10, 7, 7, 1])
     out = {"labels": labels.numpy()}
-    for agg in ("mean", "sum"):
+    cases = [("mean", "mean", dict(lora="qkvo-4", only_conv1=False, only_bias=False, only_ln=False), True),
+             ("sum", "sum", dict(lora="qkvo-4", only_conv1=False, only_bias=False, only_ln=False), True),
+             # clip_cls_ft.py:78-80: no LoRA and no only_* switch = the whole image tower trains (configs/ftclip/*vitb16.py)
+             ("full", "mean", dict(lora=-1, only_conv1=False, only_bias=False, only_ln=False), False),
+             # clip_cls_ft.py:58-77: the union of the only_* subsets
+             ("subset", "mean", dict(lora=-1, only_conv1=True, only_bias=True, only_ln=True, only_cls_fc=True,
+                                     only_cls_token=True), False)]
+    for tag, agg, flags, with_step in cases:
         clipm = clip_oracle.build_clip(arch, seed=3)
-        cd = dict(clip_model=clipm, prompt="a {}", class_names=names, agg_func=agg, lora="qkvo-4", only_conv1=False,
-                  only_bias=False, only_ln=False)
+        cd = dict(clip_model=clipm, prompt="a {}", class_names=names, agg_func=agg, **flags)
         origf = rm.FTCLIPClassifier._build_prompts
 
         def seededf(self, adapter_type, _t=torch.from_numpy(G["text"])):
@@ -287,6 +293,8 @@ def make_ft_train():
         finally:
             rm.FTCLIPClassifier._build_prompts = origf
         sd = {k[len("ft_lora_sd_"):]: torch.from_numpy(G[k]) for k in G.files if k.startswith("ft_lora_sd_")}
+        if flags["lora"] == -1:
+            sd = {"text_feats": sd["text_feats"]}      # same prompt-tuned text features, plain (un-injected) tower
         m.load_state_dict(sd, strict=False)      # the reference's override returns nothing
         for k, v in sd.items():
             assert torch.equal(m.state_dict()[k], v), k
@@ -295,18 +303,19 @@ def make_ft_train():
         o = m(data)
         loss = m.calc_train_loss(data, o)["ce_loss"]
         loss.backward()
-        out[f"{agg}_loss"] = np.float32(loss.item())
-        out[f"{agg}_logits"] = o["logits"].detach().numpy()
+        out[f"{tag}_loss"] = np.float32(loss.item())
+        out[f"{tag}_logits"] = o["logits"].detach().numpy()
         named = [(n, p) for n, p in m.named_parameters() if p.requires_grad]
         for n, p in named:
-            out[f"{agg}_grad_{n}"] = p.grad.numpy().copy()
-        # method.py:165-182: parameters outside model.visual get `lr`, those inside get `clip_lr`
-        opt = torch.optim.Adam([{"params": [p for n, p in named if "model.visual" not in n], "lr": 1e-3},
-                                {"params": [p for n, p in named if "model.visual" in n], "lr": 5e-4}])
-        opt.step()
-        for n, p in named:
-            out[f"{agg}_step1_{n}"] = p.detach().numpy().copy()
-        print("ft_train", agg, "loss", loss.item(), "trainable", len(named), sum(p.numel() for _, p in named))
+            out[f"{tag}_grad_{n}"] = p.grad.numpy().copy()
+        if with_step:
+            # method.py:165-182: parameters outside model.visual get `lr`, those inside get `clip_lr`
+            opt = torch.optim.Adam([{"params": [p for n, p in named if "model.visual" not in n], "lr": 1e-3},
+                                    {"params": [p for n, p in named if "model.visual" in n], "lr": 5e-4}])
+            opt.step()
+            for n, p in named:
+                out[f"{tag}_step1_{n}"] = p.detach().numpy().copy()
+        print("ft_train", tag, "loss", loss.item(), "trainable", len(named), sum(p.numel() for _, p in named))
     np.savez_compressed(os.path.join(HERE, "ft_train_golden.npz"), **out)
 
 

@@ -111,3 +111,26 @@ def test_fine_tune_step_gradients(G, golden_dir, agg):
     for key, (up, down) in lora.items():
         assert _close(up.grad, T[f"{agg}_grad_{names[key][0]}"], 1e-4), key
         assert _close(down.grad, T[f"{agg}_grad_{names[key][1]}"], 1e-4), key
+
+
+@pytest.mark.parametrize("tag", ["full", "subset"])
+def test_fine_tune_step_gradients_whole_tower(G, golden_dir, tag):
+    """Same for the non-LoRA trainable sets of clip_cls_ft.py:45-80: the whole tower ('full') and the union of the only_*
+    switches ('subset': conv1, biases, LayerNorms, proj, class token)."""
+    T = np.load(os.path.join(golden_dir, "ft_train_golden.npz"))
+    valid = torch.from_numpy(G["valid"])
+    g = torch.Generator().manual_seed(77)
+    imgs = torch.randn(6, 4, 3, 224, 224, generator=g) * valid[:, :, None, None, None].float()
+    clip = clip_oracle.build_clip(ARCH, seed=3)
+    names = [k[len(tag) + 6 + len("model.visual."):] for k in T.files if k.startswith(f"{tag}_grad_model.visual.")]
+    params = dict(clip.visual.named_parameters())
+    for n, p in params.items():
+        p.requires_grad_(n in names)
+    text = torch.from_numpy(G["ft_lora_sd_text_feats"]).clone().requires_grad_(True)
+    loss, o = heads_oracle.ft_train_loss(clip.visual, {}, imgs[valid], valid, text, torch.from_numpy(T["labels"]), 100.0, "mean")
+    loss.backward()
+    assert abs(loss.item() - float(T[f"{tag}_loss"])) < 1e-4 * float(T[f"{tag}_loss"])
+    assert _close(text.grad, T[f"{tag}_grad_text_feats"], 1e-4)
+    assert len(names) == (32 if tag == "full" else 23)
+    for n in names:
+        assert _close(params[n].grad, T[f"{tag}_grad_model.visual.{n}"], 2e-4), n

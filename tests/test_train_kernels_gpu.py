@@ -167,3 +167,33 @@ def test_gemm_splitk(cuda_dev, M, N, K, splits):
     assert rel(out, ref) < 2e-3
     again = ops.gemm_bf16_splitk(A.to(cuda_dev), W.to(cuda_dev), splits=splits)
     assert torch.equal(out, again)            # deterministic
+
+
+@pytest.mark.parametrize("M,N,dtype", [(12608, 768, torch.bfloat16), (197, 2304, torch.float32), (6, 50 * 128, torch.float32),
+                                       (1000, 40, torch.bfloat16)])
+def test_colsum(cuda_dev, M, N, dtype):
+    a = torch.randn(M, N).to(dtype)
+    out = ops.colsum(a.to(cuda_dev))
+    assert rel(out, a.double().sum(0)) < 1e-5
+    assert torch.equal(out, ops.colsum(a.to(cuda_dev)))           # deterministic
+
+
+@pytest.mark.parametrize("M,d,stride", [(1000, 768, None), (37, 128, None), (5, 1024, 3 * 1024)])
+def test_layernorm_param_grad(cuda_dev, M, d, stride):
+    g = torch.Generator().manual_seed(M + d)
+    rows = stride // d if stride else 1
+    xfull = torch.randn(M * rows, d, generator=g) * 2 + 0.5
+    x = xfull.view(M, rows * d)[:, :d].clone()
+    gamma, beta = torch.randn(d, generator=g).requires_grad_(True), torch.randn(d, generator=g).requires_grad_(True)
+    dy = torch.randn(M, d, generator=g)
+    F.layer_norm(x, (d,), gamma, beta).backward(dy)
+    dg, db = ops.layernorm_param_grad(xfull.to(cuda_dev), dy.to(cuda_dev), M, d, x_stride=stride)
+    assert rel(dg, gamma.grad) < 1e-5 and rel(db, beta.grad) < 1e-5
+
+
+def test_patch_rows_bf16(cuda_dev):
+    n_img, G2, d = 3, 49, 128
+    x = torch.randn(n_img * (G2 + 1), d)
+    out = ops.patch_rows_bf16(x.to(cuda_dev), n_img, G2, d).cpu()
+    ref = x.view(n_img, G2 + 1, d)[:, 1:].reshape(n_img * G2, d).to(torch.bfloat16)
+    assert torch.equal(out, ref)
