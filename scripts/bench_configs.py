@@ -119,6 +119,8 @@ if __name__ == "__main__":
         sys.exit(0)
     if "--finetune" in sys.argv:
         res = [run_finetune("C5 LoRA qkvo-16 fine-tune step ViT-B/16 N-Caltech101 (32 samples x 2 views)", "n_caltech101", "ViT-B/16", 32),
+               run_finetune("full fine-tune step ViT-B/16 N-Caltech101 (lora=-1, configs/ftclip/*ncaltech*vitb16.py, 32 x 2 views)",
+                            "n_caltech101", "ViT-B/16", 32, lora=-1),
                run_finetune("C5 at batch 128 (the 4-GPU global batch of configs/ftclip on one GPU)", "n_caltech101", "ViT-B/16", 128),
                run_finetune("LoRA qkvo-16 fine-tune step ViT-L/14 N-ImageNet (32 samples x 2 views, configs/ftclip/*lora16.py)", "n_imagenet", "ViT-L/14", 32)]
         json.dump(res, open("gpurun_out/bench_finetune.json", "w"), indent=1)
