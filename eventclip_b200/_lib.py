@@ -57,6 +57,7 @@ SIGNATURES = {
     "ec_l2norm_rows": ([_vp, _vp, _i, _i, _vp], _i),
     # fine-tune step
     "ec_gemm_splitk_choose": ([_i, _i, _i], _i),
+    "ec_gemm_bf16_tn_splitk": ([_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp], _i),
     "ec_gemm_bf16_splitk": ([_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp], _i),
     "ec_layernorm_bwd": ([_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _vp, _i64, _vp], _i),
     "ec_quickgelu": ([_vp, _vp, _i64, _vp], _i),

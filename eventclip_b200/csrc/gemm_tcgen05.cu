@@ -48,6 +48,8 @@ struct GemmParams {
     uint32_t tx_bytes;    // bytes landing per stage (A box + W box)
     int splits;           // split-K (EC_EPI_F32 only): tile index = split * tiles_m * tiles_n + tile; partial sums go to
     int kb_per_split;     //   out + split * M * ldo, each covering kb_per_split 64-wide K blocks
+    int mn_major;         // 1: operands are [K, M] / [K, N] row-major (reduction index = row): MN-major UMMA operands, tiles
+                          //    arrive as boxes of 64 (m or n) x 64 (k), one 8 KB box per 64 rows of the tile
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -153,6 +155,19 @@ __device__ __forceinline__ bool elect_one()
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// MN-major operand tile, SWIZZLE_128B: one box = 64 k-rows of 128 bytes (64 m/n elements); 8-row groups 1024 bytes apart
+// along K (SBO), consecutive 64-element m/n atoms one box = 8192 bytes apart (LBO).
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)(8192 >> 4) << 16;        // leading byte offset: next 64-wide atom along M / N
+    d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset: next 8 rows along K
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 
 // K-major operand tile, SWIZZLE_128B: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), descriptor version 1.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr)
@@ -323,7 +338,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char *sa = smem + stage * STAGE_BYTES;
                     unsigned char *sb = sa + A_BYTES;
-                    if (elect_one()) {
+                    if (p.mn_major) {
+                        // [K, M] / [K, N] operands: inner coordinate = m / n, outer = k; one 64 x 64 box per 64 rows of the tile
+                        if (elect_one()) {
+                            const int m0 = (tm * CG + (int)cta_rank) * BM, n0 = tn * BN + (int)cta_rank * (BN / CG);
+                            if (CG == 2) {
+                                if (leader) mbar_expect_tx(&full_bar[stage], p.tx_bytes);
+#pragma unroll
+                                for (int i = 0; i < BM / 64; ++i) tma_load_2d_2sm(sa + i * 8192, &map_a, &full_bar[stage], m0 + 64 * i, kb * BK);
+#pragma unroll
+                                for (int i = 0; i < BN / CG / 64; ++i) tma_load_2d_2sm(sb + i * 8192, &map_w, &full_bar[stage], n0 + 64 * i, kb * BK);
+                            } else {
+                                mbar_expect_tx(&full_bar[stage], p.tx_bytes);
+#pragma unroll
+                                for (int i = 0; i < BM / 64; ++i) tma_load_2d(sa + i * 8192, &map_a, &full_bar[stage], m0 + 64 * i, kb * BK);
+#pragma unroll
+                                for (int i = 0; i < BN / 64; ++i) tma_load_2d(sb + i * 8192, &map_w, &full_bar[stage], n0 + 64 * i, kb * BK);
+                            }
+                        }
+                    } else if (elect_one()) {
                         if (CG == 2) {
                             // both CTAs load their halves; all bytes are credited to the leader's barrier
                             if (leader) mbar_expect_tx(&full_bar[stage], p.tx_bytes);
@@ -354,14 +387,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint64_t adesc = make_smem_desc(sa);
-                    const uint64_t bdesc = make_smem_desc(sa + A_BYTES);
+                    const uint64_t adesc = p.mn_major ? make_smem_desc_mn(sa) : make_smem_desc(sa);
+                    const uint64_t bdesc = p.mn_major ? make_smem_desc_mn(sa + A_BYTES) : make_smem_desc(sa + A_BYTES);
+                    // K-major: 16 elements = 32 bytes along K inside the swizzle atom (+2 in 16-byte units);
+                    // MN-major: 16 k-rows of 128 bytes = 2048 bytes (+128)
+                    const uint64_t kstep = p.mn_major ? 128 : 2;
+                    const uint32_t idesc = p.mn_major ? (IDESC | (1u << 15) | (1u << 16)) : IDESC;
                     if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k) {
-                            // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
-                            if (CG == 2) umma_bf16_2sm(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, ((kb - kb0) | k) != 0);
-                            else umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, ((kb - kb0) | k) != 0);
+                            if (CG == 2) umma_bf16_2sm(tmem_d, adesc + kstep * k, bdesc + kstep * k, idesc, ((kb - kb0) | k) != 0);
+                            else umma_bf16(tmem_d, adesc + kstep * k, bdesc + kstep * k, idesc, ((kb - kb0) | k) != 0);
                         }
                         // smem slot reusable / accumulator readable once these MMAs retire (in both CTAs of a pair)
                         if (CG == 2) {
@@ -759,7 +795,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float4 *__rest
 }
 
 int gemm_impl(const void *A, int lda, const void *W, int ldw, const float *bias, int M, int N, int K, int epi, void *out, int ldo,
-              const float *res, int row_map, int splits, cudaStream_t stream);
+              const float *res, int row_map, int splits, cudaStream_t stream, int mn_major = 0);
 
 }  // namespace
 
@@ -803,15 +839,42 @@ extern "C" int ec_gemm_bf16_splitk(const void *A, int lda, const void *W, int ld
     return EC_OK;
 }
 
+extern "C" int ec_gemm_bf16_tn_splitk(const void *A, int lda, const void *B, int ldb, int M, int N, int K, int splits,
+                                      float *workspace, float *out, int ldo, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    EC_REQUIRE(splits >= 1 && splits <= 64, "ec_gemm_bf16_tn_splitk: splits must be in [1, 64] (got %d)", splits);
+    EC_REQUIRE(K >= BK, "ec_gemm_bf16_tn_splitk: needs at least 64 rows (tokens), got %d", K);
+    {
+        const int num_kb = (K + BK - 1) / BK, per = (num_kb + splits - 1) / splits;
+        splits = (num_kb + per - 1) / per;
+    }
+    if (splits == 1) return gemm_impl(A, lda, B, ldb, nullptr, M, N, K, EC_EPI_F32, out, ldo, nullptr, 0, 1, stream, 1);
+    EC_REQUIRE(workspace && out && ldo % 4 == 0 && N % 8 == 0 && ((uintptr_t)workspace & 15) == 0 && ((uintptr_t)out & 15) == 0,
+               "ec_gemm_bf16_tn_splitk: needs a 16-byte aligned workspace of splits*M*N floats and ldo %% 4 == 0");
+    int rc = gemm_impl(A, lda, B, ldb, nullptr, M, N, K, EC_EPI_F32, workspace, N, nullptr, 0, splits, stream, 1);
+    if (rc != EC_OK) return rc;
+    const int64_t mn4 = (int64_t)M * N / 4;
+    const int blocks = (int)((mn4 + 255) / 256 < 148 * 8 ? (mn4 + 255) / 256 : 148 * 8);
+    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>((const float4 *)workspace, splits, mn4, N / 4, ldo / 4, (float4 *)out);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
 namespace {
 
 int gemm_impl(const void *A, int lda, const void *W, int ldw, const float *bias, int M, int N, int K, int epi, void *out, int ldo,
-              const float *res, int row_map, int splits, cudaStream_t stream)
+              const float *res, int row_map, int splits, cudaStream_t stream, int mn_major)
 {
     EC_REQUIRE(A && W && out, "ec_gemm_bf16: null pointer");
     EC_REQUIRE(M > 0 && N > 0 && K >= BK, "ec_gemm_bf16: need M,N > 0 and K >= 64 (got %d,%d,%d)", M, N, K);
-    EC_REQUIRE(N % 8 == 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= K,
-               "ec_gemm_bf16: N, K, lda, ldw must be multiples of 8 (N=%d K=%d lda=%d ldw=%d)", N, K, lda, ldw);
+    if (mn_major)
+        EC_REQUIRE(M % 8 == 0 && N % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && lda >= M && ldw >= N && epi == EC_EPI_F32 && !bias,
+                   "ec_gemm (token-major operands): M, N, lda, ldw must be multiples of 8, plain fp32 epilogue (M=%d N=%d lda=%d ldw=%d)",
+                   M, N, lda, ldw);
+    else
+        EC_REQUIRE(N % 8 == 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= K,
+                   "ec_gemm_bf16: N, K, lda, ldw must be multiples of 8 (N=%d K=%d lda=%d ldw=%d)", N, K, lda, ldw);
     EC_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)out & 15) == 0,
                "ec_gemm_bf16: pointers must be 16-byte aligned");
     EC_REQUIRE(epi >= EC_EPI_BF16 && epi <= EC_EPI_PATCH, "ec_gemm_bf16: bad epilogue %d", epi);
@@ -823,16 +886,29 @@ int gemm_impl(const void *A, int lda, const void *W, int ldw, const float *bias,
     // CTA pairs (cta_group::2, 256 x 256 tiles) whenever the shape fills them; EC_GEMM_CG=1 forces the single-CTA kernel
     static const int force_cg = getenv("EC_GEMM_CG") ? atoi(getenv("EC_GEMM_CG")) : 0;
     const int CG = (force_cg == 1 || BN != 256 || M < 2 * BM) ? 1 : 2;
-    const int box_a = M < BM ? M : BM;
-    const int box_w = CG == 2 ? BN / 2 : (N < BN ? N : BN);
+    int box_a = M < BM ? M : BM;
+    int box_w = CG == 2 ? BN / 2 : (N < BN ? N : BN);
     CUtensorMap ma, mw;
-    int rc = make_map(&ma, A, M, K, lda, box_a);
-    if (rc != EC_OK) return rc;
-    rc = make_map(&mw, W, N, K, ldw, box_w);
-    if (rc != EC_OK) return rc;
+    int rc;
+    if (mn_major) {
+        // operands [K, M] and [K, N] row-major: 64 (m / n, inner, 128 bytes) x 64 (k) boxes; full tiles are always
+        // transferred (out-of-range rows and columns arrive as zeros)
+        rc = make_map(&ma, A, K, M, lda, BK);
+        if (rc != EC_OK) return rc;
+        rc = make_map(&mw, W, K, N, ldw, BK);
+        if (rc != EC_OK) return rc;
+        box_a = BM;
+        box_w = BN / CG;
+    } else {
+        rc = make_map(&ma, A, M, K, lda, box_a);
+        if (rc != EC_OK) return rc;
+        rc = make_map(&mw, W, N, K, ldw, box_w);
+        if (rc != EC_OK) return rc;
+    }
 
     GemmParams p;
     p.M = M; p.N = N; p.K = K; p.epi = epi; p.out = out; p.ldo = ldo; p.bias = bias; p.res = res; p.row_map = row_map;
+    p.mn_major = mn_major;
     p.tx_bytes = (uint32_t)(box_a + box_w) * BK * 2 * CG;   // a pair's leader barrier collects both CTAs' bytes
     {
         const int num_kb = (K + BK - 1) / BK;

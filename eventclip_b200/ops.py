@@ -503,3 +503,27 @@ def patch_rows_bf16(x, n_img, G2, d):
     with torch.cuda.device(x.device):
         L.check(L.load().ec_patch_rows_bf16(_ptr(x), n_img, G2, d, _ptr(out), _stream()), "ec_patch_rows_bf16")
     return out
+
+
+def gemm_bf16_tn(A, B, splits=None, out=None):
+    """fp32 out [M,N] = A.T @ B for token-major bf16 matrices A [K,M], B [K,N] (weight gradients dY^T X); no transposes.
+    A / B may be column blocks of wider matrices (unit column stride, row stride a multiple of 8)."""
+    for t, n in ((A, "A"), (B, "B")):
+        if not (t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1):
+            raise L.ECError(f"{n} must be a CUDA bf16 matrix with unit column stride (no CPU fallback exists)")
+    L.require_device(A.device.index)
+    K, M = A.shape
+    N = B.shape[1]
+    if B.shape[0] != K:
+        raise L.ECError(f"gemm_bf16_tn: row counts differ ({K} vs {B.shape[0]})")
+    lib = L.load()
+    if splits is None:
+        with torch.cuda.device(A.device):
+            splits = lib.ec_gemm_splitk_choose(M, N, max(K, 64))
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    ws = torch.empty((splits, M, N), dtype=torch.float32, device=A.device) if splits > 1 else None
+    with torch.cuda.device(A.device):
+        L.check(lib.ec_gemm_bf16_tn_splitk(_ptr(A), A.stride(0), _ptr(B), B.stride(0), M, N, K, int(splits), _ptr(ws), _ptr(out),
+                                           out.stride(0), _stream()), "ec_gemm_bf16_tn_splitk")
+    return out

@@ -95,10 +95,10 @@ def encoder_backward(vis, ctx, d_feats, dest=None):
     f32w = lambda t: t.detach().to(torch.float32).contiguous()
     to = (lambda p: None) if dest is None else dest
 
-    def wgrad(p, dy_bf16, x_bf16):                 # dW[out, in] = dY^T X over the token dimension (split-K tcgen05 GEMM)
+    def wgrad(p, dy_bf16, x_bf16):                 # dW[out, in] = dY^T X over the tokens: split-K tcgen05 GEMM, MN-major operands
         out = to(p)
         view = None if out is None else out.view(p.shape[0], -1)
-        g = ops.gemm_bf16_splitk(ops.transpose_bf16(dy_bf16), ops.transpose_bf16(x_bf16), out=view)
+        g = ops.gemm_bf16_tn(dy_bf16, x_bf16, out=view)
         grads[id(p)] = g.view(p.shape)
         return g
 
@@ -160,7 +160,7 @@ def encoder_backward(vis, ctx, d_feats, dest=None):
         if _req(oW):
             wgrad(oW, dx2b, att)
         elif lora_out is not None and (_req(lora_out.lora_up.weight) or _req(lora_out.lora_down.weight)):
-            dW = ops.gemm_bf16_splitk(ops.transpose_bf16(dx2b), ops.transpose_bf16(att))            # [d_out, d_in]
+            dW = ops.gemm_bf16_tn(dx2b, att)                                                          # [d_out, d_in]
             factor_grads(dW, "o", [(lora_out.lora_up.weight, lora_out.lora_down.weight)])
         dqkv = ops.attention_bwd(qkv, att, d_att, n_img, Ltok, heads)
         if _req(ib):
@@ -173,7 +173,7 @@ def encoder_backward(vis, ctx, d_feats, dest=None):
         if _req(W):
             wgrad(W, dqkv, h1)
         elif facs is not None and any(f is not None for f in facs):
-            dW = ops.gemm_bf16_splitk(ops.transpose_bf16(dqkv), ops.transpose_bf16(h1))             # [3d, d]
+            dW = ops.gemm_bf16_tn(dqkv, h1)                                                           # [3d, d]
             factor_grads(dW, "qkv", facs)
         need_ln1 = _req(blk.ln_1.weight) or _req(blk.ln_1.bias)
         if i > first or bottom or need_ln1:
@@ -200,7 +200,7 @@ def encoder_backward(vis, ctx, d_feats, dest=None):
             w = vis.conv1.weight
             kp, k = vis.k_patch, 3 * vis.patch_size ** 2
             dyp = ops.patch_rows_bf16(dx0, n_img, G2, d)
-            gw = ops.gemm_bf16_splitk(ops.transpose_bf16(dyp), ops.transpose_bf16(ctx["patches"]))   # [d, k_patch]
+            gw = ops.gemm_bf16_tn(dyp, ctx["patches"])                                                # [d, k_patch]
             gw = gw[:, :k].reshape(w.shape)
             dst = to(w)
             grads[id(w)] = gw.contiguous() if dst is None else dst.copy_(gw)

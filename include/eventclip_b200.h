@@ -131,6 +131,13 @@ EC_API int ec_gemm_splitk_choose(int M, int N, int K);
 EC_API int ec_gemm_bf16_splitk(const void *A, int lda, const void *W, int ldw, int M, int N, int K, int splits,
                                float *workspace, float *out, int ldo, void *stream);
 
+/* Weight gradient without transposing the activations: out fp32 [M,ldo] = A^T . B with A bf16 [K, lda >= M] and B bf16
+ * [K, ldb >= N] both TOKEN-major (K = tokens is the row index) -- e.g. dW[out,in] = dY^T . X.  The tiles are fetched as
+ * 64 x 64 TMA boxes and fed to tcgen05.mma as MN-major operands; K is split as in ec_gemm_bf16_splitk (rows >= K read as
+ * zeros, so K needs no padding).  M, N, lda, ldb multiples of 8. */
+EC_API int ec_gemm_bf16_tn_splitk(const void *A, int lda, const void *B, int ldb, int M, int N, int K, int splits,
+                                  float *workspace, float *out, int ldo, void *stream);
+
 /* LayerNorm over the last dim (eps 1e-5, fp32 statistics): x fp32 [M, ldx] rows -> bf16 [M,d] (out_bf16)
  * and/or fp32 [M,d] (out_f32); either output may be NULL.  row_stride_in lets ln_post read only the
  * class-token rows (stride L*d). */

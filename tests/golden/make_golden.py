@@ -319,6 +319,50 @@ def make_ft_train():
     np.savez_compressed(os.path.join(HERE, "ft_train_golden.npz"), **out)
 
 
+def make_tta():
+    """Row F4: executes the reference's OWN source lines -- the TTA aggregation / confidence filter of gen_data.py:141-164
+    and the per-class top-k of gen_data.py:201-226 (lines 204-226, minus the path -> ground-truth lookups) -- on seeded
+    synthetic probabilities, and stores inputs + outputs."""
+    import textwrap
+    import types
+    src = open(os.path.join(ref_import.REF, "gen_data.py")).read().split("\n")
+    block = textwrap.dedent("\n".join(src[140:164]))            # lines 141-164
+    assert block.startswith("if tta:") and "sel_mask &= tta_mask" in block, block[:80]
+    g = torch.Generator().manual_seed(123)
+    B, n_cls = 64, 7
+    logits4 = torch.randn(B, 4, n_cls, generator=g) * 2.0
+    logits4[: B // 2] += 3.0 * torch.nn.functional.one_hot(torch.randint(0, n_cls, (B // 2,), generator=g), n_cls)[:, None].float()
+    probs4 = logits4.softmax(-1)
+    labels = torch.randint(0, n_cls, (B,), generator=g)
+    out = {"probs4": probs4.numpy(), "labels": labels.numpy()}
+    for ci, (thr, cons, minp) in enumerate([(-1.0, False, False), (0.5, True, False), (0.4, False, True), (0.6, True, True)]):
+        ns = dict(torch=torch, tta=True, labels=labels, conf_thresh=thr,
+                  args=types.SimpleNamespace(tta_consistent=cons, tta_min_prob=minp),
+                  pred_probs=probs4.flatten(0, 1),
+                  all_acc_meter=types.SimpleNamespace(update=lambda *a: None))
+        exec(block, ns)
+        out[f"case{ci}_cfg"] = np.array([thr, float(cons), float(minp)], np.float32)
+        for k in ("probs", "max_probs", "pred_labels", "sel_mask"):
+            out[f"case{ci}_{k}"] = ns[k].numpy()
+    # per-class top-k: the reference walks a dict path -> {'cls', 'prob'}; run its loop on synthetic paths
+    tk = textwrap.dedent("\n".join(src[203:226]))                # lines 204-226
+    assert tk.startswith("for cls_name in class_names:"), tk[:60]
+    sel = torch.from_numpy(out["case1_sel_mask"])
+    names = [f"c{i}" for i in range(n_cls)]
+    pred = {f"/d/{names[labels[i]]}/{i:03d}.npy": {"cls": names[int(out['case1_pred_labels'][i])], "prob": float(out["case1_max_probs"][i])}
+            for i in range(B) if sel[i]}
+    ns = dict(torch=torch, osp=os.path, class_names=names, pred_path2cls=pred, topk=3, is_nin=False,
+              ev_dst=types.SimpleNamespace(folder2name={}), new_cnames=None, topk_pred_path2cls={}, sel_class_cnt={},
+              sel_correct_class_cnt={})
+    exec(tk, ns)
+    keep = np.zeros(B, bool)
+    for path in ns["topk_pred_path2cls"]:
+        keep[int(os.path.basename(path)[:3])] = True
+    out["topk3_keep"] = keep
+    np.savez_compressed(os.path.join(HERE, "tta_golden.npz"), **out)
+    print("tta_golden", {k: v.shape for k, v in out.items() if k.startswith("case1")}, "kept", int(keep.sum()))
+
+
 if __name__ == "__main__":
     assert ref_import.available(), "/root/reference is required to (re)generate the golden fixtures"
     vis = ref_import.load_vis()
@@ -328,4 +372,5 @@ if __name__ == "__main__":
     make_heads()
     make_event_transforms()
     make_ft_train()
+    make_tta()
     print("sizes:", {f: os.path.getsize(os.path.join(HERE, f)) for f in sorted(os.listdir(HERE)) if not f.endswith(".py")})

@@ -197,3 +197,21 @@ def test_patch_rows_bf16(cuda_dev):
     out = ops.patch_rows_bf16(x.to(cuda_dev), n_img, G2, d).cpu()
     ref = x.view(n_img, G2 + 1, d)[:, 1:].reshape(n_img * G2, d).to(torch.bfloat16)
     assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("K,M,N,splits", [(12608, 768, 768, None), (3 * 197, 2304, 768, None), (300, 384, 128, 1), (1000, 128, 128, 4),
+                                          (64, 256, 512, 1), (12608, 3072, 768, None), (777, 768, 3072, 2), (500, 768, 592, None)])
+def test_gemm_tn_token_major(cuda_dev, K, M, N, splits):
+    """out = A^T B straight from token-major activations (MN-major UMMA operands): equals the transposed-copy route."""
+    g = torch.Generator().manual_seed(K + M)
+    A = torch.randn(K, M, generator=g).to(torch.bfloat16)
+    B = (torch.randn(K, N, generator=g) * K ** -0.5).to(torch.bfloat16)
+    ref = A.float().t() @ B.float()
+    out = ops.gemm_bf16_tn(A.to(cuda_dev), B.to(cuda_dev), splits=splits)
+    torch.cuda.synchronize()
+    assert rel(out, ref) < 2e-3, rel(out, ref)
+    # strided views (a column block of a wider matrix, e.g. the q / k / v thirds of d_qkv)
+    if M % 3 == 0 and (M // 3) % 8 == 0:
+        Ad = A.to(cuda_dev)
+        part = ops.gemm_bf16_tn(Ad[:, M // 3:2 * M // 3], B.to(cuda_dev), splits=splits)
+        assert rel(part, ref[M // 3:2 * M // 3]) < 2e-3
