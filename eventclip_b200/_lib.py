@@ -63,7 +63,8 @@ SIGNATURES = {
     "ec_quickgelu": ([_vp, _vp, _i64, _vp], _i),
     "ec_quickgelu_bwd": ([_vp, _vp, _vp, _i64, _vp], _i),
     "ec_transpose_bf16": ([_vp, _vp, _i, _i, _i64, _i64, _vp], _i),
-    "ec_attention_bwd": ([_vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
+    "ec_attention_fwd_lse": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp], _i),
+    "ec_attention_bwd": ([_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
     "ec_adam": ([_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _vp], _i),
     "ec_gemm_f32_strided": ([_vp, _i64, _i64, _vp, _i64, _i64, _i, _i, _i, _f, _vp, _i64, _i, _vp], _i),
     "ec_lora_grad": ([_vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp], _i),

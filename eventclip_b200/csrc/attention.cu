@@ -188,6 +188,14 @@ extern "C" int ec_attention(const void *qkv, void *out, int n_img, int L, int he
     return ec_attention_ex(qkv, out, n_img, L, heads, 0, stream);
 }
 
+extern "C" int ec_attention_fwd_lse(const void *qkv, void *out, float *lse, int n_seq, int L, int heads, int causal, void *stream)
+{
+    EC_REQUIRE(qkv && out && lse && n_seq > 0 && L > 0 && heads > 0, "ec_attention_fwd_lse: bad arguments");
+    const int rc = ec::attention_tc(qkv, out, n_seq, L, heads, causal, (cudaStream_t)stream, lse);
+    if (rc == EC_ERR_UNSUPPORTED) ec::set_error("ec_attention_fwd_lse: L=%d is outside the tensor-memory kernels' range (<= 384)", L);
+    return rc;
+}
+
 extern "C" int ec_attention_ex(const void *qkv, void *out, int n_img, int L, int heads, int causal, void *stream)
 {
     EC_REQUIRE(qkv && out && n_img > 0 && L > 0 && heads > 0, "ec_attention: bad arguments");

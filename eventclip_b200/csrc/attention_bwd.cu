@@ -7,6 +7,9 @@
 //   phase A  warp per 16-query tile: log-sum-exp of the row (recomputed), then dS = P * (dP - D) / 8 and dQ = dS K
 //   phase B  warp per 16-key tile:  S^T and dP^T recomputed with the keys as rows, dV = P^T dO, dK = dS^T Q
 // bf16 mma.sync m16n8k16 tiles; the training batch is small (config 5: 64 images), so this kernel favours simplicity.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace {
@@ -245,10 +248,15 @@ attention_bwd_kernel(const __nv_bfloat16 *__restrict__ qkv, const __nv_bfloat16 
 
 }  // namespace
 
-extern "C" int ec_attention_bwd(const void *qkv, const void *o, const void *d_o, void *dqkv, int n_img, int L, int heads,
-                                void *stream)
+extern "C" int ec_attention_bwd(const void *qkv, const void *o, const void *d_o, const float *lse, void *dqkv, int n_img, int L,
+                                int heads, void *stream)
 {
     EC_REQUIRE(qkv && o && d_o && dqkv && n_img > 0 && L > 0 && heads > 0, "ec_attention_bwd: bad arguments");
+    static const bool force_mma = getenv("EC_ATTN_BWD") && !strcmp(getenv("EC_ATTN_BWD"), "mma");
+    if (lse && L <= 256 && !force_mma) {       // tensor-memory kernel; it needs the forward's log-sum-exp
+        const int rc = ec::attention_bwd_tc(qkv, o, d_o, lse, dqkv, n_img, L, heads, (cudaStream_t)stream);
+        if (rc != EC_ERR_UNSUPPORTED) return rc;
+    }
     EC_REQUIRE(n_img <= 65535, "ec_attention_bwd: n_img=%d exceeds grid.y", n_img);
     const int Lp = (L + 63) & ~63;
     const size_t smem = (size_t)4 * Lp * LDS * sizeof(__nv_bfloat16) + (size_t)2 * Lp * sizeof(float);

@@ -33,6 +33,7 @@ constexpr int ONES_BYTES = 2048;                // 16 rows x 64 bf16 of 1.0: B o
 
 struct AttnParams {
     __nv_bfloat16 *out;
+    float *lse;           // optional [n_img, heads, L]: log2-domain log-sum-exp of every row (kept for the backward pass)
     int L, heads, d, n_img, causal;
 };
 
@@ -189,8 +190,9 @@ __device__ __forceinline__ float fast_exp2(float x)
 template <uint32_t OCOL, uint32_t SUMCOL>
 __device__ __forceinline__ void softmax_tile(uint32_t lane_base, int L, int nch, bool live, int row, int lane, uint64_t *bar_p,
                                              uint64_t *bar_o, uint32_t o_parity, uint64_t *bar_oe, __nv_bfloat16 *orow,
-                                             int causal)
+                                             int causal, float *lse_row)
 {
+    float ms_keep = 0.f;
     const int klim = causal ? min(L, row + 1) : L;     // keys [0, klim) are visible to this row
     const float sl2 = 0.125f * 1.4426950408889634f;
                 // Single pass over S (tensor-memory reads are the scarce resource: ~64 B/clk per SM).  Softmax is invariant to
@@ -208,6 +210,7 @@ __device__ __forceinline__ void softmax_tile(uint32_t lane_base, int L, int nch,
                     for (int j = 0; j < 32; ++j)
                         if (j < klim) m = fmaxf(m, __uint_as_float(va[j]));
                     const float ms = m * sl2;
+                    ms_keep = ms;
                     auto emit = [&](const uint32_t (&v)[32], int c) {
                         uint32_t pk[16];
                         const bool full = (c + 1) * 32 <= klim;
@@ -250,7 +253,9 @@ __device__ __forceinline__ void softmax_tile(uint32_t lane_base, int L, int nch,
                     if (lane == 0) mbar_arrive(bar_oe);
                     return;
                 }
-                const float inv = 1.f / tmem_ld1(lane_base + SUMCOL);
+                const float rsum = tmem_ld1(lane_base + SUMCOL);
+                const float inv = 1.f / rsum;
+                if (lse_row && row < L) *lse_row = ms_keep + log2f(rsum);     // p_ij = exp2(s_ij * sl2 - lse)
     #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     uint32_t v[32];
@@ -393,7 +398,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
             mbar_wait(&bar_s[t], uph);
             tc_fence_after();
             softmax_tile<O_COL, SUM_COL>(lane_base, L, nch, live, row, lane, &bar_p[t], &bar_o[t], uph, &bar_oe[t],
-                                         p.out + ((size_t)img * L + row) * d + h * HD, p.causal);
+                                         p.out + ((size_t)img * L + row) * d + h * HD, p.causal,
+                                         p.lse ? p.lse + (size_t)unit * L + row : nullptr);
         }
     }
 
@@ -529,7 +535,8 @@ attention_tc_big_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnP
                 mbar_wait(&bar_s, n & 1);
                 tc_fence_after();
                 softmax_tile<BIG_O_COL, BIG_SUM_COL>(lane_base, L, nch, live, row, lane, &bar_p, &bar_o, n & 1, &bar_oe,
-                                                     p.out + ((size_t)img * L + row) * d + h * HD, p.causal);
+                                                     p.out + ((size_t)img * L + row) * d + h * HD, p.causal,
+                                                     p.lse ? p.lse + (size_t)unit * L + row : nullptr);
             }
         }
     }
@@ -537,6 +544,296 @@ attention_tc_big_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnP
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ================================================================================================================
+// Backward on the tensor cores (L <= 256).  One persistent CTA per SM walks over (image, head) units.
+//   shared memory  Q, K, V, dO as two [128 x 64] bf16 tiles each (TMA, rows >= L zero-filled), plus P and dS of the
+//                  current (128 queries x 128 keys) block as bf16 operand tiles written by the softmax warps
+//   tensor memory  S [0,128)  dP [128,256)  dQ (both query tiles) [256,384)  dK [384,448)  dV [448,512)
+//   warp 0  TMA;  warp 1  MMA issue;  warps 2-5  one thread per row: P = exp2(S*sl2 - lse), dS = P*(dP - D)/8 -> smem,
+//           and the epilogues (dK, dV per key tile; dQ per unit) -> global.
+// Per (key tile j, query tile t):  S = Q_t K_j^T, dP = dO_t V_j^T  (K-major operands)
+//                                  dV_j += P^T dO_t, dK_j += dS^T Q_t  (A = the P / dS tile read MN-major, B MN-major)
+//                                  dQ_t += dS K_j                      (A = the dS tile read K-major, B MN-major)
+// The same P / dS tile serves as a K-major and as an MN-major operand: only the descriptor changes.
+constexpr int BWD_THREADS = 192;
+constexpr uint32_t B_S = 0, B_DP = 128, B_DQ = 256, B_DK = 384, B_DV = 448;
+constexpr int BWD_SMEM = 8 * TILE_BYTES + 2 * 2 * TILE_BYTES;      // inputs + P + dS (two 64-key sub-tiles each)
+
+struct AttnBwdParams {
+    __nv_bfloat16 *dqkv;
+    const __nv_bfloat16 *o;
+    const float *lse;
+    int L, heads, d, n_img;
+};
+
+// MN-major operand: 8-row groups 1024 bytes apart along K (SBO), 64-wide atoms along M/N `lbo` bytes apart
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do, const AttnBwdParams p)
+{
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char *sQ = smem, *sK = smem + 2 * TILE_BYTES, *sV = smem + 4 * TILE_BYTES, *sdO = smem + 6 * TILE_BYTES;
+    unsigned char *sP = smem + 8 * TILE_BYTES, *sdS = smem + 10 * TILE_BYTES;
+    __shared__ __align__(8) uint64_t bar_load, bar_done, bar_s, bar_p, bar_free, bar_kv, bar_kv_free, bar_q, bar_q_free;
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int L = p.L, d = p.d, heads = p.heads;
+    const int MT = (L + 127) >> 7;
+    const int n_units = p.n_img * heads;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qkv) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_do) : "memory");
+        mbar_init(&bar_load, 1); mbar_init(&bar_done, 1); mbar_init(&bar_s, 1); mbar_init(&bar_p, 4); mbar_init(&bar_free, 1);
+        mbar_init(&bar_kv, 1); mbar_init(&bar_kv_free, 4); mbar_init(&bar_q, 1); mbar_init(&bar_q_free, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        int i = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++i) {
+            const int img = unit / heads, h = unit % heads;
+            if (i > 0) mbar_wait(&bar_done, (uint32_t)(i - 1) & 1);      // every MMA of the previous unit has retired
+            if (elect_one()) {
+                mbar_expect_tx(&bar_load, (uint32_t)(4 * MT * TILE_BYTES));
+                for (int t = 0; t < MT; ++t) {
+                    tma_load_3d(sQ + t * TILE_BYTES, &map_qkv, &bar_load, h * HD, t * 128, img);
+                    tma_load_3d(sK + t * TILE_BYTES, &map_qkv, &bar_load, d + h * HD, t * 128, img);
+                    tma_load_3d(sV + t * TILE_BYTES, &map_qkv, &bar_load, 2 * d + h * HD, t * 128, img);
+                    tma_load_3d(sdO + t * TILE_BYTES, &map_do, &bar_load, h * HD, t * 128, img);
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        // instruction descriptors: D fp32, A/B bf16, M = 128
+        const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc_kv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc_q = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint64_t p_mn = make_desc_mn(smem_u32(sP), TILE_BYTES), ds_mn = make_desc_mn(smem_u32(sdS), TILE_BYTES);
+        const uint64_t ds_k0 = make_desc(smem_u32(sdS)), ds_k1 = make_desc(smem_u32(sdS + TILE_BYTES));
+        uint32_t it = 0, kvc = 0;
+        int i = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++i) {
+            mbar_wait(&bar_load, (uint32_t)i & 1);
+            tc_fence_after();
+            for (int j = 0; j < MT; ++j) {
+                const uint64_t k_k = make_desc(smem_u32(sK + j * TILE_BYTES)), v_k = make_desc(smem_u32(sV + j * TILE_BYTES));
+                const uint64_t k_mn = make_desc_mn(smem_u32(sK + j * TILE_BYTES), TILE_BYTES);
+                for (int t = 0; t < MT; ++t, ++it) {
+                    const uint64_t q_k = make_desc(smem_u32(sQ + t * TILE_BYTES)), do_k = make_desc(smem_u32(sdO + t * TILE_BYTES));
+                    const uint64_t q_mn = make_desc_mn(smem_u32(sQ + t * TILE_BYTES), TILE_BYTES);
+                    const uint64_t do_mn = make_desc_mn(smem_u32(sdO + t * TILE_BYTES), TILE_BYTES);
+                    // S and dP may overwrite tensor memory as soon as the softmax warps have consumed the previous block
+                    // (they signalled bar_p for it, waited on below in the previous iteration)
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_ss(tmem_base + B_S, q_k + (uint64_t)(2 * k), k_k + (uint64_t)(2 * k), idesc_s, k != 0);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_ss(tmem_base + B_DP, do_k + (uint64_t)(2 * k), v_k + (uint64_t)(2 * k), idesc_s, k != 0);
+                        umma_commit(&bar_s);
+                    }
+                    __syncwarp();
+                    mbar_wait(&bar_p, it & 1);                                   // P and dS are in shared memory
+                    if (t == 0 && kvc > 0) mbar_wait(&bar_kv_free, (kvc - 1) & 1);   // dK / dV of the previous key tile were read out
+                    if (j == 0 && i > 0) mbar_wait(&bar_q_free, (uint32_t)(i - 1) & 1);   // dQ of the previous unit was read out
+                    tc_fence_after();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)      // 16 queries per step = 2048 bytes of the query-row-major tiles
+                            umma_ss(tmem_base + B_DV, p_mn + (uint64_t)(128 * k), do_mn + (uint64_t)(128 * k), idesc_kv, (t | k) != 0);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            umma_ss(tmem_base + B_DK, ds_mn + (uint64_t)(128 * k), q_mn + (uint64_t)(128 * k), idesc_kv, (t | k) != 0);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)      // 16 keys per step: 32 bytes inside a 64-key sub-tile of dS, 2048 bytes of K
+                            umma_ss(tmem_base + B_DQ + (uint32_t)(64 * t), (k < 4 ? ds_k0 : ds_k1) + (uint64_t)(2 * (k & 3)),
+                                    k_mn + (uint64_t)(128 * k), idesc_q, (j | k) != 0);
+                        umma_commit(&bar_free);
+                        if (t == MT - 1) umma_commit(&bar_kv);
+                        if (t == MT - 1 && j == MT - 1) { umma_commit(&bar_q); umma_commit(&bar_done); }
+                    }
+                    __syncwarp();
+                }
+                ++kvc;
+            }
+        }
+    } else {
+        // ===================== softmax + epilogues: thread = row of a 128-row tile =====================
+        const int quarter = warp & 3;                 // tensor-memory lane quarter this warp may access
+        const int rt = quarter * 32 + lane;           // row inside a tile
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const float sl2 = 0.125f * 1.4426950408889634f;
+        const uint32_t sw = (uint32_t)(rt & 7);
+        uint32_t it = 0, kvc = 0;
+        int i = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++i) {
+            const int img = unit / heads, h = unit % heads;
+            mbar_wait(&bar_load, (uint32_t)i & 1);
+            // D = <dO, O> and the log-sum-exp of this thread's row in each query tile
+            float Dv[2] = {0.f, 0.f}, lse[2] = {INFINITY, INFINITY};
+            for (int t = 0; t < MT; ++t) {
+                const int row = t * 128 + rt;
+                if (row < L) {
+                    const uint4 *po = reinterpret_cast<const uint4 *>(p.o + ((size_t)img * L + row) * d + h * HD);
+                    const uint32_t srow = smem_u32(sdO + t * TILE_BYTES) + (uint32_t)rt * 128;
+                    float acc = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint4 a = po[c], b = lds128u(srow + (((uint32_t)c ^ sw) << 4));
+                        const __nv_bfloat162 *ah = reinterpret_cast<const __nv_bfloat162 *>(&a), *bh = reinterpret_cast<const __nv_bfloat162 *>(&b);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 x = __bfloat1622float2(ah[e]), y = __bfloat1622float2(bh[e]);
+                            acc += x.x * y.x + x.y * y.y;
+                        }
+                    }
+                    Dv[t] = acc;
+                    lse[t] = p.lse[(size_t)unit * L + row];
+                }
+            }
+            for (int j = 0; j < MT; ++j) {
+                for (int t = 0; t < MT; ++t, ++it) {
+                    mbar_wait(&bar_s, it & 1);
+                    if (it > 0) mbar_wait(&bar_free, (it - 1) & 1);      // the MMAs that read the previous P / dS have retired
+                    tc_fence_after();
+                    const float lr = lse[t], Dr = Dv[t];
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t vs[32], vp[32];
+                        tmem_ld32_issue(lane_base + B_S + (uint32_t)(c * 32), vs);
+                        tmem_ld32(lane_base + B_DP + (uint32_t)(c * 32), vp);        // waits for both loads
+                        uint32_t pk[16], dk[16];
+                        const int key0 = j * 128 + c * 32;
+#pragma unroll
+                        for (int e = 0; e < 32; e += 2) {
+                            float p0 = fast_exp2(fmaf(__uint_as_float(vs[e]), sl2, -lr));
+                            float p1 = fast_exp2(fmaf(__uint_as_float(vs[e + 1]), sl2, -lr));
+                            if (key0 + e >= L) p0 = 0.f;
+                            if (key0 + e + 1 >= L) p1 = 0.f;
+                            const float s0 = p0 * (__uint_as_float(vp[e]) - Dr) * 0.125f;
+                            const float s1 = p1 * (__uint_as_float(vp[e + 1]) - Dr) * 0.125f;
+                            __nv_bfloat162 hp = __floats2bfloat162_rn(p0, p1), hs = __floats2bfloat162_rn(s0, s1);
+                            pk[e >> 1] = *reinterpret_cast<uint32_t *>(&hp);
+                            dk[e >> 1] = *reinterpret_cast<uint32_t *>(&hs);
+                        }
+                        // columns [32c, 32c+32) of this row: 64-key sub-tile c/2, 16-byte chunks (c%2)*4 .. +3, SWIZZLE_128B
+                        const uint32_t off = (uint32_t)(c >> 1) * TILE_BYTES + (uint32_t)rt * 128;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint32_t ch = ((uint32_t)((c & 1) * 4 + q) ^ sw) << 4;
+                            sts128(smem_u32(sP) + off + ch, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                            sts128(smem_u32(sdS) + off + ch, dk[4 * q], dk[4 * q + 1], dk[4 * q + 2], dk[4 * q + 3]);
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_p);
+                }
+                // dK_j, dV_j: rows = keys of tile j
+                mbar_wait(&bar_kv, kvc & 1);
+                tc_fence_after();
+                {
+                    const int key = j * 128 + rt;
+                    __nv_bfloat16 *ok = p.dqkv + ((size_t)img * L + key) * 3 * d + d + h * HD;
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {                // m = 0: dK, m = 1: dV
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            uint32_t v[32];
+                            tmem_ld32(lane_base + (m ? B_DV : B_DK) + (uint32_t)(c * 32), v);
+                            if (key < L) {
+#pragma unroll
+                                for (int e = 0; e < 32; e += 8) {
+                                    uint4 o;
+                                    __nv_bfloat162 hh;
+                                    hh = __floats2bfloat162_rn(__uint_as_float(v[e]), __uint_as_float(v[e + 1])); o.x = *reinterpret_cast<uint32_t *>(&hh);
+                                    hh = __floats2bfloat162_rn(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3])); o.y = *reinterpret_cast<uint32_t *>(&hh);
+                                    hh = __floats2bfloat162_rn(__uint_as_float(v[e + 4]), __uint_as_float(v[e + 5])); o.z = *reinterpret_cast<uint32_t *>(&hh);
+                                    hh = __floats2bfloat162_rn(__uint_as_float(v[e + 6]), __uint_as_float(v[e + 7])); o.w = *reinterpret_cast<uint32_t *>(&hh);
+                                    *reinterpret_cast<uint4 *>(ok + m * d + c * 32 + e) = o;
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_kv_free);
+                ++kvc;
+            }
+            // dQ of both query tiles
+            mbar_wait(&bar_q, (uint32_t)i & 1);
+            tc_fence_after();
+            for (int t = 0; t < MT; ++t) {
+                const int row = t * 128 + rt;
+                __nv_bfloat16 *oq = p.dqkv + ((size_t)img * L + row) * 3 * d + h * HD;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(lane_base + B_DQ + (uint32_t)(64 * t + c * 32), v);
+                    if (row < L) {
+#pragma unroll
+                        for (int e = 0; e < 32; e += 8) {
+                            uint4 o;
+                            __nv_bfloat162 hh;
+                            hh = __floats2bfloat162_rn(__uint_as_float(v[e]), __uint_as_float(v[e + 1])); o.x = *reinterpret_cast<uint32_t *>(&hh);
+                            hh = __floats2bfloat162_rn(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3])); o.y = *reinterpret_cast<uint32_t *>(&hh);
+                            hh = __floats2bfloat162_rn(__uint_as_float(v[e + 4]), __uint_as_float(v[e + 5])); o.z = *reinterpret_cast<uint32_t *>(&hh);
+                            hh = __floats2bfloat162_rn(__uint_as_float(v[e + 6]), __uint_as_float(v[e + 7])); o.w = *reinterpret_cast<uint32_t *>(&hh);
+                            *reinterpret_cast<uint4 *>(oq + c * 32 + e) = o;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_q_free);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
@@ -565,7 +862,7 @@ EncodeTiledFn get_encode()
 namespace ec {
 
 // Returns EC_OK when the tcgen05 kernel was launched, EC_ERR_UNSUPPORTED when the shape is outside its range.
-int attention_tc(const void *qkv, void *out, int n_img, int L, int heads, int causal, cudaStream_t stream)
+int attention_tc(const void *qkv, void *out, int n_img, int L, int heads, int causal, cudaStream_t stream, float *lse)
 {
     if (L > 384) return EC_ERR_UNSUPPORTED;
     EncodeTiledFn enc = get_encode();
@@ -591,11 +888,54 @@ int attention_tc(const void *qkv, void *out, int n_img, int L, int heads, int ca
         attr_set[dev_id] = true;
     }
     AttnParams p;
-    p.out = (__nv_bfloat16 *)out; p.L = L; p.heads = heads; p.d = d; p.n_img = n_img; p.causal = causal;
+    p.out = (__nv_bfloat16 *)out; p.lse = lse; p.L = L; p.heads = heads; p.d = d; p.n_img = n_img; p.causal = causal;
     const int units = n_img * heads;
     const int grid = units < sm_count() ? units : sm_count();
     if (L > 256) attention_tc_big_kernel<<<grid, BIG_NTHREADS, smem_big, stream>>>(map, p);
     else attention_tc_kernel<<<grid, NTHREADS, smem, stream>>>(map, p);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
+int attention_bwd_tc(const void *qkv, const void *o, const void *d_o, const float *lse, void *dqkv, int n_img, int L, int heads,
+                     cudaStream_t stream)
+{
+    if (L > 256 || !lse) return EC_ERR_UNSUPPORTED;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return EC_ERR_CUDA; }
+    const int d = heads * HD;
+    CUtensorMap mq, md;
+    cuuint32_t box[3] = {64, 128, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    {
+        cuuint64_t gdim[3] = {(cuuint64_t)3 * d, (cuuint64_t)L, (cuuint64_t)n_img};
+        cuuint64_t gstr[2] = {(cuuint64_t)3 * d * 2, (cuuint64_t)L * 3 * d * 2};
+        CUresult r = enc(&mq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(qkv), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (attention bwd qkv) failed with CUresult %d", (int)r); return EC_ERR_CUDA; }
+    }
+    {
+        cuuint64_t gdim[3] = {(cuuint64_t)d, (cuuint64_t)L, (cuuint64_t)n_img};
+        cuuint64_t gstr[2] = {(cuuint64_t)d * 2, (cuuint64_t)L * d * 2};
+        CUresult r = enc(&md, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(d_o), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (attention bwd dO) failed with CUresult %d", (int)r); return EC_ERR_CUDA; }
+    }
+    const size_t smem = BWD_SMEM + 1024;
+    static bool attr_set[64] = {false};
+    int dev_id = 0;
+    EC_CUDA_CHECK(cudaGetDevice(&dev_id));
+    if (dev_id < 64 && !attr_set[dev_id]) {
+        EC_CUDA_CHECK(cudaFuncSetAttribute(attention_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[dev_id] = true;
+    }
+    AttnBwdParams p;
+    p.dqkv = (__nv_bfloat16 *)dqkv; p.o = (const __nv_bfloat16 *)o; p.lse = lse; p.L = L; p.heads = heads; p.d = d; p.n_img = n_img;
+    const int units = n_img * heads;
+    const int grid = units < sm_count() ? units : sm_count();
+    attention_bwd_tc_kernel<<<grid, BWD_THREADS, smem, stream>>>(mq, md, p);
     EC_CUDA_CHECK(cudaGetLastError());
     return EC_OK;
 }

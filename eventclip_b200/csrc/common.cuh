@@ -34,7 +34,11 @@ void set_error(const char *fmt, ...);
 int sm_count();
 
 // tcgen05 attention (attention_tc.cu): EC_OK when launched, EC_ERR_UNSUPPORTED when the shape is outside its range
-int attention_tc(const void *qkv, void *out, int n_img, int L, int heads, int causal, cudaStream_t stream);
+int attention_tc(const void *qkv, void *out, int n_img, int L, int heads, int causal, cudaStream_t stream, float *lse = nullptr);
+
+// tcgen05 attention backward (attention_tc.cu), L <= 256; needs the forward's log-sum-exp
+int attention_bwd_tc(const void *qkv, const void *o, const void *d_o, const float *lse, void *dqkv, int n_img, int L, int heads,
+                     cudaStream_t stream);
 
 __device__ __forceinline__ float warp_sum(float v)
 {

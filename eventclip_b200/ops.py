@@ -348,13 +348,23 @@ def transpose_bf16(x, out=None, pad=8):
     return out
 
 
-def attention_bwd(qkv, o, d_o, n_img, Ltok, heads, out=None):
+def attention_fwd_lse(qkv, out, n_img, Ltok, heads, causal=False):
+    """Training forward: attention plus the per-row log-sum-exp [n_img, heads, Ltok] the tcgen05 backward needs."""
+    _dev(qkv, torch.bfloat16, "qkv")
+    lse = torch.empty((n_img, heads, Ltok), dtype=torch.float32, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        L.check(L.load().ec_attention_fwd_lse(_ptr(qkv), _ptr(out), _ptr(lse), n_img, Ltok, heads, int(bool(causal)), _stream()),
+                "ec_attention_fwd_lse")
+    return lse
+
+
+def attention_bwd(qkv, o, d_o, n_img, Ltok, heads, out=None, lse=None):
     _dev(qkv, torch.bfloat16, "qkv")
     _dev(o, torch.bfloat16, "o")
     _dev(d_o, torch.bfloat16, "d_o")
     out = torch.empty_like(qkv) if out is None else out
     with torch.cuda.device(qkv.device):
-        L.check(L.load().ec_attention_bwd(_ptr(qkv), _ptr(o), _ptr(d_o), _ptr(out), n_img, Ltok, heads, _stream()),
+        L.check(L.load().ec_attention_bwd(_ptr(qkv), _ptr(o), _ptr(d_o), _ptr(lse), _ptr(out), n_img, Ltok, heads, _stream()),
                 "ec_attention_bwd")
     return out
 

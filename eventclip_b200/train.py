@@ -61,7 +61,11 @@ def encoder_forward(vis, patches, n_img):
         h1, qkv, att = bf(M, d), bf(M, 3 * d), bf(M, d)
         ops.layernorm(x, *b["ln1"], M, d, out_bf16=h1)
         ops.gemm_bf16(h1, b["w_in"], b["b_in"], "bf16", out=qkv)
-        ops.attention(qkv, att, n_img, Ltok, heads)
+        lse = None
+        if Ltok <= 256:          # the tensor-memory backward needs the row log-sum-exp of the forward
+            lse = ops.attention_fwd_lse(qkv, att, n_img, Ltok, heads)
+        else:
+            ops.attention(qkv, att, n_img, Ltok, heads)
         x2 = f32(M, d)
         ops.gemm_bf16(att, b["w_out"], b["b_out"], "f32_resadd", out=x2, res=x)
         h2, a = bf(M, d), bf(M, 4 * d)
@@ -70,7 +74,7 @@ def encoder_forward(vis, patches, n_img):
         g = ops.quickgelu(a)
         x3 = f32(M, d)
         ops.gemm_bf16(g, b["w_proj"], b["b_proj"], "f32_resadd", out=x3, res=x2)
-        saved.append((x, h1, qkv, att, x2, h2, a, g))
+        saved.append((x, h1, qkv, att, x2, h2, a, g, lse))
         x = x3
     cls = bf(n_img, d)
     cls32 = f32(n_img, d) if _req(vis.proj) else None
@@ -132,7 +136,7 @@ def encoder_backward(vis, ctx, d_feats, dest=None):
     ops.layernorm_bwd(ctx["x_last"], d_cls, pk["ln_post"][0], n_img, d, x_stride=Ltok * d, dx=dx, dx_stride=Ltok * d)
     for i in range(len(saved) - 1, first - 1, -1):
         b, blk = pk["blocks"][i], blocks[i]
-        x, h1, qkv, att, x2, h2, a, g = saved[i]
+        x, h1, qkv, att, x2, h2, a, g, lse = saved[i]
         saved[i] = None
         W, lora_in, ib, oW, ob, lora_out = _attn_parts(blk.attn)
         fc, pj = blk.mlp.c_fc, blk.mlp.c_proj
@@ -162,7 +166,7 @@ def encoder_backward(vis, ctx, d_feats, dest=None):
         elif lora_out is not None and (_req(lora_out.lora_up.weight) or _req(lora_out.lora_down.weight)):
             dW = ops.gemm_bf16_tn(dx2b, att)                                                          # [d_out, d_in]
             factor_grads(dW, "o", [(lora_out.lora_up.weight, lora_out.lora_down.weight)])
-        dqkv = ops.attention_bwd(qkv, att, d_att, n_img, Ltok, heads)
+        dqkv = ops.attention_bwd(qkv, att, d_att, n_img, Ltok, heads, lse=lse)
         if _req(ib):
             bgrad(ib, dqkv)
         facs = None

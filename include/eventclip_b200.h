@@ -225,10 +225,16 @@ EC_API int ec_quickgelu_bwd(const void *a, const void *dh, void *da, int64_t n, 
 /* out[c, r] = in[r, c] for bf16 matrices (weight-gradient GEMMs reduce over the token dimension). */
 EC_API int ec_transpose_bf16(const void *in, void *out, int rows, int cols, int64_t ld_in, int64_t ld_out, void *stream);
 
+/* Training forward of the attention core: ec_attention_ex plus lse fp32 [n_seq, heads, L], the log2-domain log-sum-exp of
+ * every score row (p_ij = exp2(s_ij * log2(e)/8 - lse_i)), kept for the backward.  L <= 384 (tensor-memory kernels). */
+EC_API int ec_attention_fwd_lse(const void *qkv, void *out, float *lse, int n_seq, int L, int heads, int causal, void *stream);
+
 /* Attention backward for the packed QKV layout of ec_attention: dqkv bf16 [n_img*L, 3d] from qkv, the forward
- * output o bf16 [n_img*L, d] and its gradient do bf16 [n_img*L, d]; softmax recomputed per tile (flash-style). */
-EC_API int ec_attention_bwd(const void *qkv, const void *o, const void *d_o, void *dqkv, int n_img, int L, int heads,
-                            void *stream);
+ * output o bf16 [n_img*L, d] and its gradient do bf16 [n_img*L, d]; scores recomputed per tile (flash-style).
+ * lse: the forward's ec_attention_fwd_lse output -> tcgen05 kernel (L <= 256: S, dP and the dQ / dK / dV accumulators in
+ * tensor memory); NULL (or L > 256, or EC_ATTN_BWD=mma) -> mma.sync kernel that recomputes the row statistics. */
+EC_API int ec_attention_bwd(const void *qkv, const void *o, const void *d_o, const float *lse, void *dqkv, int n_img, int L,
+                            int heads, void *stream);
 
 /* One Adam update (torch.optim.Adam semantics, method.py:150-191): fp32 parameters, bias correction by `step` >= 1. */
 EC_API int ec_adam(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1,

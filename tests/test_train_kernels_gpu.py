@@ -57,7 +57,8 @@ def test_transpose_bf16(cuda_dev, R, Cc):
     assert (out[:, R:] == 0).all()
 
 
-@pytest.mark.parametrize("n_img,Ltok,heads", [(2, 197, 12), (3, 50, 4), (1, 257, 16), (2, 64, 2), (1, 77, 8)])
+@pytest.mark.parametrize("n_img,Ltok,heads", [(2, 197, 12), (3, 50, 4), (1, 257, 16), (2, 64, 2), (1, 77, 8), (40, 197, 12),
+                                              (1, 128, 1), (2, 129, 3), (1, 256, 2)])
 def test_attention_bwd(cuda_dev, n_img, Ltok, heads):
     g = torch.Generator().manual_seed(Ltok)
     d = heads * 64
@@ -71,11 +72,26 @@ def test_attention_bwd(cuda_dev, n_img, Ltok, heads):
     dev_qkv = qkv.to(cuda_dev)
     o_dev = torch.empty((n_img * Ltok, d), dtype=torch.bfloat16, device=cuda_dev)
     ops.attention(dev_qkv, o_dev, n_img, Ltok, heads)
-    dqkv = ops.attention_bwd(dev_qkv, o_dev, d_o.to(cuda_dev), n_img, Ltok, heads)
+    dqkv = ops.attention_bwd(dev_qkv, o_dev, d_o.to(cuda_dev), n_img, Ltok, heads)        # mma.sync kernel (no lse given)
     torch.cuda.synchronize()
     for j, name in enumerate("qkv"):
         r = rel(dqkv[:, j * d:(j + 1) * d].float(), x.grad[:, j * d:(j + 1) * d])
         assert r < 1.5e-2, (name, r)
+    if Ltok <= 256:
+        # tcgen05 kernel: forward with log-sum-exp export, backward with S / dP / dQ / dK / dV in tensor memory
+        o2 = torch.empty_like(o_dev)
+        lse = ops.attention_fwd_lse(dev_qkv, o2, n_img, Ltok, heads)
+        assert torch.equal(o2, o_dev)
+        s = (q @ k.transpose(-1, -2) * 0.125).detach()
+        ref_lse = torch.logsumexp(s, dim=-1) * 1.4426950408889634                           # [n_img, heads, L], log2 domain
+        assert (lse.cpu() - ref_lse).abs().max().item() < 2e-2
+        dq2 = torch.full_like(dqkv, float("nan"))
+        ops.attention_bwd(dev_qkv, o_dev, d_o.to(cuda_dev), n_img, Ltok, heads, out=dq2, lse=lse)
+        torch.cuda.synchronize()
+        assert not torch.isnan(dq2.float()).any()
+        for j, name in enumerate("qkv"):
+            r = rel(dq2[:, j * d:(j + 1) * d].float(), x.grad[:, j * d:(j + 1) * d])
+            assert r < 1.5e-2, ("tc", name, r)
 
 
 def test_adam_matches_torch(cuda_dev):
