@@ -645,7 +645,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __gri
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         // instruction descriptors: D fp32, A/B bf16, M = 128
-        const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc_s0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);     // N is filled in per key tile
         const uint32_t idesc_kv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t idesc_q = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint64_t p_mn = make_desc_mn(smem_u32(sP), TILE_BYTES), ds_mn = make_desc_mn(smem_u32(sdS), TILE_BYTES);
@@ -658,7 +658,10 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __gri
             for (int j = 0; j < MT; ++j) {
                 const uint64_t k_k = make_desc(smem_u32(sK + j * TILE_BYTES)), v_k = make_desc(smem_u32(sV + j * TILE_BYTES));
                 const uint64_t k_mn = make_desc_mn(smem_u32(sK + j * TILE_BYTES), TILE_BYTES);
+                const int kj = (min(128, L - 128 * j) + 15) >> 4;       // 16-key steps that hold real keys in this tile
+                const uint32_t idesc_s = idesc_s0 | ((uint32_t)(kj * 2) << 17);      // N = 16 * kj
                 for (int t = 0; t < MT; ++t, ++it) {
+                    const int qt = (min(128, L - 128 * t) + 15) >> 4;   // 16-query steps that hold real queries
                     const uint64_t q_k = make_desc(smem_u32(sQ + t * TILE_BYTES)), do_k = make_desc(smem_u32(sdO + t * TILE_BYTES));
                     const uint64_t q_mn = make_desc_mn(smem_u32(sQ + t * TILE_BYTES), TILE_BYTES);
                     const uint64_t do_mn = make_desc_mn(smem_u32(sdO + t * TILE_BYTES), TILE_BYTES);
@@ -677,14 +680,12 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __gri
                     if (j == 0 && i > 0) mbar_wait(&bar_q_free, (uint32_t)(i - 1) & 1);   // dQ of the previous unit was read out
                     tc_fence_after();
                     if (elect_one()) {
-#pragma unroll
-                        for (int k = 0; k < 8; ++k)      // 16 queries per step = 2048 bytes of the query-row-major tiles
+                        // rows / columns of P and dS beyond the real queries / keys are never written: their steps are skipped
+                        for (int k = 0; k < qt; ++k)     // 16 queries per step = 2048 bytes of the query-row-major tiles
                             umma_ss(tmem_base + B_DV, p_mn + (uint64_t)(128 * k), do_mn + (uint64_t)(128 * k), idesc_kv, (t | k) != 0);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k)
+                        for (int k = 0; k < qt; ++k)
                             umma_ss(tmem_base + B_DK, ds_mn + (uint64_t)(128 * k), q_mn + (uint64_t)(128 * k), idesc_kv, (t | k) != 0);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k)      // 16 keys per step: 32 bytes inside a 64-key sub-tile of dS, 2048 bytes of K
+                        for (int k = 0; k < kj; ++k)     // 16 keys per step: 32 bytes inside a 64-key sub-tile of dS, 2048 bytes of K
                             umma_ss(tmem_base + B_DQ + (uint32_t)(64 * t), (k < 4 ? ds_k0 : ds_k1) + (uint64_t)(2 * (k & 3)),
                                     k_mn + (uint64_t)(128 * k), idesc_q, (j | k) != 0);
                         umma_commit(&bar_free);
@@ -736,8 +737,11 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __gri
                     if (it > 0) mbar_wait(&bar_free, (it - 1) & 1);      // the MMAs that read the previous P / dS have retired
                     tc_fence_after();
                     const float lr = lse[t], Dr = Dv[t];
+                    const int ncol = ((min(128, L - 128 * j) + 15) >> 4) * 16;       // S / dP columns the MMAs produced
+                    const int nrow = ((min(128, L - 128 * t) + 15) >> 4) * 16;       // P / dS rows the MMAs will read
+                    const int nc = quarter * 32 < nrow ? (ncol + 31) >> 5 : 0;       // warp-uniform: nothing to do for padding rows
 #pragma unroll 1
-                    for (int c = 0; c < 4; ++c) {
+                    for (int c = 0; c < nc; ++c) {
                         uint32_t vs[32], vp[32];
                         tmem_ld32_issue(lane_base + B_S + (uint32_t)(c * 32), vs);
                         tmem_ld32(lane_base + B_DP + (uint32_t)(c * 32), vp);        // waits for both loads
@@ -747,10 +751,10 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __gri
                         for (int e = 0; e < 32; e += 2) {
                             float p0 = fast_exp2(fmaf(__uint_as_float(vs[e]), sl2, -lr));
                             float p1 = fast_exp2(fmaf(__uint_as_float(vs[e + 1]), sl2, -lr));
-                            if (key0 + e >= L) p0 = 0.f;
-                            if (key0 + e + 1 >= L) p1 = 0.f;
-                            const float s0 = p0 * (__uint_as_float(vp[e]) - Dr) * 0.125f;
-                            const float s1 = p1 * (__uint_as_float(vp[e + 1]) - Dr) * 0.125f;
+                            float s0 = p0 * (__uint_as_float(vp[e]) - Dr) * 0.125f;
+                            float s1 = p1 * (__uint_as_float(vp[e + 1]) - Dr) * 0.125f;
+                            if (key0 + e >= L) { p0 = 0.f; s0 = 0.f; }          // select, not multiply: the columns may be stale
+                            if (key0 + e + 1 >= L) { p1 = 0.f; s1 = 0.f; }
                             __nv_bfloat162 hp = __floats2bfloat162_rn(p0, p1), hs = __floats2bfloat162_rn(s0, s1);
                             pk[e >> 1] = *reinterpret_cast<uint32_t *>(&hp);
                             dk[e >> 1] = *reinterpret_cast<uint32_t *>(&hs);
