@@ -59,7 +59,7 @@ SIGNATURES = {
     "ec_gemm_splitk_choose": ([_i, _i, _i], _i),
     "ec_gemm_bf16_tn_splitk": ([_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp], _i),
     "ec_gemm_bf16_splitk": ([_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp], _i),
-    "ec_layernorm_bwd": ([_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _vp, _i64, _vp], _i),
+    "ec_layernorm_bwd": ([_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _vp, _i64, _vp, _vp], _i),
     "ec_quickgelu": ([_vp, _vp, _i64, _vp], _i),
     "ec_quickgelu_bwd": ([_vp, _vp, _vp, _i64, _vp], _i),
     "ec_transpose_bf16": ([_vp, _vp, _i, _i, _i64, _i64, _vp], _i),

@@ -6,15 +6,66 @@
 
 namespace {
 
-// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma ; one warp per row; dx is ADDED to `acc` when given
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma ; one warp per row; dx is ADDED to `acc` when given.
+// VPL > 0: the row (x and g) stays in registers, VPL float4 per lane (d == 128 * VPL): every global load is issued before
+// the first reduction.  VPL == 0: generic three-pass version.  dx_bf16 (optional): bf16 copy of dx, the A operand of the
+// next data-gradient GEMM.
+template <int VPL>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float *__restrict__ x, int64_t x_stride,
                                                             const float *__restrict__ dy, const float *__restrict__ gamma,
                                                             const float *__restrict__ acc, int64_t acc_stride, int M, int d,
-                                                            float *__restrict__ dx, int64_t dx_stride)
+                                                            float *__restrict__ dx, int64_t dx_stride, __nv_bfloat16 *__restrict__ dxb)
 {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= M) return;
     const float *xr = x + (size_t)row * x_stride, *dr = dy + (size_t)row * d;
+    if (VPL > 0) {
+        float4 xv[VPL > 0 ? VPL : 1], gv[VPL > 0 ? VPL : 1], av[VPL > 0 ? VPL : 1];
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            xv[i] = *reinterpret_cast<const float4 *>(xr + c);
+            gv[i] = *reinterpret_cast<const float4 *>(dr + c);
+            av[i] = acc ? *reinterpret_cast<const float4 *>(acc + (size_t)row * acc_stride + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
+        const float mean = ec::warp_sum(s) / (float)d;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            xv[i].x -= mean; xv[i].y -= mean; xv[i].z -= mean; xv[i].w -= mean;
+            q += xv[i].x * xv[i].x + xv[i].y * xv[i].y + xv[i].z * xv[i].z + xv[i].w * xv[i].w;
+        }
+        const float rstd = rsqrtf(ec::warp_sum(q) / (float)d + 1e-5f);
+        float sg = 0.f, sgx = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const float4 gm = *reinterpret_cast<const float4 *>(gamma + (i * 32 + lane) * 4);
+            gv[i].x *= gm.x; gv[i].y *= gm.y; gv[i].z *= gm.z; gv[i].w *= gm.w;
+            xv[i].x *= rstd; xv[i].y *= rstd; xv[i].z *= rstd; xv[i].w *= rstd;          // xhat
+            sg += (gv[i].x + gv[i].y) + (gv[i].z + gv[i].w);
+            sgx += gv[i].x * xv[i].x + gv[i].y * xv[i].y + gv[i].z * xv[i].z + gv[i].w * xv[i].w;
+        }
+        sg = ec::warp_sum(sg) / (float)d; sgx = ec::warp_sum(sgx) / (float)d;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            float4 o;
+            o.x = rstd * (gv[i].x - sg - xv[i].x * sgx) + av[i].x;
+            o.y = rstd * (gv[i].y - sg - xv[i].y * sgx) + av[i].y;
+            o.z = rstd * (gv[i].z - sg - xv[i].z * sgx) + av[i].z;
+            o.w = rstd * (gv[i].w - sg - xv[i].w * sgx) + av[i].w;
+            *reinterpret_cast<float4 *>(dx + (size_t)row * dx_stride + c) = o;
+            if (dxb) {
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
+                uint2 pk; pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
+                *reinterpret_cast<uint2 *>(dxb + (size_t)row * d + c) = pk;
+            }
+        }
+        return;
+    }
     float s = 0.f;
     for (int c = lane; c < d; c += 32) s += xr[c];
     const float mean = ec::warp_sum(s) / (float)d;
@@ -32,6 +83,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float *__restr
         float v = rstd * (g - sg - xh * sgx);
         if (acc) v += acc[(size_t)row * acc_stride + c];
         dx[(size_t)row * dx_stride + c] = v;
+        if (dxb) dxb[(size_t)row * d + c] = __float2bfloat16(v);
     }
 }
 
@@ -400,11 +452,31 @@ __global__ void __launch_bounds__(256) patch_rows_bf16_kernel(const float *__res
 }  // namespace
 
 extern "C" int ec_layernorm_bwd(const float *x, int64_t x_stride, const float *dy, const float *gamma, const float *acc,
-                                int64_t acc_stride, int M, int d, float *dx, int64_t dx_stride, void *stream)
+                                int64_t acc_stride, int M, int d, float *dx, int64_t dx_stride, void *dx_bf16, void *stream)
 {
     EC_REQUIRE(x && dy && gamma && dx && M > 0 && d > 0, "ec_layernorm_bwd: bad arguments");
-    layernorm_bwd_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, x_stride, dy, gamma, acc, acc_stride, M, d, dx,
-                                                                        dx_stride);
+    const dim3 grid((M + 7) / 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    __nv_bfloat16 *dxb = (__nv_bfloat16 *)dx_bf16;
+    const bool vec = d % 128 == 0 && d <= 1024 && x_stride % 4 == 0 && dx_stride % 4 == 0 && (!acc || acc_stride % 4 == 0) &&
+                     (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)gamma | (uintptr_t)dx | (uintptr_t)acc) & 15) == 0 &&
+                     ((uintptr_t)dxb & 7) == 0;
+#define EC_LNB(V) layernorm_bwd_kernel<V><<<grid, 256, 0, st>>>(x, x_stride, dy, gamma, acc, acc_stride, M, d, dx, dx_stride, dxb)
+    if (vec) {
+        switch (d / 128) {
+            case 1: EC_LNB(1); break;
+            case 2: EC_LNB(2); break;
+            case 3: EC_LNB(3); break;
+            case 4: EC_LNB(4); break;
+            case 5: EC_LNB(5); break;
+            case 6: EC_LNB(6); break;
+            case 7: EC_LNB(7); break;
+            default: EC_LNB(8); break;
+        }
+    } else {
+        EC_LNB(0);
+    }
+#undef EC_LNB
     EC_CUDA_CHECK(cudaGetLastError());
     return EC_OK;
 }

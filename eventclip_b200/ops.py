@@ -304,15 +304,15 @@ def l2norm_rows(x):
 
 
 # ------------------------------------------------------------------------------------------------ fine-tune step
-def layernorm_bwd(x, dy, gamma, M, d, acc=None, x_stride=None, dx=None, dx_stride=None, acc_stride=None):
-    """dx = (acc +) LayerNorm'(x) . dy; strides let ln_post touch only the class-token rows."""
+def layernorm_bwd(x, dy, gamma, M, d, acc=None, x_stride=None, dx=None, dx_stride=None, acc_stride=None, dx_bf16=None):
+    """dx = (acc +) LayerNorm'(x) . dy; strides let ln_post touch only the class-token rows; dx_bf16: optional bf16 copy."""
     _dev(x, torch.float32, "x")
     _dev(dy, torch.float32, "dy")
     if dx is None:
         dx = torch.empty((M, d), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         L.check(L.load().ec_layernorm_bwd(_ptr(x), int(x_stride or d), _ptr(dy), _ptr(gamma), _ptr(acc), int(acc_stride or d),
-                                          M, d, _ptr(dx), int(dx_stride or d), _stream()), "ec_layernorm_bwd")
+                                          M, d, _ptr(dx), int(dx_stride or d), _ptr(dx_bf16), _stream()), "ec_layernorm_bwd")
     return dx
 
 

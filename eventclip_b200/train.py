@@ -134,14 +134,14 @@ def encoder_backward(vis, ctx, d_feats, dest=None):
     lngrad(vis.ln_post, ctx["x_last"], d_cls, n_img, x_stride=Ltok * d)
     dx = torch.zeros((M, d), dtype=torch.float32, device=dev)
     ops.layernorm_bwd(ctx["x_last"], d_cls, pk["ln_post"][0], n_img, d, x_stride=Ltok * d, dx=dx, dx_stride=Ltok * d)
+    dxb = ops.f32_to_bf16(dx)
     for i in range(len(saved) - 1, first - 1, -1):
         b, blk = pk["blocks"][i], blocks[i]
         x, h1, qkv, att, x2, h2, a, g, lse = saved[i]
         saved[i] = None
         W, lora_in, ib, oW, ob, lora_out = _attn_parts(blk.attn)
         fc, pj = blk.mlp.c_fc, blk.mlp.c_proj
-        # MLP:  x3 = x2 + c_proj(QuickGELU(c_fc(ln_2(x2))))
-        dxb = ops.f32_to_bf16(dx)
+        # MLP:  x3 = x2 + c_proj(QuickGELU(c_fc(ln_2(x2))));  dxb = bf16 copy of dx (written by the previous LayerNorm backward)
         if _req(pj.weight):
             wgrad(pj.weight, dxb, g)
         if _req(pj.bias):
@@ -154,10 +154,10 @@ def encoder_backward(vis, ctx, d_feats, dest=None):
             bgrad(fc.bias, da)
         dh2 = ops.gemm_bf16(da, b["w_fc_t"], None, "f32")                    # [M, d]
         lngrad(blk.ln_2, x2, dh2, M)
-        dx2 = ops.layernorm_bwd(x2, dh2, b["ln2"][0], M, d, acc=dx)
+        dx2b = torch.empty((M, d), dtype=torch.bfloat16, device=dev)
+        dx2 = ops.layernorm_bwd(x2, dh2, b["ln2"][0], M, d, acc=dx, dx_bf16=dx2b)
         del dg, da, dh2, a, g, h2
         # attention:  x2 = x + out_proj(attn(in_proj(ln_1(x))))
-        dx2b = ops.f32_to_bf16(dx2, dst=dxb)
         d_att = ops.gemm_bf16(dx2b, b["w_out_t"], None, "bf16")              # [M, d]
         if _req(ob):
             bgrad(ob, dx2)
@@ -184,7 +184,7 @@ def encoder_backward(vis, ctx, d_feats, dest=None):
             dh1 = ops.gemm_bf16(dqkv, b["w_in_t"], None, "f32")
             lngrad(blk.ln_1, x, dh1, M)
             if i > first or bottom:                                          # nothing trainable below the first block otherwise
-                dx = ops.layernorm_bwd(x, dh1, b["ln1"][0], M, d, acc=dx2)
+                dx = ops.layernorm_bwd(x, dh1, b["ln1"][0], M, d, acc=dx2, dx_bf16=dxb)
     ctx["saved"] = None
     if bottom:
         # x = ln_pre(x0),  x0[img, 0] = class_embedding + pos[0],  x0[img, 1 + t] = conv1(patch t) + pos[1 + t]

@@ -214,9 +214,10 @@ EC_API int ec_layernorm_f32(const float *x, const float *gamma, const float *bet
 /* ---- fine-tune step (models/clip_cls_ft.py:214-269; backward the reference leaves to autograd) ------------------ */
 
 /* LayerNorm backward over rows: dx = acc + rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*gamma (eps 1e-5).
- * x fp32 rows with stride x_stride (the LayerNorm input), dy fp32 [M,d]; acc (nullable) fp32 rows added to the result. */
+ * x fp32 rows with stride x_stride (the LayerNorm input), dy fp32 [M,d]; acc (nullable) fp32 rows added to the result;
+ * dx_bf16 (nullable) bf16 [M,d] copy of the result (A operand of the next data-gradient GEMM). */
 EC_API int ec_layernorm_bwd(const float *x, int64_t x_stride, const float *dy, const float *gamma, const float *acc,
-                            int64_t acc_stride, int M, int d, float *dx, int64_t dx_stride, void *stream);
+                            int64_t acc_stride, int M, int d, float *dx, int64_t dx_stride, void *dx_bf16, void *stream);
 
 /* QuickGELU on a saved bf16 pre-activation (training forward keeps it) and its backward; n elements. */
 EC_API int ec_quickgelu(const void *a, void *h, int64_t n, void *stream);

@@ -19,7 +19,7 @@ def rel(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
-@pytest.mark.parametrize("M,d,stride", [(37, 768, None), (5, 1024, 3 * 1024), (64, 256, None)])
+@pytest.mark.parametrize("M,d,stride", [(37, 768, None), (5, 1024, 3 * 1024), (64, 256, None), (33, 200, None), (9, 1280, None)])
 def test_layernorm_bwd(cuda_dev, M, d, stride):
     g = torch.Generator().manual_seed(M)
     rows = stride // d if stride else 1
@@ -30,8 +30,11 @@ def test_layernorm_bwd(cuda_dev, M, d, stride):
     F.layer_norm(x, (d,), gamma, beta).backward(dy)
     dx = ops.layernorm_bwd(xfull.to(cuda_dev), dy.to(cuda_dev), gamma.to(cuda_dev), M, d, x_stride=stride)
     assert rel(dx, x.grad) < 1e-5
-    dx2 = ops.layernorm_bwd(xfull.to(cuda_dev), dy.to(cuda_dev), gamma.to(cuda_dev), M, d, acc=acc.to(cuda_dev), x_stride=stride)
+    dxb = torch.empty((M, d), dtype=torch.bfloat16, device=cuda_dev)
+    dx2 = ops.layernorm_bwd(xfull.to(cuda_dev), dy.to(cuda_dev), gamma.to(cuda_dev), M, d, acc=acc.to(cuda_dev), x_stride=stride,
+                            dx_bf16=dxb)
     assert rel(dx2, x.grad + acc) < 1e-5
+    assert torch.equal(dxb, dx2.to(torch.bfloat16))
 
 
 def test_quickgelu_fwd_bwd(cuda_dev):
