@@ -36,6 +36,8 @@ SIGNATURES = {
     "ec_device_check": ([], _i),
     "ec_plan_frames": ([_vp, _i, _i64, _i, _vp, _i, _vp, _i, _vp, _vp, _ip, _ip], _i),
     "ec_event2img": ([_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "ec_event2img_compact": ([_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "ec_pack_events": ([_vp, _i64, _i, _i, _vp, _vp], _i),
     "ec_event2img_geometry": ([_i, _i, _ip, _ip, _ip], _i),
     "ec_center_events": ([_vp, _vp, _i, _i, _i, _vp], _i),
     "ec_flip_events": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp], _i),

@@ -37,6 +37,7 @@ constexpr int GLUT_N = 32;             // per-frame gray LUT covers pos,neg < 32
 
 struct E2IParams {
     const float4 *events;
+    const uint32_t *events_c;   // compact wire format (row F2): one word per event, see ec_pack_events; NULL = float4 events
     const ec_frame *frames;
     int H, W, RB, CS;
     int flags, out_fmt, patch, ldk, G;
@@ -67,6 +68,13 @@ __device__ __forceinline__ float4 ld_stream(const float4 *p)
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
                  : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p)
+{
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
     return r;
 }
 
@@ -135,7 +143,7 @@ __device__ __forceinline__ unsigned clip8(int v)
 
 
 // KHMAX: compile-time bound on the horizontal taps (5 when upsampling, 11 for 640 -> 298); 0 = dynamic loop.
-template <int KHMAX, bool DBG>
+template <int KHMAX, bool DBG, bool COMPACT>
 __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
 {
     cg::cluster_group cluster = cg::this_cluster();
@@ -230,22 +238,34 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
         const int per = (fr.ev_count + CS - 1) / CS;
         const int e_lo = min(rank * per, fr.ev_count);
         const int n = min(per, fr.ev_count - e_lo);
-        const float4 *ev = p.events + fr.ev_start + e_lo;
+        constexpr bool compact = COMPACT;     // compile-time: the float path keeps its register budget
+        const float4 *ev = p.events + (compact ? 0 : fr.ev_start + e_lo);
+        const uint32_t *evc = p.events_c + (compact ? fr.ev_start + e_lo : 0);
         const int iHW = (int)HW, bandpx = RB * W;
         constexpr int U = 4;   // events in flight per thread: all loads, then all atomics, then the statistics
         for (int base = 0; base < n; base += NT * U) {
             float4 ev4[U];
+            uint32_t wc[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int i = base + u * NT + tid;
-                if (i < n) ev4[u] = ld_stream(ev + i);
+                if (i < n) {
+                    if (compact) wc[u] = ld_stream_u32(evc + i);
+                    else ev4[u] = ld_stream(ev + i);
+                }
             }
             unsigned code[U];   // bit 31: valid, bit 30: positive polarity, low bits: flat pixel index
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int i = base + u * NT + tid;
                 code[u] = 0;
-                if (i < n) {
+                if (i < n && compact) {
+                    // word = flat index (30 bits) | polarity code << 30 (0: p == 0, 1: p > 0, 2: p < 0, 3: index rejected at pack time)
+                    const uint32_t w = wc[u];
+                    const unsigned pc = w >> 30, l = w & 0x3fffffffu;
+                    if (pc == 3u || (pc != 0u && l >= (unsigned)iHW)) flags |= EC_STATUS_BAD_COORD;
+                    else if (pc != 0u) code[u] = 0x80000000u | (pc == 1u ? 0x40000000u : 0u) | l;
+                } else if (i < n) {
                     const float4 e = ev4[u];
                     const int x = __float2int_rz(e.x), y = __float2int_rz(e.y), pol = __float2int_rz(e.w);
                     if (pol != 0) {
@@ -707,15 +727,70 @@ extern "C" int ec_event2img_geometry(int H, int W, int *cluster_size, int *threa
     return EC_OK;
 }
 
+// compact wire format of row F2: word = flat pixel index as np.bincount sees it (x + y*W, 30 bits) | polarity code << 30
+__global__ void __launch_bounds__(256) pack_events_kernel(const float4 *__restrict__ ev, int64_t n, long long HW, int W,
+                                                          uint32_t *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 e = ld_stream(ev + i);
+    const int x = __float2int_rz(e.x), y = __float2int_rz(e.y), pol = __float2int_rz(e.w);
+    uint32_t w = 0;                                    // p == 0: never histogrammed, never range-checked (vis.py:9-14)
+    if (pol != 0) {
+        const long long l = (long long)x + (long long)y * W;
+        w = (l >= 0 && l < HW) ? ((uint32_t)l | (pol > 0 ? 1u << 30 : 2u << 30)) : (3u << 30);
+    }
+    out[i] = w;
+}
+
+static int event2img_impl(const float *events, const uint32_t *events_c, const ec_frame *frames, int n_frames, int H, int W, int flags,
+                          int out_fmt, int patch, int ldk, void *out, int32_t *dbg_counts, uint8_t *dbg_gray, uint8_t *dbg_u8,
+                          int32_t *status, void *stream_);
+
 extern "C" int ec_event2img(const float *events, const ec_frame *frames, int n_frames, int H, int W, int flags,
                             int out_fmt, int patch, int ldk, void *out, int32_t *dbg_counts, uint8_t *dbg_gray,
                             uint8_t *dbg_u8, int32_t *status, void *stream_)
 {
+    if (n_frames > 0) {
+        EC_REQUIRE(events, "ec_event2img: null pointer");
+        EC_REQUIRE(((uintptr_t)events & 15) == 0, "ec_event2img: events must be 16-byte aligned");
+    }
+    return event2img_impl(events, nullptr, frames, n_frames, H, W, flags, out_fmt, patch, ldk, out, dbg_counts, dbg_gray, dbg_u8,
+                          status, stream_);
+}
+
+extern "C" int ec_event2img_compact(const uint32_t *events, const ec_frame *frames, int n_frames, int H, int W, int flags,
+                                    int out_fmt, int patch, int ldk, void *out, int32_t *dbg_counts, uint8_t *dbg_gray,
+                                    uint8_t *dbg_u8, int32_t *status, void *stream_)
+{
+    if (n_frames > 0) {
+        EC_REQUIRE(events, "ec_event2img_compact: null pointer");
+        EC_REQUIRE(((uintptr_t)events & 3) == 0, "ec_event2img_compact: events must be 4-byte aligned");
+        EC_REQUIRE((long long)H * W < (1ll << 30), "ec_event2img_compact: sensor too large for the 30-bit index");
+    }
+    return event2img_impl(nullptr, events, frames, n_frames, H, W, flags, out_fmt, patch, ldk, out, dbg_counts, dbg_gray, dbg_u8,
+                          status, stream_);
+}
+
+extern "C" int ec_pack_events(const float *events, int64_t n_events, int H, int W, uint32_t *out, void *stream)
+{
+    EC_REQUIRE(n_events >= 0 && H > 0 && W > 0 && (long long)H * W < (1ll << 30), "ec_pack_events: bad arguments");
+    if (n_events == 0) return EC_OK;
+    EC_REQUIRE(events && out && ((uintptr_t)events & 15) == 0, "ec_pack_events: null or misaligned pointer");
+    pack_events_kernel<<<(unsigned)((n_events + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4 *>(events), n_events, (long long)H * W, W, out);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
+static int event2img_impl(const float *events, const uint32_t *events_c, const ec_frame *frames, int n_frames, int H, int W, int flags,
+                          int out_fmt, int patch, int ldk, void *out, int32_t *dbg_counts, uint8_t *dbg_gray, uint8_t *dbg_u8,
+                          int32_t *status, void *stream_)
+{
     cudaStream_t stream = (cudaStream_t)stream_;
     EC_REQUIRE(n_frames >= 0, "ec_event2img: n_frames < 0");
     if (n_frames == 0) return EC_OK;
-    EC_REQUIRE(events && frames && out && status, "ec_event2img: null pointer");
-    EC_REQUIRE(((uintptr_t)events & 15) == 0, "ec_event2img: events must be 16-byte aligned");
+    EC_REQUIRE(frames && out && status, "ec_event2img: null pointer");
     EC_REQUIRE(H > 0 && W > 0 && H >= 8 && W >= 8, "ec_event2img: bad sensor shape %dx%d", H, W);
     EC_REQUIRE(out_fmt >= EC_OUT_F32_NCHW && out_fmt <= EC_OUT_BF16_PATCH, "ec_event2img: bad out_fmt %d", out_fmt);
     int G = 0;
@@ -736,6 +811,7 @@ extern "C" int ec_event2img(const float *events, const ec_frame *frames, int n_f
 
     E2IParams p;
     p.events = reinterpret_cast<const float4 *>(events);
+    p.events_c = events_c;
     p.frames = frames;
     p.H = H; p.W = W; p.RB = RB; p.CS = CS;
     p.flags = flags; p.out_fmt = out_fmt; p.patch = patch; p.ldk = ldk; p.G = G;
@@ -745,8 +821,11 @@ extern "C" int ec_event2img(const float *events, const ec_frame *frames, int n_f
     p.band_magic = ((1ull << 40) + (unsigned long long)RB * W - 1) / ((unsigned long long)RB * W);
 
     const bool dbg = dbg_counts || dbg_gray || dbg_u8;
-    auto kern = dbg ? (tb.KH <= 5 ? event2img_kernel<5, true> : (tb.KH <= 11 ? event2img_kernel<11, true> : event2img_kernel<0, true>))
-                    : (tb.KH <= 5 ? event2img_kernel<5, false> : (tb.KH <= 11 ? event2img_kernel<11, false> : event2img_kernel<0, false>));
+    auto kern = events_c
+        ? (dbg ? (tb.KH <= 5 ? event2img_kernel<5, true, true> : (tb.KH <= 11 ? event2img_kernel<11, true, true> : event2img_kernel<0, true, true>))
+               : (tb.KH <= 5 ? event2img_kernel<5, false, true> : (tb.KH <= 11 ? event2img_kernel<11, false, true> : event2img_kernel<0, false, true>)))
+        : (dbg ? (tb.KH <= 5 ? event2img_kernel<5, true, false> : (tb.KH <= 11 ? event2img_kernel<11, true, false> : event2img_kernel<0, true, false>))
+               : (tb.KH <= 5 ? event2img_kernel<5, false, false> : (tb.KH <= 11 ? event2img_kernel<11, false, false> : event2img_kernel<0, false, false>)));
     {
         static std::mutex mu;
         static std::map<std::pair<int, const void *>, size_t> granted;   // the attribute is per device

@@ -59,11 +59,16 @@ def plan_frames(offsets, N, T, sel=None, compact=False):
 
 def event2img(events, frames, shape, n_slots, count_non_zero=False, background_mask=True, out="f32", patch=0,
               ldk=0, out_tensor=None, debug=False, status=None):
-    """Fused frames (ec_event2img).  events: CUDA float32 [E,4]; frames: CUDA uint8 [n_frames,16].
+    """Fused frames (ec_event2img).  events: CUDA float32 [E,4], or CUDA int32 [E] words of the compact wire format
+    (pack_events, row F2); frames: CUDA uint8 [n_frames,16].
     Returns (images, status int32[1] CUDA tensor, debug dict or None)."""
-    _dev(events, torch.float32, "events")
+    compact = events.dtype == torch.int32
+    _dev(events, torch.int32 if compact else torch.float32, "events")
     _dev(frames, torch.uint8, "frames")
-    if events.dim() != 2 or events.shape[1] != 4:
+    if compact:
+        if events.dim() != 1:
+            raise L.ECError("compact events must be a 1-D int32 tensor of packed words")
+    elif events.dim() != 2 or events.shape[1] != 4:
         raise L.ECError("events must be [E, 4] rows of (x, y, t, p)")
     H, W = shape
     n_frames = frames.shape[0]
@@ -89,10 +94,21 @@ def event2img(events, frames, shape, n_slots, count_non_zero=False, background_m
         dbg = dict(counts=dc, gray=dg, u8=du)
     flags = (L.EC_FLAG_COUNT_NON_ZERO if count_non_zero else 0) | (L.EC_FLAG_BACKGROUND_MASK if background_mask else 0)
     with torch.cuda.device(dev):
-        rc = L.load().ec_event2img(_ptr(events), _ptr(frames), n_frames, H, W, flags, fmt, int(patch), int(ldk),
-                                   _ptr(out_tensor), _ptr(dc), _ptr(dg), _ptr(du), _ptr(status), _stream())
+        fn = L.load().ec_event2img_compact if compact else L.load().ec_event2img
+        rc = fn(_ptr(events), _ptr(frames), n_frames, H, W, flags, fmt, int(patch), int(ldk),
+                _ptr(out_tensor), _ptr(dc), _ptr(dg), _ptr(du), _ptr(status), _stream())
     L.check(rc, "ec_event2img")
     return out_tensor, status, dbg
+
+
+def pack_events(events, shape):
+    """float32 [E,4] events -> int32 [E] compact words (ec_pack_events): flat pixel index | polarity code << 30."""
+    _dev(events, torch.float32, "events")
+    H, W = shape
+    out = torch.empty(events.shape[0], dtype=torch.int32, device=events.device)
+    with torch.cuda.device(events.device):
+        L.check(L.load().ec_pack_events(_ptr(events), events.shape[0], H, W, _ptr(out), _stream()), "ec_pack_events")
+    return out
 
 
 def raise_on_status(status):

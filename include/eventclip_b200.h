@@ -91,6 +91,18 @@ EC_API int ec_event2img(const float *events, const ec_frame *frames, int n_frame
                  int out_fmt, int patch, int ldk, void *out, int32_t *dbg_counts, uint8_t *dbg_gray,
                  uint8_t *dbg_u8, int32_t *status, void *stream);
 
+/* Row F2 -- compact event wire format.  One 32-bit word per event: bits [0,30) = the flat pixel index x + y*W exactly as
+ * np.bincount receives it at datasets/vis.py:9-14 (coordinates truncated like .astype(int); x >= W aliasing preserved),
+ * bits [30,32) = polarity code (0: p == 0, ignored by the histogram; 1: p > 0; 2: p < 0; 3: index outside [0, H*W) ->
+ * EC_STATUS_BAD_COORD when consumed).  t is dropped: nothing reads it after the chunking (vis.py:44-52).  4 bytes per
+ * event instead of 16 on the wire and in HBM.  ec_pack_events converts float32 [n,4] rows on the device (after
+ * ec_center_events / ec_flip_events where those apply); ec_event2img_compact is ec_event2img on packed words, with
+ * ec_frame.ev_start / ev_count counting events as before.  Frames are bit-identical to the float path. */
+EC_API int ec_pack_events(const float *events, int64_t n_events, int H, int W, uint32_t *out, void *stream);
+EC_API int ec_event2img_compact(const uint32_t *events, const ec_frame *frames, int n_frames, int H, int W, int flags,
+                                int out_fmt, int patch, int ldk, void *out, int32_t *dbg_counts, uint8_t *dbg_gray,
+                                uint8_t *dbg_u8, int32_t *status, void *stream);
+
 /* DEVICE, in place.  center_events (datasets/utils.py:38-57), applied to every sample before the frames are built
  * (datasets/caltech.py:176): per sample t -= min t, x -= ((x_max + x_min + 1) - W) // 2, y likewise (float32 math).
  *   events device float32 [*,4];  offsets device int64 [B+1] */

@@ -363,6 +363,45 @@ def make_tta():
     print("tta_golden", {k: v.shape for k, v in out.items() if k.startswith("case1")}, "kept", int(keep.sum()))
 
 
+def make_formats():
+    """Row F2: the reference's own loaders (datasets/imagenet.py::load_event, NCaltech101._load_events) on synthetic files
+    written in the two on-disk formats; stores SHA-256 of what they return."""
+    import tempfile
+    import textwrap
+    import types
+    # the dataset modules import nerv at the top; the two loaders are self-contained, so their source is executed alone
+    src = open(os.path.join(ref_import.REF, "datasets", "imagenet.py")).read()
+    ns = {"np": np}
+    exec(src[src.index("def load_event"):src.index("class NImageNet")], ns)
+    imagenet = types.SimpleNamespace(load_event=ns["load_event"])
+    src = open(os.path.join(ref_import.REF, "datasets", "caltech.py")).read().split("\n")
+    i0 = next(i for i, l in enumerate(src) if "def _load_events(event_path):" in l)
+    ns2 = {"np": np}
+    exec(textwrap.dedent("\n".join(src[i0:i0 + 3])), ns2)
+    caltech = types.SimpleNamespace(NCaltech101=types.SimpleNamespace(_load_events=ns2["_load_events"]))
+    out = []
+    with tempfile.TemporaryDirectory() as td:
+        for seed, (E, pol01) in enumerate([(5000, True), (777, False), (20000, True)]):
+            rng = np.random.default_rng(900 + seed)
+            rec = np.zeros(E, dtype=[("x", "<u2"), ("y", "<u2"), ("t", "<i8"), ("p", "?" if pol01 else "<i2")])
+            rec["x"], rec["y"] = rng.integers(0, 640, E), rng.integers(0, 480, E)
+            rec["t"] = np.sort(rng.integers(0, 55000, E))
+            rec["p"] = rng.integers(0, 2, E) if pol01 else rng.choice([-1, 1], E)
+            path = os.path.join(td, f"s{seed}.npz")
+            np.savez(path, event_data=rec)
+            ref = imagenet.load_event(path)
+            out.append(dict(kind="npz", seed=900 + seed, E=E, pol01=pol01, dtype=str(ref.dtype), sha=sha(ref)))
+        for seed, E in enumerate([3000, 1]):
+            rng = np.random.default_rng(950 + seed)
+            arr = np.stack([rng.integers(0, 240, E), rng.integers(0, 180, E), np.sort(rng.random(E)), rng.choice([-1, 1], E)], 1)
+            path = os.path.join(td, f"c{seed}.npy")
+            np.save(path, arr)                                                    # float64 on disk
+            ref = caltech.NCaltech101._load_events(path)
+            out.append(dict(kind="npy", seed=950 + seed, E=E, dtype=str(ref.dtype), sha=sha(ref)))
+    json.dump(out, open(os.path.join(HERE, "formats_sha.json"), "w"), indent=1)
+    print("formats", len(out))
+
+
 if __name__ == "__main__":
     assert ref_import.available(), "/root/reference is required to (re)generate the golden fixtures"
     vis = ref_import.load_vis()
@@ -373,4 +412,5 @@ if __name__ == "__main__":
     make_event_transforms()
     make_ft_train()
     make_tta()
+    make_formats()
     print("sizes:", {f: os.path.getsize(os.path.join(HERE, f)) for f in sorted(os.listdir(HERE)) if not f.endswith(".py")})
