@@ -20,6 +20,7 @@
 #include <cooperative_groups.h>
 
 #include <map>
+#include <tuple>
 #include <mutex>
 #include <vector>
 #include <cmath>
@@ -39,6 +40,7 @@ struct E2IParams {
     const float4 *events;
     const uint32_t *events_c;   // compact wire format (row F2): one word per event, see ec_pack_events; NULL = float4 events
     const ec_frame *frames;
+    int n_frames;
     int H, W, RB, CS;
     int flags, out_fmt, patch, ldk, G;
     void *out;
@@ -152,8 +154,7 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
     const int lane = tid & 31, wid = tid >> 5, nwarps = NT >> 5;
     const int CS = p.CS;
     const int rank = blockIdx.x % CS;
-    const int fid = blockIdx.x / CS;
-    const ec_frame fr = p.frames[fid];
+    const int n_clusters = gridDim.x / CS;        // persistent: each cluster walks over frames fid, fid + n_clusters, ...
     const int H = p.H, W = p.W, RB = p.RB;
     const int y0 = rank * RB;
     const int rows = max(0, min(H, y0 + RB) - y0);
@@ -195,6 +196,8 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
         for (int i = tid; i < OUT / 2; i += NT) { xpq[i] = (short)((2 * i) / P); xpr[i] = (short)((2 * i) % P); }
     }
 
+    for (int fid = blockIdx.x / CS; fid < p.n_frames; fid += n_clusters) {
+    const ec_frame fr = p.frames[fid];
     // ---- padding frame: the reference pads missing views with zeros (event2img.py:89-91) ----
     if (fr.ev_count <= 0) {
         const int slot = fr.out_slot;
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
                 for (size_t i = b + tid; i < e; i += NT) o[i] = __float2bfloat16(0.f);
             }
         }
-        return;
+        continue;     // uniform across the cluster; the previous frame ended with a cluster barrier
     }
 
     // ---- P0: clear the band's bins (16-byte stores; the buffer is padded to 16 bytes) ----
@@ -313,6 +316,20 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
                 }
             }
             s2 += s2p;
+        }
+    }
+    // while this frame is reduced, resampled and stored, pull this CTA's slice of the NEXT frame's events into L2
+    if (fid + n_clusters < p.n_frames) {
+        const ec_frame nx = p.frames[fid + n_clusters];
+        if (nx.ev_count > 0) {
+            const int per = (nx.ev_count + CS - 1) / CS;
+            const int e_lo = min(rank * per, nx.ev_count);
+            const int n = min(per, nx.ev_count - e_lo);
+            const char *b = COMPACT ? reinterpret_cast<const char *>(p.events_c + nx.ev_start + e_lo)
+                                    : reinterpret_cast<const char *>(p.events + nx.ev_start + e_lo);
+            const long long bytes = (long long)n * (COMPACT ? 4 : 16);
+            for (long long o = (long long)tid * 128; o < bytes; o += (long long)NT * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(b + o));
         }
     }
     // block reduction of the partials
@@ -574,7 +591,8 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
             }
         }
     }
-    cluster.sync();   // peers may still be reading this CTA's hrow
+    cluster.sync();   // peers may still be reading this CTA's hrow; also fences the shared state for the next frame
+    }   // frame loop
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -813,6 +831,7 @@ static int event2img_impl(const float *events, const uint32_t *events_c, const e
     p.events = reinterpret_cast<const float4 *>(events);
     p.events_c = events_c;
     p.frames = frames;
+    p.n_frames = n_frames;
     p.H = H; p.W = W; p.RB = RB; p.CS = CS;
     p.flags = flags; p.out_fmt = out_fmt; p.patch = patch; p.ldk = ldk; p.G = G;
     p.out = out; p.dbg_counts = dbg_counts; p.dbg_gray = dbg_gray; p.dbg_u8 = dbg_u8; p.status = status;
@@ -847,6 +866,27 @@ static int event2img_impl(const float *events, const uint32_t *events_c, const e
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
+    // persistent: as many clusters as the device holds at once; each walks over the frames with that stride
+    {
+        static std::mutex mu2;
+        static std::map<std::tuple<int, const void *, int, size_t>, int> resident;
+        std::lock_guard<std::mutex> lk(mu2);
+        int dev_id = 0;
+        EC_CUDA_CHECK(cudaGetDevice(&dev_id));
+        int &nc = resident[std::make_tuple(dev_id, (const void *)kern, NT, smem)];
+        if (nc == 0) {
+            cudaLaunchConfig_t q = cfg;
+            q.gridDim = dim3((unsigned)(ec::sm_count() * 8));     // any multiple of the cluster size
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess || n <= 0) {
+                cudaGetLastError();
+                n = ec::sm_count() / CS;
+            }
+            static const int force = getenv("EC_E2I_CLUSTERS") ? atoi(getenv("EC_E2I_CLUSTERS")) : 0;
+            nc = force > 0 ? force : n;
+        }
+        if (n_frames > nc) cfg.gridDim = dim3((unsigned)nc * CS);
+    }
     EC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
     return EC_OK;
 }
