@@ -58,6 +58,7 @@ SIGNATURES = {
     "ec_gather_rows": ([_vp, _vp, _vp, _i, _i, _vp], _i),
     "ec_l2norm_rows": ([_vp, _vp, _i, _i, _vp], _i),
     # fine-tune step
+    "ec_gemm_timing": ([_vp, _i], _i),
     "ec_gemm_splitk_choose": ([_i, _i, _i], _i),
     "ec_gemm_bf16_tn_splitk": ([_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp], _i),
     "ec_gemm_bf16_splitk": ([_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp], _i),

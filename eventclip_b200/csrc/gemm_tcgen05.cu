@@ -48,6 +48,7 @@ struct GemmParams {
     uint32_t tx_bytes;    // bytes landing per stage (A box + W box)
     int splits;           // split-K (EC_EPI_F32 only): tile index = split * tiles_m * tiles_n + tile; partial sums go to
     int kb_per_split;     //   out + split * M * ldo, each covering kb_per_split 64-wide K blocks
+    unsigned long long *stamp;   // optional {start, end} %globaltimer stamps of this launch (ec_gemm_timing)
     int mn_major;         // 1: operands are [K, M] / [K, N] row-major (reduction index = row): MN-major UMMA operands, tiles
                           //    arrive as boxes of 64 (m or n) x 64 (k), one 8 KB box per 64 rows of the tile
 };
@@ -325,6 +326,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     if (CG == 2) cluster_sync_all();     // the peer's barriers are initialised before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
+    if (p.stamp && blockIdx.x == 0 && threadIdx.x == 0) {       // first CTA: start of the launch (overwritten by every replay)
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.stamp[0] = t;
+    }
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -675,6 +681,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     tc_fence_before();
     __syncthreads();
     if (CG == 2) cluster_sync_all();     // no signal may target a CTA that has already exited
+    if (p.stamp && threadIdx.x == 0) {   // every CTA: the latest exit is the end of the launch (time is monotonic across replays)
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMax(p.stamp + 1, t);
+    }
     if (warp == 1) {
         tc_fence_after();
         if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -779,6 +790,12 @@ int launch(const CUtensorMap &ma, const CUtensorMap &mw, const CUtensorMap &mo, 
     return EC_OK;
 }
 
+// ec_gemm_timing: when a buffer is registered, launch i of ec_gemm_bf16 (since registration) records its device-side start
+// and end times (%globaltimer, ns) in buf[2i], buf[2i+1] -- also when the launch is a node of a replayed CUDA graph, where
+// events cannot be placed.  Used by bench.py to time the GEMMs inside the timed region.
+unsigned long long *g_stamp_buf = nullptr;
+int g_stamp_cap = 0, g_stamp_next = 0;
+
 // out[m, n] = sum_s ws[s, m, n] in a fixed order (split-K partial sums)
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float4 *__restrict__ ws, int splits, int64_t mn4, int n4, int ldo4,
                                                             float4 *__restrict__ out)
@@ -803,6 +820,15 @@ extern "C" int ec_gemm_bf16(const void *A, int lda, const void *W, int ldw, cons
                             int epi, void *out, int ldo, const float *res, int row_map, void *stream_)
 {
     return gemm_impl(A, lda, W, ldw, bias, M, N, K, epi, out, ldo, res, row_map, 1, (cudaStream_t)stream_);
+}
+
+extern "C" int ec_gemm_timing(uint64_t *buf, int capacity)
+{
+    EC_REQUIRE(capacity >= 0 && (buf || capacity == 0), "ec_gemm_timing: bad arguments");
+    g_stamp_buf = reinterpret_cast<unsigned long long *>(buf);
+    g_stamp_cap = buf ? capacity : 0;
+    g_stamp_next = 0;
+    return EC_OK;
 }
 
 extern "C" int ec_gemm_splitk_choose(int M, int N, int K)
@@ -909,6 +935,7 @@ int gemm_impl(const void *A, int lda, const void *W, int ldw, const float *bias,
     GemmParams p;
     p.M = M; p.N = N; p.K = K; p.epi = epi; p.out = out; p.ldo = ldo; p.bias = bias; p.res = res; p.row_map = row_map;
     p.mn_major = mn_major;
+    p.stamp = (g_stamp_buf && g_stamp_next < g_stamp_cap) ? g_stamp_buf + 2 * (g_stamp_next++) : nullptr;
     p.tx_bytes = (uint32_t)(box_a + box_w) * BK * 2 * CG;   // a pair's leader barrier collects both CTAs' bytes
     {
         const int num_kb = (K + BK - 1) / BK;

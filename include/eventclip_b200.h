@@ -135,6 +135,11 @@ EC_API int ec_event2img_geometry(int H, int W, int *cluster_size, int *threads, 
 EC_API int ec_gemm_bf16(const void *A, int lda, const void *W, int ldw, const float *bias, int M, int N, int K,
                  int epi, void *out, int ldo, const float *res, int row_map, void *stream);
 
+/* Measurement hook (bench.py's roofline): after ec_gemm_timing(buf, capacity) the i-th following GEMM launch (i < capacity)
+ * writes its device-side start / end time (%globaltimer, ns) to buf[2i], buf[2i+1] -- also as a node of a replayed CUDA
+ * graph, where events cannot be recorded.  buf: device uint64 [2*capacity], zeroed by the caller; NULL disables. */
+EC_API int ec_gemm_timing(uint64_t *buf, int capacity);
+
 /* Split-K variant for weight-gradient shapes (small M x N, long K = tokens): out fp32 [M,ldo] = A[M,K] . W[N,K]^T with the
  * K range cut into `splits` parts that run as separate tiles and are summed in a fixed order (deterministic).
  * workspace: device fp32 [splits * M * N] (unused when splits == 1).  ec_gemm_splitk_choose returns the split count that
