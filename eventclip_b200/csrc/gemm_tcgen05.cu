@@ -257,6 +257,19 @@ __device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, u
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// bias[col .. col+3] for the whole warp (same address in every lane: one broadcast load, L1-resident); zeros past N
+__device__ __forceinline__ float4 bias4(const float *bias, int col, int N)
+{
+    if (bias && col + 3 < N) return __ldg(reinterpret_cast<const float4 *>(bias + col));
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) {
+        if (col < N) b.x = bias[col];
+        if (col + 1 < N) b.y = bias[col + 1];
+        if (col + 2 < N) b.z = bias[col + 2];
+    }
+    return b;
+}
+
 __device__ __forceinline__ float quick_gelu(float x)
 {
     // x * sigmoid(1.702 x) with sigmoid(y) = 0.5 tanh(y/2) + 0.5: one SFU op (MUFU.TANH) per element instead of
@@ -450,18 +463,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll 1
                 for (int c = 0; c < NCHUNK; ++c) {
                     const int col0 = colw + c * 32;
-                    // lane j holds the bias of column col0 + j; broadcast by shuffle below
-                    float bl = 0.f;
-                    if (p.bias && col0 + lane < p.N) bl = p.bias[col0 + lane];
+                    float4 bq[8];                            // the 32 biases of this chunk: 8 broadcast loads
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) bq[q] = bias4(p.bias, col0 + 4 * q, p.N);
                     tmem_ld_wait();
                     uint32_t pk[16];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        float f0 = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bl, j);
-                        float f1 = __uint_as_float(v[j + 1]) + __shfl_sync(0xffffffffu, bl, j + 1);
-                        if (p.epi == EC_EPI_BF16_QGELU) { f0 = quick_gelu(f0); f1 = quick_gelu(f1); }
-                        __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
-                        pk[j >> 1] = *reinterpret_cast<uint32_t *>(&h);
+                    for (int q = 0; q < 8; ++q) {
+                        const float f0 = __uint_as_float(v[4 * q]) + bq[q].x, f1 = __uint_as_float(v[4 * q + 1]) + bq[q].y;
+                        const float f2 = __uint_as_float(v[4 * q + 2]) + bq[q].z, f3 = __uint_as_float(v[4 * q + 3]) + bq[q].w;
+                        __nv_bfloat162 h0, h1;
+                        if (p.epi == EC_EPI_BF16_QGELU) {
+                            h0 = __floats2bfloat162_rn(quick_gelu(f0), quick_gelu(f1));
+                            h1 = __floats2bfloat162_rn(quick_gelu(f2), quick_gelu(f3));
+                        } else {
+                            h0 = __floats2bfloat162_rn(f0, f1);
+                            h1 = __floats2bfloat162_rn(f2, f3);
+                        }
+                        pk[2 * q] = *reinterpret_cast<uint32_t *>(&h0);
+                        pk[2 * q + 1] = *reinterpret_cast<uint32_t *>(&h1);
                     }
                     if (c + 1 < NCHUNK) tmem_ld32_issue(tbase + (uint32_t)((c + 1) * 32), v);   // overlaps the store below
                     const uint32_t box = stg + (nbox & 1) * 2048;
@@ -514,8 +534,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll 1
                 for (int c = 0; c < NCHUNK; ++c) {
                     const int col0 = colw + c * 32;
-                    float bl = 0.f;
-                    if (p.bias && col0 + lane < p.N) bl = p.bias[col0 + lane];
+                    float4 bq[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) bq[q] = bias4(p.bias, col0 + 4 * q, p.N);
                     // prefetch the next residual box (next chunk, or first chunk of this CTA's next tile)
                     if (lane == 0) {
                         bulk_wait_read<0>();     // the store that last used the other buffer has finished reading it
@@ -531,10 +552,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     for (int q = 0; q < 8; ++q) {
                         const uint32_t a = rowaddr + ((q ^ sw) << 4);
                         float4 r = lds128(a);
-                        r.x += __uint_as_float(v[4 * q]) + __shfl_sync(0xffffffffu, bl, 4 * q);
-                        r.y += __uint_as_float(v[4 * q + 1]) + __shfl_sync(0xffffffffu, bl, 4 * q + 1);
-                        r.z += __uint_as_float(v[4 * q + 2]) + __shfl_sync(0xffffffffu, bl, 4 * q + 2);
-                        r.w += __uint_as_float(v[4 * q + 3]) + __shfl_sync(0xffffffffu, bl, 4 * q + 3);
+                        r.x += __uint_as_float(v[4 * q]) + bq[q].x;
+                        r.y += __uint_as_float(v[4 * q + 1]) + bq[q].y;
+                        r.z += __uint_as_float(v[4 * q + 2]) + bq[q].z;
+                        r.w += __uint_as_float(v[4 * q + 3]) + bq[q].w;
                         sts128(a, r.x, r.y, r.z, r.w);
                     }
                     if (c + 1 < NCHUNK) tmem_ld32_issue(tbase + (uint32_t)((c + 1) * 32), v);
