@@ -293,3 +293,59 @@ def test_graphed_step_matches_eager(cuda_dev):
         assert torch.equal(eager.flat_g, graphed.flat_g)
         assert torch.equal(eager.flat_p, graphed.flat_p), step
     assert len(gt.cache) == 2
+
+
+def test_ragged_views_fused_vs_autograd_and_graph_refresh(cuda_dev):
+    """Samples with one and with two valid views in the same batch (padded slots): the fused FineTuner, the autograd route
+    and the graph replay agree bitwise, and a second batch with the SAME counts but a different padding pattern reuses the
+    captured graph through the refreshed static plan."""
+    from eventclip_b200.graph import GraphedFineTuner
+    ds = "n_caltech101"
+    cfg = SENSORS[ds]
+    q = dict(max_imgs=2, N=cfg["N"], split_method="event_count", convert_method="event_histogram", grayscale=True,
+             count_non_zero=cfg["count_non_zero"], background_mask=cfg["background_mask"])
+    text = clip_oracle.synth_text_feats(cfg["n_cls"], 64, 8)
+
+    def make():
+        torch.manual_seed(0)
+        m = clip.init_weights_(clip.CLIP(ARCH), seed=9).to(cuda_dev).eval()
+        cd = dict(clip_model=m, prompt="a {}", class_names=None, agg_func="mean", lora="qkvo-4", only_conv1=False,
+                  only_bias=False, only_ln=False, text_feats=text)
+        ft = FTCLIPClassifier(adapter_dict=dict(adapter_type="text-identity", residual=True), clip_dict=cd,
+                              loss_dict=dict(use_logits_loss=True, use_probs_loss=False)).to(cuda_dev)
+        ft.attach_event_frontend(q, cfg["shape"], cfg["max_n"])
+        gen = torch.Generator().manual_seed(5)
+        with torch.no_grad():
+            for n, p in ft.named_parameters():
+                if "lora" in n:
+                    p.copy_((0.05 * torch.randn(p.shape, generator=gen)).to(cuda_dev))
+        return ft.train()
+
+    def batch(pattern, seed):
+        """pattern[b] = number of valid views of sample b (1: E = N, 2: E = 2N)."""
+        evs = [synth_batch(ds, 1, seed + b, kind="clustered", E=cfg["N"] * v)[0] for b, v in enumerate(pattern)]
+        off = np.concatenate([[0], np.cumsum([len(e) for e in evs])]).astype(np.int64)
+        return torch.from_numpy(np.concatenate(evs)).to(cuda_dev), off
+
+    labels = torch.tensor([1, 0, 1, 1, 0])
+    ft_a, ft_e, ft_g = make(), make(), make()
+    eager = train.FineTuner(ft_e, lr=1e-3)
+    gt = GraphedFineTuner(train.FineTuner(ft_g, lr=1e-3), max_events=5 * 2 * cfg["N"])
+    for step, pattern in enumerate(([2, 1, 2, 1, 1], [1, 1, 2, 2, 1])):        # 7 valid views either way
+        ev, off = batch(pattern, 500 + 10 * step)
+        if step == 0:
+            out = ft_a(dict(events=ev, event_offsets=torch.from_numpy(off)))
+            assert out["valid_masks"].sum().item() == 7 and out["valid_masks"].shape == (5, 2)
+            la = ft_a.calc_train_loss(dict(label=labels), out)["ce_loss"]
+            la.backward()
+        le = eager.step(ev, off, labels).clone()
+        lg = gt.step(ev, off, labels).clone()
+        if step == 0:
+            assert torch.equal(la.detach().reshape(1), le)
+            pa = dict(ft_a.named_parameters())
+            for n, p in ft_e.named_parameters():
+                if p.requires_grad:
+                    assert torch.equal(eager._grad_view(p), pa[n].grad), n
+        assert torch.equal(le, lg), (step, le.item(), lg.item())
+        assert torch.equal(eager.flat_p, gt.tuner.flat_p)
+    assert len(gt.cache) == 1
