@@ -30,7 +30,12 @@ def _static_plan(model, plan, dev):
 
 
 def _refresh_plan(static, plan):
-    """Copies a new host plan of the same counts into the static device tensors (async from pinned memory)."""
+    """Copies a new host plan of the same counts into the static device tensors (async from pinned memory); nothing is
+    copied when the plan equals the one already on the device (fixed-geometry streams)."""
+    sig = (plan["frames"].numpy().tobytes(), plan["valid_u8"].numpy().tobytes())
+    if static.get("_sig") == sig:
+        return
+    static["_sig"] = sig
     pin = lambda t: t if (t.is_pinned() or not torch.cuda.is_available()) else t.pin_memory()
     B, T = plan["B"], plan["T"]
     static["frames"].copy_(pin(plan["frames"]), non_blocking=True)
