@@ -15,3 +15,7 @@ run ln 300 tests/test_encoder_gpu.py -m gpu -k "layernorm"
 run attn 300 tests/test_encoder_gpu.py -m gpu -k "test_attention"
 run enc 600 tests/test_encoder_gpu.py -m gpu -k "encoder"
 run cls 600 tests/test_classifiers_gpu.py -m gpu
+run train_kernels 600 tests/test_train_kernels_gpu.py -m gpu
+run train 900 tests/test_train_gpu.py -m gpu
+run tta 300 tests/test_tta.py -m gpu
+run formats 300 tests/test_formats.py -m gpu
