@@ -53,6 +53,10 @@ struct E2IParams {
     const int32_t *vy;   // [224][2+KV]: lo, cnt, taps  (cropped output rows)
     const float *nlut;   // [3][256] normalise LUT
     int KH, KV;
+    // tensor-core resample (single-CTA frames, W % 4 == 0): int8 A fragments of the tap tables split into three signed
+    // base-256 digits, [14 tiles][KS][3 digits][32 lanes][4 regs]; ws = first source column / row of each 16-output tile
+    const int32_t *fragH, *fragV, *wsH, *wsV;
+    int KSH, KSV, imma;
 };
 
 struct Part {            // per-CTA partial statistics exchanged over DSMEM
@@ -135,6 +139,22 @@ __device__ __noinline__ unsigned gray_px(unsigned pos, unsigned neg, unsigned mx
         img = __dadd_rn(__dmul_rn(img, w), __dmul_rn(255.0, __dsub_rn(1.0, w)));
     }
     return (unsigned)__double2int_rn(img);   // np.round: half to even
+}
+
+// D (s32, 16x8) += A (s8 coefficient digits, 16x32, row) . B (u8 pixels, 32x8, col)
+__device__ __forceinline__ void imma_s8u8(int (&c)[4], const uint4 &a, uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+
+// clamp to [0, 255] in one instruction
+__device__ __forceinline__ unsigned sat8(int v)
+{
+    unsigned r;
+    asm("cvt.sat.u8.s32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
 }
 
 __device__ __forceinline__ unsigned clip8(int v)
@@ -447,6 +467,109 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
     }
     __syncthreads();
 
+    // ---- P5 / P6 on the tensor cores (single-CTA frames): both Pillow passes are banded matrix products
+    //        hT[xo][y]   = clip8((sum_x kh[xo][x] gray[y][x]  + 2^21) >> 22)      A = kh digits, B = gray rows (as stored)
+    //        out[yo][xo] = clip8((sum_y kv[yo][y] hT[xo][y]   + 2^21) >> 22)      A = kv digits, B = hT (transposed rows)
+    //      The 22-bit coefficients are split into three signed base-256 digits; pixel * digit sums are exact in int32 and
+    //      recombine to exactly Pillow's integer accumulator (mma.sync m16n8k32 s8 x u8).  A 16-output tile reads a
+    //      32*KS-wide source window starting at a multiple of 4. ----
+    const int HP = (H + 3) & ~3;                 // row pitch of the transposed intermediate
+    if (p.imma) {
+        const int g = lane >> 2, tig = lane & 3;
+        uint8_t *hT = hrow;
+        {
+            const int n_tiles = (rows + 7) >> 3, n_chunks = (n_tiles + 3) >> 2;
+            for (int item = wid; item < (OUT / 16) * n_chunks; item += nwarps) {
+                const int mt = item / n_chunks, ch = item - mt * n_chunks;
+                const int ws = __ldg(p.wsH + mt);
+                uint4 a[3];          // one K step (32 source columns) covers a 16-column tile when upsampling
+#pragma unroll
+                for (int dg = 0; dg < 3; ++dg) a[dg] = __ldg(reinterpret_cast<const uint4 *>(p.fragH) + (mt * 3 + dg) * 32 + lane);
+                const int nt0 = ch * 4, nt_end = min(n_tiles, nt0 + 4);
+                const uint8_t *src = gray + (nt0 * 8 + g) * W + ws + tig * 4;
+                uint8_t *dst = hT + (mt * 16 + g) * HP + nt0 * 8 + tig * 2;
+                int y0 = nt0 * 8 + tig * 2;
+                for (int nt = nt0; nt < nt_end; ++nt, src += 8 * W, dst += 8, y0 += 8) {
+                    int c[3][4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { c[0][e] = 1 << (PREC - 1); c[1][e] = 0; c[2][e] = 0; }   // rounding term rides in digit 0
+                    const uint32_t b0 = *reinterpret_cast<const uint32_t *>(src);
+                    const uint32_t b1 = *reinterpret_cast<const uint32_t *>(src + 16);
+#pragma unroll
+                    for (int dg = 0; dg < 3; ++dg) imma_s8u8(c[dg], a[dg], b0, b1);
+                    unsigned px[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) px[e] = sat8((c[0][e] + (c[1][e] << 8) + (c[2][e] << 16)) >> PREC);
+                    if (y0 < HP) {
+                        *reinterpret_cast<uint16_t *>(dst) = (uint16_t)(px[0] | (px[1] << 8));
+                        *reinterpret_cast<uint16_t *>(dst + 8 * HP) = (uint16_t)(px[2] | (px[3] << 8));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        {
+            uint8_t *du = (DBG && p.dbg_u8) ? p.dbg_u8 + (size_t)fid * OUT * OUT : nullptr;
+            const int slot = fr.out_slot;
+            constexpr int n_chunks = (OUT / 8) / 4;       // 28 column tiles in chunks of 4
+            const int esz = p.out_fmt == EC_OUT_F32_NCHW ? 4 : 2;
+            for (int item = wid; item < (OUT / 16) * n_chunks; item += nwarps) {
+                const int mt = item / n_chunks, ch = item - mt * n_chunks;
+                const int ws = __ldg(p.wsV + mt);
+                uint4 a[3];
+#pragma unroll
+                for (int dg = 0; dg < 3; ++dg) a[dg] = __ldg(reinterpret_cast<const uint4 *>(p.fragV) + (mt * 3 + dg) * 32 + lane);
+                // byte pointers of this thread's two output rows (yo0, yo0 + 8), channel 0; channel stride in bytes
+                const int yo0 = mt * 16 + g;
+                char *rowp[2];
+                size_t cstride;
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const int yo = yo0 + 8 * r;
+                    size_t eoff;
+                    if (p.out_fmt == EC_OUT_BF16_PATCH) eoff = ((size_t)slot * p.G * p.G + (size_t)ypq[yo] * p.G) * p.ldk + ypr[yo] * p.patch;
+                    else eoff = (((size_t)slot * 3) * OUT + yo) * OUT;
+                    rowp[r] = (char *)p.out + eoff * esz;
+                }
+                cstride = (p.out_fmt == EC_OUT_BF16_PATCH ? (size_t)p.patch * p.patch : (size_t)OUT * OUT) * esz;
+                const int nt0 = ch * 4;
+                const uint8_t *src = hT + (nt0 * 8 + g) * HP + ws + tig * 4;
+                for (int nt = nt0; nt < nt0 + 4; ++nt, src += 8 * HP) {
+                    int c[3][4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { c[0][e] = 1 << (PREC - 1); c[1][e] = 0; c[2][e] = 0; }
+                    const uint32_t b0 = *reinterpret_cast<const uint32_t *>(src);
+                    const uint32_t b1 = *reinterpret_cast<const uint32_t *>(src + 16);
+#pragma unroll
+                    for (int dg = 0; dg < 3; ++dg) imma_s8u8(c[dg], a[dg], b0, b1);
+                    unsigned px[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) px[e] = sat8((c[0][e] + (c[1][e] << 8) + (c[2][e] << 16)) >> PREC);
+                    const int xo = nt * 8 + tig * 2;
+                    const size_t coff = (p.out_fmt == EC_OUT_BF16_PATCH ? (size_t)xpq[xo >> 1] * p.ldk + xpr[xo >> 1] : (size_t)xo) * esz;
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const unsigned pa = px[2 * r], pb = px[2 * r + 1];
+                        if (du) *reinterpret_cast<uint16_t *>(du + (yo0 + 8 * r) * OUT + xo) = (uint16_t)(pa | (pb << 8));
+                        char *o = rowp[r] + coff;
+                        if (p.out_fmt == EC_OUT_F32_NCHW) {
+                            *reinterpret_cast<float2 *>(o) = make_float2(nlut[pa], nlut[pb]);
+                            *reinterpret_cast<float2 *>(o + cstride) = make_float2(nlut[256 + pa], nlut[256 + pb]);
+                            *reinterpret_cast<float2 *>(o + 2 * cstride) = make_float2(nlut[512 + pa], nlut[512 + pb]);
+                        } else {
+                            const uint2 ta = nlut3[pa], tb = nlut3[pb];
+                            *reinterpret_cast<unsigned *>(o) = __byte_perm(ta.x, tb.x, 0x5410);
+                            *reinterpret_cast<unsigned *>(o + cstride) = __byte_perm(ta.x, tb.x, 0x7632);
+                            *reinterpret_cast<unsigned *>(o + 2 * cstride) = __byte_perm(ta.y, tb.y, 0x5410);
+                        }
+                    }
+                }
+            }
+        }
+        cluster.sync();
+        continue;      // next frame
+    }
+
     // ---- P5: horizontal Pillow pass, one thread per cropped output column, taps in registers ----
     {
         const int RG = NT / OUT;
@@ -647,10 +770,62 @@ int build_axis(int in, int out, int first, std::vector<int32_t> &tab)
 }
 
 struct Tables {
-    int32_t *dev = nullptr;   // hx | vy | nlut(float bits)
+    int32_t *dev = nullptr;   // hx | vy | nlut(float bits) | fragH | fragV | wsH | wsV
     int KH = 0, KV = 0;
     size_t off_vy = 0, off_lut = 0;
+    size_t off_fragH = 0, off_fragV = 0, off_wsH = 0, off_wsV = 0;
+    int KSH = 0, KSV = 0;
 };
+
+// signed base-256 digits of a Pillow coefficient (|k| < 2^23): k = d0 + 256 d1 + 65536 d2, each in [-128, 127]
+void digits3(int32_t k, int d[3])
+{
+    d[0] = ((k + 128) & 255) - 128;
+    const int32_t k1 = (k - d[0]) >> 8;
+    d[1] = ((k1 + 128) & 255) - 128;
+    d[2] = (k1 - d[1]) >> 8;
+}
+
+// A fragments of mma.sync.m16n8k32 (row-major s8) for every 16-output tile of an axis table (lo, cnt, taps):
+// register q of lane l holds A[row = l/4 + 8*(q&1)][k = (l%4)*4 + 16*(q>>1) .. +3], lowest k in the lowest byte.
+// Returns the K steps (32 source positions each) a tile needs, or 0 when a coefficient does not fit three digits.
+int build_frags(const std::vector<int32_t> &axis, int ksize, std::vector<int32_t> &frag, std::vector<int32_t> &ws)
+{
+    const int stride = 2 + ksize, tiles = OUT / 16;
+    ws.assign(tiles, 0);
+    int KS = 1;
+    for (int mt = 0; mt < tiles; ++mt) {
+        int lo_min = 1 << 30, hi = 0;
+        for (int r = 0; r < 16; ++r) {
+            const int32_t *row = axis.data() + (size_t)(mt * 16 + r) * stride;
+            lo_min = std::min(lo_min, (int)row[0]);
+            hi = std::max(hi, (int)(row[0] + row[1]));
+        }
+        ws[mt] = lo_min & ~3;
+        KS = std::max(KS, (hi - ws[mt] + 31) / 32);
+    }
+    frag.assign((size_t)tiles * KS * 3 * 32 * 4, 0);
+    for (int mt = 0; mt < tiles; ++mt)
+        for (int ks = 0; ks < KS; ++ks)
+            for (int lane = 0; lane < 32; ++lane)
+                for (int q = 0; q < 4; ++q) {
+                    const int r = lane / 4 + 8 * (q & 1);
+                    const int32_t *row = axis.data() + (size_t)(mt * 16 + r) * stride;
+                    uint32_t w[3] = {0, 0, 0};
+                    for (int b = 0; b < 4; ++b) {
+                        const int src = ws[mt] + ks * 32 + (lane % 4) * 4 + 16 * (q >> 1) + b;
+                        int32_t k = 0;
+                        if (src >= row[0] && src < row[0] + row[1]) k = row[2 + src - row[0]];
+                        if (k <= -(1 << 23) || k >= (1 << 23)) return 0;
+                        int d[3];
+                        digits3(k, d);
+                        for (int dg = 0; dg < 3; ++dg) w[dg] |= (uint32_t)(d[dg] & 255) << (8 * b);
+                    }
+                    for (int dg = 0; dg < 3; ++dg)
+                        frag[((((size_t)mt * KS + ks) * 3 + dg) * 32 + lane) * 4 + q] = (int32_t)w[dg];
+                }
+    return KS;
+}
 
 std::mutex g_mu;
 std::map<std::tuple<int, int, int>, Tables> g_tables;
@@ -691,6 +866,16 @@ int get_tables(int H, int W, cudaStream_t stream, Tables &out)
             memcpy(&bits, &rf, 4);
             all.push_back(bits);
         }
+    {
+        std::vector<int32_t> fh, fv, wh, wv;
+        t.KSH = build_frags(hx, t.KH, fh, wh);
+        t.KSV = build_frags(vy, t.KV, fv, wv);
+        while (all.size() % 4) all.push_back(0);      // fragments are read as 16-byte vectors
+        t.off_fragH = all.size(); all.insert(all.end(), fh.begin(), fh.end());
+        t.off_fragV = all.size(); all.insert(all.end(), fv.begin(), fv.end());
+        t.off_wsH = all.size(); all.insert(all.end(), wh.begin(), wh.end());
+        t.off_wsV = all.size(); all.insert(all.end(), wv.begin(), wv.end());
+    }
     EC_CUDA_CHECK(cudaMalloc(&t.dev, all.size() * sizeof(int32_t)));
     EC_CUDA_CHECK(cudaMemcpyAsync(t.dev, all.data(), all.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
     EC_CUDA_CHECK(cudaStreamSynchronize(stream));   // one-time table upload; `all` is a stack-lifetime buffer
@@ -837,6 +1022,12 @@ static int event2img_impl(const float *events, const uint32_t *events_c, const e
     p.out = out; p.dbg_counts = dbg_counts; p.dbg_gray = dbg_gray; p.dbg_u8 = dbg_u8; p.status = status;
     p.hx = tb.dev; p.vy = tb.dev + tb.off_vy; p.nlut = reinterpret_cast<const float *>(tb.dev + tb.off_lut);
     p.KH = tb.KH; p.KV = tb.KV;
+    p.fragH = tb.dev + tb.off_fragH; p.fragV = tb.dev + tb.off_fragV; p.wsH = tb.dev + tb.off_wsH; p.wsV = tb.dev + tb.off_wsV;
+    p.KSH = tb.KSH; p.KSV = tb.KSV;
+    {
+        static const bool off = getenv("EC_E2I_IMMA") && atoi(getenv("EC_E2I_IMMA")) == 0;    // 0 forces the SIMT resample
+        p.imma = !off && CS == 1 && W % 4 == 0 && H >= 48 && tb.KSH == 1 && tb.KSV == 1;
+    }
     p.band_magic = ((1ull << 40) + (unsigned long long)RB * W - 1) / ((unsigned long long)RB * W);
 
     const bool dbg = dbg_counts || dbg_gray || dbg_u8;
