@@ -56,7 +56,8 @@ struct E2IParams {
     // tensor-core resample (single-CTA frames, W % 4 == 0): int8 A fragments of the tap tables split into three signed
     // base-256 digits, [14 tiles][KS][3 digits][32 lanes][4 regs]; ws = first source column / row of each 16-output tile
     const int32_t *fragH, *fragV, *wsH, *wsV;
-    int KSH, KSV, imma;
+    int KSH, KSV;
+    int gray_off;   // tensor-core kernel: byte offset of the gray plane in dynamic shared memory
 };
 
 struct Part {            // per-CTA partial statistics exchanged over DSMEM
@@ -141,20 +142,12 @@ __device__ __noinline__ unsigned gray_px(unsigned pos, unsigned neg, unsigned mx
     return (unsigned)__double2int_rn(img);   // np.round: half to even
 }
 
-// D (s32, 16x8) += A (s8 coefficient digits, 16x32, row) . B (u8 pixels, 32x8, col)
-__device__ __forceinline__ void imma_s8u8(int (&c)[4], const uint4 &a, uint32_t b0, uint32_t b1)
+// D (s32, 16x8) = A (s8 coefficient digits, 16x32, row) . B (u8 pixels, 32x8, col) + C (same value in all four slots)
+__device__ __forceinline__ void imma_s8u8(int (&d)[4], const uint4 &a, uint32_t b0, uint32_t b1, int c)
 {
-    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
-                 : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
-}
-
-// clamp to [0, 255] in one instruction
-__device__ __forceinline__ unsigned sat8(int v)
-{
-    unsigned r;
-    asm("cvt.sat.u8.s32 %0, %1;" : "=r"(r) : "r"(v));
-    return r;
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+                 : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1), "r"(c));
 }
 
 __device__ __forceinline__ unsigned clip8(int v)
@@ -163,6 +156,138 @@ __device__ __forceinline__ unsigned clip8(int v)
     return (unsigned)min(max(v, 0), 255);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// P1 shared by both kernels: event scan with returning shared-memory atomics
+// ------------------------------------------------------------------------------------------------
+struct ScanAcc {
+    unsigned long long s2;   // sum over events of 2c+1 (c = count before the increment) = sum of squared counts
+    unsigned nnz, nacc, mall, flags;
+};
+
+// One round = 128 consecutive events per warp, 4 per lane (lane-contiguous 512-byte loads at immediate offsets):
+// all loads, then the decode, then all atomics, then the statistics from the values the atomics returned.
+// An event becomes (flat bin index l, increment): 1 = positive field, 65536 = negative field, 0 = not histogrammed.
+template <bool COMPACT, bool MULTI, bool TAIL>
+__device__ __forceinline__ void scan_round(const float4 *ev, const uint32_t *evc, int rem, int W, unsigned uHW_fast, unsigned uHW,
+                                           long long HW, uint32_t hist_s, unsigned long long magic, unsigned bandpx, ScanAcc &acc)
+{
+    constexpr int U = 4;
+    float4 ev4[U];
+    uint32_t wc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        ev4[u] = make_float4(0.f, 0.f, 0.f, 0.f);      // a missing tail event decodes to "add 0 to bin 0"
+        wc[u] = 0;
+        if (!TAIL || u * 32 < rem) {
+            if (COMPACT) wc[u] = ld_stream_u32(evc + u * 32);
+            else ev4[u] = ld_stream(ev + u * 32);
+        }
+    }
+    unsigned l[U], inc[U], old[U];
+    int xs[U], ys[U];
+    bool ok[U], all_ok = true;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (COMPACT) {
+            // word = flat index (30 bits) | polarity code << 30 (0: p == 0, 1: p > 0, 2: p < 0, 3: index rejected at pack time)
+            const unsigned pc = wc[u] >> 30;
+            l[u] = wc[u] & 0x3fffffffu;
+            inc[u] = pc == 1u ? 1u : (pc == 2u ? 65536u : 0u);
+            ok[u] = pc != 3u && l[u] < uHW;
+        } else {
+            // .astype(int) truncates: trunc(p) != 0 <=> |p| >= 1 (vis.py:44-52); a NaN polarity is dropped like p == 0
+            xs[u] = __float2int_rz(ev4[u].x); ys[u] = __float2int_rz(ev4[u].y);
+            inc[u] = ev4[u].w >= 1.0f ? 1u : (ev4[u].w <= -1.0f ? 65536u : 0u);
+            l[u] = (unsigned)(ys[u] * W + xs[u]);      // flat index as np.bincount sees it; exact in 32 bits for x, y, W < 2^15
+            ok[u] = (unsigned)(xs[u] | ys[u]) < 32768u && l[u] < uHW_fast;
+        }
+        all_ok = all_ok && ok[u];
+    }
+    if (!all_ok) {      // rare: negative / huge coordinates (the flat index may still be in range), rejected words
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (ok[u]) continue;
+            bool good = false;
+            if (!COMPACT) {
+                const long long i64 = (long long)xs[u] + (long long)ys[u] * W;
+                good = i64 >= 0 && i64 < HW;
+                l[u] = (unsigned)i64;
+            }
+            if (!good) {
+                // p == 0 events are never indexed by the reference; a rejected compact word was a p != 0 event
+                if (COMPACT ? (wc[u] >> 30) != 0u : inc[u] != 0u) acc.flags |= EC_STATUS_BAD_COORD;
+                inc[u] = 0; l[u] = 0;
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        uint32_t addr;
+        old[u] = 0;
+        if (TAIL && inc[u] == 0u) continue;     // full rounds add 0 to bin 0 instead (no divergence); a tail would hammer that bin
+        if (MULTI) {
+            // route the event to the CTA that owns its sensor row: one distributed-shared-memory atomic
+            const unsigned owner = (unsigned)(((unsigned long long)l[u] * magic) >> 40);   // l / (RB*W), exact for l < 2^24
+            const uint32_t local = hist_s + 4u * (l[u] - owner * bandpx);
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(addr) : "r"(local), "r"(owner));
+            asm volatile("atom.shared::cluster.add.u32 %0, [%1], %2;" : "=r"(old[u]) : "r"(addr), "r"(inc[u]) : "memory");
+        } else {
+            addr = hist_s + 4u * l[u];
+            asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old[u]) : "r"(addr), "r"(inc[u]) : "memory");
+        }
+    }
+    // adding 1 to a field holding c raises sum(c^2) by 2c+1 and the non-empty count by [c == 0]
+    const bool all_valid = inc[0] && inc[1] && inc[2] && inc[3];
+    if (__all_sync(0xffffffffu, all_valid)) {
+        unsigned cs = 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned c = __byte_perm(old[u], 0u, inc[u] == 1u ? 0x4410u : 0x4432u);
+            cs += c;
+            acc.nnz += c == 0u;
+            acc.mall = max(acc.mall, c + 1u);          // 65536 here means the 16-bit field wrapped
+        }
+        acc.s2 += 2u * cs + U;                         // <= 4 * (2*65535 + 1): no 32-bit overflow within one round
+        acc.nacc += U;
+    } else {
+        unsigned s2p = 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned c = __byte_perm(old[u], 0u, inc[u] == 1u ? 0x4410u : 0x4432u);
+            const unsigned v = inc[u] != 0u;
+            s2p += (2u * c + 1u) * v;
+            acc.nnz += (c == 0u) & v;
+            acc.mall = max(acc.mall, (c + 1u) * v);
+            acc.nacc += v;
+        }
+        acc.s2 += s2p;
+    }
+}
+
+// CTA `rank` of a CS-CTA cluster scans its 1/CS slice of the frame's events
+template <bool COMPACT, bool MULTI>
+__device__ __forceinline__ void scan_events(const E2IParams &p, const ec_frame &fr, int rank, int CS, uint32_t *hist, int tid, int NT,
+                                            ScanAcc &acc)
+{
+    const int per = (fr.ev_count + CS - 1) / CS;
+    const int e_lo = min(rank * per, fr.ev_count);
+    const int n = min(per, fr.ev_count - e_lo);
+    const long long HW = (long long)p.H * p.W;
+    const unsigned uHW = HW > 0x7fffffffll ? 0x7fffffffu : (unsigned)HW;
+    const unsigned uHW_fast = p.W < 32768 ? uHW : 0u;      // wider sensors take the 64-bit index path
+    const uint32_t hist_s = (uint32_t)__cvta_generic_to_shared(hist);
+    const unsigned bandpx = (unsigned)(p.RB * p.W);
+    const int first = (tid >> 5) * 128 + (tid & 31);       // this lane's first event of a round
+    const float4 *ev = p.events + (COMPACT ? 0 : fr.ev_start + e_lo + first);
+    const uint32_t *evc = p.events_c + (COMPACT ? fr.ev_start + e_lo + first : 0);
+    const int step = NT * 4;
+    int base = 0;
+    for (; base + step <= n; base += step, ev += step, evc += step)
+        scan_round<COMPACT, MULTI, false>(ev, evc, 0, p.W, uHW_fast, uHW, HW, hist_s, p.band_magic, bandpx, acc);
+    if (base < n)
+        scan_round<COMPACT, MULTI, true>(ev, evc, n - base - first, p.W, uHW_fast, uHW, HW, hist_s, p.band_magic, bandpx, acc);
+}
 
 // KHMAX: compile-time bound on the horizontal taps (5 when upsampling, 11 for 640 -> 298); 0 = dynamic loop.
 template <int KHMAX, bool DBG, bool COMPACT>
@@ -257,86 +382,11 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
     unsigned long long s2 = 0;
     unsigned nnz = 0, nacc = 0, mall = 0, flags = 0;
     {
-        // this CTA's slice of the frame's events
-        const int per = (fr.ev_count + CS - 1) / CS;
-        const int e_lo = min(rank * per, fr.ev_count);
-        const int n = min(per, fr.ev_count - e_lo);
-        constexpr bool compact = COMPACT;     // compile-time: the float path keeps its register budget
-        const float4 *ev = p.events + (compact ? 0 : fr.ev_start + e_lo);
-        const uint32_t *evc = p.events_c + (compact ? fr.ev_start + e_lo : 0);
-        const int iHW = (int)HW, bandpx = RB * W;
-        constexpr int U = 4;   // events in flight per thread: all loads, then all atomics, then the statistics
-        for (int base = 0; base < n; base += NT * U) {
-            float4 ev4[U];
-            uint32_t wc[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int i = base + u * NT + tid;
-                if (i < n) {
-                    if (compact) wc[u] = ld_stream_u32(evc + i);
-                    else ev4[u] = ld_stream(ev + i);
-                }
-            }
-            unsigned code[U];   // bit 31: valid, bit 30: positive polarity, low bits: flat pixel index
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int i = base + u * NT + tid;
-                code[u] = 0;
-                if (i < n && compact) {
-                    // word = flat index (30 bits) | polarity code << 30 (0: p == 0, 1: p > 0, 2: p < 0, 3: index rejected at pack time)
-                    const uint32_t w = wc[u];
-                    const unsigned pc = w >> 30, l = w & 0x3fffffffu;
-                    if (pc == 3u || (pc != 0u && l >= (unsigned)iHW)) flags |= EC_STATUS_BAD_COORD;
-                    else if (pc != 0u) code[u] = 0x80000000u | (pc == 1u ? 0x40000000u : 0u) | l;
-                } else if (i < n) {
-                    const float4 e = ev4[u];
-                    const int x = __float2int_rz(e.x), y = __float2int_rz(e.y), pol = __float2int_rz(e.w);
-                    if (pol != 0) {
-                        // flat index as np.bincount sees it; 32-bit math when it provably cannot overflow
-                        unsigned l;
-                        bool ok;
-                        if (((unsigned)x | (unsigned)y) < 32768u && W < 32768) {
-                            l = (unsigned)(y * W + x);
-                            ok = l < (unsigned)iHW;
-                        } else {
-                            const long long i64 = (long long)x + (long long)y * W;
-                            ok = i64 >= 0 && i64 < HW;
-                            l = (unsigned)i64;
-                        }
-                        if (ok) code[u] = 0x80000000u | (pol > 0 ? 0x40000000u : 0u) | l;
-                        else flags |= EC_STATUS_BAD_COORD;
-                    }
-                }
-            }
-            uint32_t old[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                old[u] = 0;
-                if (code[u] & 0x80000000u) {
-                    unsigned l = code[u] & 0x3fffffffu;
-                    uint32_t *dst = hist;
-                    if (CS > 1) {
-                        const unsigned owner = (unsigned)(((unsigned long long)l * p.band_magic) >> 40);   // l / (RB*W), exact for l < 2^24
-                        l -= owner * (unsigned)bandpx;
-                        dst = cluster.map_shared_rank(hist, owner);
-                    }
-                    old[u] = atomicAdd(dst + l, (code[u] & 0x40000000u) ? 1u : 65536u);
-                }
-            }
-            unsigned s2p = 0;   // <= 4 * (2*65535 + 1): no 32-bit overflow within one round
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (code[u] & 0x80000000u) {
-                    const uint32_t c = (code[u] & 0x40000000u) ? (old[u] & 0xffffu) : (old[u] >> 16);
-                    if (c == 0xffffu) flags |= EC_STATUS_COUNT_OVERFLOW;   // the 16-bit field wraps
-                    s2p += 2u * c + 1u;
-                    nnz += (c == 0);
-                    mall = max(mall, c + 1);
-                    ++nacc;
-                }
-            }
-            s2 += s2p;
-        }
+        ScanAcc acc = {0, 0, 0, 0, 0};
+        if (CS > 1) scan_events<COMPACT, true>(p, fr, rank, CS, hist, tid, NT, acc);
+        else scan_events<COMPACT, false>(p, fr, 0, 1, hist, tid, NT, acc);
+        s2 = acc.s2; nnz = acc.nnz; nacc = acc.nacc; mall = acc.mall; flags = acc.flags;
+        if (mall > 0xffffu) flags |= EC_STATUS_COUNT_OVERFLOW;     // a 16-bit field wrapped
     }
     // while this frame is reduced, resampled and stored, pull this CTA's slice of the NEXT frame's events into L2
     if (fid + n_clusters < p.n_frames) {
@@ -466,109 +516,6 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
         }
     }
     __syncthreads();
-
-    // ---- P5 / P6 on the tensor cores (single-CTA frames): both Pillow passes are banded matrix products
-    //        hT[xo][y]   = clip8((sum_x kh[xo][x] gray[y][x]  + 2^21) >> 22)      A = kh digits, B = gray rows (as stored)
-    //        out[yo][xo] = clip8((sum_y kv[yo][y] hT[xo][y]   + 2^21) >> 22)      A = kv digits, B = hT (transposed rows)
-    //      The 22-bit coefficients are split into three signed base-256 digits; pixel * digit sums are exact in int32 and
-    //      recombine to exactly Pillow's integer accumulator (mma.sync m16n8k32 s8 x u8).  A 16-output tile reads a
-    //      32*KS-wide source window starting at a multiple of 4. ----
-    const int HP = (H + 3) & ~3;                 // row pitch of the transposed intermediate
-    if (p.imma) {
-        const int g = lane >> 2, tig = lane & 3;
-        uint8_t *hT = hrow;
-        {
-            const int n_tiles = (rows + 7) >> 3, n_chunks = (n_tiles + 3) >> 2;
-            for (int item = wid; item < (OUT / 16) * n_chunks; item += nwarps) {
-                const int mt = item / n_chunks, ch = item - mt * n_chunks;
-                const int ws = __ldg(p.wsH + mt);
-                uint4 a[3];          // one K step (32 source columns) covers a 16-column tile when upsampling
-#pragma unroll
-                for (int dg = 0; dg < 3; ++dg) a[dg] = __ldg(reinterpret_cast<const uint4 *>(p.fragH) + (mt * 3 + dg) * 32 + lane);
-                const int nt0 = ch * 4, nt_end = min(n_tiles, nt0 + 4);
-                const uint8_t *src = gray + (nt0 * 8 + g) * W + ws + tig * 4;
-                uint8_t *dst = hT + (mt * 16 + g) * HP + nt0 * 8 + tig * 2;
-                int y0 = nt0 * 8 + tig * 2;
-                for (int nt = nt0; nt < nt_end; ++nt, src += 8 * W, dst += 8, y0 += 8) {
-                    int c[3][4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) { c[0][e] = 1 << (PREC - 1); c[1][e] = 0; c[2][e] = 0; }   // rounding term rides in digit 0
-                    const uint32_t b0 = *reinterpret_cast<const uint32_t *>(src);
-                    const uint32_t b1 = *reinterpret_cast<const uint32_t *>(src + 16);
-#pragma unroll
-                    for (int dg = 0; dg < 3; ++dg) imma_s8u8(c[dg], a[dg], b0, b1);
-                    unsigned px[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) px[e] = sat8((c[0][e] + (c[1][e] << 8) + (c[2][e] << 16)) >> PREC);
-                    if (y0 < HP) {
-                        *reinterpret_cast<uint16_t *>(dst) = (uint16_t)(px[0] | (px[1] << 8));
-                        *reinterpret_cast<uint16_t *>(dst + 8 * HP) = (uint16_t)(px[2] | (px[3] << 8));
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        {
-            uint8_t *du = (DBG && p.dbg_u8) ? p.dbg_u8 + (size_t)fid * OUT * OUT : nullptr;
-            const int slot = fr.out_slot;
-            constexpr int n_chunks = (OUT / 8) / 4;       // 28 column tiles in chunks of 4
-            const int esz = p.out_fmt == EC_OUT_F32_NCHW ? 4 : 2;
-            for (int item = wid; item < (OUT / 16) * n_chunks; item += nwarps) {
-                const int mt = item / n_chunks, ch = item - mt * n_chunks;
-                const int ws = __ldg(p.wsV + mt);
-                uint4 a[3];
-#pragma unroll
-                for (int dg = 0; dg < 3; ++dg) a[dg] = __ldg(reinterpret_cast<const uint4 *>(p.fragV) + (mt * 3 + dg) * 32 + lane);
-                // byte pointers of this thread's two output rows (yo0, yo0 + 8), channel 0; channel stride in bytes
-                const int yo0 = mt * 16 + g;
-                char *rowp[2];
-                size_t cstride;
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const int yo = yo0 + 8 * r;
-                    size_t eoff;
-                    if (p.out_fmt == EC_OUT_BF16_PATCH) eoff = ((size_t)slot * p.G * p.G + (size_t)ypq[yo] * p.G) * p.ldk + ypr[yo] * p.patch;
-                    else eoff = (((size_t)slot * 3) * OUT + yo) * OUT;
-                    rowp[r] = (char *)p.out + eoff * esz;
-                }
-                cstride = (p.out_fmt == EC_OUT_BF16_PATCH ? (size_t)p.patch * p.patch : (size_t)OUT * OUT) * esz;
-                const int nt0 = ch * 4;
-                const uint8_t *src = hT + (nt0 * 8 + g) * HP + ws + tig * 4;
-                for (int nt = nt0; nt < nt0 + 4; ++nt, src += 8 * HP) {
-                    int c[3][4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) { c[0][e] = 1 << (PREC - 1); c[1][e] = 0; c[2][e] = 0; }
-                    const uint32_t b0 = *reinterpret_cast<const uint32_t *>(src);
-                    const uint32_t b1 = *reinterpret_cast<const uint32_t *>(src + 16);
-#pragma unroll
-                    for (int dg = 0; dg < 3; ++dg) imma_s8u8(c[dg], a[dg], b0, b1);
-                    unsigned px[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) px[e] = sat8((c[0][e] + (c[1][e] << 8) + (c[2][e] << 16)) >> PREC);
-                    const int xo = nt * 8 + tig * 2;
-                    const size_t coff = (p.out_fmt == EC_OUT_BF16_PATCH ? (size_t)xpq[xo >> 1] * p.ldk + xpr[xo >> 1] : (size_t)xo) * esz;
-#pragma unroll
-                    for (int r = 0; r < 2; ++r) {
-                        const unsigned pa = px[2 * r], pb = px[2 * r + 1];
-                        if (du) *reinterpret_cast<uint16_t *>(du + (yo0 + 8 * r) * OUT + xo) = (uint16_t)(pa | (pb << 8));
-                        char *o = rowp[r] + coff;
-                        if (p.out_fmt == EC_OUT_F32_NCHW) {
-                            *reinterpret_cast<float2 *>(o) = make_float2(nlut[pa], nlut[pb]);
-                            *reinterpret_cast<float2 *>(o + cstride) = make_float2(nlut[256 + pa], nlut[256 + pb]);
-                            *reinterpret_cast<float2 *>(o + 2 * cstride) = make_float2(nlut[512 + pa], nlut[512 + pb]);
-                        } else {
-                            const uint2 ta = nlut3[pa], tb = nlut3[pb];
-                            *reinterpret_cast<unsigned *>(o) = __byte_perm(ta.x, tb.x, 0x5410);
-                            *reinterpret_cast<unsigned *>(o + cstride) = __byte_perm(ta.x, tb.x, 0x7632);
-                            *reinterpret_cast<unsigned *>(o + 2 * cstride) = __byte_perm(ta.y, tb.y, 0x5410);
-                        }
-                    }
-                }
-            }
-        }
-        cluster.sync();
-        continue;      // next frame
-    }
 
     // ---- P5: horizontal Pillow pass, one thread per cropped output column, taps in registers ----
     {
@@ -715,6 +662,336 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
         }
     }
     cluster.sync();   // peers may still be reading this CTA's hrow; also fences the shared state for the next frame
+    }   // frame loop
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tensor-core variant: one CTA per frame (the whole sensor's bins fit one SM), W % 4 == 0, upsampling or mild
+// downsampling (every 16-output tile reads a source window of <= 32 pixels).
+//
+// Both Pillow passes are banded matrix products evaluated with mma.sync.m16n8k32 (s8 x u8 -> s32):
+//     hT[xo][y]   = clip8((sum_x kh[xo][x] gray[y][x] + 2^21) >> 22)      A = kh digits, B = gray rows as stored
+//     out[yo][xo] = clip8((sum_y kv[yo][y] hT[xo][y]  + 2^21) >> 22)      A = kv digits, B = rows of the transposed hT
+// The 22-bit taps are split into three signed base-256 digits; the three s32 partial sums recombine to exactly Pillow's
+// integer accumulator.  Shared memory: [bins | later hT + out8][gray plane]; the formatting phase then turns 8 output
+// bytes per thread into three 16-byte stores.
+// ------------------------------------------------------------------------------------------------
+template <bool DBG, bool COMPACT>
+__global__ void __launch_bounds__(1024, 1) event2img_tc_kernel(const E2IParams p)
+{
+    const int NT = blockDim.x;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, wid = tid >> 5, nwarps = NT >> 5;
+    const int H = p.H, W = p.W;
+    const int HW = H * W;
+    const int HP = (H + 3) & ~3;                 // row pitch of the transposed intermediate
+    const bool mask = (p.flags & EC_FLAG_BACKGROUND_MASK) != 0;
+    const bool cnz = (p.flags & EC_FLAG_COUNT_NON_ZERO) != 0;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw);
+    uint8_t *hT = smem_raw;                      // [224][HP], over the dead bins
+    uint8_t *out8 = smem_raw + OUT * HP;         // [224][224] resampled bytes
+    uint8_t *gray = smem_raw + p.gray_off;       // [H][W] (+ slack for the fragment loads of the last row tile)
+    __shared__ unsigned long long red64[32];
+    __shared__ unsigned red32[32][4];
+    __shared__ unsigned s_keep, s_mx, s_mall;
+    __shared__ uint8_t glut[GLUT_N * GLUT_N];
+    __shared__ float nlut[768];
+    __shared__ uint2 nlut3[256];                 // bf16 (c0, c1, c2, 0) of each uint8 value: one 8-byte load per pixel
+    __shared__ int rowoff[OUT], coloff[OUT / 2];   // element offset of an output row / of a column group (8 px, or 2 px for P % 8 != 0)
+    __shared__ int s_ws[2 * (OUT / 16)];            // first source column / row of each 16-output tile
+
+    constexpr int MT = OUT / 16;
+    const int parts = nwarps / MT;                  // warps per 16-output tile (>= 1: the launch uses >= 512 threads)
+    const int g = lane >> 2, tig = lane & 3;
+    const uint4 *fragH = reinterpret_cast<const uint4 *>(p.fragH) + lane;
+    const uint4 *fragV = reinterpret_cast<const uint4 *>(p.fragV) + lane;
+    const bool wide = p.out_fmt != EC_OUT_BF16_PATCH || (p.patch % 8) == 0;
+    const int cstride = p.out_fmt == EC_OUT_BF16_PATCH ? p.patch * p.patch : OUT * OUT;     // channel stride (elements)
+    const int frame_elems = p.out_fmt == EC_OUT_BF16_PATCH ? p.G * p.G * p.ldk : 3 * OUT * OUT;
+
+    if (p.out_fmt == EC_OUT_F32_NCHW)
+        for (int i = tid; i < 768; i += NT) nlut[i] = p.nlut[i];
+    for (int i = tid; i < 256; i += NT) {
+        const __nv_bfloat162 c01 = __floats2bfloat162_rn(p.nlut[i], p.nlut[256 + i]);
+        const __nv_bfloat162 c2z = __floats2bfloat162_rn(p.nlut[512 + i], 0.f);
+        nlut3[i] = make_uint2(*reinterpret_cast<const uint32_t *>(&c01), *reinterpret_cast<const uint32_t *>(&c2z));
+    }
+    {
+        const int cw = wide ? 8 : 2;                // pixels per column group
+        for (int i = tid; i < OUT; i += NT)
+            rowoff[i] = p.out_fmt == EC_OUT_BF16_PATCH ? (i / p.patch) * p.G * p.ldk + (i % p.patch) * p.patch : i * OUT;
+        for (int i = tid; i < OUT / cw; i += NT)
+            coloff[i] = p.out_fmt == EC_OUT_BF16_PATCH ? ((i * cw) / p.patch) * p.ldk + (i * cw) % p.patch : i * cw;
+        for (int i = tid; i < 2 * MT; i += NT) s_ws[i] = i < MT ? p.wsH[i] : p.wsV[i - MT];
+    }
+    __syncthreads();
+
+    for (int fid = blockIdx.x; fid < p.n_frames; fid += gridDim.x) {
+        const ec_frame fr = p.frames[fid];
+        const int slot = fr.out_slot;
+        // ---- padding frame: the reference pads missing views with zeros (event2img.py:89-91) ----
+        if (fr.ev_count <= 0) {
+            if (p.out_fmt == EC_OUT_BF16_PATCH) {
+                const int G = p.G, cols = 3 * p.patch * p.patch;
+                for (int r = 0; r < G * G; ++r) {
+                    __nv_bfloat16 *o = (__nv_bfloat16 *)p.out + ((size_t)slot * G * G + r) * p.ldk;
+                    for (int c = tid; c < cols; c += NT) o[c] = __float2bfloat16(0.f);
+                }
+            } else if (p.out_fmt == EC_OUT_F32_NCHW) {
+                float *o = (float *)p.out + (size_t)slot * 3 * OUT * OUT;
+                for (int i = tid; i < 3 * OUT * OUT; i += NT) o[i] = 0.f;
+            } else {
+                __nv_bfloat16 *o = (__nv_bfloat16 *)p.out + (size_t)slot * 3 * OUT * OUT;
+                for (int i = tid; i < 3 * OUT * OUT; i += NT) o[i] = __float2bfloat16(0.f);
+            }
+            continue;     // uniform; the previous frame ended with a barrier
+        }
+
+        // ---- P0: clear the bins (W % 4 == 0: whole 16-byte groups) ----
+        {
+            uint4 *h4 = reinterpret_cast<uint4 *>(hist);
+#pragma unroll 4
+            for (int i = tid; i < (HW >> 2); i += NT) h4[i] = make_uint4(0, 0, 0, 0);
+        }
+        __syncthreads();
+
+        // ---- P1: event scan ----
+        ScanAcc acc = {0, 0, 0, 0, 0};
+        scan_events<COMPACT, false>(p, fr, 0, 1, hist, tid, NT, acc);
+        // while this frame is reduced, resampled and stored, pull the next frame's events into L2
+        if (fid + (int)gridDim.x < p.n_frames) {
+            const ec_frame nx = p.frames[fid + gridDim.x];
+            if (nx.ev_count > 0) {
+                const char *b = COMPACT ? reinterpret_cast<const char *>(p.events_c + nx.ev_start)
+                                        : reinterpret_cast<const char *>(p.events + nx.ev_start);
+                const int bytes = nx.ev_count * (COMPACT ? 4 : 16);
+                for (int o = tid * 128; o < bytes; o += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + o));
+            }
+        }
+        // ---- P2: exact integer statistics -> hot-pixel cut ----
+        {
+            unsigned long long s2 = warp_sum_u64(acc.s2);
+            unsigned nnz = warp_sum_u32(acc.nnz), nacc = warp_sum_u32(acc.nacc), mall = warp_max_u32(acc.mall);
+            unsigned fl = __reduce_or_sync(0xffffffffu, acc.flags);
+            if (lane == 0) { red64[wid] = s2; red32[wid][0] = nnz; red32[wid][1] = nacc; red32[wid][2] = mall; red32[wid][3] = fl; }
+            __syncthreads();   // also: all atomics have landed
+            if (wid == 0) {
+                const bool on = lane < nwarps;
+                s2 = warp_sum_u64(on ? red64[lane] : 0ull);
+                nnz = warp_sum_u32(on ? red32[lane][0] : 0u);
+                nacc = warp_sum_u32(on ? red32[lane][1] : 0u);
+                mall = warp_max_u32(on ? red32[lane][2] : 0u);
+                fl = __reduce_or_sync(0xffffffffu, on ? red32[lane][3] : 0u);
+                if (lane == 0) {
+                    if (mall > 0xffffu) fl |= EC_STATUS_COUNT_OVERFLOW;      // a 16-bit field wrapped
+                    const unsigned long long n = cnz ? (unsigned long long)nnz : (unsigned long long)HW * 2ull;
+                    s_keep = compute_keep(n, nacc, s2, 10);
+                    s_mall = mall;
+                    if (fl) atomicOr(p.status, (int)fl);
+                }
+            }
+            __syncthreads();
+        }
+        const unsigned keep = s_keep;
+        unsigned mx = s_mall;
+        const bool hot = mx > keep;
+        // ---- P3 (only when some bin exceeds `keep`): max of the surviving bins ----
+        if (hot) {
+            unsigned m = 0;
+            const uint4 *h4 = reinterpret_cast<const uint4 *>(hist);
+            for (int i = tid; i < (HW >> 2); i += NT) {
+                const uint4 w4 = h4[i];
+                if ((w4.x | w4.y | w4.z | w4.w) == 0) continue;
+                const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t a = ws[q] & 0xffffu, b = ws[q] >> 16;
+                    if (a <= keep) m = max(m, a);
+                    if (b <= keep) m = max(m, b);
+                }
+            }
+            m = warp_max_u32(m);
+            if (lane == 0) red32[wid][0] = m;
+            __syncthreads();
+            if (wid == 0) {
+                m = warp_max_u32(lane < nwarps ? red32[lane][0] : 0u);
+                if (lane == 0) s_mx = m;
+            }
+            __syncthreads();
+            mx = s_mx;
+        }
+
+        // ---- P4: gray byte per pixel (small counts through a per-frame LUT) into its own plane ----
+        for (int i = tid; i < GLUT_N * GLUT_N; i += NT) glut[i] = (uint8_t)gray_px(i % GLUT_N, i / GLUT_N, mx, mask);
+        __syncthreads();
+        {
+            const uint4 *h4 = reinterpret_cast<const uint4 *>(hist);
+            uint32_t *g32 = reinterpret_cast<uint32_t *>(gray);
+            const uint32_t bg4 = 0x01010101u * glut[0];          // four empty pixels
+#pragma unroll 2
+            for (int j = tid; j < (HW >> 2); j += NT) {
+                const uint4 w4 = h4[j];
+                const uint32_t any = w4.x | w4.y | w4.z | w4.w;
+                uint32_t pk = bg4;
+                if (!DBG && !hot && (any & 0xffe0ffe0u) == 0) {
+                    // all eight counts < 32 (the common case): four byte lookups, no per-pixel branches
+                    if (any) {
+                        const unsigned g0 = glut[((w4.x >> 11) & 0x3e0u) | w4.x & 0x1fu], g1 = glut[((w4.y >> 11) & 0x3e0u) | w4.y & 0x1fu];
+                        const unsigned g2 = glut[((w4.z >> 11) & 0x3e0u) | w4.z & 0x1fu], g3 = glut[((w4.w >> 11) & 0x3e0u) | w4.w & 0x1fu];
+                        pk = __byte_perm(__byte_perm(g0, g1, 0x0040), __byte_perm(g2, g3, 0x0040), 0x5410);
+                    }
+                } else {
+                    const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
+                    pk = 0;
+#pragma unroll 1
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t w = ws[q];
+                        if (DBG && p.dbg_counts) {
+                            int32_t *dc = p.dbg_counts + ((size_t)fid * HW + 4 * j + q) * 2;
+                            dc[0] = (int32_t)(w & 0xffffu); dc[1] = (int32_t)(w >> 16);
+                        }
+                        if (hot) {   // some bin exceeds the cut (uniform): remove those fields
+                            if ((w & 0xffffu) > keep) w &= 0xffff0000u;
+                            if ((w >> 16) > keep) w &= 0x0000ffffu;
+                        }
+                        unsigned g;
+                        if ((w & 0xffe0ffe0u) == 0) g = glut[((w >> 11) & 0x3e0u) | (w & 0x1fu)];   // both counts < 32
+                        else g = gray_px(w & 0xffffu, w >> 16, mx, mask);
+                        pk |= g << (8 * q);
+                    }
+                }
+                g32[j] = pk;
+                if (DBG && p.dbg_gray) *reinterpret_cast<uint32_t *>(p.dbg_gray + (size_t)fid * HW + 4 * j) = pk;
+            }
+        }
+        __syncthreads();
+
+        // ---- P5: horizontal pass on the tensor cores, gray [y][x] -> hT [xo][y].  Warp w owns the 16-column tile
+        //      mt = w % 14 (its A fragments stay in registers for the whole pass) and 1 / parts of the 8-row tiles ----
+        {
+            const int n_tiles = (H + 7) >> 3;
+            if (wid < MT * parts) {
+                const int mt = wid % MT, part = wid / MT;
+                const int ws = s_ws[mt];
+                uint4 a[3];
+#pragma unroll
+                for (int dg = 0; dg < 3; ++dg) a[dg] = __ldg(fragH + (mt * 3 + dg) * 32);
+                const int nt0 = part * n_tiles / parts, nt1 = (part + 1) * n_tiles / parts;
+                const uint8_t *src = gray + (nt0 * 8 + g) * W + ws + tig * 4;
+                uint8_t *dst = hT + (mt * 16 + g) * HP + nt0 * 8 + tig * 2;
+                int y = nt0 * 8 + tig * 2;
+#pragma unroll 2
+                for (int nt = nt0; nt < nt1; ++nt, src += 8 * W, dst += 8, y += 8) {
+                    const uint32_t b0 = *reinterpret_cast<const uint32_t *>(src);
+                    const uint32_t b1 = *reinterpret_cast<const uint32_t *>(src + 16);
+                    int c0[4], c1[4], c2[4];
+                    imma_s8u8(c0, a[0], b0, b1, 1 << (PREC - 1));      // the rounding term rides in digit 0
+                    imma_s8u8(c1, a[1], b0, b1, 0);
+                    imma_s8u8(c2, a[2], b0, b1, 0);
+                    unsigned px[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) px[e] = (unsigned)__vimin_s32_relu((c0[e] + (c1[e] << 8) + (c2[e] << 16)) >> PREC, 255);
+                    if (y < HP) {      // rows past H (garbage in, zero vertical taps) are only kept inside the pitch
+                        *reinterpret_cast<uint16_t *>(dst) = (uint16_t)__byte_perm(px[0], px[1], 0x0040);
+                        *reinterpret_cast<uint16_t *>(dst + 8 * HP) = (uint16_t)__byte_perm(px[2], px[3], 0x0040);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- P6: vertical pass on the tensor cores, hT [xo][y] -> out8 [yo][xo] ----
+        {
+            constexpr int n_tiles = OUT / 8;
+            if (wid < MT * parts) {
+                const int mt = wid % MT, part = wid / MT;
+                const int ws = s_ws[MT + mt];
+                uint4 a[3];
+#pragma unroll
+                for (int dg = 0; dg < 3; ++dg) a[dg] = __ldg(fragV + (mt * 3 + dg) * 32);
+                const int nt0 = part * n_tiles / parts, nt1 = (part + 1) * n_tiles / parts;
+                const uint8_t *src = hT + (nt0 * 8 + g) * HP + ws + tig * 4;
+                uint8_t *dst = out8 + (mt * 16 + g) * OUT + nt0 * 8 + tig * 2;
+#pragma unroll 2
+                for (int nt = nt0; nt < nt1; ++nt, src += 8 * HP, dst += 8) {
+                    const uint32_t b0 = *reinterpret_cast<const uint32_t *>(src);
+                    const uint32_t b1 = *reinterpret_cast<const uint32_t *>(src + 16);
+                    int c0[4], c1[4], c2[4];
+                    imma_s8u8(c0, a[0], b0, b1, 1 << (PREC - 1));
+                    imma_s8u8(c1, a[1], b0, b1, 0);
+                    imma_s8u8(c2, a[2], b0, b1, 0);
+                    unsigned px[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) px[e] = (unsigned)__vimin_s32_relu((c0[e] + (c1[e] << 8) + (c2[e] << 16)) >> PREC, 255);
+                    *reinterpret_cast<uint16_t *>(dst) = (uint16_t)__byte_perm(px[0], px[1], 0x0040);
+                    *reinterpret_cast<uint16_t *>(dst + 8 * OUT) = (uint16_t)__byte_perm(px[2], px[3], 0x0040);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- P7: normalise LUT + output formatting, 8 bytes of out8 per item; offsets from two small tables ----
+        {
+            uint8_t *du = (DBG && p.dbg_u8) ? p.dbg_u8 + (size_t)fid * OUT * OUT : nullptr;
+            if (wide) {
+                constexpr int NG = OUT / 8;
+                if (p.out_fmt == EC_OUT_F32_NCHW) {
+                    float *ofr = (float *)p.out + (size_t)slot * 3 * OUT * OUT;
+                    for (int it = tid; it < OUT * NG; it += NT) {
+                        const uint2 v = *reinterpret_cast<const uint2 *>(out8 + it * 8);
+                        if (du) *reinterpret_cast<uint2 *>(du + it * 8) = v;
+                        unsigned v8[8];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { v8[j] = __byte_perm(v.x, 0u, 0x4440u + j); v8[4 + j] = __byte_perm(v.y, 0u, 0x4440u + j); }
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            float *o = ofr + c * OUT * OUT + it * 8;
+                            const float *nl = nlut + c * 256;
+                            *reinterpret_cast<float4 *>(o) = make_float4(nl[v8[0]], nl[v8[1]], nl[v8[2]], nl[v8[3]]);
+                            *reinterpret_cast<float4 *>(o + 4) = make_float4(nl[v8[4]], nl[v8[5]], nl[v8[6]], nl[v8[7]]);
+                        }
+                    }
+                } else {
+                    __nv_bfloat16 *ofr = (__nv_bfloat16 *)p.out + (size_t)slot * frame_elems;
+                    for (int it = tid; it < OUT * NG; it += NT) {
+                        const int yo = it / NG, xg = it - yo * NG;
+                        const uint2 v = *reinterpret_cast<const uint2 *>(out8 + it * 8);
+                        if (du) *reinterpret_cast<uint2 *>(du + it * 8) = v;
+                        uint2 t8[8];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            t8[j] = nlut3[__byte_perm(v.x, 0u, 0x4440u + j)];
+                            t8[4 + j] = nlut3[__byte_perm(v.y, 0u, 0x4440u + j)];
+                        }
+                        uint4 o0, o1, o2;
+                        o0.x = __byte_perm(t8[0].x, t8[1].x, 0x5410); o1.x = __byte_perm(t8[0].x, t8[1].x, 0x7632); o2.x = __byte_perm(t8[0].y, t8[1].y, 0x5410);
+                        o0.y = __byte_perm(t8[2].x, t8[3].x, 0x5410); o1.y = __byte_perm(t8[2].x, t8[3].x, 0x7632); o2.y = __byte_perm(t8[2].y, t8[3].y, 0x5410);
+                        o0.z = __byte_perm(t8[4].x, t8[5].x, 0x5410); o1.z = __byte_perm(t8[4].x, t8[5].x, 0x7632); o2.z = __byte_perm(t8[4].y, t8[5].y, 0x5410);
+                        o0.w = __byte_perm(t8[6].x, t8[7].x, 0x5410); o1.w = __byte_perm(t8[6].x, t8[7].x, 0x7632); o2.w = __byte_perm(t8[6].y, t8[7].y, 0x5410);
+                        __nv_bfloat16 *ob = ofr + (rowoff[yo] + coloff[xg]);
+                        *reinterpret_cast<uint4 *>(ob) = o0;
+                        *reinterpret_cast<uint4 *>(ob + cstride) = o1;
+                        *reinterpret_cast<uint4 *>(ob + 2 * cstride) = o2;
+                    }
+                }
+            } else {
+                // patch size not a multiple of 8 (ViT-L/14): column pairs never straddle a patch
+                __nv_bfloat16 *ofr = (__nv_bfloat16 *)p.out + (size_t)slot * frame_elems;
+                for (int it = tid; it < OUT * (OUT / 2); it += NT) {
+                    const int yo = it / (OUT / 2), xp = it - yo * (OUT / 2);
+                    const unsigned two = *reinterpret_cast<const uint16_t *>(out8 + it * 2);
+                    if (du) *reinterpret_cast<uint16_t *>(du + it * 2) = (uint16_t)two;
+                    const uint2 t0 = nlut3[two & 0xffu], t1 = nlut3[two >> 8];
+                    __nv_bfloat16 *ob = ofr + (rowoff[yo] + coloff[xp]);
+                    *reinterpret_cast<unsigned *>(ob) = __byte_perm(t0.x, t1.x, 0x5410);
+                    *reinterpret_cast<unsigned *>(ob + cstride) = __byte_perm(t0.x, t1.x, 0x7632);
+                    *reinterpret_cast<unsigned *>(ob + 2 * cstride) = __byte_perm(t0.y, t1.y, 0x5410);
+                }
+            }
+        }
+        __syncthreads();   // out8 / hT share the bins' storage
     }   // frame loop
 }
 
@@ -1024,14 +1301,30 @@ static int event2img_impl(const float *events, const uint32_t *events_c, const e
     p.KH = tb.KH; p.KV = tb.KV;
     p.fragH = tb.dev + tb.off_fragH; p.fragV = tb.dev + tb.off_fragV; p.wsH = tb.dev + tb.off_wsH; p.wsV = tb.dev + tb.off_wsV;
     p.KSH = tb.KSH; p.KSV = tb.KSV;
-    {
-        static const bool off = getenv("EC_E2I_IMMA") && atoi(getenv("EC_E2I_IMMA")) == 0;    // 0 forces the SIMT resample
-        p.imma = !off && CS == 1 && W % 4 == 0 && H >= 48 && tb.KSH == 1 && tb.KSV == 1;
-    }
+    p.gray_off = 0;
     p.band_magic = ((1ull << 40) + (unsigned long long)RB * W - 1) / ((unsigned long long)RB * W);
 
     const bool dbg = dbg_counts || dbg_gray || dbg_u8;
-    auto kern = events_c
+    // tensor-core kernel: whole sensor in one CTA, 4-byte aligned rows, one 32-wide source window per 16-output tile
+    bool tc = false;
+    {
+        static const bool off = getenv("EC_E2I_TC") && atoi(getenv("EC_E2I_TC")) == 0;    // 0 forces the SIMT kernel
+        const int HP = (H + 3) & ~3;
+        size_t region_a = (size_t)H * W * 4;
+        if (region_a < (size_t)OUT * HP + (size_t)OUT * OUT) region_a = (size_t)OUT * HP + (size_t)OUT * OUT;
+        region_a = (region_a + 15) & ~(size_t)15;
+        const size_t gray_bytes = ((size_t)(H + 8) * W + 32 + 15) & ~(size_t)15;       // last row tile reads up to 7 rows + 31 bytes past the plane
+        const size_t tc_smem = region_a + gray_bytes;
+        tc = !off && CS == 1 && W % 4 == 0 && H >= 16 && tb.KSH == 1 && tb.KSV == 1 && tc_smem <= (size_t)221 * 1024;
+        if (tc) { smem = tc_smem; p.gray_off = (int)region_a; }
+    }
+    typedef void (*kern_t)(const E2IParams);
+    kern_t kern;
+    if (tc)
+        kern = events_c ? (dbg ? event2img_tc_kernel<true, true> : event2img_tc_kernel<false, true>)
+                        : (dbg ? event2img_tc_kernel<true, false> : event2img_tc_kernel<false, false>);
+    else
+        kern = events_c
         ? (dbg ? (tb.KH <= 5 ? event2img_kernel<5, true, true> : (tb.KH <= 11 ? event2img_kernel<11, true, true> : event2img_kernel<0, true, true>))
                : (tb.KH <= 5 ? event2img_kernel<5, false, true> : (tb.KH <= 11 ? event2img_kernel<11, false, true> : event2img_kernel<0, false, true>)))
         : (dbg ? (tb.KH <= 5 ? event2img_kernel<5, true, false> : (tb.KH <= 11 ? event2img_kernel<11, true, false> : event2img_kernel<0, true, false>))
