@@ -58,6 +58,10 @@ struct E2IParams {
     const int32_t *fragH, *fragV, *wsH, *wsV;
     int KSH, KSV;
     int gray_off;   // tensor-core kernel: byte offset of the gray plane in dynamic shared memory
+    // bf16 outputs: bf16(fma(v, na[c], nb[c])) equals the bf16 rounding of the exact float32 normalise LUT for all 256 bytes
+    // (checked on the host when the tables are built); affine = 0 falls back to the LUT
+    float na[3], nb[3];
+    int affine;
 };
 
 struct Part {            // per-CTA partial statistics exchanged over DSMEM
@@ -168,22 +172,32 @@ struct ScanAcc {
 // One round = 128 consecutive events per warp, 4 per lane (lane-contiguous 512-byte loads at immediate offsets):
 // all loads, then the decode, then all atomics, then the statistics from the values the atomics returned.
 // An event becomes (flat bin index l, increment): 1 = positive field, 65536 = negative field, 0 = not histogrammed.
-template <bool COMPACT, bool MULTI, bool TAIL>
-__device__ __forceinline__ void scan_round(const float4 *ev, const uint32_t *evc, int rem, int W, unsigned uHW_fast, unsigned uHW,
-                                           long long HW, uint32_t hist_s, unsigned long long magic, unsigned bandpx, ScanAcc &acc)
+struct ScanRound {      // one lane's four events of a round (float4 rows or compact words)
+    float4 e[4];
+    uint32_t w[4];
+};
+
+template <bool COMPACT, bool TAIL>
+__device__ __forceinline__ void load_round(const float4 *ev, const uint32_t *evc, int rem, ScanRound &r)
 {
-    constexpr int U = 4;
-    float4 ev4[U];
-    uint32_t wc[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-        ev4[u] = make_float4(0.f, 0.f, 0.f, 0.f);      // a missing tail event decodes to "add 0 to bin 0"
-        wc[u] = 0;
+    for (int u = 0; u < 4; ++u) {
+        r.e[u] = make_float4(0.f, 0.f, 0.f, 0.f);      // a missing tail event decodes to "add 0 to bin 0"
+        r.w[u] = 0;
         if (!TAIL || u * 32 < rem) {
-            if (COMPACT) wc[u] = ld_stream_u32(evc + u * 32);
-            else ev4[u] = ld_stream(ev + u * 32);
+            if (COMPACT) r.w[u] = ld_stream_u32(evc + u * 32);
+            else r.e[u] = ld_stream(ev + u * 32);
         }
     }
+}
+
+template <bool COMPACT, bool MULTI, bool TAIL>
+__device__ __forceinline__ void scan_round(const ScanRound &r, int W, unsigned uHW_fast, unsigned uHW, long long HW, uint32_t hist_s,
+                                           unsigned long long magic, unsigned bandpx, ScanAcc &acc)
+{
+    constexpr int U = 4;
+    const float4 (&ev4)[4] = r.e;
+    const uint32_t (&wc)[4] = r.w;
     unsigned l[U], inc[U], old[U];
     int xs[U], ys[U];
     bool ok[U], all_ok = true;
@@ -282,11 +296,29 @@ __device__ __forceinline__ void scan_events(const E2IParams &p, const ec_frame &
     const float4 *ev = p.events + (COMPACT ? 0 : fr.ev_start + e_lo + first);
     const uint32_t *evc = p.events_c + (COMPACT ? fr.ev_start + e_lo + first : 0);
     const int step = NT * 4;
-    int base = 0;
-    for (; base + step <= n; base += step, ev += step, evc += step)
-        scan_round<COMPACT, MULTI, false>(ev, evc, 0, p.W, uHW_fast, uHW, HW, hist_s, p.band_magic, bandpx, acc);
-    if (base < n)
-        scan_round<COMPACT, MULTI, true>(ev, evc, n - base - first, p.W, uHW_fast, uHW, HW, hist_s, p.band_magic, bandpx, acc);
+    // software pipeline: the loads of round r+1 are in flight while round r is decoded and histogrammed
+    ScanRound cur, nxt;
+    if (n >= step) {
+        load_round<COMPACT, false>(ev, evc, 0, cur);
+        int base = step;
+        for (; base + step <= n; base += step) {
+            ev += step; evc += step;
+            load_round<COMPACT, false>(ev, evc, 0, nxt);
+            scan_round<COMPACT, MULTI, false>(cur, p.W, uHW_fast, uHW, HW, hist_s, p.band_magic, bandpx, acc);
+            cur = nxt;
+        }
+        if (base < n) {
+            ev += step; evc += step;
+            load_round<COMPACT, true>(ev, evc, n - base - first, nxt);
+            scan_round<COMPACT, MULTI, false>(cur, p.W, uHW_fast, uHW, HW, hist_s, p.band_magic, bandpx, acc);
+            scan_round<COMPACT, MULTI, true>(nxt, p.W, uHW_fast, uHW, HW, hist_s, p.band_magic, bandpx, acc);
+        } else {
+            scan_round<COMPACT, MULTI, false>(cur, p.W, uHW_fast, uHW, HW, hist_s, p.band_magic, bandpx, acc);
+        }
+    } else if (n > 0) {
+        load_round<COMPACT, true>(ev, evc, n - first, cur);
+        scan_round<COMPACT, MULTI, true>(cur, p.W, uHW_fast, uHW, HW, hist_s, p.band_magic, bandpx, acc);
+    }
 }
 
 // KHMAX: compile-time bound on the horizontal taps (5 when upsampling, 11 for 640 -> 298); 0 = dynamic loop.
@@ -695,7 +727,7 @@ __global__ void __launch_bounds__(1024, 1) event2img_tc_kernel(const E2IParams p
     uint8_t *gray = smem_raw + p.gray_off;       // [H][W] (+ slack for the fragment loads of the last row tile)
     __shared__ unsigned long long red64[32];
     __shared__ unsigned red32[32][4];
-    __shared__ unsigned s_keep, s_mx, s_mall;
+    __shared__ unsigned s_keep;
     __shared__ uint8_t glut[GLUT_N * GLUT_N];
     __shared__ float nlut[768];
     __shared__ uint2 nlut3[256];                 // bf16 (c0, c1, c2, 0) of each uint8 value: one 8-byte load per pixel
@@ -770,34 +802,41 @@ __global__ void __launch_bounds__(1024, 1) event2img_tc_kernel(const E2IParams p
                 for (int o = tid * 128; o < bytes; o += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + o));
             }
         }
-        // ---- P2: exact integer statistics -> hot-pixel cut ----
+        // ---- P2: exact integer statistics -> hot-pixel cut (one lane of warp 0), while the other warps already fill the
+        //      per-frame gray LUT for the common case that no bin exceeds the cut (max = largest count) ----
+        unsigned mx;
         {
             unsigned long long s2 = warp_sum_u64(acc.s2);
             unsigned nnz = warp_sum_u32(acc.nnz), nacc = warp_sum_u32(acc.nacc), mall = warp_max_u32(acc.mall);
             unsigned fl = __reduce_or_sync(0xffffffffu, acc.flags);
             if (lane == 0) { red64[wid] = s2; red32[wid][0] = nnz; red32[wid][1] = nacc; red32[wid][2] = mall; red32[wid][3] = fl; }
             __syncthreads();   // also: all atomics have landed
+            const bool on = lane < nwarps;
+            mx = warp_max_u32(on ? red32[lane][2] : 0u);
             if (wid == 0) {
-                const bool on = lane < nwarps;
                 s2 = warp_sum_u64(on ? red64[lane] : 0ull);
                 nnz = warp_sum_u32(on ? red32[lane][0] : 0u);
                 nacc = warp_sum_u32(on ? red32[lane][1] : 0u);
-                mall = warp_max_u32(on ? red32[lane][2] : 0u);
                 fl = __reduce_or_sync(0xffffffffu, on ? red32[lane][3] : 0u);
                 if (lane == 0) {
-                    if (mall > 0xffffu) fl |= EC_STATUS_COUNT_OVERFLOW;      // a 16-bit field wrapped
+                    if (mx > 0xffffu) fl |= EC_STATUS_COUNT_OVERFLOW;      // a 16-bit field wrapped
                     const unsigned long long n = cnz ? (unsigned long long)nnz : (unsigned long long)HW * 2ull;
                     s_keep = compute_keep(n, nacc, s2, 10);
-                    s_mall = mall;
                     if (fl) atomicOr(p.status, (int)fl);
+                }
+            } else {
+                // only (pos, neg) pairs up to the largest count are ever looked up
+                const int side = (int)min(mx, (unsigned)(GLUT_N - 1)) + 1;
+                for (int k = tid - 32; k < side * side; k += NT - 32) {
+                    const int neg = k / side, pos = k - neg * side;
+                    glut[neg * GLUT_N + pos] = (uint8_t)gray_px(pos, neg, mx, mask);
                 }
             }
             __syncthreads();
         }
         const unsigned keep = s_keep;
-        unsigned mx = s_mall;
         const bool hot = mx > keep;
-        // ---- P3 (only when some bin exceeds `keep`): max of the surviving bins ----
+        // ---- P3 (only when some bin exceeds `keep`): max of the surviving bins, LUT again ----
         if (hot) {
             unsigned m = 0;
             const uint4 *h4 = reinterpret_cast<const uint4 *>(hist);
@@ -815,17 +854,16 @@ __global__ void __launch_bounds__(1024, 1) event2img_tc_kernel(const E2IParams p
             m = warp_max_u32(m);
             if (lane == 0) red32[wid][0] = m;
             __syncthreads();
-            if (wid == 0) {
-                m = warp_max_u32(lane < nwarps ? red32[lane][0] : 0u);
-                if (lane == 0) s_mx = m;
+            mx = warp_max_u32(lane < nwarps ? red32[lane][0] : 0u);
+            const int side = (int)min(mx, (unsigned)(GLUT_N - 1)) + 1;
+            for (int k = tid; k < side * side; k += NT) {
+                const int neg = k / side, pos = k - neg * side;
+                glut[neg * GLUT_N + pos] = (uint8_t)gray_px(pos, neg, mx, mask);
             }
             __syncthreads();
-            mx = s_mx;
         }
 
-        // ---- P4: gray byte per pixel (small counts through a per-frame LUT) into its own plane ----
-        for (int i = tid; i < GLUT_N * GLUT_N; i += NT) glut[i] = (uint8_t)gray_px(i % GLUT_N, i / GLUT_N, mx, mask);
-        __syncthreads();
+        // ---- P4: gray byte per pixel (small counts through the LUT) into its own plane ----
         {
             const uint4 *h4 = reinterpret_cast<const uint4 *>(hist);
             uint32_t *g32 = reinterpret_cast<uint32_t *>(gray);
@@ -959,17 +997,39 @@ __global__ void __launch_bounds__(1024, 1) event2img_tc_kernel(const E2IParams p
                         const int yo = it / NG, xg = it - yo * NG;
                         const uint2 v = *reinterpret_cast<const uint2 *>(out8 + it * 8);
                         if (du) *reinterpret_cast<uint2 *>(du + it * 8) = v;
-                        uint2 t8[8];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            t8[j] = nlut3[__byte_perm(v.x, 0u, 0x4440u + j)];
-                            t8[4 + j] = nlut3[__byte_perm(v.y, 0u, 0x4440u + j)];
-                        }
                         uint4 o0, o1, o2;
-                        o0.x = __byte_perm(t8[0].x, t8[1].x, 0x5410); o1.x = __byte_perm(t8[0].x, t8[1].x, 0x7632); o2.x = __byte_perm(t8[0].y, t8[1].y, 0x5410);
-                        o0.y = __byte_perm(t8[2].x, t8[3].x, 0x5410); o1.y = __byte_perm(t8[2].x, t8[3].x, 0x7632); o2.y = __byte_perm(t8[2].y, t8[3].y, 0x5410);
-                        o0.z = __byte_perm(t8[4].x, t8[5].x, 0x5410); o1.z = __byte_perm(t8[4].x, t8[5].x, 0x7632); o2.z = __byte_perm(t8[4].y, t8[5].y, 0x5410);
-                        o0.w = __byte_perm(t8[6].x, t8[7].x, 0x5410); o1.w = __byte_perm(t8[6].x, t8[7].x, 0x7632); o2.w = __byte_perm(t8[6].y, t8[7].y, 0x5410);
+                        if (p.affine) {
+                            // byte -> float through the 2^23 trick, one fma per channel, packed bf16 conversion
+                            float f[8];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                f[j] = __uint_as_float(__byte_perm(v.x, 0x4b000000u, 0x7650u + j)) - 8388608.0f;
+                                f[4 + j] = __uint_as_float(__byte_perm(v.y, 0x4b000000u, 0x7650u + j)) - 8388608.0f;
+                            }
+                            uint32_t w[3][4];
+#pragma unroll
+                            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const __nv_bfloat162 h = __floats2bfloat162_rn(__fmaf_rn(f[2 * j], p.na[c], p.nb[c]),
+                                                                                   __fmaf_rn(f[2 * j + 1], p.na[c], p.nb[c]));
+                                    w[c][j] = *reinterpret_cast<const uint32_t *>(&h);
+                                }
+                            o0 = make_uint4(w[0][0], w[0][1], w[0][2], w[0][3]);
+                            o1 = make_uint4(w[1][0], w[1][1], w[1][2], w[1][3]);
+                            o2 = make_uint4(w[2][0], w[2][1], w[2][2], w[2][3]);
+                        } else {
+                            uint2 t8[8];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                t8[j] = nlut3[__byte_perm(v.x, 0u, 0x4440u + j)];
+                                t8[4 + j] = nlut3[__byte_perm(v.y, 0u, 0x4440u + j)];
+                            }
+                            o0.x = __byte_perm(t8[0].x, t8[1].x, 0x5410); o1.x = __byte_perm(t8[0].x, t8[1].x, 0x7632); o2.x = __byte_perm(t8[0].y, t8[1].y, 0x5410);
+                            o0.y = __byte_perm(t8[2].x, t8[3].x, 0x5410); o1.y = __byte_perm(t8[2].x, t8[3].x, 0x7632); o2.y = __byte_perm(t8[2].y, t8[3].y, 0x5410);
+                            o0.z = __byte_perm(t8[4].x, t8[5].x, 0x5410); o1.z = __byte_perm(t8[4].x, t8[5].x, 0x7632); o2.z = __byte_perm(t8[4].y, t8[5].y, 0x5410);
+                            o0.w = __byte_perm(t8[6].x, t8[7].x, 0x5410); o1.w = __byte_perm(t8[6].x, t8[7].x, 0x7632); o2.w = __byte_perm(t8[6].y, t8[7].y, 0x5410);
+                        }
                         __nv_bfloat16 *ob = ofr + (rowoff[yo] + coloff[xg]);
                         *reinterpret_cast<uint4 *>(ob) = o0;
                         *reinterpret_cast<uint4 *>(ob + cstride) = o1;
@@ -1052,6 +1112,8 @@ struct Tables {
     size_t off_vy = 0, off_lut = 0;
     size_t off_fragH = 0, off_fragV = 0, off_wsH = 0, off_wsV = 0;
     int KSH = 0, KSV = 0;
+    float na[3] = {0, 0, 0}, nb[3] = {0, 0, 0};
+    int affine = 0;
 };
 
 // signed base-256 digits of a Pillow coefficient (|k| < 2^23): k = d0 + 256 d1 + 65536 d2, each in [-128, 127]
@@ -1143,6 +1205,32 @@ int get_tables(int H, int W, cudaStream_t stream, Tables &out)
             memcpy(&bits, &rf, 4);
             all.push_back(bits);
         }
+    // one fma per channel that reproduces the bf16 rounding of the LUT above for every byte value (else: keep the LUT)
+    {
+        auto bf16_bits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16); };
+        t.affine = 1;
+        for (int c = 0; c < 3 && t.affine; ++c) {
+            const float a0 = (float)(1.0 / (255.0 * (double)stdv[c])), b0 = (float)(-(double)mean[c] / (double)stdv[c]);
+            bool found = false;
+            for (int r = 0; r <= 4 && !found; ++r)          // nudge a / b by a few ulps if the nominal pair misses a rounding boundary
+                for (int da = -r; da <= r && !found; ++da)
+                    for (int db = -r; db <= r && !found; ++db) {
+                        if (std::max(std::abs(da), std::abs(db)) != r) continue;
+                        float a = a0, b = b0;
+                        for (int k = 0; k < std::abs(da); ++k) a = std::nextafterf(a, da > 0 ? INFINITY : -INFINITY);
+                        for (int k = 0; k < std::abs(db); ++k) b = std::nextafterf(b, db > 0 ? INFINITY : -INFINITY);
+                        bool ok = true;
+                        for (int v = 0; v < 256 && ok; ++v) {
+                            float lut;
+                            memcpy(&lut, &all[t.off_lut + (size_t)c * 256 + v], 4);
+                            ok = bf16_bits(fmaf((float)v, a, b)) == bf16_bits(lut);
+                        }
+                        if (ok) { t.na[c] = a; t.nb[c] = b; found = true; }
+                    }
+            if (!found) t.affine = 0;
+        }
+        if (getenv("EC_E2I_AFFINE") && atoi(getenv("EC_E2I_AFFINE")) == 0) t.affine = 0;     // experiment hook
+    }
     {
         std::vector<int32_t> fh, fv, wh, wv;
         t.KSH = build_frags(hx, t.KH, fh, wh);
@@ -1302,6 +1390,8 @@ static int event2img_impl(const float *events, const uint32_t *events_c, const e
     p.fragH = tb.dev + tb.off_fragH; p.fragV = tb.dev + tb.off_fragV; p.wsH = tb.dev + tb.off_wsH; p.wsV = tb.dev + tb.off_wsV;
     p.KSH = tb.KSH; p.KSV = tb.KSV;
     p.gray_off = 0;
+    for (int c = 0; c < 3; ++c) { p.na[c] = tb.na[c]; p.nb[c] = tb.nb[c]; }
+    p.affine = tb.affine;
     p.band_magic = ((1ull << 40) + (unsigned long long)RB * W - 1) / ((unsigned long long)RB * W);
 
     const bool dbg = dbg_counts || dbg_gray || dbg_u8;
