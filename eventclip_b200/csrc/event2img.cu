@@ -697,6 +697,88 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
     }   // frame loop
 }
 
+// two fp32 fmas in one instruction (sm_100 packed math): d = a * b + c on both halves
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
+{
+    unsigned long long ra, rb, rc, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+
+// Normalise and store eight consecutive resampled bytes (row yo, columns x .. x+7, x % 8 == 0) in all three channels.
+__device__ __forceinline__ void emit8(const E2IParams &p, uint2 v, int yo, int x, char *ofr, uint8_t *du, bool wide, int cstride,
+                                      const int *rowoff, const int *coloff, const float *nlut, const uint2 *nlut3)
+{
+    if (du) *reinterpret_cast<uint2 *>(du + yo * OUT + x) = v;
+    if (p.out_fmt == EC_OUT_F32_NCHW) {
+        unsigned v8[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { v8[j] = __byte_perm(v.x, 0u, 0x4440u + j); v8[4 + j] = __byte_perm(v.y, 0u, 0x4440u + j); }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float *o = (float *)ofr + c * OUT * OUT + yo * OUT + x;
+            const float *nl = nlut + c * 256;
+            *reinterpret_cast<float4 *>(o) = make_float4(nl[v8[0]], nl[v8[1]], nl[v8[2]], nl[v8[3]]);
+            *reinterpret_cast<float4 *>(o + 4) = make_float4(nl[v8[4]], nl[v8[5]], nl[v8[6]], nl[v8[7]]);
+        }
+        return;
+    }
+    uint32_t w[3][4];      // [channel][pixel pair] as packed bf16
+    if (p.affine) {
+        // byte -> float through the 2^23 trick, one fma per channel, packed bf16 conversion
+        float2 f[4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            f[j] = make_float2(__uint_as_float(__byte_perm(v.x, 0x4b000000u, 0x7650u + 2 * j)) - 8388608.0f,
+                               __uint_as_float(__byte_perm(v.x, 0x4b000000u, 0x7651u + 2 * j)) - 8388608.0f);
+            f[2 + j] = make_float2(__uint_as_float(__byte_perm(v.y, 0x4b000000u, 0x7650u + 2 * j)) - 8388608.0f,
+                                   __uint_as_float(__byte_perm(v.y, 0x4b000000u, 0x7651u + 2 * j)) - 8388608.0f);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float2 na = make_float2(p.na[c], p.na[c]), nb = make_float2(p.nb[c], p.nb[c]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 r = ffma2(f[j], na, nb);
+                const __nv_bfloat162 h = __floats2bfloat162_rn(r.x, r.y);
+                w[c][j] = *reinterpret_cast<const uint32_t *>(&h);
+            }
+        }
+    } else {
+        uint2 t8[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            t8[j] = nlut3[__byte_perm(v.x, 0u, 0x4440u + j)];
+            t8[4 + j] = nlut3[__byte_perm(v.y, 0u, 0x4440u + j)];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            w[0][j] = __byte_perm(t8[2 * j].x, t8[2 * j + 1].x, 0x5410);
+            w[1][j] = __byte_perm(t8[2 * j].x, t8[2 * j + 1].x, 0x7632);
+            w[2][j] = __byte_perm(t8[2 * j].y, t8[2 * j + 1].y, 0x5410);
+        }
+    }
+    __nv_bfloat16 *orow = (__nv_bfloat16 *)ofr + rowoff[yo];
+    if (wide) {
+        __nv_bfloat16 *ob = orow + coloff[x >> 3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) *reinterpret_cast<uint4 *>(ob + c * cstride) = make_uint4(w[c][0], w[c][1], w[c][2], w[c][3]);
+    } else {
+        // patch size not a multiple of 8 (ViT-L/14): column pairs never straddle a patch
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            __nv_bfloat16 *ob = orow + coloff[(x >> 1) + j];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) *reinterpret_cast<uint32_t *>(ob + c * cstride) = w[c][j];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Tensor-core variant: one CTA per frame (the whole sensor's bins fit one SM), W % 4 == 0, upsampling or mild
 // downsampling (every 16-output tile reads a source window of <= 32 pixels).
@@ -705,8 +787,8 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
 //     hT[xo][y]   = clip8((sum_x kh[xo][x] gray[y][x] + 2^21) >> 22)      A = kh digits, B = gray rows as stored
 //     out[yo][xo] = clip8((sum_y kv[yo][y] hT[xo][y]  + 2^21) >> 22)      A = kv digits, B = rows of the transposed hT
 // The 22-bit taps are split into three signed base-256 digits; the three s32 partial sums recombine to exactly Pillow's
-// integer accumulator.  Shared memory: [bins | later hT + out8][gray plane]; the formatting phase then turns 8 output
-// bytes per thread into three 16-byte stores.
+// integer accumulator.  Shared memory: [bins | later hT][gray plane].  The vertical pass permutes its B columns so that
+// each lane ends up with 8 consecutive output pixels and stores them straight from registers (three 16-byte stores).
 // ------------------------------------------------------------------------------------------------
 template <bool DBG, bool COMPACT>
 __global__ void __launch_bounds__(1024, 1) event2img_tc_kernel(const E2IParams p)
@@ -723,7 +805,6 @@ __global__ void __launch_bounds__(1024, 1) event2img_tc_kernel(const E2IParams p
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw);
     uint8_t *hT = smem_raw;                      // [224][HP], over the dead bins
-    uint8_t *out8 = smem_raw + OUT * HP;         // [224][224] resampled bytes
     uint8_t *gray = smem_raw + p.gray_off;       // [H][W] (+ slack for the fragment loads of the last row tile)
     __shared__ unsigned long long red64[32];
     __shared__ unsigned red32[32][4];
@@ -940,118 +1021,51 @@ __global__ void __launch_bounds__(1024, 1) event2img_tc_kernel(const E2IParams p
         }
         __syncthreads();
 
-        // ---- P6: vertical pass on the tensor cores, hT [xo][y] -> out8 [yo][xo] ----
+        // ---- P6: vertical pass on the tensor cores fused with the normalisation and the output stores.
+        //      Column n of tile step t reads hT row 32 cg + 8 (n >> 1) + 2 t + (n & 1), so after four steps a lane holds
+        //      eight consecutive output pixels of rows yo and yo + 8: three 16-byte stores per row, no staging ----
         {
-            constexpr int n_tiles = OUT / 8;
+            uint8_t *du = (DBG && p.dbg_u8) ? p.dbg_u8 + (size_t)fid * OUT * OUT : nullptr;
+            char *ofr = (char *)p.out + (size_t)slot * frame_elems * (p.out_fmt == EC_OUT_F32_NCHW ? 4 : 2);
             if (wid < MT * parts) {
                 const int mt = wid % MT, part = wid / MT;
                 const int ws = s_ws[MT + mt];
                 uint4 a[3];
 #pragma unroll
                 for (int dg = 0; dg < 3; ++dg) a[dg] = __ldg(fragV + (mt * 3 + dg) * 32);
-                const int nt0 = part * n_tiles / parts, nt1 = (part + 1) * n_tiles / parts;
-                const uint8_t *src = hT + (nt0 * 8 + g) * HP + ws + tig * 4;
-                uint8_t *dst = out8 + (mt * 16 + g) * OUT + nt0 * 8 + tig * 2;
-#pragma unroll 2
-                for (int nt = nt0; nt < nt1; ++nt, src += 8 * HP, dst += 8) {
-                    const uint32_t b0 = *reinterpret_cast<const uint32_t *>(src);
-                    const uint32_t b1 = *reinterpret_cast<const uint32_t *>(src + 16);
-                    int c0[4], c1[4], c2[4];
-                    imma_s8u8(c0, a[0], b0, b1, 1 << (PREC - 1));
-                    imma_s8u8(c1, a[1], b0, b1, 0);
-                    imma_s8u8(c2, a[2], b0, b1, 0);
-                    unsigned px[4];
+                const uint8_t *src0 = hT + (8 * (g >> 1) + (g & 1)) * HP + ws + tig * 4;
+                const int yo = mt * 16 + g;
+                for (int cg = part; cg < OUT / 32; cg += parts) {
+                    uint32_t row_a[2], row_b[2];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) px[e] = (unsigned)__vimin_s32_relu((c0[e] + (c1[e] << 8) + (c2[e] << 16)) >> PREC, 255);
-                    *reinterpret_cast<uint16_t *>(dst) = (uint16_t)__byte_perm(px[0], px[1], 0x0040);
-                    *reinterpret_cast<uint16_t *>(dst + 8 * OUT) = (uint16_t)__byte_perm(px[2], px[3], 0x0040);
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t pa[2], pb[2];
+#pragma unroll
+                        for (int t = 0; t < 2; ++t) {
+                            const uint8_t *src = src0 + (32 * cg + 2 * (2 * h + t)) * HP;
+                            const uint32_t b0 = *reinterpret_cast<const uint32_t *>(src);
+                            const uint32_t b1 = *reinterpret_cast<const uint32_t *>(src + 16);
+                            int c0[4], c1[4], c2[4];
+                            imma_s8u8(c0, a[0], b0, b1, 1 << (PREC - 1));
+                            imma_s8u8(c1, a[1], b0, b1, 0);
+                            imma_s8u8(c2, a[2], b0, b1, 0);
+                            unsigned px[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                px[e] = (unsigned)__vimin_s32_relu((c0[e] + (c1[e] << 8) + (c2[e] << 16)) >> PREC, 255);
+                            pa[t] = __byte_perm(px[0], px[1], 0x0040);
+                            pb[t] = __byte_perm(px[2], px[3], 0x0040);
+                        }
+                        row_a[h] = __byte_perm(pa[0], pa[1], 0x5410);
+                        row_b[h] = __byte_perm(pb[0], pb[1], 0x5410);
+                    }
+                    const int x = 32 * cg + 8 * tig;
+                    emit8(p, make_uint2(row_a[0], row_a[1]), yo, x, ofr, du, wide, cstride, rowoff, coloff, nlut, nlut3);
+                    emit8(p, make_uint2(row_b[0], row_b[1]), yo + 8, x, ofr, du, wide, cstride, rowoff, coloff, nlut, nlut3);
                 }
             }
         }
-        __syncthreads();
-
-        // ---- P7: normalise LUT + output formatting, 8 bytes of out8 per item; offsets from two small tables ----
-        {
-            uint8_t *du = (DBG && p.dbg_u8) ? p.dbg_u8 + (size_t)fid * OUT * OUT : nullptr;
-            if (wide) {
-                constexpr int NG = OUT / 8;
-                if (p.out_fmt == EC_OUT_F32_NCHW) {
-                    float *ofr = (float *)p.out + (size_t)slot * 3 * OUT * OUT;
-                    for (int it = tid; it < OUT * NG; it += NT) {
-                        const uint2 v = *reinterpret_cast<const uint2 *>(out8 + it * 8);
-                        if (du) *reinterpret_cast<uint2 *>(du + it * 8) = v;
-                        unsigned v8[8];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) { v8[j] = __byte_perm(v.x, 0u, 0x4440u + j); v8[4 + j] = __byte_perm(v.y, 0u, 0x4440u + j); }
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            float *o = ofr + c * OUT * OUT + it * 8;
-                            const float *nl = nlut + c * 256;
-                            *reinterpret_cast<float4 *>(o) = make_float4(nl[v8[0]], nl[v8[1]], nl[v8[2]], nl[v8[3]]);
-                            *reinterpret_cast<float4 *>(o + 4) = make_float4(nl[v8[4]], nl[v8[5]], nl[v8[6]], nl[v8[7]]);
-                        }
-                    }
-                } else {
-                    __nv_bfloat16 *ofr = (__nv_bfloat16 *)p.out + (size_t)slot * frame_elems;
-                    for (int it = tid; it < OUT * NG; it += NT) {
-                        const int yo = it / NG, xg = it - yo * NG;
-                        const uint2 v = *reinterpret_cast<const uint2 *>(out8 + it * 8);
-                        if (du) *reinterpret_cast<uint2 *>(du + it * 8) = v;
-                        uint4 o0, o1, o2;
-                        if (p.affine) {
-                            // byte -> float through the 2^23 trick, one fma per channel, packed bf16 conversion
-                            float f[8];
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                f[j] = __uint_as_float(__byte_perm(v.x, 0x4b000000u, 0x7650u + j)) - 8388608.0f;
-                                f[4 + j] = __uint_as_float(__byte_perm(v.y, 0x4b000000u, 0x7650u + j)) - 8388608.0f;
-                            }
-                            uint32_t w[3][4];
-#pragma unroll
-                            for (int c = 0; c < 3; ++c)
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const __nv_bfloat162 h = __floats2bfloat162_rn(__fmaf_rn(f[2 * j], p.na[c], p.nb[c]),
-                                                                                   __fmaf_rn(f[2 * j + 1], p.na[c], p.nb[c]));
-                                    w[c][j] = *reinterpret_cast<const uint32_t *>(&h);
-                                }
-                            o0 = make_uint4(w[0][0], w[0][1], w[0][2], w[0][3]);
-                            o1 = make_uint4(w[1][0], w[1][1], w[1][2], w[1][3]);
-                            o2 = make_uint4(w[2][0], w[2][1], w[2][2], w[2][3]);
-                        } else {
-                            uint2 t8[8];
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                t8[j] = nlut3[__byte_perm(v.x, 0u, 0x4440u + j)];
-                                t8[4 + j] = nlut3[__byte_perm(v.y, 0u, 0x4440u + j)];
-                            }
-                            o0.x = __byte_perm(t8[0].x, t8[1].x, 0x5410); o1.x = __byte_perm(t8[0].x, t8[1].x, 0x7632); o2.x = __byte_perm(t8[0].y, t8[1].y, 0x5410);
-                            o0.y = __byte_perm(t8[2].x, t8[3].x, 0x5410); o1.y = __byte_perm(t8[2].x, t8[3].x, 0x7632); o2.y = __byte_perm(t8[2].y, t8[3].y, 0x5410);
-                            o0.z = __byte_perm(t8[4].x, t8[5].x, 0x5410); o1.z = __byte_perm(t8[4].x, t8[5].x, 0x7632); o2.z = __byte_perm(t8[4].y, t8[5].y, 0x5410);
-                            o0.w = __byte_perm(t8[6].x, t8[7].x, 0x5410); o1.w = __byte_perm(t8[6].x, t8[7].x, 0x7632); o2.w = __byte_perm(t8[6].y, t8[7].y, 0x5410);
-                        }
-                        __nv_bfloat16 *ob = ofr + (rowoff[yo] + coloff[xg]);
-                        *reinterpret_cast<uint4 *>(ob) = o0;
-                        *reinterpret_cast<uint4 *>(ob + cstride) = o1;
-                        *reinterpret_cast<uint4 *>(ob + 2 * cstride) = o2;
-                    }
-                }
-            } else {
-                // patch size not a multiple of 8 (ViT-L/14): column pairs never straddle a patch
-                __nv_bfloat16 *ofr = (__nv_bfloat16 *)p.out + (size_t)slot * frame_elems;
-                for (int it = tid; it < OUT * (OUT / 2); it += NT) {
-                    const int yo = it / (OUT / 2), xp = it - yo * (OUT / 2);
-                    const unsigned two = *reinterpret_cast<const uint16_t *>(out8 + it * 2);
-                    if (du) *reinterpret_cast<uint16_t *>(du + it * 2) = (uint16_t)two;
-                    const uint2 t0 = nlut3[two & 0xffu], t1 = nlut3[two >> 8];
-                    __nv_bfloat16 *ob = ofr + (rowoff[yo] + coloff[xp]);
-                    *reinterpret_cast<unsigned *>(ob) = __byte_perm(t0.x, t1.x, 0x5410);
-                    *reinterpret_cast<unsigned *>(ob + cstride) = __byte_perm(t0.x, t1.x, 0x7632);
-                    *reinterpret_cast<unsigned *>(ob + 2 * cstride) = __byte_perm(t0.y, t1.y, 0x5410);
-                }
-            }
-        }
-        __syncthreads();   // out8 / hT share the bins' storage
+        __syncthreads();   // hT shares the bins' storage
     }   // frame loop
 }
 
@@ -1400,13 +1414,13 @@ static int event2img_impl(const float *events, const uint32_t *events_c, const e
     {
         static const bool off = getenv("EC_E2I_TC") && atoi(getenv("EC_E2I_TC")) == 0;    // 0 forces the SIMT kernel
         const int HP = (H + 3) & ~3;
-        size_t region_a = (size_t)H * W * 4;
-        if (region_a < (size_t)OUT * HP + (size_t)OUT * OUT) region_a = (size_t)OUT * HP + (size_t)OUT * OUT;
+        size_t region_a = (size_t)H * W * 4;                       // bins, later the transposed horizontal result
+        if (region_a < (size_t)OUT * HP) region_a = (size_t)OUT * HP;
         region_a = (region_a + 15) & ~(size_t)15;
         const size_t gray_bytes = ((size_t)(H + 8) * W + 32 + 15) & ~(size_t)15;       // last row tile reads up to 7 rows + 31 bytes past the plane
         const size_t tc_smem = region_a + gray_bytes;
         tc = !off && CS == 1 && W % 4 == 0 && H >= 16 && tb.KSH == 1 && tb.KSV == 1 && tc_smem <= (size_t)221 * 1024;
-        if (tc) { smem = tc_smem; p.gray_off = (int)region_a; }
+        if (tc) { smem = tc_smem; p.gray_off = (int)region_a; if (NT < 512) NT = 512; }     // 14 warps carry the matrix passes
     }
     typedef void (*kern_t)(const E2IParams);
     kern_t kern;
