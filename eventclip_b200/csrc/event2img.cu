@@ -130,6 +130,30 @@ __device__ unsigned compute_keep(unsigned long long n, unsigned long long S1, un
     return c > 0xfffffffell ? 0xfffffffeu : (unsigned)c;
 }
 
+// Same result as compute_keep() for the sizes one CTA histograms (n * S2 < 2^56): 64-bit integers and a float estimate;
+// the exact integer comparison walks the estimate to the answer, so the estimate's rounding never matters.
+__device__ unsigned compute_keep_small(unsigned long long n, unsigned long long S1, unsigned long long S2, int t)
+{
+    if (t <= 0 || n == 0) return 0xffffffffu;
+    if (__umul64hi(n, S2) != 0 || n * S2 >= (1ull << 56) || n >= (1ull << 31) || t != 10) return compute_keep(n, S1, S2, t);
+    const unsigned long long T = 100ull * (n * S2 - S1 * S1);                 // t^2 n^2 var < 2^63
+    auto hot = [&](long long c) {
+        const long long d = c * (long long)n - (long long)S1;
+        if (d <= 0) return false;
+        if (d > 3037000499ll) return true;                                       // d^2 >= 2^63 > T
+        return (unsigned long long)(d * d) > T;
+    };
+    const float thr = ((float)S1 + sqrtf((float)T)) / (float)n;                 // mean + 10 std
+    long long c = (long long)floorf(thr);
+    if (c < 0) c = 0;
+    if (c > 0x7fffffffll) c = 0x7fffffffll;
+    int it = 0;
+    for (; it < 64 && c > 0 && hot(c); ++it) --c;
+    for (; it < 128 && !hot(c + 1); ++it) ++c;
+    if (it >= 128) return compute_keep(n, S1, S2, t);                            // estimate far off: take the exact slow path
+    return c > 0xfffffffell ? 0xfffffffeu : (unsigned)c;
+}
+
 // vis.py:27-39 evaluated as numpy >= 2 does (float64); `hist @ cmap` is a 2-term BLAS dot = one fma.
 __device__ __noinline__ unsigned gray_px(unsigned pos, unsigned neg, unsigned mx, bool mask)
 {
@@ -841,6 +865,8 @@ __global__ void __launch_bounds__(1024, 1) event2img_tc_kernel(const E2IParams p
     }
     __syncthreads();
 
+    const int ht16 = (OUT * HP + 15) >> 4;          // 16-byte groups of the bins that hT overlays
+    bool bins_clean = false;                        // bins above hT already zero (cleared by the spare warps of the last frame)
     for (int fid = blockIdx.x; fid < p.n_frames; fid += gridDim.x) {
         const ec_frame fr = p.frames[fid];
         const int slot = fr.out_slot;
@@ -862,11 +888,13 @@ __global__ void __launch_bounds__(1024, 1) event2img_tc_kernel(const E2IParams p
             continue;     // uniform; the previous frame ended with a barrier
         }
 
-        // ---- P0: clear the bins (W % 4 == 0: whole 16-byte groups) ----
+        // ---- P0: clear the bins (W % 4 == 0: whole 16-byte groups).  After the first frame only the part the previous
+        //      frame's hT dirtied is left: the warps without matrix work cleared the rest during the vertical pass ----
         {
             uint4 *h4 = reinterpret_cast<uint4 *>(hist);
+            const int n16 = bins_clean ? min(ht16, HW >> 2) : (HW >> 2);
 #pragma unroll 4
-            for (int i = tid; i < (HW >> 2); i += NT) h4[i] = make_uint4(0, 0, 0, 0);
+            for (int i = tid; i < n16; i += NT) h4[i] = make_uint4(0, 0, 0, 0);
         }
         __syncthreads();
 
@@ -902,7 +930,7 @@ __global__ void __launch_bounds__(1024, 1) event2img_tc_kernel(const E2IParams p
                 if (lane == 0) {
                     if (mx > 0xffffu) fl |= EC_STATUS_COUNT_OVERFLOW;      // a 16-bit field wrapped
                     const unsigned long long n = cnz ? (unsigned long long)nnz : (unsigned long long)HW * 2ull;
-                    s_keep = compute_keep(n, nacc, s2, 10);
+                    s_keep = compute_keep_small(n, nacc, s2, 10);
                     if (fl) atomicOr(p.status, (int)fl);
                 }
             } else {
@@ -1063,7 +1091,13 @@ __global__ void __launch_bounds__(1024, 1) event2img_tc_kernel(const E2IParams p
                     emit8(p, make_uint2(row_a[0], row_a[1]), yo, x, ofr, du, wide, cstride, rowoff, coloff, nlut, nlut3);
                     emit8(p, make_uint2(row_b[0], row_b[1]), yo + 8, x, ofr, du, wide, cstride, rowoff, coloff, nlut, nlut3);
                 }
+            } else {
+                // spare warps: the bins above hT are dead since P4 -- clear them for the next frame now
+                uint4 *h4 = reinterpret_cast<uint4 *>(hist);
+                const int spare = NT - MT * parts * 32;
+                for (int i = ht16 + tid - MT * parts * 32; i < (HW >> 2); i += spare) h4[i] = make_uint4(0, 0, 0, 0);
             }
+            bins_clean = nwarps > MT * parts;
         }
         __syncthreads();   // hT shares the bins' storage
     }   // frame loop
