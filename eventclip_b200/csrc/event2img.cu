@@ -1214,10 +1214,36 @@ int build_frags(const std::vector<int32_t> &axis, int ksize, std::vector<int32_t
     return KS;
 }
 
+// torchvision Resize(224) + CenterCrop(224) as the two cropped axis tables
+void resample_axes(int H, int W, std::vector<int32_t> &hx, std::vector<int32_t> &vy, int &KH, int &KV)
+{
+    // Resize(224): shorter side -> 224, longer side -> int(224 * long / short)
+    int Ho, Wo;
+    if (W <= H) { Wo = OUT; Ho = (int)(224.0 * H / W); } else { Ho = OUT; Wo = (int)(224.0 * W / H); }
+    // CenterCrop(224): offsets int(round((size - 224) / 2.0)), Python's round-half-even
+    const int top = (int)std::nearbyint((Ho - OUT) / 2.0), left = (int)std::nearbyint((Wo - OUT) / 2.0);
+    KH = build_axis(W, Wo, left, hx);
+    KV = build_axis(H, Ho, top, vy);
+}
+
+// Tensor-core kernel: whole sensor in one CTA, 4-byte aligned rows, one 32-wide source window per 16-output tile
+// (KSH == KSV == 1).  Returns whether it applies and its shared-memory layout.
+bool tc_plan(int H, int W, int CS, int KSH, int KSV, size_t &smem, int &gray_off)
+{
+    static const bool off = getenv("EC_E2I_TC") && atoi(getenv("EC_E2I_TC")) == 0;    // 0 forces the SIMT kernel
+    const int HP = (H + 3) & ~3;
+    size_t region_a = (size_t)H * W * 4;                       // bins, later the transposed horizontal result
+    if (region_a < (size_t)OUT * HP) region_a = (size_t)OUT * HP;
+    region_a = (region_a + 15) & ~(size_t)15;
+    const size_t gray_bytes = ((size_t)(H + 8) * W + 32 + 15) & ~(size_t)15;       // last row tile reads up to 7 rows + 31 bytes past the plane
+    if (off || CS != 1 || W % 4 != 0 || H < 16 || KSH != 1 || KSV != 1 || region_a + gray_bytes > (size_t)221 * 1024) return false;
+    smem = region_a + gray_bytes;
+    gray_off = (int)region_a;
+    return true;
+}
+
 std::mutex g_mu;
 std::map<std::tuple<int, int, int>, Tables> g_tables;
-
-int python_round_half_even(double v) { return (int)std::nearbyint(v); }
 
 int get_tables(int H, int W, cudaStream_t stream, Tables &out)
 {
@@ -1227,15 +1253,9 @@ int get_tables(int H, int W, cudaStream_t stream, Tables &out)
     auto key = std::make_tuple(dev, H, W);
     auto it = g_tables.find(key);
     if (it != g_tables.end()) { out = it->second; return EC_OK; }
-    // torchvision Resize(224): shorter side -> 224, longer side -> int(224 * long / short)
-    int Ho, Wo;
-    if (W <= H) { Wo = OUT; Ho = (int)(224.0 * H / W); } else { Ho = OUT; Wo = (int)(224.0 * W / H); }
-    // CenterCrop(224): offsets int(round((size - 224) / 2.0))
-    const int top = python_round_half_even((Ho - OUT) / 2.0), left = python_round_half_even((Wo - OUT) / 2.0);
     std::vector<int32_t> hx, vy;
     Tables t;
-    t.KH = build_axis(W, Wo, left, hx);
-    t.KV = build_axis(H, Ho, top, vy);
+    resample_axes(H, W, hx, vy, t.KH, t.KV);
     std::vector<int32_t> all(hx);
     t.off_vy = all.size();
     all.insert(all.end(), vy.begin(), vy.end());
@@ -1333,9 +1353,16 @@ extern "C" int ec_event2img_geometry(int H, int W, int *cluster_size, int *threa
 {
     int CS, RB, NT;
     size_t smem;
-    if (H <= 0 || W <= 0 || geometry(H, W, CS, RB, NT, smem) != EC_OK) {
+    if (H < 8 || W < 8 || geometry(H, W, CS, RB, NT, smem) != EC_OK) {
         ec::set_error("ec_event2img_geometry: sensor %dx%d unsupported", H, W);
         return EC_ERR_UNSUPPORTED;
+    }
+    if (CS == 1) {      // same choice ec_event2img makes: the tensor-core kernel when its tiling applies
+        std::vector<int32_t> hx, vy, frag, ws;
+        int KH, KV, gray_off;
+        resample_axes(H, W, hx, vy, KH, KV);
+        const int KSH = build_frags(hx, KH, frag, ws), KSV = build_frags(vy, KV, frag, ws);
+        if (tc_plan(H, W, CS, KSH, KSV, smem, gray_off) && NT < 512) NT = 512;
     }
     if (cluster_size) *cluster_size = CS;
     if (threads) *threads = NT;
@@ -1443,19 +1470,8 @@ static int event2img_impl(const float *events, const uint32_t *events_c, const e
     p.band_magic = ((1ull << 40) + (unsigned long long)RB * W - 1) / ((unsigned long long)RB * W);
 
     const bool dbg = dbg_counts || dbg_gray || dbg_u8;
-    // tensor-core kernel: whole sensor in one CTA, 4-byte aligned rows, one 32-wide source window per 16-output tile
-    bool tc = false;
-    {
-        static const bool off = getenv("EC_E2I_TC") && atoi(getenv("EC_E2I_TC")) == 0;    // 0 forces the SIMT kernel
-        const int HP = (H + 3) & ~3;
-        size_t region_a = (size_t)H * W * 4;                       // bins, later the transposed horizontal result
-        if (region_a < (size_t)OUT * HP) region_a = (size_t)OUT * HP;
-        region_a = (region_a + 15) & ~(size_t)15;
-        const size_t gray_bytes = ((size_t)(H + 8) * W + 32 + 15) & ~(size_t)15;       // last row tile reads up to 7 rows + 31 bytes past the plane
-        const size_t tc_smem = region_a + gray_bytes;
-        tc = !off && CS == 1 && W % 4 == 0 && H >= 16 && tb.KSH == 1 && tb.KSV == 1 && tc_smem <= (size_t)221 * 1024;
-        if (tc) { smem = tc_smem; p.gray_off = (int)region_a; if (NT < 512) NT = 512; }     // 14 warps carry the matrix passes
-    }
+    const bool tc = tc_plan(H, W, CS, tb.KSH, tb.KSV, smem, p.gray_off);
+    if (tc && NT < 512) NT = 512;      // 14 warps carry the matrix passes
     typedef void (*kern_t)(const E2IParams);
     kern_t kern;
     if (tc)

@@ -217,3 +217,56 @@ def test_center_and_flip_events_on_device(cuda_dev, golden_dir):
     cen = ops.center_events(torch.from_numpy(ev).to(cuda_dev), torch.tensor([0, len(ev)], device=cuda_dev), shape)
     fr = events2frames(cen, "event_count", "event_histogram", shape=shape, N=20000, grayscale=True)
     assert (fr == orc.events2frames(orc.center_events(ev, shape), shape, 20000)).all()
+
+
+@pytest.mark.parametrize("shape,N", [((34, 34), 1500),      # N-MNIST: W % 4 != 0 -> SIMT kernel, one CTA
+                                     ((128, 128), 5000),    # DVS128: tensor-core kernel
+                                     ((240, 180), 20000),   # portrait: the crop falls on the rows
+                                     ((64, 200), 6000),     # wide: both axes up-sampled, 175 columns cropped away
+                                     ((260, 346), 25000)])  # DAVIS346: two-CTA cluster, W % 4 != 0
+@pytest.mark.parametrize("flags", [(False, True), (True, False)])
+def test_other_sensor_shapes_vs_oracle(cuda_dev, shape, N, flags):
+    """Sensors outside BASELINE.json's three: every kernel variant (tensor-core, SIMT, cluster) against the oracle."""
+    cnz, bg = flags
+    for seed, kind in ((1, "uniform"), (2, "clustered"), (3, "hotpixel")):
+        ev = synth_events(shape, int(2.6 * N) + 7, seed, kind)
+        img, dbg, K = _run_frames(ev, shape, N, cnz, bg, cuda_dev)
+        i0, i1 = orc.split_event_count(len(ev), N)
+        assert K == len(i0)
+        img = img.cpu().numpy()
+        for k in range(K):
+            counts = orc.histogram(ev[i0[k]:i1[k]], shape)
+            assert (dbg["counts"][k].cpu().numpy() == counts).all(), (shape, kind, k)
+            gray, _, _ = orc.frame_from_counts(counts, cnz, bg)
+            assert (dbg["gray"][k].cpu().numpy() == gray).all(), (shape, kind, k)
+            u8 = orc.resize_crop_224(gray)
+            assert (dbg["u8"][k].cpu().numpy() == u8).all(), (shape, kind, k)
+            assert (img[k] == orc.normalize(u8)).all(), (shape, kind, k)
+
+
+def test_simt_and_tensor_core_kernels_agree(cuda_dev):
+    """EC_E2I_TC=0 forces the SIMT kernel (read once per process, hence the subprocess): same bytes as the default."""
+    import subprocess
+    import sys
+    code = ("import hashlib, numpy as np, torch\n"
+            "from eventclip_b200 import ops\n"
+            "from eventclip_b200.synth import SENSORS, synth_batch\n"
+            "for ds in ('n_caltech101', 'n_cars'):\n"
+            "    cfg = SENSORS[ds]\n"
+            "    ev, off = synth_batch(ds, 4, 77, kind='clustered')\n"
+            "    frames, valid, chunks, nv = ops.plan_frames(off, cfg['N'], 3, compact=True)\n"
+            "    dev = torch.device('cuda', 0)\n"
+            "    for out, patch in (('f32', 0), ('patch', 16)):\n"
+            "        img, st, _ = ops.event2img(torch.from_numpy(ev).to(dev), frames.to(dev), cfg['shape'], nv, cfg['count_non_zero'],\n"
+            "                                   cfg['background_mask'], out=out, patch=patch)\n"
+            "        torch.cuda.synchronize()\n"
+            "        a = img.view(torch.int16) if img.dtype == torch.bfloat16 else img\n"
+            "        print(ds, out, int(st.item()), hashlib.sha256(a.cpu().numpy().tobytes()).hexdigest())\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for tc in ("1", "0"):
+        env = dict(os.environ, EC_E2I_TC=tc, PYTHONPATH=root)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=root, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout)
+    assert outs[0] == outs[1] and len(outs[0].splitlines()) == 4, outs
