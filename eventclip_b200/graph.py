@@ -105,6 +105,72 @@ class GraphedClassifier:
         return ent.out
 
 
+    def stream(self, batches, result=None, pre=None):
+        """Pipelined serving loop over an iterable of data_dicts with PINNED HOST events -- the role the reference's
+        DataLoader prefetch + `non_blocking` copies play around `model(data_dict)` (test.py:55-81).  While batch i is
+        replayed, a copy stream uploads batch i+1 into one of two staging buffers; `result(out_dict)` (default: top-1
+        of the aggregated logits) is read back through pinned memory and yielded as a host tensor, in order, once its
+        batch has finished.  `pre()` runs on the compute stream before every replay (bench.py flushes L2 there)."""
+        dev = self.dev
+        if result is None:
+            result = lambda out: out["top5_logits"][:, 0]
+        if not hasattr(self, "_stage"):
+            self._stage = [torch.empty_like(self.events) for _ in range(2)]
+            self._copy = torch.cuda.Stream(device=dev)
+            self._uploaded = [torch.cuda.Event() for _ in range(2)]
+            self._consumed = [torch.cuda.Event() for _ in range(2)]
+        cur = torch.cuda.current_stream(dev)
+        done = [torch.cuda.Event() for _ in range(2)]
+        host_res = [None, None]
+
+        def upload(i, d):
+            ev = d["events"]
+            if ev.is_cuda:
+                return
+            if not ev.is_pinned():
+                raise L.ECError("GraphedClassifier.stream: host events must be pinned (torch.Tensor.pin_memory())")
+            if ev.shape[0] > self.events.shape[0]:
+                raise L.ECError(f"batch has {ev.shape[0]} events but the graph buffer holds {self.events.shape[0]}")
+            with torch.cuda.stream(self._copy):
+                if i >= 2:
+                    self._copy.wait_event(self._consumed[i % 2])      # batch i-2 has left this staging buffer
+                self._stage[i % 2][:ev.shape[0]].copy_(ev, non_blocking=True)
+                self._uploaded[i % 2].record(self._copy)
+
+        def launch(i, d):
+            ev = d["events"]
+            if not ev.is_cuda:
+                cur.wait_event(self._uploaded[i % 2])
+                ev = self._stage[i % 2][:ev.shape[0]]
+            if pre is not None:
+                pre()
+            out = self(dict(d, events=ev))                            # device-to-device copy into the graph's input + replay
+            self._consumed[i % 2].record(cur)
+            r = result(out)
+            if host_res[i % 2] is None or host_res[i % 2].shape != r.shape or host_res[i % 2].dtype != r.dtype:
+                host_res[i % 2] = torch.empty(r.shape, dtype=r.dtype).pin_memory()
+            host_res[i % 2].copy_(r, non_blocking=True)
+            done[i % 2].record(cur)
+
+        it = iter(batches)
+        nxt = next(it, None)
+        if nxt is None:
+            return
+        upload(0, nxt)
+        i = 0
+        while nxt is not None:
+            d, nxt = nxt, next(it, None)
+            if nxt is not None:
+                upload(i + 1, nxt)                                    # in flight while batch i computes
+            launch(i, d)
+            if i >= 1:
+                done[(i - 1) % 2].synchronize()
+                yield host_res[(i - 1) % 2].clone()
+            i += 1
+        done[(i - 1) % 2].synchronize()
+        yield host_res[(i - 1) % 2].clone()
+
+
 class GraphedFineTuner:
     """train.FineTuner with the device work replayed from CUDA graphs (a step is ~470 kernel launches on ViT-B/16).
 

@@ -219,6 +219,37 @@ def test_cuda_graph_replay_matches_eager(cuda_dev):
     assert len(g.cache) == 2
 
 
+def test_pipelined_stream_matches_sequential_calls(cuda_dev):
+    """GraphedClassifier.stream (uploads one batch ahead on a copy stream, results through pinned memory) yields, in
+    order, exactly what one call per batch returns -- including batches of different geometry and a single batch."""
+    from eventclip_b200.graph import GraphedClassifier
+    cfg = SENSORS["n_cars"]
+    q = dict(max_imgs=10, N=cfg["N"], split_method="event_count", convert_method="event_histogram", grayscale=True,
+             count_non_zero=True, background_mask=False)
+    model = clip.init_weights_(clip.CLIP("ViT-tiny/32"), seed=8).to(cuda_dev).eval()
+    text = clip_oracle.synth_text_feats(7, 64, 9)
+    zs = ZSCLIPClassifier(clip_dict=dict(clip_model=model, prompt="a {}", class_names=None, agg_func="mean",
+                                         text_feats=text)).to(cuda_dev).eval()
+    zs.attach_event_frontend(q, cfg["shape"], cfg["max_n"])
+    g = GraphedClassifier(zs, max_events=8 * 12500)
+    batches = []
+    for seed, B, E in ((1, 8, 4000), (2, 8, 4000), (3, 5, 9000), (4, 8, 4000), (5, 8, 300), (6, 8, 4000), (7, 8, 4000)):
+        ev, off = synth_batch("n_cars", B, seed, E=E)
+        batches.append(dict(events=torch.from_numpy(ev).pin_memory(), event_offsets=torch.from_numpy(off)))
+    with torch.no_grad():
+        want = [g(d)["logits"].cpu().clone() for d in batches]
+        got = list(g.stream(iter(batches), result=lambda out: out["logits"]))
+        one = list(g.stream(batches[2:3], result=lambda out: out["logits"]))
+        again = list(g.stream(batches, result=lambda out: out["logits"]))
+    assert len(got) == len(batches) and len(one) == 1
+    for a, b, c in zip(want, got, again):
+        assert torch.equal(a, b) and torch.equal(a, c)
+    assert torch.equal(one[0], want[2])
+    assert list(g.stream([])) == []
+    with pytest.raises(Exception):
+        list(g.stream([dict(events=torch.from_numpy(ev), event_offsets=torch.from_numpy(off))]))    # pageable host memory
+
+
 def test_few_shot_nimagenet_events_to_logits_vs_oracle(cuda_dev):
     """BASELINE config 3 in miniature: few-shot joint adapter (text-trans, residual 0.95) on N-ImageNet-shaped streams
     (480x640, 8-CTA cluster kernel, 14 chunks of which 2 host-drawn ones are used), ViT-B/16, 1000 classes."""
