@@ -160,6 +160,28 @@ def reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
+def event2img_cpu_mev(ds, n_samples):
+    """SURVEY 8(d) CPU baseline of the second metric: the oracle's C port of events -> float32 frames on the host cores
+    (one sample per worker thread, ctypes releases the GIL), Mevents/s of events histogrammed.  Bounded sample."""
+    from concurrent.futures import ThreadPoolExecutor
+    from eventclip_b200.datasets import Event2Image
+    from eventclip_b200.synth import SENSORS, synth_batch
+    from oracle import event2img as orc
+    cfg = SENSORS[ds]
+    T = Event2Image(qargs(cfg), cfg["shape"], cfg["max_n"]).max_imgs
+    ev, off = synth_batch(ds, n_samples, 100)
+    cores = os.cpu_count() or 1
+    work = lambda b: orc.event2img_sample(ev[off[b]:off[b + 1]], cfg["shape"], cfg["N"], T, cfg["count_non_zero"],
+                                          cfg["background_mask"], sel=np.arange(T), only_selected=True)[2]
+    work(0)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        ks = list(ex.map(work, range(n_samples)))
+    dt = time.perf_counter() - t0
+    used = sum(min(int(k), T) * min(cfg["N"], int(off[b + 1] - off[b])) for b, k in enumerate(ks))
+    return dict(mevents_per_s=used / dt / 1e6, cores=cores, kind="port", sample=f"{n_samples} samples, {used} events histogrammed")
+
+
 def event2img_metric(dev, pk):
     """BASELINE.json's second metric: Gevents/s of the fused kernel alone (bf16 patch rows out), HBM roofline."""
     from eventclip_b200 import ops
@@ -218,6 +240,10 @@ def event2img_metric(dev, pk):
                        algorithmic_bytes=byts, achieved_gbs=byts / ms / 1e6, frac=byts / ms / 1e6 / pk["hbm_gbs"],
                        input_mb=evs.nbytes / 1e6, geometry=ops.event2img_geometry(cfg["shape"]))
         del evd, outbuf
+        try:
+            out[ds]["cpu_baseline"] = event2img_cpu_mev(ds, {"n_caltech101": 64, "n_cars": 512, "n_imagenet": 16}[ds])
+        except Exception as e:      # the oracle is test infrastructure: never let it take the bench line down
+            out[ds]["cpu_baseline"] = dict(error=str(e)[:200])
     return out
 
 

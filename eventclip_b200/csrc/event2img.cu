@@ -528,7 +528,14 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
     }
 
     // ---- P4: gray byte per pixel (small counts through a per-frame LUT), compacted in place ----
-    for (int i = tid; i < GLUT_N * GLUT_N; i += NT) glut[i] = (uint8_t)gray_px(i % GLUT_N, i / GLUT_N, mx, mask);
+    // the hot-pixel cut is folded into the LUT: a count above `keep` looks up the entry of a zero count
+    {
+        const int side = (int)min(s_mall, (unsigned)(GLUT_N - 1)) + 1;      // pairs up to the largest raw count occur
+        for (int k = tid; k < side * side; k += NT) {
+            const unsigned ln = k / side, lp = k - ln * side;
+            glut[ln * GLUT_N + lp] = (uint8_t)gray_px(lp > keep ? 0u : lp, ln > keep ? 0u : ln, mx, mask);
+        }
+    }
     __syncthreads();
     {
         // Round r packs pixel groups [r*NT, (r+1)*NT): it reads words [4rNT, 4(r+1)NT) and writes words [rNT, (r+1)NT),
@@ -542,10 +549,16 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
             if (j < ng) {
                 const uint4 w4 = h4[j];
                 const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
-                if (!DBG && (w4.x | w4.y | w4.z | w4.w) == 0) {
+                const uint32_t any = w4.x | w4.y | w4.z | w4.w;
+                if (!DBG && any == 0) {
                     pk = 0x01010101u * glut[0];          // four empty pixels
+                } else if (!DBG && (any & 0xffe0ffe0u) == 0) {
+                    // all eight counts < 32: four byte lookups (the LUT already applies the cut)
+                    const unsigned g0 = glut[((w4.x >> 11) & 0x3e0u) | w4.x & 0x1fu], g1 = glut[((w4.y >> 11) & 0x3e0u) | w4.y & 0x1fu];
+                    const unsigned g2 = glut[((w4.z >> 11) & 0x3e0u) | w4.z & 0x1fu], g3 = glut[((w4.w >> 11) & 0x3e0u) | w4.w & 0x1fu];
+                    pk = __byte_perm(__byte_perm(g0, g1, 0x0040), __byte_perm(g2, g3, 0x0040), 0x5410);
                 } else
-#pragma unroll
+#pragma unroll 1
                 for (int q = 0; q < 4; ++q) {
                     uint32_t w = ws[q];
                     if (DBG && p.dbg_counts && 4 * j + q < nband) {
@@ -945,6 +958,7 @@ __global__ void __launch_bounds__(1024, 1) event2img_tc_kernel(const E2IParams p
         }
         const unsigned keep = s_keep;
         const bool hot = mx > keep;
+        const unsigned mall = mx;         // largest raw count
         // ---- P3 (only when some bin exceeds `keep`): max of the surviving bins, LUT again ----
         if (hot) {
             unsigned m = 0;
@@ -964,10 +978,11 @@ __global__ void __launch_bounds__(1024, 1) event2img_tc_kernel(const E2IParams p
             if (lane == 0) red32[wid][0] = m;
             __syncthreads();
             mx = warp_max_u32(lane < nwarps ? red32[lane][0] : 0u);
-            const int side = (int)min(mx, (unsigned)(GLUT_N - 1)) + 1;
+            // the cut is folded into the LUT (a count above `keep` reads as 0); pairs up to the largest raw count occur
+            const int side = (int)min(mall, (unsigned)(GLUT_N - 1)) + 1;
             for (int k = tid; k < side * side; k += NT) {
-                const int neg = k / side, pos = k - neg * side;
-                glut[neg * GLUT_N + pos] = (uint8_t)gray_px(pos, neg, mx, mask);
+                const unsigned ln = k / side, lp = k - ln * side;
+                glut[ln * GLUT_N + lp] = (uint8_t)gray_px(lp > keep ? 0u : lp, ln > keep ? 0u : ln, mx, mask);
             }
             __syncthreads();
         }
@@ -982,7 +997,7 @@ __global__ void __launch_bounds__(1024, 1) event2img_tc_kernel(const E2IParams p
                 const uint4 w4 = h4[j];
                 const uint32_t any = w4.x | w4.y | w4.z | w4.w;
                 uint32_t pk = bg4;
-                if (!DBG && !hot && (any & 0xffe0ffe0u) == 0) {
+                if (!DBG && (any & 0xffe0ffe0u) == 0) {
                     // all eight counts < 32 (the common case): four byte lookups, no per-pixel branches
                     if (any) {
                         const unsigned g0 = glut[((w4.x >> 11) & 0x3e0u) | w4.x & 0x1fu], g1 = glut[((w4.y >> 11) & 0x3e0u) | w4.y & 0x1fu];
