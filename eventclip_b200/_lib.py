@@ -14,7 +14,7 @@ EC_ERR_ARG, EC_ERR_CUDA, EC_ERR_UNSUPPORTED, EC_ERR_CAPACITY = -1, -2, -3, -4
 EC_STATUS_BAD_COORD, EC_STATUS_COUNT_OVERFLOW = 1, 2
 EC_FLAG_COUNT_NON_ZERO, EC_FLAG_BACKGROUND_MASK = 1, 2
 EC_OUT_F32_NCHW, EC_OUT_BF16_NCHW, EC_OUT_BF16_PATCH = 0, 1, 2
-EC_EPI_BF16, EC_EPI_BF16_QGELU, EC_EPI_F32_RESADD, EC_EPI_F32, EC_EPI_PATCH = 0, 1, 2, 3, 4
+EC_EPI_BF16, EC_EPI_BF16_QGELU, EC_EPI_F32_RESADD, EC_EPI_F32, EC_EPI_PATCH, EC_EPI_F16_RESADD = 0, 1, 2, 3, 4, 5
 EC_AGG = {"sum": 0, "mean": 1, "max": 2}
 
 
@@ -43,6 +43,7 @@ SIGNATURES = {
     "ec_flip_events": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp], _i),
     "ec_gemm_bf16": ([_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp], _i),
     "ec_layernorm": ([_vp, _i64, _vp, _vp, _i, _i, _vp, _vp, _vp], _i),
+    "ec_layernorm_ex": ([_vp, _i, _i64, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp], _i),
     "ec_attention": ([_vp, _vp, _i, _i, _i, _vp], _i),
     "ec_attention_ex": ([_vp, _vp, _i, _i, _i, _i, _vp], _i),
     "ec_embed_tokens": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp], _i),

@@ -8,6 +8,7 @@ PyTorch op on the data path: it packs weights to bf16 once and enqueues the libr
 (tcgen05 GEMMs with fused epilogues, LayerNorm, attention) through the C ABI.
 """
 import math
+import os
 from collections import OrderedDict
 
 import torch
@@ -117,8 +118,9 @@ def pack_blocks(resblocks, d, dev):
 
 
 def run_blocks(x, blocks, n_seq, Ltok, d, heads, causal=False):
-    """x: fp32 residual stream [n_seq*Ltok, d], updated in place by the GEMM epilogues."""
+    """x: residual stream [n_seq*Ltok, d], fp32 or fp16, updated in place by the GEMM epilogues."""
     M, dev = n_seq * Ltok, x.device
+    resadd = "f16_resadd" if x.dtype == torch.float16 else "f32_resadd"
     xn = torch.empty((M, d), dtype=torch.bfloat16, device=dev)
     qkv = torch.empty((M, 3 * d), dtype=torch.bfloat16, device=dev)
     att = torch.empty((M, d), dtype=torch.bfloat16, device=dev)
@@ -127,10 +129,10 @@ def run_blocks(x, blocks, n_seq, Ltok, d, heads, causal=False):
         ops.layernorm(x, *b["ln1"], M, d, out_bf16=xn)
         ops.gemm_bf16(xn, b["w_in"], b["b_in"], "bf16", out=qkv)
         ops.attention(qkv, att, n_seq, Ltok, heads, causal=causal)
-        ops.gemm_bf16(att, b["w_out"], b["b_out"], "f32_resadd", out=x, res=x)
+        ops.gemm_bf16(att, b["w_out"], b["b_out"], resadd, out=x, res=x)
         ops.layernorm(x, *b["ln2"], M, d, out_bf16=xn)
         ops.gemm_bf16(xn, b["w_fc"], b["b_fc"], "bf16_qgelu", out=hid)
-        ops.gemm_bf16(hid, b["w_proj"], b["b_proj"], "f32_resadd", out=x, res=x)
+        ops.gemm_bf16(hid, b["w_proj"], b["b_proj"], resadd, out=x, res=x)
     return x
 
 
@@ -152,6 +154,10 @@ class VisionTransformer(nn.Module):
         self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
         self._packed = None
         self._packed_key = None
+        # dtype of the residual stream of the inference forward.  fp16 = the reference's own precision on CUDA (clip.load
+        # keeps the model in fp16, test.py:26-29) at half the residual traffic; EC_RESIDUAL=fp32 keeps it in float32.
+        # The fine-tune forward (train.py) always uses fp32, as the reference's train.py:27-29 does.
+        self.residual_dtype = torch.float32 if os.environ.get("EC_RESIDUAL", "fp16") == "fp32" else torch.float16
 
     # -- weight packing -------------------------------------------------------------------------------------------
     @property
@@ -254,8 +260,13 @@ class VisionTransformer(nn.Module):
         x0 = torch.empty((M, d), dtype=torch.float32, device=dev)       # tokens before ln_pre
         ops.gemm_bf16(patches, pk["conv1"], None, "patch", out=x0, res=pk["pos"], row_map=G2, M=n_img * G2)
         ops.cls_rows(x0, pk["cls"], pk["pos"], n_img, Ltok, d)
-        x = torch.empty((M, d), dtype=torch.float32, device=dev)        # fp32 residual stream
-        ops.layernorm(x0, *pk["ln_pre"], M, d, out_f32=x)
+        # residual stream: fp16 like the reference's CUDA inference (test.py:26-29 keeps CLIP in fp16) or fp32
+        if self.residual_dtype == torch.float16:
+            x = torch.empty((M, d), dtype=torch.float16, device=dev)
+            ops.layernorm(x0, *pk["ln_pre"], M, d, out_f16=x)
+        else:
+            x = torch.empty((M, d), dtype=torch.float32, device=dev)
+            ops.layernorm(x0, *pk["ln_pre"], M, d, out_f32=x)
         del x0
         run_blocks(x, pk["blocks"], n_img, Ltok, d, heads)
         cls = torch.empty((n_img, d), dtype=torch.bfloat16, device=dev)

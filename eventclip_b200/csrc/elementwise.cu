@@ -6,21 +6,32 @@
 //   class token       x = cat([class_embedding, patches]) + positional_embedding
 //   LoRA merge        models/lora.py:138-149 (q/k/v) and 49-52 (out_proj): W + up @ down, no alpha/r scaling
 //   residual blend    models/adapter.py:22-25: in*r + new*(1-r)
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace {
 
-// One warp per row; two-pass (mean, then centred variance) on register-cached values.
-template <bool CACHE>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict__ x, int64_t row_stride,
+// One warp per row; two-pass (mean, then centred variance) on register-cached values.  TIn = float or __half (the fp16
+// residual stream); outputs: bf16 (GEMM operand), fp32, and / or fp16 (ln_pre starting an fp16 residual stream).
+__device__ __forceinline__ float4 ld4(const float *p, int j) { return reinterpret_cast<const float4 *>(p)[j]; }
+__device__ __forceinline__ float4 ld4(const __half *p, int j)
+{
+    const uint2 u = reinterpret_cast<const uint2 *>(p)[j];
+    const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2 *>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+template <bool CACHE, typename TIn>
+__global__ void __launch_bounds__(256) layernorm_kernel(const TIn *__restrict__ x, int64_t row_stride,
                                                         const float *__restrict__ gamma, const float *__restrict__ beta,
                                                         int M, int d, __nv_bfloat16 *__restrict__ out_bf16,
-                                                        float *__restrict__ out_f32)
+                                                        float *__restrict__ out_f32, __half *__restrict__ out_f16)
 {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
-    const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)row * row_stride);
+    const TIn *xr = x + (size_t)row * row_stride;
     const int n4 = d >> 2;
     constexpr int MAXV = 8;   // d <= 1024 when CACHE
     float4 v[MAXV];
@@ -29,10 +40,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict_
 #pragma unroll
         for (int i = 0; i < MAXV; ++i) {
             const int j = lane + i * 32;
-            if (j < n4) { v[i] = xr[j]; s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+            if (j < n4) { v[i] = ld4(xr, j); s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
         }
     } else {
-        for (int j = lane; j < n4; j += 32) { const float4 t = xr[j]; s += (t.x + t.y) + (t.z + t.w); }
+        for (int j = lane; j < n4; j += 32) { const float4 t = ld4(xr, j); s += (t.x + t.y) + (t.z + t.w); }
     }
     const float mean = ec::warp_sum(s) / (float)d;
     float q = 0.f;
@@ -47,7 +58,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict_
         }
     } else {
         for (int j = lane; j < n4; j += 32) {
-            const float4 t = xr[j];
+            const float4 t = ld4(xr, j);
             const float a = t.x - mean, b = t.y - mean, c = t.z - mean, e = t.w - mean;
             q += (a * a + b * b) + (c * c + e * e);
         }
@@ -70,6 +81,13 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict_
             u.y = *reinterpret_cast<uint32_t *>(&h1);
             reinterpret_cast<uint2 *>(out_bf16 + (size_t)row * d)[j] = u;
         }
+        if (out_f16) {
+            __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
+            uint2 u;
+            u.x = *reinterpret_cast<uint32_t *>(&h0);
+            u.y = *reinterpret_cast<uint32_t *>(&h1);
+            reinterpret_cast<uint2 *>(out_f16 + (size_t)row * d)[j] = u;
+        }
     };
     if (CACHE) {
 #pragma unroll
@@ -78,23 +96,32 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict_
             if (j < n4) emit(j, v[i]);
         }
     } else {
-        for (int j = lane; j < n4; j += 32) emit(j, xr[j]);
+        for (int j = lane; j < n4; j += 32) emit(j, ld4(xr, j));
     }
+}
+
+template <typename TIn>
+int launch_ln_t(const TIn *x, int64_t row_stride, const float *gamma, const float *beta, int M, int d, void *out_bf16,
+                float *out_f32, void *out_f16, cudaStream_t stream)
+{
+    EC_REQUIRE(x && gamma && beta && (out_bf16 || out_f32 || out_f16), "layernorm: null pointer");
+    EC_REQUIRE(M > 0 && d > 0 && d % 4 == 0 && row_stride % 4 == 0, "layernorm: d and row stride must be multiples of 4");
+    const int rows_per_block = 8;
+    const unsigned grid = (unsigned)((M + rows_per_block - 1) / rows_per_block);
+    if (d <= 1024)
+        layernorm_kernel<true, TIn><<<grid, 256, 0, stream>>>(x, row_stride, gamma, beta, M, d, (__nv_bfloat16 *)out_bf16, out_f32,
+                                                              (__half *)out_f16);
+    else
+        layernorm_kernel<false, TIn><<<grid, 256, 0, stream>>>(x, row_stride, gamma, beta, M, d, (__nv_bfloat16 *)out_bf16, out_f32,
+                                                               (__half *)out_f16);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
 }
 
 int launch_ln(const float *x, int64_t row_stride, const float *gamma, const float *beta, int M, int d, void *out_bf16,
               float *out_f32, cudaStream_t stream)
 {
-    EC_REQUIRE(x && gamma && beta && (out_bf16 || out_f32), "layernorm: null pointer");
-    EC_REQUIRE(M > 0 && d > 0 && d % 4 == 0 && row_stride % 4 == 0, "layernorm: d and row stride must be multiples of 4");
-    const int rows_per_block = 8;
-    const int grid = (M + rows_per_block - 1) / rows_per_block;
-    if (d <= 1024)
-        layernorm_kernel<true><<<grid, 256, 0, stream>>>(x, row_stride, gamma, beta, M, d, (__nv_bfloat16 *)out_bf16, out_f32);
-    else
-        layernorm_kernel<false><<<grid, 256, 0, stream>>>(x, row_stride, gamma, beta, M, d, (__nv_bfloat16 *)out_bf16, out_f32);
-    EC_CUDA_CHECK(cudaGetLastError());
-    return EC_OK;
+    return launch_ln_t<float>(x, row_stride, gamma, beta, M, d, out_bf16, out_f32, nullptr, stream);
 }
 
 __global__ void cls_rows_kernel(float *x, const float *cls, const float *pos, int n_img, int L, int d)
@@ -301,6 +328,14 @@ extern "C" int ec_layernorm(const float *x, int64_t row_stride_in, const float *
                             void *out_bf16, float *out_f32, void *stream)
 {
     return launch_ln(x, row_stride_in, gamma, beta, M, d, out_bf16, out_f32, (cudaStream_t)stream);
+}
+
+extern "C" int ec_layernorm_ex(const void *x, int x_is_f16, int64_t row_stride_in, const float *gamma, const float *beta, int M,
+                               int d, void *out_bf16, float *out_f32, void *out_f16, void *stream)
+{
+    if (x_is_f16)
+        return launch_ln_t<__half>((const __half *)x, row_stride_in, gamma, beta, M, d, out_bf16, out_f32, out_f16, (cudaStream_t)stream);
+    return launch_ln_t<float>((const float *)x, row_stride_in, gamma, beta, M, d, out_bf16, out_f32, out_f16, (cudaStream_t)stream);
 }
 
 extern "C" int ec_layernorm_f32(const float *x, const float *gamma, const float *beta, int M, int d, float *out,

@@ -23,6 +23,8 @@
 #include <mutex>
 #include <cstdlib>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -573,6 +575,76 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
             if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        } else if (p.epi == EC_EPI_F16_RESADD) {
+            // ---- fp16 residual stream (the reference's CUDA precision): same in-place box scheme as above with
+            //      [32 rows x 32 halves] boxes (64-byte rows, SWIZZLE_64B): half the residual bytes in and out. ----
+            uint32_t as = 0, aphase = 0, nbox = 0;
+            uint64_t *rb = res_bar[ew];
+            auto load_res = [&](int tile_, int c_, uint32_t n_) {     // lane 0 only
+                const int tm_ = tile_ / p.tiles_n, tn_ = tile_ % p.tiles_n;
+                const int r_ = (tm_ * CG + (int)cta_rank) * BM + quarter * 32;
+                const int c0_ = tn_ * BN + half * COLS_PER_WARP + c_ * 32;
+                mbar_expect_tx(&rb[n_ & 1], 2048);
+                tma_load_2d(smem + STAGES * STAGE_BYTES + ew * STG_WARP_BYTES + (n_ & 1) * 2048, &map_r, &rb[n_ & 1], c0_, r_);
+            };
+            if (lane == 0 && group_id < num_tiles) load_res(group_id, 0, 0);
+            for (int tile = group_id; tile < num_tiles; tile += num_groups) {
+                const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+                const int row0 = (tm * CG + (int)cta_rank) * BM + quarter * 32;
+                const int colw = tn * BN + half * COLS_PER_WARP;
+                mbar_wait(&tfull_bar[as], aphase);
+                tc_fence_after();
+                const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * COLS_PER_WARP);
+                uint32_t v[32];
+                tmem_ld32_issue(tbase, v);
+#pragma unroll 1
+                for (int c = 0; c < NCHUNK; ++c) {
+                    const int col0 = colw + c * 32;
+                    float4 bq[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) bq[q] = bias4(p.bias, col0 + 4 * q, p.N);
+                    if (lane == 0) {
+                        bulk_wait_read<0>();     // the store that last used the other buffer has finished reading it
+                        if (c + 1 < NCHUNK) load_res(tile, c + 1, nbox + 1);
+                        else if (tile + num_groups < num_tiles) load_res(tile + num_groups, 0, nbox + 1);
+                    }
+                    const uint32_t box = stg + (nbox & 1) * 2048;
+                    mbar_wait(&rb[nbox & 1], (nbox >> 1) & 1);
+                    tmem_ld_wait();
+                    const uint32_t rowaddr = box + (uint32_t)lane * 64;
+                    const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {          // 8 columns per 16-byte chunk
+                        const uint32_t a = rowaddr + ((q ^ sw) << 4);
+                        const float4 raw = lds128(a);
+                        const uint32_t hw[4] = {__float_as_uint(raw.x), __float_as_uint(raw.y), __float_as_uint(raw.z), __float_as_uint(raw.w)};
+                        uint32_t ow[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 r = __half22float2(*reinterpret_cast<const __half2 *>(&hw[e]));
+                            const float4 b = bq[2 * q + (e >> 1)];
+                            const float b0 = (e & 1) ? b.z : b.x, b1 = (e & 1) ? b.w : b.y;
+                            const __half2 o = __floats2half2_rn(r.x + __uint_as_float(v[8 * q + 2 * e]) + b0,
+                                                                r.y + __uint_as_float(v[8 * q + 2 * e + 1]) + b1);
+                            ow[e] = *reinterpret_cast<const uint32_t *>(&o);
+                        }
+                        sts128u(a, ow[0], ow[1], ow[2], ow[3]);
+                    }
+                    if (c + 1 < NCHUNK) tmem_ld32_issue(tbase + (uint32_t)((c + 1) * 32), v);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0 && row0 < p.M && col0 < p.N) tma_store_2d(&map_o, box, col0, row0);
+                    ++nbox;
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 2) mbar_arrive_leader(&tempty_bar[as]);
+                    else mbar_arrive(&tempty_bar[as]);
+                }
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         } else {
         const bool has_res = p.epi == EC_EPI_F32_RESADD || p.epi == EC_EPI_PATCH;
         // transposed lane mapping inside a 16-column pass
@@ -764,6 +836,22 @@ int make_out_map(CUtensorMap *m, void *base, int M, int N, int ldo)
     return EC_OK;
 }
 
+// fp16 [M, ld]: box = 32 rows x 32 columns (64 bytes), SWIZZLE_64B -- fp16 residual loads and residual-stream stores
+int make_f16_map(CUtensorMap *m, const void *base, int M, int N, int ld)
+{
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { ec::set_error("cuTensorMapEncodeTiled entry point not available"); return EC_ERR_CUDA; }
+    cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { ec::set_error("cuTensorMapEncodeTiled (fp16) failed with CUresult %d", (int)r); return EC_ERR_CUDA; }
+    return EC_OK;
+}
+
 // fp32 [M, ld]: box = 32 rows x 32 columns (128 bytes), SWIZZLE_128B -- residual loads and residual-stream stores
 int make_f32_map(CUtensorMap *m, const void *base, int M, int N, int ld)
 {
@@ -924,9 +1012,10 @@ int gemm_impl(const void *A, int lda, const void *W, int ldw, const float *bias,
                    "ec_gemm_bf16: N, K, lda, ldw must be multiples of 8 (N=%d K=%d lda=%d ldw=%d)", N, K, lda, ldw);
     EC_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)out & 15) == 0,
                "ec_gemm_bf16: pointers must be 16-byte aligned");
-    EC_REQUIRE(epi >= EC_EPI_BF16 && epi <= EC_EPI_PATCH, "ec_gemm_bf16: bad epilogue %d", epi);
+    EC_REQUIRE(epi >= EC_EPI_BF16 && epi <= EC_EPI_F16_RESADD, "ec_gemm_bf16: bad epilogue %d", epi);
     EC_REQUIRE(ldo >= N && ldo % 8 == 0, "ec_gemm_bf16: bad ldo %d", ldo);
-    if (epi == EC_EPI_F32_RESADD || epi == EC_EPI_PATCH) EC_REQUIRE(res != nullptr, "ec_gemm_bf16: epilogue needs res");
+    if (epi == EC_EPI_F32_RESADD || epi == EC_EPI_PATCH || epi == EC_EPI_F16_RESADD)
+        EC_REQUIRE(res != nullptr, "ec_gemm_bf16: epilogue needs res");
     if (epi == EC_EPI_PATCH) EC_REQUIRE(row_map > 0 && M % row_map == 0, "ec_gemm_bf16: bad row_map %d", row_map);
 
     const int BN = (N % 256 == 0) ? 256 : 128;
@@ -976,6 +1065,13 @@ int gemm_impl(const void *A, int lda, const void *W, int ldw, const float *bias,
         rc = make_f32_map(&mo, out, M, N, ldo);
         if (rc != EC_OK) return rc;
         rc = make_f32_map(&mr, res, M, N, ldo);
+        if (rc != EC_OK) return rc;
+    }
+    if (epi == EC_EPI_F16_RESADD) {      // out / res are fp16 [M, ldo]
+        EC_REQUIRE(((uintptr_t)res & 15) == 0 && ldo % 8 == 0, "ec_gemm_bf16: fp16 residual must be 16-byte aligned");
+        rc = make_f16_map(&mo, out, M, N, ldo);
+        if (rc != EC_OK) return rc;
+        rc = make_f16_map(&mr, res, M, N, ldo);
         if (rc != EC_OK) return rc;
     }
     if (CG == 2) return launch<256, 2>(ma, mw, mo, mr, p, stream);

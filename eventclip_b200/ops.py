@@ -157,7 +157,10 @@ def gemm_bf16(A, W, bias=None, epi="bf16", out=None, res=None, row_map=0, M=None
     M = A.shape[0] if M is None else M
     N, K = W.shape
     epi_id = {"bf16": L.EC_EPI_BF16, "bf16_qgelu": L.EC_EPI_BF16_QGELU, "f32_resadd": L.EC_EPI_F32_RESADD,
-              "f32": L.EC_EPI_F32, "patch": L.EC_EPI_PATCH}[epi]
+              "f32": L.EC_EPI_F32, "patch": L.EC_EPI_PATCH, "f16_resadd": L.EC_EPI_F16_RESADD}[epi]
+    if epi == "f16_resadd":
+        if out is None or res is None or out.dtype != torch.float16 or res.dtype != torch.float16:
+            raise L.ECError("f16_resadd epilogue needs fp16 `out` and `res` (the fp16 residual stream)")
     if out is None:
         if epi == "patch":
             raise L.ECError("patch epilogue needs a preallocated token matrix")
@@ -169,7 +172,15 @@ def gemm_bf16(A, W, bias=None, epi="bf16", out=None, res=None, row_map=0, M=None
     return out
 
 
-def layernorm(x, gamma, beta, M, d, row_stride=None, out_bf16=None, out_f32=None):
+def layernorm(x, gamma, beta, M, d, row_stride=None, out_bf16=None, out_f32=None, out_f16=None):
+    """x: fp32, or fp16 (the fp16 residual stream); out_f16 is what ln_pre writes to start that stream."""
+    if x.dtype == torch.float16 or out_f16 is not None:
+        _dev(x, x.dtype if x.dtype in (torch.float16, torch.float32) else torch.float32, "x")
+        with torch.cuda.device(x.device):
+            rc = L.load().ec_layernorm_ex(_ptr(x), int(x.dtype == torch.float16), int(row_stride or d), _ptr(gamma), _ptr(beta),
+                                          M, d, _ptr(out_bf16), _ptr(out_f32), _ptr(out_f16), _stream())
+        L.check(rc, "ec_layernorm_ex")
+        return
     _dev(x, torch.float32, "x")
     with torch.cuda.device(x.device):
         rc = L.load().ec_layernorm(_ptr(x), int(row_stride or d), _ptr(gamma), _ptr(beta), M, d, _ptr(out_bf16),

@@ -132,6 +132,8 @@ EC_API int ec_event2img_geometry(int H, int W, int *cluster_size, int *threads, 
 #define EC_EPI_F32_RESADD 2  /* out fp32 = res + acc + bias       (residual stream update)   */
 #define EC_EPI_F32 3         /* out fp32 = acc + bias                                        */
 #define EC_EPI_PATCH 4       /* out fp32 token rows = acc + pos[1 + m%G2]  (patch embedding) */
+#define EC_EPI_F16_RESADD 5  /* out fp16 = res(fp16) + acc + bias: residual stream in the reference's CUDA precision;
+                                `out` and `res` point to fp16 [M,ldo] (res is passed through the float* parameter) */
 EC_API int ec_gemm_bf16(const void *A, int lda, const void *W, int ldw, const float *bias, int M, int N, int K,
                  int epi, void *out, int ldo, const float *res, int row_map, void *stream);
 
@@ -160,6 +162,11 @@ EC_API int ec_gemm_bf16_tn_splitk(const void *A, int lda, const void *B, int ldb
  * class-token rows (stride L*d). */
 EC_API int ec_layernorm(const float *x, int64_t row_stride_in, const float *gamma, const float *beta, int M, int d,
                  void *out_bf16, float *out_f32, void *stream);
+/* Same LayerNorm for the fp16 residual stream of the inference forward (the reference's CUDA precision, test.py:26-29 loads
+ * CLIP in fp16): x is fp16 when x_is_f16 != 0; any of the three outputs may be NULL.  out_f16 is what ln_pre writes to
+ * start the fp16 stream. */
+EC_API int ec_layernorm_ex(const void *x, int x_is_f16, int64_t row_stride_in, const float *gamma, const float *beta, int M,
+                           int d, void *out_bf16, float *out_f32, void *out_f16, void *stream);
 
 /* Multi-head self-attention core on the packed QKV activations of nn.MultiheadAttention:
  * qkv bf16 [n_img*L, 3*d] (q | k | v, head h at columns h*64), out bf16 [n_img*L, d].
