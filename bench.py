@@ -460,7 +460,9 @@ def b200_arm(args):
             "data": "synthetic",
             "config": {"workload": f"zero-shot {ARCH} on synthetic N-Cars-shaped streams (120x100, 4000 events/sample, "
                                    f"2 classes), batch {B} per GPU, random-init CLIP (BASELINE.json configs[1])",
-                       "per_gpu_batch": B, "views_per_sample": T, "l2": "256 MiB buffer rewritten before every step (inside the timed region)",
+                       "per_gpu_batch": B, "views_per_sample": T,
+                       "numerics": "bf16 tensor-core operands, fp32 accumulation, residual stream in "
+                                   + ("fp16 (the reference's CUDA precision)" if model.visual.residual_dtype == torch.float16 else "fp32"), "l2": "256 MiB buffer rewritten before every step (inside the timed region)",
                        "sharding": "samples by rank; one all-reduce of 2 int64 counters at the end",
                        "launch": "eager" if args.no_graph else "CUDA graph replay of the device part (event2img..head)"},
             "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -52,6 +52,18 @@ def test_gemm_epilogues(cuda_dev):
     assert rel(x, acc + res) < 2e-3
     nobias = ops.gemm_bf16(Ad, Wd, None, "f32")
     assert rel(nobias, acc - bias) < 2e-3
+    # fp16 residual stream: in place on halves (TMA boxes of 32 x 32 halves), fp32 math, one rounding to fp16;
+    # shapes that exercise the single-CTA (M < 256) and the CTA-pair kernels and a ragged last row tile
+    for Mh in (394, 100, 1000):
+        Ah = bf(torch.randn(Mh, K, generator=g))
+        resh = torch.randn(Mh, N, generator=g).half()
+        xh = resh.to(cuda_dev).clone()
+        ops.gemm_bf16(Ah.to(cuda_dev), Wd, bd, "f16_resadd", out=xh, res=xh)
+        wanth = Ah.float() @ W.float().t() + bias + resh.float()
+        assert xh.dtype == torch.float16 and rel(xh.float(), wanth) < 2e-3
+        assert (xh.float().cpu() - wanth).abs().max() < 2.0 ** -9 * wanth.abs().max() + 0.03      # within fp16 rounding + bf16 product noise
+    with pytest.raises(Exception):
+        ops.gemm_bf16(Ad, Wd, bd, "f16_resadd", out=x, res=x)           # fp32 tensors are rejected
     # patch epilogue: rows land at token 1 + m % G2 of image m // G2 and get the positional embedding
     G2, n_img, d = 49, 6, 256
     P = bf(torch.randn(n_img * G2, 128, generator=g))
@@ -76,6 +88,20 @@ def test_layernorm_and_helpers(cuda_dev):
         assert (o32.cpu() - ref).abs().max() < 2e-5 * ref.abs().max().clamp_min(1)
         assert torch.equal(o16, o32.to(torch.bfloat16))
         assert (ops.layernorm_f32(x.to(cuda_dev), w.to(cuda_dev), b.to(cuda_dev)).cpu() - ref).abs().max() < 1e-4
+    # fp16 residual stream: fp16 input (statistics in fp32), fp16 output (what ln_pre writes)
+    for M, d in ((37, 768), (5, 1024), (3, 2048)):
+        x = (torch.randn(M, d, generator=g) * 3 + 1).half()
+        w, b = torch.randn(d, generator=g), torch.randn(d, generator=g)
+        ref = torch.nn.functional.layer_norm(x.float(), (d,), w, b, 1e-5)
+        o32 = torch.empty(M, d, device=cuda_dev)
+        ob = torch.empty(M, d, dtype=torch.bfloat16, device=cuda_dev)
+        oh = torch.empty(M, d, dtype=torch.float16, device=cuda_dev)
+        ops.layernorm(x.to(cuda_dev), w.to(cuda_dev), b.to(cuda_dev), M, d, out_bf16=ob, out_f32=o32, out_f16=oh)
+        assert (o32.cpu() - ref).abs().max() < 2e-5 * ref.abs().max().clamp_min(1)
+        assert torch.equal(ob, o32.to(torch.bfloat16)) and torch.equal(oh, o32.half())
+        oh2 = torch.empty(M, d, dtype=torch.float16, device=cuda_dev)
+        ops.layernorm(x.float().to(cuda_dev), w.to(cuda_dev), b.to(cuda_dev), M, d, out_f16=oh2)       # fp32 in, fp16 out
+        assert torch.equal(oh2, oh)
     # strided rows (ln_post reads the class token of every image)
     x = torch.randn(4, 5, 128, generator=g)
     w, b = torch.ones(128), torch.zeros(128)
@@ -136,6 +162,25 @@ def test_encoder_large_archs_vs_oracle(cuda_dev, arch):
         ref = oracle.encode_image(imgs)
         got = model.encode_image(imgs.to(cuda_dev))
     assert rel(got, ref) < 2e-2, rel(got, ref)
+
+
+def test_residual_stream_fp16_and_fp32_vs_oracle(cuda_dev):
+    """The inference forward keeps the residual stream in fp16 (the reference's CUDA precision) by default and in fp32 on
+    request; both stay within the encoder tolerance of the fp32 oracle and close to each other."""
+    arch = "ViT-B/16"
+    oracle = clip_oracle.build_clip(arch, seed=23)
+    model = clip.CLIP(arch)
+    model.load_state_dict(oracle.state_dict())
+    model = model.to(cuda_dev).eval()
+    imgs = torch.randn(3, 3, 224, 224, generator=torch.Generator().manual_seed(10))
+    with torch.no_grad():
+        ref = oracle.encode_image(imgs)
+        assert model.visual.residual_dtype == torch.float16
+        got16 = model.encode_image(imgs.to(cuda_dev)).cpu()
+        model.visual.residual_dtype = torch.float32
+        got32 = model.encode_image(imgs.to(cuda_dev)).cpu()
+    assert rel(got16, ref) < 2e-2 and rel(got32, ref) < 2e-2, (rel(got16, ref), rel(got32, ref))
+    assert rel(got16, got32) < 1e-2 and not torch.equal(got16, got32)
 
 
 @pytest.mark.parametrize("L,heads,n_seq", [(77, 8, 5), (16, 1, 3), (197, 12, 2), (257, 16, 1)])
