@@ -100,6 +100,110 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const TIn *__restrict__ 
     }
 }
 
+// fp16 rows with 16-byte accesses: a lane owns 8 consecutive elements per step (d % 8 == 0, d <= 1024, 16-byte aligned rows).
+// A warp normalises TWO rows at a time and keeps them packed in registers: all loads of both rows are issued before the
+// first reduction, which doubles the bytes in flight per SM (the kernel is latency-, not bandwidth-limited otherwise).
+__global__ void __launch_bounds__(256) layernorm_h8_kernel(const __half *__restrict__ x, int64_t row_stride,
+                                                           const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                           int M, int d, __nv_bfloat16 *__restrict__ out_bf16,
+                                                           float *__restrict__ out_f32, __half *__restrict__ out_f16)
+{
+    constexpr int R = 2, MAXV = 4;
+    const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
+    const int lane = threadIdx.x & 31;
+    if (row0 >= M) return;
+    const int n8 = d >> 3;
+    uint4 raw[R][MAXV];
+    auto unpack = [](const uint4 &u, float (&f)[8]) {
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 t = __half22float2(*reinterpret_cast<const __half2 *>(&w[e]));
+            f[2 * e] = t.x; f[2 * e + 1] = t.y;
+        }
+    };
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint4 *xr = reinterpret_cast<const uint4 *>(x + (size_t)min(row0 + r, M - 1) * row_stride);
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i)
+            if (lane + i * 32 < n8) raw[r][i] = xr[lane + i * 32];
+    }
+    float mean[R], rstd[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            if (lane + i * 32 < n8) {
+                float f[8];
+                unpack(raw[r][i], f);
+                s += ((f[0] + f[1]) + (f[2] + f[3])) + ((f[4] + f[5]) + (f[6] + f[7]));
+            }
+        }
+        mean[r] = s;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) mean[r] = ec::warp_sum(mean[r]) / (float)d;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            if (lane + i * 32 < n8) {
+                float f[8];
+                unpack(raw[r][i], f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { const float a = f[e] - mean[r]; q += a * a; }
+            }
+        }
+        rstd[r] = q;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) rstd[r] = rsqrtf(ec::warp_sum(rstd[r]) / (float)d + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int j = lane + i * 32;
+        if (j >= n8) continue;
+        const float4 g0 = reinterpret_cast<const float4 *>(gamma)[2 * j], g1 = reinterpret_cast<const float4 *>(gamma)[2 * j + 1];
+        const float4 b0 = reinterpret_cast<const float4 *>(beta)[2 * j], b1 = reinterpret_cast<const float4 *>(beta)[2 * j + 1];
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int row = row0 + r;
+            if (row >= M) continue;
+            float f[8], o[8];
+            unpack(raw[r][i], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = (f[e] - mean[r]) * rstd[r] * g[e] + b[e];
+            if (out_f32) {
+                float4 *of = reinterpret_cast<float4 *>(out_f32 + (size_t)row * d) + 2 * j;
+                of[0] = make_float4(o[0], o[1], o[2], o[3]);
+                of[1] = make_float4(o[4], o[5], o[6], o[7]);
+            }
+            if (out_bf16) {
+                uint4 u;
+                __nv_bfloat162 h;
+                h = __floats2bfloat162_rn(o[0], o[1]); u.x = *reinterpret_cast<uint32_t *>(&h);
+                h = __floats2bfloat162_rn(o[2], o[3]); u.y = *reinterpret_cast<uint32_t *>(&h);
+                h = __floats2bfloat162_rn(o[4], o[5]); u.z = *reinterpret_cast<uint32_t *>(&h);
+                h = __floats2bfloat162_rn(o[6], o[7]); u.w = *reinterpret_cast<uint32_t *>(&h);
+                reinterpret_cast<uint4 *>(out_bf16 + (size_t)row * d)[j] = u;
+            }
+            if (out_f16) {
+                uint4 u;
+                __half2 h;
+                h = __floats2half2_rn(o[0], o[1]); u.x = *reinterpret_cast<uint32_t *>(&h);
+                h = __floats2half2_rn(o[2], o[3]); u.y = *reinterpret_cast<uint32_t *>(&h);
+                h = __floats2half2_rn(o[4], o[5]); u.z = *reinterpret_cast<uint32_t *>(&h);
+                h = __floats2half2_rn(o[6], o[7]); u.w = *reinterpret_cast<uint32_t *>(&h);
+                reinterpret_cast<uint4 *>(out_f16 + (size_t)row * d)[j] = u;
+            }
+        }
+    }
+}
+
 template <typename TIn>
 int launch_ln_t(const TIn *x, int64_t row_stride, const float *gamma, const float *beta, int M, int d, void *out_bf16,
                 float *out_f32, void *out_f16, cudaStream_t stream)
@@ -108,6 +212,13 @@ int launch_ln_t(const TIn *x, int64_t row_stride, const float *gamma, const floa
     EC_REQUIRE(M > 0 && d > 0 && d % 4 == 0 && row_stride % 4 == 0, "layernorm: d and row stride must be multiples of 4");
     const int rows_per_block = 8;
     const unsigned grid = (unsigned)((M + rows_per_block - 1) / rows_per_block);
+    if (sizeof(TIn) == 2 && d <= 1024 && d % 8 == 0 && row_stride % 8 == 0 && ((uintptr_t)x & 15) == 0 &&
+        (((uintptr_t)out_bf16 | (uintptr_t)out_f32 | (uintptr_t)out_f16) & 15) == 0) {
+        layernorm_h8_kernel<<<(grid + 1) / 2, 256, 0, stream>>>((const __half *)x, row_stride, gamma, beta, M, d, (__nv_bfloat16 *)out_bf16,
+                                                      out_f32, (__half *)out_f16);
+        EC_CUDA_CHECK(cudaGetLastError());
+        return EC_OK;
+    }
     if (d <= 1024)
         layernorm_kernel<true, TIn><<<grid, 256, 0, stream>>>(x, row_stride, gamma, beta, M, d, (__nv_bfloat16 *)out_bf16, out_f32,
                                                               (__half *)out_f16);

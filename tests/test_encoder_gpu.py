@@ -101,7 +101,7 @@ def test_layernorm_and_helpers(cuda_dev):
         assert torch.equal(ob, o32.to(torch.bfloat16)) and torch.equal(oh, o32.half())
         oh2 = torch.empty(M, d, dtype=torch.float16, device=cuda_dev)
         ops.layernorm(x.float().to(cuda_dev), w.to(cuda_dev), b.to(cuda_dev), M, d, out_f16=oh2)       # fp32 in, fp16 out
-        assert torch.equal(oh2, oh)
+        assert (oh2.float() - oh.float()).abs().max() <= 2.0 ** -9 * oh.float().abs().max()      # other summation order, fp32 input
     # strided rows (ln_post reads the class token of every image)
     x = torch.randn(4, 5, 128, generator=g)
     w, b = torch.ones(128), torch.zeros(128)
