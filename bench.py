@@ -300,9 +300,19 @@ def b200_arm(args):
         gemm_log.append((m, Wt.shape[0], Wt.shape[1], epi))
         return _orig_gemm(A, Wt, bias, epi, out, res, row_map, M)
 
+    _orig_ln, _orig_stats = ops.gemm_ln, ops.gemm_bf16_stats
+
+    def logged_gemm_ln(x, Wg, colsum, cbias, st, n_parts, epi="bf16", out=None):
+        gemm_log.append((x.shape[0], Wg.shape[0], Wg.shape[1], "ln_" + epi))
+        return _orig_ln(x, Wg, colsum, cbias, st, n_parts, epi, out)
+
+    def logged_gemm_stats(A, W, bias, x, st):
+        gemm_log.append((A.shape[0], W.shape[0], W.shape[1], "f16_resadd_stats"))
+        return _orig_stats(A, W, bias, x, st)
+
     if not args.no_graph:
         _lib.load().ec_gemm_timing(ctypes.c_void_p(stamps.data_ptr()), STAMP_CAP)
-        clipmod.ops.gemm_bf16 = logged_gemm
+        clipmod.ops.gemm_bf16, clipmod.ops.gemm_ln, clipmod.ops.gemm_bf16_stats = logged_gemm, logged_gemm_ln, logged_gemm_stats
 
     def step(i, resident=True):
         ev, off = (devb if resident else host)[i % NB]
@@ -322,7 +332,7 @@ def b200_arm(args):
     for i in range(Wm):
         step(i)
         if i == 0 and not args.no_graph:     # the graph exists now (2 eager warm-up passes + 1 capture went through Python)
-            clipmod.ops.gemm_bf16 = _orig_gemm
+            clipmod.ops.gemm_bf16, clipmod.ops.gemm_ln, clipmod.ops.gemm_bf16_stats = _orig_gemm, _orig_ln, _orig_stats
             _lib.load().ec_gemm_timing(None, 0)          # later launches are not stamped; the graph keeps its slots
     # ---- device-timed region: K steps, inputs resident ----
     barrier()
@@ -400,15 +410,31 @@ def b200_arm(args):
             rec.append((a, b, 2.0 * m * Wt.shape[0] * Wt.shape[1], (m, Wt.shape[0], Wt.shape[1], epi)))
             return r
 
+        def timed_ln(x, Wg, colsum, cbias, st, n_parts, epi="bf16", out=None):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = _orig_ln(x, Wg, colsum, cbias, st, n_parts, epi, out)
+            b.record()
+            rec.append((a, b, 2.0 * x.shape[0] * Wg.shape[0] * Wg.shape[1], (x.shape[0], Wg.shape[0], Wg.shape[1], "ln_" + epi)))
+            return r
+
+        def timed_stats(A, W, bias, x, st):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = _orig_stats(A, W, bias, x, st)
+            b.record()
+            rec.append((a, b, 2.0 * A.shape[0] * W.shape[0] * W.shape[1], (A.shape[0], W.shape[0], W.shape[1], "f16_resadd_stats")))
+            return r
+
         import eventclip_b200.clip as clipmod
-        clipmod.ops.gemm_bf16 = timed_gemm
+        clipmod.ops.gemm_bf16, clipmod.ops.gemm_ln, clipmod.ops.gemm_bf16_stats = timed_gemm, timed_ln, timed_stats
         nrep = 3
         for i in range(nrep):       # eager launches here: events cannot be recorded around nodes of a replayed graph
             flush.zero_()
             with torch.no_grad():
                 zs(dict(events=devb[i % NB][0], event_offsets=devb[i % NB][1], sel_idx=sel))
         torch.cuda.synchronize()
-        clipmod.ops.gemm_bf16 = orig
+        clipmod.ops.gemm_bf16, clipmod.ops.gemm_ln, clipmod.ops.gemm_bf16_stats = orig, _orig_ln, _orig_stats
         gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in rec)
         gemm_flops = sum(f for _, _, f, _ in rec)
         shapes = {}

@@ -44,6 +44,10 @@ SIGNATURES = {
     "ec_gemm_bf16": ([_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp], _i),
     "ec_layernorm": ([_vp, _i64, _vp, _vp, _i, _i, _vp, _vp, _vp], _i),
     "ec_layernorm_ex": ([_vp, _i, _i64, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp], _i),
+    "ec_gemm_stats_parts": ([_i], _i),
+    "ec_gemm_bf16_stats": ([_vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp], _i),
+    "ec_gemm_ln": ([_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp], _i),
+    "ec_row_stats_f16": ([_vp, _i64, _i, _i, _vp, _i, _vp], _i),
     "ec_attention": ([_vp, _vp, _i, _i, _i, _vp], _i),
     "ec_attention_ex": ([_vp, _vp, _i, _i, _i, _i, _vp], _i),
     "ec_embed_tokens": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp], _i),

@@ -117,6 +117,51 @@ def pack_blocks(resblocks, d, dev):
     return blocks
 
 
+def pack_blocks_ln(resblocks, d, dev):
+    """Per block, the operands of the LayerNorm-folded GEMMs (ec_gemm_ln): Wg = fp16(gamma * W_eff) with every row centred
+    (LoRA factors merged as in models/lora.py:138-149) and c = W_eff beta + b, so that   LN(x) W^T + b = rstd (x Wg^T) + c
+    (the mean term drops out because sum_k (x_k - mean) = 0).  Pack-time arithmetic (runs when a parameter changes, not
+    per batch) is done with torch in fp32."""
+    f32 = lambda t: t.detach().to(torch.float32)
+    out = []
+    for blk in resblocks:
+        W, lora_in, ib, _, _, _ = _attn_weights(blk.attn)
+        W = f32(W).clone()
+        if lora_in is not None:
+            for j, n in enumerate("qkv"):
+                up, down = getattr(lora_in, f"lora_up_{n}", None), getattr(lora_in, f"lora_down_{n}", None)
+                if up is not None and down is not None:
+                    W[j * d:(j + 1) * d] += f32(up) @ f32(down)
+        e = {}
+        for name, Wf, bf_, ln in (("in", W, f32(ib), blk.ln_1), ("fc", f32(blk.mlp.c_fc.weight), f32(blk.mlp.c_fc.bias), blk.ln_2)):
+            wg = Wf * f32(ln.weight)[None, :]
+            wg = (wg - wg.mean(1, keepdim=True)).to(torch.float16).contiguous()
+            e["wg_" + name] = wg
+            e["c_" + name] = (Wf @ f32(ln.bias) + bf_).contiguous()
+        out.append(e)
+    return out
+
+
+def run_blocks_ln(x, blocks, lnb, n_seq, Ltok, d, heads):
+    """x: fp16 residual stream [n_seq*Ltok, d].  No LayerNorm kernel: in_proj and c_fc read the stream itself as their A
+    operand and apply the normalisation in their epilogues from the row statistics that the previous residual epilogue
+    (out_proj / c_proj) wrote next to the rows."""
+    M, dev = n_seq * Ltok, x.device
+    parts = ops.gemm_stats_parts(d)
+    stats = torch.empty((M, parts, 2), dtype=torch.float32, device=dev)
+    ops.row_stats_f16(x, stats, parts)                       # the rows ln_pre wrote
+    qkv = torch.empty((M, 3 * d), dtype=torch.bfloat16, device=dev)
+    att = torch.empty((M, d), dtype=torch.bfloat16, device=dev)
+    hid = torch.empty((M, 4 * d), dtype=torch.bfloat16, device=dev)
+    for b, f in zip(blocks, lnb):
+        ops.gemm_ln(x, f["wg_in"], None, f["c_in"], stats, parts, "bf16", out=qkv)
+        ops.attention(qkv, att, n_seq, Ltok, heads)
+        ops.gemm_bf16_stats(att, b["w_out"], b["b_out"], x, stats)
+        ops.gemm_ln(x, f["wg_fc"], None, f["c_fc"], stats, parts, "bf16_qgelu", out=hid)
+        ops.gemm_bf16_stats(hid, b["w_proj"], b["b_proj"], x, stats)
+    return x
+
+
 def run_blocks(x, blocks, n_seq, Ltok, d, heads, causal=False):
     """x: residual stream [n_seq*Ltok, d], fp32 or fp16, updated in place by the GEMM epilogues."""
     M, dev = n_seq * Ltok, x.device
@@ -158,6 +203,9 @@ class VisionTransformer(nn.Module):
         # keeps the model in fp16, test.py:26-29) at half the residual traffic; EC_RESIDUAL=fp32 keeps it in float32.
         # The fine-tune forward (train.py) always uses fp32, as the reference's train.py:27-29 does.
         self.residual_dtype = torch.float32 if os.environ.get("EC_RESIDUAL", "fp16") == "fp32" else torch.float16
+        # ln_1 / ln_2 folded into the in_proj / c_fc GEMMs (fp16 stream only); EC_LN_FOLD=0 keeps the LayerNorm kernels
+        self.fold_ln = os.environ.get("EC_LN_FOLD", "1") != "0"
+        self._packed_ln, self._packed_ln_key = None, None
 
     # -- weight packing -------------------------------------------------------------------------------------------
     @property
@@ -172,6 +220,7 @@ class VisionTransformer(nn.Module):
     def invalidate_packed(self):
         """Call after mutating weights in a way the version counters cannot see (e.g. .data swaps)."""
         self._packed = None
+        self._packed_ln = None
 
     def packed(self):
         """bf16 copies of the GEMM weights in the layout the kernels read (LoRA factors merged, models/lora.py:138-149).
@@ -199,6 +248,20 @@ class VisionTransformer(nn.Module):
         pk["blocks"] = blocks
         self._packed, self._packed_key = pk, key
         return pk
+
+    def packed_ln(self):
+        """Operands of the LayerNorm-folded GEMMs, rebuilt when any parameter's version counter changes."""
+        key = self._version_key()
+        if self._packed_ln is None or key != self._packed_ln_key:
+            new = pack_blocks_ln(self.transformer.resblocks, self.width, self.proj.device)
+            if self._packed_ln is None:
+                self._packed_ln = new
+            else:       # rewrite in place: captured CUDA graphs keep reading the same buffers
+                for old_b, new_b in zip(self._packed_ln, new):
+                    for k, v in new_b.items():
+                        old_b[k].copy_(v)
+            self._packed_ln_key = key
+        return self._packed_ln
 
     def packed_train(self):
         """packed() plus the transposed bf16 weights the data-gradient GEMMs read (dX = dY . W needs W^T K-major)."""
@@ -268,7 +331,10 @@ class VisionTransformer(nn.Module):
             x = torch.empty((M, d), dtype=torch.float32, device=dev)
             ops.layernorm(x0, *pk["ln_pre"], M, d, out_f32=x)
         del x0
-        run_blocks(x, pk["blocks"], n_img, Ltok, d, heads)
+        if self.fold_ln and x.dtype == torch.float16:
+            run_blocks_ln(x, pk["blocks"], self.packed_ln(), n_img, Ltok, d, heads)
+        else:
+            run_blocks(x, pk["blocks"], n_img, Ltok, d, heads)
         cls = torch.empty((n_img, d), dtype=torch.bfloat16, device=dev)
         ops.layernorm(x, *pk["ln_post"], n_img, d, row_stride=Ltok * d, out_bf16=cls)
         return ops.gemm_bf16(cls, pk["proj"], None, "f32")

@@ -449,6 +449,40 @@ extern "C" int ec_layernorm_ex(const void *x, int x_is_f16, int64_t row_stride_i
     return launch_ln_t<float>((const float *)x, row_stride_in, gamma, beta, M, d, out_bf16, out_f32, out_f16, (cudaStream_t)stream);
 }
 
+// (sum, sum of squares) of every fp16 row into part 0 of a [M, n_parts] float2 table (other parts zeroed): the statistics the
+// LayerNorm-folded GEMM (ec_gemm_ln) reads when the rows were not written by a statistics-producing epilogue
+__global__ void __launch_bounds__(256) row_stats_f16_kernel(const __half *__restrict__ x, int64_t row_stride, int M, int d,
+                                                            float2 *__restrict__ stats, int n_parts)
+{
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const uint4 *xr = reinterpret_cast<const uint4 *>(x + (size_t)row * row_stride);
+    float s1 = 0.f, s2 = 0.f;
+    for (int j = lane; j < (d >> 3); j += 32) {
+        const uint4 u = xr[j];
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w[e]));
+            s1 += f.x + f.y;
+            s2 = fmaf(f.x, f.x, fmaf(f.y, f.y, s2));
+        }
+    }
+    s1 = ec::warp_sum(s1); s2 = ec::warp_sum(s2);
+    if (lane < n_parts) stats[(size_t)row * n_parts + lane] = lane == 0 ? make_float2(s1, s2) : make_float2(0.f, 0.f);
+}
+
+extern "C" int ec_row_stats_f16(const void *x, int64_t row_stride, int M, int d, float *stats, int n_parts, void *stream)
+{
+    EC_REQUIRE(x && stats && M > 0 && d > 0 && d % 8 == 0 && row_stride % 8 == 0 && n_parts >= 1 && n_parts <= 32 &&
+               ((uintptr_t)x & 15) == 0 && ((uintptr_t)stats & 7) == 0, "ec_row_stats_f16: bad arguments");
+    row_stats_f16_kernel<<<(unsigned)((M + 7) / 8), 256, 0, (cudaStream_t)stream>>>((const __half *)x, row_stride, M, d,
+                                                                                    (float2 *)stats, n_parts);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
 extern "C" int ec_layernorm_f32(const float *x, const float *gamma, const float *beta, int M, int d, float *out,
                                 void *stream)
 {

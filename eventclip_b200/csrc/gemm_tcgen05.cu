@@ -53,6 +53,14 @@ struct GemmParams {
     unsigned long long *stamp;   // optional {start, end} %globaltimer stamps of this launch (ec_gemm_timing)
     int mn_major;         // 1: operands are [K, M] / [K, N] row-major (reduction index = row): MN-major UMMA operands, tiles
                           //    arrive as boxes of 64 (m or n) x 64 (k), one 8 KB box per 64 rows of the tile
+    // LayerNorm folded into the GEMMs (ec_gemm_ln / ec_gemm_bf16_stats):
+    int a_f16;                 // both operands hold fp16 (A = the residual stream itself, W = fp16(gamma * W)) instead of bf16
+    const float2 *ln_stats;    // consumer: [M, ln_parts] partial (sum x, sum x^2) of every row of A; NULL = plain epilogue
+    int ln_parts;
+    const float *ln_colsum;    // consumer: s_j = sum_k W'[j,k] of the gamma-scaled weight; `bias` holds c_j = beta . W[j] + b_j
+    float inv_k;               // 1 / K
+    float2 *stats_out;         // producer (EC_EPI_F16_RESADD): partial (sum, sum of squares) of the fp16 values it writes,
+                               //    one float2 per row and per 128-column half tile: [M, 2 * tiles_n]
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -413,7 +421,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     // K-major: 16 elements = 32 bytes along K inside the swizzle atom (+2 in 16-byte units);
                     // MN-major: 16 k-rows of 128 bytes = 2048 bytes (+128)
                     const uint64_t kstep = p.mn_major ? 128 : 2;
-                    const uint32_t idesc = p.mn_major ? (IDESC | (1u << 15) | (1u << 16)) : IDESC;
+                    const uint32_t idesc = (p.mn_major ? (IDESC | (1u << 15) | (1u << 16)) : IDESC) & (p.a_f16 ? ~((1u << 7) | (1u << 10)) : ~0u);   // bits 7 / 10: A / B are bf16 (a mixed fp16 x bf16 pair is rejected by the hardware)
                     if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -457,6 +465,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
                 const int row0 = (tm * CG + (int)cta_rank) * BM + quarter * 32;
                 const int colw = tn * BN + half * COLS_PER_WARP;
+                // LayerNorm folded in: out = rstd (acc - mean s_j) + c_j with this thread's row statistics
+                float ln_r = 1.f, ln_m = 0.f;
+                if (p.ln_stats) {
+                    const int r = min(row0 + lane, p.M - 1);
+                    float s1 = 0.f, s2 = 0.f;
+                    for (int i = 0; i < p.ln_parts; ++i) {
+                        const float2 t = p.ln_stats[(size_t)r * p.ln_parts + i];
+                        s1 += t.x; s2 += t.y;
+                    }
+                    const float mean = s1 * p.inv_k;
+                    ln_r = rsqrtf(fmaxf(s2 * p.inv_k - mean * mean, 0.f) + 1e-5f);
+                    ln_m = -mean * ln_r;
+                }
                 mbar_wait(&tfull_bar[as], aphase);
                 tc_fence_after();
                 const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * COLS_PER_WARP);
@@ -468,12 +489,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     float4 bq[8];                            // the 32 biases of this chunk: 8 broadcast loads
 #pragma unroll
                     for (int q = 0; q < 8; ++q) bq[q] = bias4(p.bias, col0 + 4 * q, p.N);
+                    if (p.ln_stats && p.ln_colsum) {         // c_j - mean rstd s_j (not needed when the rows of Wg sum to zero)
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 sj = bias4(p.ln_colsum, col0 + 4 * q, p.N);
+                            bq[q].x = fmaf(ln_m, sj.x, bq[q].x); bq[q].y = fmaf(ln_m, sj.y, bq[q].y);
+                            bq[q].z = fmaf(ln_m, sj.z, bq[q].z); bq[q].w = fmaf(ln_m, sj.w, bq[q].w);
+                        }
+                    }
                     tmem_ld_wait();
                     uint32_t pk[16];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        const float f0 = __uint_as_float(v[4 * q]) + bq[q].x, f1 = __uint_as_float(v[4 * q + 1]) + bq[q].y;
-                        const float f2 = __uint_as_float(v[4 * q + 2]) + bq[q].z, f3 = __uint_as_float(v[4 * q + 3]) + bq[q].w;
+                        const float f0 = fmaf(__uint_as_float(v[4 * q]), ln_r, bq[q].x), f1 = fmaf(__uint_as_float(v[4 * q + 1]), ln_r, bq[q].y);
+                        const float f2 = fmaf(__uint_as_float(v[4 * q + 2]), ln_r, bq[q].z), f3 = fmaf(__uint_as_float(v[4 * q + 3]), ln_r, bq[q].w);
                         __nv_bfloat162 h0, h1;
                         if (p.epi == EC_EPI_BF16_QGELU) {
                             h0 = __floats2bfloat162_rn(quick_gelu(f0), quick_gelu(f1));
@@ -597,6 +626,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * COLS_PER_WARP);
                 uint32_t v[32];
                 tmem_ld32_issue(tbase, v);
+                float st1 = 0.f, st2 = 0.f;      // this row's sum / sum of squares over the warp's 128 columns (as rounded to fp16)
 #pragma unroll 1
                 for (int c = 0; c < NCHUNK; ++c) {
                     const int col0 = colw + c * 32;
@@ -627,6 +657,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                             const __half2 o = __floats2half2_rn(r.x + __uint_as_float(v[8 * q + 2 * e]) + b0,
                                                                 r.y + __uint_as_float(v[8 * q + 2 * e + 1]) + b1);
                             ow[e] = *reinterpret_cast<const uint32_t *>(&o);
+                            if (p.stats_out && col0 + 8 * q + 2 * e < p.N) {
+                                const float2 of = __half22float2(o);
+                                st1 += of.x + of.y;
+                                st2 = fmaf(of.x, of.x, fmaf(of.y, of.y, st2));
+                            }
                         }
                         sts128u(a, ow[0], ow[1], ow[2], ow[3]);
                     }
@@ -636,6 +671,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     if (lane == 0 && row0 < p.M && col0 < p.N) tma_store_2d(&map_o, box, col0, row0);
                     ++nbox;
                 }
+                if (p.stats_out && row0 + lane < p.M)
+                    p.stats_out[(size_t)(row0 + lane) * (2 * p.tiles_n) + 2 * tn + half] = make_float2(st1, st2);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
@@ -920,10 +957,43 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float4 *__rest
     }
 }
 
+struct GemmExtra {            // LayerNorm folded into the GEMMs
+    int a_f16 = 0;
+    const float *ln_stats = nullptr, *ln_colsum = nullptr;
+    int ln_parts = 0;
+    float *stats_out = nullptr;
+};
+
 int gemm_impl(const void *A, int lda, const void *W, int ldw, const float *bias, int M, int N, int K, int epi, void *out, int ldo,
-              const float *res, int row_map, int splits, cudaStream_t stream, int mn_major = 0);
+              const float *res, int row_map, int splits, cudaStream_t stream, int mn_major = 0, const GemmExtra *ex = nullptr);
 
 }  // namespace
+
+extern "C" int ec_gemm_bf16_stats(const void *A, int lda, const void *W, int ldw, const float *bias, int M, int N, int K, void *out,
+                                  int ldo, const void *res, float *stats_out, void *stream_)
+{
+    EC_REQUIRE(stats_out && ((uintptr_t)stats_out & 7) == 0, "ec_gemm_bf16_stats: stats_out must be an 8-byte aligned buffer");
+    GemmExtra ex;
+    ex.stats_out = stats_out;
+    return gemm_impl(A, lda, W, ldw, bias, M, N, K, EC_EPI_F16_RESADD, out, ldo, (const float *)res, 0, 1, (cudaStream_t)stream_, 0, &ex);
+}
+
+extern "C" int ec_gemm_stats_parts(int N)
+{
+    const int BN = (N % 256 == 0) ? 256 : 128;
+    return 2 * ((N + BN - 1) / BN);
+}
+
+extern "C" int ec_gemm_ln(const void *X, int ldx, const void *Wg, int ldw, const float *colsum, const float *cbias,
+                          const float *stats, int n_parts, int M, int N, int K, int epi, void *out, int ldo, void *stream_)
+{
+    EC_REQUIRE(cbias && stats && n_parts > 0 && ((uintptr_t)stats & 7) == 0, "ec_gemm_ln: null / misaligned LayerNorm operands");
+    EC_REQUIRE(epi == EC_EPI_BF16 || epi == EC_EPI_BF16_QGELU, "ec_gemm_ln: bf16 epilogues only (got %d)", epi);
+    GemmExtra ex;
+    ex.a_f16 = 1;
+    ex.ln_stats = stats; ex.ln_parts = n_parts; ex.ln_colsum = colsum;
+    return gemm_impl(X, ldx, Wg, ldw, cbias, M, N, K, epi, out, ldo, nullptr, 0, 1, (cudaStream_t)stream_, 0, &ex);
+}
 
 extern "C" int ec_gemm_bf16(const void *A, int lda, const void *W, int ldw, const float *bias, int M, int N, int K,
                             int epi, void *out, int ldo, const float *res, int row_map, void *stream_)
@@ -999,7 +1069,7 @@ extern "C" int ec_gemm_bf16_tn_splitk(const void *A, int lda, const void *B, int
 namespace {
 
 int gemm_impl(const void *A, int lda, const void *W, int ldw, const float *bias, int M, int N, int K, int epi, void *out, int ldo,
-              const float *res, int row_map, int splits, cudaStream_t stream, int mn_major)
+              const float *res, int row_map, int splits, cudaStream_t stream, int mn_major, const GemmExtra *ex)
 {
     EC_REQUIRE(A && W && out, "ec_gemm_bf16: null pointer");
     EC_REQUIRE(M > 0 && N > 0 && K >= BK, "ec_gemm_bf16: need M,N > 0 and K >= 64 (got %d,%d,%d)", M, N, K);
@@ -1045,6 +1115,12 @@ int gemm_impl(const void *A, int lda, const void *W, int ldw, const float *bias,
     GemmParams p;
     p.M = M; p.N = N; p.K = K; p.epi = epi; p.out = out; p.ldo = ldo; p.bias = bias; p.res = res; p.row_map = row_map;
     p.mn_major = mn_major;
+    p.a_f16 = ex ? ex->a_f16 : 0;
+    p.ln_stats = ex ? reinterpret_cast<const float2 *>(ex->ln_stats) : nullptr;
+    p.ln_parts = ex ? ex->ln_parts : 0;
+    p.ln_colsum = ex ? ex->ln_colsum : nullptr;
+    p.inv_k = 1.0f / (float)K;
+    p.stats_out = ex ? reinterpret_cast<float2 *>(ex->stats_out) : nullptr;
     p.stamp = (g_stamp_buf && g_stamp_next < g_stamp_cap) ? g_stamp_buf + 2 * (g_stamp_next++) : nullptr;
     p.tx_bytes = (uint32_t)(box_a + box_w) * BK * 2 * CG;   // a pair's leader barrier collects both CTAs' bytes
     {

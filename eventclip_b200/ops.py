@@ -172,6 +172,54 @@ def gemm_bf16(A, W, bias=None, epi="bf16", out=None, res=None, row_map=0, M=None
     return out
 
 
+def gemm_stats_parts(N):
+    """float2 statistics slots per row written by gemm_bf16_stats for an N-column output."""
+    return int(L.load().ec_gemm_stats_parts(int(N)))
+
+
+def gemm_bf16_stats(A, W, bias, x, stats):
+    """x (fp16 [M,N], in place) += A @ W.T + bias, and stats float32 [M, parts, 2] = per-row partial (sum, sum of squares) of
+    the new x: what the LayerNorm-folded GEMM that reads x next needs."""
+    _dev(A, torch.bfloat16, "A")
+    _dev(W, torch.bfloat16, "W")
+    _dev(x, torch.float16, "x")
+    _dev(stats, torch.float32, "stats")
+    M, (N, K) = A.shape[0], W.shape
+    if stats.numel() < M * gemm_stats_parts(N) * 2:
+        raise L.ECError("gemm_bf16_stats: statistics buffer too small")
+    with torch.cuda.device(A.device):
+        L.check(L.load().ec_gemm_bf16_stats(_ptr(A), A.stride(0), _ptr(W), W.stride(0), _ptr(bias), M, N, K, _ptr(x), x.stride(0),
+                                            _ptr(x), _ptr(stats), _stream()), "ec_gemm_bf16_stats")
+    return x
+
+
+def gemm_ln(x, Wg, colsum, cbias, stats, n_parts, epi="bf16", out=None):
+    """out bf16 = epi(LayerNorm(x) @ W.T + b) with the LayerNorm folded into the GEMM: x fp16 [M,K] is the A operand itself,
+    Wg = fp16(gamma * W), colsum[j] = sum_k Wg[j,k], cbias[j] = beta . W[j] + b[j], stats = per-row partial sums."""
+    _dev(x, torch.float16, "x")
+    _dev(Wg, torch.float16, "Wg")
+    _dev(stats, torch.float32, "stats")
+    M, (N, K) = x.shape[0], Wg.shape
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
+    epi_id = {"bf16": L.EC_EPI_BF16, "bf16_qgelu": L.EC_EPI_BF16_QGELU}[epi]
+    with torch.cuda.device(x.device):
+        L.check(L.load().ec_gemm_ln(_ptr(x), x.stride(0), _ptr(Wg), Wg.stride(0), _ptr(colsum), _ptr(cbias), _ptr(stats), int(n_parts),
+                                    M, N, K, epi_id, _ptr(out), out.stride(0), _stream()), "ec_gemm_ln")
+    return out
+
+
+def row_stats_f16(x, stats, n_parts, M=None, row_stride=None):
+    """stats[row, 0] = (sum, sum of squares) of the fp16 row; the other parts are zeroed."""
+    _dev(x, torch.float16, "x")
+    _dev(stats, torch.float32, "stats")
+    M = x.shape[0] if M is None else M
+    d = x.shape[-1]
+    with torch.cuda.device(x.device):
+        L.check(L.load().ec_row_stats_f16(_ptr(x), int(row_stride or d), M, d, _ptr(stats), int(n_parts), _stream()), "ec_row_stats_f16")
+    return stats
+
+
 def layernorm(x, gamma, beta, M, d, row_stride=None, out_bf16=None, out_f32=None, out_f16=None):
     """x: fp32, or fp16 (the fp16 residual stream); out_f16 is what ln_pre writes to start that stream."""
     if x.dtype == torch.float16 or out_f16 is not None:

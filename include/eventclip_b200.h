@@ -168,6 +168,26 @@ EC_API int ec_layernorm(const float *x, int64_t row_stride_in, const float *gamm
 EC_API int ec_layernorm_ex(const void *x, int x_is_f16, int64_t row_stride_in, const float *gamma, const float *beta, int M,
                            int d, void *out_bf16, float *out_f32, void *out_f16, void *stream);
 
+/* ---- LayerNorm folded into the GEMMs of the fp16 residual stream (ln_1 -> in_proj, ln_2 -> c_fc of openai/CLIP's
+ *      ResidualAttentionBlock [3P], called through models/clip_cls.py:101).  With Wg = fp16(gamma * W) (column k scaled by
+ *      gamma_k; fp16 because tcgen05.mma kind::f16 rejects an fp16 x bf16 operand pair), s_j = sum_k Wg[j,k] and
+ *      c_j = beta . W[j] + b_j:   LN(x) W^T + b  =  rstd (x Wg^T - mean s) + c.   When every row of Wg is centred
+ *      (Wg[j,:] -= mean_k Wg[j,k]; allowed because sum_k (x_k - mean) = 0) s vanishes: pass colsum = NULL and the epilogue is
+ *      one fma per element.  The GEMM reads the fp16 residual rows themselves as its A operand; the row statistics arrive as
+ *      partial (sum, sum of squares) pairs written by the epilogue that produced the rows. */
+/* number of float2 statistics slots per row that ec_gemm_bf16_stats writes for an N-column output */
+EC_API int ec_gemm_stats_parts(int N);
+/* out fp16 = res(fp16) + A W^T + bias (EC_EPI_F16_RESADD) and stats_out float [M, parts, 2] = per-row partial sums of the values
+ * written (parts = ec_gemm_stats_parts(N)) */
+EC_API int ec_gemm_bf16_stats(const void *A, int lda, const void *W, int ldw, const float *bias, int M, int N, int K, void *out,
+                              int ldo, const void *res, float *stats_out, void *stream);
+/* out bf16 = epi(LayerNorm(X) W^T + b) from X fp16 [M,K] (ldx), Wg fp16 [N,K], colsum s [N] or NULL, cbias c [N], stats float
+ * [M, n_parts, 2];  epi = EC_EPI_BF16 or EC_EPI_BF16_QGELU */
+EC_API int ec_gemm_ln(const void *X, int ldx, const void *Wg, int ldw, const float *colsum, const float *cbias,
+                      const float *stats, int n_parts, int M, int N, int K, int epi, void *out, int ldo, void *stream);
+/* stats[row, 0] = (sum, sum of squares) of the fp16 row, other parts zero: statistics for rows no GEMM epilogue produced */
+EC_API int ec_row_stats_f16(const void *x, int64_t row_stride, int M, int d, float *stats, int n_parts, void *stream);
+
 /* Multi-head self-attention core on the packed QKV activations of nn.MultiheadAttention:
  * qkv bf16 [n_img*L, 3*d] (q | k | v, head h at columns h*64), out bf16 [n_img*L, d].
  * softmax(q k^T / sqrt(64)) v per (image, head); head_dim is 64 for every CLIP ViT. */

@@ -76,6 +76,48 @@ def test_gemm_epilogues(cuda_dev):
     assert rel(got[:, 1:], want) < 2e-3 and (got[:, 0] == 7.0).all()
 
 
+def test_layernorm_folded_into_gemms(cuda_dev):
+    """ec_gemm_bf16_stats writes the row statistics of the fp16 stream it produces; ec_gemm_ln reads the stream itself as A and
+    applies rstd (acc - mean s_j) + c_j -- against LayerNorm + Linear in fp32 on the same fp16 rows."""
+    g = torch.Generator().manual_seed(12)
+    for M, d, N2 in ((394, 768, 2304), (1000, 768, 3072), (300, 1024, 1024), (70, 256, 384)):
+        A = bf(torch.randn(M, d, generator=g))
+        Wo = bf(torch.randn(d, d, generator=g) * d ** -0.5)
+        bo = torch.randn(d, generator=g)
+        x0 = (torch.randn(M, d, generator=g) * 2 + 0.5).half()
+        gamma, beta = torch.rand(d, generator=g) + 0.5, torch.randn(d, generator=g) * 0.1
+        W2 = torch.randn(N2, d, generator=g) * d ** -0.5
+        b2 = torch.randn(N2, generator=g)
+        parts = ops.gemm_stats_parts(d)
+        x = x0.to(cuda_dev).clone()
+        stats = torch.full((M, parts, 2), 7.0, device=cuda_dev)
+        ops.gemm_bf16_stats(A.to(cuda_dev), Wo.to(cuda_dev), bo.to(cuda_dev), x, stats)
+        want_x = A.float() @ Wo.float().t() + bo + x0.float()
+        assert rel(x.float(), want_x) < 2e-3
+        xs = x.float().cpu()                                     # statistics are those of the ROUNDED stream
+        st = stats.cpu().sum(1)
+        assert (st[:, 0] - xs.sum(1)).abs().max() < 1e-3 * xs.abs().sum(1).max()
+        assert (st[:, 1] - (xs * xs).sum(1)).abs().max() < 1e-4 * (xs * xs).sum(1).max()
+        # consumer
+        Wg = (W2 * gamma[None, :]).half()
+        colsum, cbias = Wg.float().sum(1), W2 @ beta + b2
+        ref = torch.nn.functional.layer_norm(xs, (d,), gamma, beta, 1e-5) @ W2.t() + b2
+        for epi, want in (("bf16", ref), ("bf16_qgelu", ref * torch.sigmoid(1.702 * ref))):
+            got = ops.gemm_ln(x, Wg.to(cuda_dev), colsum.to(cuda_dev), cbias.to(cuda_dev), stats, parts, epi)
+            assert got.dtype == torch.bfloat16 and rel(got.float(), want) < 8e-3, (M, d, epi, rel(got.float(), want))
+        # centred rows of Wg: the mean term drops out, no column sums needed (what the encoder uses)
+        Wc = W2 * gamma[None, :]
+        Wc = (Wc - Wc.mean(1, keepdim=True)).half()
+        gotc = ops.gemm_ln(x, Wc.to(cuda_dev), None, cbias.to(cuda_dev), stats, parts, "bf16")
+        assert rel(gotc.float(), ref) < 8e-3, (M, d, rel(gotc.float(), ref))
+        # statistics from the stand-alone kernel (rows no epilogue produced) give the same result
+        st2 = torch.full((M, parts, 2), 3.0, device=cuda_dev)
+        ops.row_stats_f16(x, st2, parts)
+        assert (st2[:, 1:] == 0).all() and (st2[:, 0].cpu() - st).abs().max() < 1e-3 * st.abs().max()
+        got2 = ops.gemm_ln(x, Wg.to(cuda_dev), colsum.to(cuda_dev), cbias.to(cuda_dev), st2, parts, "bf16")
+        assert rel(got2.float(), ref) < 8e-3
+
+
 def test_layernorm_and_helpers(cuda_dev):
     g = torch.Generator().manual_seed(4)
     for M, d in ((37, 768), (5, 1024), (9, 128), (3, 2048)):
