@@ -461,22 +461,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             //      warp alternate; cp.async.bulk.wait_group.read guards their reuse.  Rows >= M and columns >= N are
             //      clipped by the tensor map. ----
             uint32_t as = 0, aphase = 0, nbox = 0;
+            // LayerNorm folded in: out = rstd (acc - mean s_j) + c_j with this thread's row statistics; those of the NEXT tile
+            // are fetched while the current one is processed (this epilogue is the critical path of the K = 768 GEMMs)
+            float nx1 = 0.f, nx2 = 0.f;
+            auto fetch_stats = [&](int tile_) {
+                nx1 = 0.f; nx2 = 0.f;
+                if (p.ln_stats && tile_ < num_tiles) {
+                    const int r = min(((tile_ / p.tiles_n) * CG + (int)cta_rank) * BM + quarter * 32 + lane, p.M - 1);
+                    // parts is even (two 128-column halves per tile): 16-byte loads, at most 8 of them in flight at once
+                    const float4 *sp = reinterpret_cast<const float4 *>(p.ln_stats + (size_t)r * p.ln_parts);
+                    float4 t[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) t[i] = 2 * i < p.ln_parts ? __ldg(sp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { nx1 += t[i].x + t[i].z; nx2 += t[i].y + t[i].w; }
+                }
+            };
+            fetch_stats(group_id);
             for (int tile = group_id; tile < num_tiles; tile += num_groups) {
                 const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
                 const int row0 = (tm * CG + (int)cta_rank) * BM + quarter * 32;
                 const int colw = tn * BN + half * COLS_PER_WARP;
-                // LayerNorm folded in: out = rstd (acc - mean s_j) + c_j with this thread's row statistics
                 float ln_r = 1.f, ln_m = 0.f;
                 if (p.ln_stats) {
-                    const int r = min(row0 + lane, p.M - 1);
-                    float s1 = 0.f, s2 = 0.f;
-                    for (int i = 0; i < p.ln_parts; ++i) {
-                        const float2 t = p.ln_stats[(size_t)r * p.ln_parts + i];
-                        s1 += t.x; s2 += t.y;
-                    }
-                    const float mean = s1 * p.inv_k;
-                    ln_r = rsqrtf(fmaxf(s2 * p.inv_k - mean * mean, 0.f) + 1e-5f);
+                    const float mean = nx1 * p.inv_k;
+                    ln_r = rsqrtf(fmaxf(nx2 * p.inv_k - mean * mean, 0.f) + 1e-5f);
                     ln_m = -mean * ln_r;
+                    fetch_stats(tile + num_groups);
                 }
                 mbar_wait(&tfull_bar[as], aphase);
                 tc_fence_after();
@@ -654,14 +665,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                             const float2 r = __half22float2(*reinterpret_cast<const __half2 *>(&hw[e]));
                             const float4 b = bq[2 * q + (e >> 1)];
                             const float b0 = (e & 1) ? b.z : b.x, b1 = (e & 1) ? b.w : b.y;
-                            const __half2 o = __floats2half2_rn(r.x + __uint_as_float(v[8 * q + 2 * e]) + b0,
-                                                                r.y + __uint_as_float(v[8 * q + 2 * e + 1]) + b1);
+                            const float o0 = r.x + __uint_as_float(v[8 * q + 2 * e]) + b0, o1 = r.y + __uint_as_float(v[8 * q + 2 * e + 1]) + b1;
+                            const __half2 o = __floats2half2_rn(o0, o1);
                             ow[e] = *reinterpret_cast<const uint32_t *>(&o);
-                            if (p.stats_out && col0 + 8 * q + 2 * e < p.N) {
-                                const float2 of = __half22float2(o);
-                                st1 += of.x + of.y;
-                                st2 = fmaf(of.x, of.x, fmaf(of.y, of.y, st2));
-                            }
+                            // statistics of the values before their fp16 rounding (2^-12 relative apart from what the consumer
+                            // reads); columns >= N hold exact zeros (zero-filled operands, bias and residual)
+                            st1 += o0 + o1;
+                            st2 = fmaf(o0, o0, fmaf(o1, o1, st2));
                         }
                         sts128u(a, ow[0], ow[1], ow[2], ow[3]);
                     }
@@ -987,7 +997,8 @@ extern "C" int ec_gemm_stats_parts(int N)
 extern "C" int ec_gemm_ln(const void *X, int ldx, const void *Wg, int ldw, const float *colsum, const float *cbias,
                           const float *stats, int n_parts, int M, int N, int K, int epi, void *out, int ldo, void *stream_)
 {
-    EC_REQUIRE(cbias && stats && n_parts > 0 && ((uintptr_t)stats & 7) == 0, "ec_gemm_ln: null / misaligned LayerNorm operands");
+    EC_REQUIRE(cbias && stats && n_parts > 0 && n_parts <= 16 && n_parts % 2 == 0 && ((uintptr_t)stats & 15) == 0,
+               "ec_gemm_ln: null / misaligned LayerNorm operands (statistics: 16-byte aligned, an even number of parts <= 16)");
     EC_REQUIRE(epi == EC_EPI_BF16 || epi == EC_EPI_BF16_QGELU, "ec_gemm_ln: bf16 epilogues only (got %d)", epi);
     GemmExtra ex;
     ex.a_f16 = 1;
