@@ -331,7 +331,7 @@ class VisionTransformer(nn.Module):
             x = torch.empty((M, d), dtype=torch.float32, device=dev)
             ops.layernorm(x0, *pk["ln_pre"], M, d, out_f32=x)
         del x0
-        if self.fold_ln and x.dtype == torch.float16:
+        if self.fold_ln and x.dtype == torch.float16 and ops.gemm_stats_parts(d) <= 8:
             run_blocks_ln(x, pk["blocks"], self.packed_ln(), n_img, Ltok, d, heads)
         else:
             run_blocks(x, pk["blocks"], n_img, Ltok, d, heads)

@@ -463,19 +463,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             uint32_t as = 0, aphase = 0, nbox = 0;
             // LayerNorm folded in: out = rstd (acc - mean s_j) + c_j with this thread's row statistics; those of the NEXT tile
             // are fetched while the current one is processed (this epilogue is the critical path of the K = 768 GEMMs)
-            float nx1 = 0.f, nx2 = 0.f;
+            // The raw partials stay in registers until the next tile starts, so the loads never stall this in-order warp.
+            float4 nt[4];             // <= 8 partial (sum, sum of squares) pairs of the next tile's row
             auto fetch_stats = [&](int tile_) {
-                nx1 = 0.f; nx2 = 0.f;
-                if (p.ln_stats && tile_ < num_tiles) {
-                    const int r = min(((tile_ / p.tiles_n) * CG + (int)cta_rank) * BM + quarter * 32 + lane, p.M - 1);
-                    // parts is even (two 128-column halves per tile): 16-byte loads, at most 8 of them in flight at once
-                    const float4 *sp = reinterpret_cast<const float4 *>(p.ln_stats + (size_t)r * p.ln_parts);
-                    float4 t[8];
+                const bool on = p.ln_stats && tile_ < num_tiles;
+                const int r = min(((tile_ / p.tiles_n) * CG + (int)cta_rank) * BM + quarter * 32 + lane, p.M - 1);
+                const float4 *sp = reinterpret_cast<const float4 *>(p.ln_stats + (size_t)(on ? r : 0) * p.ln_parts);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) t[i] = 2 * i < p.ln_parts ? __ldg(sp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) { nx1 += t[i].x + t[i].z; nx2 += t[i].y + t[i].w; }
-                }
+                for (int i = 0; i < 4; ++i) nt[i] = (on && 2 * i < p.ln_parts) ? __ldg(sp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             };
             fetch_stats(group_id);
             for (int tile = group_id; tile < num_tiles; tile += num_groups) {
@@ -484,8 +479,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 const int colw = tn * BN + half * COLS_PER_WARP;
                 float ln_r = 1.f, ln_m = 0.f;
                 if (p.ln_stats) {
-                    const float mean = nx1 * p.inv_k;
-                    ln_r = rsqrtf(fmaxf(nx2 * p.inv_k - mean * mean, 0.f) + 1e-5f);
+                    const float s1 = (nt[0].x + nt[0].z) + (nt[1].x + nt[1].z) + (nt[2].x + nt[2].z) + (nt[3].x + nt[3].z);
+                    const float s2 = (nt[0].y + nt[0].w) + (nt[1].y + nt[1].w) + (nt[2].y + nt[2].w) + (nt[3].y + nt[3].w);
+                    const float mean = s1 * p.inv_k;
+                    ln_r = rsqrtf(fmaxf(s2 * p.inv_k - mean * mean, 0.f) + 1e-5f);
                     ln_m = -mean * ln_r;
                     fetch_stats(tile + num_groups);
                 }
@@ -997,8 +994,8 @@ extern "C" int ec_gemm_stats_parts(int N)
 extern "C" int ec_gemm_ln(const void *X, int ldx, const void *Wg, int ldw, const float *colsum, const float *cbias,
                           const float *stats, int n_parts, int M, int N, int K, int epi, void *out, int ldo, void *stream_)
 {
-    EC_REQUIRE(cbias && stats && n_parts > 0 && n_parts <= 16 && n_parts % 2 == 0 && ((uintptr_t)stats & 15) == 0,
-               "ec_gemm_ln: null / misaligned LayerNorm operands (statistics: 16-byte aligned, an even number of parts <= 16)");
+    EC_REQUIRE(cbias && stats && n_parts > 0 && n_parts <= 8 && n_parts % 2 == 0 && ((uintptr_t)stats & 15) == 0,
+               "ec_gemm_ln: null / misaligned LayerNorm operands (statistics: 16-byte aligned, an even number of parts <= 8)");
     EC_REQUIRE(epi == EC_EPI_BF16 || epi == EC_EPI_BF16_QGELU, "ec_gemm_ln: bf16 epilogues only (got %d)", epi);
     GemmExtra ex;
     ex.a_f16 = 1;
