@@ -63,6 +63,13 @@ class GraphedClassifier:
         self.status = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.cache = {}
         self.max_graphs = max_graphs
+        self._params = list(model.parameters())
+        self._weights_sig = self._signature()
+
+    def _signature(self):
+        """Changes whenever a parameter is updated in place or replaced (optimizer step, load_state_dict): the captured
+        graphs read packed copies of the weights whose buffers are re-created then, so they must be captured again."""
+        return sum(p._version for p in self._params) + sum(p.data_ptr() for p in self._params[:1])
 
     def _build(self, plan):
         e = _Entry()
@@ -91,6 +98,11 @@ class GraphedClassifier:
         n = ev.shape[0]
         if n > self.events.shape[0]:
             raise L.ECError(f"batch has {n} events but the graph buffer holds {self.events.shape[0]}")
+        sig = self._signature()
+        if sig != self._weights_sig:          # weights changed since the graphs were captured
+            torch.cuda.synchronize(self.dev)
+            self.cache.clear()
+            self._weights_sig = sig
         key = _plan_key(plan)
         ent = self.cache.get(key)
         if ent is None:

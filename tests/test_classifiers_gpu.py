@@ -217,6 +217,13 @@ def test_cuda_graph_replay_matches_eager(cuda_dev):
         for k in ("full_logits", "logits", "probs", "top5_logits"):
             assert torch.equal(got[k], eager[k]), (seed, k)
     assert len(g.cache) == 2
+    # a weight update after the capture is picked up: the graphs are captured again over the re-packed weights
+    with torch.no_grad():
+        model.visual.transformer.resblocks[0].ln_1.weight.mul_(1.5)
+        model.visual.proj.mul_(0.5)
+        eager = zs(d)
+        got = g(d)
+    assert torch.equal(got["logits"], eager["logits"]) and len(g.cache) == 1
 
 
 def test_pipelined_stream_matches_sequential_calls(cuda_dev):
