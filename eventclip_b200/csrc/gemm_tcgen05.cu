@@ -489,10 +489,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 mbar_wait(&tfull_bar[as], aphase);
                 tc_fence_after();
                 const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * COLS_PER_WARP);
-                uint32_t v[32];
-                tmem_ld32_issue(tbase, v);
-#pragma unroll 1
-                for (int c = 0; c < NCHUNK; ++c) {
+                // two register sets for the accumulator chunks: the tensor-memory load of chunk c+1 is issued as soon as
+                // chunk c has landed, so its latency hides behind the math, the staging and the store of chunk c
+                uint32_t va[32], vb[32];
+                tmem_ld32_issue(tbase, va);
+                auto chunk = [&](const int c, uint32_t (&v)[32], uint32_t (&vn)[32]) {
                     const int col0 = colw + c * 32;
                     float4 bq[8];                            // the 32 biases of this chunk: 8 broadcast loads
 #pragma unroll
@@ -506,6 +507,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                         }
                     }
                     tmem_ld_wait();
+                    if (c + 1 < NCHUNK) tmem_ld32_issue(tbase + (uint32_t)((c + 1) * 32), vn);
                     uint32_t pk[16];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
@@ -522,7 +524,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                         pk[2 * q] = *reinterpret_cast<uint32_t *>(&h0);
                         pk[2 * q + 1] = *reinterpret_cast<uint32_t *>(&h1);
                     }
-                    if (c + 1 < NCHUNK) tmem_ld32_issue(tbase + (uint32_t)((c + 1) * 32), v);   // overlaps the store below
                     const uint32_t box = stg + (nbox & 1) * 2048;
                     if (lane == 0) bulk_wait_read<1>();       // the store issued two boxes ago has drained this buffer
                     __syncwarp();
@@ -537,6 +538,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                         if (lane == 0 && row0 < p.M) tma_store_2d(&map_o, box, col0, row0);
                     }
                     ++nbox;
+                };
+#pragma unroll 1
+                for (int c = 0; c < NCHUNK; c += 2) {
+                    chunk(c, va, vb);
+                    if (c + 1 < NCHUNK) chunk(c + 1, vb, va);
                 }
                 tc_fence_before();
                 __syncwarp();
