@@ -36,10 +36,25 @@ def test_header_constants_match_binding():
     for name in ("EC_OK", "EC_ERR_ARG", "EC_ERR_CUDA", "EC_ERR_UNSUPPORTED", "EC_ERR_CAPACITY", "EC_STATUS_BAD_COORD",
                  "EC_STATUS_COUNT_OVERFLOW", "EC_FLAG_COUNT_NON_ZERO", "EC_FLAG_BACKGROUND_MASK", "EC_OUT_F32_NCHW",
                  "EC_OUT_BF16_NCHW", "EC_OUT_BF16_PATCH", "EC_EPI_BF16", "EC_EPI_BF16_QGELU", "EC_EPI_F32_RESADD",
-                 "EC_EPI_F32", "EC_EPI_PATCH"):
+                 "EC_EPI_F32", "EC_EPI_PATCH", "EC_EPI_F16_RESADD"):
         m = re.search(rf"#define {name}\s+(-?\d+)", hdr)
         assert m and int(m.group(1)) == getattr(_lib, name), name
     assert ctypes.sizeof(_lib.ECFrame) == 16
+
+
+def test_event_kernel_selection_and_gemm_statistics_layout(built_lib):
+    """Host-only entry points: which event kernel a sensor gets (one CTA + tensor-core passes when the bins fit one SM, rows
+    are 4-byte aligned and the resize up-samples; clusters otherwise) and how many statistics slots a residual GEMM writes."""
+    geo = {s: ops.event2img_geometry(s) for s in ((180, 240), (100, 120), (480, 640), (34, 34), (260, 346), (128, 128))}
+    assert geo[(180, 240)] == dict(cluster=1, threads=1024, smem=217952)        # bins 172 800 + gray plane (188 rows + 32, 16-byte rounded)
+    assert geo[(100, 120)]["cluster"] == 1 and geo[(100, 120)]["threads"] == 512 and geo[(100, 120)]["smem"] == 60992
+    assert geo[(480, 640)]["cluster"] == 8 and geo[(260, 346)]["cluster"] == 2
+    assert geo[(34, 34)]["cluster"] == 1 and geo[(128, 128)]["cluster"] == 1
+    for s, g in geo.items():
+        assert g["smem"] <= 227 * 1024 - 8 * 1024, (s, g)                       # leaves room for the kernels' static tables
+    with pytest.raises(_lib.ECError):
+        ops.event2img_geometry((4, 4))
+    assert [ops.gemm_stats_parts(n) for n in (768, 1024, 512, 384, 1280)] == [6, 8, 4, 6, 10]
 
 
 def _frames_np(frames):
