@@ -195,3 +195,41 @@ def test_classifier_construction_and_state_dict_names(golden_dir):
     p.model = "nope"
     with pytest.raises(NotImplementedError):
         build_model(p)
+
+
+def test_layernorm_folding_operands_reproduce_layernorm_plus_linear():
+    """pack_blocks_ln (host, pack time): with Wg = fp16(gamma * W_eff) row-centred and c = W_eff beta + b,
+    rstd * (x Wg^T) + c equals LayerNorm(x) W_eff^T + b -- also with non-zero LoRA factors merged (models/lora.py:138-149)."""
+    from eventclip_b200.models.lora import inject_trainable_lora
+    torch.manual_seed(3)
+    model = clip.CLIP("ViT-tiny/32")
+    with torch.no_grad():
+        for blk in model.visual.transformer.resblocks:
+            for ln in (blk.ln_1, blk.ln_2):
+                ln.weight.copy_(torch.rand_like(ln.weight) + 0.5)
+                ln.bias.copy_(torch.randn_like(ln.bias) * 0.2)
+    for with_lora in (False, True):
+        if with_lora:
+            inject_trainable_lora(model.visual, "qkvo-4")
+            with torch.no_grad():
+                for n, p in model.visual.named_parameters():
+                    if "lora_up" in n:
+                        p.copy_(torch.randn_like(p) * 0.05)
+        d = model.visual.width
+        packed = clip.pack_blocks_ln(model.visual.transformer.resblocks, d, torch.device("cpu"))
+        x = torch.randn(37, d) * 2 + 0.7
+        mean, var = x.mean(1, keepdim=True), x.var(1, unbiased=False, keepdim=True)
+        rstd = torch.rsqrt(var + 1e-5)
+        for blk, e in zip(model.visual.transformer.resblocks, packed):
+            W, lora_in, ib, _, _, _ = clip._attn_weights(blk.attn)
+            W = W.detach().float().clone()
+            if lora_in is not None:
+                for j, nme in enumerate("qkv"):
+                    W[j * d:(j + 1) * d] += getattr(lora_in, f"lora_up_{nme}").detach() @ getattr(lora_in, f"lora_down_{nme}").detach()
+            for name, Wf, bf_, ln in (("in", W, ib.detach(), blk.ln_1),
+                                      ("fc", blk.mlp.c_fc.weight.detach(), blk.mlp.c_fc.bias.detach(), blk.ln_2)):
+                want = torch.nn.functional.layer_norm(x, (d,), ln.weight, ln.bias, 1e-5) @ Wf.t() + bf_
+                got = rstd * (x @ e["wg_" + name].float().t()) + e["c_" + name]
+                assert e["wg_" + name].dtype == torch.float16
+                assert e["wg_" + name].float().sum(1).abs().max() < 2e-2                  # centred rows (up to fp16 rounding)
+                assert (got - want).norm() / want.norm() < 2e-3, (with_lora, name)
