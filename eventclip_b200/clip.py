@@ -136,6 +136,11 @@ def pack_blocks_ln(resblocks, d, dev):
         for name, Wf, bf_, ln in (("in", W, f32(ib), blk.ln_1), ("fc", f32(blk.mlp.c_fc.weight), f32(blk.mlp.c_fc.bias), blk.ln_2)):
             wg = Wf * f32(ln.weight)[None, :]
             wg = (wg - wg.mean(1, keepdim=True)).to(torch.float16).contiguous()
+            # the fp16 rounding leaves a row sum r_j != 0 that would multiply the row mean of x: fold it into the largest
+            # element of the row, so that |sum_k Wg[j,k]| drops to one rounding of that element
+            r = wg.to(torch.float32).sum(1)
+            kmax = wg.abs().argmax(1, keepdim=True)
+            wg.scatter_(1, kmax, (wg.gather(1, kmax).to(torch.float32) - r[:, None]).to(torch.float16))
             e["wg_" + name] = wg
             e["c_" + name] = (Wf @ f32(ln.bias) + bf_).contiguous()
         out.append(e)

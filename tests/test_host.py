@@ -231,5 +231,5 @@ def test_layernorm_folding_operands_reproduce_layernorm_plus_linear():
                 want = torch.nn.functional.layer_norm(x, (d,), ln.weight, ln.bias, 1e-5) @ Wf.t() + bf_
                 got = rstd * (x @ e["wg_" + name].float().t()) + e["c_" + name]
                 assert e["wg_" + name].dtype == torch.float16
-                assert e["wg_" + name].float().sum(1).abs().max() < 2e-2                  # centred rows (up to fp16 rounding)
+                assert e["wg_" + name].float().sum(1).abs().max() < 2e-3                  # centred rows (up to one fp16 rounding)
                 assert (got - want).norm() / want.norm() < 2e-3, (with_lora, name)
