@@ -8,6 +8,7 @@ tests or golden vectors of its own, so these files are the
   gray_lut.npz          datasets/vis.py:27-39 uint8 value for (pos, neg, max) grids, both background_mask settings
   event2img_small.npz   full stage-by-stage arrays for a small sensor (events, counts, frames, resized u8)
   event2img_sha.json    sha256 of every stage for the three real sensor shapes x {uniform, clustered, hotpixel}
+  event2img_shapes_sha.json  the same for five other sensor shapes x both flag settings x the three stream kinds
   heads_golden.npz      outputs of the reference ZS / FS / FT classifiers (models/clip_cls.py, clip_cls_ft.py,
                         adapter.py, lora.py) driven by the oracle CLIP image tower on seeded inputs
 """
@@ -139,6 +140,29 @@ def make_event2img(vis):
                              img=sha(tens)))
             print(ds, kind, frames.shape)
     json.dump(shas, open(os.path.join(HERE, "event2img_sha.json"), "w"), indent=1)
+
+
+OTHER_SHAPES = [((34, 34), 1500), ((128, 128), 5000), ((240, 180), 20000), ((64, 200), 6000), ((260, 346), 25000)]
+
+
+def make_event2img_shapes(vis):
+    """Sensors outside BASELINE.json's three (N-MNIST, DVS128, a portrait and a wide sensor, DAVIS346): per-stage checksums
+    of the reference pipeline, both flag settings, the three stream kinds -- pins the oracle (and through it every event
+    kernel variant) on shapes with other aspect ratios, crops on the other axis and W % 4 != 0."""
+    prep = clip_preprocess()
+    out = []
+    for shape, N in OTHER_SHAPES:
+        for cnz, bg in ((False, True), (True, False)):
+            for seed, kind in ((1, "uniform"), (2, "clustered"), (3, "hotpixel")):
+                ev = synth_events(shape, int(2.6 * N) + 7, seed, kind)
+                q = dict(N=N, grayscale=True, count_non_zero=cnz, background_mask=bg)
+                frames, u8, tens = ref_pipeline(vis, prep, ev, shape, q)
+                counts = ref_counts(vis, ev, shape, N)
+                out.append(dict(shape=list(shape), N=N, count_non_zero=cnz, background_mask=bg, seed=seed, kind=kind,
+                                E=int(len(ev)), K=int(frames.shape[0]), events=sha(ev), counts=sha(counts.astype(np.int32)),
+                                frames=sha(frames[..., 0]), u8=sha(u8), img=sha(tens)))
+    json.dump(out, open(os.path.join(HERE, "event2img_shapes_sha.json"), "w"), indent=1)
+    print("event2img shapes", len(out))
 
 
 def make_heads():
@@ -408,6 +432,7 @@ if __name__ == "__main__":
     make_split_cases(vis)
     make_gray_lut(vis)
     make_event2img(vis)
+    make_event2img_shapes(vis)
     make_heads()
     make_event_transforms()
     make_ft_train()

@@ -225,12 +225,19 @@ def test_center_and_flip_events_on_device(cuda_dev, golden_dir):
                                      ((64, 200), 6000),     # wide: both axes up-sampled, 175 columns cropped away
                                      ((260, 346), 25000)])  # DAVIS346: two-CTA cluster, W % 4 != 0
 @pytest.mark.parametrize("flags", [(False, True), (True, False)])
-def test_other_sensor_shapes_vs_oracle(cuda_dev, shape, N, flags):
-    """Sensors outside BASELINE.json's three: every kernel variant (tensor-core, SIMT, cluster) against the oracle."""
+def test_other_sensor_shapes_vs_oracle(cuda_dev, golden_dir, shape, N, flags):
+    """Sensors outside BASELINE.json's three: every kernel variant (tensor-core, SIMT, cluster) against the oracle stage by
+    stage, and the float32 tensor against the checksum of the UNMODIFIED reference's output (event2img_shapes_sha.json)."""
     cnz, bg = flags
+    gold = {(tuple(c["shape"]), c["count_non_zero"], c["seed"]): c
+            for c in json.load(open(os.path.join(golden_dir, "event2img_shapes_sha.json")))}
     for seed, kind in ((1, "uniform"), (2, "clustered"), (3, "hotpixel")):
         ev = synth_events(shape, int(2.6 * N) + 7, seed, kind)
         img, dbg, K = _run_frames(ev, shape, N, cnz, bg, cuda_dev)
+        c = gold[(tuple(shape), cnz, seed)]
+        assert sha(ev) == c["events"] and K == c["K"]
+        assert sha(img.cpu().numpy()) == c["img"] and sha(dbg["u8"].cpu().numpy()) == c["u8"], (shape, kind)
+        assert sha(dbg["counts"].cpu().numpy().astype(np.int32)) == c["counts"] and sha(dbg["gray"].cpu().numpy()) == c["frames"]
         i0, i1 = orc.split_event_count(len(ev), N)
         assert K == len(i0)
         img = img.cpu().numpy()

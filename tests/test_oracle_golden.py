@@ -80,6 +80,25 @@ def test_real_sensor_checksums(golden_dir, idx):
     assert sha(img) == c["img"]
 
 
+@pytest.mark.parametrize("idx", range(30))
+def test_other_sensor_shapes_checksums(golden_dir, idx):
+    """The oracle against the UNMODIFIED reference on five more sensor shapes (N-MNIST 34x34, DVS128, portrait 240x180, wide
+    64x200, DAVIS346 260x346): other aspect ratios, the crop on the other axis, W % 4 != 0; both flag settings."""
+    c = json.load(open(os.path.join(golden_dir, "event2img_shapes_sha.json")))[idx]
+    shape = tuple(c["shape"])
+    ev = synth_events(shape, c["E"], c["seed"], c["kind"])
+    assert sha(ev) == c["events"], "synthetic generator drifted from the one the goldens were made with"
+    i0, i1 = orc.split_event_count(len(ev), c["N"])
+    assert len(i0) == c["K"]
+    counts = np.stack([orc.histogram(ev[a:b], shape) for a, b in zip(i0, i1)])
+    assert sha(counts.astype(np.int32)) == c["counts"]
+    grays = np.stack([orc.frame_from_counts(k, c["count_non_zero"], c["background_mask"])[0] for k in counts])
+    assert sha(grays) == c["frames"]
+    u8 = np.stack([orc.resize_crop_224(g) for g in grays])
+    assert sha(u8) == c["u8"]
+    assert sha(np.stack([orc.normalize(u) for u in u8])) == c["img"]
+
+
 def test_event2img_sample_padding_and_selection():
     cfg = SENSORS["n_caltech101"]
     ev = synth_events(cfg["shape"], 50001, 3, "uniform")
