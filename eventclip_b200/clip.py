@@ -211,6 +211,9 @@ class VisionTransformer(nn.Module):
         # ln_1 / ln_2 folded into the in_proj / c_fc GEMMs (fp16 stream only); EC_LN_FOLD=0 keeps the LayerNorm kernels
         self.fold_ln = os.environ.get("EC_LN_FOLD", "1") != "0"
         self._packed_ln, self._packed_ln_key = None, None
+        # bumped by everything that rewrites parameters behind the version counters' back (the fused optimizer kernel of
+        # train.FineTuner writes through raw pointers): the LayerNorm-folded operands and captured graphs key on it
+        self._epoch = 0
 
     # -- weight packing -------------------------------------------------------------------------------------------
     @property
@@ -226,6 +229,13 @@ class VisionTransformer(nn.Module):
         """Call after mutating weights in a way the version counters cannot see (e.g. .data swaps)."""
         self._packed = None
         self._packed_ln = None
+        self._epoch += 1
+
+    def mark_weights_changed(self):
+        """Parameters were updated in place without touching their version counters (ec_adam on the flat buffer).  The
+        bf16 copies are rewritten by refresh_packed(); the LayerNorm-folded operands (merged LoRA q/k/v, gamma*W, W beta + b)
+        are recomputed -- into the same buffers -- by the next packed_ln() call, and GraphedClassifier captures again."""
+        self._epoch += 1
 
     def packed(self):
         """bf16 copies of the GEMM weights in the layout the kernels read (LoRA factors merged, models/lora.py:138-149).
@@ -256,7 +266,7 @@ class VisionTransformer(nn.Module):
 
     def packed_ln(self):
         """Operands of the LayerNorm-folded GEMMs, rebuilt when any parameter's version counter changes."""
-        key = self._version_key()
+        key = (self._version_key(), self._epoch)
         if self._packed_ln is None or key != self._packed_ln_key:
             new = pack_blocks_ln(self.transformer.resblocks, self.width, self.proj.device)
             if self._packed_ln is None:
@@ -317,7 +327,7 @@ class VisionTransformer(nn.Module):
     def forward_patches(self, patches, n_img):
         """patches: bf16 [n_img*G*G, k_patch] im2col rows (what ec_event2img's EC_OUT_BF16_PATCH writes).
         Returns fp32 [n_img, output_dim]."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             from . import train
             return train.encode_patches_autograd(self, patches, n_img)
         pk = self.packed()
@@ -488,7 +498,12 @@ def load(name, device="cuda", seed=0, state_dict=None, text=True):
     model = CLIP(name, text=text)
     init_weights_(model, seed)
     if state_dict is not None:
-        model.load_state_dict(state_dict, strict=False)
+        # openai-CLIP checkpoints carry non-parameter entries and (when text=False here) the text tower: those may be
+        # unexpected.  A MISSING key would silently leave seeded-random weights in place, so it is an error.
+        res = model.load_state_dict(state_dict, strict=False)
+        if res.missing_keys:
+            raise L.ECError("clip.load: checkpoint lacks %d parameter(s) of %s, e.g. %s"
+                            % (len(res.missing_keys), name, ", ".join(res.missing_keys[:4])))
     return model.to(device).eval(), _transform(224)
 
 

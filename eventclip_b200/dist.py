@@ -30,8 +30,12 @@ class AccuracyMeter:
 
     def __init__(self, device="cpu"):
         self.counters = torch.zeros(6, dtype=torch.int64, device=device)
+        self._status = []
 
     def update(self, out_dict, labels):
+        st = out_dict.get("status")
+        if st is not None and not any(st is s for s in self._status):
+            self._status.append(st)          # device status words of the event kernel: read (once) when the meter reports
         labels = labels.to(out_dict["logits"].device).long()
         B = labels.shape[0]
         if "top5_logits" in out_dict:
@@ -49,12 +53,20 @@ class AccuracyMeter:
         self.counters += upd
 
     def all_reduce(self):
-        """The one collective of the inference path."""
+        """The one collective of the inference path.  Before it, the event kernel's status words are checked: bad event
+        coordinates raise ValueError here, as numpy does inside the reference's data loader (datasets/vis.py:9-14)."""
+        self.check_status()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.counters, op=dist.ReduceOp.SUM)
         return self
 
+    def check_status(self):
+        from . import ops
+        for st in self._status:
+            ops.raise_on_status(st)
+
     def result(self):
+        self.check_status()
         c = self.counters.tolist()
         n = max(c[0], 1)
         return dict(n=c[0], probs_acc=c[1] / n, logits_acc=c[2] / n, probs_acc5=c[3] / n, logits_acc5=c[4] / n,
@@ -107,6 +119,13 @@ class FlatParams:
                 off += k
             self.spans.append((lo, off))
         self.numel = n
+
+    def broadcast(self, group=None, src=0):
+        """Every rank takes rank `src`'s parameters (DDP's construction-time broadcast); no-op without a process group."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            gsrc = dist.get_global_rank(group, src) if group is not None else src
+            dist.broadcast(self.flat_p, src=gsrc, group=group)
+        return self.flat_p
 
     def grad_view(self, p):
         off, k, shape = self._where[id(p)]

@@ -69,7 +69,9 @@ class GraphedClassifier:
     def _signature(self):
         """Changes whenever a parameter is updated in place or replaced (optimizer step, load_state_dict): the captured
         graphs read packed copies of the weights whose buffers are re-created then, so they must be captured again."""
-        return sum(p._version for p in self._params) + sum(p.data_ptr() for p in self._params[:1])
+        vis = getattr(getattr(self.model, "model", None), "visual", None)
+        return (sum(p._version for p in self._params) + sum(p.data_ptr() for p in self._params[:1]),
+                getattr(vis, "_epoch", 0))      # _epoch: in-place updates the version counters cannot see (train.FineTuner)
 
     def _build(self, plan):
         e = _Entry()
@@ -116,6 +118,11 @@ class GraphedClassifier:
         L.LAUNCHES += ent.n_launch
         return ent.out
 
+    def check_status(self):
+        """Synchronising read of the event kernel's status word (sticky across replays): raises ValueError for event
+        coordinates outside the sensor, as the reference's numpy path does (datasets/vis.py:9-14)."""
+        from . import ops
+        ops.raise_on_status(self.status)
 
     def stream(self, batches, result=None, pre=None):
         """Pipelined serving loop over an iterable of data_dicts with PINNED HOST events -- the role the reference's
@@ -134,6 +141,14 @@ class GraphedClassifier:
         cur = torch.cuda.current_stream(dev)
         done = [torch.cuda.Event() for _ in range(2)]
         host_res = [None, None]
+        host_st = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(2)]   # status word rides with the result
+
+        def finish(j):
+            done[j].synchronize()
+            if int(host_st[j][0]) != 0:
+                from . import ops
+                ops.raise_on_status(host_st[j])
+            return host_res[j].clone()
 
         def upload(i, d):
             ev = d["events"]
@@ -162,6 +177,7 @@ class GraphedClassifier:
             if host_res[i % 2] is None or host_res[i % 2].shape != r.shape or host_res[i % 2].dtype != r.dtype:
                 host_res[i % 2] = torch.empty(r.shape, dtype=r.dtype).pin_memory()
             host_res[i % 2].copy_(r, non_blocking=True)
+            host_st[i % 2].copy_(self.status, non_blocking=True)
             done[i % 2].record(cur)
 
         it = iter(batches)
@@ -176,11 +192,9 @@ class GraphedClassifier:
                 upload(i + 1, nxt)                                    # in flight while batch i computes
             launch(i, d)
             if i >= 1:
-                done[(i - 1) % 2].synchronize()
-                yield host_res[(i - 1) % 2].clone()
+                yield finish((i - 1) % 2)
             i += 1
-        done[(i - 1) % 2].synchronize()
-        yield host_res[(i - 1) % 2].clone()
+        yield finish((i - 1) % 2)
 
 
 class GraphedFineTuner:

@@ -129,9 +129,19 @@ class _CLIPClassifierBase(nn.Module):
         patches, st, _ = ops.event2img(events, plan["frames"], fe.resolution, plan["n_valid"], fe.count_non_zero,
                                        fe.background_mask, out="patch", patch=visual.patch_size, ldk=visual.k_patch,
                                        status=status)
-        self._last_status = st
+        self._last_status, self._last_patches = st, patches     # kept for status checks / parity checks of the frames
         feats = visual.forward_patches(patches, plan["n_valid"])
-        return self._head(feats, plan)
+        out = self._head(feats, plan)
+        out["status"] = st          # device status word of the event kernel (EC_STATUS_*); see check_status()
+        return out
+
+    def check_status(self):
+        """The reference's numpy path raises ValueError on coordinates outside the sensor (datasets/vis.py:9-14).  The fused
+        route only sets a bit in a device word; this reads it (synchronising) and raises the same exception.  Called by
+        dist.AccuracyMeter before it reports, by GraphedClassifier.stream() with every batch it reads back, or at will."""
+        st = getattr(self, "_last_status", None)
+        if st is not None:
+            ops.raise_on_status(st)
 
     def _head(self, feats, plan):
         B, T = plan["B"], plan["T"]
@@ -332,8 +342,10 @@ class FTCLIPClassifier(_AdaptedClassifier):
         patches, st, _ = ops.event2img(events, plan["frames"], fe.resolution, plan["n_valid"], fe.count_non_zero,
                                        fe.background_mask, out="patch", patch=visual.patch_size, ldk=visual.k_patch,
                                        status=status)
-        self._last_status = st
-        return self._head(visual.forward_patches(patches, plan["n_valid"]), plan)
+        self._last_status, self._last_patches = st, patches
+        out = self._head(visual.forward_patches(patches, plan["n_valid"]), plan)
+        out["status"] = st
+        return out
 
     def _head(self, feats, plan):
         if not self._training_active():

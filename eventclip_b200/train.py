@@ -354,6 +354,10 @@ class FineTuner:
         from .dist import FlatParams
         self.flat = FlatParams([self.group0, self.group1])
         self.flat_p, self.flat_g = self.flat.flat_p, self.flat.flat_g
+        # What DDP does at construction (the reference trains under nerv's DDP wrapper): every rank starts from rank 0's
+        # parameters.  LoRA `lora_down` is drawn from the global RNG at injection, so ranks seeded differently would
+        # otherwise average gradients of different weights and stay diverged.
+        self.flat.broadcast(self.pg)
         self.m, self.v = torch.zeros_like(self.flat_g), torch.zeros_like(self.flat_g)
         self.vis.invalidate_packed()
         self.t = 0
@@ -396,6 +400,9 @@ class FineTuner:
         for (lo, hi), rate in zip(self.flat.spans, (lr, clip_lr)):
             if hi > lo:
                 ops.adam(self.flat_p[lo:hi], self.flat_g[lo:hi], self.m[lo:hi], self.v[lo:hi], rate, self.t, self.betas, self.eps)
+        # ec_adam writes through raw pointers: version counters do not move, so tell the tower (LayerNorm-folded operands,
+        # captured inference graphs) that its weights changed
+        self.vis.mark_weights_changed()
         if refresh:
             self.refresh_weights()
 
@@ -408,3 +415,10 @@ class FineTuner:
         self.allreduce()
         self.optimizer_step(lr, clip_lr)
         return loss
+
+    def check_status(self):
+        """Raises what the reference's numpy path raises for the events of the last step (ValueError for coordinates
+        outside the sensor, datasets/vis.py:9-14).  Synchronises on the status word; call it once per epoch / at will."""
+        st = self.last.get("status")
+        if st is not None:
+            ops.raise_on_status(st)
