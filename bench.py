@@ -29,6 +29,7 @@ One JSON line on stdout (rank 0):
              their own parity check; under torchrun C4 and the C5 fine-tune step (gradient all-reduce) run at every N
 """
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -398,22 +399,23 @@ class Workload:
                                           cfg["background_mask"], out="patch", patch=vis.patch_size, ldk=vis.k_patch)
             feats = vis.forward_patches(patches, nv).float().cpu()
         first = torch.from_numpy(np.concatenate([[0], np.cumsum(valid.sum(1).numpy())[:-1]]))     # first view of every sample
-        self.text = calibrate_text_feats(feats[first], cfg["n_cls"], labels=None if cfg["n_cls"] == 2 else labc[:nc])
+        self.text = calibrate_text_feats(feats[first], cfg["n_cls"])
         del patches, feats
         cd = dict(clip_model=self.model, prompt="a point cloud image of a {}", class_names=None, agg_func="mean",
                   text_feats=self.text)
-        if c["kind"] == "zs":
-            m = ZSCLIPClassifier(clip_dict=cd)
-        elif c["kind"] == "fs":
-            ad = dict(adapter_type="text-trans", in_dim=self.C, d_model=256, num_heads=4, ffn_dim=1024, norm_first=True,
-                      num_layers=2, residual=0.95)
-            torch.manual_seed(3)
-            m = FSCLIPClassifier(adapter_dict=ad, clip_dict=cd, loss_dict=dict(use_logits_loss=True, use_probs_loss=False))
-        else:
-            cd.update(lora="qkvo-16", only_conv1=False, only_bias=False, only_ln=False)
-            torch.manual_seed(0)                                     # LoRA lora_down draws from the global RNG
-            m = FTCLIPClassifier(adapter_dict=dict(adapter_type="text-identity", residual=True), clip_dict=cd,
-                                 loss_dict=dict(use_logits_loss=True, use_probs_loss=False))
+        with contextlib.redirect_stdout(sys.stderr):                 # the classifiers print like the reference's do; stdout carries
+            if c["kind"] == "zs":                                    # the one JSON line only
+                m = ZSCLIPClassifier(clip_dict=cd)
+            elif c["kind"] == "fs":
+                ad = dict(adapter_type="text-trans", in_dim=self.C, d_model=256, num_heads=4, ffn_dim=1024, norm_first=True,
+                          num_layers=2, residual=0.95)
+                torch.manual_seed(3)
+                m = FSCLIPClassifier(adapter_dict=ad, clip_dict=cd, loss_dict=dict(use_logits_loss=True, use_probs_loss=False))
+            else:
+                cd.update(lora="qkvo-16", only_conv1=False, only_bias=False, only_ln=False)
+                torch.manual_seed(0)                                 # LoRA lora_down draws from the global RNG
+                m = FTCLIPClassifier(adapter_dict=dict(adapter_type="text-identity", residual=True), clip_dict=cd,
+                                     loss_dict=dict(use_logits_loss=True, use_probs_loss=False))
         self.cls = m.to(dev)
         self.cls = self.cls.train() if c["kind"] == "ft" else self.cls.eval()
         self.cls.attach_event_frontend(q, cfg["shape"], cfg["max_n"])

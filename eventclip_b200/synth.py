@@ -87,7 +87,8 @@ def calibrate_text_feats(feats, n_cls, labels=None):
       labels given : t_c = normalise(P (mean of class c - mean of the class means))
       n_cls == 2   : t_0 = -t_1 = first principal direction of P (f - m), tilted along m so that the median calibration
                      sample sits on the decision boundary (an even split)
-      otherwise    : t_c = normalise(P (f_c - m)) for the first min(n_cls, n) calibration samples (prototypes)
+      otherwise    : t_2k = +v_k, t_2k+1 = -v_k for the principal directions v_k of P (f - m), strongest first (as many as
+                     the calibration batch supports): the logits then spread like the features themselves do
     Classes without data get a seeded Gaussian direction projected the same way.  feats: float [n, C] on any device.
     Returns float32 [n_cls, C] on the CPU, rows L2-normalised (what clip_cls.py:84-85 caches)."""
     import torch
@@ -114,8 +115,11 @@ def calibrate_text_feats(feats, n_cls, labels=None):
         t1 = t1 / t1.norm()
         return torch.stack([-t1, t1]).float()
     if labels is None:
-        k = min(n_cls, n)
-        proto[:k], have[:k] = f[:k], True
+        U, S, V = torch.linalg.svd(d, full_matrices=False)
+        k = min(n_cls // 2, int((S > 1e-9 * S[0]).sum()))
+        for j in range(k):
+            proto[2 * j], proto[2 * j + 1] = mid + V[j], mid - V[j]
+        have[:2 * k] = True
     spread = d.norm(dim=1).mean()
     for c in range(n_cls):
         if not have[c]:

@@ -7,6 +7,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+if os.path.join(ROOT, "tests") not in sys.path:
+    sys.path.insert(0, os.path.join(ROOT, "tests"))      # parity_util.py (shared helpers of the GPU tests)
 
 
 def pytest_configure(config):
@@ -33,3 +35,4 @@ def cuda_dev(built_lib):
     if not torch.cuda.is_available():
         pytest.fail("a -m gpu test was selected but no CUDA device is visible; there is no CPU fallback")
     return torch.device("cuda", 0)
+

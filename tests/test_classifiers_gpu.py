@@ -188,6 +188,12 @@ def test_events_to_logits_vs_oracle(cuda_dev, ds, arch, B):
     ref = heads_oracle.zs_head(feats, valid, text, 100.0, "mean")
     assert torch.equal(o["valid_masks"].cpu(), valid)
     assert rel(o["logits"], ref["logits"]) < 2e-2, rel(o["logits"], ref["logits"])
+    # the same error against the part of the logits that differs between samples (batch mean removed)
+    from parity_util import record_metric, rel_l2_centered
+    cen = rel_l2_centered(o["logits"], ref["logits"])
+    record_metric("events_to_logits_vs_oracle", ds=ds, arch=arch, B=B, rel_l2=rel(o["logits"], ref["logits"]), rel_l2_centered=cen)
+    if B >= 4:
+        assert cen < 0.25, cen
     assert np.abs(o["probs"].cpu().numpy() - ref["probs"].numpy()).max() < 5e-2
     _assert_top1(o["logits"], ref["logits"])
     with torch.no_grad():

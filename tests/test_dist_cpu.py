@@ -121,3 +121,38 @@ def test_flat_gradient_allreduce_two_ranks():
             assert torch.allclose(got_p[i], params[i] - 0.1 * mean, atol=1e-6)
     for a, b in zip(res[0][3], res[1][3]):                 # both ranks end with identical parameters
         assert torch.equal(a, b)
+
+
+def _bcast_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from eventclip_b200.dist import FlatParams
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(50 + rank)           # DIFFERENT initial parameters per rank (LoRA lora_down is drawn
+    params = [torch.nn.Parameter(torch.randn(s, generator=g)) for s in ((5, 8), (3,))]   # from the global RNG at injection)
+    flat = FlatParams([params[:1], params[1:]])
+    flat.broadcast()                                       # what DDP does at construction; train.FineTuner calls it
+    q.put((rank, [p.detach().clone() for p in params]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_params_broadcast_rank0_two_ranks():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bcast_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(50)
+    want = [torch.randn(s, generator=g) for s in ((5, 8), (3,))]
+    for rank, got in res:
+        for a, b in zip(got, want):
+            assert torch.equal(a, b), rank                 # every rank holds rank 0's draw

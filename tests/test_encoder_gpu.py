@@ -185,6 +185,9 @@ def test_encoder_vs_oracle(cuda_dev, arch, n):
         got_bf = model.encode_image(imgs.to(cuda_dev).to(torch.bfloat16))
     assert got.shape == ref.shape and got.dtype == torch.float32
     assert rel(got, ref) < 2e-2, rel(got, ref)
+    from parity_util import record_metric, rel_l2_centered
+    record_metric("encoder_vs_oracle", arch=arch, rel_l2=rel(got, ref), rel_l2_centered=rel_l2_centered(got, ref))
+    assert rel_l2_centered(got, ref) < 5e-2, rel_l2_centered(got, ref)      # error against the input-dependent part only
     assert rel(got_bf, ref) < 2e-2
     # weight updates are picked up (version counters) -- optimizer steps / load_state_dict must not see stale packs
     with torch.no_grad():
