@@ -25,6 +25,7 @@
 #include <vector>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -62,6 +63,10 @@ struct E2IParams {
     // (checked on the host when the tables are built); affine = 0 falls back to the LUT
     float na[3], nb[3];
     int affine;
+    // band-exchange cluster kernel (event2img_big_kernel): byte offsets of its regions in dynamic shared memory, pitches of the
+    // gray plane / the transposed horizontal result, events per CTA and exchange round, multiply-shift constant of y / RB
+    int big_off_b, big_off_ht, big_gp, big_hpb, big_cap;
+    unsigned big_rb_magic;
 };
 
 struct Part {            // per-CTA partial statistics exchanged over DSMEM
@@ -1118,6 +1123,666 @@ __global__ void __launch_bounds__(1024, 1) event2img_tc_kernel(const E2IParams p
     }   // frame loop
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Band-exchange cluster kernel: sensors whose bins do not fit one SM (N-ImageNet 480x640: 1.2 MB of packed bins).
+//
+// A cluster of CS CTAs owns a frame; CTA `rank` owns the bins of a band of RB sensor rows.  Only LOCAL shared-memory atomics
+// touch the bins.  Per frame (and per round of at most CS * cap events):
+//   S1  every CTA reads 1 / CS of the events once (16-byte loads), decodes them, and counting-sorts them BY OWNER BAND into a
+//       word list in its own shared memory: word = bin index inside the owner's band | polarity << 16.  The events of a
+//       round live in registers between the counting pass (one shared-memory atomic per event on a per-warp, per-owner
+//       counter, which also yields the event's slot) and the placement pass.
+//   S2  every CTA PULLS its segment of each peer's list through distributed shared memory (coalesced 4-byte loads, four in
+//       flight per lane) and histograms it with returning local atomics; the returned counts give the exact statistics on the
+//       fly: sum of squares, largest count, and how many fields reached 1, 2, ... 8 events -- from which the largest
+//       surviving count after the hot-pixel cut follows without another pass over the bins whenever the cut is <= 7.
+//   P2  one cluster exchange of the partial statistics -> cut, maximum, per-frame gray LUT
+//   P4  gray byte per pixel into a padded plane (over the dead word list)
+//   P5  horizontal Pillow pass on the tensor cores (two 32-pixel source windows per 16 outputs), band rows -> hT band
+//   P6  vertical pass on the tensor cores: (16 output rows x 32 columns) units spread over all warps of the cluster, source
+//       rows fetched from the owners' hT bands through distributed shared memory, normalise + store from registers
+// Three cluster barriers per frame; the bins are cleared for the next frame by warps that carry no matrix work.
+// A 16-bit field that wraps (>= 65536 events of one polarity on one pixel) marks its pixel as suspect: those pixels (at most
+// eight per band) are recounted exactly in 32 bits and the statistics are recomputed from the bins -- a rare path that
+// keeps the result identical to the reference's int64 histogram (datasets/vis.py:9-14).
+// ------------------------------------------------------------------------------------------------
+constexpr int BIG_NT = 1024;
+constexpr int BIG_KMAX = 10;                        // events per thread and round (kept in registers between the two S1 passes)
+constexpr int BIG_CAP = BIG_NT * BIG_KMAX;          // events per CTA and round
+constexpr int BIG_SUS = 8;                          // suspect pixels per band
+
+struct BigPart {                 // per-CTA partial statistics exchanged over DSMEM
+    unsigned long long s2;       // sum of squared counts
+    unsigned ge[8];              // ge[v-1] = fields whose count reached v (v = 1 .. 8)
+    unsigned nacc, mall, flags, nsus, mx, pad;
+};
+
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n)      // PTX shl: amounts >= 32 give 0
+{
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
+    return r;
+}
+__device__ __forceinline__ uint32_t map_cluster(uint32_t saddr, int cta)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ uint32_t ld_cluster_u32(uint32_t caddr)
+{
+    uint32_t r;
+    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(r) : "r"(caddr) : "memory");
+    return r;
+}
+__device__ __forceinline__ void imma_s8u8_acc(int (&d)[4], const uint4 &a, uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                 : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+
+// one event of the frame as (flat bin index, polarity 0 none / 1 positive / 2 negative); false = not histogrammed
+template <bool COMPACT>
+__device__ __forceinline__ bool decode_event(const E2IParams &p, long long e, long long HW, unsigned &l, unsigned &pol, unsigned &flags)
+{
+    if (COMPACT) {
+        const uint32_t w = ld_stream_u32(p.events_c + e);
+        const unsigned pc = w >> 30;
+        l = w & 0x3fffffffu;
+        pol = pc == 1u ? 1u : (pc == 2u ? 2u : 0u);
+        if (pc == 3u || (pc != 0u && (long long)l >= HW)) { flags |= EC_STATUS_BAD_COORD; return false; }
+        return pol != 0u;
+    }
+    const float4 ev = ld_stream(p.events + e);
+    const int xs = __float2int_rz(ev.x), ys = __float2int_rz(ev.y);
+    pol = ev.w >= 1.0f ? 1u : (ev.w <= -1.0f ? 2u : 0u);
+    if (pol == 0u) return false;                 // p == 0 (or NaN): never indexed by the reference
+    const long long i64 = (long long)xs + (long long)ys * p.W;
+    if (i64 < 0 || i64 >= HW) { flags |= EC_STATUS_BAD_COORD; return false; }
+    l = (unsigned)i64;
+    return true;
+}
+
+template <bool DBG, bool COMPACT>
+__global__ void __launch_bounds__(BIG_NT, 1) event2img_big_kernel(const E2IParams p)
+{
+    cg::cluster_group cluster = cg::this_cluster();
+    constexpr int NT = BIG_NT, NW = BIG_NT / 32, MT = OUT / 16;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int g = lane >> 2, tig = lane & 3;
+    const int CS = p.CS;
+    const int rank = blockIdx.x % CS;
+    const int n_clusters = gridDim.x / CS;
+    const int H = p.H, W = p.W, RB = p.RB, GP = p.big_gp, HPB = p.big_hpb;
+    const int y0 = rank * RB;
+    const int rows = max(0, min(H, y0 + RB) - y0);
+    const int nband = rows * W;
+    const unsigned bandpx = (unsigned)(RB * W);
+    const long long band_lo = (long long)y0 * W;
+    const long long HW = (long long)H * W;
+    const bool mask = (p.flags & EC_FLAG_BACKGROUND_MASK) != 0;
+    const bool cnz = (p.flags & EC_FLAG_COUNT_NON_ZERO) != 0;
+    const int W4 = W >> 2;
+    const int n16 = (RB * W) >> 2;                      // 16-byte groups of the bins (RB * W is a multiple of 4)
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *bins = reinterpret_cast<uint32_t *>(smem_raw);
+    uint8_t *gray = smem_raw + p.big_off_b;             // [RB rounded up to 8][GP], over the dead word list
+    uint32_t *sorted = reinterpret_cast<uint32_t *>(smem_raw + p.big_off_b);
+    uint8_t *hT = smem_raw + p.big_off_ht;              // [224][HPB]: the band's rows of the horizontal result, transposed
+    __shared__ BigPart part;
+    __shared__ uint32_t s_seg[16];                      // (first word, words) of this CTA's list for each owner band
+    __shared__ uint32_t s_cnt[NW * 8], s_base[NW * 8], s_tot[8];
+    __shared__ unsigned long long red64[NW];
+    __shared__ unsigned red32[NW][12];
+    __shared__ unsigned s_keep, s_mx, s_mall, s_need_pass, s_nsus_tot, s_nacc;
+    __shared__ unsigned s_sus[BIG_SUS], s_nsus, s_exact[BIG_SUS][2];
+    __shared__ uint8_t glut[GLUT_N * GLUT_N];
+    __shared__ uint2 nlut3[256];
+    __shared__ int rowoff[OUT], coloff[OUT / 2];
+    __shared__ int s_ws[2 * MT];
+
+    const uint32_t bins_s = (uint32_t)__cvta_generic_to_shared(bins);
+    const uint32_t sorted_s = (uint32_t)__cvta_generic_to_shared(sorted);
+    const uint32_t hT_s = (uint32_t)__cvta_generic_to_shared(hT);
+    const uint32_t seg_s = (uint32_t)__cvta_generic_to_shared(s_seg);
+    const bool wide = p.out_fmt != EC_OUT_BF16_PATCH || (p.patch % 8) == 0;
+    const int cstride = p.out_fmt == EC_OUT_BF16_PATCH ? p.patch * p.patch : OUT * OUT;
+    const int frame_elems = p.out_fmt == EC_OUT_BF16_PATCH ? p.G * p.G * p.ldk : 3 * OUT * OUT;
+
+    for (int i = tid; i < 256; i += NT) {
+        const __nv_bfloat162 c01 = __floats2bfloat162_rn(p.nlut[i], p.nlut[256 + i]);
+        const __nv_bfloat162 c2z = __floats2bfloat162_rn(p.nlut[512 + i], 0.f);
+        nlut3[i] = make_uint2(*reinterpret_cast<const uint32_t *>(&c01), *reinterpret_cast<const uint32_t *>(&c2z));
+    }
+    {
+        const int cw = wide ? 8 : 2;
+        for (int i = tid; i < OUT; i += NT)
+            rowoff[i] = p.out_fmt == EC_OUT_BF16_PATCH ? (i / p.patch) * p.G * p.ldk + (i % p.patch) * p.patch : i * OUT;
+        for (int i = tid; i < OUT / cw; i += NT)
+            coloff[i] = p.out_fmt == EC_OUT_BF16_PATCH ? ((i * cw) / p.patch) * p.ldk + (i * cw) % p.patch : i * cw;
+        for (int i = tid; i < 2 * MT; i += NT) s_ws[i] = i < MT ? p.wsH[i] : p.wsV[i - MT];
+        uint4 *b4 = reinterpret_cast<uint4 *>(bins);
+        for (int i = tid; i < n16; i += NT) b4[i] = make_uint4(0, 0, 0, 0);
+    }
+    cluster.sync();        // every CTA of the cluster runs before anyone touches a peer's shared memory
+
+    // block reduction of the per-thread statistics into `part`
+    auto publish = [&](unsigned long long s2, unsigned (&ge)[8], unsigned mall, unsigned flags) {
+        s2 = warp_sum_u64(s2);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) ge[v] = warp_sum_u32(ge[v]);
+        mall = warp_max_u32(mall);
+        flags = __reduce_or_sync(0xffffffffu, flags);
+        if (lane == 0) {
+            red64[wid] = s2;
+#pragma unroll
+            for (int v = 0; v < 8; ++v) red32[wid][v] = ge[v];
+            red32[wid][8] = mall; red32[wid][9] = flags;
+        }
+        __syncthreads();
+        if (tid < 8) { unsigned a = 0; for (int w = 0; w < NW; ++w) a += red32[w][tid]; part.ge[tid] = a; }
+        else if (tid == 8) { unsigned a = 0; for (int w = 0; w < NW; ++w) a = max(a, red32[w][8]); part.mall = a; }
+        else if (tid == 9) { unsigned a = 0; for (int w = 0; w < NW; ++w) a |= red32[w][9]; part.flags = a; }
+        else if (tid == 10) { unsigned long long a = 0; for (int w = 0; w < NW; ++w) a += red64[w]; part.s2 = a; }
+        else if (tid == 11) { part.nacc = s_nacc; part.nsus = s_nsus; }
+    };
+    // cluster totals -> hot-pixel cut, largest surviving count (or the request for a pass over the bins)
+    auto derive = [&]() {
+        if (tid == 0) {
+            unsigned long long S1 = 0, S2 = 0;
+            unsigned long long GE[9];
+            for (int v = 0; v < 9; ++v) GE[v] = 0;
+            unsigned M = 0, fl = 0, ns = 0;
+            for (int r = 0; r < CS; ++r) {
+                const BigPart *q = cluster.map_shared_rank(&part, r);
+                S1 += q->nacc; S2 += q->s2; M = max(M, q->mall); fl |= q->flags; ns += q->nsus;
+                for (int v = 0; v < 8; ++v) GE[v] += q->ge[v];
+            }
+            const unsigned long long n = cnz ? GE[0] : (unsigned long long)HW * 2ull;
+            const unsigned keep = compute_keep_small(n, S1, S2, 10);
+            unsigned mx = M, need = 0;
+            if (M > keep) {
+                if (keep <= 7u) {
+                    mx = 0;
+                    for (int v = (int)keep; v >= 1; --v)
+                        if (GE[v - 1] > GE[v]) { mx = (unsigned)v; break; }      // some field ended at exactly v
+                } else
+                    need = 1;
+            }
+            s_keep = keep; s_mall = M; s_mx = mx; s_need_pass = need; s_nsus_tot = ns;
+            if (rank == 0 && fl) atomicOr(p.status, (int)fl);
+        }
+        __syncthreads();
+    };
+
+    for (int fid = blockIdx.x / CS; fid < p.n_frames; fid += n_clusters) {
+        const ec_frame fr = p.frames[fid];
+        const int slot = fr.out_slot;
+        // ---- padding frame: the reference pads missing views with zeros (event2img.py:89-91) ----
+        if (fr.ev_count <= 0) {
+            if (p.out_fmt == EC_OUT_BF16_PATCH) {
+                const int G = p.G, cols = 3 * p.patch * p.patch;
+                for (int r = rank; r < G * G; r += CS) {
+                    __nv_bfloat16 *o = (__nv_bfloat16 *)p.out + ((size_t)slot * G * G + r) * p.ldk;
+                    for (int c = tid; c < cols; c += NT) o[c] = __float2bfloat16(0.f);
+                }
+            } else {
+                const size_t n = (size_t)3 * OUT * OUT;
+                const size_t b = n * rank / CS, e = n * (rank + 1) / CS;
+                if (p.out_fmt == EC_OUT_F32_NCHW) {
+                    float *o = (float *)p.out + (size_t)slot * n;
+                    for (size_t i = b + tid; i < e; i += NT) o[i] = 0.f;
+                } else {
+                    __nv_bfloat16 *o = (__nv_bfloat16 *)p.out + (size_t)slot * n;
+                    for (size_t i = b + tid; i < e; i += NT) o[i] = __float2bfloat16(0.f);
+                }
+            }
+            continue;     // uniform across the cluster
+        }
+
+        unsigned long long acc_s2 = 0;
+        unsigned ge32[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        unsigned mall = 0, flags = 0;
+        if (tid == 0) { s_nsus = 0; s_nacc = 0; }
+        const int EC = fr.ev_count;
+        const int round_cap = CS * p.big_cap;
+        for (int rb = 0; rb < EC; rb += round_cap) {
+            const int n_round = min(round_cap, EC - rb);
+            const int per = (n_round + CS - 1) / CS;                 // <= big_cap
+            const int e_lo = min(rank * per, n_round);
+            const int n = min(per, n_round - e_lo);
+            // ================= S1: decode this CTA's slice, count by owner, sort into the word list =================
+            if (tid < NW * 8) s_cnt[tid] = 0;
+            __syncthreads();
+            const int pw = ((((n + 31) >> 5) + 31) >> 5) << 5;       // events per warp: a multiple of 32, <= 32 * KMAX
+            const int w_lo = wid * pw;
+            const int w_n = max(0, min(pw, n - w_lo));
+            const long long e0 = fr.ev_start + rb + e_lo + w_lo + lane;
+            uint32_t pk[BIG_KMAX];     // local bin (16) | negative << 16 | owner << 17 | slot within (warp, owner) << 20 | valid << 31
+#pragma unroll
+            for (int k0 = 0; k0 < BIG_KMAX; k0 += 5) {
+                float4 ev[5];
+                uint32_t wc[5];
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const int i = 32 * (k0 + j) + lane;
+                    ev[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    wc[j] = 0;
+                    if (i < w_n) {
+                        if (COMPACT) wc[j] = ld_stream_u32(p.events_c + e0 + 32 * (k0 + j));
+                        else ev[j] = ld_stream(p.events + e0 + 32 * (k0 + j));
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const int k = k0 + j;
+                    pk[k] = 0;
+                    if (32 * k < w_n) {                               // warp-uniform
+                        unsigned l, neg;
+                        bool take;
+                        if (COMPACT) {
+                            const unsigned pc = wc[j] >> 30;
+                            l = wc[j] & 0x3fffffffu;
+                            neg = pc == 2u;
+                            take = (pc == 1u || pc == 2u) && (long long)l < HW;
+                            if (pc == 3u || (pc != 0u && !take)) flags |= EC_STATUS_BAD_COORD;
+                        } else {
+                            // .astype(int) truncates: trunc(p) != 0 <=> |p| >= 1 (vis.py:44-52); a NaN polarity is dropped like p == 0
+                            const int xs = __float2int_rz(ev[j].x), ys = __float2int_rz(ev[j].y);
+                            const bool pos = ev[j].w >= 1.0f;
+                            neg = ev[j].w <= -1.0f;
+                            l = (unsigned)(ys * W + xs);              // flat index as np.bincount sees it; exact in 32 bits for x, y, W < 2^15
+                            bool ok = (unsigned)(xs | ys) < 32768u && (long long)l < HW;
+                            if (!ok) {                                // rare: negative / huge coordinates whose flat index may still be in range
+                                const long long i64 = (long long)xs + (long long)ys * W;
+                                ok = i64 >= 0 && i64 < HW;
+                                l = (unsigned)i64;
+                            }
+                            take = ok && (pos || neg);
+                            if (!ok && (pos || neg)) flags |= EC_STATUS_BAD_COORD;    // p == 0 events are never range-checked
+                        }
+                        if (take && 32 * k + lane < w_n) {
+                            const unsigned owner = (unsigned)(((unsigned long long)l * p.band_magic) >> 40);   // l / (RB * W)
+                            const unsigned local = l - owner * bandpx;
+                            const unsigned pos_in = atomicAdd(&s_cnt[wid * 8 + owner], 1u);
+                            pk[k] = local | (neg << 16) | (owner << 17) | (pos_in << 20) | 0x80000000u;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid < 256) {           // warp o scans the counters of owner o over the 32 producer warps
+                const int o = tid >> 5;
+                const unsigned v = s_cnt[lane * 8 + o];
+                unsigned incl = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                s_base[lane * 8 + o] = incl - v;
+                if (lane == 31) s_tot[o] = incl;
+            }
+            __syncthreads();
+            if (tid < 256) {
+                const int o = tid >> 5;
+                unsigned start = 0;
+                for (int q = 0; q < o; ++q) start += s_tot[q];
+                s_base[lane * 8 + o] += start;
+                if (lane == 0) { s_seg[2 * o] = start; s_seg[2 * o + 1] = s_tot[o]; }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < BIG_KMAX; ++k)
+                if (pk[k] & 0x80000000u)
+                    sorted[s_base[wid * 8 + ((pk[k] >> 17) & 7u)] + ((pk[k] >> 20) & 0x7ffu)] = pk[k] & 0x1ffffu;
+            cluster.sync();            // every list and segment table of the cluster is complete
+
+            // ================= S2: pull this band's segments, local returning atomics, statistics on the fly =================
+            {
+                const int wps = NW / CS;                              // warps per source CTA
+                const int src = (rank + (wid % CS)) % CS;
+                const int sub = wid / CS;
+                const uint32_t rseg = map_cluster(seg_s + 8u * (uint32_t)rank, src);
+                const unsigned start = ld_cluster_u32(rseg), len = ld_cluster_u32(rseg + 4u);
+                if (sub == 0 && lane == 0) atomicAdd(&s_nacc, len);
+                const uint32_t rlist = map_cluster(sorted_s, src) + 4u * start;
+                const unsigned stride = (unsigned)wps * 32u;
+                const unsigned jb = (unsigned)sub * 32u + (unsigned)lane;
+                unsigned ge_lo = 0, ge_hi = 0;
+                for (unsigned base = 0; base < len; base += 4u * stride) {
+                    uint32_t w[4];
+                    bool v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const unsigned j = base + (unsigned)u * stride + jb;
+                        v[u] = j < len;
+                        w[u] = 0;
+                        if (v[u]) w[u] = ld_cluster_u32(rlist + 4u * j);
+                    }
+                    const bool all4 = __all_sync(0xffffffffu, v[0] && v[1] && v[2] && v[3]);
+                    unsigned old[4], inc[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        inc[u] = v[u] ? ((w[u] >> 16) ? 65536u : 1u) : 0u;
+                        old[u] = 0;
+                        if (all4 || v[u])
+                            asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old[u]) : "r"(bins_s + 4u * (w[u] & 0xffffu)), "r"(inc[u]) : "memory");
+                    }
+                    unsigned s2p = 0;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const unsigned c = __byte_perm(old[u], 0u, inc[u] == 65536u ? 0x4432u : 0x4410u);
+                        const unsigned on = all4 ? 1u : (unsigned)v[u];
+                        s2p += (2u * c + 1u) * on;
+                        mall = max(mall, (c + 1u) * on);
+                        const unsigned sh = 8u * c;
+                        ge_lo += shl_clamp(on, sh);                   // fields that reach 1 .. 4 events
+                        ge_hi += shl_clamp(on, sh - 32u);             // ... 5 .. 8 (a shift amount outside [0, 32) yields 0)
+                        if (on && c == 65535u) {                      // the 16-bit field wrapped: recount this pixel exactly later
+                            const unsigned q = atomicAdd(&s_nsus, 1u);
+                            if (q < BIG_SUS) s_sus[q] = w[u] & 0xffffu;
+                        }
+                    }
+                    acc_s2 += s2p;
+                }
+#pragma unroll
+                for (int v8 = 0; v8 < 4; ++v8) {
+                    ge32[v8] += (ge_lo >> (8 * v8)) & 0xffu;
+                    ge32[4 + v8] += (ge_hi >> (8 * v8)) & 0xffu;
+                }
+            }
+            if (rb + round_cap < EC) cluster.sync();                  // peers have consumed this round's list before it is rewritten
+        }   // rounds
+
+        // ================= P2: statistics -> cut, maximum =================
+        publish(acc_s2, ge32, mall, flags);
+        cluster.sync();                // partials visible; also: every peer has finished pulling (the word list is dead)
+        derive();
+        if (s_nsus_tot) {              // cluster-uniform, rare: some 16-bit field wrapped
+            if (tid == 0) {
+                const unsigned raw = s_nsus;
+                unsigned m = 0;
+                for (unsigned i = 0; i < min(raw, (unsigned)BIG_SUS); ++i) {
+                    bool dup = false;
+                    for (unsigned j = 0; j < m; ++j) dup = dup || s_sus[j] == s_sus[i];
+                    if (!dup) s_sus[m++] = s_sus[i];
+                }
+                s_nsus = m;
+                if (raw > (unsigned)BIG_SUS) atomicOr(p.status, EC_STATUS_COUNT_OVERFLOW);     // more wrapped pixels than the side table holds
+            }
+            if (tid < 2 * BIG_SUS) (&s_exact[0][0])[tid] = 0;
+            __syncthreads();
+            const int ns = (int)s_nsus;
+            if (ns > 0) {
+                unsigned fl2 = 0;
+                for (long long e = tid; e < EC; e += NT) {
+                    unsigned l, pol;
+                    if (!decode_event<COMPACT>(p, fr.ev_start + e, HW, l, pol, fl2)) continue;
+                    const long long ll = (long long)l - band_lo;
+                    if (ll < 0 || ll >= (long long)nband) continue;
+                    for (int s = 0; s < ns; ++s)
+                        if ((unsigned)ll == s_sus[s]) atomicAdd(&s_exact[s][pol - 1u], 1u);
+                }
+            }
+            __syncthreads();
+            unsigned long long s2 = 0;
+            unsigned ge[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            unsigned ml = 0;
+            for (int i = tid; i < nband; i += NT) {
+                const uint32_t w = bins[i];
+                unsigned a = w & 0xffffu, b = w >> 16;
+                for (int s = 0; s < ns; ++s)
+                    if ((unsigned)i == s_sus[s]) { a = s_exact[s][0]; b = s_exact[s][1]; }
+                s2 += (unsigned long long)a * a + (unsigned long long)b * b;
+                ml = max(ml, max(a, b));
+#pragma unroll
+                for (int v = 0; v < 8; ++v) ge[v] += (a > (unsigned)v) + (b > (unsigned)v);
+            }
+            __syncthreads();
+            publish(s2, ge, ml, 0u);
+            cluster.sync();
+            derive();
+        }
+        const unsigned keep = s_keep;
+        const unsigned mall_all = s_mall;
+        const bool hot = mall_all > keep;
+        const int nsus = s_nsus_tot ? (int)s_nsus : 0;
+        if (s_need_pass) {             // cluster-uniform: the cut is above 8 and some bin exceeds it -> max of the survivors from the bins
+            unsigned m = 0;
+            const uint4 *h4 = reinterpret_cast<const uint4 *>(bins);
+            for (int i = tid; i < ((nband + 3) >> 2); i += NT) {
+                const uint4 w4 = h4[i];
+                if ((w4.x | w4.y | w4.z | w4.w) == 0) continue;
+                const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    unsigned a = ws[q] & 0xffffu, b = ws[q] >> 16;
+                    for (int s = 0; s < nsus; ++s)
+                        if ((unsigned)(4 * i + q) == s_sus[s]) { a = s_exact[s][0]; b = s_exact[s][1]; }
+                    if (a <= keep) m = max(m, a);
+                    if (b <= keep) m = max(m, b);
+                }
+            }
+            m = warp_max_u32(m);
+            if (lane == 0) red32[wid][10] = m;
+            __syncthreads();
+            if (tid == 0) {
+                unsigned mm = 0;
+                for (int w = 0; w < NW; ++w) mm = max(mm, red32[w][10]);
+                part.mx = mm;
+            }
+            cluster.sync();
+            if (tid == 0) {
+                unsigned mm = 0;
+                for (int r = 0; r < CS; ++r) mm = max(mm, cluster.map_shared_rank(&part, r)->mx);
+                s_mx = mm;
+            }
+            __syncthreads();
+        }
+        const unsigned mx = s_mx;
+
+        // ================= P4: per-frame gray LUT (the cut folded in), gray byte per pixel =================
+        {
+            const int side = (int)min(mall_all, (unsigned)(GLUT_N - 1)) + 1;
+            for (int k = tid; k < side * side; k += NT) {
+                const unsigned ln = k / side, lp = k - ln * side;
+                glut[ln * GLUT_N + lp] = (uint8_t)gray_px(lp > keep ? 0u : lp, ln > keep ? 0u : ln, mx, mask);
+            }
+        }
+        __syncthreads();
+        {
+            const uint32_t bg4 = 0x01010101u * glut[0];
+            for (int y = wid; y < rows; y += NW) {
+                const uint4 *h4 = reinterpret_cast<const uint4 *>(bins + y * W);
+                uint32_t *g32 = reinterpret_cast<uint32_t *>(gray + y * GP);
+                for (int c4 = lane; c4 < W4; c4 += 32) {
+                    const uint4 w4 = h4[c4];
+                    const uint32_t any = w4.x | w4.y | w4.z | w4.w;
+                    uint32_t pkb = bg4;
+                    if (!DBG && (any & 0xffe0ffe0u) == 0) {
+                        if (any) {
+                            const unsigned g0 = glut[((w4.x >> 11) & 0x3e0u) | w4.x & 0x1fu], g1 = glut[((w4.y >> 11) & 0x3e0u) | w4.y & 0x1fu];
+                            const unsigned g2 = glut[((w4.z >> 11) & 0x3e0u) | w4.z & 0x1fu], g3 = glut[((w4.w >> 11) & 0x3e0u) | w4.w & 0x1fu];
+                            pkb = __byte_perm(__byte_perm(g0, g1, 0x0040), __byte_perm(g2, g3, 0x0040), 0x5410);
+                        }
+                    } else {
+                        const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
+                        pkb = 0;
+#pragma unroll 1
+                        for (int q = 0; q < 4; ++q) {
+                            uint32_t w = ws[q];
+                            if (DBG && p.dbg_counts) {
+                                int32_t *dc = p.dbg_counts + ((size_t)fid * HW + band_lo + (size_t)y * W + 4 * c4 + q) * 2;
+                                dc[0] = (int32_t)(w & 0xffffu); dc[1] = (int32_t)(w >> 16);
+                            }
+                            if (hot) {
+                                if ((w & 0xffffu) > keep) w &= 0xffff0000u;
+                                if ((w >> 16) > keep) w &= 0x0000ffffu;
+                            }
+                            unsigned gq;
+                            if ((w & 0xffe0ffe0u) == 0) gq = glut[((w >> 11) & 0x3e0u) | (w & 0x1fu)];
+                            else gq = gray_px(w & 0xffffu, w >> 16, mx, mask);
+                            pkb |= gq << (8 * q);
+                        }
+                    }
+                    g32[c4] = pkb;
+                    if (DBG && p.dbg_gray) *reinterpret_cast<uint32_t *>(p.dbg_gray + (size_t)fid * HW + band_lo + (size_t)y * W + 4 * c4) = pkb;
+                }
+            }
+        }
+        __syncthreads();
+        if (nsus > 0 && tid < nsus) {      // wrapped pixels: exact 32-bit counts
+            const unsigned i = s_sus[tid];
+            const unsigned a = s_exact[tid][0], b = s_exact[tid][1];
+            const unsigned gq = gray_px(a > keep ? 0u : a, b > keep ? 0u : b, mx, mask);
+            const unsigned yy = i / (unsigned)W, xx = i - yy * (unsigned)W;
+            gray[yy * GP + xx] = (uint8_t)gq;
+            if (DBG && p.dbg_counts) {
+                int32_t *dc = p.dbg_counts + ((size_t)fid * HW + band_lo + i) * 2;
+                dc[0] = (int32_t)a; dc[1] = (int32_t)b;
+            }
+            if (DBG && p.dbg_gray) p.dbg_gray[(size_t)fid * HW + band_lo + i] = (uint8_t)gq;
+        }
+        if (nsus > 0) __syncthreads();
+        // while this frame is resampled and stored, pull this CTA's first slice of the NEXT frame's events into L2
+        if (fid + n_clusters < p.n_frames) {
+            const ec_frame nx = p.frames[fid + n_clusters];
+            if (nx.ev_count > 0) {
+                const int n_round = min(round_cap, nx.ev_count);
+                const int per = (n_round + CS - 1) / CS;
+                const int e_lo = min(rank * per, n_round);
+                const int n = min(per, n_round - e_lo);
+                const char *b = COMPACT ? reinterpret_cast<const char *>(p.events_c + nx.ev_start + e_lo)
+                                        : reinterpret_cast<const char *>(p.events + nx.ev_start + e_lo);
+                const long long bytes = (long long)n * (COMPACT ? 4 : 16);
+                for (long long o = (long long)tid * 128; o < bytes; o += (long long)NT * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(b + o));
+            }
+        }
+
+        // ================= P5: horizontal pass on the tensor cores, gray [y][x] -> hT [xo][y - y0] =================
+        {
+            constexpr int HW_WARPS = 2 * MT;           // 28 warps: tile mt = wid % 14, half of the 8-row tiles each
+            if (wid < HW_WARPS) {
+                const int mt = wid % MT, half = wid / MT;
+                const int ws = s_ws[mt];
+                const uint4 *fragH = reinterpret_cast<const uint4 *>(p.fragH) + lane;
+                uint4 a[2][3];
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                    for (int dg = 0; dg < 3; ++dg)
+                        a[ks][dg] = p.KSH > ks ? __ldg(fragH + ((mt * p.KSH + ks) * 3 + dg) * 32) : make_uint4(0, 0, 0, 0);
+                const int n_tiles = (rows + 7) >> 3;
+                const int nt0 = half * n_tiles / 2, nt1 = (half + 1) * n_tiles / 2;
+                for (int nt = nt0; nt < nt1; ++nt) {
+                    const uint8_t *src = gray + (nt * 8 + g) * GP + ws + tig * 4;
+                    const uint32_t b00 = *reinterpret_cast<const uint32_t *>(src), b01 = *reinterpret_cast<const uint32_t *>(src + 16);
+                    const uint32_t b10 = *reinterpret_cast<const uint32_t *>(src + 32), b11 = *reinterpret_cast<const uint32_t *>(src + 48);
+                    int c0[4], c1[4], c2[4];
+                    imma_s8u8(c0, a[0][0], b00, b01, 1 << (PREC - 1));
+                    imma_s8u8(c1, a[0][1], b00, b01, 0);
+                    imma_s8u8(c2, a[0][2], b00, b01, 0);
+                    imma_s8u8_acc(c0, a[1][0], b10, b11);
+                    imma_s8u8_acc(c1, a[1][1], b10, b11);
+                    imma_s8u8_acc(c2, a[1][2], b10, b11);
+                    unsigned px[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) px[e] = (unsigned)__vimin_s32_relu((c0[e] + (c1[e] << 8) + (c2[e] << 16)) >> PREC, 255);
+                    uint8_t *dst = hT + (mt * 16 + g) * HPB + nt * 8 + tig * 2;
+                    *reinterpret_cast<uint16_t *>(dst) = (uint16_t)__byte_perm(px[0], px[1], 0x0040);
+                    *reinterpret_cast<uint16_t *>(dst + 8 * HPB) = (uint16_t)__byte_perm(px[2], px[3], 0x0040);
+                }
+            } else {
+                // spare warps: the bins are dead since P4 -- clear the first quarter for the next frame
+                uint4 *b4 = reinterpret_cast<uint4 *>(bins);
+                for (int i = tid - HW_WARPS * 32; i < (n16 >> 2); i += NT - HW_WARPS * 32) b4[i] = make_uint4(0, 0, 0, 0);
+            }
+        }
+        cluster.sync();                // every band of hT is complete
+
+        // ================= P6: vertical pass on the tensor cores (source rows over DSMEM), normalise, store =================
+        {
+            uint8_t *du = (DBG && p.dbg_u8) ? p.dbg_u8 + (size_t)fid * OUT * OUT : nullptr;
+            char *ofr = (char *)p.out + (size_t)slot * frame_elems * (p.out_fmt == EC_OUT_F32_NCHW ? 4 : 2);
+            constexpr int UNITS = MT * (OUT / 32);     // (16 output rows) x (32 output columns)
+            const int my_units = rank < UNITS ? (UNITS - rank + CS - 1) / CS : 0;     // units u = rank + CS * k, one per warp k
+            const int unit_warps = min(my_units, NW);
+            if (wid < unit_warps) {
+                const uint4 *fragV = reinterpret_cast<const uint4 *>(p.fragV) + lane;
+                for (int u = rank + CS * wid; u < UNITS; u += CS * NW) {
+                    const int mt = u % MT, cgp = u / MT;
+                    const int ws = s_ws[MT + mt];
+                    uint4 a[2][3];
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                        for (int dg = 0; dg < 3; ++dg)
+                            a[ks][dg] = p.KSV > ks ? __ldg(fragV + ((mt * p.KSV + ks) * 3 + dg) * 32) : make_uint4(0, 0, 0, 0);
+                    // the lane's four 4-byte source groups of a K step pair: sensor rows ws + 32 ks + 16 h + 4 tig .. + 3
+                    uint32_t raddr[4];
+                    bool rok[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const unsigned y = (unsigned)(ws + 16 * q + 4 * tig);
+                        const unsigned band = (y * p.big_rb_magic) >> 20;             // y / RB
+                        rok[q] = band < (unsigned)CS;
+                        raddr[q] = rok[q] ? map_cluster(hT_s + (y - band * (unsigned)RB), (int)band) : 0u;
+                    }
+                    const int yo = mt * 16 + g;
+                    uint32_t row_a[2], row_b[2];
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        uint32_t pa[2], pb[2];
+#pragma unroll
+                        for (int t = 0; t < 2; ++t) {
+                            const uint32_t off = (uint32_t)((32 * cgp + 8 * (g >> 1) + (g & 1) + 2 * (2 * hh + t)) * HPB);
+                            uint32_t b[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) b[q] = rok[q] ? ld_cluster_u32(raddr[q] + off) : 0u;
+                            int c0[4], c1[4], c2[4];
+                            imma_s8u8(c0, a[0][0], b[0], b[1], 1 << (PREC - 1));
+                            imma_s8u8(c1, a[0][1], b[0], b[1], 0);
+                            imma_s8u8(c2, a[0][2], b[0], b[1], 0);
+                            imma_s8u8_acc(c0, a[1][0], b[2], b[3]);
+                            imma_s8u8_acc(c1, a[1][1], b[2], b[3]);
+                            imma_s8u8_acc(c2, a[1][2], b[2], b[3]);
+                            unsigned px[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                px[e] = (unsigned)__vimin_s32_relu((c0[e] + (c1[e] << 8) + (c2[e] << 16)) >> PREC, 255);
+                            pa[t] = __byte_perm(px[0], px[1], 0x0040);
+                            pb[t] = __byte_perm(px[2], px[3], 0x0040);
+                        }
+                        row_a[hh] = __byte_perm(pa[0], pa[1], 0x5410);
+                        row_b[hh] = __byte_perm(pb[0], pb[1], 0x5410);
+                    }
+                    const int x = 32 * cgp + 8 * tig;
+                    emit8(p, make_uint2(row_a[0], row_a[1]), yo, x, ofr, du, wide, cstride, rowoff, coloff, p.nlut, nlut3);
+                    emit8(p, make_uint2(row_b[0], row_b[1]), yo + 8, x, ofr, du, wide, cstride, rowoff, coloff, p.nlut, nlut3);
+                }
+            } else {
+                // warps without a unit clear the rest of the bins
+                uint4 *b4 = reinterpret_cast<uint4 *>(bins);
+                const int spare = NT - unit_warps * 32;
+                for (int i = (n16 >> 2) + tid - unit_warps * 32; i < n16; i += spare) b4[i] = make_uint4(0, 0, 0, 0);
+            }
+            if (unit_warps == NW) {    // no spare warp (tiny clusters): everybody clears after the units
+                __syncthreads();
+                uint4 *b4 = reinterpret_cast<uint4 *>(bins);
+                for (int i = (n16 >> 2) + tid; i < n16; i += NT) b4[i] = make_uint4(0, 0, 0, 0);
+            }
+        }
+        // no barrier here: the next frame's S1 only writes the word list (this CTA's P5 has read the gray plane), its
+        // barriers order the bin clearing before S2, and peers reach the next cluster barrier only after their P6
+    }   // frame loop
+    cluster.sync();                    // no CTA leaves while a peer may still read its shared memory
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side: Pillow coefficient tables (ImagingResample precompute_coeffs + normalize_coeffs_8bpc)
 // ------------------------------------------------------------------------------------------------
@@ -1257,6 +1922,62 @@ bool tc_plan(int H, int W, int CS, int KSH, int KSV, size_t &smem, int &gray_off
     return true;
 }
 
+// Band-exchange cluster kernel: the bins do not fit one CTA, rows are 4-byte aligned, every 16-output tile of both axes reads
+// a source window of <= 64 pixels (two K steps), a band holds <= 65536 bins.  Returns whether it applies, the cluster size,
+// the band height (a multiple of 4 rows, so that a 4-byte group of the transposed intermediate never straddles two bands)
+// and the shared-memory layout.  EC_E2I_BIG=0 disables it, EC_E2I_BIG=force also takes sensors that fit one CTA (tests of the
+// 2- and 4-CTA paths), EC_E2I_BIG_CAP lowers the events per CTA and round (tests of the multi-round exchange).
+struct BigPlan {
+    int CS = 0, RB = 0, gp = 0, hpb = 0, off_b = 0, off_ht = 0, cap = 0;
+    unsigned rb_magic = 0;
+    size_t smem = 0;
+};
+
+bool big_plan(int H, int W, int KSH, int KSV, bool fits_one_cta, BigPlan &bp)
+{
+    const char *mode = getenv("EC_E2I_BIG");
+    const bool force = mode && !strcmp(mode, "force");
+    if (mode && atoi(mode) == 0 && !force) return false;
+    if (fits_one_cta && !force) return false;
+    if (W % 4 != 0 || H < 16 || W < 64 || KSH < 1 || KSH > 2 || KSV < 1 || KSV > 2 || (long long)H * W >= (1 << 24)) return false;
+    const size_t limit = (size_t)227 * 1024 - 9 * 1024;        // static shared memory of the kernel: ~8.7 KB
+    for (int CS = 2; CS <= 8; CS *= 2) {
+        const int RB = (((H + CS - 1) / CS) + 3) & ~3;
+        if ((long long)RB * (CS - 1) >= H) continue;           // the last band would be empty
+        if ((long long)RB * W > 65536) continue;
+        const int RB8 = (RB + 7) & ~7;
+        int gpw = W / 4;
+        while (gpw % 8 != 4) ++gpw;                             // pitch = 4 (mod 8) words: the eight rows of a B fragment hit distinct banks
+        const int gp = 4 * gpw;
+        const int hpb = RB8 + 4;
+        const size_t bins = (size_t)RB * W * 4;
+        size_t regb = (size_t)RB8 * gp + 128;
+        int cap = BIG_CAP;
+        if (const char *e = getenv("EC_E2I_BIG_CAP")) { const int c = atoi(e); if (c >= 32 && c < cap) cap = c; }
+        if (regb < (size_t)cap * 4) {
+            // a small band: the word list does not fit the gray plane's footprint -- shrink the round rather than grow the region
+            // beyond what the gray plane needs, unless shared memory is plentiful
+            const size_t want = (size_t)cap * 4;
+            if (bins + want + (size_t)OUT * hpb + 64 <= limit) regb = want;
+            else cap = (int)(regb / 4);
+        }
+        regb = (regb + 15) & ~(size_t)15;
+        const size_t ht = ((size_t)OUT * hpb + 15) & ~(size_t)15;
+        if (bins + regb + ht > limit) continue;
+        bp.CS = CS; bp.RB = RB; bp.gp = gp; bp.hpb = hpb; bp.cap = cap;
+        bp.off_b = (int)bins; bp.off_ht = (int)(bins + regb);
+        bp.smem = bins + regb + ht;
+        bp.rb_magic = (unsigned)(((1u << 20) + (unsigned)RB - 1) / (unsigned)RB);
+        for (unsigned y = 0; y < (unsigned)(CS * RB + 128); ++y)                 // the multiply-shift division is exact where it is used
+            if (((y * bp.rb_magic) >> 20) != y / (unsigned)RB) return false;
+        const unsigned long long d = (unsigned long long)RB * W, magic = ((1ull << 40) + d - 1) / d;
+        for (unsigned long long k = 1; k <= (unsigned long long)CS; ++k)
+            if ((((k * d - 1) * magic) >> 40) != k - 1 || (((k * d) * magic) >> 40) != k) return false;
+        return true;
+    }
+    return false;
+}
+
 std::mutex g_mu;
 std::map<std::tuple<int, int, int>, Tables> g_tables;
 
@@ -1372,12 +2093,16 @@ extern "C" int ec_event2img_geometry(int H, int W, int *cluster_size, int *threa
         ec::set_error("ec_event2img_geometry: sensor %dx%d unsupported", H, W);
         return EC_ERR_UNSUPPORTED;
     }
-    if (CS == 1) {      // same choice ec_event2img makes: the tensor-core kernel when its tiling applies
+    {      // same choice ec_event2img makes: the tensor-core kernel when its tiling applies, the band-exchange kernel for clusters
         std::vector<int32_t> hx, vy, frag, ws;
         int KH, KV, gray_off;
         resample_axes(H, W, hx, vy, KH, KV);
         const int KSH = build_frags(hx, KH, frag, ws), KSV = build_frags(vy, KV, frag, ws);
-        if (tc_plan(H, W, CS, KSH, KSV, smem, gray_off) && NT < 512) NT = 512;
+        size_t tsmem = smem;
+        const bool tc = CS == 1 && tc_plan(H, W, CS, KSH, KSV, tsmem, gray_off);
+        BigPlan bp;
+        if (big_plan(H, W, KSH, KSV, CS == 1, bp)) { CS = bp.CS; NT = BIG_NT; smem = bp.smem; }
+        else if (tc) { smem = tsmem; if (NT < 512) NT = 512; }
     }
     if (cluster_size) *cluster_size = CS;
     if (threads) *threads = NT;
@@ -1483,13 +2208,25 @@ static int event2img_impl(const float *events, const uint32_t *events_c, const e
     for (int c = 0; c < 3; ++c) { p.na[c] = tb.na[c]; p.nb[c] = tb.nb[c]; }
     p.affine = tb.affine;
     p.band_magic = ((1ull << 40) + (unsigned long long)RB * W - 1) / ((unsigned long long)RB * W);
+    p.big_off_b = p.big_off_ht = p.big_gp = p.big_hpb = p.big_cap = 0;
+    p.big_rb_magic = 0;
 
     const bool dbg = dbg_counts || dbg_gray || dbg_u8;
-    const bool tc = tc_plan(H, W, CS, tb.KSH, tb.KSV, smem, p.gray_off);
+    BigPlan bp;
+    const bool big = big_plan(H, W, tb.KSH, tb.KSV, CS == 1, bp);
+    const bool tc = !big && tc_plan(H, W, CS, tb.KSH, tb.KSV, smem, p.gray_off);
     if (tc && NT < 512) NT = 512;      // 14 warps carry the matrix passes
     typedef void (*kern_t)(const E2IParams);
     kern_t kern;
-    if (tc)
+    if (big) {
+        CS = bp.CS; RB = bp.RB; NT = BIG_NT; smem = bp.smem;
+        p.CS = CS; p.RB = RB;
+        p.big_off_b = bp.off_b; p.big_off_ht = bp.off_ht; p.big_gp = bp.gp; p.big_hpb = bp.hpb; p.big_cap = bp.cap;
+        p.big_rb_magic = bp.rb_magic;
+        p.band_magic = ((1ull << 40) + (unsigned long long)RB * W - 1) / ((unsigned long long)RB * W);
+        kern = events_c ? (dbg ? event2img_big_kernel<true, true> : event2img_big_kernel<false, true>)
+                        : (dbg ? event2img_big_kernel<true, false> : event2img_big_kernel<false, false>);
+    } else if (tc)
         kern = events_c ? (dbg ? event2img_tc_kernel<true, true> : event2img_tc_kernel<false, true>)
                         : (dbg ? event2img_tc_kernel<true, false> : event2img_tc_kernel<false, false>);
     else
@@ -1522,11 +2259,11 @@ static int event2img_impl(const float *events, const uint32_t *events_c, const e
     // persistent: as many clusters as the device holds at once; each walks over the frames with that stride
     {
         static std::mutex mu2;
-        static std::map<std::tuple<int, const void *, int, size_t>, int> resident;
+        static std::map<std::tuple<int, const void *, int, size_t, int>, int> resident;
         std::lock_guard<std::mutex> lk(mu2);
         int dev_id = 0;
         EC_CUDA_CHECK(cudaGetDevice(&dev_id));
-        int &nc = resident[std::make_tuple(dev_id, (const void *)kern, NT, smem)];
+        int &nc = resident[std::make_tuple(dev_id, (const void *)kern, NT, smem, CS)];
         if (nc == 0) {
             cudaLaunchConfig_t q = cfg;
             q.gridDim = dim3((unsigned)(ec::sm_count() * 8));     // any multiple of the cluster size

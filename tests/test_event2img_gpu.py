@@ -156,16 +156,94 @@ def test_error_flags(cuda_dev):
     ev[3, 0], ev[3, 1] = 125, 4
     fr = events2frames(ev, "event_count", "event_histogram", shape=(100, 120), N=30000)
     assert (fr == orc.events2frames(ev, (100, 120), 30000)).all()
-    # 16-bit packed bins: 70000 events on one pixel of one polarity must be reported, not silently wrapped
-    ev = np.zeros((70000, 4), np.float32)
-    ev[:, 0], ev[:, 1], ev[:, 3] = 5, 6, 1
-    ev[:3000, 0] = np.arange(3000) % 640
-    ev[:, 2] = np.linspace(0, 1, 70000)
-    frames, _, _, K = ops.plan_frames([0, 70000], 70000, 2, compact=True)
-    _, status, _ = ops.event2img(torch.from_numpy(ev).to(cuda_dev), frames.to(cuda_dev), (480, 640), K)
-    assert int(status.item()) & _lib.EC_STATUS_COUNT_OVERFLOW
-    with pytest.raises(_lib.ECError):
-        ops.raise_on_status(status)
+
+
+def _overflow_stream(n_hot_pos, n_hot_neg, n_rest, seed):
+    """N-ImageNet-shaped frame in which one pixel receives n_hot_pos positive and n_hot_neg negative events."""
+    rng = np.random.default_rng(seed)
+    E = n_hot_pos + n_hot_neg + n_rest
+    ev = np.zeros((E, 4), np.float32)
+    ev[:, 0], ev[:, 1] = 333, 257
+    ev[:n_hot_pos, 3] = 1
+    ev[n_hot_pos:n_hot_pos + n_hot_neg, 3] = -1
+    ev[n_hot_pos + n_hot_neg:, 0] = rng.integers(0, 640, n_rest)
+    ev[n_hot_pos + n_hot_neg:, 1] = rng.integers(0, 480, n_rest)
+    ev[n_hot_pos + n_hot_neg:, 3] = np.where(rng.random(n_rest) < 0.5, -1.0, 1.0)
+    ev = ev[rng.permutation(E)]
+    ev[:, 2] = np.linspace(0, 0.05, E)
+    return ev
+
+
+@pytest.mark.parametrize("hot_pos,hot_neg,rest", [(70000, 0, 0), (66000, 0, 4000), (0, 67001, 2999), (65536, 1200, 3000),
+                                                  (65535, 0, 4465), (65536, 0, 1)])
+def test_counts_above_65535_are_exact(cuda_dev, hot_pos, hot_neg, rest):
+    """The reference's histogram is int64 (datasets/vis.py:9-14); N-ImageNet's N = 70000 lets one 16-bit field of the packed
+    bins wrap.  The wrapped pixel is recounted in 32 bits and the statistics are redone from the bins: counts, gray frame,
+    resampled bytes and the float32 tensor equal the oracle's, and no status bit is raised."""
+    ev = _overflow_stream(hot_pos, hot_neg, rest, seed=hot_pos % 97 + rest)
+    N = 70000
+    frames, _, _, K = ops.plan_frames([0, len(ev)], N, 2, compact=True)
+    img, status, dbg = ops.event2img(torch.from_numpy(ev).to(cuda_dev), frames.to(cuda_dev), (480, 640), K, False, True,
+                                     out="f32", debug=True)
+    assert int(status.item()) == 0
+    counts = orc.histogram(ev[:N], (480, 640))
+    assert counts.max() >= 65535
+    assert (dbg["counts"][0].cpu().numpy() == counts).all()
+    gray, _, _ = orc.frame_from_counts(counts, False, True)
+    assert (dbg["gray"][0].cpu().numpy() == gray).all()
+    assert (dbg["u8"][0].cpu().numpy() == orc.resize_crop_224(gray)).all()
+    oimg, _, _ = orc.event2img_sample(ev, (480, 640), N, 1, False, True)
+    assert (img[0].cpu().numpy() == oimg[0]).all()
+    # the non-debug kernel variant and the compact wire format take the same path
+    img2, status2, _ = ops.event2img(torch.from_numpy(ev).to(cuda_dev), frames.to(cuda_dev), (480, 640), K, False, True, out="f32")
+    words = ops.pack_events(torch.from_numpy(ev).to(cuda_dev), (480, 640))
+    img3, status3, _ = ops.event2img(words, frames.to(cuda_dev), (480, 640), K, False, True, out="f32")
+    assert torch.equal(img2, img) and torch.equal(img3, img) and int(status2.item()) == 0 and int(status3.item()) == 0
+
+
+def test_band_exchange_kernel_cluster_sizes_and_rounds(cuda_dev):
+    """event2img_big_kernel outside its home shape: EC_E2I_BIG=force routes sensors that fit one SM through 2-CTA clusters,
+    480x320 takes a 4-CTA cluster, and EC_E2I_BIG_CAP shrinks the exchange round so that a frame needs several rounds.
+    Every stage equals the oracle's (the environment is read per call)."""
+    old = {k: os.environ.get(k) for k in ("EC_E2I_BIG", "EC_E2I_BIG_CAP")}
+    try:
+        for shape, N, cnz, bg, force, cap, want_cs in (((180, 240), 20000, False, True, True, None, 2),
+                                                       ((180, 240), 20000, True, False, True, "1024", 2),
+                                                       ((128, 128), 9000, False, True, True, "96", 2),
+                                                       ((480, 320), 50000, False, True, False, None, 4),
+                                                       ((480, 640), 70000, False, True, False, "2048", 8)):
+            os.environ.pop("EC_E2I_BIG", None)
+            os.environ.pop("EC_E2I_BIG_CAP", None)
+            if force:
+                os.environ["EC_E2I_BIG"] = "force"
+            if cap:
+                os.environ["EC_E2I_BIG_CAP"] = cap
+            assert ops.event2img_geometry(shape)["cluster"] == want_cs, shape
+            for kind in ("uniform", "clustered", "hotpixel"):
+                ev = synth_events(shape, int(2.6 * N) + 17, 31, kind)
+                img, dbg, K = _run_frames(ev, shape, N, cnz, bg, cuda_dev)
+                i0, i1 = orc.split_event_count(len(ev), N)
+                assert K == len(i0) == 3
+                for k in range(K):
+                    counts = orc.histogram(ev[i0[k]:i1[k]], shape)
+                    assert (dbg["counts"][k].cpu().numpy() == counts).all(), (shape, kind, k)
+                    gray, _, _ = orc.frame_from_counts(counts, cnz, bg)
+                    assert (dbg["gray"][k].cpu().numpy() == gray).all(), (shape, kind, k)
+                    assert (dbg["u8"][k].cpu().numpy() == orc.resize_crop_224(gray)).all(), (shape, kind, k)
+                oimg, _, _ = orc.event2img_sample(ev, shape, N, K, cnz, bg)
+                assert (img.cpu().numpy() == oimg[:K]).all(), (shape, kind)
+                # non-debug variant, bf16 patch rows
+                frames, _, _, K2 = ops.plan_frames([0, len(ev)], N, K, compact=True)
+                pt, st, _ = ops.event2img(torch.from_numpy(ev).to(cuda_dev), frames.to(cuda_dev), shape, K2, cnz, bg, out="patch",
+                                          patch=16, ldk=768)
+                ref = img.to(torch.bfloat16).view(-1, 3, 14, 16, 14, 16).permute(0, 2, 4, 1, 3, 5).reshape(-1, 768)
+                assert torch.equal(pt, ref) and int(st.item()) == 0, (shape, kind)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
 
 
 def test_full_size_properties(cuda_dev):
