@@ -215,10 +215,11 @@ def parity_stats(got_logits, ref_logits, k=1):
 
 
 def patches_bit_exact(patches, imgs, valid, P):
-    """bf16 im2col rows written by the fused event kernel vs RNE-bf16 of the oracle's float32 frames (bitwise)."""
+    """16-bit im2col rows written by the fused event kernel vs the round-to-nearest-even of the oracle's float32 frames in the
+    same format (bf16 or fp16), bitwise."""
     x = imgs[valid]                                                  # [nv, 3, 224, 224]
     n, G = x.shape[0], 224 // P
-    ref = x.reshape(n, 3, G, P, G, P).permute(0, 2, 4, 1, 3, 5).reshape(n * G * G, 3 * P * P).to(torch.bfloat16)
+    ref = x.reshape(n, 3, G, P, G, P).permute(0, 2, 4, 1, 3, 5).reshape(n * G * G, 3 * P * P).to(patches.dtype)
     got = patches[: n * G * G, : 3 * P * P].cpu()
     return bool(torch.equal(got.view(torch.int16), ref.view(torch.int16)))
 
@@ -396,7 +397,7 @@ class Workload:
         frames, valid, _, nv = ops.plan_frames(offc, self.e2i.N, self.T, sel=selc, compact=True)
         with torch.no_grad():
             patches, _, _ = ops.event2img(torch.from_numpy(evc).to(dev), frames.to(dev), cfg["shape"], nv, cfg["count_non_zero"],
-                                          cfg["background_mask"], out="patch", patch=vis.patch_size, ldk=vis.k_patch)
+                                          cfg["background_mask"], out=vis.patch_fmt, patch=vis.patch_size, ldk=vis.k_patch)
             feats = vis.forward_patches(patches, nv).float().cpu()
         first = torch.from_numpy(np.concatenate([[0], np.cumsum(valid.sum(1).numpy())[:-1]]))     # first view of every sample
         self.text = calibrate_text_feats(feats[first], cfg["n_cls"])
@@ -672,6 +673,21 @@ def b200_arm(args):
             lab0 = torch.full((B,), -1, dtype=torch.int32)
             lab0[:args.parity_samples] = ref["logits"].argmax(-1).to(torch.int32)
             labels[0].copy_(lab0)
+            # the same batch through the other numeric settings of the inference forward (eager launches, not timed): what the
+            # 16-bit operand format and the residual stream's dtype each cost in error
+            vis = model.visual
+            keep = (vis.operand_dtype, vis.residual_dtype)
+            variants = {}
+            for name, op, res in (("bf16_operands_fp16_residual", torch.bfloat16, torch.float16),
+                                  ("fp16_operands_fp16_residual", torch.float16, torch.float16),
+                                  ("fp16_operands_fp32_residual", torch.float16, torch.float32)):
+                vis.operand_dtype, vis.residual_dtype = op, res
+                with torch.no_grad():
+                    lg = zs(w.data(0))["logits"].float().cpu()
+                st = parity_stats(lg[:args.parity_samples], ref["logits"])
+                variants[name] = {k: st[k] for k in ("logits_centered_rel_l2", "max_abs_logit_err", "top1_agree", "top1_disagreements")}
+            vis.operand_dtype, vis.residual_dtype = keep
+            parity["numeric_variants"] = variants
         except Exception as ex:
             parity = dict(error=repr(ex)[:300])
     counters.zero_()
@@ -825,6 +841,7 @@ def b200_arm(args):
                   sample="2 steps x 32 samples of the bench workload through the oracle (C event2img + fp32 PyTorch CLIP + head)")
     enc_flops = clip.flops_per_image(arch) * B * T
     residual = "fp16 (the reference's CUDA precision)" if model.visual.residual_dtype == torch.float16 else "fp32"
+    operands = "fp16" if model.visual.operand_dtype == torch.float16 else "bf16"
     acc = counters.tolist()
     del runner, w, zs, model, host, devb
     torch.cuda.empty_cache()
@@ -849,14 +866,15 @@ def b200_arm(args):
         peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": Wm,
-            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": operands,
             "data": "synthetic",
             "config": {"workload": f"zero-shot {arch} on synthetic N-Cars-shaped streams (120x100, 4000 events/sample, "
                                    f"2 classes), batch {B} per GPU, random-init CLIP (BASELINE.json configs[1])",
                        "streams": "labelled synthetic samples with per-sample blob layouts (synth.synth_labeled_batch); text "
                                   "features calibrated on a disjoint batch so the predictions split evenly",
                        "per_gpu_batch": B, "views_per_sample": T,
-                       "numerics": "bf16 tensor-core operands, fp32 accumulation, residual stream in " + residual,
+                       "numerics": operands + " tensor-core operands (tcgen05 kind::f16; EC_OPERANDS selects bf16 / fp16, same rate), fp32 "
+                                   "accumulation, residual stream in " + residual,
                        "l2": "256 MiB buffer rewritten before every step (inside the timed region)",
                        "sharding": "samples by rank; one all-reduce of 2 int64 counters at the end",
                        "launch": "eager" if args.no_graph else "CUDA graph replay of the device part (event2img..head)"},

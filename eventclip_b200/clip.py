@@ -117,6 +117,27 @@ def pack_blocks(resblocks, d, dev):
     return blocks
 
 
+def pack_blocks_f16(resblocks, d, dev):
+    """fp16 copies of the GEMM weights of every block (LoRA factors merged in fp32, models/lora.py:138-149, 49-52) for the
+    fp16-operand inference forward.  Pack-time arithmetic in torch, like pack_blocks_ln."""
+    f32 = lambda t: t.detach().to(torch.float32)
+    out = []
+    for blk in resblocks:
+        W, lora_in, _, oW, _, lora_out = _attn_weights(blk.attn)
+        W = f32(W).clone()
+        if lora_in is not None:
+            for j, n in enumerate("qkv"):
+                up, down = getattr(lora_in, f"lora_up_{n}", None), getattr(lora_in, f"lora_down_{n}", None)
+                if up is not None and down is not None:
+                    W[j * d:(j + 1) * d] += f32(up) @ f32(down)
+        oW = f32(oW)
+        if lora_out is not None:
+            oW = oW + f32(lora_out.lora_up.weight) @ f32(lora_out.lora_down.weight)
+        h = lambda t: t.to(torch.float16).contiguous()
+        out.append(dict(w_in=h(W), w_out=h(oW), w_fc=h(f32(blk.mlp.c_fc.weight)), w_proj=h(f32(blk.mlp.c_proj.weight))))
+    return out
+
+
 def pack_blocks_ln(resblocks, d, dev):
     """Per block, the operands of the LayerNorm-folded GEMMs (ec_gemm_ln): Wg = fp16(gamma * W_eff) with every row centred
     (LoRA factors merged as in models/lora.py:138-149) and c = W_eff beta + b, so that   LN(x) W^T + b = rstd (x Wg^T) + c
@@ -143,6 +164,9 @@ def pack_blocks_ln(resblocks, d, dev):
             wg.scatter_(1, kmax, (wg.gather(1, kmax).to(torch.float32) - r[:, None]).to(torch.float16))
             e["wg_" + name] = wg
             e["c_" + name] = (Wf @ f32(ln.bias) + bf_).contiguous()
+        _, _, _, _, ob, _ = _attn_weights(blk.attn)
+        e["b_out"] = f32(ob).contiguous().clone()
+        e["b_proj"] = f32(blk.mlp.c_proj.bias).contiguous().clone()
         out.append(e)
     return out
 
@@ -150,39 +174,45 @@ def pack_blocks_ln(resblocks, d, dev):
 def run_blocks_ln(x, blocks, lnb, n_seq, Ltok, d, heads):
     """x: fp16 residual stream [n_seq*Ltok, d].  No LayerNorm kernel: in_proj and c_fc read the stream itself as their A
     operand and apply the normalisation in their epilogues from the row statistics that the previous residual epilogue
-    (out_proj / c_proj) wrote next to the rows."""
+    (out_proj / c_proj) wrote next to the rows.  blocks: bf16 or fp16 weight copies; the activations between the GEMMs
+    (qkv, attention output, MLP hidden) take the same 16-bit dtype."""
     M, dev = n_seq * Ltok, x.device
     parts = ops.gemm_stats_parts(d)
     stats = torch.empty((M, parts, 2), dtype=torch.float32, device=dev)
     ops.row_stats_f16(x, stats, parts)                       # the rows ln_pre wrote
-    qkv = torch.empty((M, 3 * d), dtype=torch.bfloat16, device=dev)
-    att = torch.empty((M, d), dtype=torch.bfloat16, device=dev)
-    hid = torch.empty((M, 4 * d), dtype=torch.bfloat16, device=dev)
+    dt = blocks[0]["w_out"].dtype
+    qkv = torch.empty((M, 3 * d), dtype=dt, device=dev)
+    att = torch.empty((M, d), dtype=dt, device=dev)
+    hid = torch.empty((M, 4 * d), dtype=dt, device=dev)
     for b, f in zip(blocks, lnb):
         ops.gemm_ln(x, f["wg_in"], None, f["c_in"], stats, parts, "bf16", out=qkv)
         ops.attention(qkv, att, n_seq, Ltok, heads)
-        ops.gemm_bf16_stats(att, b["w_out"], b["b_out"], x, stats)
+        ops.gemm_bf16_stats(att, b["w_out"], f["b_out"], x, stats)
         ops.gemm_ln(x, f["wg_fc"], None, f["c_fc"], stats, parts, "bf16_qgelu", out=hid)
-        ops.gemm_bf16_stats(hid, b["w_proj"], b["b_proj"], x, stats)
+        ops.gemm_bf16_stats(hid, b["w_proj"], f["b_proj"], x, stats)
     return x
 
 
-def run_blocks(x, blocks, n_seq, Ltok, d, heads, causal=False):
-    """x: residual stream [n_seq*Ltok, d], fp32 or fp16, updated in place by the GEMM epilogues."""
+def run_blocks(x, blocks, n_seq, Ltok, d, heads, causal=False, w16=None):
+    """x: residual stream [n_seq*Ltok, d], fp32 or fp16, updated in place by the GEMM epilogues.  w16: per-block fp16 weight
+    copies (pack_blocks_f16) -> fp16 operands and activations; None -> the bf16 copies of `blocks`."""
     M, dev = n_seq * Ltok, x.device
     resadd = "f16_resadd" if x.dtype == torch.float16 else "f32_resadd"
-    xn = torch.empty((M, d), dtype=torch.bfloat16, device=dev)
-    qkv = torch.empty((M, 3 * d), dtype=torch.bfloat16, device=dev)
-    att = torch.empty((M, d), dtype=torch.bfloat16, device=dev)
-    hid = torch.empty((M, 4 * d), dtype=torch.bfloat16, device=dev)
-    for b in blocks:
-        ops.layernorm(x, *b["ln1"], M, d, out_bf16=xn)
-        ops.gemm_bf16(xn, b["w_in"], b["b_in"], "bf16", out=qkv)
+    dt = torch.bfloat16 if w16 is None else torch.float16
+    xn = torch.empty((M, d), dtype=dt, device=dev)
+    qkv = torch.empty((M, 3 * d), dtype=dt, device=dev)
+    att = torch.empty((M, d), dtype=dt, device=dev)
+    hid = torch.empty((M, 4 * d), dtype=dt, device=dev)
+    ln_out = dict(out_f16=xn) if dt == torch.float16 else dict(out_bf16=xn)
+    for i, b in enumerate(blocks):
+        w = b if w16 is None else w16[i]
+        ops.layernorm(x, *b["ln1"], M, d, **ln_out)
+        ops.gemm_bf16(xn, w["w_in"], b["b_in"], "bf16", out=qkv)
         ops.attention(qkv, att, n_seq, Ltok, heads, causal=causal)
-        ops.gemm_bf16(att, b["w_out"], b["b_out"], resadd, out=x, res=x)
-        ops.layernorm(x, *b["ln2"], M, d, out_bf16=xn)
-        ops.gemm_bf16(xn, b["w_fc"], b["b_fc"], "bf16_qgelu", out=hid)
-        ops.gemm_bf16(hid, b["w_proj"], b["b_proj"], resadd, out=x, res=x)
+        ops.gemm_bf16(att, w["w_out"], b["b_out"], resadd, out=x, res=x)
+        ops.layernorm(x, *b["ln2"], M, d, **ln_out)
+        ops.gemm_bf16(xn, w["w_fc"], b["b_fc"], "bf16_qgelu", out=hid)
+        ops.gemm_bf16(hid, w["w_proj"], b["b_proj"], resadd, out=x, res=x)
     return x
 
 
@@ -211,6 +241,13 @@ class VisionTransformer(nn.Module):
         # ln_1 / ln_2 folded into the in_proj / c_fc GEMMs (fp16 stream only); EC_LN_FOLD=0 keeps the LayerNorm kernels
         self.fold_ln = os.environ.get("EC_LN_FOLD", "1") != "0"
         self._packed_ln, self._packed_ln_key = None, None
+        # 16-bit format of the tensor-core operands and of the activations between the GEMMs in the INFERENCE forward.  fp16 is
+        # what the reference itself runs on CUDA (clip.load keeps fp16 weights, test.py:26-29) and rounds 8 times finer than bf16
+        # at the same tcgen05 rate: on event frames the encoder's error relative to the part of the features that differs
+        # between samples drops accordingly (tests/test_bench_geometry_gpu.py).  EC_OPERANDS=bf16 selects bf16 (wider exponent
+        # range).  The fine-tune forward / backward (train.py) always uses bf16 operands and an fp32 residual stream.
+        self.operand_dtype = torch.bfloat16 if os.environ.get("EC_OPERANDS", "fp16") == "bf16" else torch.float16
+        self._packed16, self._packed16_key = None, None
         # bumped by everything that rewrites parameters behind the version counters' back (the fused optimizer kernel of
         # train.FineTuner writes through raw pointers): the LayerNorm-folded operands and captured graphs key on it
         self._epoch = 0
@@ -229,7 +266,13 @@ class VisionTransformer(nn.Module):
         """Call after mutating weights in a way the version counters cannot see (e.g. .data swaps)."""
         self._packed = None
         self._packed_ln = None
+        self._packed16 = None
         self._epoch += 1
+
+    @property
+    def patch_fmt(self):
+        """ec_event2img output format that feeds this tower's patch GEMM in the inference forward."""
+        return "patch_f16" if self.operand_dtype == torch.float16 else "patch"
 
     def mark_weights_changed(self):
         """Parameters were updated in place without touching their version counters (ec_adam on the flat buffer).  The
@@ -277,6 +320,32 @@ class VisionTransformer(nn.Module):
                         old_b[k].copy_(v)
             self._packed_ln_key = key
         return self._packed_ln
+
+    def packed_f16(self):
+        """fp16 copies of the GEMM weights for the fp16-operand inference forward (conv1, proj, per block in_proj / out_proj /
+        c_fc / c_proj with the LoRA factors merged).  Rebuilt -- into the same buffers, so captured graphs stay valid -- when a
+        parameter's version counter or the tower's epoch (mark_weights_changed) moves."""
+        key = (self._version_key(), self._epoch)
+        if self._packed16 is None or key != self._packed16_key:
+            d, P, dev = self.width, self.patch_size, self.proj.device
+            f32 = lambda t: t.detach().to(torch.float32)
+            w = f32(self.conv1.weight).reshape(d, 3 * P * P)
+            if self.k_patch != 3 * P * P:
+                wp = torch.zeros((d, self.k_patch), dtype=torch.float32, device=dev)
+                wp[:, :3 * P * P] = w
+                w = wp
+            new = dict(conv1=w.to(torch.float16).contiguous(), proj=f32(self.proj).t().to(torch.float16).contiguous(),
+                       blocks=pack_blocks_f16(self.transformer.resblocks, d, dev))
+            if self._packed16 is None:
+                self._packed16 = new
+            else:
+                self._packed16["conv1"].copy_(new["conv1"])
+                self._packed16["proj"].copy_(new["proj"])
+                for old_b, new_b in zip(self._packed16["blocks"], new["blocks"]):
+                    for k, v in new_b.items():
+                        old_b[k].copy_(v)
+            self._packed16_key = key
+        return self._packed16
 
     def packed_train(self):
         """packed() plus the transposed bf16 weights the data-gradient GEMMs read (dX = dY . W needs W^T K-major)."""
@@ -331,12 +400,17 @@ class VisionTransformer(nn.Module):
             from . import train
             return train.encode_patches_autograd(self, patches, n_img)
         pk = self.packed()
+        f16 = self.operand_dtype == torch.float16
+        if patches.dtype != self.operand_dtype:
+            raise L.ECError(f"patch rows are {patches.dtype} but this tower computes with {self.operand_dtype} operands "
+                            f"(ec_event2img out='{self.patch_fmt}'; EC_OPERANDS / visual.operand_dtype select the format)")
+        p16 = self.packed_f16() if f16 else None
         d, G2, heads = self.width, self.grid ** 2, self.heads
         Ltok = G2 + 1
         M = n_img * Ltok
         dev = patches.device
         x0 = torch.empty((M, d), dtype=torch.float32, device=dev)       # tokens before ln_pre
-        ops.gemm_bf16(patches, pk["conv1"], None, "patch", out=x0, res=pk["pos"], row_map=G2, M=n_img * G2)
+        ops.gemm_bf16(patches, p16["conv1"] if f16 else pk["conv1"], None, "patch", out=x0, res=pk["pos"], row_map=G2, M=n_img * G2)
         ops.cls_rows(x0, pk["cls"], pk["pos"], n_img, Ltok, d)
         # residual stream: fp16 like the reference's CUDA inference (test.py:26-29 keeps CLIP in fp16) or fp32
         if self.residual_dtype == torch.float16:
@@ -347,12 +421,12 @@ class VisionTransformer(nn.Module):
             ops.layernorm(x0, *pk["ln_pre"], M, d, out_f32=x)
         del x0
         if self.fold_ln and x.dtype == torch.float16 and ops.gemm_stats_parts(d) <= 8:
-            run_blocks_ln(x, pk["blocks"], self.packed_ln(), n_img, Ltok, d, heads)
+            run_blocks_ln(x, p16["blocks"] if f16 else pk["blocks"], self.packed_ln(), n_img, Ltok, d, heads)
         else:
-            run_blocks(x, pk["blocks"], n_img, Ltok, d, heads)
-        cls = torch.empty((n_img, d), dtype=torch.bfloat16, device=dev)
-        ops.layernorm(x, *pk["ln_post"], n_img, d, row_stride=Ltok * d, out_bf16=cls)
-        return ops.gemm_bf16(cls, pk["proj"], None, "f32")
+            run_blocks(x, pk["blocks"], n_img, Ltok, d, heads, w16=p16["blocks"] if f16 else None)
+        cls = torch.empty((n_img, d), dtype=self.operand_dtype, device=dev)
+        ops.layernorm(x, *pk["ln_post"], n_img, d, row_stride=Ltok * d, **(dict(out_f16=cls) if f16 else dict(out_bf16=cls)))
+        return ops.gemm_bf16(cls, p16["proj"] if f16 else pk["proj"], None, "f32")
 
     def forward(self, x):
         """x: CUDA [n,3,224,224] float32 / bfloat16 images (the reference's data_dict['img'] rows)."""
@@ -361,7 +435,8 @@ class VisionTransformer(nn.Module):
         n = x.shape[0]
         if n == 0:
             return torch.empty((0, self.output_dim), dtype=torch.float32, device=x.device)
-        patches = ops.im2col(x.contiguous(), self.patch_size, self.k_patch)
+        training = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        patches = ops.im2col(x.contiguous(), self.patch_size, self.k_patch, dtype=torch.bfloat16 if training else self.operand_dtype)
         return self.forward_patches(patches, n)
 
 

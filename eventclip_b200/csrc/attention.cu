@@ -207,7 +207,7 @@ extern "C" int ec_attention_ex(const void *qkv, void *out, int n_img, int L, int
         const int rc = ec::attention_tc(qkv, out, n_img, L, heads, causal, (cudaStream_t)stream);
         if (rc != EC_ERR_UNSUPPORTED) return rc;
     }
-    EC_REQUIRE(!causal, "ec_attention_ex: the causal mask is only built into the tensor-memory kernels (L <= 384)");
+    EC_REQUIRE(!causal, "ec_attention_ex: the causal mask and fp16 operands are only built into the tensor-memory kernels (L <= 384)");
     const int Lp = (L + 15) & ~15;
     const size_t smem = (size_t)3 * Lp * LDS * sizeof(__nv_bfloat16);
     EC_REQUIRE(smem <= 220 * 1024, "ec_attention: L=%d needs %zu bytes of shared memory", L, smem);

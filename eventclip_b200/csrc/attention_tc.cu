@@ -17,6 +17,8 @@
 
 #include <mutex>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -35,9 +37,20 @@ struct AttnParams {
     __nv_bfloat16 *out;
     float *lse;           // optional [n_img, heads, L]: log2-domain log-sum-exp of every row (kept for the backward pass)
     int L, heads, d, n_img, causal;
+    int f16;              // q, k, v, P and the output are fp16 instead of bf16 (the inference forward's fp16-operand mode)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// two fp32 values -> one packed 16-bit pair (low half = a), bf16 or fp16, round to nearest even
+__device__ __forceinline__ uint32_t pack16x2(float a, float b, int f16)
+{
+    if (f16) {
+        const __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<const uint32_t *>(&h);
+    }
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -190,7 +203,7 @@ __device__ __forceinline__ float fast_exp2(float x)
 template <uint32_t OCOL, uint32_t SUMCOL>
 __device__ __forceinline__ void softmax_tile(uint32_t lane_base, int L, int nch, bool live, int row, int lane, uint64_t *bar_p,
                                              uint64_t *bar_o, uint32_t o_parity, uint64_t *bar_oe, __nv_bfloat16 *orow,
-                                             int causal, float *lse_row)
+                                             int causal, float *lse_row, int f16)
 {
     float ms_keep = 0.f;
     const int klim = causal ? min(L, row + 1) : L;     // keys [0, klim) are visible to this row
@@ -222,8 +235,7 @@ __device__ __forceinline__ void softmax_tile(uint32_t lane_base, int L, int nch,
                                 if (c * 32 + j >= klim) x0 = -INFINITY;
                                 if (c * 32 + j + 1 >= klim) x1 = -INFINITY;
                             }
-                            __nv_bfloat162 hh = __floats2bfloat162_rn(fast_exp2(x0), fast_exp2(x1));
-                            pk[j >> 1] = *reinterpret_cast<uint32_t *>(&hh);
+                            pk[j >> 1] = pack16x2(fast_exp2(x0), fast_exp2(x1), f16);
                         }
                         tmem_st16(lane_base + (uint32_t)(c * 16), pk);
                     };
@@ -264,11 +276,10 @@ __device__ __forceinline__ void softmax_tile(uint32_t lane_base, int L, int nch,
     #pragma unroll
                         for (int j = 0; j < 32; j += 8) {
                             uint4 o;
-                            __nv_bfloat162 hh;
-                            hh = __floats2bfloat162_rn(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv); o.x = *reinterpret_cast<uint32_t *>(&hh);
-                            hh = __floats2bfloat162_rn(__uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv); o.y = *reinterpret_cast<uint32_t *>(&hh);
-                            hh = __floats2bfloat162_rn(__uint_as_float(v[j + 4]) * inv, __uint_as_float(v[j + 5]) * inv); o.z = *reinterpret_cast<uint32_t *>(&hh);
-                            hh = __floats2bfloat162_rn(__uint_as_float(v[j + 6]) * inv, __uint_as_float(v[j + 7]) * inv); o.w = *reinterpret_cast<uint32_t *>(&hh);
+                            o.x = pack16x2(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv, f16);
+                            o.y = pack16x2(__uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv, f16);
+                            o.z = pack16x2(__uint_as_float(v[j + 4]) * inv, __uint_as_float(v[j + 5]) * inv, f16);
+                            o.w = pack16x2(__uint_as_float(v[j + 6]) * inv, __uint_as_float(v[j + 7]) * inv, f16);
                             *reinterpret_cast<uint4 *>(orow + c * 32 + j) = o;
                         }
                     }
@@ -311,7 +322,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < ONES_BYTES / 4; i += NTHREADS) reinterpret_cast<uint32_t *>(sOnes)[i] = 0x3f803f80u;   // bf16 1.0 x2
+    for (int i = threadIdx.x; i < ONES_BYTES / 4; i += NTHREADS) reinterpret_cast<uint32_t *>(sOnes)[i] = p.f16 ? 0x3c003c00u : 0x3f803f80u;   // 1.0 x2 (fp16 / bf16)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
     tc_fence_before();
     __syncthreads();
@@ -332,10 +343,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
             mbar_expect_tx(&bar_v[stage], (uint32_t)(MT * TILE_BYTES));
             for (int b = 0; b < MT; ++b) tma_load_3d(sV + b * TILE_BYTES, &map_qkv, &bar_v[stage], 2 * d + h * HD, b * 128, img);
         };
-        // S: D fp32, A/B bf16 K-major, M = 128, N = KP.   O: B is MN-major (bit 16), N = 64.   sums: N = 16.
-        const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        const uint32_t idesc_1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        // S: D fp32, A/B bf16 (bits 7, 10) or fp16 K-major, M = 128, N = KP.   O: B is MN-major (bit 16), N = 64.   sums: N = 16.
+        const uint32_t FMT16 = p.f16 ? 0u : ((1u << 7) | (1u << 10));
+        const uint32_t idesc_s = (1u << 4) | FMT16 | ((uint32_t)(KP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc_o = (1u << 4) | FMT16 | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc_1 = (1u << 4) | FMT16 | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint64_t odesc = make_desc(smem_u32(sOnes));
         if ((int)blockIdx.x < n_units && elect_one()) load_unit(blockIdx.x, 0);
         __syncwarp();
@@ -399,7 +411,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
             tc_fence_after();
             softmax_tile<O_COL, SUM_COL>(lane_base, L, nch, live, row, lane, &bar_p[t], &bar_o[t], uph, &bar_oe[t],
                                          p.out + ((size_t)img * L + row) * d + h * HD, p.causal,
-                                         p.lse ? p.lse + (size_t)unit * L + row : nullptr);
+                                         p.lse ? p.lse + (size_t)unit * L + row : nullptr, p.f16);
         }
     }
 
@@ -447,7 +459,7 @@ attention_tc_big_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnP
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < ONES_BYTES / 4; i += BIG_NTHREADS) reinterpret_cast<uint32_t *>(sOnes)[i] = 0x3f803f80u;
+    for (int i = threadIdx.x; i < ONES_BYTES / 4; i += BIG_NTHREADS) reinterpret_cast<uint32_t *>(sOnes)[i] = p.f16 ? 0x3c003c00u : 0x3f803f80u;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
     __syncthreads();
@@ -469,10 +481,11 @@ attention_tc_big_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnP
             for (int b = 0; b < MT; ++b) tma_load_3d(sV + b * TILE_BYTES, &map_qkv, &bar_v, 2 * d + h * HD, b * 128, img);
         };
         const int n1 = KP < 256 ? KP : 256, n2 = KP - n1;          // S is issued in two column blocks
-        const uint32_t idesc_s1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n1 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        const uint32_t idesc_s2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n2 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        const uint32_t idesc_1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t FMT16 = p.f16 ? 0u : ((1u << 7) | (1u << 10));
+        const uint32_t idesc_s1 = (1u << 4) | FMT16 | ((uint32_t)(n1 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc_s2 = (1u << 4) | FMT16 | ((uint32_t)(n2 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc_o = (1u << 4) | FMT16 | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc_1 = (1u << 4) | FMT16 | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint64_t odesc = make_desc(smem_u32(sOnes));
         const uint64_t kdesc = make_desc(smem_u32(sK)), k2desc = make_desc(smem_u32(sK + 2 * TILE_BYTES));
         const uint64_t vdesc = make_desc(smem_u32(sV));
@@ -536,7 +549,7 @@ attention_tc_big_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnP
                 tc_fence_after();
                 softmax_tile<BIG_O_COL, BIG_SUM_COL>(lane_base, L, nch, live, row, lane, &bar_p, &bar_o, n & 1, &bar_oe,
                                                      p.out + ((size_t)img * L + row) * d + h * HD, p.causal,
-                                                     p.lse ? p.lse + (size_t)unit * L + row : nullptr);
+                                                     p.lse ? p.lse + (size_t)unit * L + row : nullptr, p.f16);
             }
         }
     }
@@ -892,7 +905,8 @@ int attention_tc(const void *qkv, void *out, int n_img, int L, int heads, int ca
         attr_set[dev_id] = true;
     }
     AttnParams p;
-    p.out = (__nv_bfloat16 *)out; p.lse = lse; p.L = L; p.heads = heads; p.d = d; p.n_img = n_img; p.causal = causal;
+    p.out = (__nv_bfloat16 *)out; p.lse = lse; p.L = L; p.heads = heads; p.d = d; p.n_img = n_img;
+    p.causal = causal & 1; p.f16 = (causal >> 1) & 1;       // EC_ATTN_CAUSAL | EC_ATTN_F16
     const int units = n_img * heads;
     const int grid = units < sm_count() ? units : sm_count();
     if (L > 256) attention_tc_big_kernel<<<grid, BIG_NTHREADS, smem_big, stream>>>(map, p);

@@ -260,7 +260,7 @@ __global__ void f32_to_bf16_kernel(const float *src, __nv_bfloat16 *dst, int64_t
 
 // NCHW [n,3,224,224] -> rows [n*G*G, ldk], column order (c, dy, dx) = conv1.weight.flatten(1) order.
 template <typename T>
-__global__ void im2col_kernel(const T *img, int n_img, int P, int G, int ldk, __nv_bfloat16 *out)
+__global__ void im2col_kernel(const T *img, int n_img, int P, int G, int ldk, __nv_bfloat16 *out, int out_f16)
 {
     const int K = 3 * P * P;
     const int64_t total = (int64_t)n_img * G * G * K;
@@ -271,7 +271,8 @@ __global__ void im2col_kernel(const T *img, int n_img, int P, int G, int ldk, __
         const int py = pr / G, px = pr % G;
         const int c = col / (P * P), dy = (col / P) % P, dx = col % P;
         const float v = (float)img[(((size_t)img_i * 3 + c) * 224 + py * P + dy) * 224 + px * P + dx];
-        out[row * ldk + col] = __float2bfloat16(v);
+        if (out_f16) reinterpret_cast<__half *>(out)[row * ldk + col] = __float2half_rn(v);
+        else out[row * ldk + col] = __float2bfloat16(v);
     }
 }
 
@@ -517,12 +518,13 @@ extern "C" int ec_im2col(const void *img, int in_is_bf16, int n_img, int patch, 
     const int G = 224 / patch;
     const int64_t total = (int64_t)n_img * G * G * 3 * patch * patch;
     const unsigned grid = (unsigned)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);
-    if (in_is_bf16)
+    const int out_f16 = (in_is_bf16 >> 1) & 1;
+    if (in_is_bf16 & 1)
         im2col_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)img, n_img, patch, G, ldk,
-                                                                              (__nv_bfloat16 *)out);
+                                                                              (__nv_bfloat16 *)out, out_f16);
     else
         im2col_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float *)img, n_img, patch, G, ldk,
-                                                                      (__nv_bfloat16 *)out);
+                                                                      (__nv_bfloat16 *)out, out_f16);
     EC_CUDA_CHECK(cudaGetLastError());
     return EC_OK;
 }

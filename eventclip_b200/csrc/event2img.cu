@@ -18,6 +18,7 @@
 //   P5  Pillow horizontal 8-bit bicubic pass for the 224 cropped columns -> band rows in smem
 //   P6  vertical pass reading neighbour bands through DSMEM, 256-entry normalise LUT, output store
 #include <cooperative_groups.h>
+#include <cuda_fp16.h>
 
 #include <map>
 #include <tuple>
@@ -63,6 +64,7 @@ struct E2IParams {
     // (checked on the host when the tables are built); affine = 0 falls back to the LUT
     float na[3], nb[3];
     int affine;
+    int f16;        // 16-bit outputs are fp16 instead of bf16 (EC_OUT_F16_PATCH; out_fmt then reads EC_OUT_BF16_PATCH for the layout)
     // band-exchange cluster kernel (event2img_big_kernel): byte offsets of its regions in dynamic shared memory, pitches of the
     // gray plane / the transposed horizontal result, events per CTA and exchange round, multiply-shift constant of y / RB
     int big_off_b, big_off_ht, big_gp, big_hpb, big_cap;
@@ -77,6 +79,17 @@ struct Part {            // per-CTA partial statistics exchanged over DSMEM
     unsigned mx;             // largest surviving count (second exchange, only when needed)
     unsigned flags;          // EC_STATUS_* bits seen by this CTA
 };
+
+// two fp32 values -> one packed 16-bit pair (low half = a), bf16 or fp16, round to nearest even
+__device__ __forceinline__ uint32_t pack16x2(float a, float b, int f16)
+{
+    if (f16) {
+        const __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<const uint32_t *>(&h);
+    }
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
 
 __device__ __forceinline__ float4 ld_stream(const float4 *p)
 {
@@ -388,9 +401,7 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
 
     for (int i = tid; i < 768; i += NT) nlut[i] = p.nlut[i];
     for (int i = tid; i < 256; i += NT) {
-        const __nv_bfloat162 c01 = __floats2bfloat162_rn(p.nlut[i], p.nlut[256 + i]);
-        const __nv_bfloat162 c2z = __floats2bfloat162_rn(p.nlut[512 + i], 0.f);
-        nlut3[i] = make_uint2(*reinterpret_cast<const uint32_t *>(&c01), *reinterpret_cast<const uint32_t *>(&c2z));
+        nlut3[i] = make_uint2(pack16x2(p.nlut[i], p.nlut[256 + i], p.f16), pack16x2(p.nlut[512 + i], 0.f, p.f16));
     }
     const bool vsm = p.KV <= 11;
     if (vsm)
@@ -787,8 +798,7 @@ __device__ __forceinline__ void emit8(const E2IParams &p, uint2 v, int yo, int x
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float2 r = ffma2(f[j], na, nb);
-                const __nv_bfloat162 h = __floats2bfloat162_rn(r.x, r.y);
-                w[c][j] = *reinterpret_cast<const uint32_t *>(&h);
+                w[c][j] = pack16x2(r.x, r.y, p.f16);
             }
         }
     } else {
@@ -869,9 +879,7 @@ __global__ void __launch_bounds__(1024, 1) event2img_tc_kernel(const E2IParams p
     if (p.out_fmt == EC_OUT_F32_NCHW)
         for (int i = tid; i < 768; i += NT) nlut[i] = p.nlut[i];
     for (int i = tid; i < 256; i += NT) {
-        const __nv_bfloat162 c01 = __floats2bfloat162_rn(p.nlut[i], p.nlut[256 + i]);
-        const __nv_bfloat162 c2z = __floats2bfloat162_rn(p.nlut[512 + i], 0.f);
-        nlut3[i] = make_uint2(*reinterpret_cast<const uint32_t *>(&c01), *reinterpret_cast<const uint32_t *>(&c2z));
+        nlut3[i] = make_uint2(pack16x2(p.nlut[i], p.nlut[256 + i], p.f16), pack16x2(p.nlut[512 + i], 0.f, p.f16));
     }
     {
         const int cw = wide ? 8 : 2;                // pixels per column group
@@ -952,8 +960,9 @@ __global__ void __launch_bounds__(1024, 1) event2img_tc_kernel(const E2IParams p
                     if (fl) atomicOr(p.status, (int)fl);
                 }
             } else {
-                // only (pos, neg) pairs up to the largest count are ever looked up
-                const int side = (int)min(mx, (unsigned)(GLUT_N - 1)) + 1;
+                // only (pos, neg) pairs up to the largest count are ever looked up.  This fill bets on "no bin exceeds the cut"
+                // (max = largest count); frames with large counts usually lose the bet, so it stops at 8 x 8 entries
+                const int side = (int)min(mx, 7u) + 1;
                 for (int k = tid - 32; k < side * side; k += NT - 32) {
                     const int neg = k / side, pos = k - neg * side;
                     glut[neg * GLUT_N + pos] = (uint8_t)gray_px(pos, neg, mx, mask);
@@ -964,13 +973,16 @@ __global__ void __launch_bounds__(1024, 1) event2img_tc_kernel(const E2IParams p
         const unsigned keep = s_keep;
         const bool hot = mx > keep;
         const unsigned mall = mx;         // largest raw count
-        // ---- P3 (only when some bin exceeds `keep`): max of the surviving bins, LUT again ----
+        // ---- P3 (only when some bin exceeds `keep`): max of the surviving bins ----
         if (hot) {
             unsigned m = 0;
             const uint4 *h4 = reinterpret_cast<const uint4 *>(hist);
             for (int i = tid; i < (HW >> 2); i += NT) {
                 const uint4 w4 = h4[i];
-                if ((w4.x | w4.y | w4.z | w4.w) == 0) continue;
+                const unsigned m4 = __vmaxu2(__vmaxu2(w4.x, w4.y), __vmaxu2(w4.z, w4.w));     // per-polarity maxima of the four pixels
+                if (m4 == 0) continue;
+                const unsigned hi = m4 >> 16, lo = m4 & 0xffffu;
+                if (max(hi, lo) <= keep) { m = max(m, max(hi, lo)); continue; }               // no field of the group is cut
                 const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -983,13 +995,28 @@ __global__ void __launch_bounds__(1024, 1) event2img_tc_kernel(const E2IParams p
             if (lane == 0) red32[wid][0] = m;
             __syncthreads();
             mx = warp_max_u32(lane < nwarps ? red32[lane][0] : 0u);
-            // the cut is folded into the LUT (a count above `keep` reads as 0); pairs up to the largest raw count occur
+        }
+        // ---- gray LUT for the final maximum: entries up to the cut are computed (fp64), the rest of the square that the raw
+        //      counts can index repeats them (a count above `keep` reads as 0).  Frames without a cut only extend the 8 x 8
+        //      entries filled above ----
+        {
             const int side = (int)min(mall, (unsigned)(GLUT_N - 1)) + 1;
-            for (int k = tid; k < side * side; k += NT) {
-                const unsigned ln = k / side, lp = k - ln * side;
-                glut[ln * GLUT_N + lp] = (uint8_t)gray_px(lp > keep ? 0u : lp, ln > keep ? 0u : ln, mx, mask);
+            const int kside = (int)min((unsigned)(side - 1), keep) + 1;                       // distinct surviving counts per axis
+            if (hot || side > 8) {
+                const int skip = hot ? 0 : 8;                                                 // not hot: [0,8) x [0,8) is already there
+                for (int k = tid; k < kside * kside; k += NT) {
+                    const int ln = k / kside, lp = k - ln * kside;
+                    if (ln >= skip || lp >= skip) glut[ln * GLUT_N + lp] = (uint8_t)gray_px(lp, ln, mx, mask);
+                }
+                __syncthreads();
+                if (kside < side) {
+                    for (int k = tid; k < side * side; k += NT) {
+                        const int ln = k / side, lp = k - ln * side;
+                        if (ln >= kside || lp >= kside) glut[ln * GLUT_N + lp] = glut[(ln >= kside ? 0 : ln) * GLUT_N + (lp >= kside ? 0 : lp)];
+                    }
+                }
+                __syncthreads();
             }
-            __syncthreads();
         }
 
         // ---- P4: gray byte per pixel (small counts through the LUT) into its own plane ----
@@ -1226,6 +1253,8 @@ __global__ void __launch_bounds__(BIG_NT, 1) event2img_big_kernel(const E2IParam
     const bool cnz = (p.flags & EC_FLAG_COUNT_NON_ZERO) != 0;
     const int W4 = W >> 2;
     const int n16 = (RB * W) >> 2;                      // 16-byte groups of the bins (RB * W is a multiple of 4)
+    const unsigned uHW = (unsigned)HW;                  // < 2^24 (big_plan)
+    const unsigned owner_magic = (unsigned)p.band_magic;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *bins = reinterpret_cast<uint32_t *>(smem_raw);
@@ -1234,7 +1263,7 @@ __global__ void __launch_bounds__(BIG_NT, 1) event2img_big_kernel(const E2IParam
     uint8_t *hT = smem_raw + p.big_off_ht;              // [224][HPB]: the band's rows of the horizontal result, transposed
     __shared__ BigPart part;
     __shared__ uint32_t s_seg[16];                      // (first word, words) of this CTA's list for each owner band
-    __shared__ uint32_t s_cnt[NW * 8], s_base[NW * 8], s_tot[8];
+    __shared__ uint32_t s_cnt[NW * 8], s_base[NW * 8];
     __shared__ unsigned long long red64[NW];
     __shared__ unsigned red32[NW][12];
     __shared__ unsigned s_keep, s_mx, s_mall, s_need_pass, s_nsus_tot, s_nacc;
@@ -1253,9 +1282,7 @@ __global__ void __launch_bounds__(BIG_NT, 1) event2img_big_kernel(const E2IParam
     const int frame_elems = p.out_fmt == EC_OUT_BF16_PATCH ? p.G * p.G * p.ldk : 3 * OUT * OUT;
 
     for (int i = tid; i < 256; i += NT) {
-        const __nv_bfloat162 c01 = __floats2bfloat162_rn(p.nlut[i], p.nlut[256 + i]);
-        const __nv_bfloat162 c2z = __floats2bfloat162_rn(p.nlut[512 + i], 0.f);
-        nlut3[i] = make_uint2(*reinterpret_cast<const uint32_t *>(&c01), *reinterpret_cast<const uint32_t *>(&c2z));
+        nlut3[i] = make_uint2(pack16x2(p.nlut[i], p.nlut[256 + i], p.f16), pack16x2(p.nlut[512 + i], 0.f, p.f16));
     }
     {
         const int cw = wide ? 8 : 2;
@@ -1266,6 +1293,7 @@ __global__ void __launch_bounds__(BIG_NT, 1) event2img_big_kernel(const E2IParam
         for (int i = tid; i < 2 * MT; i += NT) s_ws[i] = i < MT ? p.wsH[i] : p.wsV[i - MT];
         uint4 *b4 = reinterpret_cast<uint4 *>(bins);
         for (int i = tid; i < n16; i += NT) b4[i] = make_uint4(0, 0, 0, 0);
+        if (tid < NW * 8) s_cnt[tid] = 0;
     }
     cluster.sync();        // every CTA of the cluster runs before anyone touches a peer's shared memory
 
@@ -1291,35 +1319,44 @@ __global__ void __launch_bounds__(BIG_NT, 1) event2img_big_kernel(const E2IParam
     };
     // cluster totals -> hot-pixel cut, largest surviving count (or the request for a pass over the bins)
     auto derive = [&]() {
-        if (tid == 0) {
-            unsigned long long S1 = 0, S2 = 0;
+        if (wid == 0) {
+            // lane r < CS fetches CTA r's partials over DSMEM (all in flight at once), the warp reduces them
+            BigPart q;
+            q.s2 = 0; q.nacc = q.mall = q.flags = q.nsus = 0;
+#pragma unroll
+            for (int v = 0; v < 8; ++v) q.ge[v] = 0;
+            if (lane < CS) q = *cluster.map_shared_rank(&part, lane);
+            const unsigned long long S2 = warp_sum_u64(q.s2);
+            const unsigned long long S1 = warp_sum_u64((unsigned long long)q.nacc);
             unsigned long long GE[9];
-            for (int v = 0; v < 9; ++v) GE[v] = 0;
-            unsigned M = 0, fl = 0, ns = 0;
-            for (int r = 0; r < CS; ++r) {
-                const BigPart *q = cluster.map_shared_rank(&part, r);
-                S1 += q->nacc; S2 += q->s2; M = max(M, q->mall); fl |= q->flags; ns += q->nsus;
-                for (int v = 0; v < 8; ++v) GE[v] += q->ge[v];
+#pragma unroll
+            for (int v = 0; v < 8; ++v) GE[v] = warp_sum_u64((unsigned long long)q.ge[v]);
+            GE[8] = 0;
+            const unsigned M = warp_max_u32(q.mall), ns = warp_sum_u32(q.nsus);
+            const unsigned fl = __reduce_or_sync(0xffffffffu, q.flags);
+            if (lane == 0) {
+                const unsigned long long n = cnz ? GE[0] : (unsigned long long)HW * 2ull;
+                const unsigned keep = compute_keep_small(n, S1, S2, 10);
+                unsigned mx = M, need = 0;
+                if (M > keep) {
+                    if (keep <= 7u) {
+                        mx = 0;
+                        for (int v = (int)keep; v >= 1; --v)
+                            if (GE[v - 1] > GE[v]) { mx = (unsigned)v; break; }      // some field ended at exactly v
+                    } else
+                        need = 1;
+                }
+                s_keep = keep; s_mall = M; s_mx = mx; s_need_pass = need; s_nsus_tot = ns;
+                if (rank == 0 && fl) atomicOr(p.status, (int)fl);
             }
-            const unsigned long long n = cnz ? GE[0] : (unsigned long long)HW * 2ull;
-            const unsigned keep = compute_keep_small(n, S1, S2, 10);
-            unsigned mx = M, need = 0;
-            if (M > keep) {
-                if (keep <= 7u) {
-                    mx = 0;
-                    for (int v = (int)keep; v >= 1; --v)
-                        if (GE[v - 1] > GE[v]) { mx = (unsigned)v; break; }      // some field ended at exactly v
-                } else
-                    need = 1;
-            }
-            s_keep = keep; s_mall = M; s_mx = mx; s_need_pass = need; s_nsus_tot = ns;
-            if (rank == 0 && fl) atomicOr(p.status, (int)fl);
         }
         __syncthreads();
     };
 
+    ec_frame fr_next = p.frames[min((int)(blockIdx.x / CS), p.n_frames - 1)];
     for (int fid = blockIdx.x / CS; fid < p.n_frames; fid += n_clusters) {
-        const ec_frame fr = p.frames[fid];
+        const ec_frame fr = fr_next;
+        fr_next = p.frames[min(fid + n_clusters, p.n_frames - 1)];       // in flight during this frame
         const int slot = fr.out_slot;
         // ---- padding frame: the reference pads missing views with zeros (event2img.py:89-91) ----
         if (fr.ev_count <= 0) {
@@ -1355,8 +1392,6 @@ __global__ void __launch_bounds__(BIG_NT, 1) event2img_big_kernel(const E2IParam
             const int e_lo = min(rank * per, n_round);
             const int n = min(per, n_round - e_lo);
             // ================= S1: decode this CTA's slice, count by owner, sort into the word list =================
-            if (tid < NW * 8) s_cnt[tid] = 0;
-            __syncthreads();
             const int pw = ((((n + 31) >> 5) + 31) >> 5) << 5;       // events per warp: a multiple of 32, <= 32 * KMAX
             const int w_lo = wid * pw;
             const int w_n = max(0, min(pw, n - w_lo));
@@ -1387,7 +1422,7 @@ __global__ void __launch_bounds__(BIG_NT, 1) event2img_big_kernel(const E2IParam
                             const unsigned pc = wc[j] >> 30;
                             l = wc[j] & 0x3fffffffu;
                             neg = pc == 2u;
-                            take = (pc == 1u || pc == 2u) && (long long)l < HW;
+                            take = (pc == 1u || pc == 2u) && l < uHW;
                             if (pc == 3u || (pc != 0u && !take)) flags |= EC_STATUS_BAD_COORD;
                         } else {
                             // .astype(int) truncates: trunc(p) != 0 <=> |p| >= 1 (vis.py:44-52); a NaN polarity is dropped like p == 0
@@ -1395,7 +1430,7 @@ __global__ void __launch_bounds__(BIG_NT, 1) event2img_big_kernel(const E2IParam
                             const bool pos = ev[j].w >= 1.0f;
                             neg = ev[j].w <= -1.0f;
                             l = (unsigned)(ys * W + xs);              // flat index as np.bincount sees it; exact in 32 bits for x, y, W < 2^15
-                            bool ok = (unsigned)(xs | ys) < 32768u && (long long)l < HW;
+                            bool ok = (unsigned)(xs | ys) < 32768u && l < uHW;
                             if (!ok) {                                // rare: negative / huge coordinates whose flat index may still be in range
                                 const long long i64 = (long long)xs + (long long)ys * W;
                                 ok = i64 >= 0 && i64 < HW;
@@ -1405,7 +1440,7 @@ __global__ void __launch_bounds__(BIG_NT, 1) event2img_big_kernel(const E2IParam
                             if (!ok && (pos || neg)) flags |= EC_STATUS_BAD_COORD;    // p == 0 events are never range-checked
                         }
                         if (take && 32 * k + lane < w_n) {
-                            const unsigned owner = (unsigned)(((unsigned long long)l * p.band_magic) >> 40);   // l / (RB * W)
+                            const unsigned owner = __umulhi(l, owner_magic) >> 4;      // l / (RB * W): ceil(2^36 / d), checked on the host
                             const unsigned local = l - owner * bandpx;
                             const unsigned pos_in = atomicAdd(&s_cnt[wid * 8 + owner], 1u);
                             pk[k] = local | (neg << 16) | (owner << 17) | (pos_in << 20) | 0x80000000u;
@@ -1414,25 +1449,25 @@ __global__ void __launch_bounds__(BIG_NT, 1) event2img_big_kernel(const E2IParam
                 }
             }
             __syncthreads();
-            if (tid < 256) {           // warp o scans the counters of owner o over the 32 producer warps
-                const int o = tid >> 5;
-                const unsigned v = s_cnt[lane * 8 + o];
-                unsigned incl = v;
+            if (wid == 0) {
+                // one warp turns the 32 x 8 counters into list offsets in owner-major, warp-minor order: lane q covers the eight
+                // consecutive entries (owner q / 4, producer warps 8 (q % 4) .. + 7); the counters are left zeroed for the next round
+                const int o = lane >> 2, w0 = 8 * (lane & 3);
+                unsigned v[8], tot = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { v[i] = s_cnt[(w0 + i) * 8 + o]; s_cnt[(w0 + i) * 8 + o] = 0; tot += v[i]; }
+                unsigned incl = tot;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
                     const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
                     if (lane >= d) incl += t;
                 }
-                s_base[lane * 8 + o] = incl - v;
-                if (lane == 31) s_tot[o] = incl;
-            }
-            __syncthreads();
-            if (tid < 256) {
-                const int o = tid >> 5;
-                unsigned start = 0;
-                for (int q = 0; q < o; ++q) start += s_tot[q];
-                s_base[lane * 8 + o] += start;
-                if (lane == 0) { s_seg[2 * o] = start; s_seg[2 * o + 1] = s_tot[o]; }
+                unsigned run = incl - tot;
+                const unsigned ostart = __shfl_sync(0xffffffffu, run, lane & ~3);     // first entry of this owner
+                const unsigned oend = __shfl_sync(0xffffffffu, incl, lane | 3);
+                if ((lane & 3) == 0) { s_seg[2 * o] = ostart; s_seg[2 * o + 1] = oend - ostart; }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { s_base[(w0 + i) * 8 + o] = run; run += v[i]; }
             }
             __syncthreads();
 #pragma unroll
@@ -1467,7 +1502,7 @@ __global__ void __launch_bounds__(BIG_NT, 1) event2img_big_kernel(const E2IParam
                     unsigned old[4], inc[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        inc[u] = v[u] ? ((w[u] >> 16) ? 65536u : 1u) : 0u;
+                        inc[u] = v[u] ? 1u + (w[u] >> 16) * 65535u : 0u;
                         old[u] = 0;
                         if (all4 || v[u])
                             asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old[u]) : "r"(bins_s + 4u * (w[u] & 0xffffu)), "r"(inc[u]) : "memory");
@@ -1475,7 +1510,7 @@ __global__ void __launch_bounds__(BIG_NT, 1) event2img_big_kernel(const E2IParam
                     unsigned s2p = 0;
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const unsigned c = __byte_perm(old[u], 0u, inc[u] == 65536u ? 0x4432u : 0x4410u);
+                        const unsigned c = __byte_perm(old[u], 0u, 0x4410u + (w[u] >> 16) * 0x22u);      // the incremented field
                         const unsigned on = all4 ? 1u : (unsigned)v[u];
                         s2p += (2u * c + 1u) * on;
                         mall = max(mall, (c + 1u) * on);
@@ -1556,7 +1591,10 @@ __global__ void __launch_bounds__(BIG_NT, 1) event2img_big_kernel(const E2IParam
             const uint4 *h4 = reinterpret_cast<const uint4 *>(bins);
             for (int i = tid; i < ((nband + 3) >> 2); i += NT) {
                 const uint4 w4 = h4[i];
-                if ((w4.x | w4.y | w4.z | w4.w) == 0) continue;
+                const unsigned m4 = __vmaxu2(__vmaxu2(w4.x, w4.y), __vmaxu2(w4.z, w4.w));
+                if (m4 == 0) continue;
+                const unsigned hi = m4 >> 16, lo = m4 & 0xffffu;
+                if (nsus == 0 && max(hi, lo) <= keep) { m = max(m, max(hi, lo)); continue; }
                 const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -1587,11 +1625,19 @@ __global__ void __launch_bounds__(BIG_NT, 1) event2img_big_kernel(const E2IParam
 
         // ================= P4: per-frame gray LUT (the cut folded in), gray byte per pixel =================
         {
+            // entries up to the cut are computed (fp64); the rest of the square the raw counts can index repeats them
             const int side = (int)min(mall_all, (unsigned)(GLUT_N - 1)) + 1;
-            for (int k = tid; k < side * side; k += NT) {
-                const unsigned ln = k / side, lp = k - ln * side;
-                glut[ln * GLUT_N + lp] = (uint8_t)gray_px(lp > keep ? 0u : lp, ln > keep ? 0u : ln, mx, mask);
+            const int kside = (int)min((unsigned)(side - 1), keep) + 1;
+            for (int k = tid; k < kside * kside; k += NT) {
+                const int ln = k / kside, lp = k - ln * kside;
+                glut[ln * GLUT_N + lp] = (uint8_t)gray_px(lp, ln, mx, mask);
             }
+            __syncthreads();
+            if (kside < side)
+                for (int k = tid; k < side * side; k += NT) {
+                    const int ln = k / side, lp = k - ln * side;
+                    if (ln >= kside || lp >= kside) glut[ln * GLUT_N + lp] = glut[(ln >= kside ? 0 : ln) * GLUT_N + (lp >= kside ? 0 : lp)];
+                }
         }
         __syncthreads();
         {
@@ -1650,7 +1696,7 @@ __global__ void __launch_bounds__(BIG_NT, 1) event2img_big_kernel(const E2IParam
         if (nsus > 0) __syncthreads();
         // while this frame is resampled and stored, pull this CTA's first slice of the NEXT frame's events into L2
         if (fid + n_clusters < p.n_frames) {
-            const ec_frame nx = p.frames[fid + n_clusters];
+            const ec_frame nx = fr_next;
             if (nx.ev_count > 0) {
                 const int n_round = min(round_cap, nx.ev_count);
                 const int per = (n_round + CS - 1) / CS;
@@ -1842,6 +1888,8 @@ struct Tables {
     int KSH = 0, KSV = 0;
     float na[3] = {0, 0, 0}, nb[3] = {0, 0, 0};
     int affine = 0;
+    float na16[3] = {0, 0, 0}, nb16[3] = {0, 0, 0};      // the same for fp16 outputs
+    int affine16 = 0;
 };
 
 // signed base-256 digits of a Pillow coefficient (|k| < 2^23): k = d0 + 256 d1 + 65536 d2, each in [-128, 127]
@@ -1916,7 +1964,7 @@ bool tc_plan(int H, int W, int CS, int KSH, int KSV, size_t &smem, int &gray_off
     if (region_a < (size_t)OUT * HP) region_a = (size_t)OUT * HP;
     region_a = (region_a + 15) & ~(size_t)15;
     const size_t gray_bytes = ((size_t)(H + 8) * W + 32 + 15) & ~(size_t)15;       // last row tile reads up to 7 rows + 31 bytes past the plane
-    if (off || CS != 1 || W % 4 != 0 || H < 16 || KSH != 1 || KSV != 1 || region_a + gray_bytes > (size_t)221 * 1024) return false;
+    if (off || CS != 1 || W % 4 != 0 || H < 16 || KSH != 1 || KSV != 1 || region_a + gray_bytes > (size_t)218 * 1024) return false;     // + 8.4 KB of static tables <= 227 KB
     smem = region_a + gray_bytes;
     gray_off = (int)region_a;
     return true;
@@ -1940,7 +1988,7 @@ bool big_plan(int H, int W, int KSH, int KSV, bool fits_one_cta, BigPlan &bp)
     if (mode && atoi(mode) == 0 && !force) return false;
     if (fits_one_cta && !force) return false;
     if (W % 4 != 0 || H < 16 || W < 64 || KSH < 1 || KSH > 2 || KSV < 1 || KSV > 2 || (long long)H * W >= (1 << 24)) return false;
-    const size_t limit = (size_t)227 * 1024 - 9 * 1024;        // static shared memory of the kernel: ~8.7 KB
+    const size_t limit = (size_t)227 * 1024 - 10 * 1024;       // static shared memory of the kernel: 9.5 KB
     for (int CS = 2; CS <= 8; CS *= 2) {
         const int RB = (((H + CS - 1) / CS) + 3) & ~3;
         if ((long long)RB * (CS - 1) >= H) continue;           // the last band would be empty
@@ -1970,9 +2018,10 @@ bool big_plan(int H, int W, int KSH, int KSV, bool fits_one_cta, BigPlan &bp)
         bp.rb_magic = (unsigned)(((1u << 20) + (unsigned)RB - 1) / (unsigned)RB);
         for (unsigned y = 0; y < (unsigned)(CS * RB + 128); ++y)                 // the multiply-shift division is exact where it is used
             if (((y * bp.rb_magic) >> 20) != y / (unsigned)RB) return false;
-        const unsigned long long d = (unsigned long long)RB * W, magic = ((1ull << 40) + d - 1) / d;
+        const unsigned long long d = (unsigned long long)RB * W, magic = ((1ull << 36) + d - 1) / d;     // owner = (l * magic) >> 36
+        if (magic >> 32) return false;
         for (unsigned long long k = 1; k <= (unsigned long long)CS; ++k)
-            if ((((k * d - 1) * magic) >> 40) != k - 1 || (((k * d) * magic) >> 40) != k) return false;
+            if ((((k * d - 1) * magic) >> 36) != k - 1 || (((k * d) * magic) >> 36) != k) return false;
         return true;
     }
     return false;
@@ -2009,31 +2058,37 @@ int get_tables(int H, int W, cudaStream_t stream, Tables &out)
             memcpy(&bits, &rf, 4);
             all.push_back(bits);
         }
-    // one fma per channel that reproduces the bf16 rounding of the LUT above for every byte value (else: keep the LUT)
+    // one fma per channel that reproduces the 16-bit rounding (bf16, fp16) of the LUT above for every byte value (else: keep the LUT)
     {
-        auto bf16_bits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16); };
-        t.affine = 1;
-        for (int c = 0; c < 3 && t.affine; ++c) {
-            const float a0 = (float)(1.0 / (255.0 * (double)stdv[c])), b0 = (float)(-(double)mean[c] / (double)stdv[c]);
-            bool found = false;
-            for (int r = 0; r <= 4 && !found; ++r)          // nudge a / b by a few ulps if the nominal pair misses a rounding boundary
-                for (int da = -r; da <= r && !found; ++da)
-                    for (int db = -r; db <= r && !found; ++db) {
-                        if (std::max(std::abs(da), std::abs(db)) != r) continue;
-                        float a = a0, b = b0;
-                        for (int k = 0; k < std::abs(da); ++k) a = std::nextafterf(a, da > 0 ? INFINITY : -INFINITY);
-                        for (int k = 0; k < std::abs(db); ++k) b = std::nextafterf(b, db > 0 ? INFINITY : -INFINITY);
-                        bool ok = true;
-                        for (int v = 0; v < 256 && ok; ++v) {
-                            float lut;
-                            memcpy(&lut, &all[t.off_lut + (size_t)c * 256 + v], 4);
-                            ok = bf16_bits(fmaf((float)v, a, b)) == bf16_bits(lut);
+        auto bf16_bits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return (uint32_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16); };
+        auto f16_bits = [](float f) { return (uint32_t)__half_as_ushort(__float2half_rn(f)); };
+        for (int fmt = 0; fmt < 2; ++fmt) {
+            int ok_all = 1;
+            float *pa = fmt ? t.na16 : t.na, *pb = fmt ? t.nb16 : t.nb;
+            for (int c = 0; c < 3 && ok_all; ++c) {
+                const float a0 = (float)(1.0 / (255.0 * (double)stdv[c])), b0 = (float)(-(double)mean[c] / (double)stdv[c]);
+                bool found = false;
+                for (int r = 0; r <= 4 && !found; ++r)          // nudge a / b by a few ulps if the nominal pair misses a rounding boundary
+                    for (int da = -r; da <= r && !found; ++da)
+                        for (int db = -r; db <= r && !found; ++db) {
+                            if (std::max(std::abs(da), std::abs(db)) != r) continue;
+                            float a = a0, b = b0;
+                            for (int k = 0; k < std::abs(da); ++k) a = std::nextafterf(a, da > 0 ? INFINITY : -INFINITY);
+                            for (int k = 0; k < std::abs(db); ++k) b = std::nextafterf(b, db > 0 ? INFINITY : -INFINITY);
+                            bool ok = true;
+                            for (int v = 0; v < 256 && ok; ++v) {
+                                float lut;
+                                memcpy(&lut, &all[t.off_lut + (size_t)c * 256 + v], 4);
+                                const float y = fmaf((float)v, a, b);
+                                ok = fmt ? f16_bits(y) == f16_bits(lut) : bf16_bits(y) == bf16_bits(lut);
+                            }
+                            if (ok) { pa[c] = a; pb[c] = b; found = true; }
                         }
-                        if (ok) { t.na[c] = a; t.nb[c] = b; found = true; }
-                    }
-            if (!found) t.affine = 0;
+                if (!found) ok_all = 0;
+            }
+            if (getenv("EC_E2I_AFFINE") && atoi(getenv("EC_E2I_AFFINE")) == 0) ok_all = 0;     // experiment hook
+            (fmt ? t.affine16 : t.affine) = ok_all;
         }
-        if (getenv("EC_E2I_AFFINE") && atoi(getenv("EC_E2I_AFFINE")) == 0) t.affine = 0;     // experiment hook
     }
     {
         std::vector<int32_t> fh, fv, wh, wv;
@@ -2175,7 +2230,9 @@ static int event2img_impl(const float *events, const uint32_t *events_c, const e
     if (n_frames == 0) return EC_OK;
     EC_REQUIRE(frames && out && status, "ec_event2img: null pointer");
     EC_REQUIRE(H > 0 && W > 0 && H >= 8 && W >= 8, "ec_event2img: bad sensor shape %dx%d", H, W);
-    EC_REQUIRE(out_fmt >= EC_OUT_F32_NCHW && out_fmt <= EC_OUT_BF16_PATCH, "ec_event2img: bad out_fmt %d", out_fmt);
+    EC_REQUIRE(out_fmt >= EC_OUT_F32_NCHW && out_fmt <= EC_OUT_F16_PATCH, "ec_event2img: bad out_fmt %d", out_fmt);
+    const int f16 = out_fmt == EC_OUT_F16_PATCH;
+    if (f16) out_fmt = EC_OUT_BF16_PATCH;      // same layout; the kernels pick the 16-bit format from E2IParams::f16
     int G = 0;
     if (out_fmt == EC_OUT_BF16_PATCH) {
         EC_REQUIRE(patch > 0 && patch % 2 == 0 && OUT % patch == 0, "ec_event2img: patch %d must be even and divide 224", patch);
@@ -2205,8 +2262,9 @@ static int event2img_impl(const float *events, const uint32_t *events_c, const e
     p.fragH = tb.dev + tb.off_fragH; p.fragV = tb.dev + tb.off_fragV; p.wsH = tb.dev + tb.off_wsH; p.wsV = tb.dev + tb.off_wsV;
     p.KSH = tb.KSH; p.KSV = tb.KSV;
     p.gray_off = 0;
-    for (int c = 0; c < 3; ++c) { p.na[c] = tb.na[c]; p.nb[c] = tb.nb[c]; }
-    p.affine = tb.affine;
+    for (int c = 0; c < 3; ++c) { p.na[c] = f16 ? tb.na16[c] : tb.na[c]; p.nb[c] = f16 ? tb.nb16[c] : tb.nb[c]; }
+    p.affine = f16 ? tb.affine16 : tb.affine;
+    p.f16 = f16;
     p.band_magic = ((1ull << 40) + (unsigned long long)RB * W - 1) / ((unsigned long long)RB * W);
     p.big_off_b = p.big_off_ht = p.big_gp = p.big_hpb = p.big_cap = 0;
     p.big_rb_magic = 0;
@@ -2223,7 +2281,7 @@ static int event2img_impl(const float *events, const uint32_t *events_c, const e
         p.CS = CS; p.RB = RB;
         p.big_off_b = bp.off_b; p.big_off_ht = bp.off_ht; p.big_gp = bp.gp; p.big_hpb = bp.hpb; p.big_cap = bp.cap;
         p.big_rb_magic = bp.rb_magic;
-        p.band_magic = ((1ull << 40) + (unsigned long long)RB * W - 1) / ((unsigned long long)RB * W);
+        p.band_magic = ((1ull << 36) + (unsigned long long)RB * W - 1) / ((unsigned long long)RB * W);     // 32-bit, __umulhi(l, magic) >> 4
         kern = events_c ? (dbg ? event2img_big_kernel<true, true> : event2img_big_kernel<false, true>)
                         : (dbg ? event2img_big_kernel<true, false> : event2img_big_kernel<false, false>);
     } else if (tc)

@@ -55,6 +55,7 @@ struct GemmParams {
                           //    arrive as boxes of 64 (m or n) x 64 (k), one 8 KB box per 64 rows of the tile
     // LayerNorm folded into the GEMMs (ec_gemm_ln / ec_gemm_bf16_stats):
     int a_f16;                 // both operands hold fp16 (A = the residual stream itself, W = fp16(gamma * W)) instead of bf16
+    int out_f16;               // EC_EPI_BF16 / EC_EPI_BF16_QGELU write fp16 instead of bf16 (EC_EPI_F16_OPERANDS)
     const float2 *ln_stats;    // consumer: [M, ln_parts] partial (sum x, sum x^2) of every row of A; NULL = plain epilogue
     int ln_parts;
     const float *ln_colsum;    // consumer: s_j = sum_k W'[j,k] of the gamma-scaled weight; `bias` holds c_j = beta . W[j] + b_j
@@ -64,6 +65,17 @@ struct GemmParams {
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// two fp32 values -> one packed 16-bit pair (low half = a), bf16 or fp16, round to nearest even
+__device__ __forceinline__ uint32_t pack16x2(float a, float b, int f16)
+{
+    if (f16) {
+        const __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<const uint32_t *>(&h);
+    }
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
@@ -513,16 +525,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     for (int q = 0; q < 8; ++q) {
                         const float f0 = fmaf(__uint_as_float(v[4 * q]), ln_r, bq[q].x), f1 = fmaf(__uint_as_float(v[4 * q + 1]), ln_r, bq[q].y);
                         const float f2 = fmaf(__uint_as_float(v[4 * q + 2]), ln_r, bq[q].z), f3 = fmaf(__uint_as_float(v[4 * q + 3]), ln_r, bq[q].w);
-                        __nv_bfloat162 h0, h1;
                         if (p.epi == EC_EPI_BF16_QGELU) {
-                            h0 = __floats2bfloat162_rn(quick_gelu(f0), quick_gelu(f1));
-                            h1 = __floats2bfloat162_rn(quick_gelu(f2), quick_gelu(f3));
+                            pk[2 * q] = pack16x2(quick_gelu(f0), quick_gelu(f1), p.out_f16);
+                            pk[2 * q + 1] = pack16x2(quick_gelu(f2), quick_gelu(f3), p.out_f16);
                         } else {
-                            h0 = __floats2bfloat162_rn(f0, f1);
-                            h1 = __floats2bfloat162_rn(f2, f3);
+                            pk[2 * q] = pack16x2(f0, f1, p.out_f16);
+                            pk[2 * q + 1] = pack16x2(f2, f3, p.out_f16);
                         }
-                        pk[2 * q] = *reinterpret_cast<uint32_t *>(&h0);
-                        pk[2 * q + 1] = *reinterpret_cast<uint32_t *>(&h1);
                     }
                     const uint32_t box = stg + (nbox & 1) * 2048;
                     if (lane == 0) bulk_wait_read<1>();       // the store issued two boxes ago has drained this buffer
@@ -798,11 +807,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                                     for (int e = 0; e < 8; ++e) f[e] = quick_gelu(f[e]);
                                 }
                                 uint4 o;
-                                __nv_bfloat162 h;
-                                h = __floats2bfloat162_rn(f[0], f[1]); o.x = *reinterpret_cast<uint32_t *>(&h);
-                                h = __floats2bfloat162_rn(f[2], f[3]); o.y = *reinterpret_cast<uint32_t *>(&h);
-                                h = __floats2bfloat162_rn(f[4], f[5]); o.z = *reinterpret_cast<uint32_t *>(&h);
-                                h = __floats2bfloat162_rn(f[6], f[7]); o.w = *reinterpret_cast<uint32_t *>(&h);
+                                o.x = pack16x2(f[0], f[1], p.out_f16); o.y = pack16x2(f[2], f[3], p.out_f16);
+                                o.z = pack16x2(f[4], f[5], p.out_f16); o.w = pack16x2(f[6], f[7], p.out_f16);
                                 *reinterpret_cast<uint4 *>((__nv_bfloat16 *)p.out + (size_t)r * p.ldo + col) = o;
                             }
                         }
@@ -970,8 +976,8 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float4 *__rest
     }
 }
 
-struct GemmExtra {            // LayerNorm folded into the GEMMs
-    int a_f16 = 0;
+struct GemmExtra {            // LayerNorm folded into the GEMMs; fp16 operand / output mode
+    int a_f16 = 0, out_f16 = 0;
     const float *ln_stats = nullptr, *ln_colsum = nullptr;
     int ln_parts = 0;
     float *stats_out = nullptr;
@@ -983,11 +989,12 @@ int gemm_impl(const void *A, int lda, const void *W, int ldw, const float *bias,
 }  // namespace
 
 extern "C" int ec_gemm_bf16_stats(const void *A, int lda, const void *W, int ldw, const float *bias, int M, int N, int K, void *out,
-                                  int ldo, const void *res, float *stats_out, void *stream_)
+                                  int ldo, const void *res, float *stats_out, int f16_operands, void *stream_)
 {
     EC_REQUIRE(stats_out && ((uintptr_t)stats_out & 7) == 0, "ec_gemm_bf16_stats: stats_out must be an 8-byte aligned buffer");
     GemmExtra ex;
     ex.stats_out = stats_out;
+    ex.a_f16 = f16_operands != 0;
     return gemm_impl(A, lda, W, ldw, bias, M, N, K, EC_EPI_F16_RESADD, out, ldo, (const float *)res, 0, 1, (cudaStream_t)stream_, 0, &ex);
 }
 
@@ -1002,9 +1009,12 @@ extern "C" int ec_gemm_ln(const void *X, int ldx, const void *Wg, int ldw, const
 {
     EC_REQUIRE(cbias && stats && n_parts > 0 && n_parts <= 8 && n_parts % 2 == 0 && ((uintptr_t)stats & 15) == 0,
                "ec_gemm_ln: null / misaligned LayerNorm operands (statistics: 16-byte aligned, an even number of parts <= 8)");
-    EC_REQUIRE(epi == EC_EPI_BF16 || epi == EC_EPI_BF16_QGELU, "ec_gemm_ln: bf16 epilogues only (got %d)", epi);
+    const int f16_out = (epi & EC_EPI_F16_OPERANDS) != 0;
+    epi &= ~EC_EPI_F16_OPERANDS;
+    EC_REQUIRE(epi == EC_EPI_BF16 || epi == EC_EPI_BF16_QGELU, "ec_gemm_ln: 16-bit output epilogues only (got %d)", epi);
     GemmExtra ex;
     ex.a_f16 = 1;
+    ex.out_f16 = f16_out;
     ex.ln_stats = stats; ex.ln_parts = n_parts; ex.ln_colsum = colsum;
     return gemm_impl(X, ldx, Wg, ldw, cbias, M, N, K, epi, out, ldo, nullptr, 0, 1, (cudaStream_t)stream_, 0, &ex);
 }
@@ -1012,6 +1022,11 @@ extern "C" int ec_gemm_ln(const void *X, int ldx, const void *Wg, int ldw, const
 extern "C" int ec_gemm_bf16(const void *A, int lda, const void *W, int ldw, const float *bias, int M, int N, int K,
                             int epi, void *out, int ldo, const float *res, int row_map, void *stream_)
 {
+    if (epi & EC_EPI_F16_OPERANDS) {      // A and W hold fp16; 16-bit outputs are fp16 too
+        GemmExtra ex;
+        ex.a_f16 = ex.out_f16 = 1;
+        return gemm_impl(A, lda, W, ldw, bias, M, N, K, epi & ~EC_EPI_F16_OPERANDS, out, ldo, res, row_map, 1, (cudaStream_t)stream_, 0, &ex);
+    }
     return gemm_impl(A, lda, W, ldw, bias, M, N, K, epi, out, ldo, res, row_map, 1, (cudaStream_t)stream_);
 }
 
@@ -1130,6 +1145,7 @@ int gemm_impl(const void *A, int lda, const void *W, int ldw, const float *bias,
     p.M = M; p.N = N; p.K = K; p.epi = epi; p.out = out; p.ldo = ldo; p.bias = bias; p.res = res; p.row_map = row_map;
     p.mn_major = mn_major;
     p.a_f16 = ex ? ex->a_f16 : 0;
+    p.out_f16 = ex ? ex->out_f16 : 0;
     p.ln_stats = ex ? reinterpret_cast<const float2 *>(ex->ln_stats) : nullptr;
     p.ln_parts = ex ? ex->ln_parts : 0;
     p.ln_colsum = ex ? ex->ln_colsum : nullptr;

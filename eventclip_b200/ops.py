@@ -7,7 +7,7 @@ import torch
 
 from . import _lib as L
 
-OUT_FMT = {"f32": L.EC_OUT_F32_NCHW, "bf16": L.EC_OUT_BF16_NCHW, "patch": L.EC_OUT_BF16_PATCH}
+OUT_FMT = {"f32": L.EC_OUT_F32_NCHW, "bf16": L.EC_OUT_BF16_NCHW, "patch": L.EC_OUT_BF16_PATCH, "patch_f16": L.EC_OUT_F16_PATCH}
 
 
 def _stream():
@@ -82,7 +82,8 @@ def event2img(events, frames, shape, n_slots, count_non_zero=False, background_m
         else:
             G = 224 // patch
             ldk = ldk or 3 * patch * patch
-            out_tensor = torch.zeros((n_slots * G * G, ldk), dtype=torch.bfloat16, device=dev)
+            out_tensor = torch.zeros((n_slots * G * G, ldk), dtype=torch.float16 if fmt == L.EC_OUT_F16_PATCH else torch.bfloat16,
+                                     device=dev)
     if status is None:
         status = torch.zeros(1, dtype=torch.int32, device=dev)
     dbg = None
@@ -151,22 +152,27 @@ def event2img_geometry(shape):
 
 # ------------------------------------------------------------------------------------------------ encoder pieces
 def gemm_bf16(A, W, bias=None, epi="bf16", out=None, res=None, row_map=0, M=None):
-    """out = epilogue(A @ W.T).  A bf16 [M,K] (row stride may exceed K), W bf16 [N,K]."""
-    _dev(A, torch.bfloat16, "A")
-    _dev(W, torch.bfloat16, "W")
+    """out = epilogue(A @ W.T).  A [M,K] (row stride may exceed K) and W [N,K] are both bf16 or both fp16; with fp16 operands the
+    16-bit outputs ("bf16", "bf16_qgelu" epilogues) are fp16 as well (EC_EPI_F16_OPERANDS)."""
+    f16 = A.dtype == torch.float16
+    _dev(A, torch.float16 if f16 else torch.bfloat16, "A")
+    _dev(W, A.dtype, "W")
     M = A.shape[0] if M is None else M
     N, K = W.shape
     epi_id = {"bf16": L.EC_EPI_BF16, "bf16_qgelu": L.EC_EPI_BF16_QGELU, "f32_resadd": L.EC_EPI_F32_RESADD,
               "f32": L.EC_EPI_F32, "patch": L.EC_EPI_PATCH, "f16_resadd": L.EC_EPI_F16_RESADD}[epi]
+    flag = L.EC_EPI_F16_OPERANDS if f16 else 0
     if epi == "f16_resadd":
         if out is None or res is None or out.dtype != torch.float16 or res.dtype != torch.float16:
             raise L.ECError("f16_resadd epilogue needs fp16 `out` and `res` (the fp16 residual stream)")
     if out is None:
         if epi == "patch":
             raise L.ECError("patch epilogue needs a preallocated token matrix")
-        out = torch.empty((M, N), dtype=torch.bfloat16 if epi_id <= 1 else torch.float32, device=A.device)
+        out = torch.empty((M, N), dtype=A.dtype if epi_id <= 1 else torch.float32, device=A.device)
+    elif epi_id <= 1 and out.dtype != A.dtype:
+        raise L.ECError(f"16-bit epilogue writes {A.dtype} (the operands' dtype), got an output of {out.dtype}")
     with torch.cuda.device(A.device):
-        rc = L.load().ec_gemm_bf16(_ptr(A), A.stride(0), _ptr(W), W.stride(0), _ptr(bias), M, N, K, epi_id,
+        rc = L.load().ec_gemm_bf16(_ptr(A), A.stride(0), _ptr(W), W.stride(0), _ptr(bias), M, N, K, epi_id | flag,
                                    _ptr(out), out.stride(0), _ptr(res), int(row_map), _stream())
     L.check(rc, "ec_gemm_bf16")
     return out
@@ -179,9 +185,10 @@ def gemm_stats_parts(N):
 
 def gemm_bf16_stats(A, W, bias, x, stats):
     """x (fp16 [M,N], in place) += A @ W.T + bias, and stats float32 [M, parts, 2] = per-row partial (sum, sum of squares) of
-    the new x: what the LayerNorm-folded GEMM that reads x next needs."""
-    _dev(A, torch.bfloat16, "A")
-    _dev(W, torch.bfloat16, "W")
+    the new x: what the LayerNorm-folded GEMM that reads x next needs.  A and W: both bf16 or both fp16."""
+    f16 = A.dtype == torch.float16
+    _dev(A, torch.float16 if f16 else torch.bfloat16, "A")
+    _dev(W, A.dtype, "W")
     _dev(x, torch.float16, "x")
     _dev(stats, torch.float32, "stats")
     M, (N, K) = A.shape[0], W.shape
@@ -189,20 +196,23 @@ def gemm_bf16_stats(A, W, bias, x, stats):
         raise L.ECError("gemm_bf16_stats: statistics buffer too small")
     with torch.cuda.device(A.device):
         L.check(L.load().ec_gemm_bf16_stats(_ptr(A), A.stride(0), _ptr(W), W.stride(0), _ptr(bias), M, N, K, _ptr(x), x.stride(0),
-                                            _ptr(x), _ptr(stats), _stream()), "ec_gemm_bf16_stats")
+                                            _ptr(x), _ptr(stats), int(f16), _stream()), "ec_gemm_bf16_stats")
     return x
 
 
-def gemm_ln(x, Wg, colsum, cbias, stats, n_parts, epi="bf16", out=None):
-    """out bf16 = epi(LayerNorm(x) @ W.T + b) with the LayerNorm folded into the GEMM: x fp16 [M,K] is the A operand itself,
-    Wg = fp16(gamma * W), colsum[j] = sum_k Wg[j,k], cbias[j] = beta . W[j] + b[j], stats = per-row partial sums."""
+def gemm_ln(x, Wg, colsum, cbias, stats, n_parts, epi="bf16", out=None, out_dtype=torch.bfloat16):
+    """out = epi(LayerNorm(x) @ W.T + b) with the LayerNorm folded into the GEMM: x fp16 [M,K] is the A operand itself,
+    Wg = fp16(gamma * W), colsum[j] = sum_k Wg[j,k], cbias[j] = beta . W[j] + b[j], stats = per-row partial sums.
+    The output is bf16, or fp16 when `out` / `out_dtype` says so."""
     _dev(x, torch.float16, "x")
     _dev(Wg, torch.float16, "Wg")
     _dev(stats, torch.float32, "stats")
     M, (N, K) = x.shape[0], Wg.shape
     if out is None:
-        out = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
+        out = torch.empty((M, N), dtype=out_dtype, device=x.device)
     epi_id = {"bf16": L.EC_EPI_BF16, "bf16_qgelu": L.EC_EPI_BF16_QGELU}[epi]
+    if out.dtype == torch.float16:
+        epi_id |= L.EC_EPI_F16_OPERANDS
     with torch.cuda.device(x.device):
         L.check(L.load().ec_gemm_ln(_ptr(x), x.stride(0), _ptr(Wg), Wg.stride(0), _ptr(colsum), _ptr(cbias), _ptr(stats), int(n_parts),
                                     M, N, K, epi_id, _ptr(out), out.stride(0), _stream()), "ec_gemm_ln")
@@ -237,9 +247,13 @@ def layernorm(x, gamma, beta, M, d, row_stride=None, out_bf16=None, out_f32=None
 
 
 def attention(qkv, out, n_img, Ltok, heads, causal=False):
-    _dev(qkv, torch.bfloat16, "qkv")
+    """softmax(q k^T / 8) v on packed qkv [n*L, 3d]; qkv and out are both bf16 or both fp16."""
+    f16 = qkv.dtype == torch.float16
+    _dev(qkv, torch.float16 if f16 else torch.bfloat16, "qkv")
+    _dev(out, qkv.dtype, "out")
+    flags = (L.EC_ATTN_CAUSAL if causal else 0) | (L.EC_ATTN_F16 if f16 else 0)
     with torch.cuda.device(qkv.device):
-        rc = L.load().ec_attention_ex(_ptr(qkv), _ptr(out), n_img, Ltok, heads, int(bool(causal)), _stream())
+        rc = L.load().ec_attention_ex(_ptr(qkv), _ptr(out), n_img, Ltok, heads, flags, _stream())
     L.check(rc, "ec_attention")
     return out
 
@@ -272,8 +286,8 @@ def f32_to_bf16(src, dst=None):
     return dst
 
 
-def im2col(img, patch, ldk=None):
-    """img CUDA [n,3,224,224] fp32 or bf16 -> bf16 [n*G*G, ldk]."""
+def im2col(img, patch, ldk=None, dtype=torch.bfloat16):
+    """img CUDA [n,3,224,224] fp32 or bf16 -> bf16 (or fp16) [n*G*G, ldk]."""
     _dev(img, None, "img")
     if img.dtype not in (torch.float32, torch.bfloat16):
         raise L.ECError(f"img must be float32 or bfloat16, got {img.dtype}")
@@ -281,10 +295,10 @@ def im2col(img, patch, ldk=None):
     G = 224 // patch
     K = 3 * patch * patch
     ldk = ldk or K
-    out = (torch.zeros if ldk != K else torch.empty)((n * G * G, ldk), dtype=torch.bfloat16, device=img.device)
+    out = (torch.zeros if ldk != K else torch.empty)((n * G * G, ldk), dtype=dtype, device=img.device)
     with torch.cuda.device(img.device):
-        L.check(L.load().ec_im2col(_ptr(img), int(img.dtype == torch.bfloat16), n, patch, ldk, _ptr(out), _stream()),
-                "ec_im2col")
+        L.check(L.load().ec_im2col(_ptr(img), int(img.dtype == torch.bfloat16) | (2 if dtype == torch.float16 else 0), n, patch, ldk,
+                                   _ptr(out), _stream()), "ec_im2col")
     return out
 
 

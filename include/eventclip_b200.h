@@ -45,6 +45,7 @@ extern "C" {
 #define EC_OUT_F32_NCHW 0  /* float32 [slot,3,224,224] -- the tensor the reference DataLoader yields */
 #define EC_OUT_BF16_NCHW 1 /* same layout, bf16 (round-to-nearest-even of the float32 value)      */
 #define EC_OUT_BF16_PATCH 2 /* bf16 [slot, G*G, ldk] im2col rows (c,dy,dx) feeding the patch GEMM  */
+#define EC_OUT_F16_PATCH 3  /* the same rows in fp16 (round-to-nearest-even of the float32 value): the fp16-operand inference forward */
 
 EC_API const char *ec_last_error(void);
 EC_API int ec_version(void);
@@ -134,6 +135,10 @@ EC_API int ec_event2img_geometry(int H, int W, int *cluster_size, int *threads, 
 #define EC_EPI_PATCH 4       /* out fp32 token rows = acc + pos[1 + m%G2]  (patch embedding) */
 #define EC_EPI_F16_RESADD 5  /* out fp16 = res(fp16) + acc + bias: residual stream in the reference's CUDA precision;
                                 `out` and `res` point to fp16 [M,ldo] (res is passed through the float* parameter) */
+#define EC_EPI_F16_OPERANDS 0x100 /* OR-ed into epi: A and W hold fp16 instead of bf16 (tcgen05.mma kind::f16 takes either, at the same
+                                rate, but not a mixed pair) and the 16-bit outputs (EC_EPI_BF16, EC_EPI_BF16_QGELU) are written as
+                                fp16 -- the reference's own CUDA inference dtype (clip.load keeps fp16 weights, test.py:26-29),
+                                3 more mantissa bits than bf16 at every rounding point of the encoder */
 EC_API int ec_gemm_bf16(const void *A, int lda, const void *W, int ldw, const float *bias, int M, int N, int K,
                  int epi, void *out, int ldo, const float *res, int row_map, void *stream);
 
@@ -180,9 +185,9 @@ EC_API int ec_gemm_stats_parts(int N);
 /* out fp16 = res(fp16) + A W^T + bias (EC_EPI_F16_RESADD) and stats_out float [M, parts, 2] = per-row partial sums of the values
  * written (parts = ec_gemm_stats_parts(N)) */
 EC_API int ec_gemm_bf16_stats(const void *A, int lda, const void *W, int ldw, const float *bias, int M, int N, int K, void *out,
-                              int ldo, const void *res, float *stats_out, void *stream);
+                              int ldo, const void *res, float *stats_out, int f16_operands, void *stream);
 /* out bf16 = epi(LayerNorm(X) W^T + b) from X fp16 [M,K] (ldx), Wg fp16 [N,K], colsum s [N] or NULL, cbias c [N], stats float
- * [M, n_parts, 2];  epi = EC_EPI_BF16 or EC_EPI_BF16_QGELU */
+ * [M, n_parts, 2];  epi = EC_EPI_BF16 or EC_EPI_BF16_QGELU, optionally | EC_EPI_F16_OPERANDS for an fp16 output */
 EC_API int ec_gemm_ln(const void *X, int ldx, const void *Wg, int ldw, const float *colsum, const float *cbias,
                       const float *stats, int n_parts, int M, int N, int K, int epi, void *out, int ldo, void *stream);
 /* stats[row, 0] = (sum, sum of squares) of the fp16 row, other parts zero: statistics for rows no GEMM epilogue produced */
@@ -195,7 +200,9 @@ EC_API int ec_attention(const void *qkv, void *out, int n_img, int L, int heads,
 
 /* Same with an optional causal mask (key j visible to query i iff j <= i): the attention of CLIP's text tower
  * (openai-CLIP encode_text [3P], called at models/clip_cls.py:84, models/clip_cls_ft.py:152). */
-EC_API int ec_attention_ex(const void *qkv, void *out, int n_seq, int L, int heads, int causal, void *stream);
+#define EC_ATTN_CAUSAL 1
+#define EC_ATTN_F16 2 /* qkv, the probabilities and out are fp16 instead of bf16 (tensor-memory kernels, L <= 384) */
+EC_API int ec_attention_ex(const void *qkv, void *out, int n_seq, int L, int heads, int causal /* EC_ATTN_* bits */, void *stream);
 
 /* Text-tower input: out[n*L + l, :] = token_embedding[tokens[n,l], :] + positional_embedding[l, :]  (fp32).
  * tokens device int32 [n_seq, L]. */
@@ -210,7 +217,8 @@ EC_API int ec_f32_to_bf16(const float *src, void *dst, int64_t n, void *stream);
 
 /* NCHW image (fp32 or bf16) -> bf16 im2col rows [n_img*G*G, ldk] for images that did not come from
  * ec_event2img (the reference's data_dict['img'] input, models/clip_cls.py:133). in_is_bf16: 0 fp32, 1 bf16. */
-EC_API int ec_im2col(const void *img, int in_is_bf16, int n_img, int patch, int ldk, void *out, void *stream);
+EC_API int ec_im2col(const void *img, int in_is_bf16 /* bit 0: input is bf16; bit 1: write fp16 rows */, int n_img, int patch, int ldk,
+                     void *out, void *stream);
 
 /* LoRA merge (models/lora.py:138-149 q/k/v, 49-52 out_proj): Wm[rows,d] bf16 = W[rows,d] + up[rows,r] . down[r,d],
  * fp32 math, one rounding to bf16.  up/down NULL copies W. */

@@ -22,8 +22,8 @@ def test_bench_workload_parity_at_bench_geometry(cuda_dev):
     assert w.B == 256 and w.T == 1
     g = GraphedClassifier(w.cls, max_events=w.max_events)
     with torch.no_grad():
-        for i in range(3):                      # capture + replays; batch 0 last
-            out = g(w.data((i + 1) % 2))
+        for i in range(3):                      # capture + replays: batches 0, 1, 0
+            out = g(w.data(i % 2))
         logits = out["logits"].float().cpu().clone()
         pred = out["top5_logits"][:, 0].cpu().clone()
         patches = w.cls._last_patches

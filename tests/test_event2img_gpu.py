@@ -203,14 +203,14 @@ def test_counts_above_65535_are_exact(cuda_dev, hot_pos, hot_neg, rest):
 
 def test_band_exchange_kernel_cluster_sizes_and_rounds(cuda_dev):
     """event2img_big_kernel outside its home shape: EC_E2I_BIG=force routes sensors that fit one SM through 2-CTA clusters,
-    480x320 takes a 4-CTA cluster, and EC_E2I_BIG_CAP shrinks the exchange round so that a frame needs several rounds.
+    256x512 takes a 4-CTA cluster, and EC_E2I_BIG_CAP shrinks the exchange round so that a frame needs several rounds.
     Every stage equals the oracle's (the environment is read per call)."""
     old = {k: os.environ.get(k) for k in ("EC_E2I_BIG", "EC_E2I_BIG_CAP")}
     try:
         for shape, N, cnz, bg, force, cap, want_cs in (((180, 240), 20000, False, True, True, None, 2),
                                                        ((180, 240), 20000, True, False, True, "1024", 2),
                                                        ((128, 128), 9000, False, True, True, "96", 2),
-                                                       ((480, 320), 50000, False, True, False, None, 4),
+                                                       ((256, 512), 50000, False, True, False, None, 4),
                                                        ((480, 640), 70000, False, True, False, "2048", 8)):
             os.environ.pop("EC_E2I_BIG", None)
             os.environ.pop("EC_E2I_BIG_CAP", None)

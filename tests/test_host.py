@@ -51,7 +51,7 @@ def test_event_kernel_selection_and_gemm_statistics_layout(built_lib):
     assert geo[(480, 640)]["cluster"] == 8 and geo[(260, 346)]["cluster"] == 2
     assert geo[(34, 34)]["cluster"] == 1 and geo[(128, 128)]["cluster"] == 1
     for s, g in geo.items():
-        assert g["smem"] <= 227 * 1024 - 8 * 1024, (s, g)                       # leaves room for the kernels' static tables
+        assert g["smem"] <= 227 * 1024 - 13 * 1024, (s, g)                      # leaves room for the kernels' static tables
     with pytest.raises(_lib.ECError):
         ops.event2img_geometry((4, 4))
     assert [ops.gemm_stats_parts(n) for n in (768, 1024, 512, 384, 1280)] == [6, 8, 4, 6, 10]
