@@ -10,9 +10,12 @@ from parity_util import record_metric, rel_l2, rel_l2_centered
 
 pytestmark = pytest.mark.gpu
 
-# centred relative L2 of the logits (batch mean removed): the bf16 / fp16-residual encoder against the fp32 oracle on
-# event frames of a random-init tower, whose input-dependent part is < 1 % of the feature norm
-CENTERED_TOL = 0.25
+# Centred relative L2 (batch mean removed) of the fp16-operand / fp16-residual encoder against the fp32 oracle on event frames
+# of a random-init tower, whose input-dependent part is only 0.6 % (N-Cars, ViT-B/16) to 1.3 % (N-Caltech101, ViT-B/32) of the
+# feature norm.  Measured on B200 (gpurun_out/test_metrics.jsonl): features 0.17 / 0.073 (plain rel-L2 1.1e-3), bench logits
+# 0.033 (0.073 with bf16 operands, 0.009 with an fp32 residual stream).
+CENTERED_TOL = 0.30
+LOGITS_CENTERED_TOL = 0.08
 
 
 def test_bench_workload_parity_at_bench_geometry(cuda_dev):
@@ -38,7 +41,7 @@ def test_bench_workload_parity_at_bench_geometry(cuda_dev):
     split = np.bincount(pred.numpy(), minlength=2) / 256.0
     assert split.min() > 0.25, split
     assert st["oracle_classes_predicted"] == 2
-    assert st["logits_centered_rel_l2"] < CENTERED_TOL, st
+    assert st["logits_centered_rel_l2"] < LOGITS_CENTERED_TOL, st
     assert st["top1_agree_clear_margin"] == 1.0 and st["clear_margin_samples"] >= n // 2, st
     g.check_status()
 

