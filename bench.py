@@ -657,6 +657,10 @@ def b200_arm(args):
     # ---- parity of the path that is about to be timed (rank 0): graph replay of batch 0 vs the oracle on the whole batch.
     #      Its predictions become the labels of batch 0, so the accuracy counters of the timed region mean something. ----
     parity = None
+    if world > 1:
+        args.parity_samples = min(args.parity_samples, 64)       # the other ranks wait at the barrier meanwhile
+    # torchrun exports OMP_NUM_THREADS=1: the oracle (rank 0 only, the other ranks idle at a barrier) takes the host's cores back
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // (1 if world == 1 else 2)))
     if rank == 0 and not args.quick:
         try:
             with torch.no_grad():
