@@ -60,6 +60,8 @@ SIGNATURES = {
     "ec_head": ([_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "ec_gemm_f32": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
     "ec_adapter_attention": ([_vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
+    "ec_adapter_attention_bwd": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
+    "ec_relu_bwd": ([_vp, _vp, _vp, _i64, _vp], _i),
     "ec_blend": ([_vp, _vp, _d, _vp, _i64, _vp], _i),
     "ec_layernorm_f32": ([_vp, _vp, _vp, _i, _i, _vp, _vp], _i),
     "ec_gather_rows": ([_vp, _vp, _vp, _i, _i, _vp], _i),
@@ -83,6 +85,7 @@ SIGNATURES = {
     "ec_patch_rows_bf16": ([_vp, _i, _i, _i, _vp, _vp], _i),
     "ec_l2norm_rows_bwd": ([_vp, _vp, _vp, _i, _i, _vp, _vp], _i),
     "ec_ce_loss_bwd": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp], _i),
+    "ec_probs_loss_bwd": ([_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp], _i),
 }
 
 _lib = None

@@ -255,7 +255,108 @@ __global__ void adapter_attention_kernel(const float *__restrict__ qkv, const ui
     }
 }
 
+// Backward of adapter_attention_kernel: one CTA per sample, one warp per head, T <= 16 views.  The probabilities are recomputed
+// (T x T per head); dV = P^T dO, dP = dO V^T, dS = P (dP - rowsum(P dP)), dQ = dS K / sqrt(hd), dK = dS^T Q / sqrt(hd).
+// Masked keys have P = 0, so they receive no dK / dV; every query row (valid or padded) is differentiated like the reference's
+// nn.TransformerEncoder does.
+__global__ void adapter_attention_bwd_kernel(const float *__restrict__ qkv, const uint8_t *__restrict__ valid,
+                                             const float *__restrict__ d_out, int T, int D, int heads, float *__restrict__ d_qkv)
+{
+    extern __shared__ float s_att[];             // [heads][2][16][16]: probabilities and dS of every head
+    const int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (h >= heads) return;
+    const int hd = D / heads;
+    const float sc = rsqrtf((float)hd);
+    const float *base = qkv + (size_t)b * T * 3 * D + h * hd;
+    const float *dob = d_out + (size_t)b * T * D + h * hd;
+    float *dqb = d_qkv + (size_t)b * T * 3 * D + h * hd;
+    float (*P)[16] = reinterpret_cast<float (*)[16]>(s_att + (size_t)h * 512);
+    float (*dS)[16] = reinterpret_cast<float (*)[16]>(s_att + (size_t)h * 512 + 256);
+    // probabilities and dP
+    for (int t = 0; t < T; ++t) {
+        float s[16], dp[16];
+        float m = -INFINITY;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            s[u] = -INFINITY; dp[u] = 0.f;
+            if (u < T) {
+                float acc = 0.f, acc2 = 0.f;
+                for (int c = lane; c < hd; c += 32) {
+                    acc = fmaf(base[(size_t)t * 3 * D + c], base[(size_t)u * 3 * D + D + c], acc);
+                    acc2 = fmaf(dob[(size_t)t * D + c], base[(size_t)u * 3 * D + 2 * D + c], acc2);
+                }
+                acc = ec::warp_sum(acc) * sc;
+                dp[u] = ec::warp_sum(acc2);
+                if (valid[(size_t)b * T + u]) { s[u] = acc; m = fmaxf(m, acc); }
+            }
+        }
+        float den = 0.f;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            s[u] = (u < T && s[u] != -INFINITY) ? expf(s[u] - m) : 0.f;
+            den += s[u];
+        }
+        float dot = 0.f;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) { s[u] /= den; dot = fmaf(s[u], dp[u], dot); }
+        if (lane < 16) {
+            // every lane holds the full row; lane u keeps column u
+            float pu = 0.f, du = 0.f;
+#pragma unroll
+            for (int u = 0; u < 16; ++u)
+                if (u == lane) { pu = s[u]; du = s[u] * (dp[u] - dot); }
+            P[t][lane] = pu;
+            dS[t][lane] = du;
+        }
+    }
+    __syncwarp();
+    for (int c = lane; c < hd; c += 32) {
+        for (int t = 0; t < T; ++t) {          // dQ[t] = sc * sum_u dS[t][u] K[u]
+            float acc = 0.f;
+            for (int u = 0; u < T; ++u) acc = fmaf(dS[t][u], base[(size_t)u * 3 * D + D + c], acc);
+            dqb[(size_t)t * 3 * D + c] = acc * sc;
+        }
+        for (int u = 0; u < T; ++u) {          // dK[u] = sc * sum_t dS[t][u] Q[t];  dV[u] = sum_t P[t][u] dO[t]
+            float ak = 0.f, av = 0.f;
+            for (int t = 0; t < T; ++t) {
+                ak = fmaf(dS[t][u], base[(size_t)t * 3 * D + c], ak);
+                av = fmaf(P[t][u], dob[(size_t)t * D + c], av);
+            }
+            dqb[(size_t)u * 3 * D + D + c] = ak * sc;
+            dqb[(size_t)u * 3 * D + 2 * D + c] = av;
+        }
+    }
+}
+
+__global__ void relu_bwd_kernel(const float *__restrict__ y, const float *__restrict__ dy, float *__restrict__ dx, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dx[i] = y[i] > 0.f ? dy[i] : 0.f;
+}
+
 }  // namespace
+
+extern "C" int ec_adapter_attention_bwd(const float *qkv, const uint8_t *valid, const float *d_out, int B, int T, int D, int heads,
+                                        float *d_qkv, void *stream)
+{
+    EC_REQUIRE(qkv && valid && d_out && d_qkv, "ec_adapter_attention_bwd: null pointer");
+    EC_REQUIRE(B > 0 && T > 0 && T <= 16 && heads > 0 && heads <= 32 && D % heads == 0,
+               "ec_adapter_attention_bwd: bad shape B=%d T=%d D=%d heads=%d", B, T, D, heads);
+    EC_REQUIRE(heads <= 16, "ec_adapter_attention_bwd: at most 16 heads (got %d)", heads);
+    adapter_attention_bwd_kernel<<<B, heads * 32, (size_t)heads * 2048, (cudaStream_t)stream>>>(qkv, valid, d_out, T, D, heads, d_qkv);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
+/* dx = dy where y > 0 else 0: backward of the ReLU fused into ec_gemm_f32 (act = 1); y is the activation's OUTPUT */
+extern "C" int ec_relu_bwd(const float *y, const float *dy, float *dx, int64_t n, void *stream)
+{
+    EC_REQUIRE(y && dy && dx && n >= 0, "ec_relu_bwd: bad arguments");
+    if (n == 0) return EC_OK;
+    relu_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(y, dy, dx, n);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
 
 extern "C" int ec_head(const float *feats, const uint8_t *valid, const float *text, int B, int T, int C, int n_cls,
                        float scale, int normalize, int agg, float *out_full, float *out_logits, float *out_probs,

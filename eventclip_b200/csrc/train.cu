@@ -334,9 +334,57 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const float *__restrict__ f
         for (int t = 0; t < T; ++t) z += fb[(size_t)t * K + k];
         z *= w;
         const float g = (__expf(z - lse) - (k == y ? 1.f : 0.f)) * invB * w;
-        // every view slot receives the gradient of the sum (the reference sums over all T rows; invalid rows are zero
-        // features, whose gradient is cut by the mask downstream)
-        for (int t = 0; t < T; ++t) dfull[((size_t)b * T + t) * K + k] = g;
+        // every VALID view slot receives the gradient of the sum.  The reference sums over all T rows, but its padded rows are
+        // features multiplied by the valid mask (clip_cls.py:330-333): zero rows whose logits carry no gradient to anything.
+        // Writing zeros there keeps d_text exact when the padded slots hold non-zero adapter outputs (few-shot training).
+        for (int t = 0; t < T; ++t) dfull[((size_t)b * T + t) * K + k] = valid[b * T + t] ? g : 0.f;
+    }
+}
+
+// Probability loss of the reference (use_probs_loss, models/clip_cls_ft.py:265-267 / clip_cls.py:173-175): probs = mean over the
+// valid views of softmax(full_logits[b,t,:]) (clip_cls.py:123-129), loss = -log(probs[label] + 1e-6).  One warp per sample.
+// d loss / d z[t,k] = -s_t[y] (delta_ky - s_t[k]) / ((p_y + 1e-6) n_valid) for valid views, 0 for padded ones.
+constexpr int PROBS_MAX_T = 16;
+__global__ void __launch_bounds__(256) probs_bwd_kernel(const float *__restrict__ full, const uint8_t *__restrict__ valid,
+                                                        const int32_t *__restrict__ labels, int B, int T, int K,
+                                                        float *__restrict__ loss_b, float *__restrict__ dfull)
+{
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= B) return;
+    const float *fb = full + (size_t)b * T * K;
+    const int y = labels[b];
+    float lse[PROBS_MAX_T], sy[PROBS_MAX_T];
+    int nv = 0;
+    float py = 0.f;
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) {
+        lse[t] = 0.f; sy[t] = 0.f;
+        if (!valid[b * T + t]) continue;
+        ++nv;
+        const float *z = fb + (size_t)t * K;
+        float mx = -INFINITY;
+        for (int k = lane; k < K; k += 32) mx = fmaxf(mx, z[k]);
+        mx = ec::warp_max(mx);
+        float se = 0.f;
+        for (int k = lane; k < K; k += 32) se += expf(z[k] - mx);
+        se = ec::warp_sum(se);
+        lse[t] = mx + logf(se);
+        sy[t] = expf(z[y] - lse[t]);
+        py += sy[t];
+    }
+    py /= (float)nv;                                   // nv == 0 gives nan exactly like the reference's 0/0
+    if (lane == 0) loss_b[b] = -logf(py + 1e-6f);
+    const float coef = -1.f / ((py + 1e-6f) * (float)nv * (float)B);
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) {
+        float *g = dfull + ((size_t)b * T + t) * K;
+        if (!valid[b * T + t]) {
+            for (int k = lane; k < K; k += 32) g[k] = 0.f;
+            continue;
+        }
+        const float *z = fb + (size_t)t * K;
+        const float c = coef * sy[t];
+        for (int k = lane; k < K; k += 32) g[k] = c * ((k == y ? 1.f : 0.f) - expf(z[k] - lse[t]));
     }
 }
 
@@ -549,6 +597,18 @@ extern "C" int ec_ce_loss_bwd(const float *full_logits, const uint8_t *valid, co
                "ec_ce_loss_bwd: bad arguments");
     EC_REQUIRE(agg == EC_AGG_SUM || agg == EC_AGG_MEAN, "ec_ce_loss_bwd: training supports agg sum / mean (got %d)", agg);
     ce_bwd_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(full_logits, valid, labels, B, T, n_cls, agg, loss_per_sample, d_full);
+    mean_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(loss_per_sample, B, loss_mean);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
+}
+
+extern "C" int ec_probs_loss_bwd(const float *full_logits, const uint8_t *valid, const int32_t *labels, int B, int T, int n_cls,
+                                 float *loss_per_sample, float *loss_mean, float *d_full, void *stream)
+{
+    EC_REQUIRE(full_logits && valid && labels && loss_per_sample && loss_mean && d_full && B > 0 && T > 0 && n_cls > 0,
+               "ec_probs_loss_bwd: bad arguments");
+    EC_REQUIRE(T <= PROBS_MAX_T, "ec_probs_loss_bwd: at most %d views per sample (got %d)", PROBS_MAX_T, T);
+    probs_bwd_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(full_logits, valid, labels, B, T, n_cls, loss_per_sample, d_full);
     mean_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(loss_per_sample, B, loss_mean);
     EC_CUDA_CHECK(cudaGetLastError());
     return EC_OK;

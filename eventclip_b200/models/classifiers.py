@@ -286,6 +286,32 @@ class FSCLIPClassifier(_AdaptedClassifier):
     def _adapt(self, full_feats, valid_masks):
         return self.adapter(full_feats, valid_masks)
 
+    # ---- training (clip_cls.py:308-350 under autograd in the reference): CLIP stays frozen, gradients reach the adapter
+    #      (models/adapter._AdapterFn) and, with a 'text-*' adapter type, the prompt-tuned text features (train._HeadFn) ----
+    def _training_active(self):
+        return self.training and torch.is_grad_enabled()
+
+    def _head(self, feats, plan):
+        if not self._training_active():
+            return super()._head(feats, plan)
+        from .. import train
+        B, T = plan["B"], plan["T"]
+        feats = feats.detach().float().contiguous()
+        full = feats if plan["row_of_slot"] is None else ops.gather_rows(feats, plan["row_of_slot"], B * T)
+        adapted = self._adapt(full.view(B, T, -1), plan["valid_dev"]).reshape(B * T, -1)
+        slot_plan = dict(plan)
+        slot_plan["row_of_slot"] = None                  # the head sees one feature row per (sample, view) slot
+        text_raw = self.text_feats if self.prompt_tuning else self._clip_text_feats().float()
+        full_l, logits, probs, t5l, t5p = train._HeadFn.apply(adapted, text_raw, slot_plan, self.logit_scale, self.agg_func)
+        return {"full_logits": full_l, "valid_masks": plan["valid_dev"], "logits": logits, "probs": probs,
+                "top5_logits": t5l, "top5_probs": t5p, "_plan": slot_plan}
+
+    def calc_train_loss(self, data_dict, out_dict):
+        if "_plan" in out_dict and torch.is_grad_enabled():
+            from .. import train
+            return train.train_loss(self, data_dict, out_dict)
+        return super().calc_train_loss(data_dict, out_dict)
+
 
 class FTCLIPClassifier(_AdaptedClassifier):
     """Fine-tuned CLIP (clip_cls_ft.py:15-333): trainable subsets of model.visual or LoRA; the adapter call is

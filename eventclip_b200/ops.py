@@ -354,6 +354,27 @@ def adapter_attention(qkv, valid_u8, B, T, D, heads):
     return out
 
 
+def adapter_attention_bwd(qkv, valid_u8, d_out, B, T, D, heads):
+    """d_qkv of ec_adapter_attention (few-shot adapter training)."""
+    _dev(qkv, torch.float32, "qkv")
+    _dev(d_out, torch.float32, "d_out")
+    d_qkv = torch.empty_like(qkv)
+    with torch.cuda.device(qkv.device):
+        L.check(L.load().ec_adapter_attention_bwd(_ptr(qkv), _ptr(valid_u8), _ptr(d_out), B, T, D, heads, _ptr(d_qkv), _stream()),
+                "ec_adapter_attention_bwd")
+    return d_qkv
+
+
+def relu_bwd(y, dy):
+    """dy masked by y > 0 (y = output of the ReLU fused into gemm_f32(act=1))."""
+    _dev(y, torch.float32, "y")
+    _dev(dy, torch.float32, "dy")
+    dx = torch.empty_like(y)
+    with torch.cuda.device(y.device):
+        L.check(L.load().ec_relu_bwd(_ptr(y), _ptr(dy), _ptr(dx), y.numel(), _stream()), "ec_relu_bwd")
+    return dx
+
+
 def blend(a, b, r):
     _dev(a, torch.float32, "a")
     out = torch.empty_like(a)
@@ -498,6 +519,21 @@ def l2norm_rows_bwd(x, dy, mask_u8=None):
         L.check(L.load().ec_l2norm_rows_bwd(_ptr(x), _ptr(dy), _ptr(mask_u8), M, Cdim, _ptr(dx), _stream()),
                 "ec_l2norm_rows_bwd")
     return dx
+
+
+def probs_loss_bwd(full_logits, valid_u8, labels_i32):
+    """The reference's probability loss (use_probs_loss, clip_cls_ft.py:265-267): nll of log(mean-over-views softmax + 1e-6).
+    Returns (per-sample loss [B], mean loss [1], d mean-loss / d full_logits [B,T,K])."""
+    _dev(full_logits, torch.float32, "full_logits")
+    _dev(labels_i32, torch.int32, "labels")
+    B, T, K = full_logits.shape
+    loss_b = torch.empty(B, dtype=torch.float32, device=full_logits.device)
+    loss = torch.empty(1, dtype=torch.float32, device=full_logits.device)
+    dfull = torch.empty_like(full_logits)
+    with torch.cuda.device(full_logits.device):
+        L.check(L.load().ec_probs_loss_bwd(_ptr(full_logits), _ptr(valid_u8), _ptr(labels_i32), B, T, K, _ptr(loss_b),
+                                           _ptr(loss), _ptr(dfull), _stream()), "ec_probs_loss_bwd")
+    return loss_b, loss, dfull
 
 
 def ce_loss_bwd(full_logits, valid_u8, labels_i32, agg):

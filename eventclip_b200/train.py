@@ -293,7 +293,10 @@ class _CELossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(fctx, full_logits, valid_u8, labels_i32, agg):
-        _, loss, d_full = ops.ce_loss_bwd(full_logits.detach().contiguous(), valid_u8, labels_i32, agg)
+        if agg == "probs":        # use_probs_loss: nll of the view-averaged probabilities (clip_cls_ft.py:265-267)
+            _, loss, d_full = ops.probs_loss_bwd(full_logits.detach().contiguous(), valid_u8, labels_i32)
+        else:
+            _, loss, d_full = ops.ce_loss_bwd(full_logits.detach().contiguous(), valid_u8, labels_i32, agg)
         fctx.d_full = d_full
         return loss.reshape(())
 
@@ -321,13 +324,12 @@ def train_forward(model, feats, plan):
 
 
 def train_loss(model, data_dict, out_dict):
-    """calc_train_loss in training mode (clip_cls_ft.py:258-269, use_logits_loss)."""
-    if not model.use_logits_loss:
-        raise NotImplementedError("the B200 fine-tune step implements the logits loss (use_logits_loss=True), the one the "
-                                  "reference's fine-tune configs use")
+    """calc_train_loss in training mode (clip_cls_ft.py:258-269): cross-entropy of the aggregated logits (use_logits_loss) or
+    nll of the view-averaged probabilities (use_probs_loss)."""
     plan = out_dict["_plan"]
     labels = data_dict["label"].to(device=out_dict["full_logits"].device, dtype=torch.int32).contiguous()
-    return {"ce_loss": _CELossFn.apply(out_dict["full_logits"], plan["valid_u8"], labels, model.agg_func)}
+    kind = model.agg_func if model.use_logits_loss else "probs"
+    return {"ce_loss": _CELossFn.apply(out_dict["full_logits"], plan["valid_u8"], labels, kind)}
 
 
 # ------------------------------------------------------------------------------------------------ fused trainer
@@ -383,7 +385,10 @@ class FineTuner:
                                            fe.background_mask, out="patch", patch=self.vis.patch_size, ldk=self.vis.k_patch)
             feats, ctx = encoder_forward(self.vis, patches, plan["n_valid"])
             out, hctx = head_forward(feats, plan, model.text_feats.detach(), model.logit_scale, model.agg_func)
-            _, loss, d_full = ops.ce_loss_bwd(out["full_logits"], plan["valid_u8"], labels, model.agg_func)
+            if model.use_logits_loss:
+                _, loss, d_full = ops.ce_loss_bwd(out["full_logits"], plan["valid_u8"], labels, model.agg_func)
+            else:     # use_probs_loss (clip_cls_ft.py:265-267)
+                _, loss, d_full = ops.probs_loss_bwd(out["full_logits"], plan["valid_u8"], labels)
             d_feats, d_text = head_backward(hctx, d_full)
             encoder_backward(self.vis, ctx, d_feats, dest=self.flat.grad_view)
             self._grad_view(model.text_feats).copy_(d_text)

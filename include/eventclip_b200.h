@@ -250,6 +250,13 @@ EC_API int ec_gemm_f32(const float *A, const float *W, const float *bias, const 
 EC_API int ec_adapter_attention(const float *qkv, const uint8_t *valid, int B, int T, int D, int heads, float *out,
                          void *stream);
 
+/* Backward of ec_adapter_attention (training of the few-shot feature adapter, models/adapter.py:82-105 under autograd in the
+ * reference): d_qkv fp32 [B*T, 3*D] from qkv, the mask and d_out fp32 [B*T, D].  heads <= 16, T <= 16. */
+EC_API int ec_adapter_attention_bwd(const float *qkv, const uint8_t *valid, const float *d_out, int B, int T, int D, int heads,
+                                    float *d_qkv, void *stream);
+/* dx = dy where y > 0, else 0: backward of the ReLU that ec_gemm_f32 (act = 1) fuses; y is the activation's output. */
+EC_API int ec_relu_bwd(const float *y, const float *dy, float *dx, int64_t n, void *stream);
+
 /* out = r*a + (1-r)*b  (Adapter.residual_add, models/adapter.py:22-25); n elements. */
 EC_API int ec_blend(const float *a, const float *b, double r, float *out, int64_t n, void *stream);
 
@@ -328,6 +335,12 @@ EC_API int ec_l2norm_rows_bwd(const float *x, const float *dy, const uint8_t *ma
  * labels device int32 [B].  Outputs: per-sample loss [B], mean loss [1], d(mean loss)/d(full_logits) [B,T,n_cls]. */
 EC_API int ec_ce_loss_bwd(const float *full_logits, const uint8_t *valid, const int32_t *labels, int B, int T, int n_cls, int agg,
                           float *loss_per_sample, float *loss_mean, float *d_full, void *stream);
+
+/* The reference's other loss (loss_dict['use_probs_loss'], models/clip_cls_ft.py:265-267, clip_cls.py:173-175):
+ * probs = mean over the valid views of softmax(full_logits[b,t,:]) (clip_cls.py:123-129), loss = F.nll_loss(log(probs + 1e-6)).
+ * Same outputs as ec_ce_loss_bwd; padded views receive a zero gradient.  T <= 16. */
+EC_API int ec_probs_loss_bwd(const float *full_logits, const uint8_t *valid, const int32_t *labels, int B, int T, int n_cls,
+                             float *loss_per_sample, float *loss_mean, float *d_full, void *stream);
 
 #ifdef __cplusplus
 }

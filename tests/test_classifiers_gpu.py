@@ -357,3 +357,76 @@ def test_text_features_from_prompts(cuda_dev):
                         "a point cloud image of a car side"]
     ref = ref / ref.norm(dim=-1, keepdim=True)
     assert rel(tf, ref) < 2e-2 and zs.get_text_feats() is tf      # cached (clip_cls.py:71-72)
+
+
+@pytest.mark.parametrize("kind,loss", [("text-trans", "logits"), ("trans", "probs")])
+def test_few_shot_training_gradients_vs_oracle_autograd(cuda_dev, kind, loss):
+    """Few-shot training (frozen CLIP, trainable TransformerAdapter and -- with 'text-trans' -- prompt-tuned text features,
+    models/clip_cls.py:308-350 + adapter.py:82-105 under autograd in the reference): loss and every gradient of the B200
+    route (explicit backward through the library's kernels) against torch autograd through the oracle's restatement fed the
+    same features.  Dropout is inactive on both sides."""
+    g = torch.Generator().manual_seed(5)
+    B, T, C, n_cls = 6, 4, 64, 11
+    valid = torch.rand(B, T, generator=g) > 0.35
+    valid[:, 0] = True
+    imgs = torch.randn(B, T, 3, 224, 224, generator=g) * valid[:, :, None, None, None].float()
+    text = clip_oracle.synth_text_feats(n_cls, C, 6)
+    ad = dict(adapter_type=kind, in_dim=C, d_model=32, num_heads=2, ffn_dim=64, norm_first=True, num_layers=2, residual=0.8)
+    torch.manual_seed(3)
+    fs = FSCLIPClassifier(adapter_dict=ad, clip_dict=dict(clip_model=_clip(cuda_dev), prompt="a {}", class_names=NAMES, agg_func="mean",
+                                                         text_feats=text),
+                          loss_dict=dict(use_logits_loss=loss == "logits", use_probs_loss=loss == "probs")).to(cuda_dev)
+    labels = torch.randint(0, n_cls, (B,), generator=g)
+    data = dict(img=imgs.to(cuda_dev), valid_mask=valid.to(cuda_dev), label=labels)
+    fs.eval()
+    with torch.no_grad():
+        feats = fs.get_img_feats(imgs[valid].to(cuda_dev)).float().cpu()      # the frozen tower's features (same on both sides)
+    fs.train()
+    out = fs(data)
+    val = fs.calc_train_loss(data, out)["ce_loss"]
+    val.backward()
+    # oracle: autograd through the restated adapter + head on the CPU
+    sd = {k: v.detach().cpu().clone() for k, v in fs.state_dict().items()}
+    ap = {k[len("adapter."):]: v.requires_grad_(True) for k, v in sd.items() if k.startswith("adapter.")}
+    tparam = sd["text_feats"].requires_grad_(True) if "text_feats" in sd else text.clone()
+    adapter = lambda f, v: heads_oracle.adapter_forward(ap, f, v, num_heads=2, residual=0.8)
+    ref = heads_oracle.fs_head(feats, valid, tparam, 100.0, "mean", adapter)
+    if loss == "logits":
+        want = torch.nn.functional.cross_entropy(ref["logits"], labels)
+    else:
+        want = torch.nn.functional.nll_loss((ref["probs"] + 1e-6).log(), labels)
+    want.backward()
+    assert abs(val.item() - want.item()) < 2e-4 * max(1.0, abs(want.item())), (val.item(), want.item())
+    named = dict(fs.named_parameters())
+    checked = 0
+    for k, v in ap.items():
+        p = named["adapter." + k]
+        assert p.grad is not None, k
+        assert rel(p.grad, v.grad) < 2e-3, (k, rel(p.grad, v.grad))
+        checked += 1
+    assert checked == 2 + 2 * 12 + 2
+    if kind.startswith("text-"):
+        assert rel(named["text_feats"].grad, tparam.grad) < 2e-3
+    for n, p in named.items():
+        if n.startswith("model."):
+            assert p.grad is None and not p.requires_grad           # CLIP stays frozen (clip_cls.py:36-41)
+
+
+def test_post_norm_adapter_forward_vs_torch(cuda_dev):
+    """norm_first=False (models/adapter.py:72-78 passes it to nn.TransformerEncoderLayer): the post-norm layer order against
+    torch's own module on the CPU, eval mode."""
+    torch.manual_seed(7)
+    from eventclip_b200.models.adapter import TransformerAdapter
+    for nf in (False, True):
+        ad = TransformerAdapter(in_dim=48, d_model=32, num_heads=2, ffn_dim=64, norm_first=nf, num_layers=2, residual=0.5).eval()
+        g = torch.Generator().manual_seed(1)
+        B, T = 5, 3
+        valid = torch.rand(B, T, generator=g) > 0.3
+        valid[:, 0] = True
+        feats = torch.randn(B, T, 48, generator=g)
+        with torch.no_grad():
+            x = ad.in_proj(feats)
+            x = ad.transformer_encoder(x, src_key_padding_mask=~valid)
+            want = feats * 0.5 + ad.out_proj(x) * 0.5
+            got = ad.to(cuda_dev)(feats.to(cuda_dev), valid.to(cuda_dev)).cpu()
+        assert rel(got[valid], want[valid]) < 1e-4, (nf, rel(got[valid], want[valid]))

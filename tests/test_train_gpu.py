@@ -19,6 +19,7 @@ import os
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 from eventclip_b200 import clip, train
 from eventclip_b200.models import FTCLIPClassifier
@@ -172,6 +173,43 @@ def test_fused_step_whole_tower(cuda_dev, G, T):
         ft_b.model.visual.invalidate_packed()
         o2 = ft_b(dict(events=evd, event_offsets=torch.from_numpy(off)))["logits"]
     assert torch.equal(o1, o2)
+
+
+def test_probs_loss_routes_agree_and_follow_the_oracle(cuda_dev, G):
+    """loss_dict use_probs_loss=True (clip_cls_ft.py:265-267) through the autograd route and the fused FineTuner: same loss
+    and gradients bit for bit, and the loss equals the oracle head's nll of the view-averaged probabilities."""
+    def make():
+        m = clip.CLIP(ARCH)
+        m.load_state_dict(clip_oracle.build_clip(ARCH, seed=3).state_dict())
+        cd = dict(clip_model=m.to(cuda_dev).eval(), prompt="a {}", class_names=NAMES, agg_func="mean", lora="qkvo-4",
+                  only_conv1=False, only_bias=False, only_ln=False, text_feats=torch.from_numpy(G["text"]))
+        torch.manual_seed(0)
+        ft = FTCLIPClassifier(adapter_dict=dict(adapter_type="text-identity", residual=True), clip_dict=cd,
+                              loss_dict=dict(use_logits_loss=False, use_probs_loss=True)).to(cuda_dev).train()
+        cfg = SENSORS["n_cars"]
+        ft.attach_event_frontend(dict(max_imgs=2, N=3000, split_method="event_count", convert_method="event_histogram",
+                                      grayscale=True, count_non_zero=cfg["count_non_zero"],
+                                      background_mask=cfg["background_mask"]), cfg["shape"], cfg["max_n"])
+        return ft
+    ev, off = synth_batch("n_cars", 5, 41, kind="clustered", E=4000)       # 4000 events, N = 3000: one full view + a dropped tail
+    evd, labels = torch.from_numpy(ev).to(cuda_dev), torch.tensor([1, 0, 3, 2, 1])
+    ft_a, ft_b = make(), make()
+    out = ft_a(dict(events=evd, event_offsets=torch.from_numpy(off)))
+    loss_a = ft_a.calc_train_loss(dict(label=labels), out)["ce_loss"]
+    loss_a.backward()
+    probs = out["probs"].detach().float().cpu()
+    want = F.nll_loss((probs + 1e-6).log(), labels)
+    assert abs(loss_a.item() - want.item()) < 1e-4 * max(1.0, abs(want.item()))
+    tuner = train.FineTuner(ft_b, lr=1e-3, clip_lr=1e-4)
+    loss_b = tuner.forward_backward(evd, off, labels)
+    assert torch.equal(loss_a.detach().reshape(1), loss_b)
+    pa = dict(ft_a.named_parameters())
+    n_grad = 0
+    for n, p in ft_b.named_parameters():
+        if p.requires_grad:
+            assert torch.equal(tuner._grad_view(p), pa[n].grad), n
+            n_grad += int(pa[n].grad.abs().sum().item() > 0)
+    assert n_grad > 0
 
 
 def test_adam_two_learning_rates_vs_reference_golden(cuda_dev, G, T):

@@ -152,7 +152,30 @@ def test_ce_loss_bwd(cuda_dev, agg):
                                     labels.to(torch.int32).to(cuda_dev), agg)
     assert abs(lm.item() - loss.item()) < 1e-5 * max(1.0, abs(loss.item()))
     assert rel(lb, F.cross_entropy(logits, labels, reduction="none").detach()) < 1e-5
-    assert rel(dfull, full.grad) < 1e-5
+    # padded views: the reference's rows are features * valid mask, i.e. constants (clip_cls.py:330-333) -> zero gradient here
+    assert rel(dfull.cpu()[valid], full.grad[valid]) < 1e-5
+    assert (dfull.cpu()[~valid] == 0).all()
+
+
+def test_probs_loss_bwd(cuda_dev):
+    """use_probs_loss (clip_cls_ft.py:265-267): nll of log(mean-over-valid-views softmax + 1e-6), restated with torch and
+    differentiated by autograd; padded views (zero logits) get a zero gradient."""
+    g = torch.Generator().manual_seed(19)
+    for B, T, K in ((9, 3, 101), (4, 10, 1000), (5, 1, 2)):
+        valid = torch.rand(B, T, generator=g) > 0.3
+        valid[:, 0] = True
+        full = (torch.randn(B, T, K, generator=g) * 3 * valid[..., None].float()).requires_grad_(True)
+        labels = torch.randint(0, K, (B,), generator=g)
+        vm = valid.float()
+        probs = (full.softmax(-1) * vm[..., None]).sum(1) / vm.sum(1, keepdim=True)        # clip_cls.py:123-129
+        loss = F.nll_loss((probs + 1e-6).log(), labels)
+        loss.backward()
+        lb, lm, dfull = ops.probs_loss_bwd(full.detach().to(cuda_dev), valid.to(torch.uint8).to(cuda_dev),
+                                           labels.to(torch.int32).to(cuda_dev))
+        assert abs(lm.item() - loss.item()) < 1e-5 * max(1.0, abs(loss.item()))
+        assert rel(lb, F.nll_loss((probs + 1e-6).log(), labels, reduction="none").detach()) < 1e-5
+        assert rel(dfull, full.grad) < 1e-4
+        assert (dfull.cpu()[~valid] == 0).all()
 
 
 @pytest.mark.parametrize("rows,d,r,skip", [(128, 128, 4, None), (768, 768, 16, 1), (96, 200, 20, None)])
