@@ -269,6 +269,29 @@ class VisionTransformer(nn.Module):
         self._packed16 = None
         self._epoch += 1
 
+    def validate_ln_fold(self, patches, n_img, tol=1e-2):
+        """Guard of the LayerNorm folding (ln_1 -> in_proj, ln_2 -> c_fc): the folded GEMMs evaluate var = E[x^2] - mean^2 on
+        the un-centred fp16 rows, which loses log2(|mean| / sigma) bits where the LayerNorm kernel would not.  Random-init and
+        pretrained CLIP streams (per-row means of the order of sigma, a few outlier CHANNELS) are far from that regime, but a
+        tower whose rows carry |mean| >> sigma is not.  Runs the encoder once with and once without the folding on `patches`
+        and switches the folding off for this tower when the features differ by more than `tol` (relative L2) or are not
+        finite.  Returns the measured difference.  GraphedClassifier calls this on its first warm-up batch."""
+        if not (self.fold_ln and self.residual_dtype == torch.float16 and ops.gemm_stats_parts(self.width) <= 8):
+            self._fold_checked = True
+            return 0.0
+        with torch.no_grad():
+            a = self.forward_patches(patches, n_img).float()
+            self.fold_ln = False
+            b = self.forward_patches(patches, n_img).float()
+            self.fold_ln = True
+        err = float(((a - b).norm() / b.norm().clamp_min(1e-30)).item())
+        if not (err <= tol) or not bool(torch.isfinite(a).all()):
+            import warnings
+            warnings.warn(f"LayerNorm folding disabled for this tower: folded vs unfolded features differ by {err:.3g} (> {tol})")
+            self.fold_ln = False
+        self._fold_checked = True
+        return err
+
     @property
     def patch_fmt(self):
         """ec_event2img output format that feeds this tower's patch GEMM in the inference forward."""

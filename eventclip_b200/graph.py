@@ -65,6 +65,7 @@ class GraphedClassifier:
         self.max_graphs = max_graphs
         self._params = list(model.parameters())
         self._weights_sig = self._signature()
+        self._nonempty = False                # the static event buffer holds a real batch (set by the first call)
 
     def _signature(self):
         """Changes whenever a parameter is updated in place or replaced (optimizer step, load_state_dict): the captured
@@ -82,6 +83,11 @@ class GraphedClassifier:
         with torch.cuda.stream(side), torch.no_grad():      # warm-up outside capture: tables, packed weights, attributes
             for _ in range(2):
                 self.model.device_forward(self.events, e.plan, status=self.status)
+            vis = getattr(getattr(self.model, "model", None), "visual", None)
+            if vis is not None and hasattr(vis, "validate_ln_fold") and not getattr(vis, "_fold_checked", False) \
+                    and not getattr(self.model, "training", False) and self._nonempty:
+                # first real batch: check the LayerNorm folding against the LayerNorm kernels on this tower's own activations
+                vis.validate_ln_fold(self.model._last_patches, e.plan["n_valid"])
         torch.cuda.current_stream(self.dev).wait_stream(side)
         torch.cuda.synchronize(self.dev)
         e.graph = torch.cuda.CUDAGraph()
@@ -110,6 +116,8 @@ class GraphedClassifier:
         if ent is None:
             if len(self.cache) >= self.max_graphs:
                 self.cache.pop(next(iter(self.cache)))
+            self.events[:n].copy_(ev, non_blocking=True)      # the warm-up passes of _build run on this batch
+            self._nonempty = True
             ent = self.cache[key] = self._build(plan)
         else:
             _refresh_plan(ent.plan, plan)

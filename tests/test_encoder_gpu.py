@@ -118,6 +118,41 @@ def test_layernorm_folded_into_gemms(cuda_dev):
         assert rel(got2.float(), ref) < 8e-3
 
 
+def test_layernorm_folding_on_clip_like_statistics(cuda_dev):
+    """Pretrained CLIP streams are not Gaussian: a few channels sit at 50-500 x the typical magnitude on every token and rows
+    can carry a mean well away from zero.  The folded LayerNorm (var = E[x^2] - mean^2 on un-centred fp16 rows) is checked
+    against the fp32 oracle on towers engineered to have (a) two outlier channels at +80 / -60 sigma, (b) a common offset of
+    6 sigma on every channel, (c) an offset of 3000 sigma -- a regime where the folding loses most of its bits and the guard
+    (VisionTransformer.validate_ln_fold) has to switch it off."""
+    arch = "ViT-tiny/16"
+    imgs = torch.randn(6, 3, 224, 224, generator=torch.Generator().manual_seed(10))
+    for tag, edit, fold_must_hold in (("outlier_channels", lambda v: (v.ln_pre.bias.data.__setitem__(3, 80.0), v.ln_pre.bias.data.__setitem__(77, -60.0)), True),
+                                      ("row_offset_6_sigma", lambda v: v.ln_pre.bias.data.add_(6.0), True),
+                                      ("row_offset_3000_sigma", lambda v: v.ln_pre.bias.data.add_(3000.0), False)):
+        oracle = clip_oracle.build_clip(arch, seed=24)
+        edit(oracle.visual)
+        model = clip.CLIP(arch)
+        model.load_state_dict(oracle.state_dict())
+        model = model.to(cuda_dev).eval()
+        vis = model.visual
+        assert vis.fold_ln and vis.residual_dtype == torch.float16
+        with torch.no_grad():
+            ref = oracle.encode_image(imgs)
+            patches = ops.im2col(imgs.to(cuda_dev), vis.patch_size, vis.k_patch, dtype=vis.operand_dtype)
+            diff = vis.validate_ln_fold(patches, imgs.shape[0])
+            got = model.encode_image(imgs.to(cuda_dev)).cpu()
+        from parity_util import record_metric
+        record_metric("ln_fold_robustness", case=tag, fold_vs_unfolded=diff, fold_kept=bool(vis.fold_ln), rel_l2=rel(got, ref))
+        if fold_must_hold:
+            assert vis.fold_ln and diff < 1e-2, (tag, diff)
+            assert rel(got, ref) < 2e-2, (tag, rel(got, ref))
+        else:
+            # the guard notices and falls back to the LayerNorm kernels; fp16 cannot hold a 3000-sigma offset exactly either
+            # (2^-11 * 3000 = 1.5 sigma per element), so only the switch itself and finiteness are asserted
+            assert not vis.fold_ln, (tag, diff)
+            assert torch.isfinite(got).all()
+
+
 def test_layernorm_and_helpers(cuda_dev):
     g = torch.Generator().manual_seed(4)
     for M, d in ((37, 768), (5, 1024), (9, 128), (3, 2048)):
