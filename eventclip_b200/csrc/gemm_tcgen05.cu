@@ -292,6 +292,87 @@ __device__ __forceinline__ float4 bias4(const float *bias, int col, int N)
     return b;
 }
 
+// the 32 biases of a chunk whose columns are all inside N and whose bias vector is 16-byte aligned: 8 broadcast loads, no
+// per-load range checks (ncu: the checked helper was 17 % of the kernel's instructions in the K = 768 GEMMs)
+__device__ __forceinline__ void bias_chunk(const float *bias, int col0, int N, bool fast, float4 (&bq)[8])
+{
+    if (fast) {
+        const float4 *bp = reinterpret_cast<const float4 *>(bias + col0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) bq[q] = __ldg(bp + q);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) bq[q] = bias4(bias, col0 + 4 * q, N);
+    }
+}
+
+// (tm, tn) of the tiles a CTA group walks over (tile, tile + step, ...) without a division per tile
+struct TileWalk {
+    int tm, tn, dq, dr, tiles_n;
+    __device__ __forceinline__ TileWalk(int first, int step, int tiles_n_) : tiles_n(tiles_n_)
+    {
+        tm = first / tiles_n_; tn = first - tm * tiles_n_;
+        dq = step / tiles_n_; dr = step - dq * tiles_n_;
+    }
+    __device__ __forceinline__ void next()
+    {
+        tm += dq; tn += dr;
+        if (tn >= tiles_n) { tn -= tiles_n; ++tm; }
+    }
+};
+
+// packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2: one issue slot for two lanes) -- the epilogues of the K = 768 GEMMs are
+// issue-bound on their eight warps, so every per-element instruction counts
+struct f2 { unsigned long long v; };
+__device__ __forceinline__ f2 mk2(float a, float b)
+{
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ f2 mk2u(uint32_t a, uint32_t b)
+{
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ void un2(f2 x, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x.v)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c)
+{
+    f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b)
+{
+    f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b)
+{
+    f2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+// QuickGELU of a pair: x sigmoid(1.702 x) = h + h tanh(1.702 h), h = x / 2 (see quick_gelu below)
+__device__ __forceinline__ f2 quick_gelu2(f2 x)
+{
+    const f2 h = mul2(x, mk2(0.5f, 0.5f));
+    const f2 a = mul2(h, mk2(1.702f, 1.702f));
+    float a0, a1, t0, t1;
+    un2(a, a0, a1);
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(a0));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(a1));
+    return fma2(h, mk2(t0, t1), h);
+}
+__device__ __forceinline__ uint32_t pack16x2_2(f2 x, int f16)
+{
+    float a, b;
+    un2(x, a, b);
+    return pack16x2(a, b, f16);
+}
+
 __device__ __forceinline__ float quick_gelu(float x)
 {
     // x * sigmoid(1.702 x) with sigmoid(y) = 0.5 tanh(y/2) + 0.5: one SFU op (MUFU.TANH) per element instead of
@@ -477,18 +558,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             // are fetched while the current one is processed (this epilogue is the critical path of the K = 768 GEMMs)
             // The raw partials stay in registers until the next tile starts, so the loads never stall this in-order warp.
             float4 nt[4];             // <= 8 partial (sum, sum of squares) pairs of the next tile's row
-            auto fetch_stats = [&](int tile_) {
+            auto fetch_stats = [&](int tile_, int tm_) {
                 const bool on = p.ln_stats && tile_ < num_tiles;
-                const int r = min(((tile_ / p.tiles_n) * CG + (int)cta_rank) * BM + quarter * 32 + lane, p.M - 1);
+                const int r = min((tm_ * CG + (int)cta_rank) * BM + quarter * 32 + lane, p.M - 1);
                 const float4 *sp = reinterpret_cast<const float4 *>(p.ln_stats + (size_t)(on ? r : 0) * p.ln_parts);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) nt[i] = (on && 2 * i < p.ln_parts) ? __ldg(sp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             };
-            fetch_stats(group_id);
-            for (int tile = group_id; tile < num_tiles; tile += num_groups) {
-                const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+            TileWalk tw(group_id, num_groups, p.tiles_n), tw_next(group_id, num_groups, p.tiles_n);
+            fetch_stats(group_id, tw.tm);
+            for (int tile = group_id; tile < num_tiles; tile += num_groups, tw.next()) {
+                const int tm = tw.tm, tn = tw.tn;
                 const int row0 = (tm * CG + (int)cta_rank) * BM + quarter * 32;
                 const int colw = tn * BN + half * COLS_PER_WARP;
+                const bool bias_fast = p.bias && colw + COLS_PER_WARP <= p.N && ((uintptr_t)p.bias & 15) == 0;
                 float ln_r = 1.f, ln_m = 0.f;
                 if (p.ln_stats) {
                     const float s1 = (nt[0].x + nt[0].z) + (nt[1].x + nt[1].z) + (nt[2].x + nt[2].z) + (nt[3].x + nt[3].z);
@@ -496,7 +579,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     const float mean = s1 * p.inv_k;
                     ln_r = rsqrtf(fmaxf(s2 * p.inv_k - mean * mean, 0.f) + 1e-5f);
                     ln_m = -mean * ln_r;
-                    fetch_stats(tile + num_groups);
+                    tw_next.next();
+                    fetch_stats(tile + num_groups, tw_next.tm);
                 }
                 mbar_wait(&tfull_bar[as], aphase);
                 tc_fence_after();
@@ -508,8 +592,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 auto chunk = [&](const int c, uint32_t (&v)[32], uint32_t (&vn)[32]) {
                     const int col0 = colw + c * 32;
                     float4 bq[8];                            // the 32 biases of this chunk: 8 broadcast loads
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) bq[q] = bias4(p.bias, col0 + 4 * q, p.N);
+                    bias_chunk(p.bias, col0, p.N, bias_fast, bq);
                     if (p.ln_stats && p.ln_colsum) {         // c_j - mean rstd s_j (not needed when the rows of Wg sum to zero)
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
@@ -522,16 +605,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     if (c + 1 < NCHUNK) tmem_ld32_issue(tbase + (uint32_t)((c + 1) * 32), vn);
                     uint32_t pk[16];
 #pragma unroll
+                    const f2 lnr2 = mk2(ln_r, ln_r);
                     for (int q = 0; q < 8; ++q) {
-                        const float f0 = fmaf(__uint_as_float(v[4 * q]), ln_r, bq[q].x), f1 = fmaf(__uint_as_float(v[4 * q + 1]), ln_r, bq[q].y);
-                        const float f2 = fmaf(__uint_as_float(v[4 * q + 2]), ln_r, bq[q].z), f3 = fmaf(__uint_as_float(v[4 * q + 3]), ln_r, bq[q].w);
-                        if (p.epi == EC_EPI_BF16_QGELU) {
-                            pk[2 * q] = pack16x2(quick_gelu(f0), quick_gelu(f1), p.out_f16);
-                            pk[2 * q + 1] = pack16x2(quick_gelu(f2), quick_gelu(f3), p.out_f16);
-                        } else {
-                            pk[2 * q] = pack16x2(f0, f1, p.out_f16);
-                            pk[2 * q + 1] = pack16x2(f2, f3, p.out_f16);
-                        }
+                        f2 g01 = fma2(mk2u(v[4 * q], v[4 * q + 1]), lnr2, mk2(bq[q].x, bq[q].y));
+                        f2 g23 = fma2(mk2u(v[4 * q + 2], v[4 * q + 3]), lnr2, mk2(bq[q].z, bq[q].w));
+                        if (p.epi == EC_EPI_BF16_QGELU) { g01 = quick_gelu2(g01); g23 = quick_gelu2(g23); }
+                        pk[2 * q] = pack16x2_2(g01, p.out_f16);
+                        pk[2 * q + 1] = pack16x2_2(g23, p.out_f16);
                     }
                     const uint32_t box = stg + (nbox & 1) * 2048;
                     if (lane == 0) bulk_wait_read<1>();       // the store issued two boxes ago has drained this buffer
@@ -568,18 +648,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             //      the same box goes back out through a TMA store.  No per-thread global loads or stores. ----
             uint32_t as = 0, aphase = 0, nbox = 0;
             uint64_t *rb = res_bar[ew];
-            auto load_res = [&](int tile_, int c_, uint32_t n_) {     // lane 0 only
-                const int tm_ = tile_ / p.tiles_n, tn_ = tile_ % p.tiles_n;
+            auto load_res = [&](int tm_, int tn_, int c_, uint32_t n_) {     // lane 0 only
                 const int r_ = (tm_ * CG + (int)cta_rank) * BM + quarter * 32;
                 const int c0_ = tn_ * BN + half * COLS_PER_WARP + c_ * 32;
                 mbar_expect_tx(&rb[n_ & 1], 4096);
                 tma_load_2d(smem + STAGES * STAGE_BYTES + ew * STG_WARP_BYTES + (n_ & 1) * 4096, &map_r, &rb[n_ & 1], c0_, r_);
             };
-            if (lane == 0 && group_id < num_tiles) load_res(group_id, 0, 0);
-            for (int tile = group_id; tile < num_tiles; tile += num_groups) {
-                const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+            TileWalk tw(group_id, num_groups, p.tiles_n), tw_next(group_id, num_groups, p.tiles_n);
+            if (lane == 0 && group_id < num_tiles) load_res(tw.tm, tw.tn, 0, 0);
+            for (int tile = group_id; tile < num_tiles; tile += num_groups, tw.next()) {
+                const int tm = tw.tm, tn = tw.tn;
+                tw_next.next();
                 const int row0 = (tm * CG + (int)cta_rank) * BM + quarter * 32;
                 const int colw = tn * BN + half * COLS_PER_WARP;
+                const bool bias_fast = p.bias && colw + COLS_PER_WARP <= p.N && ((uintptr_t)p.bias & 15) == 0;
                 mbar_wait(&tfull_bar[as], aphase);
                 tc_fence_after();
                 const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * COLS_PER_WARP);
@@ -589,13 +671,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 for (int c = 0; c < NCHUNK; ++c) {
                     const int col0 = colw + c * 32;
                     float4 bq[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) bq[q] = bias4(p.bias, col0 + 4 * q, p.N);
+                    bias_chunk(p.bias, col0, p.N, bias_fast, bq);
                     // prefetch the next residual box (next chunk, or first chunk of this CTA's next tile)
                     if (lane == 0) {
                         bulk_wait_read<0>();     // the store that last used the other buffer has finished reading it
-                        if (c + 1 < NCHUNK) load_res(tile, c + 1, nbox + 1);
-                        else if (tile + num_groups < num_tiles) load_res(tile + num_groups, 0, nbox + 1);
+                        if (c + 1 < NCHUNK) load_res(tm, tn, c + 1, nbox + 1);
+                        else if (tile + num_groups < num_tiles) load_res(tw_next.tm, tw_next.tn, 0, nbox + 1);
                     }
                     const uint32_t box = stg + (nbox & 1) * 4096;
                     mbar_wait(&rb[nbox & 1], (nbox >> 1) & 1);
@@ -632,34 +713,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             //      [32 rows x 32 halves] boxes (64-byte rows, SWIZZLE_64B): half the residual bytes in and out. ----
             uint32_t as = 0, aphase = 0, nbox = 0;
             uint64_t *rb = res_bar[ew];
-            auto load_res = [&](int tile_, int c_, uint32_t n_) {     // lane 0 only
-                const int tm_ = tile_ / p.tiles_n, tn_ = tile_ % p.tiles_n;
+            auto load_res = [&](int tm_, int tn_, int c_, uint32_t n_) {     // lane 0 only
                 const int r_ = (tm_ * CG + (int)cta_rank) * BM + quarter * 32;
                 const int c0_ = tn_ * BN + half * COLS_PER_WARP + c_ * 32;
                 mbar_expect_tx(&rb[n_ & 1], 2048);
                 tma_load_2d(smem + STAGES * STAGE_BYTES + ew * STG_WARP_BYTES + (n_ & 1) * 2048, &map_r, &rb[n_ & 1], c0_, r_);
             };
-            if (lane == 0 && group_id < num_tiles) load_res(group_id, 0, 0);
-            for (int tile = group_id; tile < num_tiles; tile += num_groups) {
-                const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+            TileWalk tw(group_id, num_groups, p.tiles_n), tw_next(group_id, num_groups, p.tiles_n);
+            if (lane == 0 && group_id < num_tiles) load_res(tw.tm, tw.tn, 0, 0);
+            for (int tile = group_id; tile < num_tiles; tile += num_groups, tw.next()) {
+                const int tm = tw.tm, tn = tw.tn;
+                tw_next.next();                      // coordinates of this CTA's next tile (first residual box prefetched below)
                 const int row0 = (tm * CG + (int)cta_rank) * BM + quarter * 32;
                 const int colw = tn * BN + half * COLS_PER_WARP;
+                const bool bias_fast = p.bias && colw + COLS_PER_WARP <= p.N && ((uintptr_t)p.bias & 15) == 0;
                 mbar_wait(&tfull_bar[as], aphase);
                 tc_fence_after();
                 const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * COLS_PER_WARP);
                 uint32_t v[32];
                 tmem_ld32_issue(tbase, v);
-                float st1 = 0.f, st2 = 0.f;      // this row's sum / sum of squares over the warp's 128 columns (as rounded to fp16)
+                f2 st1x = mk2(0.f, 0.f), st2x = mk2(0.f, 0.f);   // this row's sum / sum of squares over the warp's 128 columns, as
+                                                                 // even / odd column partial sums (packed fp32 pairs)
 #pragma unroll 1
                 for (int c = 0; c < NCHUNK; ++c) {
                     const int col0 = colw + c * 32;
                     float4 bq[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) bq[q] = bias4(p.bias, col0 + 4 * q, p.N);
+                    bias_chunk(p.bias, col0, p.N, bias_fast, bq);
                     if (lane == 0) {
                         bulk_wait_read<0>();     // the store that last used the other buffer has finished reading it
-                        if (c + 1 < NCHUNK) load_res(tile, c + 1, nbox + 1);
-                        else if (tile + num_groups < num_tiles) load_res(tile + num_groups, 0, nbox + 1);
+                        if (c + 1 < NCHUNK) load_res(tm, tn, c + 1, nbox + 1);
+                        else if (tile + num_groups < num_tiles) load_res(tw_next.tm, tw_next.tn, 0, nbox + 1);
                     }
                     const uint32_t box = stg + (nbox & 1) * 2048;
                     mbar_wait(&rb[nbox & 1], (nbox >> 1) & 1);
@@ -676,14 +759,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                         for (int e = 0; e < 4; ++e) {
                             const float2 r = __half22float2(*reinterpret_cast<const __half2 *>(&hw[e]));
                             const float4 b = bq[2 * q + (e >> 1)];
-                            const float b0 = (e & 1) ? b.z : b.x, b1 = (e & 1) ? b.w : b.y;
-                            const float o0 = r.x + __uint_as_float(v[8 * q + 2 * e]) + b0, o1 = r.y + __uint_as_float(v[8 * q + 2 * e + 1]) + b1;
-                            const __half2 o = __floats2half2_rn(o0, o1);
-                            ow[e] = *reinterpret_cast<const uint32_t *>(&o);
+                            const f2 bb = (e & 1) ? mk2(b.z, b.w) : mk2(b.x, b.y);
+                            const f2 o = add2(add2(mk2(r.x, r.y), mk2u(v[8 * q + 2 * e], v[8 * q + 2 * e + 1])), bb);
+                            ow[e] = pack16x2_2(o, 1);
                             // statistics of the values before their fp16 rounding (2^-12 relative apart from what the consumer
                             // reads); columns >= N hold exact zeros (zero-filled operands, bias and residual)
-                            st1 += o0 + o1;
-                            st2 = fmaf(o0, o0, fmaf(o1, o1, st2));
+                            st1x = add2(st1x, o);
+                            st2x = fma2(o, o, st2x);
                         }
                         sts128u(a, ow[0], ow[1], ow[2], ow[3]);
                     }
@@ -693,8 +775,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     if (lane == 0 && row0 < p.M && col0 < p.N) tma_store_2d(&map_o, box, col0, row0);
                     ++nbox;
                 }
-                if (p.stats_out && row0 + lane < p.M)
-                    p.stats_out[(size_t)(row0 + lane) * (2 * p.tiles_n) + 2 * tn + half] = make_float2(st1, st2);
+                if (p.stats_out && row0 + lane < p.M) {
+                    float s1a, s1b, s2a, s2b;
+                    un2(st1x, s1a, s1b);
+                    un2(st2x, s2a, s2b);
+                    p.stats_out[(size_t)(row0 + lane) * (2 * p.tiles_n) + 2 * tn + half] = make_float2(s1a + s1b, s2a + s2b);
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {

@@ -48,6 +48,12 @@ def main():
     tab = line_table(obj, kernel)
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
+    launch = next((int(a.split("=")[1]) for a in sys.argv[4:] if a.startswith("launch=")), 0)
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]      # one section per profiled launch
+    if starts:
+        lo = starts[min(launch, len(starts) - 1)]
+        hi_ = starts[launch + 1] if launch + 1 < len(starts) else len(rows)
+        rows = rows[lo:hi_]
     hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     hdr = rows[hi]
     ix = {h: i for i, h in enumerate(hdr)}
@@ -67,7 +73,8 @@ def main():
             stall[line][h] += int(r[ix[h]] or 0)
     ti, ts = sum(inst.values()), sum(samp.values())
     print(f"total warp instructions {ti}, stall samples {ts}")
-    src = open("/root/repo/eventclip_b200/csrc/event2img.cu").read().splitlines() if "event2img" in kernel else []
+    srcfile = next((a.split("=")[1] for a in sys.argv[4:] if a.startswith("src=")), "eventclip_b200/csrc/event2img.cu")
+    src = open(srcfile).read().splitlines()
     print("\n-- lines by executed warp instructions")
     for line, n in inst.most_common(top):
         t = src[line - 1].strip()[:90] if 0 < line <= len(src) else ""
