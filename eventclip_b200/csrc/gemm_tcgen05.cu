@@ -56,6 +56,7 @@ struct GemmParams {
     // LayerNorm folded into the GEMMs (ec_gemm_ln / ec_gemm_bf16_stats):
     int a_f16;                 // both operands hold fp16 (A = the residual stream itself, W = fp16(gamma * W)) instead of bf16
     int out_f16;               // EC_EPI_BF16 / EC_EPI_BF16_QGELU write fp16 instead of bf16 (EC_EPI_F16_OPERANDS)
+    int res_ring;              // EC_EPI_F16_RESADD: residual boxes in flight per epilogue warp (4, or 2 with EC_GEMM_RING=2)
     const float2 *ln_stats;    // consumer: [M, ln_parts] partial (sum x, sum x^2) of every row of A; NULL = plain epilogue
     int ln_parts;
     const float *ln_colsum;    // consumer: s_j = sum_k W'[j,k] of the gamma-scaled weight; `bias` holds c_j = beta . W[j] + b_j
@@ -407,7 +408,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     __shared__ __align__(8) uint64_t tfull_bar[2];
     __shared__ __align__(8) uint64_t tempty_bar[2];
     __shared__ uint32_t tmem_base_slot;
-    __shared__ __align__(8) uint64_t res_bar[EPI_WARPS][2];   // residual boxes landed (fp32 residual epilogue)
+    __shared__ __align__(8) uint64_t res_bar[EPI_WARPS][4];   // residual boxes landed (two fp32 boxes or a ring of four fp16 boxes per warp)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -421,7 +422,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_o) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], EPI_WARPS * CG); }
-        for (int w = 0; w < EPI_WARPS; ++w) { mbar_init(&res_bar[w][0], 1); mbar_init(&res_bar[w][1], 1); }
+        for (int w = 0; w < EPI_WARPS; ++w)
+            for (int b = 0; b < 4; ++b) mbar_init(&res_bar[w][b], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -710,17 +712,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         } else if (p.epi == EC_EPI_F16_RESADD) {
             // ---- fp16 residual stream (the reference's CUDA precision): same in-place box scheme as above with
-            //      [32 rows x 32 halves] boxes (64-byte rows, SWIZZLE_64B): half the residual bytes in and out. ----
+            //      [32 rows x 32 halves] boxes (64-byte rows, SWIZZLE_64B): half the residual bytes in and out.  The warp's
+            //      8 KB of staging hold a ring of FOUR boxes: the residual of chunk n + 2 is requested while chunk n is processed
+            //      (a TMA load from L2 takes about as long as a chunk at tensor-core pace, so one box ahead was exposed). ----
             uint32_t as = 0, aphase = 0, nbox = 0;
             uint64_t *rb = res_bar[ew];
+            const uint32_t RM = (uint32_t)p.res_ring - 1u, RS = p.res_ring == 4 ? 2u : 1u, PF = (uint32_t)p.res_ring >> 1;   // ring mask, log2, prefetch distance
             auto load_res = [&](int tm_, int tn_, int c_, uint32_t n_) {     // lane 0 only
                 const int r_ = (tm_ * CG + (int)cta_rank) * BM + quarter * 32;
                 const int c0_ = tn_ * BN + half * COLS_PER_WARP + c_ * 32;
-                mbar_expect_tx(&rb[n_ & 1], 2048);
-                tma_load_2d(smem + STAGES * STAGE_BYTES + ew * STG_WARP_BYTES + (n_ & 1) * 2048, &map_r, &rb[n_ & 1], c0_, r_);
+                mbar_expect_tx(&rb[n_ & RM], 2048);
+                tma_load_2d(smem + STAGES * STAGE_BYTES + ew * STG_WARP_BYTES + (n_ & RM) * 2048, &map_r, &rb[n_ & RM], c0_, r_);
             };
             TileWalk tw(group_id, num_groups, p.tiles_n), tw_next(group_id, num_groups, p.tiles_n);
-            if (lane == 0 && group_id < num_tiles) load_res(tw.tm, tw.tn, 0, 0);
+            if (lane == 0 && group_id < num_tiles) {
+                load_res(tw.tm, tw.tn, 0, 0);
+                if (PF == 2) load_res(tw.tm, tw.tn, 1, 1);      // NCHUNK >= 2
+            }
             for (int tile = group_id; tile < num_tiles; tile += num_groups, tw.next()) {
                 const int tm = tw.tm, tn = tw.tn;
                 tw_next.next();                      // coordinates of this CTA's next tile (first residual box prefetched below)
@@ -740,12 +748,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     float4 bq[8];
                     bias_chunk(p.bias, col0, p.N, bias_fast, bq);
                     if (lane == 0) {
-                        bulk_wait_read<0>();     // the store that last used the other buffer has finished reading it
-                        if (c + 1 < NCHUNK) load_res(tm, tn, c + 1, nbox + 1);
-                        else if (tile + num_groups < num_tiles) load_res(tw_next.tm, tw_next.tn, 0, nbox + 1);
+                        // the store of chunk n - PF (last user of the box chunk n + PF lands in) has been read
+                        if (PF == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+                        const int cn = c + (int)PF;
+                        if (cn < NCHUNK) load_res(tm, tn, cn, nbox + PF);
+                        else if (tile + num_groups < num_tiles) load_res(tw_next.tm, tw_next.tn, cn - NCHUNK, nbox + PF);
                     }
-                    const uint32_t box = stg + (nbox & 1) * 2048;
-                    mbar_wait(&rb[nbox & 1], (nbox >> 1) & 1);
+                    const uint32_t box = stg + (nbox & RM) * 2048;
+                    mbar_wait(&rb[nbox & RM], (nbox >> RS) & 1);
                     tmem_ld_wait();
                     const uint32_t rowaddr = box + (uint32_t)lane * 64;
                     const uint32_t sw = (uint32_t)((lane >> 1) & 3);
@@ -1232,6 +1242,10 @@ int gemm_impl(const void *A, int lda, const void *W, int ldw, const float *bias,
     p.mn_major = mn_major;
     p.a_f16 = ex ? ex->a_f16 : 0;
     p.out_f16 = ex ? ex->out_f16 : 0;
+    {
+        static const int ring = getenv("EC_GEMM_RING") && atoi(getenv("EC_GEMM_RING")) == 2 ? 2 : 4;
+        p.res_ring = ring;
+    }
     p.ln_stats = ex ? reinterpret_cast<const float2 *>(ex->ln_stats) : nullptr;
     p.ln_parts = ex ? ex->ln_parts : 0;
     p.ln_colsum = ex ? ex->ln_colsum : nullptr;
