@@ -504,7 +504,9 @@ def other_inference_config(cname, dev, rank, world, K, barrier, pk, parity_n):
              ms_per_step=ms, samples_per_s=world * w.B / ms * 1e3, views_per_s=world * nv / ms * 1e3,
              encoder_tflops=fl / ms / 1e9, encoder_frac_of_peak=fl / ms / 1e9 / peak,
              e2e=dict(value=world * w.B * K / float(dt.item()), unit="samples/s",
-                      h2d_bytes_per_step=int(w.host[0][0].numel() * 4), d2h_bytes_per_step=w.B * 4))
+                      h2d_bytes_per_step=int(g.h2d_bytes // K + nv * 16), d2h_bytes_per_step=w.B * 4 + 4,
+                      events_in_host_batch_bytes=int(w.host[0][0].numel() * 4),
+                      note="only the event ranges the frame plan reads are uploaded (2 of 14 chunks per N-ImageNet sample)"))
     if rank == 0 and parity_n > 0:
         try:
             with torch.no_grad():

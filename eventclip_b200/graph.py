@@ -53,6 +53,34 @@ def _plan_key(plan):
     return (plan["frames"].shape[0], plan["n_valid"], plan["B"], plan["T"])
 
 
+_FRAME_DT = [("s", "<i8"), ("n", "<i4"), ("o", "<i4")]
+
+
+def _used_ranges(plan, n_events, min_saving=0.25):
+    """When the plan reads only part of a HOST event stream (N-ImageNet: 2 of 14 chunks per sample), the rest need not cross
+    PCIe.  Returns (ranges, plan') with ranges = [(src_start, count, dst_start)] of the events the frames histogram, packed
+    back to back, and plan' = the plan with its frame table re-based onto that packing; (None, plan) when nearly everything
+    is used anyway.  Overlapping chunks (a tail chunk starting inside its predecessor, vis.py:55-72) are copied once each."""
+    import numpy as np
+    rec = np.frombuffer(plan["frames"].numpy().tobytes(), dtype=_FRAME_DT).copy()
+    used = int(rec["n"].clip(min=0).sum())
+    if used >= (1.0 - min_saving) * n_events:
+        return None, plan
+    ranges, cur = [], 0
+    for i in range(rec.shape[0]):
+        c = int(rec["n"][i])
+        if c <= 0:
+            continue
+        ranges.append((int(rec["s"][i]), c, cur))
+        rec["s"][i] = cur
+        cur += c
+    frames = torch.from_numpy(np.frombuffer(rec.tobytes(), dtype=np.uint8).reshape(-1, 16).copy())
+    p2 = dict(plan)
+    p2["frames"] = frames.pin_memory() if torch.cuda.is_available() else frames
+    p2["_n_events"] = cur
+    return ranges, p2
+
+
 class GraphedClassifier:
     def __init__(self, model, max_events, max_graphs=8):
         self.model = model
@@ -100,10 +128,28 @@ class GraphedClassifier:
 
     def __call__(self, data_dict):
         """data_dict: {'events' float32 [sum E,4] (pinned host or CUDA), 'event_offsets', optional 'sel_idx'}.
-        Returns the classifier's out_dict; its tensors are the graph's static outputs (overwritten by the next call)."""
+        Returns the classifier's out_dict; its tensors are the graph's static outputs (overwritten by the next call).
+        Host events are copied range by range when the plan uses only part of the stream (see _used_ranges)."""
         plan = self.model.plan_events(data_dict["event_offsets"], data_dict.get("sel_idx", None))
         ev = data_dict["events"]
-        n = ev.shape[0]
+        ranges = None
+        if not ev.is_cuda:
+            ranges, plan = _used_ranges(plan, ev.shape[0])
+        return self._run(plan, ev, ranges)
+
+    def _copy_in(self, dst, ev, ranges):
+        """events -> dst (device), whole or as the packed ranges of _used_ranges; returns the bytes moved."""
+        if ranges is None:
+            dst[:ev.shape[0]].copy_(ev, non_blocking=True)
+            return ev.shape[0] * 16
+        for s0, c, d0 in ranges:
+            dst[d0:d0 + c].copy_(ev[s0:s0 + c], non_blocking=True)
+        return sum(c for _, c, _ in ranges) * 16
+
+    def _run(self, plan, ev, ranges, staged=False):
+        """Replay (or capture) the graph of this plan's geometry on `ev`: a host / device event tensor, or -- staged=True --
+        a device tensor that already holds the packed ranges."""
+        n = plan.get("_n_events", ev.shape[0])
         if n > self.events.shape[0]:
             raise L.ECError(f"batch has {n} events but the graph buffer holds {self.events.shape[0]}")
         sig = self._signature()
@@ -113,15 +159,17 @@ class GraphedClassifier:
             self._weights_sig = sig
         key = _plan_key(plan)
         ent = self.cache.get(key)
+        fill = (lambda: self.events[:n].copy_(ev[:n], non_blocking=True)) if staged or ranges is None else \
+            (lambda: self._copy_in(self.events, ev, ranges))
         if ent is None:
             if len(self.cache) >= self.max_graphs:
                 self.cache.pop(next(iter(self.cache)))
-            self.events[:n].copy_(ev, non_blocking=True)      # the warm-up passes of _build run on this batch
+            fill()                                # the warm-up passes of _build run on this batch
             self._nonempty = True
             ent = self.cache[key] = self._build(plan)
         else:
             _refresh_plan(ent.plan, plan)
-        self.events[:n].copy_(ev, non_blocking=True)
+        fill()
         ent.graph.replay()
         L.LAUNCHES += ent.n_launch
         return ent.out
@@ -158,28 +206,38 @@ class GraphedClassifier:
                 ops.raise_on_status(host_st[j])
             return host_res[j].clone()
 
+        plans = [None, None]
+        self.h2d_bytes = 0                                            # event bytes uploaded by the last stream() (all batches)
+
         def upload(i, d):
             ev = d["events"]
-            if ev.is_cuda:
-                return
-            if not ev.is_pinned():
-                raise L.ECError("GraphedClassifier.stream: host events must be pinned (torch.Tensor.pin_memory())")
-            if ev.shape[0] > self.events.shape[0]:
-                raise L.ECError(f"batch has {ev.shape[0]} events but the graph buffer holds {self.events.shape[0]}")
-            with torch.cuda.stream(self._copy):
-                if i >= 2:
-                    self._copy.wait_event(self._consumed[i % 2])      # batch i-2 has left this staging buffer
-                self._stage[i % 2][:ev.shape[0]].copy_(ev, non_blocking=True)
-                self._uploaded[i % 2].record(self._copy)
+            plan = self.model.plan_events(d["event_offsets"], d.get("sel_idx", None))
+            ranges = None
+            if not ev.is_cuda:
+                if not ev.is_pinned():
+                    raise L.ECError("GraphedClassifier.stream: host events must be pinned (torch.Tensor.pin_memory())")
+                ranges, plan = _used_ranges(plan, ev.shape[0])
+                if ranges is None:
+                    plan = dict(plan, _n_events=ev.shape[0])
+                n = plan["_n_events"]
+                if n > self.events.shape[0]:
+                    raise L.ECError(f"batch has {n} events but the graph buffer holds {self.events.shape[0]}")
+                with torch.cuda.stream(self._copy):
+                    if i >= 2:
+                        self._copy.wait_event(self._consumed[i % 2])      # batch i-2 has left this staging buffer
+                    self.h2d_bytes += self._copy_in(self._stage[i % 2], ev, ranges)
+                    self._uploaded[i % 2].record(self._copy)
+            plans[i % 2] = plan
 
         def launch(i, d):
             ev = d["events"]
+            plan = plans[i % 2]
             if not ev.is_cuda:
                 cur.wait_event(self._uploaded[i % 2])
-                ev = self._stage[i % 2][:ev.shape[0]]
+                ev = self._stage[i % 2]
             if pre is not None:
                 pre()
-            out = self(dict(d, events=ev))                            # device-to-device copy into the graph's input + replay
+            out = self._run(plan, ev, None, staged=True)              # device-to-device copy into the graph's input + replay
             self._consumed[i % 2].record(cur)
             r = result(out)
             if host_res[i % 2] is None or host_res[i % 2].shape != r.shape or host_res[i % 2].dtype != r.dtype:

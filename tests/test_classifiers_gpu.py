@@ -430,3 +430,32 @@ def test_post_norm_adapter_forward_vs_torch(cuda_dev):
             want = feats * 0.5 + ad.out_proj(x) * 0.5
             got = ad.to(cuda_dev)(feats.to(cuda_dev), valid.to(cuda_dev)).cpu()
         assert rel(got[valid], want[valid]) < 1e-4, (nf, rel(got[valid], want[valid]))
+
+
+def test_partial_upload_of_host_events_matches_full_upload(cuda_dev):
+    """N-ImageNet-shaped samples use 2 of 14 chunks: GraphedClassifier copies only those event ranges from pinned host memory
+    (re-based frame table) -- same logits as the whole stream resident on the device, through __call__ and stream()."""
+    from eventclip_b200.graph import GraphedClassifier
+    cfg = SENSORS["n_imagenet"]
+    q = dict(max_imgs=10, N=cfg["N"], split_method="event_count", convert_method="event_histogram", grayscale=True,
+             count_non_zero=False, background_mask=True)
+    model = clip.init_weights_(clip.CLIP("ViT-tiny/32"), seed=8).to(cuda_dev).eval()
+    zs = ZSCLIPClassifier(clip_dict=dict(clip_model=model, prompt="a {}", class_names=None, agg_func="mean",
+                                         text_feats=clip_oracle.synth_text_feats(7, 64, 9))).to(cuda_dev).eval()
+    zs.attach_event_frontend(q, cfg["shape"], cfg["max_n"])
+    batches = []
+    for seed, lens in ((1, [400000, 300001]), (2, [400000, 300001]), (3, [150000, 400000])):
+        evs = [synth_batch("n_imagenet", 1, seed * 10 + i, E=E)[0] for i, E in enumerate(lens)]
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        sel = zs.event_frontend.draw_selection(off, generator=torch.Generator().manual_seed(seed))
+        batches.append(dict(events=torch.from_numpy(np.concatenate(evs)).pin_memory(), event_offsets=torch.from_numpy(off),
+                            sel_idx=torch.from_numpy(sel)))
+    g = GraphedClassifier(zs, max_events=800000)
+    with torch.no_grad():
+        want = [zs(dict(d, events=d["events"].to(cuda_dev)))["logits"].cpu().clone() for d in batches]
+        got_call = [g(d)["logits"].cpu().clone() for d in batches]
+        got_stream = list(g.stream(iter(batches), result=lambda out: out["logits"]))
+    for a, b, c in zip(want, got_call, got_stream):
+        assert torch.equal(a, b) and torch.equal(a, c)
+    used = 3 * 2 * 2 * 70000 * 16
+    assert g.h2d_bytes == used, (g.h2d_bytes, used)          # 2 views x 70 000 events per sample instead of 700 001 / 550 000 events
