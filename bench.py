@@ -82,7 +82,9 @@ def qargs(cfg, max_imgs=10):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    """nvidia-smi clocks / throttle reasons during the timed work (B200_PROFILING.md clocks line): started before the
+    device-timed region and stopped after the end-to-end loop -- the same steps under the same load -- because the timed
+    region alone (K x 9 ms) is shorter than nvidia-smi's first few sampling periods."""
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
@@ -92,7 +94,7 @@ class ClockSampler:
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
                                          text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
@@ -701,14 +703,20 @@ def b200_arm(args):
     barrier()
     l0 = _lib.LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
-        e0.record()
-        for i in range(K):
-            step(i)
-        if world > 1:
-            dist.all_reduce(counters)                    # the only collective of the inference path
-        e1.record()
-        barrier()
+    clk = ClockSampler(local)
+    clk.__enter__()
+    for i in range(2):                                   # nvidia-smi is up and sampling before the timed steps start
+        step(i)
+    barrier()
+    counters.zero_()
+    l0 = _lib.LAUNCHES
+    e0.record()
+    for i in range(K):
+        step(i)
+    if world > 1:
+        dist.all_reduce(counters)                        # the only collective of the inference path
+    e1.record()
+    barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     launches = _lib.LAUNCHES - l0
     if world > 1:
@@ -726,6 +734,7 @@ def b200_arm(args):
             in_step = dict(keys=gemm_log[2 * n_g:], dur_us=dur_us)
 
     if args.quick:
+        clk.__exit__()
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": value, "ms_per_step": ms_total / K, "gpu_launches": launches, "quick": True}))
         if world > 1:
@@ -756,6 +765,7 @@ def b200_arm(args):
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e = world * B * K / float(dt.item())
+    clk.__exit__()
     h2d = host[0][0].numel() * 4 + B * T * 16
     d2h = B * 4 + 4
 
