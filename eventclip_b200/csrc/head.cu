@@ -55,6 +55,10 @@ __device__ float block_reduce(float v, float *sv, bool is_max)
 }
 
 // One CTA per sample.  smem: feats [T][C] | logits [T][n_cls] | agg [n_cls] | probs [n_cls]
+// MODE 0: everything in one launch.  With many classes (N-ImageNet: 1000) one CTA per sample walks 125 text rows per warp with
+// little memory-level parallelism (ncu: 1.1 ms for 64 samples), so the work is split: MODE 1, grid (B, S): logits of a slice of
+// the classes -> out_full;  MODE 2, grid B: reads out_full back and does the aggregation, the probabilities and top-5.
+template <int MODE>
 __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const float *__restrict__ feats, const uint8_t *__restrict__ valid,
                                                             const float *__restrict__ text, int T, int C, int n_cls,
                                                             float scale, int normalize, int agg, float *out_full,
@@ -76,6 +80,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const float *__restr
     for (int t = 0; t < T; ++t) nvalid += vmask[t];
 
     // features of the T views: optional L2 normalisation (F.normalize eps 1e-12), mask, then * scale
+    if (MODE != 2)
     for (int t = warp; t < T; t += nwarp) {
         const float *f = feats + ((size_t)b * T + t) * C;
         float mul = 0.f;
@@ -93,7 +98,10 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const float *__restr
     __syncthreads();
 
     // logits[t][k] = <scale * f_t, text_k>; one warp per class row, all views at once
-    for (int k = warp; k < n_cls; k += nwarp) {
+    const int k_per = MODE == 1 ? (n_cls + (int)gridDim.y - 1) / (int)gridDim.y : n_cls;
+    const int k_lo = MODE == 1 ? (int)blockIdx.y * k_per : 0, k_hi = min(n_cls, k_lo + k_per);
+    if (MODE != 2)
+    for (int k = k_lo + warp; k < k_hi; k += nwarp) {
         const float *tx = text + (size_t)k * C;
         float acc[16];
 #pragma unroll
@@ -108,9 +116,15 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const float *__restr
         for (int t = 0; t < 16; ++t)
             if (t < T) {
                 const float v = ec::warp_sum(acc[t]);
-                if (lane == 0) sl[(size_t)t * n_cls + k] = vmask[t] != 0.f ? v : 0.f;
+                if (lane == 0) {
+                    if (MODE == 1) out_full[((size_t)b * T + t) * n_cls + k] = vmask[t] != 0.f ? v : 0.f;
+                    else sl[(size_t)t * n_cls + k] = vmask[t] != 0.f ? v : 0.f;
+                }
             }
     }
+    if (MODE == 1) return;
+    if (MODE == 2)
+        for (int i = tid; i < T * n_cls; i += blockDim.x) sl[i] = out_full[(size_t)b * T * n_cls + i];
     __syncthreads();
 
     // aggregated logits
@@ -127,7 +141,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const float *__restr
         sagg[k] = a;
         sprob[k] = 0.f;
         if (out_logits) out_logits[(size_t)b * n_cls + k] = a;
-        if (out_full)
+        if (MODE == 0 && out_full)
             for (int t = 0; t < T; ++t) out_full[((size_t)b * T + t) * n_cls + k] = sl[(size_t)t * n_cls + k];
     }
     __syncthreads();
@@ -215,6 +229,66 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float *__restrict__ A,
                 out[(size_t)m * N + n] = v;
             }
         }
+}
+
+// Skinny variant for the adapter's shapes (M = B*T <= a few hundred rows, K a multiple of 32 up to 1024): the 64 x 64 tile kernel
+// above runs 8-32 CTAs with a load -> barrier -> 16 k-steps -> barrier loop and is latency-bound (ncu: 65 us per launch, 10 launches
+// per few-shot step).  Here a CTA owns NC output columns, keeps their W rows in shared memory, and its warps stream the rows of A
+// two at a time through registers; each dot product is reduced over the lanes in a fixed order (deterministic).
+template <int NC>
+__global__ void __launch_bounds__(256) sgemm_skinny_kernel(const float *__restrict__ A, const float *__restrict__ W,
+                                                           const float *__restrict__ bias, const float *__restrict__ res, int M,
+                                                           int N, int K, int act, float *__restrict__ out)
+{
+    extern __shared__ __align__(16) float sw[];        // [NC][K]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n0 = blockIdx.x * NC;
+    const int KJ = K >> 5;                             // values per lane (K % 32 == 0, K <= 1024)
+    for (int i = tid; i < NC * K; i += 256) {
+        const int c = i / K, k = i - c * K;
+        sw[i] = n0 + c < N ? W[(size_t)(n0 + c) * K + k] : 0.f;
+    }
+    __syncthreads();
+    for (int m = 2 * warp; m < M; m += 16) {
+        const bool two = m + 1 < M;
+        float a0[32], a1[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            a0[j] = 0.f; a1[j] = 0.f;
+            if (j < KJ) {
+                a0[j] = A[(size_t)m * K + lane + 32 * j];
+                if (two) a1[j] = A[(size_t)(m + 1) * K + lane + 32 * j];
+            }
+        }
+        float r0 = 0.f, r1 = 0.f;                      // lane c keeps column n0 + c
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < KJ) {
+                    const float w = sw[c * K + lane + 32 * j];
+                    s0 = fmaf(a0[j], w, s0);
+                    s1 = fmaf(a1[j], w, s1);
+                }
+            s0 = ec::warp_sum(s0);
+            s1 = ec::warp_sum(s1);
+            if (lane == c) { r0 = s0; r1 = s1; }
+        }
+        if (lane < NC && n0 + lane < N) {
+            const int n = n0 + lane;
+            float v = r0 + (bias ? bias[n] : 0.f);
+            if (act == 1) v = fmaxf(v, 0.f);
+            if (res) v += res[(size_t)m * N + n];
+            out[(size_t)m * N + n] = v;
+            if (two) {
+                float u = r1 + (bias ? bias[n] : 0.f);
+                if (act == 1) u = fmaxf(u, 0.f);
+                if (res) u += res[(size_t)(m + 1) * N + n];
+                out[(size_t)(m + 1) * N + n] = u;
+            }
+        }
+    }
 }
 
 // One CTA per sample, one warp per head; T <= 16 views.
@@ -368,13 +442,32 @@ extern "C" int ec_head(const float *feats, const uint8_t *valid, const float *te
     EC_REQUIRE(agg >= EC_AGG_SUM && agg <= EC_AGG_MAX, "ec_head: bad aggregation %d", agg);
     const size_t smem = ((size_t)T * C + (size_t)T * n_cls + 2 * (size_t)n_cls) * sizeof(float);
     EC_REQUIRE(smem <= 220 * 1024, "ec_head: T*C + T*n_cls too large for shared memory (%zu bytes)", smem);
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-        EC_CUDA_CHECK(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
+    const bool split = n_cls >= 256 && out_full != nullptr;
+    static size_t attr[3] = {0, 0, 0};
+    auto grant = [&](int mode, const void *fn) -> int {
+        if (smem > 48 * 1024 && smem > attr[mode]) {
+            EC_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr[mode] = smem;
+        }
+        return EC_OK;
+    };
+    if (split) {
+        int rc = grant(1, (const void *)head_kernel<1>);
+        if (rc != EC_OK) return rc;
+        rc = grant(2, (const void *)head_kernel<2>);
+        if (rc != EC_OK) return rc;
+        int S = (4 * ec::sm_count() + B - 1) / B;                    // about four CTAs per SM in the logits launch
+        S = S < 1 ? 1 : (S > n_cls / 32 ? n_cls / 32 : S);
+        head_kernel<1><<<dim3(B, S), HEAD_THREADS, smem, (cudaStream_t)stream>>>(feats, valid, text, T, C, n_cls, scale, normalize, agg,
+                                                                                out_full, out_logits, out_probs, out_top);
+        head_kernel<2><<<B, HEAD_THREADS, smem, (cudaStream_t)stream>>>(feats, valid, text, T, C, n_cls, scale, normalize, agg, out_full,
+                                                                        out_logits, out_probs, out_top);
+    } else {
+        const int rc = grant(0, (const void *)head_kernel<0>);
+        if (rc != EC_OK) return rc;
+        head_kernel<0><<<B, HEAD_THREADS, smem, (cudaStream_t)stream>>>(feats, valid, text, T, C, n_cls, scale, normalize, agg, out_full,
+                                                                        out_logits, out_probs, out_top);
     }
-    head_kernel<<<B, HEAD_THREADS, smem, (cudaStream_t)stream>>>(feats, valid, text, T, C, n_cls, scale, normalize, agg, out_full,
-                                                                 out_logits, out_probs, out_top);
     EC_CUDA_CHECK(cudaGetLastError());
     return EC_OK;
 }
@@ -384,7 +477,13 @@ extern "C" int ec_gemm_f32(const float *A, const float *W, const float *bias, co
 {
     EC_REQUIRE(A && W && out && M > 0 && N > 0 && K > 0, "ec_gemm_f32: bad arguments");
     EC_REQUIRE(act == 0 || act == 1, "ec_gemm_f32: bad activation %d", act);
-    sgemm_kernel<<<dim3((N + 63) / 64, (M + 63) / 64), 256, 0, (cudaStream_t)stream>>>(A, W, bias, res, M, N, K, act, out);
+    if (M <= 1024 && K % 32 == 0 && K <= 1024) {
+        constexpr int NC = 8;
+        const size_t smem = (size_t)NC * K * sizeof(float);          // <= 32 KB
+        sgemm_skinny_kernel<NC><<<(N + NC - 1) / NC, 256, smem, (cudaStream_t)stream>>>(A, W, bias, res, M, N, K, act, out);
+    } else {
+        sgemm_kernel<<<dim3((N + 63) / 64, (M + 63) / 64), 256, 0, (cudaStream_t)stream>>>(A, W, bias, res, M, N, K, act, out);
+    }
     EC_CUDA_CHECK(cudaGetLastError());
     return EC_OK;
 }
