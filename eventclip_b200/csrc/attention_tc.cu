@@ -15,6 +15,8 @@
 // S never leaves the SM and P never touches shared memory.
 #include <cuda.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include <cuda_fp16.h>
@@ -38,6 +40,8 @@ struct AttnParams {
     float *lse;           // optional [n_img, heads, L]: log2-domain log-sum-exp of every row (kept for the backward pass)
     int L, heads, d, n_img, causal;
     int f16;              // q, k, v, P and the output are fp16 instead of bf16 (the inference forward's fp16-operand mode)
+    long long *dbg;       // EC_ATTN_DBG: clock64 stamps of CTA 0 (profiling only)
+    int stagger;          // two-tile units: issue the tiles' MMAs half a period apart (EC_ATTN_STAGGER=0 restores side by side)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -197,14 +201,41 @@ __device__ __forceinline__ float fast_exp2(float x)
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-
+// packed fp32 pairs (Blackwell FFMA2 / FADD2: two lanes of fp32 math per issued instruction)
+struct f2 { unsigned long long v; };
+__device__ __forceinline__ f2 mk2(float a, float b)
+{
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ f2 mk2u(uint32_t a, uint32_t b)
+{
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ void un2(f2 x, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x.v)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c)
+{
+    f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b)
+{
+    f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
 // Softmax of one 128-query tile (thread = query row) followed by the O epilogue.
 // causal != 0: key j contributes to query `row` only if j <= row (text tower).
 template <uint32_t OCOL, uint32_t SUMCOL>
 __device__ __forceinline__ void softmax_tile(uint32_t lane_base, int L, int nch, bool live, int row, int lane, uint64_t *bar_p,
                                              uint64_t *bar_o, uint32_t o_parity, uint64_t *bar_oe, __nv_bfloat16 *orow,
-                                             int causal, float *lse_row, int f16)
+                                             int causal, float *lse_row, int f16, long long *dbg = nullptr)
 {
+    if (dbg && lane == 0) dbg[0] = clock64();                  // S landed
     float ms_keep = 0.f;
     const int klim = causal ? min(L, row + 1) : L;     // keys [0, klim) are visible to this row
     const float sl2 = 0.125f * 1.4426950408889634f;
@@ -224,18 +255,29 @@ __device__ __forceinline__ void softmax_tile(uint32_t lane_base, int L, int nch,
                         if (j < klim) m = fmaxf(m, __uint_as_float(va[j]));
                     const float ms = m * sl2;
                     ms_keep = ms;
+                    // chunk c of the row: 32 scores -> 16 packed probabilities.  `full` chunks (every key visible) take the
+                    // straight-line path without the visibility selects.
+                    const f2 sl2x = mk2(sl2, sl2), msx = mk2(-ms, -ms);
                     auto emit = [&](const uint32_t (&v)[32], int c) {
                         uint32_t pk[16];
-                        const bool full = (c + 1) * 32 <= klim;
+                        if ((c + 1) * 32 <= klim) {
     #pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            float x0 = fminf(fmaf(__uint_as_float(v[j]), sl2, -ms), 120.f);
-                            float x1 = fminf(fmaf(__uint_as_float(v[j + 1]), sl2, -ms), 120.f);
-                            if (!full) {
+                            for (int j = 0; j < 32; j += 2) {
+                                float x0, x1;
+                                un2(fma2(mk2u(v[j], v[j + 1]), sl2x, msx), x0, x1);
+                                x0 = fminf(x0, 120.f);
+                                x1 = fminf(x1, 120.f);
+                                pk[j >> 1] = pack16x2(fast_exp2(x0), fast_exp2(x1), f16);
+                            }
+                        } else {
+    #pragma unroll
+                            for (int j = 0; j < 32; j += 2) {
+                                float x0 = fminf(fmaf(__uint_as_float(v[j]), sl2, -ms), 120.f);
+                                float x1 = fminf(fmaf(__uint_as_float(v[j + 1]), sl2, -ms), 120.f);
                                 if (c * 32 + j >= klim) x0 = -INFINITY;
                                 if (c * 32 + j + 1 >= klim) x1 = -INFINITY;
+                                pk[j >> 1] = pack16x2(fast_exp2(x0), fast_exp2(x1), f16);
                             }
-                            pk[j >> 1] = pack16x2(fast_exp2(x0), fast_exp2(x1), f16);
                         }
                         tmem_st16(lane_base + (uint32_t)(c * 16), pk);
                     };
@@ -256,9 +298,11 @@ __device__ __forceinline__ void softmax_tile(uint32_t lane_base, int L, int nch,
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_p);
+                if (dbg && lane == 0) dbg[1] = clock64();      // P written
                 // epilogue: O / rowsum -> bf16 -> global
                 mbar_wait(bar_o, o_parity);
                 tc_fence_after();
+                if (dbg && lane == 0) dbg[2] = clock64();      // O landed
                 if (!live) {      // nothing to store: keep the barrier protocol and move on
                     tc_fence_before();
                     __syncwarp();
@@ -287,6 +331,7 @@ __device__ __forceinline__ void softmax_tile(uint32_t lane_base, int L, int nch,
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_oe);
+                if (dbg && lane == 0) dbg[3] = clock64();      // epilogue done
 }
 
 // Persistent: one CTA per SM walks over (image, head) units.  Shared memory holds two units (the next one is fetched
@@ -295,6 +340,7 @@ __device__ __forceinline__ void softmax_tile(uint32_t lane_base, int L, int nch,
 __global__ void __launch_bounds__(NTHREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
 {
+    const bool stagger = p.stagger != 0;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     // stage s: Q (2 tiles) | K (2 tiles, K-major B of S = Q K^T) | V (2 tiles, MN-major B of O = P V)
@@ -351,47 +397,100 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
         const uint64_t odesc = make_desc(smem_u32(sOnes));
         if ((int)blockIdx.x < n_units && elect_one()) load_unit(blockIdx.x, 0);
         __syncwarp();
-        int i = 0;
-        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++i) {
-            const int stage = i & 1;
-            const uint32_t sph = (uint32_t)(i >> 1) & 1, uph = (uint32_t)i & 1;
-            const int next = unit + gridDim.x;
-            if (next < n_units) {
-                // the other stage was last read by the MMAs of unit i-1
-                if (i >= 1) mbar_wait(&bar_free[stage ^ 1], (uint32_t)((i - 1) >> 1) & 1);
-                if (elect_one()) load_unit(next, stage ^ 1);
-                __syncwarp();
-            }
-            unsigned char *sQ = smem + stage * STAGE_BYTES, *sK = sQ + 2 * TILE_BYTES, *sV = sQ + 4 * TILE_BYTES;
-            mbar_wait(&bar_qk[stage], sph);
-            tc_fence_after();
-            const uint64_t kdesc = make_desc(smem_u32(sK));
-            for (int t = 0; t < MT; ++t) {
-                if (i >= 1) { mbar_wait(&bar_oe[t], uph ^ 1); tc_fence_after(); }   // tile t's TMEM of unit i-1 fully consumed
-                const uint64_t qdesc = make_desc(smem_u32(sQ + t * TILE_BYTES));
-                const uint32_t tb = tmem_base + (uint32_t)(t * TILE_COLS);
-                if (elect_one()) {
+        int dbg_i = 0, dbg_pv = 0;      // unit index of the S issue / (unit * 2 + tile) of the PV issue, for the stamps
+        auto issue_s = [&](int stage, int t) {
+            unsigned char *sQ = smem + stage * STAGE_BYTES, *sK = sQ + 2 * TILE_BYTES;
+            const uint64_t kdesc = make_desc(smem_u32(sK)), qdesc = make_desc(smem_u32(sQ + t * TILE_BYTES));
+            const uint32_t tb = tmem_base + (uint32_t)(t * TILE_COLS);
+            if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_ss(tb, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, k != 0);
-                    umma_commit(&bar_s[t]);
-                }
-                __syncwarp();
+                for (int k = 0; k < 4; ++k) umma_ss(tb, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, k != 0);
+                umma_commit(&bar_s[t]);
+                if (p.dbg && blockIdx.x == 0 && dbg_i < 16) p.dbg[(dbg_i * 2 + t) * 2] = clock64();
             }
-            mbar_wait(&bar_v[stage], sph);
+            __syncwarp();
+        };
+        auto issue_pv = [&](int stage, int t, bool release_stage) {
+            unsigned char *sV = smem + stage * STAGE_BYTES + 4 * TILE_BYTES;
             const uint64_t vdesc = make_desc(smem_u32(sV));
-            for (int t = 0; t < MT; ++t) {
-                mbar_wait(&bar_p[t], uph);               // P is in tensor memory
-                tc_fence_after();
-                const uint32_t tb = tmem_base + (uint32_t)(t * TILE_COLS);
-                if (elect_one()) {
-                    for (int j = 0; j < KP / 16; ++j) {   // 16 keys per step: 8 packed columns of P, 16 rows (2048 B) of V
-                        umma_ts(tb + O_COL, tb + (uint32_t)(8 * j), vdesc + (uint64_t)(128 * j), idesc_o, j != 0);
-                        umma_ts(tb + SUM_COL, tb + (uint32_t)(8 * j), odesc, idesc_1, j != 0);   // += P . 1
-                    }
-                    umma_commit(&bar_o[t]);
-                    if (t == MT - 1) umma_commit(&bar_free[stage]);   // every MMA that reads this stage has retired
+            const uint32_t tb = tmem_base + (uint32_t)(t * TILE_COLS);
+            if (elect_one()) {
+                for (int j = 0; j < KP / 16; ++j) {   // 16 keys per step: 8 packed columns of P, 16 rows (2048 B) of V
+                    umma_ts(tb + O_COL, tb + (uint32_t)(8 * j), vdesc + (uint64_t)(128 * j), idesc_o, j != 0);
+                    umma_ts(tb + SUM_COL, tb + (uint32_t)(8 * j), odesc, idesc_1, j != 0);   // += P . 1
                 }
-                __syncwarp();
+                umma_commit(&bar_o[t]);
+                if (release_stage) umma_commit(&bar_free[stage]);   // every MMA that reads this stage has retired
+                if (p.dbg && blockIdx.x == 0 && dbg_pv < 32) { p.dbg[(dbg_pv >> 1) * 4 + (dbg_pv & 1) * 2 + 1] = clock64(); }
+            }
+            __syncwarp();
+        };
+        if (MT == 2 && stagger) {
+            // Two 128-query tiles = two dependent chains  S -> softmax -> P V -> epilogue -> S (next unit).  Issued side by side
+            // they run in phase: both softmax warpgroups compete for the SFU and the tensor-memory read port at the same time and
+            // both wait at the same time.  Issue order  S0(i), PV1(i-1), S1(i), PV0(i)  keeps the chains half a period apart: the
+            // softmax of one tile runs while the other tile is in its MMA / epilogue / barrier phases.
+            int i = 0;
+            for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++i) {
+                const int stage = i & 1;
+                const uint32_t sph = (uint32_t)(i >> 1) & 1, uph = (uint32_t)i & 1;
+                const int next = unit + gridDim.x;
+                mbar_wait(&bar_qk[stage], sph);
+                if (i >= 1) mbar_wait(&bar_oe[0], uph ^ 1);      // tile 0's tensor memory of unit i-1 fully consumed
+                tc_fence_after();
+                dbg_i = i;
+                issue_s(stage, 0);
+                if (i >= 1) {
+                    mbar_wait(&bar_p[1], uph ^ 1);               // P of tile 1, unit i-1 (its V was awaited for tile 0)
+                    tc_fence_after();
+                    dbg_pv = (i - 1) * 2 + 1;
+                    issue_pv(stage ^ 1, 1, true);
+                }
+                if (next < n_units) {
+                    if (i >= 1) mbar_wait(&bar_free[stage ^ 1], (uint32_t)((i - 1) >> 1) & 1);
+                    if (elect_one()) load_unit(next, stage ^ 1);
+                    __syncwarp();
+                }
+                if (i >= 1) { mbar_wait(&bar_oe[1], uph ^ 1); tc_fence_after(); }
+                issue_s(stage, 1);
+                mbar_wait(&bar_v[stage], sph);
+                mbar_wait(&bar_p[0], uph);
+                tc_fence_after();
+                dbg_pv = i * 2;
+                issue_pv(stage, 0, false);
+            }
+            if (i >= 1) {                                        // tile 1 of the last unit
+                mbar_wait(&bar_p[1], (uint32_t)(i - 1) & 1);
+                tc_fence_after();
+                dbg_pv = (i - 1) * 2 + 1;
+                issue_pv((i - 1) & 1, 1, true);
+            }
+        } else {
+            int i = 0;
+            for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++i) {
+                const int stage = i & 1;
+                const uint32_t sph = (uint32_t)(i >> 1) & 1, uph = (uint32_t)i & 1;
+                const int next = unit + gridDim.x;
+                if (next < n_units) {
+                    // the other stage was last read by the MMAs of unit i-1
+                    if (i >= 1) mbar_wait(&bar_free[stage ^ 1], (uint32_t)((i - 1) >> 1) & 1);
+                    if (elect_one()) load_unit(next, stage ^ 1);
+                    __syncwarp();
+                }
+                mbar_wait(&bar_qk[stage], sph);
+                tc_fence_after();
+                for (int t = 0; t < MT; ++t) {
+                    if (i >= 1) { mbar_wait(&bar_oe[t], uph ^ 1); tc_fence_after(); }   // tile t's TMEM of unit i-1 fully consumed
+                    dbg_i = i;
+                    issue_s(stage, t);
+                }
+                mbar_wait(&bar_v[stage], sph);
+                for (int t = 0; t < MT; ++t) {
+                    mbar_wait(&bar_p[t], uph);               // P is in tensor memory
+                    tc_fence_after();
+                    dbg_pv = i * 2 + t;
+                    issue_pv(stage, t, t == MT - 1);
+                }
             }
         }
     } else if ((warp - 1) / 4 < MT) {
@@ -411,7 +510,252 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
             tc_fence_after();
             softmax_tile<O_COL, SUM_COL>(lane_base, L, nch, live, row, lane, &bar_p[t], &bar_o[t], uph, &bar_oe[t],
                                          p.out + ((size_t)img * L + row) * d + h * HD, p.causal,
-                                         p.lse ? p.lse + (size_t)unit * L + row : nullptr, p.f16);
+                                         p.lse ? p.lse + (size_t)unit * L + row : nullptr, p.f16,
+                                         (p.dbg && blockIdx.x == 0 && quarter == 0 && i < 16) ? p.dbg + 64 + (i * 2 + t) * 4 : nullptr);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ================================================================================================================
+// v2 (L <= 256): two threads per query row and two independent chains in flight.
+//
+// What the round-2 timeline (clock64 stamps per phase, profiles/r02_attention_timeline.txt) showed about v1: a tcgen05.ld
+// of 32 columns holds its warp for ~256 cycles (tensor memory -> registers moves 16 B/clk per SM sub-partition) and does not
+// overlap that warp's own math, so one thread per row spends 7 x (256 load + ~360 math/SFU) = 4300 cycles in the softmax of
+// a 197-key row and 2000 more in the O epilogue, with the tensor pipe idle meanwhile.  Here
+//   * every 128-row tile is served by EIGHT warps: the two warps that share a tensor-memory lane quarter (same sub-partition)
+//     take the even / odd 32-column chunks of S, so one warp's load overlaps the other's exponentials; the row reference
+//     (maximum of the first 32 scores) goes from the even warp to the odd one through shared memory and a 64-thread named
+//     barrier, which also orders the P stores (P chunk c overwrites S columns of chunk c/2) against the partner's loads;
+//   * the two tensor-memory slots are two chains  S -> softmax -> P V -> epilogue  issued half a period apart
+//     (S(j), PV(j-1), S(j+1), ...): for L <= 128 the slots hold DIFFERENT (image, head) units, four of which are resident
+//     in shared memory, so ViT-B/32 (L = 50) and the text tower (L = 77) no longer leave half the CTA idle.
+// ================================================================================================================
+constexpr int NTHREADS2 = 544;                  // warp 0: TMA + MMA issue; warps 1-8 / 9-16: slot 0 / 1 (x even / odd chunks)
+
+__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+template <int MT, int F16>      // MT: 128-query tiles per unit; F16: fp16 (else bf16) operands and output
+__global__ void __launch_bounds__(NTHREADS2, 1)
+attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
+{
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char *sOnes = smem + 2 * STAGE_BYTES;    // all-ones operand: O's companion MMA yields the softmax denominators
+    __shared__ __align__(8) uint64_t bar_qk[4], bar_v[4], bar_free[4];          // per smem stage
+    __shared__ __align__(8) uint64_t bar_s[2], bar_p[2], bar_o[2], bar_oe[2];   // per tensor-memory slot
+    __shared__ float s_ref[2][128];                                              // row reference, even -> odd warp of a pair
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int L = p.L, d = p.d, heads = p.heads;
+    const int KP = (L + 15) & ~15;                    // keys rounded to a whole MMA K step
+    const int NST = MT == 2 ? 2 : 4;                  // units resident in shared memory
+    const int stage_bytes = 3 * MT * TILE_BYTES;
+    const int n_units = p.n_img * heads;
+    const int n_my = (int)blockIdx.x < n_units ? (n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int n_items = n_my * MT;                    // item j = (unit j / MT, tile j % MT) runs in slot j & 1
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qkv) : "memory");
+        for (int i = 0; i < 4; ++i) { mbar_init(&bar_qk[i], 1); mbar_init(&bar_v[i], 1); mbar_init(&bar_free[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 8); mbar_init(&bar_o[i], 1); mbar_init(&bar_oe[i], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < ONES_BYTES / 4; i += NTHREADS2) reinterpret_cast<uint32_t *>(sOnes)[i] = F16 ? 0x3c003c00u : 0x3f803f80u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA + MMA issuer =====================
+        auto load_unit = [&](int u) {                 // elected lane only; u = this CTA's u-th unit
+            const int unit = (int)blockIdx.x + u * (int)gridDim.x, stage = u % NST;
+            const int img = unit / heads, h = unit % heads;
+            unsigned char *sQ = smem + stage * stage_bytes, *sK = sQ + MT * TILE_BYTES, *sV = sQ + 2 * MT * TILE_BYTES;
+            mbar_expect_tx(&bar_qk[stage], (uint32_t)(2 * MT * TILE_BYTES));
+            for (int b = 0; b < MT; ++b) {
+                tma_load_3d(sK + b * TILE_BYTES, &map_qkv, &bar_qk[stage], d + h * HD, b * 128, img);
+                tma_load_3d(sQ + b * TILE_BYTES, &map_qkv, &bar_qk[stage], h * HD, b * 128, img);
+            }
+            mbar_expect_tx(&bar_v[stage], (uint32_t)(MT * TILE_BYTES));
+            for (int b = 0; b < MT; ++b) tma_load_3d(sV + b * TILE_BYTES, &map_qkv, &bar_v[stage], 2 * d + h * HD, b * 128, img);
+        };
+        const uint32_t FMT16 = F16 ? 0u : ((1u << 7) | (1u << 10));
+        const uint32_t idesc_s = (1u << 4) | FMT16 | ((uint32_t)(KP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc_o = (1u << 4) | FMT16 | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc_1 = (1u << 4) | FMT16 | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint64_t odesc = make_desc(smem_u32(sOnes));
+        if (elect_one())
+            for (int u = 0; u < NST && u < n_my; ++u) load_unit(u);
+        __syncwarp();
+        auto issue_s = [&](int j) {
+            const int u = j / MT, t = j - u * MT, stage = u % NST, slot = j & 1;
+            mbar_wait(&bar_qk[stage], (uint32_t)(u / NST) & 1);
+            if (j >= 2) mbar_wait(&bar_oe[slot], (uint32_t)((j - 2) >> 1) & 1);      // the slot's previous item is fully consumed
+            tc_fence_after();
+            unsigned char *sQ = smem + stage * stage_bytes, *sK = sQ + MT * TILE_BYTES;
+            const uint64_t kdesc = make_desc(smem_u32(sK)), qdesc = make_desc(smem_u32(sQ + t * TILE_BYTES));
+            const uint32_t tb = tmem_base + (uint32_t)(slot * TILE_COLS);
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_ss(tb, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, k != 0);
+                umma_commit(&bar_s[slot]);
+                if (p.dbg && blockIdx.x == 0 && j < 32) p.dbg[j * 2] = clock64();
+            }
+            __syncwarp();
+        };
+        auto issue_pv = [&](int j) {
+            const int u = j / MT, t = j - u * MT, stage = u % NST, slot = j & 1;
+            mbar_wait(&bar_v[stage], (uint32_t)(u / NST) & 1);
+            mbar_wait(&bar_p[slot], (uint32_t)(j >> 1) & 1);                         // P is in tensor memory
+            tc_fence_after();
+            unsigned char *sV = smem + stage * stage_bytes + 2 * MT * TILE_BYTES;
+            const uint64_t vdesc = make_desc(smem_u32(sV));
+            const uint32_t tb = tmem_base + (uint32_t)(slot * TILE_COLS);
+            const bool last = t == MT - 1;
+            const int nk = KP / 16;
+            if (elect_one()) {
+                for (int k = 0; k < nk; ++k) {        // 16 keys per step: 8 packed columns of P, 16 rows (2048 B) of V
+                    umma_ts(tb + O_COL, tb + (uint32_t)(8 * k), vdesc + (uint64_t)(128 * k), idesc_o, k != 0);
+                    umma_ts(tb + SUM_COL, tb + (uint32_t)(8 * k), odesc, idesc_1, k != 0);   // += P . 1
+                }
+                umma_commit(&bar_o[slot]);
+                if (last) umma_commit(&bar_free[stage]);      // every MMA that reads this stage has retired
+                if (p.dbg && blockIdx.x == 0 && j < 32) p.dbg[j * 2 + 1] = clock64();
+            }
+            __syncwarp();
+            if (last && u + NST < n_my) {             // the stage is free once those MMAs have retired: fetch the unit NST ahead
+                mbar_wait(&bar_free[stage], (uint32_t)(u / NST) & 1);
+                if (elect_one()) load_unit(u + NST);
+                __syncwarp();
+            }
+        };
+        for (int j = 0; j < n_items; ++j) {
+            issue_s(j);
+            if (j >= 1) issue_pv(j - 1);
+        }
+        if (n_items >= 1) issue_pv(n_items - 1);
+    } else {
+        // ===================== softmax + epilogue: two threads per query row =====================
+        const int slot = (warp - 1) >> 3;             // tensor-memory slot served by this warp
+        const int half = ((warp - 1) >> 2) & 1;       // 0: even 32-column chunks (and the row reference), 1: odd chunks
+        const int quarter = warp & 3;                 // TMEM lane quarter (hardware: a warp reaches lanes 32 * (warp % 4) .. + 31)
+        const int pair_id = 1 + slot * 4 + quarter;   // named barrier of the two warps that share the rows
+        const uint32_t lane_base = tmem_base + (uint32_t)(slot * TILE_COLS) + ((uint32_t)(quarter * 32) << 16);
+        const float sl2 = 0.125f * 1.4426950408889634f;
+        const int nch = (KP + 31) >> 5;               // 32-column chunks of S
+        const int n_steps = max(2, (nch - half + 1) >> 1);
+        float *ref = &s_ref[slot][quarter * 32 + lane];
+        constexpr int f16 = F16;
+        int k = 0;
+        for (int j = slot; j < n_items; j += 2, ++k) {
+            const int u = j / MT, t = j - u * MT;
+            const int unit = (int)blockIdx.x + u * (int)gridDim.x;
+            const int img = unit / heads, h = unit % heads;
+            const int row = t * 128 + quarter * 32 + lane;
+            const bool live = t * 128 + quarter * 32 < L;     // pair-uniform: these warps own at least one real query row
+            const uint32_t ph = (uint32_t)k & 1;
+            long long *dbg = (p.dbg && blockIdx.x == 0 && quarter == 0 && half == 0 && lane == 0 && j < 32) ? p.dbg + 64 + j * 4 : nullptr;
+            mbar_wait(&bar_s[slot], ph);
+            tc_fence_after();
+            if (dbg) dbg[0] = clock64();
+            float ms = 0.f;
+            if (live) {
+                const int klim = p.causal ? min(L, row + 1) : L;     // keys [0, klim) are visible to this row
+                for (int st = 0; st < n_steps; ++st) {
+                    const int c = 2 * st + half;
+                    const bool has = c < nch;
+                    uint32_t v[32];
+                    if (has) {
+                        tmem_ld32_issue(lane_base + (uint32_t)(c * 32), v);
+                        tmem_ld_wait();
+                    }
+                    if (st == 0) {
+                        if (half == 0) {
+                            float m = -INFINITY;
+#pragma unroll
+                            for (int q = 0; q < 32; ++q)
+                                if (q < klim) m = fmaxf(m, __uint_as_float(v[q]));
+                            ms = m * sl2;
+                            *ref = ms;
+                        }
+                        pair_sync(pair_id);           // reference visible; chunks 0 and 1 are in registers
+                        if (half == 1) ms = *ref;
+                    } else if (st == 1)
+                        pair_sync(pair_id);           // chunks 2 and 3 are in registers: P chunks 5 and 6 may overwrite them
+                    if (has) {
+                        uint32_t pk[16];
+                        const f2 sl2x = mk2(sl2, sl2), msx = mk2(-ms, -ms);
+                        if ((c + 1) * 32 <= klim) {
+#pragma unroll
+                            for (int q = 0; q < 32; q += 2) {
+                                float x0, x1;
+                                un2(fma2(mk2u(v[q], v[q + 1]), sl2x, msx), x0, x1);
+                                x0 = fminf(x0, 120.f);
+                                x1 = fminf(x1, 120.f);
+                                pk[q >> 1] = pack16x2(fast_exp2(x0), fast_exp2(x1), f16);
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 32; q += 2) {
+                                float x0 = fminf(fmaf(__uint_as_float(v[q]), sl2, -ms), 120.f);
+                                float x1 = fminf(fmaf(__uint_as_float(v[q + 1]), sl2, -ms), 120.f);
+                                if (c * 32 + q >= klim) x0 = -INFINITY;
+                                if (c * 32 + q + 1 >= klim) x1 = -INFINITY;
+                                pk[q >> 1] = pack16x2(fast_exp2(x0), fast_exp2(x1), f16);
+                            }
+                        }
+                        tmem_st16(lane_base + (uint32_t)(c * 16), pk);
+                    }
+                }
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_p[slot]);
+            if (dbg) dbg[1] = clock64();
+            // epilogue: O / rowsum -> 16 bits -> global; this warp takes 32 of the 64 head columns
+            mbar_wait(&bar_o[slot], ph);
+            tc_fence_after();
+            if (dbg) dbg[2] = clock64();
+            if (live) {
+                uint32_t v[32];
+                tmem_ld32_issue(lane_base + O_COL + (uint32_t)(half * 32), v);
+                const float rsum = tmem_ld1(lane_base + SUM_COL);      // (waits for both loads)
+                const float inv = 1.f / rsum;
+                if (row < L) {
+                    if (p.lse && half == 0) p.lse[(size_t)unit * L + row] = ms + log2f(rsum);     // p_ij = exp2(s_ij * sl2 - lse)
+                    __nv_bfloat16 *orow = p.out + ((size_t)img * L + row) * d + h * HD + half * 32;
+#pragma unroll
+                    for (int q = 0; q < 32; q += 8) {
+                        uint4 o;
+                        o.x = pack16x2(__uint_as_float(v[q]) * inv, __uint_as_float(v[q + 1]) * inv, f16);
+                        o.y = pack16x2(__uint_as_float(v[q + 2]) * inv, __uint_as_float(v[q + 3]) * inv, f16);
+                        o.z = pack16x2(__uint_as_float(v[q + 4]) * inv, __uint_as_float(v[q + 5]) * inv, f16);
+                        o.w = pack16x2(__uint_as_float(v[q + 6]) * inv, __uint_as_float(v[q + 7]) * inv, f16);
+                        *reinterpret_cast<uint4 *>(orow + q) = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_oe[slot]);
+            if (dbg) dbg[3] = clock64();
         }
     }
 
@@ -901,16 +1245,49 @@ int attention_tc(const void *qkv, void *out, int n_img, int L, int heads, int ca
     EC_CUDA_CHECK(cudaGetDevice(&dev_id));
     if (dev_id < 64 && !attr_set[dev_id]) {
         EC_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        EC_CUDA_CHECK(cudaFuncSetAttribute(attention_tc2_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        EC_CUDA_CHECK(cudaFuncSetAttribute(attention_tc2_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        EC_CUDA_CHECK(cudaFuncSetAttribute(attention_tc2_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        EC_CUDA_CHECK(cudaFuncSetAttribute(attention_tc2_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         EC_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
         attr_set[dev_id] = true;
     }
+    // A/B hooks: EC_ATTN_V=1 selects the round-1 kernel (one thread per row), EC_ATTN_STAGGER=0 issues its two tiles side by side
+    static const int stagger = [] { const char *e = getenv("EC_ATTN_STAGGER"); return e ? atoi(e) : 1; }();
+    static const int version = [] { const char *e = getenv("EC_ATTN_V"); return e ? atoi(e) : 2; }();
     AttnParams p;
     p.out = (__nv_bfloat16 *)out; p.lse = lse; p.L = L; p.heads = heads; p.d = d; p.n_img = n_img;
     p.causal = causal & 1; p.f16 = (causal >> 1) & 1;       // EC_ATTN_CAUSAL | EC_ATTN_F16
+    p.stagger = stagger;
+    p.dbg = nullptr;
+    static const int dbg_on = [] { const char *e = getenv("EC_ATTN_DBG"); return e ? atoi(e) : 0; }();
+    static long long *dbg_buf = nullptr;
+    if (dbg_on) {
+        if (!dbg_buf) EC_CUDA_CHECK(cudaMalloc(&dbg_buf, 256 * sizeof(long long)));
+        EC_CUDA_CHECK(cudaMemsetAsync(dbg_buf, 0, 256 * sizeof(long long), stream));
+        p.dbg = dbg_buf;
+    }
     const int units = n_img * heads;
     const int grid = units < sm_count() ? units : sm_count();
     if (L > 256) attention_tc_big_kernel<<<grid, BIG_NTHREADS, smem_big, stream>>>(map, p);
-    else attention_tc_kernel<<<grid, NTHREADS, smem, stream>>>(map, p);
+    else if (version == 2) {
+        const bool two = L > 128;
+        auto k = two ? (p.f16 ? attention_tc2_kernel<2, 1> : attention_tc2_kernel<2, 0>) : (p.f16 ? attention_tc2_kernel<1, 1> : attention_tc2_kernel<1, 0>);
+        k<<<grid, NTHREADS2, smem, stream>>>(map, p);
+    } else
+        attention_tc_kernel<<<grid, NTHREADS, smem, stream>>>(map, p);
+    if (dbg_on && L <= 256) {      // profiling only: per-unit timeline of CTA 0 in SM clocks, relative to the first S issue
+        long long h[256];
+        EC_CUDA_CHECK(cudaStreamSynchronize(stream));
+        EC_CUDA_CHECK(cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
+        const long long t0 = h[0];
+        for (int u = 0; u < 12; ++u)
+            for (int t = 0; t < 2; ++t) {
+                const long long *m = h + (u * 2 + t) * 2, *w = h + 64 + (u * 2 + t) * 4;
+                fprintf(stderr, "unit %2d tile %d: S issue %7lld | S landed %7lld | P written %7lld | PV issue %7lld | O landed %7lld | epilogue done %7lld\n",
+                        u, t, m[0] - t0, w[0] - t0, w[1] - t0, m[1] - t0, w[2] - t0, w[3] - t0);
+            }
+    }
     EC_CUDA_CHECK(cudaGetLastError());
     return EC_OK;
 }
