@@ -684,17 +684,18 @@ def b200_arm(args):
             # the same batch through the other numeric settings of the inference forward (eager launches, not timed): what the
             # 16-bit operand format and the residual stream's dtype each cost in error
             vis = model.visual
-            keep = (vis.operand_dtype, vis.residual_dtype)
+            keep = (vis.operand_dtype, vis.residual_dtype, vis.residual_split)
             variants = {}
-            for name, op, res in (("bf16_operands_fp16_residual", torch.bfloat16, torch.float16),
-                                  ("fp16_operands_fp16_residual", torch.float16, torch.float16),
-                                  ("fp16_operands_fp32_residual", torch.float16, torch.float32)):
-                vis.operand_dtype, vis.residual_dtype = op, res
+            for name, op, res, split in (("bf16_operands_fp16_residual", torch.bfloat16, torch.float16, False),
+                                         ("fp16_operands_fp16_residual", torch.float16, torch.float16, False),
+                                         ("fp16_operands_fp16x2_residual", torch.float16, torch.float16, True),
+                                         ("fp16_operands_fp32_residual", torch.float16, torch.float32, False)):
+                vis.operand_dtype, vis.residual_dtype, vis.residual_split = op, res, split
                 with torch.no_grad():
                     lg = zs(w.data(0))["logits"].float().cpu()
                 st = parity_stats(lg[:args.parity_samples], ref["logits"])
                 variants[name] = {k: st[k] for k in ("logits_centered_rel_l2", "max_abs_logit_err", "top1_agree", "top1_disagreements")}
-            vis.operand_dtype, vis.residual_dtype = keep
+            vis.operand_dtype, vis.residual_dtype, vis.residual_split = keep
             parity["numeric_variants"] = variants
         except Exception as ex:
             parity = dict(error=repr(ex)[:300])
@@ -856,7 +857,9 @@ def b200_arm(args):
         cb = dict(value=cpu_value, unit="samples/s", cores=cores, kind="port",
                   sample="2 steps x 32 samples of the bench workload through the oracle (C event2img + fp32 PyTorch CLIP + head)")
     enc_flops = clip.flops_per_image(arch) * B * T
-    residual = "fp16 (the reference's CUDA precision)" if model.visual.residual_dtype == torch.float16 else "fp32"
+    residual = ("fp16 kept as a (hi, lo) pair of fp16 planes: hi = fp16(x) feeds the GEMMs, lo carries the rounding residue through every update"
+                if model.visual.residual_split and model.visual.residual_dtype == torch.float16 else
+                "fp16 (the reference's CUDA precision)" if model.visual.residual_dtype == torch.float16 else "fp32")
     operands = "fp16" if model.visual.operand_dtype == torch.float16 else "bf16"
     acc = counters.tolist()
     del runner, w, zs, model, host, devb

@@ -14,7 +14,7 @@ EC_ERR_ARG, EC_ERR_CUDA, EC_ERR_UNSUPPORTED, EC_ERR_CAPACITY = -1, -2, -3, -4
 EC_STATUS_BAD_COORD, EC_STATUS_COUNT_OVERFLOW = 1, 2
 EC_FLAG_COUNT_NON_ZERO, EC_FLAG_BACKGROUND_MASK = 1, 2
 EC_OUT_F32_NCHW, EC_OUT_BF16_NCHW, EC_OUT_BF16_PATCH, EC_OUT_F16_PATCH = 0, 1, 2, 3
-EC_EPI_BF16, EC_EPI_BF16_QGELU, EC_EPI_F32_RESADD, EC_EPI_F32, EC_EPI_PATCH, EC_EPI_F16_RESADD = 0, 1, 2, 3, 4, 5
+EC_EPI_BF16, EC_EPI_BF16_QGELU, EC_EPI_F32_RESADD, EC_EPI_F32, EC_EPI_PATCH, EC_EPI_F16_RESADD, EC_EPI_F16X2_RESADD = 0, 1, 2, 3, 4, 5, 6
 EC_EPI_F16_OPERANDS = 0x100
 EC_ATTN_CAUSAL, EC_ATTN_F16 = 1, 2
 EC_AGG = {"sum": 0, "mean": 1, "max": 2}
@@ -48,6 +48,8 @@ SIGNATURES = {
     "ec_layernorm_ex": ([_vp, _i, _i64, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp], _i),
     "ec_gemm_stats_parts": ([_i], _i),
     "ec_gemm_bf16_stats": ([_vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp], _i),
+    "ec_gemm_bf16_stats2": ([_vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp], _i),
+    "ec_layernorm_f16x2": ([_vp, _i64, _vp, _vp, _i, _i, _vp, _vp, _vp], _i),
     "ec_gemm_ln": ([_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp], _i),
     "ec_row_stats_f16": ([_vp, _i64, _i, _i, _vp, _i, _vp], _i),
     "ec_attention": ([_vp, _vp, _i, _i, _i, _vp], _i),

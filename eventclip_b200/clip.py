@@ -171,8 +171,9 @@ def pack_blocks_ln(resblocks, d, dev):
     return out
 
 
-def run_blocks_ln(x, blocks, lnb, n_seq, Ltok, d, heads):
-    """x: fp16 residual stream [n_seq*Ltok, d].  No LayerNorm kernel: in_proj and c_fc read the stream itself as their A
+def run_blocks_ln(x, blocks, lnb, n_seq, Ltok, d, heads, x2=None):
+    """x: fp16 residual stream [n_seq*Ltok, d]; x2: optional [2, M, d] (hi, lo) pair of fp16 planes with x = x2[0] -- the
+    residual updates then keep the rounding residue of every update in x2[1] (ec_gemm_bf16_stats2).  No LayerNorm kernel: in_proj and c_fc read the stream itself as their A
     operand and apply the normalisation in their epilogues from the row statistics that the previous residual epilogue
     (out_proj / c_proj) wrote next to the rows.  blocks: bf16 or fp16 weight copies; the activations between the GEMMs
     (qkv, attention output, MLP hidden) take the same 16-bit dtype."""
@@ -187,9 +188,15 @@ def run_blocks_ln(x, blocks, lnb, n_seq, Ltok, d, heads):
     for b, f in zip(blocks, lnb):
         ops.gemm_ln(x, f["wg_in"], None, f["c_in"], stats, parts, "bf16", out=qkv)
         ops.attention(qkv, att, n_seq, Ltok, heads)
-        ops.gemm_bf16_stats(att, b["w_out"], f["b_out"], x, stats)
+        if x2 is None:
+            ops.gemm_bf16_stats(att, b["w_out"], f["b_out"], x, stats)
+        else:
+            ops.gemm_bf16_stats2(att, b["w_out"], f["b_out"], x2, stats)
         ops.gemm_ln(x, f["wg_fc"], None, f["c_fc"], stats, parts, "bf16_qgelu", out=hid)
-        ops.gemm_bf16_stats(hid, b["w_proj"], f["b_proj"], x, stats)
+        if x2 is None:
+            ops.gemm_bf16_stats(hid, b["w_proj"], f["b_proj"], x, stats)
+        else:
+            ops.gemm_bf16_stats2(hid, b["w_proj"], f["b_proj"], x2, stats)
     return x
 
 
@@ -238,6 +245,10 @@ class VisionTransformer(nn.Module):
         # keeps the model in fp16, test.py:26-29) at half the residual traffic; EC_RESIDUAL=fp32 keeps it in float32.
         # The fine-tune forward (train.py) always uses fp32, as the reference's train.py:27-29 does.
         self.residual_dtype = torch.float32 if os.environ.get("EC_RESIDUAL", "fp16") == "fp32" else torch.float16
+        # fp16 stream kept as a (hi, lo) pair of fp16 planes (EC_RESIDUAL=fp16x2): hi = fp16(x) is the GEMM operand, lo the
+        # residue of that rounding, carried through every residual update (ec_gemm_bf16_stats2).  The accuracy of a float32
+        # stream without the LayerNorm kernels a float32 stream needs; used with the folded LayerNorm only.
+        self.residual_split = os.environ.get("EC_RESIDUAL", "fp16") == "fp16x2"
         # ln_1 / ln_2 folded into the in_proj / c_fc GEMMs (fp16 stream only); EC_LN_FOLD=0 keeps the LayerNorm kernels
         self.fold_ln = os.environ.get("EC_LN_FOLD", "1") != "0"
         self._packed_ln, self._packed_ln_key = None, None
@@ -436,15 +447,21 @@ class VisionTransformer(nn.Module):
         ops.gemm_bf16(patches, p16["conv1"] if f16 else pk["conv1"], None, "patch", out=x0, res=pk["pos"], row_map=G2, M=n_img * G2)
         ops.cls_rows(x0, pk["cls"], pk["pos"], n_img, Ltok, d)
         # residual stream: fp16 like the reference's CUDA inference (test.py:26-29 keeps CLIP in fp16) or fp32
-        if self.residual_dtype == torch.float16:
+        fold = self.fold_ln and self.residual_dtype == torch.float16 and ops.gemm_stats_parts(d) <= 8
+        x2 = None
+        if fold and self.residual_split and d <= 1024:
+            x2 = torch.empty((2, M, d), dtype=torch.float16, device=dev)
+            ops.layernorm_f16x2(x0, *pk["ln_pre"], M, d, x2)
+            x = x2[0]
+        elif self.residual_dtype == torch.float16:
             x = torch.empty((M, d), dtype=torch.float16, device=dev)
             ops.layernorm(x0, *pk["ln_pre"], M, d, out_f16=x)
         else:
             x = torch.empty((M, d), dtype=torch.float32, device=dev)
             ops.layernorm(x0, *pk["ln_pre"], M, d, out_f32=x)
         del x0
-        if self.fold_ln and x.dtype == torch.float16 and ops.gemm_stats_parts(d) <= 8:
-            run_blocks_ln(x, p16["blocks"] if f16 else pk["blocks"], self.packed_ln(), n_img, Ltok, d, heads)
+        if fold:
+            run_blocks_ln(x, p16["blocks"] if f16 else pk["blocks"], self.packed_ln(), n_img, Ltok, d, heads, x2=x2)
         else:
             run_blocks(x, pk["blocks"], n_img, Ltok, d, heads, w16=p16["blocks"] if f16 else None)
         cls = torch.empty((n_img, d), dtype=self.operand_dtype, device=dev)

@@ -26,7 +26,8 @@ template <bool CACHE, typename TIn>
 __global__ void __launch_bounds__(256) layernorm_kernel(const TIn *__restrict__ x, int64_t row_stride,
                                                         const float *__restrict__ gamma, const float *__restrict__ beta,
                                                         int M, int d, __nv_bfloat16 *__restrict__ out_bf16,
-                                                        float *__restrict__ out_f32, __half *__restrict__ out_f16)
+                                                        float *__restrict__ out_f32, __half *__restrict__ out_f16,
+                                                        __half *__restrict__ out_lo = nullptr)
 {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -87,6 +88,14 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const TIn *__restrict__ 
             u.x = *reinterpret_cast<uint32_t *>(&h0);
             u.y = *reinterpret_cast<uint32_t *>(&h1);
             reinterpret_cast<uint2 *>(out_f16 + (size_t)row * d)[j] = u;
+            if (out_lo) {      // residue of the fp16 rounding: the (hi, lo) residual stream of ec_gemm_bf16_stats2
+                const float2 b0 = __half22float2(h0), b1 = __half22float2(h1);
+                __half2 l0 = __floats2half2_rn(o.x - b0.x, o.y - b0.y), l1 = __floats2half2_rn(o.z - b1.x, o.w - b1.y);
+                uint2 ul;
+                ul.x = *reinterpret_cast<uint32_t *>(&l0);
+                ul.y = *reinterpret_cast<uint32_t *>(&l1);
+                reinterpret_cast<uint2 *>(out_lo + (size_t)row * d)[j] = ul;
+            }
         }
     };
     if (CACHE) {
@@ -440,6 +449,18 @@ extern "C" int ec_layernorm(const float *x, int64_t row_stride_in, const float *
                             void *out_bf16, float *out_f32, void *stream)
 {
     return launch_ln(x, row_stride_in, gamma, beta, M, d, out_bf16, out_f32, (cudaStream_t)stream);
+}
+
+extern "C" int ec_layernorm_f16x2(const float *x, int64_t row_stride, const float *gamma, const float *beta, int M, int d, void *out_hi,
+                                  void *out_lo, void *stream)
+{
+    EC_REQUIRE(x && gamma && beta && out_hi && out_lo, "ec_layernorm_f16x2: null pointer");
+    EC_REQUIRE(M > 0 && d > 0 && d % 4 == 0 && d <= 1024 && row_stride % 4 == 0, "ec_layernorm_f16x2: d must be a multiple of 4, at most 1024");
+    const unsigned grid = (unsigned)((M + 7) / 8);
+    layernorm_kernel<true, float><<<grid, 256, 0, (cudaStream_t)stream>>>(x, row_stride, gamma, beta, M, d, nullptr, nullptr, (__half *)out_hi,
+                                                                           (__half *)out_lo);
+    EC_CUDA_CHECK(cudaGetLastError());
+    return EC_OK;
 }
 
 extern "C" int ec_layernorm_ex(const void *x, int x_is_f16, int64_t row_stride_in, const float *gamma, const float *beta, int M,

@@ -800,6 +800,99 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
             if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        } else if (p.epi == EC_EPI_F16X2_RESADD) {
+            // ---- fp16 residual stream kept as a PAIR of fp16 planes  x = hi + lo  (hi = fp16(x): the A operand of the next
+            //      LayerNorm-folded GEMM; lo = fp16(x - hi): the residue the fp16 rounding of every update would discard).
+            //      The value carries ~22 mantissa bits for the bytes of an fp32 stream, and no LayerNorm kernel has to turn it
+            //      into a 16-bit operand.  map_o: hi plane, map_r: lo plane, both updated in place.  Each epilogue warp's 8 KB
+            //      hold two (hi, lo) box pairs: the pair of the next chunk is fetched while this one is processed. ----
+            uint32_t as = 0, aphase = 0, nbox = 0;
+            uint64_t *rb = res_bar[ew];
+            auto load_res = [&](int tm_, int tn_, int c_, uint32_t n_) {     // lane 0 only
+                const int r_ = (tm_ * CG + (int)cta_rank) * BM + quarter * 32;
+                const int c0_ = tn_ * BN + half * COLS_PER_WARP + c_ * 32;
+                unsigned char *dst = smem + STAGES * STAGE_BYTES + ew * STG_WARP_BYTES + (n_ & 1) * 4096;
+                mbar_expect_tx(&rb[n_ & 1], 4096);
+                tma_load_2d(dst, &map_o, &rb[n_ & 1], c0_, r_);
+                tma_load_2d(dst + 2048, &map_r, &rb[n_ & 1], c0_, r_);
+            };
+            TileWalk tw(group_id, num_groups, p.tiles_n), tw_next(group_id, num_groups, p.tiles_n);
+            if (lane == 0 && group_id < num_tiles) load_res(tw.tm, tw.tn, 0, 0);
+            for (int tile = group_id; tile < num_tiles; tile += num_groups, tw.next()) {
+                const int tm = tw.tm, tn = tw.tn;
+                tw_next.next();
+                const int row0 = (tm * CG + (int)cta_rank) * BM + quarter * 32;
+                const int colw = tn * BN + half * COLS_PER_WARP;
+                const bool bias_fast = p.bias && colw + COLS_PER_WARP <= p.N && ((uintptr_t)p.bias & 15) == 0;
+                mbar_wait(&tfull_bar[as], aphase);
+                tc_fence_after();
+                const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + half * COLS_PER_WARP);
+                uint32_t v[32];
+                tmem_ld32_issue(tbase, v);
+                f2 st1x = mk2(0.f, 0.f), st2x = mk2(0.f, 0.f);
+#pragma unroll 1
+                for (int c = 0; c < NCHUNK; ++c) {
+                    const int col0 = colw + c * 32;
+                    float4 bq[8];
+                    bias_chunk(p.bias, col0, p.N, bias_fast, bq);
+                    if (lane == 0) {
+                        bulk_wait_read<0>();     // the stores that last used the other pair have finished reading it
+                        if (c + 1 < NCHUNK) load_res(tm, tn, c + 1, nbox + 1);
+                        else if (tile + num_groups < num_tiles) load_res(tw_next.tm, tw_next.tn, 0, nbox + 1);
+                    }
+                    const uint32_t box = stg + (nbox & 1) * 4096;
+                    mbar_wait(&rb[nbox & 1], (nbox >> 1) & 1);
+                    tmem_ld_wait();
+                    const uint32_t rowaddr = box + (uint32_t)lane * 64;
+                    const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {          // 8 columns per 16-byte chunk
+                        const uint32_t a = rowaddr + ((q ^ sw) << 4);
+                        const float4 rh = lds128(a), rl = lds128(a + 2048);
+                        const uint32_t hw[4] = {__float_as_uint(rh.x), __float_as_uint(rh.y), __float_as_uint(rh.z), __float_as_uint(rh.w)};
+                        const uint32_t lw[4] = {__float_as_uint(rl.x), __float_as_uint(rl.y), __float_as_uint(rl.z), __float_as_uint(rl.w)};
+                        uint32_t oh[4], ol[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 rhi = __half22float2(*reinterpret_cast<const __half2 *>(&hw[e]));
+                            const float2 rlo = __half22float2(*reinterpret_cast<const __half2 *>(&lw[e]));
+                            const float4 b = bq[2 * q + (e >> 1)];
+                            const f2 bb = (e & 1) ? mk2(b.z, b.w) : mk2(b.x, b.y);
+                            // (lo + update) first: the small terms meet before the large one joins
+                            const f2 o = add2(mk2(rhi.x, rhi.y), add2(mk2(rlo.x, rlo.y), add2(mk2u(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]), bb)));
+                            oh[e] = pack16x2_2(o, 1);
+                            const float2 back = __half22float2(*reinterpret_cast<const __half2 *>(&oh[e]));
+                            ol[e] = pack16x2_2(add2(o, mk2(-back.x, -back.y)), 1);
+                            st1x = add2(st1x, o);
+                            st2x = fma2(o, o, st2x);
+                        }
+                        sts128u(a, oh[0], oh[1], oh[2], oh[3]);
+                        sts128u(a + 2048, ol[0], ol[1], ol[2], ol[3]);
+                    }
+                    if (c + 1 < NCHUNK) tmem_ld32_issue(tbase + (uint32_t)((c + 1) * 32), v);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0 && row0 < p.M && col0 < p.N) {
+                        tma_store_2d(&map_o, box, col0, row0);
+                        tma_store_2d(&map_r, box + 2048, col0, row0);
+                    }
+                    ++nbox;
+                }
+                if (p.stats_out && row0 + lane < p.M) {
+                    float s1a, s1b, s2a, s2b;
+                    un2(st1x, s1a, s1b);
+                    un2(st2x, s2a, s2b);
+                    p.stats_out[(size_t)(row0 + lane) * (2 * p.tiles_n) + 2 * tn + half] = make_float2(s1a + s1b, s2a + s2b);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 2) mbar_arrive_leader(&tempty_bar[as]);
+                    else mbar_arrive(&tempty_bar[as]);
+                }
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         } else {
         const bool has_res = p.epi == EC_EPI_F32_RESADD || p.epi == EC_EPI_PATCH;
         // transposed lane mapping inside a 16-column pass
@@ -1094,6 +1187,17 @@ extern "C" int ec_gemm_bf16_stats(const void *A, int lda, const void *W, int ldw
     return gemm_impl(A, lda, W, ldw, bias, M, N, K, EC_EPI_F16_RESADD, out, ldo, (const float *)res, 0, 1, (cudaStream_t)stream_, 0, &ex);
 }
 
+extern "C" int ec_gemm_bf16_stats2(const void *A, int lda, const void *W, int ldw, const float *bias, int M, int N, int K, void *x_hi,
+                                   void *x_lo, int ldo, float *stats_out, int f16_operands, void *stream_)
+{
+    EC_REQUIRE(stats_out && ((uintptr_t)stats_out & 7) == 0, "ec_gemm_bf16_stats2: stats_out must be an 8-byte aligned buffer");
+    EC_REQUIRE(x_hi && x_lo, "ec_gemm_bf16_stats2: null plane");
+    GemmExtra ex;
+    ex.stats_out = stats_out;
+    ex.a_f16 = f16_operands != 0;
+    return gemm_impl(A, lda, W, ldw, bias, M, N, K, EC_EPI_F16X2_RESADD, x_hi, ldo, (const float *)x_lo, 0, 1, (cudaStream_t)stream_, 0, &ex);
+}
+
 extern "C" int ec_gemm_stats_parts(int N)
 {
     const int BN = (N % 256 == 0) ? 256 : 128;
@@ -1207,9 +1311,9 @@ int gemm_impl(const void *A, int lda, const void *W, int ldw, const float *bias,
                    "ec_gemm_bf16: N, K, lda, ldw must be multiples of 8 (N=%d K=%d lda=%d ldw=%d)", N, K, lda, ldw);
     EC_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)out & 15) == 0,
                "ec_gemm_bf16: pointers must be 16-byte aligned");
-    EC_REQUIRE(epi >= EC_EPI_BF16 && epi <= EC_EPI_F16_RESADD, "ec_gemm_bf16: bad epilogue %d", epi);
+    EC_REQUIRE(epi >= EC_EPI_BF16 && epi <= EC_EPI_F16X2_RESADD, "ec_gemm_bf16: bad epilogue %d", epi);
     EC_REQUIRE(ldo >= N && ldo % 8 == 0, "ec_gemm_bf16: bad ldo %d", ldo);
-    if (epi == EC_EPI_F32_RESADD || epi == EC_EPI_PATCH || epi == EC_EPI_F16_RESADD)
+    if (epi == EC_EPI_F32_RESADD || epi == EC_EPI_PATCH || epi == EC_EPI_F16_RESADD || epi == EC_EPI_F16X2_RESADD)
         EC_REQUIRE(res != nullptr, "ec_gemm_bf16: epilogue needs res");
     if (epi == EC_EPI_PATCH) EC_REQUIRE(row_map > 0 && M % row_map == 0, "ec_gemm_bf16: bad row_map %d", row_map);
 
@@ -1275,6 +1379,13 @@ int gemm_impl(const void *A, int lda, const void *W, int ldw, const float *bias,
     }
     if (epi == EC_EPI_F16_RESADD) {      // out / res are fp16 [M, ldo]
         EC_REQUIRE(((uintptr_t)res & 15) == 0 && ldo % 8 == 0, "ec_gemm_bf16: fp16 residual must be 16-byte aligned");
+        rc = make_f16_map(&mo, out, M, N, ldo);
+        if (rc != EC_OK) return rc;
+        rc = make_f16_map(&mr, res, M, N, ldo);
+        if (rc != EC_OK) return rc;
+    }
+    if (epi == EC_EPI_F16X2_RESADD) {    // out: hi plane, res: lo plane, fp16 [M, ldo] each, updated in place
+        EC_REQUIRE(res && (((uintptr_t)res | (uintptr_t)out) & 15) == 0 && ldo % 8 == 0, "ec_gemm_bf16_stats2: planes must be 16-byte aligned");
         rc = make_f16_map(&mo, out, M, N, ldo);
         if (rc != EC_OK) return rc;
         rc = make_f16_map(&mr, res, M, N, ldo);

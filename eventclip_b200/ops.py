@@ -200,6 +200,35 @@ def gemm_bf16_stats(A, W, bias, x, stats):
     return x
 
 
+def gemm_bf16_stats2(A, W, bias, x2, stats):
+    """The same update on a residual stream kept as two fp16 planes x2 [2, M, N] (x = x2[0] + x2[1], hi = fp16(x), lo = fp16(x - hi)),
+    both updated in place; stats as in gemm_bf16_stats."""
+    f16 = A.dtype == torch.float16
+    _dev(A, torch.float16 if f16 else torch.bfloat16, "A")
+    _dev(W, A.dtype, "W")
+    _dev(x2, torch.float16, "x2")
+    _dev(stats, torch.float32, "stats")
+    M, (N, K) = A.shape[0], W.shape
+    if x2.dim() != 3 or x2.shape[0] != 2 or x2.shape[1] != M or x2.shape[2] != N or not x2.is_contiguous():
+        raise L.ECError("gemm_bf16_stats2: x2 must be a contiguous fp16 [2, M, N] tensor")
+    if stats.numel() < M * gemm_stats_parts(N) * 2:
+        raise L.ECError("gemm_bf16_stats2: statistics buffer too small")
+    with torch.cuda.device(A.device):
+        L.check(L.load().ec_gemm_bf16_stats2(_ptr(A), A.stride(0), _ptr(W), W.stride(0), _ptr(bias), M, N, K, _ptr(x2[0]), _ptr(x2[1]),
+                                             N, _ptr(stats), int(f16), _stream()), "ec_gemm_bf16_stats2")
+    return x2
+
+
+def layernorm_f16x2(x, gamma, beta, M, d, out2, row_stride=None):
+    """LayerNorm of fp32 rows into the (hi, lo) fp16 pair out2 [2, M, d]."""
+    _dev(x, torch.float32, "x")
+    _dev(out2, torch.float16, "out2")
+    with torch.cuda.device(x.device):
+        L.check(L.load().ec_layernorm_f16x2(_ptr(x), int(row_stride or d), _ptr(gamma), _ptr(beta), M, d, _ptr(out2[0]), _ptr(out2[1]),
+                                            _stream()), "ec_layernorm_f16x2")
+    return out2
+
+
 def gemm_ln(x, Wg, colsum, cbias, stats, n_parts, epi="bf16", out=None, out_dtype=torch.bfloat16):
     """out = epi(LayerNorm(x) @ W.T + b) with the LayerNorm folded into the GEMM: x fp16 [M,K] is the A operand itself,
     Wg = fp16(gamma * W), colsum[j] = sum_k Wg[j,k], cbias[j] = beta . W[j] + b[j], stats = per-row partial sums.

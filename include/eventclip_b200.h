@@ -135,6 +135,7 @@ EC_API int ec_event2img_geometry(int H, int W, int *cluster_size, int *threads, 
 #define EC_EPI_PATCH 4       /* out fp32 token rows = acc + pos[1 + m%G2]  (patch embedding) */
 #define EC_EPI_F16_RESADD 5  /* out fp16 = res(fp16) + acc + bias: residual stream in the reference's CUDA precision;
                                 `out` and `res` point to fp16 [M,ldo] (res is passed through the float* parameter) */
+#define EC_EPI_F16X2_RESADD 6 /* ec_gemm_bf16_stats2 only: the fp16 residual stream as a (hi, lo) pair of fp16 planes, see there */
 #define EC_EPI_F16_OPERANDS 0x100 /* OR-ed into epi: A and W hold fp16 instead of bf16 (tcgen05.mma kind::f16 takes either, at the same
                                 rate, but not a mixed pair) and the 16-bit outputs (EC_EPI_BF16, EC_EPI_BF16_QGELU) are written as
                                 fp16 -- the reference's own CUDA inference dtype (clip.load keeps fp16 weights, test.py:26-29),
@@ -180,6 +181,17 @@ EC_API int ec_layernorm_ex(const void *x, int x_is_f16, int64_t row_stride_in, c
  *      (Wg[j,:] -= mean_k Wg[j,k]; allowed because sum_k (x_k - mean) = 0) s vanishes: pass colsum = NULL and the epilogue is
  *      one fma per element.  The GEMM reads the fp16 residual rows themselves as its A operand; the row statistics arrive as
  *      partial (sum, sum of squares) pairs written by the epilogue that produced the rows. */
+/* The same update on a residual stream kept as TWO fp16 planes, x = hi + lo (hi = fp16(x), lo = fp16(x - hi)): the value keeps
+ * ~22 mantissa bits across the 24 residual updates of a 12-block tower (an fp16 stream rounds it to 11 bits after every update),
+ * while hi stays directly usable as the fp16 A operand of the next LayerNorm-folded GEMM (ec_gemm_ln).  Both planes [M, ldo] are
+ * read and written in place; stats_out as in ec_gemm_bf16_stats (statistics of hi + lo before rounding).
+ * Replaces the same reference lines as ec_gemm_bf16 with EC_EPI_F32_RESADD (x += out_proj(...) / c_proj(...) of openai-CLIP's
+ * ResidualAttentionBlock, called through models/clip_cls.py:101). */
+EC_API int ec_gemm_bf16_stats2(const void *A, int lda, const void *W, int ldw, const float *bias, int M, int N, int K, void *x_hi,
+                               void *x_lo, int ldo, float *stats_out, int f16_operands, void *stream);
+/* LayerNorm of fp32 rows written as that (hi, lo) pair: out_hi = fp16(y), out_lo = fp16(y - out_hi)  (ln_pre of the tower) */
+EC_API int ec_layernorm_f16x2(const float *x, int64_t row_stride, const float *gamma, const float *beta, int M, int d, void *out_hi,
+                              void *out_lo, void *stream);
 /* number of float2 statistics slots per row that ec_gemm_bf16_stats writes for an N-column output */
 EC_API int ec_gemm_stats_parts(int N);
 /* out fp16 = res(fp16) + A W^T + bias (EC_EPI_F16_RESADD) and stats_out float [M, parts, 2] = per-row partial sums of the values

@@ -244,6 +244,61 @@ def test_encoder_large_archs_vs_oracle(cuda_dev, arch):
     assert rel(got, ref) < 2e-2, rel(got, ref)
 
 
+def test_split_residual_stream_update(cuda_dev):
+    """ec_gemm_bf16_stats2: the stream as a (hi, lo) pair of fp16 planes.  After an update hi + lo equals the fp32 result to
+    ~2^-21 relative (hi alone only to 2^-11), lo stays below half an ulp of hi, and the statistics are those of the sum; a chain of
+    updates drifts far less than the plain fp16 stream."""
+    g = torch.Generator().manual_seed(31)
+    for M, d, K in ((394, 768, 768), (1000, 768, 3072), (70, 256, 128)):
+        A = torch.randn(M, K, generator=g).half()
+        Wo = (torch.randn(d, K, generator=g) * K ** -0.5).half()
+        bo = torch.randn(d, generator=g)
+        x_true = (torch.randn(M, d, generator=g) * 2 + 0.5).double()
+        hi0 = x_true.float().half()
+        lo0 = (x_true.float() - hi0.float()).half()
+        x2 = torch.stack([hi0, lo0]).to(cuda_dev).contiguous()
+        x1 = hi0.to(cuda_dev).clone()
+        parts = ops.gemm_stats_parts(d)
+        stats = torch.full((M, parts, 2), 7.0, device=cuda_dev)
+        stats1 = torch.empty_like(stats)
+        upd = A.double() @ Wo.double().t() + bo.double()
+        want = hi0.double() + lo0.double()
+        for it in range(6):
+            ops.gemm_bf16_stats2(A.to(cuda_dev), Wo.to(cuda_dev), bo.to(cuda_dev), x2, stats)
+            ops.gemm_bf16_stats(A.to(cuda_dev), Wo.to(cuda_dev), bo.to(cuda_dev), x1, stats1)
+            want = want + upd
+        hi, lo = x2[0].cpu(), x2[1].cpu()
+        got = hi.double() + lo.double()
+        err2 = float((got - want).norm() / want.norm())
+        err1 = float((x1.cpu().double() - want).norm() / want.norm())
+        assert err2 < 5e-6 and err1 > 20 * err2, (M, d, K, err1, err2)       # fp32-accumulator noise vs six fp16 roundings
+        assert (lo.float().abs() <= hi.float().abs() * 2.0 ** -10 + 1e-7).all()    # lo is a rounding residue: at most half an ulp of hi
+        st = stats.cpu().sum(1).double()
+        assert (st[:, 0] - got.sum(1)).abs().max() < 1e-3 * got.abs().sum(1).max()
+        assert (st[:, 1] - (got * got).sum(1)).abs().max() < 1e-4 * (got * got).sum(1).max()
+
+
+def test_split_residual_stream_encoder_vs_oracle(cuda_dev):
+    """EC_RESIDUAL=fp16x2 / visual.residual_split: the encoder with the (hi, lo) stream is closer to the fp32 oracle than with
+    the plain fp16 stream, on the part of the features that differs between images (centred error)."""
+    from parity_util import record_metric, rel_l2_centered
+    arch = "ViT-B/16"
+    oracle = clip_oracle.build_clip(arch, seed=29)
+    model = clip.CLIP(arch)
+    model.load_state_dict(oracle.state_dict())
+    model = model.to(cuda_dev).eval()
+    imgs = torch.randn(6, 3, 224, 224, generator=torch.Generator().manual_seed(11))
+    with torch.no_grad():
+        ref = oracle.encode_image(imgs)
+        got16 = model.encode_image(imgs.to(cuda_dev)).cpu()
+        model.visual.residual_split = True
+        got2 = model.encode_image(imgs.to(cuda_dev)).cpu()
+        model.visual.residual_split = False
+    e16, e2 = rel_l2_centered(got16, ref), rel_l2_centered(got2, ref)
+    record_metric("encoder_split_stream", arch=arch, centred_fp16=e16, centred_fp16x2=e2, plain_fp16x2=rel(got2, ref))
+    assert rel(got2, ref) < 2e-2 and e2 < 0.75 * e16, (e16, e2)
+
+
 def test_residual_stream_fp16_and_fp32_vs_oracle(cuda_dev):
     """The inference forward keeps the residual stream in fp16 (the reference's CUDA precision) by default and in fp32 on
     request; both stay within the encoder tolerance of the fp32 oracle and close to each other."""

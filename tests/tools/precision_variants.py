@@ -27,10 +27,13 @@ for ds, arch, n in (("n_cars", "ViT-B/16", 32), ("n_caltech101", "ViT-B/32", 16)
     x = imgs[:, 0]
     with torch.no_grad():
         ref = oracle.encode_image(x)
-        for op, res, fold in ((torch.float16, torch.float16, True), (torch.float16, torch.float16, False), (torch.float16, torch.float32, False),
-                              (torch.bfloat16, torch.float16, True), (torch.bfloat16, torch.float16, False), (torch.bfloat16, torch.float32, False)):
+        for op, res, fold, split in ((torch.float16, torch.float16, True, True), (torch.float16, torch.float16, True, False),
+                                     (torch.float16, torch.float16, False, False), (torch.float16, torch.float32, False, False),
+                                     (torch.bfloat16, torch.float16, True, True), (torch.bfloat16, torch.float16, True, False),
+                                     (torch.bfloat16, torch.float16, False, False), (torch.bfloat16, torch.float32, False, False)):
             model.visual.operand_dtype, model.visual.residual_dtype, model.visual.fold_ln = op, res, fold
+            model.visual.residual_split = split
             model.visual.invalidate_packed()
             got = model.encode_image(x.to(dev)).cpu()
-            print(ds, arch, "operands", str(op).split(".")[1], "residual", str(res).split(".")[1], "fold_ln", fold,
+            print(ds, arch, "operands", str(op).split(".")[1], "residual", str(res).split(".")[1] + ("x2 (hi, lo)" if split else ""), "fold_ln", fold,
                   "rel_l2 %.3e centred %.3f" % (rel_l2(got, ref), rel_l2_centered(got, ref)), flush=True)
