@@ -194,7 +194,10 @@ def test_layernorm_and_helpers(cuda_dev):
     assert torch.equal(ops.lora_merge(W.to(cuda_dev), None, None).cpu(), W.to(torch.bfloat16))
 
 
-@pytest.mark.parametrize("L,heads,n_img", [(50, 12, 3), (197, 12, 2), (257, 16, 2), (5, 2, 4), (64, 2, 1), (65, 2, 1)])
+# the last three cases give every persistent CTA several (image, head) units: the shared-memory ring of the two-slot kernel
+# wraps (four resident units for L <= 128, two for L <= 256), the slots alternate, odd and even unit counts per CTA
+@pytest.mark.parametrize("L,heads,n_img", [(50, 12, 3), (197, 12, 2), (257, 16, 2), (5, 2, 4), (64, 2, 1), (65, 2, 1),
+                                           (50, 12, 131), (128, 4, 333), (197, 12, 57), (129, 2, 260)])
 def test_attention(cuda_dev, L, heads, n_img):
     g = torch.Generator().manual_seed(L)
     d = heads * 64
@@ -296,7 +299,9 @@ def test_split_residual_stream_encoder_vs_oracle(cuda_dev):
         model.visual.residual_split = False
     e16, e2 = rel_l2_centered(got16, ref), rel_l2_centered(got2, ref)
     record_metric("encoder_split_stream", arch=arch, centred_fp16=e16, centred_fp16x2=e2, plain_fp16x2=rel(got2, ref))
-    assert rel(got2, ref) < 2e-2 and e2 < 0.75 * e16, (e16, e2)
+    # with bf16 operands (EC_OPERANDS=bf16) the operand roundings dominate and the stream's format hardly matters
+    gain = 0.75 if model.visual.operand_dtype == torch.float16 else 1.05
+    assert rel(got2, ref) < 2e-2 and e2 < gain * e16, (e16, e2)
 
 
 def test_residual_stream_fp16_and_fp32_vs_oracle(cuda_dev):
@@ -318,7 +323,7 @@ def test_residual_stream_fp16_and_fp32_vs_oracle(cuda_dev):
     assert rel(got16, got32) < 1e-2 and not torch.equal(got16, got32)
 
 
-@pytest.mark.parametrize("L,heads,n_seq", [(77, 8, 5), (16, 1, 3), (197, 12, 2), (257, 16, 1)])
+@pytest.mark.parametrize("L,heads,n_seq", [(77, 8, 5), (16, 1, 3), (197, 12, 2), (257, 16, 1), (77, 8, 301), (197, 12, 40)])
 def test_causal_attention(cuda_dev, L, heads, n_seq):
     """Text-tower attention: key j is visible to query i iff j <= i (both tensor-memory kernels)."""
     g = torch.Generator().manual_seed(L + 1)
