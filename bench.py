@@ -634,9 +634,16 @@ def b200_arm(args):
         gemm_log.append((A.shape[0], W.shape[0], W.shape[1], "f16_resadd_stats"))
         return _orig_stats(A, W, bias, x, st)
 
+    _orig_stats2_log = ops.gemm_bf16_stats2
+
+    def logged_gemm_stats2(A, W, bias, x2, st):
+        gemm_log.append((A.shape[0], W.shape[0], W.shape[1], "f16x2_resadd_stats"))
+        return _orig_stats2_log(A, W, bias, x2, st)
+
     if not args.no_graph:
         _lib.load().ec_gemm_timing(ctypes.c_void_p(stamps.data_ptr()), STAMP_CAP)
         clipmod.ops.gemm_bf16, clipmod.ops.gemm_ln, clipmod.ops.gemm_bf16_stats = logged_gemm, logged_gemm_ln, logged_gemm_stats
+        clipmod.ops.gemm_bf16_stats2 = logged_gemm_stats2
 
     def step(i, resident=True):
         flush.zero_()                                    # L2 flush between iterations (inside the timed region)
@@ -657,6 +664,7 @@ def b200_arm(args):
         step(i)
         if i == 0 and not args.no_graph:     # the graph exists now (2 eager warm-up passes + 1 capture went through Python)
             clipmod.ops.gemm_bf16, clipmod.ops.gemm_ln, clipmod.ops.gemm_bf16_stats = _orig_gemm, _orig_ln, _orig_stats
+            clipmod.ops.gemm_bf16_stats2 = _orig_stats2_log
             _lib.load().ec_gemm_timing(None, 0)          # later launches are not stamped; the graph keeps its slots
     # ---- parity of the path that is about to be timed (rank 0): graph replay of batch 0 vs the oracle on the whole batch.
     #      Its predictions become the labels of batch 0, so the accuracy counters of the timed region mean something. ----
@@ -802,7 +810,18 @@ def b200_arm(args):
             rec.append((a, b, 2.0 * A.shape[0] * W.shape[0] * W.shape[1], (A.shape[0], W.shape[0], W.shape[1], "f16_resadd_stats")))
             return r
 
+        _orig_stats2 = ops.gemm_bf16_stats2
+
+        def timed_stats2(A, W, bias, x2, st):       # EC_RESIDUAL=fp16x2: the (hi, lo) residual update
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = _orig_stats2(A, W, bias, x2, st)
+            b.record()
+            rec.append((a, b, 2.0 * A.shape[0] * W.shape[0] * W.shape[1], (A.shape[0], W.shape[0], W.shape[1], "f16x2_resadd_stats")))
+            return r
+
         clipmod.ops.gemm_bf16, clipmod.ops.gemm_ln, clipmod.ops.gemm_bf16_stats = timed_gemm, timed_ln, timed_stats
+        clipmod.ops.gemm_bf16_stats2 = timed_stats2
         nrep = 3
         for i in range(nrep):       # eager launches here: events cannot be recorded around nodes of a replayed graph
             flush.zero_()
@@ -810,6 +829,7 @@ def b200_arm(args):
                 zs(w.data(i))
         torch.cuda.synchronize()
         clipmod.ops.gemm_bf16, clipmod.ops.gemm_ln, clipmod.ops.gemm_bf16_stats = orig, _orig_ln, _orig_stats
+        clipmod.ops.gemm_bf16_stats2 = _orig_stats2
         gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in rec)
         gemm_flops = sum(f for _, _, f, _ in rec)
         shapes = {}
