@@ -82,12 +82,18 @@ def _used_ranges(plan, n_events, min_saving=0.25):
 
 
 class GraphedClassifier:
-    def __init__(self, model, max_events, max_graphs=8):
+    def __init__(self, model, max_events, max_graphs=8, compact=False):
+        """compact=True: the event batches arrive in the compact wire format (int32 [sum E] words of
+        datasets.formats.pack_events_host / ops.pack_events: 4 bytes per event across PCIe instead of 16)."""
         self.model = model
         self.dev = model.device
         if self.dev.type != "cuda":
             raise L.ECError("GraphedClassifier needs the model on a CUDA device")
-        self.events = torch.zeros((max_events, 4), dtype=torch.float32, device=self.dev)   # static input buffer
+        self.compact = bool(compact)
+        self.ev_bytes = 4 if self.compact else 16
+        # static input buffer
+        self.events = torch.zeros((max_events,), dtype=torch.int32, device=self.dev) if self.compact else \
+            torch.zeros((max_events, 4), dtype=torch.float32, device=self.dev)
         self.status = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.cache = {}
         self.max_graphs = max_graphs
@@ -127,7 +133,8 @@ class GraphedClassifier:
         return e
 
     def __call__(self, data_dict):
-        """data_dict: {'events' float32 [sum E,4] (pinned host or CUDA), 'event_offsets', optional 'sel_idx'}.
+        """data_dict: {'events' float32 [sum E,4] -- or int32 [sum E] packed words with compact=True -- (pinned host or CUDA),
+        'event_offsets', optional 'sel_idx'}.
         Returns the classifier's out_dict; its tensors are the graph's static outputs (overwritten by the next call).
         Host events are copied range by range when the plan uses only part of the stream (see _used_ranges)."""
         plan = self.model.plan_events(data_dict["event_offsets"], data_dict.get("sel_idx", None))
@@ -139,12 +146,14 @@ class GraphedClassifier:
 
     def _copy_in(self, dst, ev, ranges):
         """events -> dst (device), whole or as the packed ranges of _used_ranges; returns the bytes moved."""
+        if ev.dtype != dst.dtype:
+            raise L.ECError(f"GraphedClassifier(compact={self.compact}) expects {dst.dtype} events, got {ev.dtype}")
         if ranges is None:
             dst[:ev.shape[0]].copy_(ev, non_blocking=True)
-            return ev.shape[0] * 16
+            return ev.shape[0] * self.ev_bytes
         for s0, c, d0 in ranges:
             dst[d0:d0 + c].copy_(ev[s0:s0 + c], non_blocking=True)
-        return sum(c for _, c, _ in ranges) * 16
+        return sum(c for _, c, _ in ranges) * self.ev_bytes
 
     def _run(self, plan, ev, ranges, staged=False):
         """Replay (or capture) the graph of this plan's geometry on `ev`: a host / device event tensor, or -- staged=True --

@@ -232,6 +232,40 @@ def test_cuda_graph_replay_matches_eager(cuda_dev):
     assert torch.equal(got["logits"], eager["logits"]) and len(g.cache) == 1
 
 
+def test_compact_wire_format_through_the_serving_loop(cuda_dev):
+    """GraphedClassifier(compact=True): the batches cross PCIe as 4-byte words (datasets.formats.pack_events_host) -- also range
+    by range when the plan reads only part of a stream -- and the logits equal those of the float32 route bit for bit."""
+    from eventclip_b200.datasets.formats import pack_events_host
+    from eventclip_b200.graph import GraphedClassifier
+    cfg = SENSORS["n_caltech101"]
+    q = dict(max_imgs=2, N=cfg["N"], split_method="event_count", convert_method="event_histogram", grayscale=True,
+             count_non_zero=False, background_mask=True)
+    model = clip.init_weights_(clip.CLIP("ViT-tiny/32"), seed=5).to(cuda_dev).eval()
+    text = clip_oracle.synth_text_feats(cfg["n_cls"], 64, 6)
+    zs = ZSCLIPClassifier(clip_dict=dict(clip_model=model, prompt="a {}", class_names=None, agg_func="mean",
+                                         text_feats=text)).to(cuda_dev).eval()
+    zs.attach_event_frontend(q, cfg["shape"], cfg["max_n"])
+    gf = GraphedClassifier(zs, max_events=4 * 100000)
+    gc = GraphedClassifier(zs, max_events=4 * 100000, compact=True)
+    fl, pk = [], []
+    for seed, E in ((1, 100000), (2, 100000), (3, 30001)):          # K = 5 > T = 2: three of five chunks stay on the host
+        ev, off = synth_batch("n_caltech101", 3, seed, E=E)
+        sel = torch.tensor([[0, 3], [4, 1], [2, 0]], dtype=torch.int32) if E == 100000 else None
+        base = dict(event_offsets=torch.from_numpy(off))
+        if sel is not None:
+            base["sel_idx"] = sel
+        fl.append(dict(base, events=torch.from_numpy(ev).pin_memory()))
+        pk.append(dict(base, events=torch.from_numpy(pack_events_host(ev, cfg["shape"]).view(np.int32)).pin_memory()))
+    with torch.no_grad():
+        want = list(gf.stream(fl, result=lambda out: out["logits"]))
+        got = list(gc.stream(pk, result=lambda out: out["logits"]))
+    for a, b in zip(want, got):
+        assert torch.equal(a, b)
+    assert gc.h2d_bytes * 4 == gf.h2d_bytes
+    with pytest.raises(Exception):
+        gc(fl[0])                                                    # float events into the compact runner
+
+
 def test_pipelined_stream_matches_sequential_calls(cuda_dev):
     """GraphedClassifier.stream (uploads one batch ahead on a copy stream, results through pinned memory) yields, in
     order, exactly what one call per batch returns -- including batches of different geometry and a single batch."""
