@@ -217,10 +217,20 @@ def parity_stats(got_logits, ref_logits, k=1):
 
 
 def patches_bit_exact(patches, imgs, valid, P):
-    """16-bit im2col rows written by the fused event kernel vs the round-to-nearest-even of the oracle's float32 frames in the
-    same format (bf16 or fp16), bitwise."""
+    """16-bit im2col rows written by the fused event kernel vs the oracle's frames, bitwise.  Three-channel formats: the
+    round-to-nearest-even of the oracle's float32 tensor (bf16 or fp16).  Gray format (one plane, conv1 folded): the oracle's
+    resampled byte / 128, recovered from its float32 tensor and checked to reproduce all three channels exactly."""
     x = imgs[valid]                                                  # [nv, 3, 224, 224]
     n, G = x.shape[0], 224 // P
+    if patches.shape[1] < 3 * P * P:
+        mean = torch.tensor([0.48145466, 0.4578275, 0.40821073], dtype=torch.float32).view(1, 3, 1, 1)
+        std = torch.tensor([0.26862954, 0.26130258, 0.27577711], dtype=torch.float32).view(1, 3, 1, 1)
+        g = torch.round((x[:, :1].double() * 0.26862954 + 0.48145466) * 255.0).abs().to(torch.float32)      # the byte behind channel 0 (abs: no -0.0)
+        if not torch.equal((g / 255.0 - mean) / std, x):                # ToTensor + Normalize in float32, as the oracle does
+            return False
+        ref = (g / 128.0).reshape(n, G, P, G, P).permute(0, 1, 3, 2, 4).reshape(n * G * G, P * P).to(patches.dtype)
+        got = patches[: n * G * G, : P * P].cpu()
+        return bool(torch.equal(got.view(torch.int16), ref.view(torch.int16)))
     ref = x.reshape(n, 3, G, P, G, P).permute(0, 2, 4, 1, 3, 5).reshape(n * G * G, 3 * P * P).to(patches.dtype)
     got = patches[: n * G * G, : 3 * P * P].cpu()
     return bool(torch.equal(got.view(torch.int16), ref.view(torch.int16)))
@@ -399,7 +409,7 @@ class Workload:
         frames, valid, _, nv = ops.plan_frames(offc, self.e2i.N, self.T, sel=selc, compact=True)
         with torch.no_grad():
             patches, _, _ = ops.event2img(torch.from_numpy(evc).to(dev), frames.to(dev), cfg["shape"], nv, cfg["count_non_zero"],
-                                          cfg["background_mask"], out=vis.patch_fmt, patch=vis.patch_size, ldk=vis.k_patch)
+                                          cfg["background_mask"], out=vis.patch_fmt, patch=vis.patch_size, ldk=vis.patch_ldk)
             feats = vis.forward_patches(patches, nv).float().cpu()
         first = torch.from_numpy(np.concatenate([[0], np.cumsum(valid.sum(1).numpy())[:-1]]))     # first view of every sample
         self.text = calibrate_text_feats(feats[first], cfg["n_cls"])

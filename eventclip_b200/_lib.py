@@ -13,7 +13,7 @@ EC_OK = 0
 EC_ERR_ARG, EC_ERR_CUDA, EC_ERR_UNSUPPORTED, EC_ERR_CAPACITY = -1, -2, -3, -4
 EC_STATUS_BAD_COORD, EC_STATUS_COUNT_OVERFLOW = 1, 2
 EC_FLAG_COUNT_NON_ZERO, EC_FLAG_BACKGROUND_MASK = 1, 2
-EC_OUT_F32_NCHW, EC_OUT_BF16_NCHW, EC_OUT_BF16_PATCH, EC_OUT_F16_PATCH = 0, 1, 2, 3
+EC_OUT_F32_NCHW, EC_OUT_BF16_NCHW, EC_OUT_BF16_PATCH, EC_OUT_F16_PATCH, EC_OUT_GRAY_BF16_PATCH, EC_OUT_GRAY_F16_PATCH = 0, 1, 2, 3, 4, 5
 EC_EPI_BF16, EC_EPI_BF16_QGELU, EC_EPI_F32_RESADD, EC_EPI_F32, EC_EPI_PATCH, EC_EPI_F16_RESADD, EC_EPI_F16X2_RESADD = 0, 1, 2, 3, 4, 5, 6
 EC_EPI_F16_OPERANDS = 0x100
 EC_ATTN_CAUSAL, EC_ATTN_F16 = 1, 2

@@ -223,6 +223,11 @@ def run_blocks(x, blocks, n_seq, Ltok, d, heads, causal=False, w16=None):
     return x
 
 
+# constants of CLIP's preprocess (Normalize), confirmed by the reference's method.py:17-18
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
 class VisionTransformer(nn.Module):
     def __init__(self, input_resolution, patch_size, width, layers, heads, output_dim):
         super().__init__()
@@ -249,6 +254,10 @@ class VisionTransformer(nn.Module):
         # residue of that rounding, carried through every residual update (ec_gemm_bf16_stats2).  The accuracy of a float32
         # stream without the LayerNorm kernels a float32 stream needs; used with the folded LayerNorm only.
         self.residual_split = os.environ.get("EC_RESIDUAL", "fp16") == "fp16x2"
+        # fused events route: the event kernel writes ONE gray plane per patch row and conv1 is folded onto it (packed_gray);
+        # EC_GRAY_FOLD=0 keeps the three normalised channels (the reference's tensor, rounded to 16 bits)
+        self.gray_fold = os.environ.get("EC_GRAY_FOLD", "1") != "0"
+        self._packed_gray, self._packed_gray_key = None, None
         # ln_1 / ln_2 folded into the in_proj / c_fc GEMMs (fp16 stream only); EC_LN_FOLD=0 keeps the LayerNorm kernels
         self.fold_ln = os.environ.get("EC_LN_FOLD", "1") != "0"
         self._packed_ln, self._packed_ln_key = None, None
@@ -276,6 +285,7 @@ class VisionTransformer(nn.Module):
     def invalidate_packed(self):
         """Call after mutating weights in a way the version counters cannot see (e.g. .data swaps)."""
         self._packed = None
+        self._packed_gray = None
         self._packed_ln = None
         self._packed16 = None
         self._epoch += 1
@@ -304,9 +314,51 @@ class VisionTransformer(nn.Module):
         return err
 
     @property
+    def k_gray(self):
+        """Row length of the single-plane (gray) patch matrix: P*P rounded up to a multiple of 8."""
+        return (self.patch_size ** 2 + 7) // 8 * 8
+
+    @property
     def patch_fmt(self):
         """ec_event2img output format that feeds this tower's patch GEMM in the inference forward."""
-        return "patch_f16" if self.operand_dtype == torch.float16 else "patch"
+        f16 = self.operand_dtype == torch.float16
+        if self.gray_fold:
+            return "gray_f16" if f16 else "gray"
+        return "patch_f16" if f16 else "patch"
+
+    @property
+    def patch_ldk(self):
+        """Row stride of that format: k_gray (one plane, conv1 folded) or k_patch (three normalised channels)."""
+        return self.k_gray if self.gray_fold else self.k_patch
+
+    def packed_gray(self):
+        """conv1 folded onto the gray plane.  Event frames are grayscale (datasets/vis.py:94-104): the three channels CLIP's
+        preprocess yields are x_c = (g / 255 - mean_c) / std_c of ONE resampled byte g, so
+            conv1(x)[j] = sum_c sum_k W[j,c,k] x_c[k] = sum_k (sum_c W[j,c,k] / (255 std_c)) g[k] - sum_c (mean_c / std_c) sum_k W[j,c,k].
+        The event kernel writes g / 128 exactly (EC_OUT_GRAY_*_PATCH); Wg = 128 sum_c W_c / (255 std_c) keeps the weights at their
+        original scale, and the constant term joins the positional embedding of the patch tokens.  A third of the patch rows'
+        bytes and of the patch GEMM's K; the A operand carries no rounding error at all.  SURVEY section 8(d) names this folding;
+        FLOPs and bytes are still reported against the three-channel formulas."""
+        key = (self._version_key(), self._epoch, self.operand_dtype)
+        if getattr(self, "_packed_gray", None) is None or key != self._packed_gray_key:
+            d, P, dev = self.width, self.patch_size, self.proj.device
+            w = self.conv1.weight.detach().to(torch.float64).reshape(d, 3, P * P)
+            mean = torch.tensor(CLIP_MEAN, dtype=torch.float64, device=dev)
+            std = torch.tensor(CLIP_STD, dtype=torch.float64, device=dev)
+            wg = (w * (128.0 / (255.0 * std)).view(1, 3, 1)).sum(1)
+            bias = -(w.sum(2) * (mean / std).view(1, 3)).sum(1)
+            wp = torch.zeros((d, self.k_gray), dtype=torch.float32, device=dev)
+            wp[:, :P * P] = wg.to(torch.float32)
+            pos = self.positional_embedding.detach().to(torch.float32).clone()
+            pos[1:] += bias.to(torch.float32)
+            new = dict(conv1=wp.to(self.operand_dtype).contiguous(), pos=pos.contiguous())
+            if getattr(self, "_packed_gray", None) is None or self._packed_gray["conv1"].dtype != new["conv1"].dtype:
+                self._packed_gray = new
+            else:                                   # same buffers: captured graphs stay valid
+                self._packed_gray["conv1"].copy_(new["conv1"])
+                self._packed_gray["pos"].copy_(new["pos"])
+            self._packed_gray_key = key
+        return self._packed_gray
 
     def mark_weights_changed(self):
         """Parameters were updated in place without touching their version counters (ec_adam on the flat buffer).  The
@@ -435,6 +487,7 @@ class VisionTransformer(nn.Module):
             return train.encode_patches_autograd(self, patches, n_img)
         pk = self.packed()
         f16 = self.operand_dtype == torch.float16
+        gray = patches.shape[1] == self.k_gray and self.k_gray != self.k_patch      # single-plane rows of the gray format
         if patches.dtype != self.operand_dtype:
             raise L.ECError(f"patch rows are {patches.dtype} but this tower computes with {self.operand_dtype} operands "
                             f"(ec_event2img out='{self.patch_fmt}'; EC_OPERANDS / visual.operand_dtype select the format)")
@@ -444,7 +497,11 @@ class VisionTransformer(nn.Module):
         M = n_img * Ltok
         dev = patches.device
         x0 = torch.empty((M, d), dtype=torch.float32, device=dev)       # tokens before ln_pre
-        ops.gemm_bf16(patches, p16["conv1"] if f16 else pk["conv1"], None, "patch", out=x0, res=pk["pos"], row_map=G2, M=n_img * G2)
+        if gray:
+            pg = self.packed_gray()
+            ops.gemm_bf16(patches, pg["conv1"], None, "patch", out=x0, res=pg["pos"], row_map=G2, M=n_img * G2)
+        else:
+            ops.gemm_bf16(patches, p16["conv1"] if f16 else pk["conv1"], None, "patch", out=x0, res=pk["pos"], row_map=G2, M=n_img * G2)
         ops.cls_rows(x0, pk["cls"], pk["pos"], n_img, Ltok, d)
         # residual stream: fp16 like the reference's CUDA inference (test.py:26-29 keeps CLIP in fp16) or fp32
         fold = self.fold_ln and self.residual_dtype == torch.float16 and ops.gemm_stats_parts(d) <= 8

@@ -65,6 +65,8 @@ struct E2IParams {
     float na[3], nb[3];
     int affine;
     int f16;        // 16-bit outputs are fp16 instead of bf16 (EC_OUT_F16_PATCH; out_fmt then reads EC_OUT_BF16_PATCH for the layout)
+    int gray;       // EC_OUT_GRAY_*_PATCH: ONE plane per patch row -- the resampled byte itself as an exact 16-bit float (P*P columns);
+                    // the three normalised channels are affine in it, so conv1 is folded to K = P*P (clip.py::packed_gray)
     // band-exchange cluster kernel (event2img_big_kernel): byte offsets of its regions in dynamic shared memory, pitches of the
     // gray plane / the transposed horizontal result, events per CTA and exchange round, multiply-shift constant of y / RB
     int big_off_b, big_off_ht, big_gp, big_hpb, big_cap;
@@ -202,6 +204,33 @@ __device__ __forceinline__ unsigned clip8(int v)
     return (unsigned)min(max(v, 0), 255);
 }
 
+
+// Eight resampled bytes b as eight 16-bit floats holding b / 128 EXACTLY -- the rows of the gray patch format (the 2^-7 keeps the
+// folded conv1 weights at the scale of the original ones, inside fp16's normal range).  fp16: 0x4800 | b = 8 + b / 128 (the ulp of
+// [8, 16) is 2^-7), minus 8; bf16: the high half of (65536 + b / 128) - 65536 (float ulp 2^-7 there, 8 significant bits).
+__device__ __forceinline__ uint4 gray16x8(uint2 v, int f16)
+{
+    uint32_t w[4];
+    if (f16) {
+        const uint32_t k = 0x48004800u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t src = j < 2 ? v.x : v.y;
+            const uint32_t h = __byte_perm(src, k, (j & 1) ? 0x5352u : 0x5150u);
+            const __half2 r = __hsub2(*reinterpret_cast<const __half2 *>(&h), *reinterpret_cast<const __half2 *>(&k));
+            w[j] = *reinterpret_cast<const uint32_t *>(&r);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t src = j < 2 ? v.x : v.y;
+            const float a = __uint_as_float(__byte_perm(src, 0x47800000u, 0x7650u + 2 * (j & 1))) - 65536.0f;
+            const float b = __uint_as_float(__byte_perm(src, 0x47800000u, 0x7651u + 2 * (j & 1))) - 65536.0f;
+            w[j] = __byte_perm(__float_as_uint(a), __float_as_uint(b), 0x7632);      // exact: a byte has at most 8 significant bits
+        }
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
 
 // ------------------------------------------------------------------------------------------------
 // P1 shared by both kernels: event scan with returning shared-memory atomics
@@ -420,7 +449,7 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
         const int slot = fr.out_slot;
         if (p.out_fmt == EC_OUT_BF16_PATCH) {
             const int P = p.patch, G = p.G;
-            const int cols = 3 * P * P;
+            const int cols = (p.gray ? 1 : 3) * P * P;
             for (int r = rank; r < G * G; r += CS) {
                 __nv_bfloat16 *o = (__nv_bfloat16 *)p.out + ((size_t)slot * G * G + r) * p.ldk;
                 for (int c = tid; c < cols; c += NT) o[c] = __float2bfloat16(0.f);
@@ -692,6 +721,13 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
                         *reinterpret_cast<float4 *>(o) = make_float4(nl[v8[0]], nl[v8[1]], nl[v8[2]], nl[v8[3]]);
                         *reinterpret_cast<float4 *>(o + 4) = make_float4(nl[v8[4]], nl[v8[5]], nl[v8[6]], nl[v8[7]]);
                     }
+                } else if (p.gray) {
+                    uint2 pk;
+                    pk.x = v8[0] | (v8[1] << 8) | (v8[2] << 16) | (v8[3] << 24);
+                    pk.y = v8[4] | (v8[5] << 8) | (v8[6] << 16) | (v8[7] << 24);
+                    const int P = p.patch;
+                    const size_t obase = ((size_t)slot * p.G * p.G + (size_t)ypq[yo] * p.G + xpq[x >> 1]) * p.ldk + ypr[yo] * P + xpr[x >> 1];
+                    *reinterpret_cast<uint4 *>((__nv_bfloat16 *)p.out + obase) = gray16x8(pk, p.f16);
                 } else {
                     // bf16: one 8-byte LUT read per pixel yields all three channels
                     uint2 t8[8];
@@ -738,8 +774,12 @@ __global__ void __launch_bounds__(1024, 1) event2img_kernel(const E2IParams p)
                 const unsigned v0 = clip8(s0), v1 = clip8(s1);
                 if (du) { du[yo * OUT + x] = (uint8_t)v0; du[yo * OUT + x + 1] = (uint8_t)v1; }
                 const size_t obase = ((size_t)slot * p.G * p.G + (size_t)ypq[yo] * p.G + xpq[xp]) * p.ldk + ypr[yo] * P + xpr[xp];
-                const uint2 t0 = nlut3[v0], t1 = nlut3[v1];
                 __nv_bfloat16 *ob = (__nv_bfloat16 *)p.out + obase;
+                if (p.gray) {
+                    *reinterpret_cast<unsigned *>(ob) = gray16x8(make_uint2(v0 | (v1 << 8), 0u), p.f16).x;
+                    continue;
+                }
+                const uint2 t0 = nlut3[v0], t1 = nlut3[v1];
                 *reinterpret_cast<unsigned *>(ob) = __byte_perm(t0.x, t1.x, 0x5410);
                 *reinterpret_cast<unsigned *>(ob + (size_t)P * P) = __byte_perm(t0.x, t1.x, 0x7632);
                 *reinterpret_cast<unsigned *>(ob + 2 * (size_t)P * P) = __byte_perm(t0.y, t1.y, 0x5410);
@@ -768,6 +808,17 @@ __device__ __forceinline__ void emit8(const E2IParams &p, uint2 v, int yo, int x
                                       const int *rowoff, const int *coloff, const float *nlut, const uint2 *nlut3)
 {
     if (du) *reinterpret_cast<uint2 *>(du + yo * OUT + x) = v;
+    if (p.gray) {
+        const uint4 o = gray16x8(v, p.f16);
+        __nv_bfloat16 *orow = (__nv_bfloat16 *)ofr + rowoff[yo];
+        if (wide) *reinterpret_cast<uint4 *>(orow + coloff[x >> 3]) = o;
+        else {
+            const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint32_t *>(orow + coloff[(x >> 1) + j]) = w4[j];
+        }
+        return;
+    }
     if (p.out_fmt == EC_OUT_F32_NCHW) {
         unsigned v8[8];
 #pragma unroll
@@ -899,7 +950,7 @@ __global__ void __launch_bounds__(1024, 1) event2img_tc_kernel(const E2IParams p
         // ---- padding frame: the reference pads missing views with zeros (event2img.py:89-91) ----
         if (fr.ev_count <= 0) {
             if (p.out_fmt == EC_OUT_BF16_PATCH) {
-                const int G = p.G, cols = 3 * p.patch * p.patch;
+                const int G = p.G, cols = (p.gray ? 1 : 3) * p.patch * p.patch;
                 for (int r = 0; r < G * G; ++r) {
                     __nv_bfloat16 *o = (__nv_bfloat16 *)p.out + ((size_t)slot * G * G + r) * p.ldk;
                     for (int c = tid; c < cols; c += NT) o[c] = __float2bfloat16(0.f);
@@ -1361,7 +1412,7 @@ __global__ void __launch_bounds__(BIG_NT, 1) event2img_big_kernel(const E2IParam
         // ---- padding frame: the reference pads missing views with zeros (event2img.py:89-91) ----
         if (fr.ev_count <= 0) {
             if (p.out_fmt == EC_OUT_BF16_PATCH) {
-                const int G = p.G, cols = 3 * p.patch * p.patch;
+                const int G = p.G, cols = (p.gray ? 1 : 3) * p.patch * p.patch;
                 for (int r = rank; r < G * G; r += CS) {
                     __nv_bfloat16 *o = (__nv_bfloat16 *)p.out + ((size_t)slot * G * G + r) * p.ldk;
                     for (int c = tid; c < cols; c += NT) o[c] = __float2bfloat16(0.f);
@@ -2230,13 +2281,14 @@ static int event2img_impl(const float *events, const uint32_t *events_c, const e
     if (n_frames == 0) return EC_OK;
     EC_REQUIRE(frames && out && status, "ec_event2img: null pointer");
     EC_REQUIRE(H > 0 && W > 0 && H >= 8 && W >= 8, "ec_event2img: bad sensor shape %dx%d", H, W);
-    EC_REQUIRE(out_fmt >= EC_OUT_F32_NCHW && out_fmt <= EC_OUT_F16_PATCH, "ec_event2img: bad out_fmt %d", out_fmt);
-    const int f16 = out_fmt == EC_OUT_F16_PATCH;
-    if (f16) out_fmt = EC_OUT_BF16_PATCH;      // same layout; the kernels pick the 16-bit format from E2IParams::f16
+    EC_REQUIRE(out_fmt >= EC_OUT_F32_NCHW && out_fmt <= EC_OUT_GRAY_F16_PATCH, "ec_event2img: bad out_fmt %d", out_fmt);
+    const int f16 = out_fmt == EC_OUT_F16_PATCH || out_fmt == EC_OUT_GRAY_F16_PATCH;
+    const int gray = out_fmt == EC_OUT_GRAY_BF16_PATCH || out_fmt == EC_OUT_GRAY_F16_PATCH;
+    if (f16 || gray) out_fmt = EC_OUT_BF16_PATCH;      // same row layout; the kernels pick the 16-bit format / the plane count from E2IParams
     int G = 0;
     if (out_fmt == EC_OUT_BF16_PATCH) {
         EC_REQUIRE(patch > 0 && patch % 2 == 0 && OUT % patch == 0, "ec_event2img: patch %d must be even and divide 224", patch);
-        EC_REQUIRE(ldk >= 3 * patch * patch && ldk % 2 == 0, "ec_event2img: ldk %d too small / odd", ldk);
+        EC_REQUIRE(ldk >= (gray ? 1 : 3) * patch * patch && ldk % 2 == 0, "ec_event2img: ldk %d too small / odd", ldk);
         G = OUT / patch;
     }
     int CS, RB, NT;
@@ -2265,6 +2317,7 @@ static int event2img_impl(const float *events, const uint32_t *events_c, const e
     for (int c = 0; c < 3; ++c) { p.na[c] = f16 ? tb.na16[c] : tb.na[c]; p.nb[c] = f16 ? tb.nb16[c] : tb.nb[c]; }
     p.affine = f16 ? tb.affine16 : tb.affine;
     p.f16 = f16;
+    p.gray = gray;
     p.band_magic = ((1ull << 40) + (unsigned long long)RB * W - 1) / ((unsigned long long)RB * W);
     p.big_off_b = p.big_off_ht = p.big_gp = p.big_hpb = p.big_cap = 0;
     p.big_rb_magic = 0;

@@ -127,7 +127,7 @@ class _CLIPClassifierBase(nn.Module):
         """events: CUDA float32 [sum E, 4]; plan: output of plan_to_device.  Enqueues kernels only."""
         fe, visual = self.event_frontend, self.model.visual
         patches, st, _ = ops.event2img(events, plan["frames"], fe.resolution, plan["n_valid"], fe.count_non_zero,
-                                       fe.background_mask, out=visual.patch_fmt, patch=visual.patch_size, ldk=visual.k_patch,
+                                       fe.background_mask, out=visual.patch_fmt, patch=visual.patch_size, ldk=visual.patch_ldk,
                                        status=status)
         self._last_status, self._last_patches = st, patches     # kept for status checks / parity checks of the frames
         feats = visual.forward_patches(patches, plan["n_valid"])

@@ -7,7 +7,8 @@ import torch
 
 from . import _lib as L
 
-OUT_FMT = {"f32": L.EC_OUT_F32_NCHW, "bf16": L.EC_OUT_BF16_NCHW, "patch": L.EC_OUT_BF16_PATCH, "patch_f16": L.EC_OUT_F16_PATCH}
+OUT_FMT = {"f32": L.EC_OUT_F32_NCHW, "bf16": L.EC_OUT_BF16_NCHW, "patch": L.EC_OUT_BF16_PATCH, "patch_f16": L.EC_OUT_F16_PATCH,
+           "gray": L.EC_OUT_GRAY_BF16_PATCH, "gray_f16": L.EC_OUT_GRAY_F16_PATCH}
 
 
 def _stream():
@@ -81,9 +82,10 @@ def event2img(events, frames, shape, n_slots, count_non_zero=False, background_m
             out_tensor = torch.empty((n_slots, 3, 224, 224), dtype=torch.bfloat16, device=dev)
         else:
             G = 224 // patch
-            ldk = ldk or 3 * patch * patch
-            out_tensor = torch.zeros((n_slots * G * G, ldk), dtype=torch.float16 if fmt == L.EC_OUT_F16_PATCH else torch.bfloat16,
-                                     device=dev)
+            gray = fmt in (L.EC_OUT_GRAY_BF16_PATCH, L.EC_OUT_GRAY_F16_PATCH)
+            ldk = ldk or (1 if gray else 3) * patch * patch
+            out_tensor = torch.zeros((n_slots * G * G, ldk), device=dev,
+                                     dtype=torch.float16 if fmt in (L.EC_OUT_F16_PATCH, L.EC_OUT_GRAY_F16_PATCH) else torch.bfloat16)
     if status is None:
         status = torch.zeros(1, dtype=torch.int32, device=dev)
     dbg = None

@@ -46,6 +46,10 @@ extern "C" {
 #define EC_OUT_BF16_NCHW 1 /* same layout, bf16 (round-to-nearest-even of the float32 value)      */
 #define EC_OUT_BF16_PATCH 2 /* bf16 [slot, G*G, ldk] im2col rows (c,dy,dx) feeding the patch GEMM  */
 #define EC_OUT_F16_PATCH 3  /* the same rows in fp16 (round-to-nearest-even of the float32 value): the fp16-operand inference forward */
+#define EC_OUT_GRAY_BF16_PATCH 4 /* ONE plane: bf16 [slot, G*G, ldk >= P*P] rows (dy,dx) holding the resampled gray byte / 128 exactly.  The three
+                                    normalised channels of a frame are affine in that byte (grayscale frames, datasets/vis.py:94-104 +
+                                    CLIP's Normalize), so the caller folds conv1 to K = P*P and a per-output bias (SURVEY 8(d) note) */
+#define EC_OUT_GRAY_F16_PATCH 5  /* the same in fp16 */
 
 EC_API const char *ec_last_error(void);
 EC_API int ec_version(void);
@@ -82,7 +86,7 @@ EC_API int ec_plan_frames(const int64_t *offsets, int B, int64_t N, int T, const
  *   events    device float32 [*,4] packed (x,y,t,p) rows, 16-byte aligned
  *   frames    device ec_frame [n_frames]
  *   H, W      sensor shape;  flags EC_FLAG_*;  out_fmt EC_OUT_*
- *   patch, ldk  only for EC_OUT_BF16_PATCH: patch size P and row stride (elements, >= 3*P*P)
+ *   patch, ldk  only for the *_PATCH formats: patch size P and row stride (elements, >= 3*P*P; >= P*P for the gray formats)
  *   out       device output images (format above)
  *   dbg_counts device int32 [n_frames,H,W,2] or NULL   (parity taps: raw counts,
  *   dbg_gray   device uint8 [n_frames,H,W]   or NULL    uint8 frame = any channel of vis.py's output,

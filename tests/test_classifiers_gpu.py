@@ -198,7 +198,11 @@ def test_events_to_logits_vs_oracle(cuda_dev, ds, arch, B):
     _assert_top1(o["logits"], ref["logits"])
     with torch.no_grad():
         o2 = zs(dict(img=imgs.to(cuda_dev), valid_mask=valid.to(cuda_dev)))
-    assert torch.equal(o2["logits"], o["logits"])     # same bf16 patch rows either way -> bitwise equal logits
+        model.visual.gray_fold = False              # three normalised channels out of the event kernel, like the image route's im2col
+        o3 = zs(dict(events=torch.from_numpy(ev).to(cuda_dev), event_offsets=torch.from_numpy(off)))
+        model.visual.gray_fold = True
+    assert torch.equal(o2["logits"], o3["logits"])    # same 16-bit patch rows either way -> bitwise equal logits
+    assert rel(o["logits"], o3["logits"]) < 5e-3      # the gray plane + folded conv1 is the same function up to operand rounding
 
 
 def test_cuda_graph_replay_matches_eager(cuda_dev):
@@ -230,6 +234,43 @@ def test_cuda_graph_replay_matches_eager(cuda_dev):
         eager = zs(d)
         got = g(d)
     assert torch.equal(got["logits"], eager["logits"]) and len(g.cache) == 1
+
+
+def test_gray_folded_conv1_matches_three_channel_route(cuda_dev):
+    """visual.gray_fold: the event kernel writes one gray plane and conv1 is folded onto it (clip.packed_gray).  Same function of
+    the events: the logits agree with the three-channel route to the operand rounding and sit at least as close to the fp32 oracle."""
+    cfg = SENSORS["n_caltech101"]
+    q = dict(max_imgs=3, N=cfg["N"], split_method="event_count", convert_method="event_histogram", grayscale=True,
+             count_non_zero=False, background_mask=True)
+    arch = "ViT-B/32"
+    oracle = clip_oracle.build_clip(arch, seed=14)
+    model = clip.CLIP(arch)
+    model.load_state_dict(oracle.state_dict())
+    model = model.to(cuda_dev).eval()
+    text = clip_oracle.synth_text_feats(cfg["n_cls"], 512, 3)
+    zs = ZSCLIPClassifier(clip_dict=dict(clip_model=model, prompt="a {}", class_names=None, agg_func="mean",
+                                         text_feats=text)).to(cuda_dev).eval()
+    zs.attach_event_frontend(q, cfg["shape"], cfg["max_n"])
+    ev, off = synth_batch("n_caltech101", 4, 17, E=60000)
+    d = dict(events=torch.from_numpy(ev).to(cuda_dev), event_offsets=torch.from_numpy(off))
+    vis = model.visual
+    assert vis.gray_fold and vis.patch_fmt.startswith("gray") and vis.patch_ldk == 1024
+    with torch.no_grad():
+        lg = zs(d)["logits"].float().cpu()
+        assert zs._last_patches.shape[1] == 1024
+        vis.gray_fold = False
+        l3 = zs(d)["logits"].float().cpu()
+        assert zs._last_patches.shape[1] == 3072
+        vis.gray_fold = True
+    B = 4
+    imgs = np.stack([orc.event2img_sample(ev[off[b]:off[b + 1]], cfg["shape"], cfg["N"], 3, False, True)[0] for b in range(B)])
+    with torch.no_grad():
+        feats = oracle.encode_image(torch.from_numpy(imgs).reshape(B * 3, 3, 224, 224))
+    ref = heads_oracle.zs_head(feats, torch.ones(B, 3, dtype=torch.bool), text, 100.0, "mean")["logits"]
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    assert rel(lg, l3) < 5e-3, rel(lg, l3)
+    assert rel(lg, ref) < 2e-2 and rel(lg, ref) <= 1.25 * rel(l3, ref) + 1e-4, (rel(lg, ref), rel(l3, ref))
+    assert torch.equal(lg.argmax(-1), ref.argmax(-1))
 
 
 def test_compact_wire_format_through_the_serving_loop(cuda_dev):

@@ -124,6 +124,31 @@ def test_output_formats_agree(cuda_dev):
         assert torch.equal(ops.im2col(f32["img"][valid.to(cuda_dev)].contiguous(), P, ldk), pt["img"])
 
 
+@pytest.mark.parametrize("ds", ["n_caltech101", "n_cars", "n_imagenet"])
+def test_gray_patch_format(cuda_dev, ds):
+    """EC_OUT_GRAY_*_PATCH: one plane per patch row holding the resampled byte / 128 exactly (fp16 and bf16), for every kernel
+    family (single-CTA tensor-core, band-exchange cluster) and patch size (32, 16, 14 = the narrow store path): equal to the
+    debug output of the resampled bytes, which the other tests pin against the reference."""
+    cfg = SENSORS[ds]
+    ev, off = synth_batch(ds, 2, 91, kind="clustered")
+    frames, valid, chunks, nv = ops.plan_frames(off, cfg["N"], 2, compact=True)
+    evd, fd = torch.from_numpy(ev).to(cuda_dev), frames.to(cuda_dev)
+    _, _, dbg = ops.event2img(evd, fd, cfg["shape"], nv, cfg["count_non_zero"], cfg["background_mask"], out="f32", debug=True)
+    u8 = dbg["u8"].cpu().float()                                                        # [nv, 224, 224]
+    for P, ldk in ((32, 1024), (16, 256), (14, 200)):
+        G = 224 // P
+        want = (u8 / 128.0).view(nv, G, P, G, P).permute(0, 1, 3, 2, 4).reshape(nv * G * G, P * P)
+        for fmt, dt in (("gray_f16", torch.float16), ("gray", torch.bfloat16)):
+            pt, st, _ = ops.event2img(evd, fd, cfg["shape"], nv, cfg["count_non_zero"], cfg["background_mask"], out=fmt, patch=P, ldk=ldk)
+            assert int(st.item()) == 0 and pt.dtype == dt and pt.shape == (nv * G * G, ldk)
+            assert torch.equal(pt[:, :P * P].cpu().float(), want), (ds, P, fmt)
+            assert (pt[:, P * P:] == 0).all()
+    words = ops.pack_events(evd, cfg["shape"])
+    ptc, _, _ = ops.event2img(words, fd, cfg["shape"], nv, cfg["count_non_zero"], cfg["background_mask"], out="gray_f16", patch=16, ldk=256)
+    pt, _, _ = ops.event2img(evd, fd, cfg["shape"], nv, cfg["count_non_zero"], cfg["background_mask"], out="gray_f16", patch=16, ldk=256)
+    assert torch.equal(ptc, pt)
+
+
 def test_events2frames_drop_in(cuda_dev):
     """Same call as the reference's datasets.vis.events2frames; uint8 [K,H,W,3] identical to the oracle."""
     for ds in ("n_caltech101", "n_cars"):
