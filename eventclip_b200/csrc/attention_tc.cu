@@ -41,6 +41,7 @@ struct AttnParams {
     int L, heads, d, n_img, causal;
     int f16;              // q, k, v, P and the output are fp16 instead of bf16 (the inference forward's fp16-operand mode)
     long long *dbg;       // EC_ATTN_DBG: clock64 stamps of CTA 0 (profiling only)
+    int exact;            // row reference = the exact row maximum (one extra pass over S) instead of the maximum of the first 32 scores
     int stagger;          // two-tile units: issue the tiles' MMAs half a period apart (EC_ATTN_STAGGER=0 restores side by side)
 };
 
@@ -230,10 +231,10 @@ __device__ __forceinline__ f2 add2(f2 a, f2 b)
 }
 // Softmax of one 128-query tile (thread = query row) followed by the O epilogue.
 // causal != 0: key j contributes to query `row` only if j <= row (text tower).
-template <uint32_t OCOL, uint32_t SUMCOL>
+template <uint32_t OCOL, uint32_t SUMCOL, int NF>      // NF: tensor-memory loads in flight in the exact-maximum pass
 __device__ __forceinline__ void softmax_tile(uint32_t lane_base, int L, int nch, bool live, int row, int lane, uint64_t *bar_p,
                                              uint64_t *bar_o, uint32_t o_parity, uint64_t *bar_oe, __nv_bfloat16 *orow,
-                                             int causal, float *lse_row, int f16, long long *dbg = nullptr)
+                                             int causal, float *lse_row, int f16, int exact, long long *dbg = nullptr)
 {
     if (dbg && lane == 0) dbg[0] = clock64();                  // S landed
     float ms_keep = 0.f;
@@ -253,6 +254,32 @@ __device__ __forceinline__ void softmax_tile(uint32_t lane_base, int L, int nch,
     #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (j < klim) m = fmaxf(m, __uint_as_float(va[j]));
+                    if (exact) {                       // the other chunks too, NF loads in flight (vb is one more: the waits cover it)
+                        for (int c = 1; c < nch; c += NF) {
+                            uint32_t vc[NF][32];
+    #pragma unroll
+                            for (int u = 0; u < NF; ++u)
+                                if (c + u < nch) tmem_ld32_issue(lane_base + (uint32_t)((c + u) * 32), vc[u]);
+                            tmem_ld_wait();
+    #pragma unroll
+                            for (int u = 0; u < NF; ++u)
+                                if (c + u < nch) {
+                                    if ((c + u + 1) * 32 <= klim) {
+                                        float m0 = __uint_as_float(vc[u][0]), m1 = __uint_as_float(vc[u][1]);
+    #pragma unroll
+                                        for (int j = 2; j < 32; j += 2) {
+                                            m0 = fmaxf(m0, __uint_as_float(vc[u][j]));
+                                            m1 = fmaxf(m1, __uint_as_float(vc[u][j + 1]));
+                                        }
+                                        m = fmaxf(m, fmaxf(m0, m1));
+                                    } else {
+    #pragma unroll
+                                        for (int j = 0; j < 32; ++j)
+                                            if ((c + u) * 32 + j < klim) m = fmaxf(m, __uint_as_float(vc[u][j]));
+                                    }
+                                }
+                        }
+                    }
                     const float ms = m * sl2;
                     ms_keep = ms;
                     // chunk c of the row: 32 scores -> 16 packed probabilities.  `full` chunks (every key visible) take the
@@ -508,9 +535,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParam
             const int img = unit / heads, h = unit % heads;
             mbar_wait(&bar_s[t], uph);
             tc_fence_after();
-            softmax_tile<O_COL, SUM_COL>(lane_base, L, nch, live, row, lane, &bar_p[t], &bar_o[t], uph, &bar_oe[t],
+            softmax_tile<O_COL, SUM_COL, 1>(lane_base, L, nch, live, row, lane, &bar_p[t], &bar_o[t], uph, &bar_oe[t],
                                          p.out + ((size_t)img * L + row) * d + h * HD, p.causal,
-                                         p.lse ? p.lse + (size_t)unit * L + row : nullptr, p.f16,
+                                         p.lse ? p.lse + (size_t)unit * L + row : nullptr, p.f16, p.exact,
                                          (p.dbg && blockIdx.x == 0 && quarter == 0 && i < 16) ? p.dbg + 64 + (i * 2 + t) * 4 : nullptr);
         }
     }
@@ -552,6 +579,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPara
     __shared__ __align__(8) uint64_t bar_qk[4], bar_v[4], bar_free[4];          // per smem stage
     __shared__ __align__(8) uint64_t bar_s[2], bar_p[2], bar_o[2], bar_oe[2];   // per tensor-memory slot
     __shared__ float s_ref[2][128];                                              // row reference, even -> odd warp of a pair
+    __shared__ float s_ref1[2][128];                                             // exact mode: the odd warp's partial row maximum
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -677,6 +705,35 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPara
             float ms = 0.f;
             if (live) {
                 const int klim = p.causal ? min(L, row + 1) : L;     // keys [0, klim) are visible to this row
+                if (p.exact) {
+                    // exact row maximum: one extra pass over this thread's chunks, partial maxima exchanged through shared memory.
+                    // With it no exponent is positive, so the 16-bit P cannot overflow whatever the scores are (fp16 operands:
+                    // a key 11 nats above the first 32 would otherwise give inf).
+                    float m = -INFINITY;
+                    for (int c = half; c < nch; c += 2) {
+                        uint32_t v[32];
+                        tmem_ld32_issue(lane_base + (uint32_t)(c * 32), v);
+                        tmem_ld_wait();
+                        if ((c + 1) * 32 <= klim) {
+                            float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]);
+#pragma unroll
+                            for (int q = 2; q < 32; q += 2) {
+                                m0 = fmaxf(m0, __uint_as_float(v[q]));
+                                m1 = fmaxf(m1, __uint_as_float(v[q + 1]));
+                            }
+                            m = fmaxf(m, fmaxf(m0, m1));
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 32; ++q)
+                                if (c * 32 + q < klim) m = fmaxf(m, __uint_as_float(v[q]));
+                        }
+                    }
+                    float *mine = half ? &s_ref1[slot][quarter * 32 + lane] : ref;
+                    float *other = half ? ref : &s_ref1[slot][quarter * 32 + lane];
+                    *mine = m;
+                    pair_sync(pair_id);
+                    ms = fmaxf(m, *other) * sl2;
+                }
                 for (int st = 0; st < n_steps; ++st) {
                     const int c = 2 * st + half;
                     const bool has = c < nch;
@@ -686,7 +743,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPara
                         tmem_ld_wait();
                     }
                     if (st == 0) {
-                        if (half == 0) {
+                        if (!p.exact && half == 0) {
                             float m = -INFINITY;
 #pragma unroll
                             for (int q = 0; q < 32; ++q)
@@ -695,7 +752,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPara
                             *ref = ms;
                         }
                         pair_sync(pair_id);           // reference visible; chunks 0 and 1 are in registers
-                        if (half == 1) ms = *ref;
+                        if (!p.exact && half == 1) ms = *ref;
                     } else if (st == 1)
                         pair_sync(pair_id);           // chunks 2 and 3 are in registers: P chunks 5 and 6 may overwrite them
                     if (has) {
@@ -773,8 +830,9 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPara
 // Shared memory holds one unit (3 tiles each of Q, K, V); Q/K of the next unit are fetched as soon as the last S MMA
 // of the current one has retired, V after the last P V MMA.
 constexpr uint32_t BIG_O_COL = 384, BIG_SUM_COL = 448;
-constexpr int BIG_NTHREADS = 160;
+constexpr int BIG_NTHREADS = 192;                // warp 0: TMA + MMA issue; warps 1-4: softmax; warp 5: rows >= 256 when there are at most BIG_TAIL_MAX
 constexpr int BIG_TILES = 3;
+constexpr int BIG_TAIL_MAX = 4;
 
 __global__ void __launch_bounds__(BIG_NTHREADS, 1)
 attention_tc_big_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
@@ -785,16 +843,23 @@ attention_tc_big_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnP
     unsigned char *sOnes = smem + 3 * BIG_TILES * TILE_BYTES;
     __shared__ __align__(8) uint64_t bar_qk, bar_v, bar_qk_free, bar_v_free, bar_s, bar_p, bar_o, bar_oe;
     __shared__ uint32_t tmem_slot;
+    __shared__ float s_tail[BIG_TAIL_MAX][BIG_TILES * 128];     // scores / probabilities of the tail rows (warp 5)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int L = p.L, d = p.d, heads = p.heads;
     const int KP = (L + 15) & ~15;
-    const int MT = (L + 127) >> 7;                    // 3 for L = 257
+    const int MT_all = (L + 127) >> 7;                // tiles of Q, K, V in shared memory: 3 for L = 257
+    // A unit of L = 257 is two full 128-query tiles plus ONE row (the class token's 256 patches + itself).  As a third tile that row
+    // would cost a whole S -> softmax -> P V -> epilogue chain (a third of the kernel's time); instead warp 5 computes the rows
+    // >= 256 with plain FMAs from the operands in shared memory while the tensor cores work on the two full tiles.
+    const int n_tail = (L > 256 && L - 256 <= BIG_TAIL_MAX) ? L - 256 : 0;
+    const int MT = n_tail ? 2 : MT_all;               // 128-query tiles that go through the tensor cores
     const int n_units = p.n_img * heads;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qkv) : "memory");
-        mbar_init(&bar_qk, 1); mbar_init(&bar_v, 1); mbar_init(&bar_qk_free, 1); mbar_init(&bar_v_free, 1);
+        mbar_init(&bar_qk, 1); mbar_init(&bar_v, 1);
+        mbar_init(&bar_qk_free, n_tail ? 2 : 1); mbar_init(&bar_v_free, n_tail ? 2 : 1);      // + the tail warp's arrival
         mbar_init(&bar_s, 1); mbar_init(&bar_p, 4); mbar_init(&bar_o, 1); mbar_init(&bar_oe, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -813,16 +878,16 @@ attention_tc_big_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnP
     if (warp == 0) {
         auto load_qk = [&](int unit) {
             const int img = unit / heads, h = unit % heads;
-            mbar_expect_tx(&bar_qk, (uint32_t)(2 * MT * TILE_BYTES));
-            for (int b = 0; b < MT; ++b) {
+            mbar_expect_tx(&bar_qk, (uint32_t)(2 * MT_all * TILE_BYTES));
+            for (int b = 0; b < MT_all; ++b) {
                 tma_load_3d(sK + b * TILE_BYTES, &map_qkv, &bar_qk, d + h * HD, b * 128, img);
                 tma_load_3d(sQ + b * TILE_BYTES, &map_qkv, &bar_qk, h * HD, b * 128, img);
             }
         };
         auto load_v = [&](int unit) {
             const int img = unit / heads, h = unit % heads;
-            mbar_expect_tx(&bar_v, (uint32_t)(MT * TILE_BYTES));
-            for (int b = 0; b < MT; ++b) tma_load_3d(sV + b * TILE_BYTES, &map_qkv, &bar_v, 2 * d + h * HD, b * 128, img);
+            mbar_expect_tx(&bar_v, (uint32_t)(MT_all * TILE_BYTES));
+            for (int b = 0; b < MT_all; ++b) tma_load_3d(sV + b * TILE_BYTES, &map_qkv, &bar_v, 2 * d + h * HD, b * 128, img);
         };
         const int n1 = KP < 256 ? KP : 256, n2 = KP - n1;          // S is issued in two column blocks
         const uint32_t FMT16 = p.f16 ? 0u : ((1u << 7) | (1u << 10));
@@ -879,7 +944,7 @@ attention_tc_big_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnP
                 __syncwarp();
             }
         }
-    } else {
+    } else if (warp <= 4) {
         const int quarter = warp & 3;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const int nch = (KP + 31) >> 5;
@@ -891,10 +956,106 @@ attention_tc_big_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnP
                 const bool live = t * 128 + quarter * 32 < L;
                 mbar_wait(&bar_s, n & 1);
                 tc_fence_after();
-                softmax_tile<BIG_O_COL, BIG_SUM_COL>(lane_base, L, nch, live, row, lane, &bar_p, &bar_o, n & 1, &bar_oe,
+                softmax_tile<BIG_O_COL, BIG_SUM_COL, 3>(lane_base, L, nch, live, row, lane, &bar_p, &bar_o, n & 1, &bar_oe,
                                                      p.out + ((size_t)img * L + row) * d + h * HD, p.causal,
-                                                     p.lse ? p.lse + (size_t)unit * L + row : nullptr, p.f16);
+                                                     p.lse ? p.lse + (size_t)unit * L + row : nullptr, p.f16, p.exact);
             }
+        }
+    } else if (n_tail) {
+        // ===================== tail rows (>= 256) on the FMA pipe, one warp =====================
+        // element (r, col) of a 128 x 64 SWIZZLE_128B tile: r * 128 + (((col >> 3) ^ (r & 7)) << 4) + (col & 7) * 2 bytes
+        const float sl2 = 0.125f * 1.4426950408889634f;
+        const int f16 = p.f16;
+        auto unpack = [&](uint32_t w, float &a, float &b) {
+            if (f16) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w));
+                a = f.x; b = f.y;
+            } else {
+                a = __uint_as_float(w << 16); b = __uint_as_float(w & 0xffff0000u);
+            }
+        };
+        int i = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++i) {
+            const uint32_t uph = (uint32_t)i & 1;
+            const int img = unit / heads, h = unit % heads;
+            mbar_wait(&bar_qk, uph);
+            for (int tr = 0; tr < n_tail; ++tr) {
+                const int row = 256 + tr;
+                const int klim = p.causal ? min(L, row + 1) : L;
+                float q[64];
+                const unsigned char *qrow = sQ + 2 * TILE_BYTES + tr * 128;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint4 w = *reinterpret_cast<const uint4 *>(qrow + ((c ^ (tr & 7)) << 4));
+                    unpack(w.x, q[8 * c], q[8 * c + 1]); unpack(w.y, q[8 * c + 2], q[8 * c + 3]);
+                    unpack(w.z, q[8 * c + 4], q[8 * c + 5]); unpack(w.w, q[8 * c + 6], q[8 * c + 7]);
+                }
+                for (int j = lane; j < BIG_TILES * 128; j += 32) {
+                    float sc = -INFINITY;
+                    if (j < klim) {
+                        const unsigned char *krow = sK + (j >> 7) * TILE_BYTES + (j & 127) * 128;
+                        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const uint4 w = *reinterpret_cast<const uint4 *>(krow + ((c ^ (j & 7)) << 4));
+                            float k0, k1;
+                            unpack(w.x, k0, k1); a0 = fmaf(q[8 * c], k0, a0); a1 = fmaf(q[8 * c + 1], k1, a1);
+                            unpack(w.y, k0, k1); a0 = fmaf(q[8 * c + 2], k0, a0); a1 = fmaf(q[8 * c + 3], k1, a1);
+                            unpack(w.z, k0, k1); a0 = fmaf(q[8 * c + 4], k0, a0); a1 = fmaf(q[8 * c + 5], k1, a1);
+                            unpack(w.w, k0, k1); a0 = fmaf(q[8 * c + 6], k0, a0); a1 = fmaf(q[8 * c + 7], k1, a1);
+                        }
+                        sc = (a0 + a1) * sl2;
+                    }
+                    s_tail[tr][j] = sc;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_qk_free);        // Q and K of this unit are no longer read by this warp
+            mbar_wait(&bar_v, uph);
+            for (int tr = 0; tr < n_tail; ++tr) {
+                const int row = 256 + tr;
+                const int klim = p.causal ? min(L, row + 1) : L;
+                float m = -INFINITY;
+                for (int j = lane; j < BIG_TILES * 128; j += 32) m = fmaxf(m, s_tail[tr][j]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                float sum = 0.f;
+                for (int j = lane; j < BIG_TILES * 128; j += 32) {
+                    const float e = fast_exp2(s_tail[tr][j] - m);          // exp2(-inf) = 0 for the keys this row does not see
+                    s_tail[tr][j] = e;
+                    sum += e;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                __syncwarp();
+                // this lane's two head columns 2 * lane, 2 * lane + 1: chunk lane >> 2, byte (lane & 3) * 4 inside it
+                float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+                const int cb = lane >> 2, inb = (lane & 3) * 4;
+                int j = 0;
+                for (; j + 1 < klim; j += 2) {
+                    const unsigned char *v0 = sV + (j >> 7) * TILE_BYTES + (j & 127) * 128 + ((cb ^ (j & 7)) << 4) + inb;
+                    const unsigned char *v1 = sV + ((j + 1) >> 7) * TILE_BYTES + ((j + 1) & 127) * 128 + ((cb ^ ((j + 1) & 7)) << 4) + inb;
+                    float a, b, c2, d2;
+                    unpack(*reinterpret_cast<const uint32_t *>(v0), a, b);
+                    unpack(*reinterpret_cast<const uint32_t *>(v1), c2, d2);
+                    const float p0 = s_tail[tr][j], p1 = s_tail[tr][j + 1];
+                    o0 = fmaf(p0, a, o0); o1 = fmaf(p0, b, o1);
+                    o2 = fmaf(p1, c2, o2); o3 = fmaf(p1, d2, o3);
+                }
+                if (j < klim) {
+                    const unsigned char *v0 = sV + (j >> 7) * TILE_BYTES + (j & 127) * 128 + ((cb ^ (j & 7)) << 4) + inb;
+                    float a, b;
+                    unpack(*reinterpret_cast<const uint32_t *>(v0), a, b);
+                    const float p0 = s_tail[tr][j];
+                    o0 = fmaf(p0, a, o0); o1 = fmaf(p0, b, o1);
+                }
+                const float inv = 1.f / sum;
+                __nv_bfloat16 *orow = p.out + ((size_t)img * L + row) * d + h * HD + 2 * lane;
+                *reinterpret_cast<uint32_t *>(orow) = pack16x2((o0 + o2) * inv, (o1 + o3) * inv, f16);
+                if (p.lse && lane == 0) p.lse[(size_t)unit * L + row] = m + log2f(sum);
+                __syncwarp();
+            }
+            if (lane == 0) mbar_arrive(&bar_v_free);         // V of this unit is no longer read by this warp
         }
     }
 
@@ -1259,6 +1420,10 @@ int attention_tc(const void *qkv, void *out, int n_img, int L, int heads, int ca
     p.out = (__nv_bfloat16 *)out; p.lse = lse; p.L = L; p.heads = heads; p.d = d; p.n_img = n_img;
     p.causal = causal & 1; p.f16 = (causal >> 1) & 1;       // EC_ATTN_CAUSAL | EC_ATTN_F16
     p.stagger = stagger;
+    // EC_ATTN_EXACT: 1 = exact row maximum as the softmax reference, 0 = maximum of the first 32 scores (single pass).  Default: exact
+    // with fp16 operands (P is stored as fp16: an exponent above 2^16 would be inf), single pass with bf16 (range 2^127, clamped).
+    static const int exact_env = [] { const char *e = getenv("EC_ATTN_EXACT"); return e ? atoi(e) : -1; }();
+    p.exact = exact_env >= 0 ? exact_env : p.f16;
     p.dbg = nullptr;
     static const int dbg_on = [] { const char *e = getenv("EC_ATTN_DBG"); return e ? atoi(e) : 0; }();
     static long long *dbg_buf = nullptr;

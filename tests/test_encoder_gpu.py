@@ -197,7 +197,9 @@ def test_layernorm_and_helpers(cuda_dev):
 # the last three cases give every persistent CTA several (image, head) units: the shared-memory ring of the two-slot kernel
 # wraps (four resident units for L <= 128, two for L <= 256), the slots alternate, odd and even unit counts per CTA
 @pytest.mark.parametrize("L,heads,n_img", [(50, 12, 3), (197, 12, 2), (257, 16, 2), (5, 2, 4), (64, 2, 1), (65, 2, 1),
-                                           (50, 12, 131), (128, 4, 333), (197, 12, 57), (129, 2, 260)])
+                                           (50, 12, 131), (128, 4, 333), (197, 12, 57), (129, 2, 260),
+                                           # 256 < L: rows >= 256 on the FMA pipe (at most four), else a third tile; many units per CTA
+                                           (258, 2, 3), (260, 2, 2), (261, 2, 2), (257, 16, 40), (384, 2, 2)])
 def test_attention(cuda_dev, L, heads, n_img):
     g = torch.Generator().manual_seed(L)
     d = heads * 64
@@ -207,6 +209,31 @@ def test_attention(cuda_dev, L, heads, n_img):
     q, k, v = [t.view(n_img, L, heads, 64).transpose(1, 2) for t in qkv.float().chunk(3, -1)]
     ref = (torch.softmax(q @ k.transpose(-1, -2) / 8.0, -1) @ v).transpose(1, 2).reshape(n_img * L, d)
     assert rel(out.float(), ref) < 8e-3, rel(out.float(), ref)
+
+
+@pytest.mark.parametrize("L,heads,n_img,dt", [(197, 2, 3, torch.float16), (197, 2, 3, torch.bfloat16), (50, 2, 5, torch.float16),
+                                             (257, 2, 2, torch.float16), (77, 2, 4, torch.float16)])
+def test_attention_peaked_rows_beyond_the_first_keys(cuda_dev, L, heads, n_img, dt):
+    """Trained towers have attention sinks: one key can sit 20+ nats above every other, anywhere in the row.  The tcgen05 kernels
+    take the EXACT row maximum as the softmax reference with fp16 operands (EC_ATTN_EXACT; bf16 keeps the single pass, range
+    2^127), so the 16-bit P never overflows: rows whose dominant key lies beyond the first 32 keys (the single-pass reference
+    window) and is 24 nats above the rest must come out as that key's value row, finite."""
+    g = torch.Generator().manual_seed(L + heads)
+    d = heads * 64
+    q = torch.ones(n_img, L, heads, 64) + 0.05 * torch.randn(n_img, L, heads, 64, generator=g)
+    k = 0.05 * torch.randn(n_img, L, heads, 64, generator=g)
+    v = torch.randn(n_img, L, heads, 64, generator=g)
+    hot = L - 7                                       # far beyond key 31; with a causal mask it would be visible to the last rows only
+    k[:, hot] = 3.0                                   # q . k = 192 -> 24 nats after the 1/8 scale
+    k[:, :, 1] = 0.05 * torch.randn(n_img, L, 64, generator=g)      # head 1 stays flat: ordinary rows in the same launch
+    qkv = torch.cat([q.reshape(n_img * L, d), k.reshape(n_img * L, d), v.reshape(n_img * L, d)], 1).to(dt)
+    out = torch.empty(n_img * L, d, dtype=dt, device=cuda_dev)
+    ops.attention(qkv.to(cuda_dev), out, n_img, L, heads)
+    qf, kf, vf = [t.view(n_img, L, heads, 64).transpose(1, 2) for t in qkv.double().chunk(3, -1)]
+    ref = (torch.softmax(qf @ kf.transpose(-1, -2) / 8.0, -1) @ vf).transpose(1, 2).reshape(n_img * L, d).float()
+    got = out.float().cpu()
+    assert torch.isfinite(got).all()
+    assert rel(got, ref) < 8e-3, rel(got, ref)
 
 
 @pytest.mark.parametrize("arch,n", [("ViT-tiny/32", 5), ("ViT-tiny/16", 3), ("ViT-B/32", 4)])
