@@ -363,7 +363,18 @@ def event2img_metric(dev, pk, kinds=("uniform", "clustered", "hotpixel"), cpu=Tr
             compact = dict(ms=msc, gevents_per_s=ev_read / msc / 1e6, frac_reference_bytes=byts / msc / 1e6 / pk["hbm_gbs"],
                            frac_compact_bytes=bytc / msc / 1e6 / pk["hbm_gbs"], input_mb=words.numel() * 4 / 1e6)
             del words
-            out[ds] = dict(compact_wire_format=compact, frames=int(nv), events_histogrammed=ev_read, events_in_streams=int(off[-1]), ms=ms,
+            # the format the classifiers really consume since round 2: ONE exact gray plane per patch row, conv1 folded onto it
+            # (clip.packed_gray): a third of the output bytes.  Reported against the reference's byte count (three normalised
+            # float channels -> 16-bit) and against the bytes this format really writes.
+            outg = torch.zeros((nv * 196, 256), dtype=torch.float16, device=dev)
+            rung = lambda: ops.event2img(evd, fd, cfg["shape"], nv, cfg["count_non_zero"], cfg["background_mask"], out="gray_f16",
+                                         patch=16, ldk=256, out_tensor=outg, status=status)
+            msg = timed(rung, reps)
+            bytg = 16 * ev_read + nv * 224 * 224 * 2
+            gray = dict(ms=msg, gevents_per_s=ev_read / msg / 1e6, frac_reference_bytes=byts / msg / 1e6 / pk["hbm_gbs"],
+                        frac_gray_bytes=bytg / msg / 1e6 / pk["hbm_gbs"], output_mb=nv * 224 * 224 * 2 / 1e6)
+            del outg
+            out[ds] = dict(compact_wire_format=compact, gray_patch_format=gray, frames=int(nv), events_histogrammed=ev_read, events_in_streams=int(off[-1]), ms=ms,
                            gevents_per_s=ev_read / ms / 1e6, gevents_per_s_stream=int(off[-1]) / ms / 1e6,
                            algorithmic_bytes=byts, achieved_gbs=byts / ms / 1e6, frac=byts / ms / 1e6 / pk["hbm_gbs"],
                            input_mb=evs.nbytes / 1e6, geometry=ops.event2img_geometry(cfg["shape"]))
