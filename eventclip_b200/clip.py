@@ -310,6 +310,12 @@ class VisionTransformer(nn.Module):
             import warnings
             warnings.warn(f"LayerNorm folding disabled for this tower: folded vs unfolded features differ by {err:.3g} (> {tol})")
             self.fold_ln = False
+        if not bool(torch.isfinite(b).all()):
+            # the fp16 residual stream itself leaves its range (|x| > 65504 somewhere): keep the stream in float32 for this tower,
+            # as EC_RESIDUAL=fp32 would (the reference's own fp16 CUDA inference overflows on such a tower too)
+            import warnings
+            warnings.warn("fp16 residual stream overflows on this tower: switching its residual stream to float32")
+            self.residual_dtype = torch.float32
         self._fold_checked = True
         return err
 
