@@ -942,7 +942,9 @@ __global__ void __launch_bounds__(1024, 1) event2img_tc_kernel(const E2IParams p
     }
     __syncthreads();
 
-    const int ht16 = (OUT * HP + 15) >> 4;          // 16-byte groups of the bins that hT overlays
+    // 16-byte groups of the bins that hT overlays, plus the 32 bytes the last rows' source windows of P6 may read beyond hT's end
+    // (zero taps, but the spare warps must not clear them concurrently: compute-sanitizer racecheck)
+    const int ht16 = ((OUT * HP + 15) >> 4) + 2;
     bool bins_clean = false;                        // bins above hT already zero (cleared by the spare warps of the last frame)
     for (int fid = blockIdx.x; fid < p.n_frames; fid += gridDim.x) {
         const ec_frame fr = p.frames[fid];
