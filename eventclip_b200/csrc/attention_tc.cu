@@ -824,6 +824,224 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPara
     }
 }
 
+// ================================================================================================================
+// Small sequences (L <= 64: ViT-B/32's 50 tokens): FOUR chains in flight.
+//
+// A (image, head) unit of 50 x 50 scores is a few hundred cycles of work for every pipe, but its chain S -> softmax -> P V ->
+// epilogue costs thousands of cycles of latency (barrier hand-offs, tensor-memory round trips): with the two slots of
+// attention_tc2_kernel a unit takes ~6 900 cycles.  Here a slot needs only 128 tensor-memory columns (S [0,64) with P packed over
+// its first half, O [64,128); the denominators are summed by the row's own thread), so four units are in flight, each served by
+// one warpgroup with ONE thread per query row; Q, K, V travel as 64-row boxes (24 KB per unit, eight units resident in shared
+// memory, fetched four units ahead).  The 128-row MMA reads 64 more rows behind Q (this unit's K): finite garbage in accumulator
+// rows 64-127, which no thread reads.  Warp 0 issues the S MMAs as far ahead as slots free up, warp 17 the TMA loads and the P V MMAs.
+// ================================================================================================================
+constexpr int S4_TILE = 64 * 128;               // 64 rows x 64 16-bit columns, SWIZZLE_128B
+constexpr int S4_UNIT = 3 * S4_TILE;            // Q, K, V of one unit
+constexpr int S4_STAGES = 8;
+constexpr uint32_t S4_SLOT_W = 128, S4_O_COL = 64;
+constexpr int NTHREADS4 = 576;                  // warp 0: S issue; warps 1-16: four softmax warpgroups; warp 17: TMA + P V issue
+
+template <int F16>
+__global__ void __launch_bounds__(NTHREADS4, 1)
+attention_tc4_kernel(const __grid_constant__ CUtensorMap map_qkv64, const AttnParams p)
+{
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t bar_ld[S4_STAGES], bar_free[S4_STAGES];      // per smem stage
+    __shared__ __align__(8) uint64_t bar_s[4], bar_p[4], bar_o[4], bar_oe[4];    // per tensor-memory slot
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int L = p.L, d = p.d, heads = p.heads;
+    const int KP = (L + 15) & ~15;                    // <= 64
+    const int n_units = p.n_img * heads;
+    const int n_my = (int)blockIdx.x < n_units ? (n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qkv64) : "memory");
+        for (int i = 0; i < S4_STAGES; ++i) { mbar_init(&bar_ld[i], 1); mbar_init(&bar_free[i], 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 4); mbar_init(&bar_o[i], 1); mbar_init(&bar_oe[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0 || warp == 17) {
+        // ===================== warp 0: S issuer; warp 17: TMA + P V issuer (no head-of-line blocking between the two) =====================
+        auto load_unit = [&](int u) {                 // elected lane only; u = this CTA's u-th unit
+            const int unit = (int)blockIdx.x + u * (int)gridDim.x, stage = u % S4_STAGES;
+            const int img = unit / heads, h = unit % heads;
+            unsigned char *sQ = smem + stage * S4_UNIT;
+            mbar_expect_tx(&bar_ld[stage], (uint32_t)S4_UNIT);
+            tma_load_3d(sQ + S4_TILE, &map_qkv64, &bar_ld[stage], d + h * HD, 0, img);
+            tma_load_3d(sQ, &map_qkv64, &bar_ld[stage], h * HD, 0, img);
+            tma_load_3d(sQ + 2 * S4_TILE, &map_qkv64, &bar_ld[stage], 2 * d + h * HD, 0, img);
+        };
+        const uint32_t FMT16 = F16 ? 0u : ((1u << 7) | (1u << 10));
+        const uint32_t idesc_s = (1u << 4) | FMT16 | ((uint32_t)(KP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc_o = (1u << 4) | FMT16 | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        if (warp == 17) {
+            if (elect_one())
+                for (int u = 0; u < S4_STAGES && u < n_my; ++u) load_unit(u);
+            __syncwarp();
+        }
+        auto issue_s = [&](int j) {
+            const int stage = j % S4_STAGES, slot = j & 3;
+            mbar_wait(&bar_ld[stage], (uint32_t)(j / S4_STAGES) & 1);
+            if (j >= 4) mbar_wait(&bar_oe[slot], (uint32_t)((j >> 2) - 1) & 1);      // the slot's previous unit is fully consumed
+            tc_fence_after();
+            unsigned char *sQ = smem + stage * S4_UNIT;
+            const uint64_t qdesc = make_desc(smem_u32(sQ)), kdesc = make_desc(smem_u32(sQ + S4_TILE));
+            const uint32_t tb = tmem_base + (uint32_t)slot * S4_SLOT_W;
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_ss(tb, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, k != 0);
+                umma_commit(&bar_s[slot]);
+            }
+            __syncwarp();
+        };
+        auto issue_pv = [&](int j) {
+            const int stage = j % S4_STAGES, slot = j & 3;
+            mbar_wait(&bar_p[slot], (uint32_t)(j >> 2) & 1);                         // P is in tensor memory
+            tc_fence_after();
+            const uint64_t vdesc = make_desc(smem_u32(smem + stage * S4_UNIT + 2 * S4_TILE));
+            const uint32_t tb = tmem_base + (uint32_t)slot * S4_SLOT_W;
+            const int nk = KP / 16;
+            if (elect_one()) {
+                for (int k = 0; k < nk; ++k)          // 16 keys per step: 8 packed columns of P, 16 rows (2048 B) of V
+                    umma_ts(tb + S4_O_COL, tb + (uint32_t)(8 * k), vdesc + (uint64_t)(128 * k), idesc_o, k != 0);
+                umma_commit(&bar_o[slot]);
+                umma_commit(&bar_free[stage]);        // every MMA that reads this stage has retired
+            }
+            __syncwarp();
+        };
+        if (warp == 0) {
+            for (int j = 0; j < n_my; ++j) issue_s(j);            // as far ahead as slots free up
+        } else {
+            for (int j = 0; j < n_my; ++j) {
+                if (j >= 2 && j - 2 + S4_STAGES < n_my) {     // the P V of unit j - 2 retired long ago: refill its stage (no wait in practice)
+                    mbar_wait(&bar_free[(j - 2) % S4_STAGES], (uint32_t)((j - 2) / S4_STAGES) & 1);
+                    if (elect_one()) load_unit(j - 2 + S4_STAGES);
+                    __syncwarp();
+                }
+                issue_pv(j);
+            }
+        }
+    } else {
+        // ===================== softmax + epilogue: one warpgroup per slot, one thread per query row =====================
+        const int slot = (warp - 1) >> 2;
+        const int quarter = warp & 3;                 // TMEM lane quarter (hardware: a warp reaches lanes 32 * (warp % 4) .. + 31)
+        const uint32_t lane_base = tmem_base + (uint32_t)slot * S4_SLOT_W + ((uint32_t)(quarter * 32) << 16);
+        const float sl2 = 0.125f * 1.4426950408889634f;
+        const int row = quarter * 32 + lane;
+        const bool live = quarter * 32 < L;           // warp-uniform
+        const int klim = p.causal ? min(L, row + 1) : L;
+        const int nch = (KP + 31) >> 5;               // 1 or 2
+        constexpr int f16 = F16;
+        int k = 0;
+        for (int j = slot; j < n_my; j += 4, ++k) {
+            const int unit = (int)blockIdx.x + j * (int)gridDim.x;
+            const int img = unit / heads, h = unit % heads;
+            const uint32_t ph = (uint32_t)k & 1;
+            mbar_wait(&bar_s[slot], ph);
+            tc_fence_after();
+            float ms = 0.f, rsum = 0.f;
+            if (live) {
+                uint32_t va[32];
+                tmem_ld32_issue(lane_base, va);
+                // row reference: exact maximum over the visible keys (the second chunk is loaded again for its exponentials:
+                // 96 registers do not hold two chunks next to the packed probabilities)
+                float m = -INFINITY;
+                if (nch > 1) {
+                    uint32_t vb[32];
+                    tmem_ld32_issue(lane_base + 32u, vb);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 32; ++q)
+                        if (32 + q < klim) m = fmaxf(m, __uint_as_float(vb[q]));
+                } else
+                    tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 32; ++q)
+                    if (q < klim) m = fmaxf(m, __uint_as_float(va[q]));
+                ms = m * sl2;
+                f2 acc2 = mk2(0.f, 0.f);
+                auto emit = [&](const uint32_t (&v)[32], int c) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int q = 0; q < 32; q += 2) {
+                        float x0 = fmaf(__uint_as_float(v[q]), sl2, -ms), x1 = fmaf(__uint_as_float(v[q + 1]), sl2, -ms);
+                        if (c * 32 + q >= klim) x0 = -INFINITY;
+                        if (c * 32 + q + 1 >= klim) x1 = -INFINITY;
+                        const float e0 = fast_exp2(x0), e1 = fast_exp2(x1);
+                        acc2 = add2(acc2, mk2(e0, e1));
+                        pk[q >> 1] = pack16x2(e0, e1, f16);
+                    }
+                    tmem_st16(lane_base + (uint32_t)(c * 16), pk);
+                };
+                emit(va, 0);
+                if (nch > 1) {
+                    tmem_ld32_issue(lane_base + 32u, va);
+                    tmem_ld_wait();
+                    emit(va, 1);
+                }
+                float a0, a1;
+                un2(acc2, a0, a1);
+                rsum = a0 + a1;
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_p[slot]);
+            // epilogue: O / rowsum -> 16 bits -> global
+            mbar_wait(&bar_o[slot], ph);
+            tc_fence_after();
+            if (live) {
+                uint32_t v0[32], v1[32];
+                tmem_ld32_issue(lane_base + S4_O_COL, v0);
+                tmem_ld32_issue(lane_base + S4_O_COL + 32u, v1);
+                tmem_ld_wait();
+                const float inv = 1.f / rsum;
+                if (row < L) {
+                    if (p.lse) p.lse[(size_t)unit * L + row] = ms + log2f(rsum);     // p_ij = exp2(s_ij * sl2 - lse)
+                    __nv_bfloat16 *orow = p.out + ((size_t)img * L + row) * d + h * HD;
+#pragma unroll
+                    for (int q = 0; q < 32; q += 8) {
+                        uint4 o;
+                        o.x = pack16x2(__uint_as_float(v0[q]) * inv, __uint_as_float(v0[q + 1]) * inv, f16);
+                        o.y = pack16x2(__uint_as_float(v0[q + 2]) * inv, __uint_as_float(v0[q + 3]) * inv, f16);
+                        o.z = pack16x2(__uint_as_float(v0[q + 4]) * inv, __uint_as_float(v0[q + 5]) * inv, f16);
+                        o.w = pack16x2(__uint_as_float(v0[q + 6]) * inv, __uint_as_float(v0[q + 7]) * inv, f16);
+                        *reinterpret_cast<uint4 *>(orow + q) = o;
+                        o.x = pack16x2(__uint_as_float(v1[q]) * inv, __uint_as_float(v1[q + 1]) * inv, f16);
+                        o.y = pack16x2(__uint_as_float(v1[q + 2]) * inv, __uint_as_float(v1[q + 3]) * inv, f16);
+                        o.z = pack16x2(__uint_as_float(v1[q + 4]) * inv, __uint_as_float(v1[q + 5]) * inv, f16);
+                        o.w = pack16x2(__uint_as_float(v1[q + 6]) * inv, __uint_as_float(v1[q + 7]) * inv, f16);
+                        *reinterpret_cast<uint4 *>(orow + 32 + q) = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_oe[slot]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 // Variant for 256 < L <= 384 (ViT-L/14: 257 tokens).  The S row no longer fits twice in tensor memory, so the 128-query
 // tiles of a unit are processed one after the other by a single softmax warpgroup:
 //   TMEM  S [0,384)  P [0,192)  O [384,448)  sums [448,464);   S = Q K^T is issued as N = 256 plus N = KP-256 MMAs.
@@ -1434,14 +1652,32 @@ int attention_tc(const void *qkv, void *out, int n_img, int L, int heads, int ca
     }
     const int units = n_img * heads;
     const int grid = units < sm_count() ? units : sm_count();
+    static const int small_on = [] { const char *e = getenv("EC_ATTN_SMALL"); return e ? atoi(e) : 1; }();
     if (L > 256) attention_tc_big_kernel<<<grid, BIG_NTHREADS, smem_big, stream>>>(map, p);
-    else if (version == 2) {
+    else if (version == 2 && L <= 64 && small_on) {
+        // four-chain kernel for small sequences: 64-row boxes
+        CUtensorMap map64;
+        cuuint32_t box64[3] = {64, 64, 1};
+        CUresult r64 = enc(&map64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(qkv), gdim, gstr, box64, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r64 != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (attention, 64-row boxes) failed with CUresult %d", (int)r64); return EC_ERR_CUDA; }
+        const size_t smem4 = (size_t)S4_STAGES * S4_UNIT + 1024;
+        static bool attr4[64] = {false};
+        if (dev_id < 64 && !attr4[dev_id]) {
+            EC_CUDA_CHECK(cudaFuncSetAttribute(attention_tc4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+            EC_CUDA_CHECK(cudaFuncSetAttribute(attention_tc4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+            attr4[dev_id] = true;
+        }
+        if (p.f16) attention_tc4_kernel<1><<<grid, NTHREADS4, smem4, stream>>>(map64, p);
+        else attention_tc4_kernel<0><<<grid, NTHREADS4, smem4, stream>>>(map64, p);
+    } else if (version == 2) {
         const bool two = L > 128;
         auto k = two ? (p.f16 ? attention_tc2_kernel<2, 1> : attention_tc2_kernel<2, 0>) : (p.f16 ? attention_tc2_kernel<1, 1> : attention_tc2_kernel<1, 0>);
         k<<<grid, NTHREADS2, smem, stream>>>(map, p);
     } else
         attention_tc_kernel<<<grid, NTHREADS, smem, stream>>>(map, p);
-    if (dbg_on && L <= 256) {      // profiling only: per-unit timeline of CTA 0 in SM clocks, relative to the first S issue
+    if (dbg_on && L <= 256 && !(L <= 64 && small_on)) {      // profiling only: per-unit timeline of CTA 0 in SM clocks, relative to the first S issue
         long long h[256];
         EC_CUDA_CHECK(cudaStreamSynchronize(stream));
         EC_CUDA_CHECK(cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
