@@ -37,6 +37,7 @@ constexpr int ONES_BYTES = 2048;                // 16 rows x 64 bf16 of 1.0: B o
 
 struct AttnParams {
     __nv_bfloat16 *out;
+    const __nv_bfloat16 *qkv;      // the packed input (attention_tc2x_kernel reads key / value row 0 and query row 256 directly)
     float *lse;           // optional [n_img, heads, L]: log2-domain log-sum-exp of every row (kept for the backward pass)
     int L, heads, d, n_img, causal;
     int f16;              // q, k, v, P and the output are fp16 instead of bf16 (the inference forward's fp16-operand mode)
@@ -823,6 +824,420 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPara
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
+
+// ================================================================================================================
+// ViT-L/14 (L = 257 = class token + 16 x 16 patches) on the two-slot kernel.
+//
+// 257 keys need 272 score columns and two slots of them do not fit tensor memory, which is why attention_tc_big_kernel runs ONE
+// chain at a time.  Here the tensor cores see exactly 256 keys (keys 1 .. 256: K and V boxes start at row 1) and 256 queries
+// (rows 0 .. 255), i.e. attention_tc2_kernel's geometry with two 256-column slots, and the two leftovers are folded in:
+//   * key 0: every softmax thread computes its half of q_row . k_0 (q from the swizzled tile in shared memory, k_0 from global),
+//     the two halves meet in the exchange of the exact-maximum pass; p_0 = exp2(s_0 - max) joins the denominator and p_0 v_0 is
+//     added to the O row in the epilogue (fp32);
+//   * query row 256: warps 17-19 compute it with plain FMAs from the K / V tiles in shared memory, a third of the keys each.
+// Always the exact row maximum.  Non-causal only.
+// ================================================================================================================
+constexpr int NTHREADS2X = 640;                 // warp 0: TMA + MMA issue; warps 1-16: softmax; warps 17-19: query row 256
+
+__device__ __forceinline__ void unpack16x2(uint32_t w, int f16, float &a, float &b)
+{
+    if (f16) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w));
+        a = f.x; b = f.y;
+    } else {
+        a = __uint_as_float(w << 16); b = __uint_as_float(w & 0xffff0000u);
+    }
+}
+
+template <int F16>
+__global__ void __launch_bounds__(NTHREADS2X, 1)
+attention_tc2x_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
+{
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char *sOnes = smem + 2 * STAGE_BYTES;    // all-ones operand: O's companion MMA yields the softmax denominators
+    __shared__ __align__(8) uint64_t bar_qk[4], bar_v[4], bar_free[4];          // per smem stage
+    __shared__ __align__(8) uint64_t bar_s[2], bar_p[2], bar_o[2], bar_oe[2];   // per tensor-memory slot
+    __shared__ float s_ref[2][128];                                              // row reference, even -> odd warp of a pair
+    __shared__ float s_ref1[2][128];                                             // the odd warp's partial row maximum
+    __shared__ float s_dot[2][2][128];                                           // partial q . k_0 of the two warps of a pair
+    __shared__ float s_tail[272];                                                // scores / probabilities of query row 256 (warps 17-19)
+    __shared__ float s_tpart[3][66];                                             // their partial outputs, maxima and sums
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int L = p.L, d = p.d, heads = p.heads;
+    constexpr int MT = 2;                             // query rows 0 .. 255; row 256 belongs to warp 17
+    const int KP = 256;                               // keys 1 .. 256 go through the tensor cores; key 0 is folded in by the softmax threads
+    const int NST = 2;                                // units resident in shared memory
+    const int stage_bytes = 3 * MT * TILE_BYTES;
+    const int n_units = p.n_img * heads;
+    const int n_my = (int)blockIdx.x < n_units ? (n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int n_items = n_my * MT;                    // item j = (unit j / MT, tile j % MT) runs in slot j & 1
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qkv) : "memory");
+        for (int i = 0; i < 4; ++i) { mbar_init(&bar_qk[i], 1); mbar_init(&bar_v[i], 1); mbar_init(&bar_free[i], 4); }   // bar_free: MMA commit + warps 17-19
+        for (int i = 0; i < 2; ++i) { mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 8); mbar_init(&bar_o[i], 1); mbar_init(&bar_oe[i], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < ONES_BYTES / 4; i += NTHREADS2X) reinterpret_cast<uint32_t *>(sOnes)[i] = F16 ? 0x3c003c00u : 0x3f803f80u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA + MMA issuer =====================
+        auto load_unit = [&](int u) {                 // elected lane only; u = this CTA's u-th unit
+            const int unit = (int)blockIdx.x + u * (int)gridDim.x, stage = u % NST;
+            const int img = unit / heads, h = unit % heads;
+            unsigned char *sQ = smem + stage * stage_bytes, *sK = sQ + MT * TILE_BYTES, *sV = sQ + 2 * MT * TILE_BYTES;
+            mbar_expect_tx(&bar_qk[stage], (uint32_t)(2 * MT * TILE_BYTES));
+            for (int b = 0; b < MT; ++b) {
+                tma_load_3d(sK + b * TILE_BYTES, &map_qkv, &bar_qk[stage], d + h * HD, 1 + b * 128, img);      // keys 1 .. 256
+                tma_load_3d(sQ + b * TILE_BYTES, &map_qkv, &bar_qk[stage], h * HD, b * 128, img);
+            }
+            mbar_expect_tx(&bar_v[stage], (uint32_t)(MT * TILE_BYTES));
+            for (int b = 0; b < MT; ++b) tma_load_3d(sV + b * TILE_BYTES, &map_qkv, &bar_v[stage], 2 * d + h * HD, 1 + b * 128, img);
+        };
+        const uint32_t FMT16 = F16 ? 0u : ((1u << 7) | (1u << 10));
+        const uint32_t idesc_s = (1u << 4) | FMT16 | ((uint32_t)(KP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc_o = (1u << 4) | FMT16 | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc_1 = (1u << 4) | FMT16 | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint64_t odesc = make_desc(smem_u32(sOnes));
+        if (elect_one())
+            for (int u = 0; u < NST && u < n_my; ++u) load_unit(u);
+        __syncwarp();
+        auto issue_s = [&](int j) {
+            const int u = j / MT, t = j - u * MT, stage = u % NST, slot = j & 1;
+            mbar_wait(&bar_qk[stage], (uint32_t)(u / NST) & 1);
+            if (j >= 2) mbar_wait(&bar_oe[slot], (uint32_t)((j - 2) >> 1) & 1);      // the slot's previous item is fully consumed
+            tc_fence_after();
+            unsigned char *sQ = smem + stage * stage_bytes, *sK = sQ + MT * TILE_BYTES;
+            const uint64_t kdesc = make_desc(smem_u32(sK)), qdesc = make_desc(smem_u32(sQ + t * TILE_BYTES));
+            const uint32_t tb = tmem_base + (uint32_t)(slot * TILE_COLS);
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_ss(tb, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, k != 0);
+                umma_commit(&bar_s[slot]);
+                if (p.dbg && blockIdx.x == 0 && j < 32) p.dbg[j * 2] = clock64();
+            }
+            __syncwarp();
+        };
+        auto issue_pv = [&](int j) {
+            const int u = j / MT, t = j - u * MT, stage = u % NST, slot = j & 1;
+            mbar_wait(&bar_v[stage], (uint32_t)(u / NST) & 1);
+            mbar_wait(&bar_p[slot], (uint32_t)(j >> 1) & 1);                         // P is in tensor memory
+            tc_fence_after();
+            unsigned char *sV = smem + stage * stage_bytes + 2 * MT * TILE_BYTES;
+            const uint64_t vdesc = make_desc(smem_u32(sV));
+            const uint32_t tb = tmem_base + (uint32_t)(slot * TILE_COLS);
+            const bool last = t == MT - 1;
+            const int nk = KP / 16;
+            if (elect_one()) {
+                for (int k = 0; k < nk; ++k) {        // 16 keys per step: 8 packed columns of P, 16 rows (2048 B) of V
+                    umma_ts(tb + O_COL, tb + (uint32_t)(8 * k), vdesc + (uint64_t)(128 * k), idesc_o, k != 0);
+                    umma_ts(tb + SUM_COL, tb + (uint32_t)(8 * k), odesc, idesc_1, k != 0);   // += P . 1
+                }
+                umma_commit(&bar_o[slot]);
+                if (last) umma_commit(&bar_free[stage]);      // every MMA that reads this stage has retired
+                if (p.dbg && blockIdx.x == 0 && j < 32) p.dbg[j * 2 + 1] = clock64();
+            }
+            __syncwarp();
+            if (last && u + NST < n_my) {             // the stage is free once those MMAs have retired: fetch the unit NST ahead
+                mbar_wait(&bar_free[stage], (uint32_t)(u / NST) & 1);
+                if (elect_one()) load_unit(u + NST);
+                __syncwarp();
+            }
+        };
+        for (int j = 0; j < n_items; ++j) {
+            issue_s(j);
+            if (j >= 1) issue_pv(j - 1);
+        }
+        if (n_items >= 1) issue_pv(n_items - 1);
+    } else if (warp <= 16) {
+        // ===================== softmax + epilogue: two threads per query row =====================
+        const int slot = (warp - 1) >> 3;             // tensor-memory slot served by this warp
+        const int half = ((warp - 1) >> 2) & 1;       // 0: even 32-column chunks (and the row reference), 1: odd chunks
+        const int quarter = warp & 3;                 // TMEM lane quarter (hardware: a warp reaches lanes 32 * (warp % 4) .. + 31)
+        const int pair_id = 1 + slot * 4 + quarter;   // named barrier of the two warps that share the rows
+        const uint32_t lane_base = tmem_base + (uint32_t)(slot * TILE_COLS) + ((uint32_t)(quarter * 32) << 16);
+        const float sl2 = 0.125f * 1.4426950408889634f;
+        const int nch = (KP + 31) >> 5;               // 32-column chunks of S
+        const int n_steps = max(2, (nch - half + 1) >> 1);
+        float *ref = &s_ref[slot][quarter * 32 + lane];
+        constexpr int f16 = F16;
+        int k = 0;
+        for (int j = slot; j < n_items; j += 2, ++k) {
+            const int u = j / MT, t = j - u * MT;
+            const int unit = (int)blockIdx.x + u * (int)gridDim.x;
+            const int img = unit / heads, h = unit % heads;
+            const int row = t * 128 + quarter * 32 + lane;
+            const bool live = t * 128 + quarter * 32 < L;     // pair-uniform: these warps own at least one real query row
+            const uint32_t ph = (uint32_t)k & 1;
+            long long *dbg = (p.dbg && blockIdx.x == 0 && quarter == 0 && half == 0 && lane == 0 && j < 32) ? p.dbg + 64 + j * 4 : nullptr;
+            // key 0 (the class token's key): this thread's half of q_row . k_0, q from the swizzled tile in shared memory, k_0 from global
+            const int stage = u % NST, rt = quarter * 32 + lane;
+            const __nv_bfloat16 *kv0 = p.qkv + (size_t)img * L * 3 * d + d + h * HD;      // k_0 of this head; v_0 lies d elements further
+            mbar_wait(&bar_qk[stage], (uint32_t)(u / NST) & 1);                           // the TMA writes of Q are visible to this thread
+            float dp = 0.f;
+            {
+                const unsigned char *qrow = smem + stage * stage_bytes + t * TILE_BYTES + rt * 128;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint4 qa = *reinterpret_cast<const uint4 *>(qrow + (((4 * half + c) ^ (rt & 7)) << 4));
+                    const uint4 kb = __ldg(reinterpret_cast<const uint4 *>(kv0) + 4 * half + c);
+                    const uint32_t qa4[4] = {qa.x, qa.y, qa.z, qa.w}, kb4[4] = {kb.x, kb.y, kb.z, kb.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float q0, q1, k0, k1;
+                        unpack16x2(qa4[e], f16, q0, q1);
+                        unpack16x2(kb4[e], f16, k0, k1);
+                        dp = fmaf(q0, k0, fmaf(q1, k1, dp));
+                    }
+                }
+            }
+            mbar_wait(&bar_s[slot], ph);
+            tc_fence_after();
+            if (dbg) dbg[0] = clock64();
+            float ms = 0.f, p0 = 0.f;
+            if (live) {
+                const int klim = 256;                                // every tensor-core key (1 .. 256) is visible
+                {
+                    // exact row maximum: one extra pass over this thread's chunks, partial maxima exchanged through shared memory.
+                    // With it no exponent is positive, so the 16-bit P cannot overflow whatever the scores are (fp16 operands:
+                    // a key 11 nats above the first 32 would otherwise give inf).
+                    float m = -INFINITY;
+                    for (int c = half; c < nch; c += 2) {
+                        uint32_t v[32];
+                        tmem_ld32_issue(lane_base + (uint32_t)(c * 32), v);
+                        tmem_ld_wait();
+                        if ((c + 1) * 32 <= klim) {
+                            float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]);
+#pragma unroll
+                            for (int q = 2; q < 32; q += 2) {
+                                m0 = fmaxf(m0, __uint_as_float(v[q]));
+                                m1 = fmaxf(m1, __uint_as_float(v[q + 1]));
+                            }
+                            m = fmaxf(m, fmaxf(m0, m1));
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 32; ++q)
+                                if (c * 32 + q < klim) m = fmaxf(m, __uint_as_float(v[q]));
+                        }
+                    }
+                    float *mine = half ? &s_ref1[slot][quarter * 32 + lane] : ref;
+                    float *other = half ? ref : &s_ref1[slot][quarter * 32 + lane];
+                    *mine = m;
+                    s_dot[half][slot][rt] = dp;
+                    pair_sync(pair_id);
+                    const float s0 = dp + s_dot[half ^ 1][slot][rt];         // q_row . k_0
+                    ms = fmaxf(fmaxf(m, *other), s0) * sl2;
+                    p0 = fast_exp2(fmaf(s0, sl2, -ms));
+                }
+                for (int st = 0; st < n_steps; ++st) {
+                    const int c = 2 * st + half;
+                    const bool has = c < nch;
+                    uint32_t v[32];
+                    if (has) {
+                        tmem_ld32_issue(lane_base + (uint32_t)(c * 32), v);
+                        tmem_ld_wait();
+                    }
+                    if (st == 0) {
+                        pair_sync(pair_id);           // chunks 0 and 1 are in registers
+                    } else if (st == 1)
+                        pair_sync(pair_id);           // chunks 2 and 3 are in registers: P chunks 5 and 6 may overwrite them
+                    if (has) {
+                        uint32_t pk[16];
+                        const f2 sl2x = mk2(sl2, sl2), msx = mk2(-ms, -ms);
+                        if ((c + 1) * 32 <= klim) {
+#pragma unroll
+                            for (int q = 0; q < 32; q += 2) {
+                                float x0, x1;
+                                un2(fma2(mk2u(v[q], v[q + 1]), sl2x, msx), x0, x1);
+                                x0 = fminf(x0, 120.f);
+                                x1 = fminf(x1, 120.f);
+                                pk[q >> 1] = pack16x2(fast_exp2(x0), fast_exp2(x1), f16);
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 32; q += 2) {
+                                float x0 = fminf(fmaf(__uint_as_float(v[q]), sl2, -ms), 120.f);
+                                float x1 = fminf(fmaf(__uint_as_float(v[q + 1]), sl2, -ms), 120.f);
+                                if (c * 32 + q >= klim) x0 = -INFINITY;
+                                if (c * 32 + q + 1 >= klim) x1 = -INFINITY;
+                                pk[q >> 1] = pack16x2(fast_exp2(x0), fast_exp2(x1), f16);
+                            }
+                        }
+                        tmem_st16(lane_base + (uint32_t)(c * 16), pk);
+                    }
+                }
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_p[slot]);
+            if (dbg) dbg[1] = clock64();
+            // epilogue: O / rowsum -> 16 bits -> global; this warp takes 32 of the 64 head columns
+            mbar_wait(&bar_o[slot], ph);
+            tc_fence_after();
+            if (dbg) dbg[2] = clock64();
+            if (live) {
+                uint32_t v[32];
+                tmem_ld32_issue(lane_base + O_COL + (uint32_t)(half * 32), v);
+                const float rsum = tmem_ld1(lane_base + SUM_COL) + p0;      // (waits for both loads); + key 0
+                const float inv = 1.f / rsum;
+                {
+                    if (p.lse && half == 0) p.lse[(size_t)unit * L + row] = ms + log2f(rsum);     // p_ij = exp2(s_ij * sl2 - lse)
+                    __nv_bfloat16 *orow = p.out + ((size_t)img * L + row) * d + h * HD + half * 32;
+                    const uint4 *v0p = reinterpret_cast<const uint4 *>(kv0 + d) + 4 * half;       // v_0, this warp's 32 head columns
+#pragma unroll
+                    for (int q = 0; q < 32; q += 8) {
+                        const uint4 vv = __ldg(v0p + (q >> 3));
+                        float a0, a1, a2, a3, a4, a5, a6, a7;
+                        unpack16x2(vv.x, f16, a0, a1); unpack16x2(vv.y, f16, a2, a3);
+                        unpack16x2(vv.z, f16, a4, a5); unpack16x2(vv.w, f16, a6, a7);
+                        uint4 o;
+                        o.x = pack16x2(fmaf(p0, a0, __uint_as_float(v[q])) * inv, fmaf(p0, a1, __uint_as_float(v[q + 1])) * inv, f16);
+                        o.y = pack16x2(fmaf(p0, a2, __uint_as_float(v[q + 2])) * inv, fmaf(p0, a3, __uint_as_float(v[q + 3])) * inv, f16);
+                        o.z = pack16x2(fmaf(p0, a4, __uint_as_float(v[q + 4])) * inv, fmaf(p0, a5, __uint_as_float(v[q + 5])) * inv, f16);
+                        o.w = pack16x2(fmaf(p0, a6, __uint_as_float(v[q + 6])) * inv, fmaf(p0, a7, __uint_as_float(v[q + 7])) * inv, f16);
+                        *reinterpret_cast<uint4 *>(orow + q) = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_oe[slot]);
+            if (dbg) dbg[3] = clock64();
+        }
+    } else {
+        // ===================== warps 17-19: query row 256 on the FMA pipe, a third of the 257 keys each =====================
+        // (one warp needs ~24 k cycles per unit for the row -- more than the two tiles take on the tensor-core path)
+        const float sl2 = 0.125f * 1.4426950408889634f;
+        constexpr int f16 = F16;
+        const int row = 256, w = warp - 17;
+        const int j0 = w * 86, j1 = min(L, j0 + 86);             // this warp's keys [j0, j1)
+        for (int u = 0; u < n_my; ++u) {
+            const int unit = (int)blockIdx.x + u * (int)gridDim.x, stage = u % NST;
+            const int img = unit / heads, h = unit % heads;
+            const uint32_t sph = (uint32_t)(u / NST) & 1;
+            const __nv_bfloat16 *base = p.qkv + (size_t)img * L * 3 * d + h * HD;
+            float q[64];
+            {
+                const uint4 *qp = reinterpret_cast<const uint4 *>(base + (size_t)row * 3 * d);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint4 x = __ldg(qp + c);
+                    unpack16x2(x.x, f16, q[8 * c], q[8 * c + 1]); unpack16x2(x.y, f16, q[8 * c + 2], q[8 * c + 3]);
+                    unpack16x2(x.z, f16, q[8 * c + 4], q[8 * c + 5]); unpack16x2(x.w, f16, q[8 * c + 6], q[8 * c + 7]);
+                }
+            }
+            mbar_wait(&bar_qk[stage], sph);
+            unsigned char *sK = smem + stage * stage_bytes + MT * TILE_BYTES, *sV = smem + stage * stage_bytes + 2 * MT * TILE_BYTES;
+            // score of key j: j = 0 from global (k_0), j >= 1 from the K tiles (tile row j - 1)
+            float m = -INFINITY;
+            for (int j = j0 + lane; j < j0 + 96; j += 32) {
+                float sc = -INFINITY;
+                if (j < j1) {
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        uint4 x;
+                        if (j == 0) x = __ldg(reinterpret_cast<const uint4 *>(base + d) + c);
+                        else {
+                            const int kk = j - 1;
+                            x = *reinterpret_cast<const uint4 *>(sK + (kk >> 7) * TILE_BYTES + (kk & 127) * 128 + ((c ^ (kk & 7)) << 4));
+                        }
+                        float k0, k1;
+                        unpack16x2(x.x, f16, k0, k1); a0 = fmaf(q[8 * c], k0, a0); a1 = fmaf(q[8 * c + 1], k1, a1);
+                        unpack16x2(x.y, f16, k0, k1); a2 = fmaf(q[8 * c + 2], k0, a2); a3 = fmaf(q[8 * c + 3], k1, a3);
+                        unpack16x2(x.z, f16, k0, k1); a0 = fmaf(q[8 * c + 4], k0, a0); a1 = fmaf(q[8 * c + 5], k1, a1);
+                        unpack16x2(x.w, f16, k0, k1); a2 = fmaf(q[8 * c + 6], k0, a2); a3 = fmaf(q[8 * c + 7], k1, a3);
+                    }
+                    sc = ((a0 + a1) + (a2 + a3)) * sl2;
+                    s_tail[j] = sc;
+                }
+                m = fmaxf(m, sc);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            __syncwarp();
+            float sum = 0.f;
+            for (int j = j0 + lane; j < j1; j += 32) {
+                const float e = fast_exp2(s_tail[j] - m);
+                s_tail[j] = e;
+                sum += e;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            __syncwarp();
+            mbar_wait(&bar_v[stage], sph);
+            // this lane's two head columns 2 * lane, 2 * lane + 1: 16-byte chunk lane >> 2, byte (lane & 3) * 4 inside it
+            const int cb = lane >> 2, inb = (lane & 3) * 4;
+            float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+            int j = j0;
+            if (j == 0) {
+                float a, b;
+                unpack16x2(__ldg(reinterpret_cast<const uint32_t *>(base + 2 * d) + lane), f16, a, b);      // v_0
+                o0 = s_tail[0] * a; o1 = s_tail[0] * b;
+                j = 1;
+            }
+            for (; j + 1 < j1; j += 2) {
+                const int ka = j - 1, kb = j;
+                const unsigned char *va = sV + (ka >> 7) * TILE_BYTES + (ka & 127) * 128 + ((cb ^ (ka & 7)) << 4) + inb;
+                const unsigned char *vb = sV + (kb >> 7) * TILE_BYTES + (kb & 127) * 128 + ((cb ^ (kb & 7)) << 4) + inb;
+                float a, b, c2, d2;
+                unpack16x2(*reinterpret_cast<const uint32_t *>(va), f16, a, b);
+                unpack16x2(*reinterpret_cast<const uint32_t *>(vb), f16, c2, d2);
+                const float pa = s_tail[j], pb = s_tail[j + 1];
+                o0 = fmaf(pa, a, o0); o1 = fmaf(pa, b, o1);
+                o2 = fmaf(pb, c2, o2); o3 = fmaf(pb, d2, o3);
+            }
+            if (j < j1) {
+                const int ka = j - 1;
+                const unsigned char *va = sV + (ka >> 7) * TILE_BYTES + (ka & 127) * 128 + ((cb ^ (ka & 7)) << 4) + inb;
+                float a, b;
+                unpack16x2(*reinterpret_cast<const uint32_t *>(va), f16, a, b);
+                const float pa = s_tail[j];
+                o0 = fmaf(pa, a, o0); o1 = fmaf(pa, b, o1);
+            }
+            // partials -> warp 17 combines the three key ranges
+            s_tpart[w][2 * lane] = o0 + o2; s_tpart[w][2 * lane + 1] = o1 + o3;
+            if (lane == 0) { s_tpart[w][64] = m; s_tpart[w][65] = sum; }
+            asm volatile("bar.sync 9, 96;" ::: "memory");
+            if (w == 0) {
+                const float m0 = s_tpart[0][64], m1 = s_tpart[1][64], m2 = s_tpart[2][64];
+                const float mm = fmaxf(m0, fmaxf(m1, m2));
+                const float c0 = fast_exp2(m0 - mm), c1 = fast_exp2(m1 - mm), c2 = fast_exp2(m2 - mm);
+                const float tot = s_tpart[0][65] * c0 + s_tpart[1][65] * c1 + s_tpart[2][65] * c2;
+                const float inv = 1.f / tot;
+                const float x0 = s_tpart[0][2 * lane] * c0 + s_tpart[1][2 * lane] * c1 + s_tpart[2][2 * lane] * c2;
+                const float x1 = s_tpart[0][2 * lane + 1] * c0 + s_tpart[1][2 * lane + 1] * c1 + s_tpart[2][2 * lane + 1] * c2;
+                __nv_bfloat16 *orow = p.out + ((size_t)img * L + row) * d + h * HD + 2 * lane;
+                *reinterpret_cast<uint32_t *>(orow) = pack16x2(x0 * inv, x1 * inv, f16);
+                if (p.lse && lane == 0) p.lse[(size_t)unit * L + row] = mm + log2f(tot);
+            }
+            asm volatile("bar.sync 9, 96;" ::: "memory");        // the partials have been read: the next unit may overwrite them
+            if (lane == 0) mbar_arrive(&bar_free[stage]);        // this warp no longer reads the stage
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 
 // ================================================================================================================
 // Small sequences (L <= 64: ViT-B/32's 50 tokens): FOUR chains in flight.
@@ -1635,7 +2050,7 @@ int attention_tc(const void *qkv, void *out, int n_img, int L, int heads, int ca
     static const int stagger = [] { const char *e = getenv("EC_ATTN_STAGGER"); return e ? atoi(e) : 1; }();
     static const int version = [] { const char *e = getenv("EC_ATTN_V"); return e ? atoi(e) : 2; }();
     AttnParams p;
-    p.out = (__nv_bfloat16 *)out; p.lse = lse; p.L = L; p.heads = heads; p.d = d; p.n_img = n_img;
+    p.out = (__nv_bfloat16 *)out; p.qkv = (const __nv_bfloat16 *)qkv; p.lse = lse; p.L = L; p.heads = heads; p.d = d; p.n_img = n_img;
     p.causal = causal & 1; p.f16 = (causal >> 1) & 1;       // EC_ATTN_CAUSAL | EC_ATTN_F16
     p.stagger = stagger;
     // EC_ATTN_EXACT: 1 = exact row maximum as the softmax reference, 0 = maximum of the first 32 scores (single pass).  Default: exact
@@ -1653,7 +2068,17 @@ int attention_tc(const void *qkv, void *out, int n_img, int L, int heads, int ca
     const int units = n_img * heads;
     const int grid = units < sm_count() ? units : sm_count();
     static const int small_on = [] { const char *e = getenv("EC_ATTN_SMALL"); return e ? atoi(e) : 1; }();
-    if (L > 256) attention_tc_big_kernel<<<grid, BIG_NTHREADS, smem_big, stream>>>(map, p);
+    static const int x257 = [] { const char *e = getenv("EC_ATTN_257"); return e ? atoi(e) : 1; }();
+    if (L == 257 && !p.causal && x257 && version == 2) {
+        static bool attrx[64] = {false};
+        if (dev_id < 64 && !attrx[dev_id]) {
+            EC_CUDA_CHECK(cudaFuncSetAttribute(attention_tc2x_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            EC_CUDA_CHECK(cudaFuncSetAttribute(attention_tc2x_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attrx[dev_id] = true;
+        }
+        if (p.f16) attention_tc2x_kernel<1><<<grid, NTHREADS2X, smem, stream>>>(map, p);
+        else attention_tc2x_kernel<0><<<grid, NTHREADS2X, smem, stream>>>(map, p);
+    } else if (L > 256) attention_tc_big_kernel<<<grid, BIG_NTHREADS, smem_big, stream>>>(map, p);
     else if (version == 2 && L <= 64 && small_on) {
         // four-chain kernel for small sequences: 64-row boxes
         CUtensorMap map64;
