@@ -834,10 +834,11 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPara
 //   * key 0: every softmax thread computes its half of q_row . k_0 (q from the swizzled tile in shared memory, k_0 from global),
 //     the two halves meet in the exchange of the exact-maximum pass; p_0 = exp2(s_0 - max) joins the denominator and p_0 v_0 is
 //     added to the O row in the epilogue (fp32);
-//   * query row 256: warps 17-19 compute it with plain FMAs from the K / V tiles in shared memory, a third of the keys each.
+//   * query row 256: warps 17-19 compute it with mma.sync m16n8k16 from the K / V tiles in shared memory (the row is row 0 of the A
+//     fragments), a third of the keys each with its own maximum; warp 17 combines the three partial rows.
 // Always the exact row maximum.  Non-causal only.
 // ================================================================================================================
-constexpr int NTHREADS2X = 640;                 // warp 0: TMA + MMA issue; warps 1-16: softmax; warps 17-19: query row 256
+constexpr int NTHREADS2X = 640;                 // warp 0: TMA + MMA issue; warps 1-16: softmax; warps 17-19: query row 256 (mma.sync)
 
 __device__ __forceinline__ void unpack16x2(uint32_t w, int f16, float &a, float &b)
 {
@@ -847,6 +848,17 @@ __device__ __forceinline__ void unpack16x2(uint32_t w, int f16, float &a, float 
     } else {
         a = __uint_as_float(w << 16); b = __uint_as_float(w & 0xffff0000u);
     }
+}
+
+template <int F16>
+__device__ __forceinline__ void mma16816(float (&dd)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+{
+    if (F16)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(dd[0]), "+f"(dd[1]), "+f"(dd[2]), "+f"(dd[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    else
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(dd[0]), "+f"(dd[1]), "+f"(dd[2]), "+f"(dd[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
 template <int F16>
@@ -862,7 +874,7 @@ attention_tc2x_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPar
     __shared__ float s_ref1[2][128];                                             // the odd warp's partial row maximum
     __shared__ float s_dot[2][2][128];                                           // partial q . k_0 of the two warps of a pair
     __shared__ float s_tail[272];                                                // scores / probabilities of query row 256 (warps 17-19)
-    __shared__ float s_tpart[3][66];                                             // their partial outputs, maxima and sums
+    __shared__ float s_tpart[3][66];                                             // their partial rows, maxima and sums
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1119,59 +1131,66 @@ attention_tc2x_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPar
             if (dbg) dbg[3] = clock64();
         }
     } else {
-        // ===================== warps 17-19: query row 256 on the FMA pipe, a third of the 257 keys each =====================
-        // (one warp needs ~24 k cycles per unit for the row -- more than the two tiles take on the tensor-core path)
+        // ===================== warps 17-19: query row 256 with mma.sync (m16n8k16, the row is row 0 of the A fragments) =====================
+        // scores: A = q (16 x 16 per k step, rows 1-15 zero), B = K^T straight from the swizzled tile (two 32-bit loads per step);
+        // P V: A = p rounded to 16 bits, B = V through ldmatrix.trans; key 0 (k_0, v_0 from global) is added with plain FMAs by warp 17.
+        // Each warp takes a third of the keys (whole 16-key steps) with its own maximum; warp 17 combines the three partial rows.
         const float sl2 = 0.125f * 1.4426950408889634f;
         constexpr int f16 = F16;
-        const int row = 256, w = warp - 17;
-        const int j0 = w * 86, j1 = min(L, j0 + 86);             // this warp's keys [j0, j1)
+        const int row = 256, g = lane >> 2, tq = lane & 3, w = warp - 17;
+        const int ks0 = w == 0 ? 0 : (w == 1 ? 6 : 11), ks1 = w == 0 ? 6 : (w == 1 ? 11 : 16);      // 16-key steps [ks0, ks1) of the tiles
+        const int jlo = w == 0 ? 0 : 1 + 16 * ks0, jhi = 1 + 16 * ks1;                              // s_tail indices (keys) of this warp
         for (int u = 0; u < n_my; ++u) {
             const int unit = (int)blockIdx.x + u * (int)gridDim.x, stage = u % NST;
             const int img = unit / heads, h = unit % heads;
             const uint32_t sph = (uint32_t)(u / NST) & 1;
             const __nv_bfloat16 *base = p.qkv + (size_t)img * L * 3 * d + h * HD;
-            float q[64];
-            {
-                const uint4 *qp = reinterpret_cast<const uint4 *>(base + (size_t)row * 3 * d);
+            const uint32_t *qw = reinterpret_cast<const uint32_t *>(base + (size_t)row * 3 * d);     // 32 words = 64 dims of q_256
+            uint32_t qa[4][2];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const uint4 x = __ldg(qp + c);
-                    unpack16x2(x.x, f16, q[8 * c], q[8 * c + 1]); unpack16x2(x.y, f16, q[8 * c + 2], q[8 * c + 3]);
-                    unpack16x2(x.z, f16, q[8 * c + 4], q[8 * c + 5]); unpack16x2(x.w, f16, q[8 * c + 6], q[8 * c + 7]);
-                }
+            for (int ks = 0; ks < 4; ++ks) {
+                qa[ks][0] = g == 0 ? __ldg(qw + 8 * ks + tq) : 0u;
+                qa[ks][1] = g == 0 ? __ldg(qw + 8 * ks + 4 + tq) : 0u;
+            }
+            if (w == 0) {                                     // key 0: every lane two dims
+                float q0, q1, k0, k1;
+                unpack16x2(__ldg(qw + lane), f16, q0, q1);
+                unpack16x2(__ldg(reinterpret_cast<const uint32_t *>(base + d) + lane), f16, k0, k1);
+                float s0 = fmaf(q0, k0, q1 * k1);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                if (lane == 0) s_tail[0] = s0 * sl2;
             }
             mbar_wait(&bar_qk[stage], sph);
-            unsigned char *sK = smem + stage * stage_bytes + MT * TILE_BYTES, *sV = smem + stage * stage_bytes + 2 * MT * TILE_BYTES;
-            // score of key j: j = 0 from global (k_0), j >= 1 from the K tiles (tile row j - 1)
-            float m = -INFINITY;
-            for (int j = j0 + lane; j < j0 + 96; j += 32) {
-                float sc = -INFINITY;
-                if (j < j1) {
-                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            const uint32_t sK_s = smem_u32(smem + stage * stage_bytes + MT * TILE_BYTES);
+            const uint32_t sV_s = smem_u32(smem + stage * stage_bytes + 2 * MT * TILE_BYTES);
+            for (int nt = 2 * ks0; nt < 2 * ks1; nt += 2) {   // two independent 8-key tiles per pass: tile rows 8 nt + g, 8 nt + 8 + g
+                const int kka = 8 * nt + g, kkb = kka + 8;
+                const uint32_t ra = sK_s + (uint32_t)((kka >> 7) * TILE_BYTES + (kka & 127) * 128 + 4 * tq);
+                const uint32_t rb = sK_s + (uint32_t)((kkb >> 7) * TILE_BYTES + (kkb & 127) * 128 + 4 * tq);
+                float da[4] = {0.f, 0.f, 0.f, 0.f}, db[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        uint4 x;
-                        if (j == 0) x = __ldg(reinterpret_cast<const uint4 *>(base + d) + c);
-                        else {
-                            const int kk = j - 1;
-                            x = *reinterpret_cast<const uint4 *>(sK + (kk >> 7) * TILE_BYTES + (kk & 127) * 128 + ((c ^ (kk & 7)) << 4));
-                        }
-                        float k0, k1;
-                        unpack16x2(x.x, f16, k0, k1); a0 = fmaf(q[8 * c], k0, a0); a1 = fmaf(q[8 * c + 1], k1, a1);
-                        unpack16x2(x.y, f16, k0, k1); a2 = fmaf(q[8 * c + 2], k0, a2); a3 = fmaf(q[8 * c + 3], k1, a3);
-                        unpack16x2(x.z, f16, k0, k1); a0 = fmaf(q[8 * c + 4], k0, a0); a1 = fmaf(q[8 * c + 5], k1, a1);
-                        unpack16x2(x.w, f16, k0, k1); a2 = fmaf(q[8 * c + 6], k0, a2); a3 = fmaf(q[8 * c + 7], k1, a3);
-                    }
-                    sc = ((a0 + a1) + (a2 + a3)) * sl2;
-                    s_tail[j] = sc;
+                for (int ks = 0; ks < 4; ++ks) {
+                    uint32_t a0, a1, b0, b1;
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(a0) : "r"(ra + (uint32_t)(((2 * ks) ^ (kka & 7)) << 4)));
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(a1) : "r"(ra + (uint32_t)(((2 * ks + 1) ^ (kka & 7)) << 4)));
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(b0) : "r"(rb + (uint32_t)(((2 * ks) ^ (kkb & 7)) << 4)));
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(b1) : "r"(rb + (uint32_t)(((2 * ks + 1) ^ (kkb & 7)) << 4)));
+                    mma16816<F16>(da, qa[ks][0], 0u, qa[ks][1], 0u, a0, a1);
+                    mma16816<F16>(db, qa[ks][0], 0u, qa[ks][1], 0u, b0, b1);
                 }
-                m = fmaxf(m, sc);
+                if (g == 0) {
+                    s_tail[1 + 8 * nt + 2 * tq] = da[0] * sl2; s_tail[2 + 8 * nt + 2 * tq] = da[1] * sl2;
+                    s_tail[9 + 8 * nt + 2 * tq] = db[0] * sl2; s_tail[10 + 8 * nt + 2 * tq] = db[1] * sl2;
+                }
             }
+            __syncwarp();
+            float m = -INFINITY;
+            for (int j = jlo + lane; j < jhi; j += 32) m = fmaxf(m, s_tail[j]);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-            __syncwarp();
             float sum = 0.f;
-            for (int j = j0 + lane; j < j1; j += 32) {
+            for (int j = jlo + lane; j < jhi; j += 32) {
                 const float e = fast_exp2(s_tail[j] - m);
                 s_tail[j] = e;
                 sum += e;
@@ -1180,38 +1199,39 @@ attention_tc2x_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPar
             for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
             __syncwarp();
             mbar_wait(&bar_v[stage], sph);
-            // this lane's two head columns 2 * lane, 2 * lane + 1: 16-byte chunk lane >> 2, byte (lane & 3) * 4 inside it
-            const int cb = lane >> 2, inb = (lane & 3) * 4;
-            float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-            int j = j0;
-            if (j == 0) {
-                float a, b;
-                unpack16x2(__ldg(reinterpret_cast<const uint32_t *>(base + 2 * d) + lane), f16, a, b);      // v_0
-                o0 = s_tail[0] * a; o1 = s_tail[0] * b;
-                j = 1;
+            float oacc[8][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) { oacc[nt][0] = oacc[nt][1] = oacc[nt][2] = oacc[nt][3] = 0.f; }
+            for (int ks = ks0; ks < ks1; ++ks) {              // sixteen keys per step: tile rows 16 ks .. + 15 = keys 1 + 16 ks ..
+                uint32_t pa0 = 0u, pa2 = 0u;
+                if (g == 0) {
+                    pa0 = pack16x2(s_tail[1 + 16 * ks + 2 * tq], s_tail[2 + 16 * ks + 2 * tq], f16);
+                    pa2 = pack16x2(s_tail[9 + 16 * ks + 2 * tq], s_tail[10 + 16 * ks + 2 * tq], f16);
+                }
+                const int vr = 16 * ks + (lane & 15);         // the row this lane addresses for ldmatrix (lanes 16-31 repeat 0-15)
+                const uint32_t vrow = sV_s + (uint32_t)((vr >> 7) * TILE_BYTES + (vr & 127) * 128);
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    uint32_t b0, b1;
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];"
+                                 : "=r"(b0), "=r"(b1) : "r"(vrow + (uint32_t)((nt ^ (vr & 7)) << 4)));
+                    mma16816<F16>(oacc[nt], pa0, 0u, pa2, 0u, b0, b1);
+                }
             }
-            for (; j + 1 < j1; j += 2) {
-                const int ka = j - 1, kb = j;
-                const unsigned char *va = sV + (ka >> 7) * TILE_BYTES + (ka & 127) * 128 + ((cb ^ (ka & 7)) << 4) + inb;
-                const unsigned char *vb = sV + (kb >> 7) * TILE_BYTES + (kb & 127) * 128 + ((cb ^ (kb & 7)) << 4) + inb;
-                float a, b, c2, d2;
-                unpack16x2(*reinterpret_cast<const uint32_t *>(va), f16, a, b);
-                unpack16x2(*reinterpret_cast<const uint32_t *>(vb), f16, c2, d2);
-                const float pa = s_tail[j], pb = s_tail[j + 1];
-                o0 = fmaf(pa, a, o0); o1 = fmaf(pa, b, o1);
-                o2 = fmaf(pb, c2, o2); o3 = fmaf(pb, d2, o3);
+            // partial row (dims 8 nt + 2 tq, + 1 in the lanes with g == 0), maximum and sum of this warp's keys
+            if (g == 0) {
+                float p0 = 0.f;
+                const uint32_t *v0w = reinterpret_cast<const uint32_t *>(base + 2 * d);              // v_0: 32 words
+                if (w == 0) p0 = s_tail[0];
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    float a = 0.f, b2 = 0.f;
+                    if (w == 0) unpack16x2(__ldg(v0w + 4 * nt + tq), f16, a, b2);
+                    s_tpart[w][8 * nt + 2 * tq] = fmaf(p0, a, oacc[nt][0]);
+                    s_tpart[w][8 * nt + 2 * tq + 1] = fmaf(p0, b2, oacc[nt][1]);
+                }
+                if (tq == 0) { s_tpart[w][64] = m; s_tpart[w][65] = sum; }
             }
-            if (j < j1) {
-                const int ka = j - 1;
-                const unsigned char *va = sV + (ka >> 7) * TILE_BYTES + (ka & 127) * 128 + ((cb ^ (ka & 7)) << 4) + inb;
-                float a, b;
-                unpack16x2(*reinterpret_cast<const uint32_t *>(va), f16, a, b);
-                const float pa = s_tail[j];
-                o0 = fmaf(pa, a, o0); o1 = fmaf(pa, b, o1);
-            }
-            // partials -> warp 17 combines the three key ranges
-            s_tpart[w][2 * lane] = o0 + o2; s_tpart[w][2 * lane + 1] = o1 + o3;
-            if (lane == 0) { s_tpart[w][64] = m; s_tpart[w][65] = sum; }
             asm volatile("bar.sync 9, 96;" ::: "memory");
             if (w == 0) {
                 const float m0 = s_tpart[0][64], m1 = s_tpart[1][64], m2 = s_tpart[2][64];
