@@ -13,6 +13,11 @@
 //               half of S's own columns (tcgen05.st); the softmax denominators come from a companion MMA (P . ones);
 //               O / denominator -> global.
 // S never leaves the SM and P never touches shared memory.
+//
+// Kernels of this file (dispatch in ec::attention_tc): attention_tc4_kernel (L <= 64: four chains in flight), attention_tc2_kernel
+// (64 < L <= 256: two slots, two threads per query row), attention_tc2x_kernel (L = 257: the same with the class key and the last
+// query row folded in), attention_tc_big_kernel (other 256 < L <= 384), attention_tc_kernel (round 1, EC_ATTN_V=1), and the
+// tensor-memory backward attention_bwd_tc_kernel.
 #include <cuda.h>
 
 #include <cstdio>
