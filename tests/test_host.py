@@ -233,3 +233,29 @@ def test_layernorm_folding_operands_reproduce_layernorm_plus_linear():
                 assert e["wg_" + name].dtype == torch.float16
                 assert e["wg_" + name].float().sum(1).abs().max() < 2e-3                  # centred rows (up to one fp16 rounding)
                 assert (got - want).norm() / want.norm() < 2e-3, (with_lora, name)
+
+
+@pytest.mark.parametrize("arch", ["ViT-tiny/16", "ViT-tiny/32", "ViT-L/14"])
+def test_gray_folded_conv1_reproduces_conv1_on_the_normalised_channels(arch):
+    """clip.VisionTransformer.packed_gray (CPU): event frames are grayscale, so CLIP's preprocess yields three channels that are
+    affine in ONE byte g; conv1 folded onto the plane g / 128 (+ the constant that joins the positional embedding) must equal
+    conv1 on ToTensor + Normalize of the gray image, for every byte value."""
+    m = clip.init_weights_(clip.CLIP(arch), seed=5)
+    vis = m.visual
+    vis.operand_dtype = torch.float32                    # the algebra, without the 16-bit rounding of the packed operand
+    pg = vis.packed_gray()
+    P, d = vis.patch_size, vis.width
+    g = torch.Generator().manual_seed(1)
+    byte = torch.randint(0, 256, (3, 1, 224, 224), generator=g).float()
+    byte[0, 0, :16, :16] = torch.arange(256.).view(16, 16)          # every byte value occurs
+    mean = torch.tensor(clip.CLIP_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(clip.CLIP_STD).view(1, 3, 1, 1)
+    x = (byte / 255.0 - mean) / std                                  # [3, 3, 224, 224]: the reference's tensor
+    ref = torch.nn.functional.conv2d(x.double(), vis.conv1.weight.double(), stride=P)          # [3, d, G, G]
+    G = 224 // P
+    rows = (byte / 128.0).view(3, G, P, G, P).permute(0, 1, 3, 2, 4).reshape(3 * G * G, P * P).double()
+    got = rows @ pg["conv1"][:, :P * P].double().t()                 # [3 G G, d]
+    got = got + (pg["pos"][1:].double() - vis.positional_embedding[1:].double()).repeat(3, 1)   # the folded constant
+    want = ref.permute(0, 2, 3, 1).reshape(3 * G * G, d)
+    assert pg["conv1"].shape == (d, vis.k_gray) and (pg["conv1"][:, P * P:] == 0).all()
+    assert (got - want).abs().max() < 2e-5 * want.abs().max().clamp_min(1.0)
