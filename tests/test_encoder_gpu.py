@@ -216,6 +216,25 @@ def test_attention(cuda_dev, L, heads, n_img):
     assert rel(out.float(), ref) < 8e-3, rel(out.float(), ref)
 
 
+@pytest.mark.parametrize("L,heads,n_img", [(50, 12, 131), (257, 16, 40), (197, 12, 57), (64, 2, 300)])
+def test_attention_fp16_many_units_per_cta(cuda_dev, L, heads, n_img):
+    """The fp16-operand launches (what the inference forward uses) with several units per persistent CTA: the eight-stage ring of
+    the small-sequence kernel, the two-stage ring + tail-row warps of the L = 257 kernel, the two-slot kernel."""
+    g = torch.Generator().manual_seed(1000 + L)
+    d = heads * 64
+    qkv = torch.randn(n_img * L, 3 * d, generator=g).half()
+    out = torch.empty(n_img * L, d, dtype=torch.float16, device=cuda_dev)
+    ops.attention(qkv.to(cuda_dev), out, n_img, L, heads)
+    q, k, v = [t.view(n_img, L, heads, 64).transpose(1, 2) for t in qkv.float().chunk(3, -1)]
+    ref = (torch.softmax(q @ k.transpose(-1, -2) / 8.0, -1) @ v).transpose(1, 2).reshape(n_img * L, d)
+    got = out.float().cpu()
+    assert rel(got, ref) < 2e-3, rel(got, ref)
+    # the last query row and the first key of the L = 257 kernel take their own routes: check them on their own
+    if L == 257:
+        rows = torch.arange(n_img) * L + 256
+        assert rel(got[rows], ref[rows]) < 2e-3, rel(got[rows], ref[rows])
+
+
 @pytest.mark.parametrize("L,heads,n_img,dt", [(197, 2, 3, torch.float16), (197, 2, 3, torch.bfloat16), (50, 2, 5, torch.float16),
                                              (257, 2, 2, torch.float16), (77, 2, 4, torch.float16)])
 def test_attention_peaked_rows_beyond_the_first_keys(cuda_dev, L, heads, n_img, dt):
