@@ -54,6 +54,34 @@ __device__ float block_reduce(float v, float *sv, bool is_max)
     return sv[0];
 }
 
+// logits of class row k for all T views of sample b: <scale * f_t, text_k>, TT views per pass over the text row
+template <int TT, int MODE>
+__device__ __forceinline__ void head_dots(const float *sf, const float *__restrict__ tx, const float *vmask, int T, int C, int n_cls,
+                                          int b, int k, int lane, float *out_full, float *sl)
+{
+    for (int t0 = 0; t0 < T; t0 += TT) {
+        float acc[TT];
+#pragma unroll
+        for (int j = 0; j < TT; ++j) acc[j] = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float w = __ldg(tx + c);
+#pragma unroll
+            for (int j = 0; j < TT; ++j)
+                if (t0 + j < T) acc[j] = fmaf(sf[(size_t)(t0 + j) * C + c], w, acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < TT; ++j)
+            if (t0 + j < T) {
+                const int t = t0 + j;
+                const float v = ec::warp_sum(acc[j]);
+                if (lane == 0) {
+                    if (MODE == 1) out_full[((size_t)b * T + t) * n_cls + k] = vmask[t] != 0.f ? v : 0.f;
+                    else sl[(size_t)t * n_cls + k] = vmask[t] != 0.f ? v : 0.f;
+                }
+            }
+    }
+}
+
 // One CTA per sample.  smem: feats [T][C] | logits [T][n_cls] | agg [n_cls] | probs [n_cls]
 // MODE 0: everything in one launch.  With many classes (N-ImageNet: 1000) one CTA per sample walks 125 text rows per warp with
 // little memory-level parallelism (ncu: 1.1 ms for 64 samples), so the work is split: MODE 1, grid (B, S): logits of a slice of
@@ -103,24 +131,11 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const float *__restr
     if (MODE != 2)
     for (int k = k_lo + warp; k < k_hi; k += nwarp) {
         const float *tx = text + (size_t)k * C;
-        float acc[16];
-#pragma unroll
-        for (int t = 0; t < 16; ++t) acc[t] = 0.f;
-        for (int c = lane; c < C; c += 32) {
-            const float w = tx[c];
-#pragma unroll
-            for (int t = 0; t < 16; ++t)
-                if (t < T) acc[t] = fmaf(sf[(size_t)t * C + c], w, acc[t]);
-        }
-#pragma unroll
-        for (int t = 0; t < 16; ++t)
-            if (t < T) {
-                const float v = ec::warp_sum(acc[t]);
-                if (lane == 0) {
-                    if (MODE == 1) out_full[((size_t)b * T + t) * n_cls + k] = vmask[t] != 0.f ? v : 0.f;
-                    else sl[(size_t)t * n_cls + k] = vmask[t] != 0.f ? v : 0.f;
-                }
-            }
+        // TT views per pass over the text row (register tile): the old fixed 16-view tile issued 16 predicated LDS + FMA pairs per
+        // column whatever T was -- 8 x the useful work at T = 2, 3 x at T = 5
+        if (T == 1) head_dots<1, MODE>(sf, tx, vmask, T, C, n_cls, b, k, lane, out_full, sl);
+        else if (T == 2) head_dots<2, MODE>(sf, tx, vmask, T, C, n_cls, b, k, lane, out_full, sl);
+        else head_dots<4, MODE>(sf, tx, vmask, T, C, n_cls, b, k, lane, out_full, sl);
     }
     if (MODE == 1) return;
     if (MODE == 2)
@@ -442,7 +457,9 @@ extern "C" int ec_head(const float *feats, const uint8_t *valid, const float *te
     EC_REQUIRE(agg >= EC_AGG_SUM && agg <= EC_AGG_MAX, "ec_head: bad aggregation %d", agg);
     const size_t smem = ((size_t)T * C + (size_t)T * n_cls + 2 * (size_t)n_cls) * sizeof(float);
     EC_REQUIRE(smem <= 220 * 1024, "ec_head: T*C + T*n_cls too large for shared memory (%zu bytes)", smem);
-    const bool split = n_cls >= 256 && out_full != nullptr;
+    // one CTA per sample is latency- and issue-bound as soon as a sample has a few thousand (view, class) pairs (C1: 32 samples x 5 views x
+    // 101 classes took 166 us on 32 SMs): spread the logits over the GPU unless the batch alone fills it
+    const bool split = out_full != nullptr && n_cls >= 32;
     static size_t attr[3] = {0, 0, 0};
     auto grant = [&](int mode, const void *fn) -> int {
         if (smem > 48 * 1024 && smem > attr[mode]) {
@@ -457,7 +474,7 @@ extern "C" int ec_head(const float *feats, const uint8_t *valid, const float *te
         rc = grant(2, (const void *)head_kernel<2>);
         if (rc != EC_OK) return rc;
         int S = (4 * ec::sm_count() + B - 1) / B;                    // about four CTAs per SM in the logits launch
-        S = S < 1 ? 1 : (S > n_cls / 32 ? n_cls / 32 : S);
+        S = S < 1 ? 1 : (S > n_cls / 8 ? n_cls / 8 : S);               // at least one class row per warp of a slice
         head_kernel<1><<<dim3(B, S), HEAD_THREADS, smem, (cudaStream_t)stream>>>(feats, valid, text, T, C, n_cls, scale, normalize, agg,
                                                                                 out_full, out_logits, out_probs, out_top);
         head_kernel<2><<<B, HEAD_THREADS, smem, (cudaStream_t)stream>>>(feats, valid, text, T, C, n_cls, scale, normalize, agg, out_full,
