@@ -202,6 +202,63 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const float *__restr
     }
 }
 
+// ---- fp32 GEMM for a few hundred rows (the few-shot adapter: 128 x 512 activations): lane = output column, eight rows per warp ----
+// out = act(A W^T + bias) (+ res).  A CTA of four warps owns 32 rows x 32 columns and walks K in chunks of 128: the chunk of A
+// ([32][128], read back as broadcast 16-byte words) and of W ([32 columns][128], pitch 132 floats: the 16-byte reads of the eight lanes
+// of a quarter warp fall on 32 distinct banks) are staged in shared memory with coalesced 16-byte loads; the K sum of an output is one
+// sequential chain in a single thread -- no shuffles, a fixed summation order (deterministic), 8 independent chains per lane.
+// The lane-split kernel below reduces every output with two 5-step shuffle trees (36 us for 128 x 1536 x 512).
+constexpr int RT_KC = 128, RT_WP = RT_KC + 4;
+__global__ void __launch_bounds__(128) sgemm_rows_kernel(const float *__restrict__ A, const float *__restrict__ W,
+                                                         const float *__restrict__ bias, const float *__restrict__ res, int M,
+                                                         int N, int K, int act, float *__restrict__ out)
+{
+    __shared__ __align__(16) float sa[32][RT_KC];
+    __shared__ __align__(16) float sw[32][RT_WP];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+    float acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+    for (int kc = 0; kc < K; kc += RT_KC) {
+        const int kn = min(RT_KC, K - kc);                 // a multiple of 4
+        const int q4 = kn >> 2;
+        for (int i = tid; i < 32 * q4; i += 128) {
+            const int row = i / q4, c4 = i - row * q4;
+            float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vw = va;
+            if (m0 + row < M) va = *reinterpret_cast<const float4 *>(A + (size_t)(m0 + row) * K + kc + 4 * c4);
+            if (n0 + row < N) vw = __ldg(reinterpret_cast<const float4 *>(W + (size_t)(n0 + row) * K + kc + 4 * c4));
+            *reinterpret_cast<float4 *>(&sa[row][4 * c4]) = va;
+            *reinterpret_cast<float4 *>(&sw[row][4 * c4]) = vw;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int k4 = 0; k4 < q4; ++k4) {
+            const float4 w = *reinterpret_cast<const float4 *>(&sw[lane][4 * k4]);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const float4 a = *reinterpret_cast<const float4 *>(&sa[8 * warp + r][4 * k4]);
+                acc[r] = fmaf(a.w, w.w, fmaf(a.z, w.z, fmaf(a.y, w.y, fmaf(a.x, w.x, acc[r]))));
+            }
+        }
+        __syncthreads();
+    }
+    const int n = n0 + lane;
+    if (n < N) {
+        const float bv = bias ? bias[n] : 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int m = m0 + 8 * warp + r;
+            if (m < M) {
+                float v = acc[r] + bv;
+                if (act == 1) v = fmaxf(v, 0.f);
+                if (res) v += res[(size_t)m * N + n];
+                out[(size_t)m * N + n] = v;
+            }
+        }
+    }
+}
+
 // ---- fp32 SGEMM for the adapter: out = act(A W^T + bias) (+ res); 64x64 tile, 16-deep, 256 threads, 4x4 per thread ----
 __global__ void __launch_bounds__(256) sgemm_kernel(const float *__restrict__ A, const float *__restrict__ W,
                                                     const float *__restrict__ bias, const float *__restrict__ res, int M,
@@ -494,7 +551,10 @@ extern "C" int ec_gemm_f32(const float *A, const float *W, const float *bias, co
 {
     EC_REQUIRE(A && W && out && M > 0 && N > 0 && K > 0, "ec_gemm_f32: bad arguments");
     EC_REQUIRE(act == 0 || act == 1, "ec_gemm_f32: bad activation %d", act);
-    if (M <= 1024 && K % 32 == 0 && K <= 1024) {
+    static const int rows_on = [] { const char *e = getenv("EC_SGEMM_ROWS"); return e ? atoi(e) : 1; }();
+    if (rows_on && M >= 16 && M <= 4096 && K % 4 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0) {
+        sgemm_rows_kernel<<<dim3((N + 31) / 32, (M + 31) / 32), 128, 0, (cudaStream_t)stream>>>(A, W, bias, res, M, N, K, act, out);
+    } else if (M <= 1024 && K % 32 == 0 && K <= 1024) {
         constexpr int NC = 8;
         const size_t smem = (size_t)NC * K * sizeof(float);          // <= 32 KB
         sgemm_skinny_kernel<NC><<<(N + NC - 1) / NC, 256, smem, (cudaStream_t)stream>>>(A, W, bias, res, M, N, K, act, out);
