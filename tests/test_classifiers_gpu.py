@@ -534,3 +534,27 @@ def test_partial_upload_of_host_events_matches_full_upload(cuda_dev):
         assert torch.equal(a, b) and torch.equal(a, c)
     used = 3 * 2 * 2 * 70000 * 16
     assert g.h2d_bytes == used, (g.h2d_bytes, used)          # 2 views x 70 000 events per sample instead of 700 001 / 550 000 events
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 1536, 512), (37, 130, 260), (16, 32, 4), (33, 65, 132), (200, 512, 2048), (5, 70, 96),
+                                   (1, 512, 512), (128, 512, 100)])
+def test_fp32_gemm_every_kernel_and_edge(cuda_dev, M, N, K):
+    """ec_gemm_f32 (the adapter's GEMMs): out = act(A W^T + bias) (+ res) against float64, for the row-tiled kernel (16 <= M, K % 4 == 0:
+    ragged M / N tiles, K chunks that are not multiples of 128), the lane-split kernel (small M) and the 64 x 64 tile kernel (other K)."""
+    g = torch.Generator().manual_seed(M * 7 + N)
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) * K ** -0.5
+    b = torch.randn(N, generator=g)
+    R = torch.randn(M, N, generator=g)
+    for act, bias, res in ((0, None, None), (1, b, None), (0, b, R), (1, b, R)):
+        ref = A.double() @ W.double().t()
+        if bias is not None:
+            ref = ref + bias.double()
+        if act:
+            ref = torch.relu(ref)
+        if res is not None:
+            ref = ref + res.double()
+        got = ops.gemm_f32(A.to(cuda_dev), W.to(cuda_dev), None if bias is None else bias.to(cuda_dev),
+                           None if res is None else res.to(cuda_dev), act).cpu().double()
+        assert got.shape == (M, N)
+        assert (got - ref).abs().max() <= 5e-6 * ref.abs().max().clamp_min(1.0), (act, bias is not None, res is not None)
