@@ -558,3 +558,34 @@ def test_fp32_gemm_every_kernel_and_edge(cuda_dev, M, N, K):
                            None if res is None else res.to(cuda_dev), act).cpu().double()
         assert got.shape == (M, N)
         assert (got - ref).abs().max() <= 5e-6 * ref.abs().max().clamp_min(1.0), (act, bias is not None, res is not None)
+
+
+@pytest.mark.parametrize("B,T,C,K", [(32, 5, 512, 101), (64, 2, 512, 1000), (256, 1, 512, 2), (3, 10, 64, 33), (7, 3, 768, 40)])
+def test_head_kernel_modes_against_torch(cuda_dev, B, T, C, K):
+    """ec_head on its one-launch route (fewer than 32 classes) and its two-launch route (logits spread over the GPU, then one CTA per
+    sample), with padded views, both normalisation settings and the three aggregations (models/clip_cls.py:104-129, 144-154, 326-342)."""
+    g = torch.Generator().manual_seed(B + K)
+    f = torch.randn(B * T, C, generator=g)
+    text = torch.nn.functional.normalize(torch.randn(K, C, generator=g), dim=-1)
+    valid = torch.rand(B, T, generator=g) > 0.3
+    valid[:, 0] = True
+    for normalize in (0, 1):
+        for agg in ("mean", "sum", "max"):
+            full, logits, probs, top = ops.head(f.to(cuda_dev), valid.reshape(-1).to(torch.uint8).to(cuda_dev), text.to(cuda_dev), B, T, 30.0,
+                                                normalize, agg)
+            ff = torch.nn.functional.normalize(f.double(), dim=-1) if normalize else f.double()
+            ref = (30.0 * ff @ text.double().t()).view(B, T, K) * valid.unsqueeze(-1)
+            assert (full.cpu().double() - ref).abs().max() <= 2e-5 * ref.abs().max()
+            v = valid.double()
+            if agg == "sum":
+                ra = ref.sum(1)
+            elif agg == "mean":
+                ra = ref.sum(1) / v.sum(1, keepdim=True)
+            else:
+                ra = (ref - (1.0 - v).unsqueeze(-1) * 1e6).max(1).values
+            assert (logits.cpu().double() - ra).abs().max() <= 2e-5 * ra.abs().max().clamp_min(1.0)
+            rp = (torch.softmax(ref, -1) * v.unsqueeze(-1)).sum(1) / v.sum(1, keepdim=True)
+            assert (probs.cpu().double() - rp).abs().max() <= 2e-5
+            gap = ra.topk(2, -1).values
+            clear = (gap[:, 0] - gap[:, 1]) > 1e-3 * ra.abs().max()
+            assert torch.equal(top[:, 0, 0].cpu().long()[clear], ra.argmax(-1)[clear])
